@@ -1,0 +1,687 @@
+"""CPU oracle for the ESLAM render-and-optimise hot path.
+
+THIS FILE IS TEST INFRASTRUCTURE, NOT PRODUCT CODE.  Only `tests/`,
+`__graft_entry__.smoke()` and `bench.py`'s CPU-baseline / `--impl reference`
+legs may import it.  Nothing under `myslam_b200/` imports it, and the product
+path has no CPU fallback: it raises when the CUDA library is missing.
+
+What it is: a plain PyTorch (fp32, autograd, any device but meant for CPU)
+restatement of the algorithm the reference implements in
+`src/common.py`, `src/utils/Renderer.py`, `src/networks/decoders.py`,
+`src/Tracker.py:114-210`, `src/Mapper.py:110-144,211-364` and
+`src/utils/Mesher.py:130-186`.  Each function cites the reference lines it
+follows.  Two deliberate differences from the reference's *shape* (not its
+arithmetic):
+
+* every random draw is INJECTED through a `Draws` object instead of being taken
+  from the global generator, so the CUDA path and this oracle can consume the
+  same numbers (`LiveDraws` reproduces the reference's call order and shapes on
+  a torch generator; `ReplayDraws` replays a recorded list);
+* state lives in a small `Field` record instead of in `ESLAM`/`Tracker`/`Mapper`
+  attributes.
+
+Parity pin: the reference ships no tests or golden
+vectors, so this oracle is pinned against the reference ITSELF, imported
+unmodified from /root/reference in the build container by
+`tests/golden/make_golden.py` (bit-exact for pixel indices, z_vals, rays and
+masks; <=1e-6 for rendered values, losses, gradients and post-Adam state).  The
+resulting vectors are committed under `tests/golden/` and replayed by the
+`-m "not gpu"` tests.  The one boundary the reference itself cannot pin is
+`pytorch3d.transforms` (third-party, `pytorch3d==0.7.1`, not vendored, absent
+here): `quaternion_to_matrix` / `matrix_to_quaternion` below restate its
+published algorithm and are pinned against scipy's Rotation -- for that
+boundary alone: PARITY UNPINNED against pytorch3d proper.
+"""
+from __future__ import annotations
+
+import math
+from dataclasses import dataclass, field as _dc_field
+from typing import Dict, List, Optional, Sequence, Tuple
+
+import numpy as np
+import torch
+import torch.nn.functional as F
+
+# ----------------------------------------------------------------------------
+# random draws (injected)
+# ----------------------------------------------------------------------------
+
+
+class LiveDraws:
+    """Draw from a torch generator in the reference's order and shapes and keep a log.
+
+    Order per iteration (SURVEY.md 7 'Bit-exact sampling'): randint(n*b) at
+    common.py:108, rand[R1,S] at Renderer.py:59 (via :103), and only when
+    depth-less rays exist rand[R0,n_strat] (Renderer.py:59 via :120) then
+    rand[R0,n_imp] (common.py:59).
+    """
+
+    def __init__(self, generator: Optional[torch.Generator] = None, device="cpu"):
+        self.gen = generator
+        self.device = device
+        self.log: List[torch.Tensor] = []
+
+    def randint(self, high: int, n: int) -> torch.Tensor:
+        t = torch.randint(high, (n,), generator=self.gen, device=self.device)
+        self.log.append(t.clone())
+        return t
+
+    def rand(self, *shape: int) -> torch.Tensor:
+        t = torch.rand(*shape, generator=self.gen, device=self.device)
+        self.log.append(t.clone())
+        return t
+
+
+class ReplayDraws:
+    """Replay a recorded list of draws; shapes are checked so a mismatch is loud."""
+
+    def __init__(self, recorded: Sequence[torch.Tensor]):
+        self.recorded = list(recorded)
+        self.pos = 0
+
+    def _next(self, shape) -> torch.Tensor:
+        if self.pos >= len(self.recorded):
+            raise RuntimeError("ReplayDraws exhausted")
+        t = self.recorded[self.pos]
+        self.pos += 1
+        if tuple(t.shape) != tuple(shape):
+            raise RuntimeError(f"draw {self.pos - 1}: recorded shape {tuple(t.shape)} != requested {tuple(shape)}")
+        return t
+
+    def randint(self, high: int, n: int) -> torch.Tensor:
+        t = self._next((n,))
+        assert int(t.max()) < high
+        return t
+
+    def rand(self, *shape: int) -> torch.Tensor:
+        return self._next(shape)
+
+
+# ----------------------------------------------------------------------------
+# pose <-> matrix   (pytorch3d 0.7.1 published algorithm; common.py:155-181)
+# ----------------------------------------------------------------------------
+
+
+def quaternion_to_matrix(q: torch.Tensor) -> torch.Tensor:
+    """Real-first quaternion [...,4] -> rotation [...,3,3], scaled by 2/|q|^2 so
+    un-normalised (Adam-updated) quaternions stay valid.  pytorch3d 0.7.1
+    `transforms.rotation_conversions.quaternion_to_matrix`; called at common.py:178."""
+    r, i, j, k = torch.unbind(q, -1)
+    two_s = 2.0 / (q * q).sum(-1)
+    m = torch.stack(
+        (
+            1 - two_s * (j * j + k * k), two_s * (i * j - k * r), two_s * (i * k + j * r),
+            two_s * (i * j + k * r), 1 - two_s * (i * i + k * k), two_s * (j * k - i * r),
+            two_s * (i * k - j * r), two_s * (j * k + i * r), 1 - two_s * (i * i + j * j),
+        ),
+        -1,
+    )
+    return m.reshape(q.shape[:-1] + (3, 3))
+
+
+def _sqrt_pos(x: torch.Tensor) -> torch.Tensor:
+    out = torch.zeros_like(x)
+    pos = x > 0
+    out[pos] = torch.sqrt(x[pos])
+    return out
+
+
+def matrix_to_quaternion(M: torch.Tensor) -> torch.Tensor:
+    """Rotation [...,3,3] -> real-first quaternion, best-conditioned of the four
+    candidate rows (argmax of |q_i|, 0.1 floor), sign NOT standardised.
+    pytorch3d 0.7.1 `matrix_to_quaternion`; called at common.py:165,167."""
+    batch = M.shape[:-2]
+    m00, m01, m02, m10, m11, m12, m20, m21, m22 = torch.unbind(M.reshape(batch + (9,)), -1)
+    q_abs = _sqrt_pos(
+        torch.stack(
+            [1.0 + m00 + m11 + m22, 1.0 + m00 - m11 - m22, 1.0 - m00 + m11 - m22, 1.0 - m00 - m11 + m22], -1
+        )
+    )
+    cand = torch.stack(
+        [
+            torch.stack([q_abs[..., 0] ** 2, m21 - m12, m02 - m20, m10 - m01], -1),
+            torch.stack([m21 - m12, q_abs[..., 1] ** 2, m10 + m01, m02 + m20], -1),
+            torch.stack([m02 - m20, m10 + m01, q_abs[..., 2] ** 2, m12 + m21], -1),
+            torch.stack([m10 - m01, m20 + m02, m21 + m12, q_abs[..., 3] ** 2], -1),
+        ],
+        -2,
+    )
+    floor = torch.tensor(0.1, dtype=q_abs.dtype, device=q_abs.device)
+    cand = cand / (2.0 * q_abs[..., None].max(floor))
+    pick = F.one_hot(q_abs.argmax(-1), num_classes=4) > 0.5
+    return cand[pick, :].reshape(batch + (4,))
+
+
+def cam_pose_to_matrix(poses: torch.Tensor) -> torch.Tensor:
+    """[B,7]=(qw,qx,qy,qz,tx,ty,tz) -> [B,4,4].  common.py:169-181."""
+    B = poses.shape[0]
+    c2w = torch.eye(4, device=poses.device).unsqueeze(0).repeat(B, 1, 1)
+    c2w[:, :3, :3] = quaternion_to_matrix(poses[:, :4])
+    c2w[:, :3, 3] = poses[:, 4:]
+    return c2w
+
+
+def matrix_to_cam_pose(mats: torch.Tensor) -> torch.Tensor:
+    """[B,4,4] -> [B,7] rotation first.  common.py:155-167 (RT=True branch)."""
+    return torch.cat([matrix_to_quaternion(mats[:, :3, :3]), mats[:, :3, 3]], -1)
+
+
+# ----------------------------------------------------------------------------
+# scene record
+# ----------------------------------------------------------------------------
+
+DECODER_KEYS = (
+    "linears.0.weight", "linears.0.bias", "linears.1.weight", "linears.1.bias",
+    "c_linears.0.weight", "c_linears.0.bias", "c_linears.1.weight", "c_linears.1.bias",
+    "output_linear.weight", "output_linear.bias", "c_output_linear.weight", "c_output_linear.bias",
+)
+
+
+@dataclass
+class Field:
+    """The map: 6 plane lists [coarse, fine] of [1,C,H,W] (ESLAM.py:175-218 layout:
+    xy=[ny,nx], xz=[nz,nx], yz=[nz,ny]), decoder weights keyed like
+    `Decoders.state_dict()` (decoders.py:39-62), beta, bound[3,2]."""
+
+    planes: Tuple[List[torch.Tensor], ...]  # (xy, xz, yz, c_xy, c_xz, c_yz)
+    dec: Dict[str, torch.Tensor]
+    beta: torch.Tensor  # shape [1]
+    bound: torch.Tensor  # [3,2] fp32
+
+    def leaves(self) -> List[torch.Tensor]:
+        out = [p for group in self.planes for p in group]
+        out += [self.dec[k] for k in DECODER_KEYS]
+        out.append(self.beta)
+        return out
+
+    def clone(self, requires_grad: bool = False) -> "Field":
+        cp = lambda t: t.detach().clone().requires_grad_(requires_grad)
+        return Field(
+            tuple([cp(p) for p in g] for g in self.planes),
+            {k: cp(v) for k, v in self.dec.items()},
+            cp(self.beta),
+            self.bound.clone(),
+        )
+
+
+def rounded_bound(bound, bound_dividable: float, scale: float = 1.0) -> torch.Tensor:
+    """fp32 round-up of the upper bound to a multiple of `bound_dividable`.  ESLAM.py:159-173."""
+    b = torch.from_numpy(np.array(bound) * scale).float()
+    b[:, 1] = (((b[:, 1] - b[:, 0]) / bound_dividable).int() + 1) * bound_dividable + b[:, 0]
+    return b
+
+
+def plane_shapes(bound: torch.Tensor, res: float) -> Tuple[Tuple[int, int], ...]:
+    """(H,W) of the xy, xz, yz planes at one resolution.  ESLAM.py:196-203: fp32
+    length / res truncated with int(), then the (x,z) swap."""
+    nx, ny, nz = map(int, ((bound[:, 1] - bound[:, 0]) / res).tolist())
+    return (ny, nx), (nz, nx), (nz, ny)
+
+
+def make_field(bound: torch.Tensor, planes_res=(0.24, 0.06), c_planes_res=(0.24, 0.03), c_dim=32,
+               hidden=16, generator: Optional[torch.Generator] = None, std=0.01, dec_scale=1.0) -> Field:
+    """Random-init field with the reference's shapes and distributions
+    (planes N(0,0.01) ESLAM.py:201-210; nn.Linear default init decoders.py:46-56; beta=10 :58-61)."""
+    g = generator
+
+    def plane(hw):
+        return torch.empty(1, c_dim, *hw).normal_(0, std, generator=g)
+
+    groups: List[List[torch.Tensor]] = [[], [], [], [], [], []]
+    for r in planes_res:
+        for k, hw in enumerate(plane_shapes(bound, r)):
+            groups[k].append(plane(hw))
+    for r in c_planes_res:
+        for k, hw in enumerate(plane_shapes(bound, r)):
+            groups[3 + k].append(plane(hw))
+
+    def linear(o, i):
+        lim = 1.0 / math.sqrt(i)
+        w = (torch.rand(o, i, generator=g) * 2 - 1) * lim * dec_scale
+        b = (torch.rand(o, generator=g) * 2 - 1) * lim * dec_scale
+        return w, b
+
+    dec: Dict[str, torch.Tensor] = {}
+    for pre, n_out in (("", 1), ("c_", 3)):
+        dec[f"{pre}linears.0.weight"], dec[f"{pre}linears.0.bias"] = linear(hidden, 2 * c_dim)
+        dec[f"{pre}linears.1.weight"], dec[f"{pre}linears.1.bias"] = linear(hidden, hidden)
+        dec[f"{pre}output_linear.weight"], dec[f"{pre}output_linear.bias"] = linear(n_out, hidden)
+    return Field(tuple(groups), dec, 10.0 * torch.ones(1), bound.clone())
+
+
+# ----------------------------------------------------------------------------
+# A2/A3: pixel pick and rays   (common.py:87-153)
+# ----------------------------------------------------------------------------
+
+
+def pick_pixels(H0, H1, W0, W1, n, depths, colors, draws):
+    """One `randint` for all b images, with replacement; row bi uses
+    indices[bi*n:(bi+1)*n].  common.py:101-139.  Returns i,j [b,n] f32, depth [b,n],
+    colour [b,n,3] and the flat indices [b*n] into the cropped image."""
+    b = depths.shape[0]
+    dev = depths.device
+    d = depths[:, H0:H1, W0:W1]
+    c = colors[:, H0:H1, W0:W1]
+    # i[r,c] = W0+c, j[r,c] = H0+r on the (H1-H0, W1-W0) crop, flattened row-major
+    gi, gj = torch.meshgrid(torch.linspace(W0, W1 - 1, W1 - W0, device=dev),
+                            torch.linspace(H0, H1 - 1, H1 - H0, device=dev), indexing="ij")
+    gi = gi.t().reshape(-1)
+    gj = gj.t().reshape(-1)
+    idx = draws.randint(gi.shape[0], n * b)
+    idx = idx.clamp(0, gi.shape[0])  # a no-op, kept: common.py:109
+    i = gi[idx].reshape(b, -1)
+    j = gj[idx].reshape(b, -1)
+    idx_b = idx.reshape(b, -1)
+    dsel = torch.gather(d.reshape(b, -1), 1, idx_b)
+    csel = torch.gather(c.reshape(b, -1, 3), 1, idx_b.unsqueeze(-1).expand(-1, -1, 3))
+    return i, j, dsel, csel, idx
+
+
+def rays_from_pixels(i, j, c2ws, fx, fy, cx, cy):
+    """dir_cam=((i-cx)/fx, -(j-cy)/fy, -1); rays_d = R.dir (un-normalised);
+    rays_o = t.  common.py:87-99."""
+    dirs = torch.stack([(i - cx) / fx, -(j - cy) / fy, -torch.ones_like(i)], -1)
+    rays_d = torch.sum(dirs.unsqueeze(-2) * c2ws[:, None, :3, :3], -1)
+    rays_o = c2ws[:, None, :3, -1].expand(rays_d.shape)
+    return rays_o, rays_d
+
+
+def sample_rays(H0, H1, W0, W1, n, fx, fy, cx, cy, c2ws, depths, colors, draws):
+    """get_samples (common.py:141-153): -> rays_o[b*n,3], rays_d[b*n,3], depth[b*n],
+    colour[b*n,3] (fp64 if `colors` is), plus the pixel indices."""
+    i, j, d, c, idx = pick_pixels(H0, H1, W0, W1, n, depths, colors, draws)
+    ro, rd = rays_from_pixels(i, j, c2ws, fx, fy, cx, cy)
+    return ro.reshape(-1, 3), rd.reshape(-1, 3), d.reshape(-1), c.reshape(-1, 3), idx
+
+
+# ----------------------------------------------------------------------------
+# A4: bounding-box pre-filter   (Tracker.py:175-187, Mapper.py:322-332)
+# ----------------------------------------------------------------------------
+
+
+def bbox_exit(rays_o, rays_d, bound):
+    """Distance (in units of |d|) at which the ray leaves the bound box:
+    min over axes of max over {lo,hi} of (bound-o)/d."""
+    t = (bound.unsqueeze(0) - rays_o.detach().unsqueeze(-1)) / rays_d.detach().unsqueeze(-1)
+    return torch.min(torch.max(t, dim=2)[0], dim=1)[0]
+
+
+def bbox_keep(rays_o, rays_d, depth, bound, need_depth: bool):
+    keep = bbox_exit(rays_o, rays_d, bound) >= depth
+    if need_depth:  # tracker only, Tracker.py:182
+        keep = keep & (depth > 0)
+    return keep
+
+
+# ----------------------------------------------------------------------------
+# A6-A8: field decode   (common.py:204-218, decoders.py:64-146)
+# ----------------------------------------------------------------------------
+
+
+def normalize_pts(p, bound):
+    """((p-lo)/(hi-lo))*2-1 per axis.  common.py:204-218."""
+    p = p.reshape(-1, 3)
+    cols = [((p[:, a] - bound[a, 0]) / (bound[a, 1] - bound[a, 0])) * 2 - 1.0 for a in range(3)]
+    return torch.stack(cols, -1)
+
+
+def plane_features(p_nor, pxy, pxz, pyz):
+    """Bilinear (border, align_corners) fetch from the 3 planes of each scale,
+    (xy+xz)+yz per scale, concat coarse|fine.  decoders.py:64-85."""
+    grid = p_nor[None, :, None]
+    feats = []
+    for s in range(len(pxy)):
+        taps = []
+        for plane, axes in ((pxy[s], [0, 1]), (pxz[s], [0, 2]), (pyz[s], [1, 2])):
+            v = F.grid_sample(plane, grid[..., axes], padding_mode="border", align_corners=True, mode="bilinear")
+            taps.append(v.squeeze(0).squeeze(-1).transpose(0, 1))
+        feats.append(taps[0] + taps[1] + taps[2])
+    return torch.cat(feats, -1)
+
+
+def _trunk(h, dec, pre):
+    h = F.relu(F.linear(h, dec[f"{pre}linears.0.weight"], dec[f"{pre}linears.0.bias"]))
+    h = F.relu(F.linear(h, dec[f"{pre}linears.1.weight"], dec[f"{pre}linears.1.bias"]))
+    return F.linear(h, dec[f"{pre}output_linear.weight"], dec[f"{pre}output_linear.bias"])
+
+
+def raw_sdf(p_nor, fld: Field):
+    """64->16->16->1, tanh.  decoders.py:87-105."""
+    f = plane_features(p_nor, fld.planes[0], fld.planes[1], fld.planes[2])
+    return torch.tanh(_trunk(f, fld.dec, "")).squeeze(-1)
+
+
+def raw_rgb(p_nor, fld: Field):
+    """64->16->16->3, sigmoid.  decoders.py:107-125."""
+    f = plane_features(p_nor, fld.planes[3], fld.planes[4], fld.planes[5])
+    return torch.sigmoid(_trunk(f, fld.dec, "c_"))
+
+
+def decode(p, fld: Field):
+    """raw[...,4] = (r,g,b,sdf).  decoders.py:127-146."""
+    shp = p.shape
+    pn = normalize_pts(p, fld.bound)
+    raw = torch.cat([raw_rgb(pn, fld), raw_sdf(pn, fld).unsqueeze(-1)], -1)
+    return raw.reshape(*shp[:-1], -1)
+
+
+# ----------------------------------------------------------------------------
+# A5/A9: sampling along rays and compositing   (Renderer.py:46-153, common.py:41-77)
+# ----------------------------------------------------------------------------
+
+
+def sdf2alpha(sdf, beta):
+    """1-exp(-beta*sigmoid(-sdf*beta)).  Renderer.py:149-153."""
+    return 1.0 - torch.exp(-beta * torch.sigmoid(-sdf * beta))
+
+
+def transmittance_weights(alpha):
+    """w_k = alpha_k * prod_{j<k}(1-alpha_j+1e-10).  Renderer.py:128-129,141-142."""
+    ones = torch.ones((alpha.shape[0], 1), device=alpha.device)
+    return alpha * torch.cumprod(torch.cat([ones, 1.0 - alpha + 1e-10], -1), -1)[:, :-1]
+
+
+def perturb(z, u):
+    """Stratified jitter inside the midpoints' intervals.  Renderer.py:46-61."""
+    mids = 0.5 * (z[..., 1:] + z[..., :-1])
+    upper = torch.cat([mids, z[..., -1:]], -1)
+    lower = torch.cat([z[..., :1], mids], -1)
+    return lower + (upper - lower) * u
+
+
+def inverse_cdf(bins, weights, u):
+    """sample_pdf (common.py:41-77) with its quirks: the pdf is the UN-normalised
+    weights (:47-48), searchsorted right=True, `above` clamped to the last cdf
+    entry, denominators < 1e-5 replaced by 1."""
+    cdf = torch.cumsum(weights, -1)
+    cdf = torch.cat([torch.zeros_like(cdf[..., :1]), cdf], -1)
+    inds = torch.searchsorted(cdf, u.contiguous(), right=True)
+    below = (inds - 1).clamp(min=0)
+    above = inds.clamp(max=cdf.shape[-1] - 1)
+    c0, c1 = torch.gather(cdf, 1, below), torch.gather(cdf, 1, above)
+    b0, b1 = torch.gather(bins, 1, below), torch.gather(bins, 1, above)
+    denom = c1 - c0
+    denom = torch.where(denom < 1e-5, torch.ones_like(denom), denom)
+    return b0 + ((u - c0) / denom) * (b1 - b0)
+
+
+def ray_depths(fld: Field, rays_o, rays_d, gt_depth, truncation, n_strat, n_imp, draws, perturb_on=True):
+    """z_vals [R, n_strat+n_imp] (no grad).  Renderer.py:81-134."""
+    R = rays_o.shape[0]
+    dev = rays_o.device
+    z = torch.empty(R, n_strat + n_imp, device=dev)
+    t_uni = torch.linspace(0.0, 1.0, steps=n_strat, device=dev)
+    t_surf = torch.linspace(0.0, 1.0, steps=n_imp, device=dev)
+    d = gt_depth.reshape(-1, 1)
+    has = (d > 0).squeeze(-1)
+    dn = d[has]
+    # rays with depth: surface band +-1.5*trunc and free space up to 1.2*d  (Renderer.py:94-106)
+    z_surf = dn.expand(-1, n_imp) - (1.5 * truncation) + (3 * truncation * t_surf)
+    z_free = 0.0 + 1.2 * dn.expand(-1, n_strat) * t_uni
+    zs, _ = torch.sort(torch.cat([z_free, z_surf], -1), -1)
+    if perturb_on:
+        zs = perturb(zs, draws.rand(*zs.shape))
+    z[has] = zs
+    # depth-less rays: coarse pass + inverse-cdf resampling  (Renderer.py:108-134)
+    if not bool(has.all()):
+        with torch.no_grad():
+            o, dd = rays_o[~has].detach(), rays_d[~has].detach()
+            tb = (fld.bound.unsqueeze(0) - o.unsqueeze(-1)) / dd.unsqueeze(-1)
+            far = torch.min(torch.max(tb, dim=2)[0], dim=1)[0].unsqueeze(-1)
+            far = far + 0.01
+            zu = 0.0 * (1.0 - t_uni) + far * t_uni
+            if perturb_on:
+                zu = perturb(zu, draws.rand(*zu.shape))
+            pts = o.unsqueeze(1) + dd.unsqueeze(1) * zu.unsqueeze(-1)
+            s = raw_sdf(normalize_pts(pts.clone(), fld.bound), fld).reshape(pts.shape[0], pts.shape[1])
+            w = transmittance_weights(sdf2alpha(s, fld.beta))
+            mid = 0.5 * (zu[..., 1:] + zu[..., :-1])
+            wmid = w[..., 1:-1]
+            zi = inverse_cdf(mid, wmid, draws.rand(wmid.shape[0], n_imp))
+            zu, _ = torch.sort(torch.cat([zu, zi], -1), -1)
+            z[~has] = zu
+    return z
+
+
+def composite(fld: Field, rays_o, rays_d, z):
+    """pts -> raw -> alpha -> weights -> depth, rgb.  Renderer.py:136-147."""
+    pts = rays_o[..., None, :] + rays_d[..., None, :] * z[..., :, None]
+    raw = decode(pts, fld)
+    w = transmittance_weights(sdf2alpha(raw[..., -1], fld.beta))
+    rgb = torch.sum(w[..., None] * raw[..., :3], -2)
+    depth = torch.sum(w * z, -1)
+    return depth, rgb, raw[..., -1], w, raw
+
+
+def render_rays(fld: Field, rays_o, rays_d, gt_depth, truncation, n_strat, n_imp, draws, perturb_on=True):
+    """Renderer.render_batch_ray (Renderer.py:63-147) -> depth[R], rgb[R,3], sdf[R,S], z[R,S]."""
+    z = ray_depths(fld, rays_o, rays_d, gt_depth, truncation, n_strat, n_imp, draws, perturb_on)
+    depth, rgb, sdf, _, _ = composite(fld, rays_o, rays_d, z)
+    return depth, rgb, sdf, z
+
+
+# ----------------------------------------------------------------------------
+# A10: losses   (Tracker.py:114-148,192-204; Mapper.py:110-144,337-346)
+# ----------------------------------------------------------------------------
+
+
+def sdf_band_masks(z, d, truncation):
+    """front / center / tail boolean masks [R,S] from z vs gt depth d[R]."""
+    dd = d[:, None]
+    front = z < (dd - truncation)
+    back = z > (dd + truncation)
+    center = (z > (dd - 0.4 * truncation)) & (z < (dd + 0.4 * truncation))
+    tail = (~front) & (~back) & (~center)
+    return front, center, tail
+
+
+def sdf_loss(sdf, z, d, truncation, w_fs, w_center, w_tail):
+    front, center, tail = sdf_band_masks(z, d, truncation)
+    fs = torch.mean(torch.square(sdf[front] - 1.0))
+    resid = z + sdf * truncation - d[:, None]
+    ce = torch.mean(torch.square(resid[center]))
+    ta = torch.mean(torch.square(resid[tail]))
+    return w_fs * fs + w_center * ce + w_tail * ta
+
+
+@dataclass
+class LossWeights:
+    fs: float
+    center: float
+    tail: float
+    depth: float
+    color: float
+
+
+TRACK_W = LossWeights(10, 200, 50, 1, 5)  # ESLAM.yaml:29-33
+MAP_W = LossWeights(5, 200, 10, 0.1, 5)  # ESLAM.yaml:53-57
+
+
+def tracking_loss(depth, rgb, sdf, z, gt_d, gt_c, truncation, w: LossWeights):
+    """Tracker.py:192-204: lower-median outlier mask (10x) applied to every term."""
+    err = (gt_d - depth.detach()).abs()
+    mask = err < 10 * err.median()
+    loss = sdf_loss(sdf[mask], z[mask], gt_d[mask], truncation, w.fs, w.center, w.tail)
+    loss = loss + w.color * torch.square(gt_c - rgb)[mask].mean()
+    loss = loss + w.depth * torch.square(gt_d[mask] - depth[mask]).mean()
+    return loss, mask
+
+
+def mapping_loss(depth, rgb, sdf, z, gt_d, gt_c, truncation, w: LossWeights):
+    """Mapper.py:337-346: sdf and depth terms over depth>0 rays, colour over all rays."""
+    mask = gt_d > 0
+    loss = sdf_loss(sdf[mask], z[mask], gt_d[mask], truncation, w.fs, w.center, w.tail)
+    loss = loss + w.color * torch.square(gt_c - rgb).mean()
+    loss = loss + w.depth * torch.square(gt_d[mask] - depth[mask]).mean()
+    return loss, mask
+
+
+# ----------------------------------------------------------------------------
+# A11: Adam   (torch/optim/adam.py single-tensor path; Tracker.py:291-296, Mapper.py:288-306)
+# ----------------------------------------------------------------------------
+
+
+def adam_update(p, g, m, v, step: int, lr: float, beta1=0.9, beta2=0.999, eps=1e-8):
+    """In-place on p,m,v.  m.lerp_(g,1-b1); v=b2*v+(1-b2)g^2;
+    p -= (lr/(1-b1^t)) * m / (sqrt(v)/sqrt(1-b2^t)+eps)."""
+    m.lerp_(g, 1 - beta1)
+    v.mul_(beta2).addcmul_(g, g, value=1 - beta2)
+    bc1 = 1 - beta1 ** step
+    bc2 = 1 - beta2 ** step
+    denom = (v.sqrt() / math.sqrt(bc2)).add_(eps)
+    p.addcdiv_(m, denom, value=-(lr / bc1))
+
+
+# ----------------------------------------------------------------------------
+# whole iterations
+# ----------------------------------------------------------------------------
+
+
+@dataclass
+class Camera:
+    H: int
+    W: int
+    fx: float
+    fy: float
+    cx: float
+    cy: float
+
+
+@dataclass
+class RenderCfg:
+    n_stratified: int = 32
+    n_importance: int = 8
+    truncation: float = 0.06
+    perturb: bool = True
+
+
+@dataclass
+class IterOut:
+    loss: torch.Tensor
+    idx: torch.Tensor
+    keep: torch.Tensor
+    rays_o: torch.Tensor
+    rays_d: torch.Tensor
+    gt_depth: torch.Tensor
+    gt_color: torch.Tensor
+    depth: torch.Tensor
+    rgb: torch.Tensor
+    sdf: torch.Tensor
+    z: torch.Tensor
+    mask: torch.Tensor
+    extra: dict = _dc_field(default_factory=dict)
+
+
+def tracking_forward(fld: Field, cam: Camera, rc: RenderCfg, w: LossWeights, cam_pose, gt_color, gt_depth,
+                     n_pixels, edge_h, edge_w, draws) -> IterOut:
+    """Tracker.optimize_tracking up to the loss (Tracker.py:150-204).  `cam_pose`
+    [1,7] may require grad; planes/decoders are used as given."""
+    c2w = cam_pose_to_matrix(cam_pose)
+    ro, rd, d, c, idx = sample_rays(edge_h, cam.H - edge_h, edge_w, cam.W - edge_w, n_pixels,
+                                    cam.fx, cam.fy, cam.cx, cam.cy, c2w, gt_depth, gt_color, draws)
+    with torch.no_grad():
+        keep = bbox_keep(ro, rd, d, fld.bound, need_depth=True)
+    ro, rd, d, c = ro[keep], rd[keep], d[keep], c[keep]
+    depth, rgb, sdf, z = render_rays(fld, ro, rd, d, rc.truncation, rc.n_stratified, rc.n_importance, draws, rc.perturb)
+    loss, mask = tracking_loss(depth, rgb, sdf, z, d, c, rc.truncation, w)
+    return IterOut(loss, idx, keep, ro, rd, d, c, depth, rgb, sdf, z, mask)
+
+
+def mapping_forward(fld: Field, cam: Camera, rc: RenderCfg, w: LossWeights, c2ws, gt_colors, gt_depths,
+                    pix_per_image, draws) -> IterOut:
+    """One iteration of Mapper.optimize_mapping up to the loss (Mapper.py:318-346).
+    `c2ws` [b,4,4] (may carry grad through cam_pose_to_matrix for joint_opt)."""
+    ro, rd, d, c, idx = sample_rays(0, cam.H, 0, cam.W, pix_per_image, cam.fx, cam.fy, cam.cx, cam.cy,
+                                    c2ws, gt_depths, gt_colors, draws)
+    with torch.no_grad():
+        keep = bbox_keep(ro, rd, d, fld.bound, need_depth=False)
+    ro, rd, d, c = ro[keep], rd[keep], d[keep], c[keep]
+    depth, rgb, sdf, z = render_rays(fld, ro, rd, d, rc.truncation, rc.n_stratified, rc.n_importance, draws, rc.perturb)
+    loss, mask = mapping_loss(depth, rgb, sdf, z, d, c, rc.truncation, w)
+    return IterOut(loss, idx, keep, ro, rd, d, c, depth, rgb, sdf, z, mask)
+
+
+def track_frame(fld: Field, cam: Camera, rc: RenderCfg, w: LossWeights, init_pose, gt_color, gt_depth,
+                n_pixels, edge_h, edge_w, iters, lr_T, lr_R, draws):
+    """The camera-iteration loop of Tracker.run (Tracker.py:291-309): Adam(betas .5,.999)
+    over T and R, best pose = the pose BEFORE the step with the lowest loss."""
+    T = torch.nn.Parameter(init_pose[:, -3:].clone())
+    Rq = torch.nn.Parameter(init_pose[:, :4].clone())
+    opt = torch.optim.Adam([{"params": [T], "lr": lr_T, "betas": (0.5, 0.999)},
+                            {"params": [Rq], "lr": lr_R, "betas": (0.5, 0.999)}])
+    best, best_pose, losses = float("inf"), None, []
+    for _ in range(iters):
+        pose = torch.cat([Rq, T], -1)
+        out = tracking_forward(fld, cam, rc, w, pose, gt_color, gt_depth, n_pixels, edge_h, edge_w, draws)
+        opt.zero_grad()
+        out.loss.backward()
+        opt.step()
+        lv = out.loss.item()
+        losses.append(lv)
+        if lv < best:
+            best, best_pose = lv, pose.clone().detach()
+    return best_pose, torch.cat([Rq, T], -1).detach(), losses
+
+
+def map_window(fld: Field, cam: Camera, rc: RenderCfg, w: LossWeights, c2ws, gt_colors, gt_depths, n_pixels, iters,
+               lr_dec, lr_planes, lr_cplanes, joint_opt, lr_cam, draws):
+    """The per-call body of Mapper.optimize_mapping (Mapper.py:249-362) for an
+    already-selected window: fresh Adam, per-group lrs, first pose fixed.
+    Updates `fld` in place; returns (updated c2ws [b,4,4], losses)."""
+    b = c2ws.shape[0]
+    pix = n_pixels // b
+    dec_params = [fld.dec[k].requires_grad_(True) for k in DECODER_KEYS] + [fld.beta.requires_grad_(True)]
+    pl = [p.requires_grad_(True) for g in fld.planes[:3] for p in g]
+    cpl = [p.requires_grad_(True) for g in fld.planes[3:] for p in g]
+    groups = [{"params": dec_params, "lr": lr_dec}, {"params": pl, "lr": lr_planes}, {"params": cpl, "lr": lr_cplanes}]
+    if joint_opt:
+        poses = torch.nn.Parameter(matrix_to_cam_pose(c2ws[1:]))
+        groups.append({"params": [poses], "lr": lr_cam})
+    opt = torch.optim.Adam(groups)
+    losses = []
+    for _ in range(iters):
+        cw = torch.cat([c2ws[0:1], cam_pose_to_matrix(poses)], 0) if joint_opt else c2ws
+        out = mapping_forward(fld, cam, rc, w, cw, gt_colors, gt_depths, pix, draws)
+        opt.zero_grad()
+        out.loss.backward()
+        opt.step()
+        losses.append(out.loss.item())
+    for t in dec_params + pl + cpl:
+        t.requires_grad_(False)
+    if joint_opt:
+        c2ws = torch.cat([c2ws[0:1], cam_pose_to_matrix(poses.detach())], 0)
+    return c2ws, losses
+
+
+# ----------------------------------------------------------------------------
+# A12: dense grid query for meshing   (Mesher.py:130-186)
+# ----------------------------------------------------------------------------
+
+
+def grid_axes(mc_bound, resolution, padding=0.05):
+    """Per-axis sample positions (float64 numpy) of get_grid_uniform (Mesher.py:159-177)."""
+    axes = []
+    mc = torch.as_tensor(np.array(mc_bound))
+    for a in range(3):
+        n = int(((mc[a][1] - mc[a][0] + 2 * padding) / resolution).round().int().item())
+        axes.append(np.linspace(float(mc[a][0]) - padding, float(mc[a][1]) + padding, n))
+    return axes
+
+
+def grid_points(axes):
+    """Flat point list in the reference's order: meshgrid(indexing='xy'), so
+    flat = (iy*nx + ix)*nz + iz.  Mesher.py:179-184."""
+    xt, yt, zt = (torch.from_numpy(a).float() for a in axes)
+    gx, gy, gz = torch.meshgrid(xt, yt, zt, indexing="xy")
+    return torch.stack([gx.reshape(-1), gy.reshape(-1), gz.reshape(-1)], 1)
+
+
+def query_points(fld: Field, p):
+    """eval_points (Mesher.py:130-157): decode, then force sdf=-1 outside the OPEN bound box."""
+    b = fld.bound
+    inside = ((p[:, 0] < b[0][1]) & (p[:, 0] > b[0][0]) & (p[:, 1] < b[1][1]) & (p[:, 1] > b[1][0])
+              & (p[:, 2] < b[2][1]) & (p[:, 2] > b[2][0]))
+    with torch.no_grad():
+        ret = decode(p, fld)
+    ret[~inside, -1] = -1
+    return ret
