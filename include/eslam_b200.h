@@ -1,0 +1,220 @@
+/*
+ * eslam_b200.h -- C ABI of the B200-native ESLAM render-and-optimise hot path.
+ *
+ * The reference (MohammadJohari/myslam) is pure Python and has NO FFI; this header is the boundary
+ * a maintainer would bind from `src/` with ctypes.  Each entry point names the
+ * reference code it replaces (paths relative to the reference root).
+ *
+ * Conventions
+ *  - Every pointer is a DEVICE pointer unless its name ends in `_host`.  The library never
+ *    allocates, frees or synchronises; the caller owns every buffer and passes the CUDA stream.
+ *  - Return value: 0 on success, otherwise a cudaError_t (>0) or a negative ESLAM_E* code;
+ *    eslam_last_error() gives a thread-local message.  No exceptions cross the ABI.
+ *  - Parameters live in ONE fp32 arena per process: the 12 feature planes in channels-last
+ *    [H][W][32] order (one 128-byte line per texel), then the packed decoders (ESLAM_DEC_FLOATS),
+ *    described by eslam_field_t.  Gradients and Adam moments use arenas of the same layout.
+ *  - Random numbers are INPUTS (pixel indices, uniforms): the caller draws them with torch so the
+ *    stream is the reference's (common.py:108, Renderer.py:59, common.py:59).
+ *  - The decoder weights are read through constant memory: eslam_bind_decoders() must be called on
+ *    the same stream after every change of the packed decoder block and before any kernel below
+ *    that decodes.  This is the only process-global state in the library.
+ */
+#ifndef ESLAM_B200_H
+#define ESLAM_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ESLAM_ABI_VERSION 1
+#define ESLAM_C_DIM 32        /* model.c_dim, configs/ESLAM.yaml:77 */
+#define ESLAM_HIDDEN 16       /* decoders.py:39 hidden_size */
+#define ESLAM_N_PLANES 12
+#define ESLAM_DEC_FLOATS 2700 /* 1329 (sdf, padded to 1332) + 1363 (rgb, padded to 1364) + beta, padded */
+#define ESLAM_MAX_SAMPLES 64  /* n_stratified + n_importance per ray */
+
+#define ESLAM_EINVAL (-1)
+#define ESLAM_EUNSUPPORTED (-2)
+
+typedef void* eslam_stream_t; /* cudaStream_t */
+
+/* One feature plane inside the arena. */
+typedef struct {
+  int64_t offset; /* float offset of texel (0,0) channel 0; multiple of 4 */
+  int32_t H, W;   /* rows, cols as in the reference's [1,32,H,W] tensors (ESLAM.py:196-210) */
+} eslam_plane_t;
+
+/* Plane order: sdf coarse xy,xz,yz | sdf fine xy,xz,yz | rgb coarse xy,xz,yz | rgb fine xy,xz,yz.
+ * xy is [ny][nx], xz is [nz][nx], yz is [nz][ny] (ESLAM.py:200 swap). */
+typedef struct {
+  eslam_plane_t plane[ESLAM_N_PLANES];
+  int64_t dec_offset;   /* float offset of the packed decoders in the arena */
+  int64_t n_floats;     /* arena length */
+  float bound[3][2];    /* scene bound after ESLAM.load_bound rounding (ESLAM.py:159-173) */
+} eslam_field_t;
+
+/* Packed decoder block, float offsets (row-major [out][in] like nn.Linear.weight; decoders.py:46-61);
+ * every sub-block starts on a multiple of 4 floats, pads are zero:
+ *   sdf:  W1[16][64] @0     b1[16] @1024  W2[16][16] @1040  b2[16] @1296  W3[1][16] @1312  b3[1] @1328
+ *   rgb:  W1[16][64] @1332  b1[16] @2356  W2[16][16] @2372  b2[16] @2628  W3[3][16] @2644  b3[3] @2692
+ *   beta[1] @2696                                                                                   */
+#define ESLAM_DEC_BETA 2696
+
+typedef struct {
+  int32_t H, W;              /* image size */
+  float fx, fy, cx, cy;
+  int32_t H0, H1, W0, W1;    /* crop the pixels are drawn from (Tracker.py:170-173, Mapper.py:318-319) */
+} eslam_camera_t;
+
+/* Scalars stay DOUBLE across the ABI: the reference evaluates e.g. `1.5 * truncation` in Python
+ * doubles and only then rounds to fp32 (Renderer.py:97), which differs from rounding first. */
+typedef struct {
+  int32_t n_stratified, n_importance;  /* rendering.* in the yaml */
+  double truncation;                   /* model.truncation */
+  double w_fs, w_center, w_tail, w_depth, w_color;
+} eslam_render_cfg_t;
+
+/* Device-side counters written by eslam_sample_rays / eslam_track_mask (int32[8]):
+ * [0] R rays kept  [1] R0 depth-less rays among them  [2] rays in the loss mask
+ * [3] front samples [4] center samples [5] tail samples (over masked rays)  [6],[7] reserved */
+#define ESLAM_N_COUNTERS 8
+/* Device-side loss accumulators (double[8]): fs, center, tail, depth, colour sums; [5] = loss */
+#define ESLAM_N_LOSS 8
+
+const char* eslam_last_error(void);
+int eslam_abi_version(void);
+
+/* ---- layout: the reference's NCHW planes <-> the channels-last arena ------------------------ */
+/* replaces nothing in the reference; it is the price of keeping ESLAM.py's [1,32,H,W] storage. */
+int eslam_plane_import(const float* nchw, float* arena, const eslam_plane_t* plane_host, eslam_stream_t s);
+int eslam_plane_export(const float* arena, float* nchw, const eslam_plane_t* plane_host, eslam_stream_t s);
+
+/* ---- decoders --------------------------------------------------------------------------------- */
+/* Copy the packed decoder block (device, ESLAM_DEC_FLOATS floats) into constant memory. */
+int eslam_bind_decoders(const float* dec, eslam_stream_t s);
+
+/* Decoders.forward / get_raw_sdf / get_raw_rgb (src/networks/decoders.py:87-146) on N points.
+ * raw[N][4] = (r,g,b,sdf).  flags: bit0 = sdf only (rgb left untouched), bit1 = Mesher.eval_points
+ * masking, sdf=-1 outside the OPEN bound box (src/utils/Mesher.py:143-153), bit2 = pts are already
+ * normalised to [-1,1] (get_raw_sdf / get_raw_rgb take p_nor). */
+int eslam_decode_points(const eslam_field_t* field_host, const float* arena, const float* pts, int64_t n,
+                        float* raw, int flags, eslam_stream_t s);
+
+/* Backward of eslam_decode_points for an upstream gradient g_raw[N][4]: grad_arena (+=, may be NULL) and
+ * g_pts[N][3] (=, may be NULL).  This is autograd through Decoders.forward (decoders.py:127-146). */
+int eslam_decode_backward(const eslam_field_t* field_host, const float* arena, const float* pts, int64_t n,
+                          const float* g_raw, float* grad_arena, float* g_pts, eslam_stream_t s);
+
+/* Decoders.sample_plane_feature (decoders.py:64-85): feat[N][64] for the sdf (which=0) or rgb (1) planes
+ * from NORMALISED coordinates p_nor[N][3]. */
+int eslam_sample_plane_feature(const eslam_field_t* field_host, const float* arena, const float* p_nor, int64_t n,
+                               int which, float* feat, eslam_stream_t s);
+
+/* Mesher.get_grid_uniform + eval_points sdf (src/utils/Mesher.py:130-186) for flat grid indices
+ * [start, start+count): flat = (iy*nx + ix)*nz + iz, coordinates from the three axis arrays. */
+int eslam_grid_sdf(const eslam_field_t* field_host, const float* arena, const float* xs, const float* ys,
+                   const float* zs, int nx, int ny, int nz, int64_t start, int64_t count, float* sdf,
+                   eslam_stream_t s);
+
+/* ---- pixel pick, rays, bbox filter, depth-guided samples --------------------------------------- */
+/* get_samples + the bbox pre-filter + the depth>0 half of render_batch_ray's sampling
+ * (src/common.py:87-153, src/Tracker.py:175-187, src/Mapper.py:322-332, src/utils/Renderer.py:81-106).
+ *   pix_idx[n_img*n_per_img]  int64 draws of torch.randint(Hc*Wc, ...) (common.py:108)
+ *   c2w[n_img][16]; if poses != NULL, frames >= pose_first take (qw,qx,qy,qz,tx,ty,tz) from poses[n_img][7]
+ *   depth[n_img][H][W] f32, color[n_img][H][W][3] f64
+ *   u_depth[>=R1][S] uniforms for the perturbation of depth>0 rays, indexed by their ORDINAL among the
+ *   depth>0 kept rays (the reference draws rand[R1,S], Renderer.py:59); NULL = no perturbation
+ *   t_uni[n_stratified], t_surf[n_importance] = torch.linspace(0,1,n) tables (Renderer.py:85-86)
+ * Outputs (capacity n_img*n_per_img rays, compacted in the reference's order):
+ *   rays_o/rays_d[R][3], gt_depth[R], gt_color[R][3] f64, src[R] = original slot (frame = src / n_per_img),
+ *   z[R][S] (filled for depth>0 rays), dl_list[R0] = compact index of each depth-less ray,
+ *   band[R][4] u8 = (#front,#center,#tail,depth>0) per ray, counters (see above; [2..5] filled with the
+ *   mapper's depth>0 mask), c2w_out[n_img][16] (may be NULL).  need_depth=1 drops depth<=0 rays (tracker). */
+int eslam_sample_rays(const eslam_field_t* field_host, const eslam_camera_t* cam_host,
+                      const eslam_render_cfg_t* cfg_host, const int64_t* pix_idx, int n_img, int n_per_img,
+                      const float* c2w, const float* poses, int pose_first, const float* depth,
+                      const double* color, const float* u_depth, const float* t_uni, const float* t_surf,
+                      int need_depth, float* rays_o, float* rays_d, float* gt_depth, double* gt_color,
+                      int32_t* src, float* z, int32_t* dl_list, uint8_t* band, int32_t* counters, float* c2w_out,
+                      eslam_stream_t s);
+
+/* Depth-guided z_vals for an already compacted ray list with explicit gt_depth (the first half of
+ * render_batch_ray when called through the reference's API, Renderer.py:88-106): fills the z rows of
+ * depth>0 rays, lists the others in dl_list, counters[0]=n_rays, counters[1]=R0. */
+int eslam_depth_samples(const eslam_render_cfg_t* cfg_host, const float* gt_depth, int n_rays, const float* u_depth,
+                        const float* t_uni, const float* t_surf, float* z, int32_t* dl_list, int32_t* counters,
+                        eslam_stream_t s);
+
+/* The depth-less half of render_batch_ray's sampling (Renderer.py:108-134, common.py:41-77):
+ * coarse SDF pass + inverse-cdf resampling for the rays in dl_list; fills their rows of z.
+ * u_coarse[>=R0][n_stratified], u_fine[>=R0][n_importance] indexed by depth-less ordinal.
+ * max_rays bounds the launch (R0 is read on the device from counters[1]). */
+int eslam_importance_samples(const eslam_field_t* field_host, const float* arena, const eslam_render_cfg_t* cfg_host,
+                             const float* rays_o, const float* rays_d, const int32_t* dl_list,
+                             const int32_t* counters, int max_rays, const float* u_coarse, const float* u_fine,
+                             const float* t_uni, float* z, eslam_stream_t s);
+
+/* ---- render --------------------------------------------------------------------------------- */
+/* The second half of Renderer.render_batch_ray (Renderer.py:136-147): points -> decoders -> sdf2alpha ->
+ * transmittance weights -> depth[R], rgb[R][3], sdf[R][S] (sdf may be NULL).  n_rays may be an upper bound
+ * when counters != NULL (R = counters[0] is read on the device). */
+int eslam_render_forward(const eslam_field_t* field_host, const float* arena, const float* rays_o,
+                         const float* rays_d, const float* z, int n_rays, int n_samples, const int32_t* counters,
+                         float* depth, float* rgb, float* sdf, eslam_stream_t s);
+
+/* Backward of the above for arbitrary upstream gradients (autograd through render_batch_ray):
+ * g_depth[R], g_rgb[R][3], g_sdf[R][S] (may be NULL) -> grad_arena (+=, planes and decoders incl. beta; may
+ * be NULL), g_rays_o/g_rays_d[R][3] (=, both or neither). */
+int eslam_render_backward(const eslam_field_t* field_host, const float* arena, const float* rays_o,
+                          const float* rays_d, const float* z, int n_rays, int n_samples, const float* g_depth,
+                          const float* g_rgb, const float* g_sdf, float* grad_arena, float* g_rays_o,
+                          float* g_rays_d, eslam_stream_t s);
+
+/* ---- fused iteration pieces ----------------------------------------------------------------- */
+/* Tracker.py:192-195: lower-median outlier mask over the kept rays and the masked band counts.
+ * ray_mask[R] u8, counters[2..5]; scratch: max_rays+1 floats (scratch[max_rays] = the median). */
+int eslam_track_mask(const float* gt_depth, const float* depth, const uint8_t* band, int max_rays,
+                     int32_t* counters, uint8_t* ray_mask, float* scratch, eslam_stream_t s);
+
+/* Forward recompute + the five losses + full backward in one pass
+ * (Tracker.py:114-148,192-208; Mapper.py:110-144,337-349).
+ *   ray_mask == NULL: mapper rule (sdf/depth terms over depth>0 rays, colour over all rays);
+ *   else tracker rule (every term over masked rays).  counters[0] bounds the rays of THIS launch; the loss
+ *   normalisers are norm_counters[0,2..5] (NULL = counters; on several GPUs the all-reduced counters, so every
+ *   rank differentiates the same global-batch loss).
+ *   grad_arena != NULL: plane + decoder + beta gradients are accumulated (+=).
+ *   pose_grad != NULL: d loss / d c2w[frame][3][4] accumulated per frame (frame = src / n_per_img).
+ *   loss_acc: double[ESLAM_N_LOSS] accumulators (+=), may be NULL. */
+int eslam_loss_backward(const eslam_field_t* field_host, const float* arena, const eslam_camera_t* cam_host,
+                        const eslam_render_cfg_t* cfg_host, const float* rays_o, const float* rays_d,
+                        const float* z, const float* gt_depth, const double* gt_color, const int32_t* src,
+                        const int64_t* pix_idx, int n_per_img, const uint8_t* ray_mask, const int32_t* counters,
+                        const int32_t* norm_counters, int max_rays, float* grad_arena, float* pose_grad,
+                        double* loss_acc, eslam_stream_t s);
+
+/* torch.optim.Adam single-tensor update (torch/optim/adam.py) over a flat arena with up to 4 lr segments
+ * [seg_end[i-1], seg_end[i]) (multiples of 4 floats); zeroes the gradient afterwards (the zero_grad of the
+ * next iteration).  Bias corrections are computed from `step` (1-based) on the host in doubles. */
+int eslam_adam_step(float* param, float* grad, float* exp_avg, float* exp_avg_sq, int64_t n,
+                    const int64_t* seg_end_host, const double* seg_lr_host, int n_seg, int step, double beta1,
+                    double beta2, double eps, eslam_stream_t s);
+
+/* cam_pose_to_matrix backward (common.py:169-181 with pytorch3d quaternion_to_matrix) for frames
+ * [first, n): pose_grad[n][12] (d loss / d c2w[:3,:4]) -> grad7[n][7] = d loss / d (q,t) (may be NULL);
+ * if apply: Adam step on poses[n][7] with lr_q / lr_t and state exp_avg/exp_avg_sq[n][7]; zeroes pose_grad. */
+int eslam_pose_adam_step(float* poses, float* pose_grad, float* exp_avg, float* exp_avg_sq, int n, int first,
+                         double lr_q, double lr_t, int step, double beta1, double beta2, double eps, float* grad7,
+                         int apply, eslam_stream_t s);
+
+/* loss_acc[5] = w_fs*fs/Nf + w_center*ce/Nc + w_tail*ta/Nt + w_color*col/(3*Ncol) + w_depth*dep/Nd (float64
+ * like the reference's loss, whose colour term is float64), also written as float to loss_out (may be NULL);
+ * loss_acc[0..4] are reset to 0. */
+int eslam_finalize_loss(const eslam_render_cfg_t* cfg_host, const int32_t* counters, int tracker_rule,
+                        double* loss_acc, float* loss_out, eslam_stream_t s);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ESLAM_B200_H */

@@ -1,0 +1,131 @@
+"""ctypes binding of libeslam_b200.so (include/eslam_b200.h).
+
+There is NO fallback: if the library is missing or a call fails, a RuntimeError is raised.
+The library is built in-tree by `__graft_entry__.build()` / `myslam_b200.build.build_library()`.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libeslam_b200.so")
+
+N_PLANES = 12
+DEC_FLOATS = 2700
+DEC_BETA = 2696
+N_COUNTERS = 8
+N_LOSS = 8
+MAX_SAMPLES = 64
+ABI_VERSION = 1
+
+
+class Plane(C.Structure):
+    _fields_ = [("offset", C.c_int64), ("H", C.c_int32), ("W", C.c_int32)]
+
+
+class FieldDesc(C.Structure):
+    _fields_ = [("plane", Plane * N_PLANES), ("dec_offset", C.c_int64), ("n_floats", C.c_int64),
+                ("bound", (C.c_float * 2) * 3)]
+
+
+class Camera(C.Structure):
+    _fields_ = [("H", C.c_int32), ("W", C.c_int32), ("fx", C.c_float), ("fy", C.c_float), ("cx", C.c_float),
+                ("cy", C.c_float), ("H0", C.c_int32), ("H1", C.c_int32), ("W0", C.c_int32), ("W1", C.c_int32)]
+
+
+class RenderCfg(C.Structure):
+    _fields_ = [("n_stratified", C.c_int32), ("n_importance", C.c_int32), ("truncation", C.c_double),
+                ("w_fs", C.c_double), ("w_center", C.c_double), ("w_tail", C.c_double), ("w_depth", C.c_double),
+                ("w_color", C.c_double)]
+
+
+_P = C.c_void_p
+_I = C.c_int
+_L = C.c_int64
+_D = C.c_double
+_FP = C.POINTER(FieldDesc)
+_CP = C.POINTER(Camera)
+_RP = C.POINTER(RenderCfg)
+_PP = C.POINTER(Plane)
+
+# name -> argtypes, exactly include/eslam_b200.h
+PROTOTYPES = {
+    "eslam_plane_import": [_P, _P, _PP, _P],
+    "eslam_plane_export": [_P, _P, _PP, _P],
+    "eslam_bind_decoders": [_P, _P],
+    "eslam_decode_points": [_FP, _P, _P, _L, _P, _I, _P],
+    "eslam_decode_backward": [_FP, _P, _P, _L, _P, _P, _P, _P],
+    "eslam_sample_plane_feature": [_FP, _P, _P, _L, _I, _P, _P],
+    "eslam_grid_sdf": [_FP, _P, _P, _P, _P, _I, _I, _I, _L, _L, _P, _P],
+    "eslam_sample_rays": [_FP, _CP, _RP, _P, _I, _I, _P, _P, _I, _P, _P, _P, _P, _P, _I, _P, _P, _P, _P, _P, _P, _P,
+                          _P, _P, _P, _P],
+    "eslam_depth_samples": [_RP, _P, _I, _P, _P, _P, _P, _P, _P, _P],
+    "eslam_importance_samples": [_FP, _P, _RP, _P, _P, _P, _P, _I, _P, _P, _P, _P, _P],
+    "eslam_render_forward": [_FP, _P, _P, _P, _P, _I, _I, _P, _P, _P, _P, _P],
+    "eslam_render_backward": [_FP, _P, _P, _P, _P, _I, _I, _P, _P, _P, _P, _P, _P, _P],
+    "eslam_track_mask": [_P, _P, _P, _I, _P, _P, _P, _P],
+    "eslam_loss_backward": [_FP, _P, _CP, _RP, _P, _P, _P, _P, _P, _P, _P, _I, _P, _P, _P, _I, _P, _P, _P, _P],
+    "eslam_adam_step": [_P, _P, _P, _P, _L, C.POINTER(C.c_int64), C.POINTER(C.c_double), _I, _I, _D, _D, _D, _P],
+    "eslam_pose_adam_step": [_P, _P, _P, _P, _I, _I, _D, _D, _I, _D, _D, _D, _P, _I, _P],
+    "eslam_finalize_loss": [_RP, _P, _I, _P, _P, _P],
+}
+
+_lib = None
+
+
+def load():
+    """Load the shared library (once).  Raises if it has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise RuntimeError(
+            f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+            "(nvcc, sm_100a).  myslam_b200 has no CPU or PyTorch fallback.")
+    lib = C.CDLL(LIB_PATH)
+    lib.eslam_last_error.restype = C.c_char_p
+    lib.eslam_last_error.argtypes = []
+    lib.eslam_abi_version.restype = C.c_int
+    lib.eslam_abi_version.argtypes = []
+    for name, argtypes in PROTOTYPES.items():
+        fn = getattr(lib, name)  # AttributeError if the symbol is not exported
+        fn.restype = C.c_int
+        fn.argtypes = argtypes
+    if lib.eslam_abi_version() != ABI_VERSION:
+        raise RuntimeError(f"libeslam_b200.so ABI {lib.eslam_abi_version()} != binding {ABI_VERSION}; rebuild")
+    _lib = lib
+    return lib
+
+
+def ptr(t):
+    """Device (or host) address of a tensor; None -> NULL."""
+    if t is None:
+        return None
+    assert t.is_contiguous(), "eslam kernels take contiguous buffers"
+    return t.data_ptr()
+
+
+def stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+LAUNCHES = 0  # kernels launched through the ABI (bench.py reports it as gpu_launches)
+_NO_KERNEL = ("eslam_bind_decoders",)
+
+
+def call(name, *args):
+    global LAUNCHES
+    lib = load()
+    rc = getattr(lib, name)(*args)
+    if name not in _NO_KERNEL:
+        LAUNCHES += 1
+    if rc != 0:
+        raise RuntimeError(f"{name} failed ({rc}): {lib.eslam_last_error().decode()}")
+
+
+def require_cuda(t, what):
+    if not (torch.is_tensor(t) and t.is_cuda):
+        raise RuntimeError(f"{what}: expected a CUDA tensor; myslam_b200 has no CPU path")

@@ -1,0 +1,549 @@
+// C ABI of the B200-native ESLAM hot path (include/eslam_b200.h).  One translation unit: the constant
+// decoder block is shared by every kernel.  Host side: argument checks, kernel-argument packing, launches.
+#include <cstdio>
+#include <cstring>
+#include <cmath>
+
+#include "field.cuh"
+
+#include "render.cuh"
+#include "sample.cuh"
+#include "optim.cuh"
+
+using namespace eslam;
+
+static thread_local char g_err[512] = "";
+
+static int fail(int code, const char* what) {
+  if (code > 0)
+    snprintf(g_err, sizeof(g_err), "%s: %s", what, cudaGetErrorString((cudaError_t)code));
+  else
+    snprintf(g_err, sizeof(g_err), "%s: invalid or unsupported argument (%d)", what, code);
+  return code;
+}
+
+#define CHECK_LAUNCH(what)                         \
+  do {                                             \
+    cudaError_t e_ = cudaGetLastError();           \
+    if (e_ != cudaSuccess) return fail((int)e_, what); \
+  } while (0)
+
+#define REQUIRE(cond, what) \
+  do {                      \
+    if (!(cond)) return fail(ESLAM_EINVAL, what); \
+  } while (0)
+
+static inline cudaStream_t S_(eslam_stream_t s) { return (cudaStream_t)s; }
+
+struct CfgK {
+  int n_strat, n_imp;
+  float tr, tr15, tr3, tr04;
+  float w_fs, w_center, w_tail, w_depth;
+  double w_color;
+};
+
+// Python evaluates `1.5 * truncation`, `3 * truncation`, `0.4 * truncation` in doubles before torch rounds
+// the scalar to fp32 (Renderer.py:97, Tracker.py:135)
+static CfgK make_cfg(const eslam_render_cfg_t* c) {
+  CfgK k;
+  k.n_strat = c->n_stratified;
+  k.n_imp = c->n_importance;
+  k.tr = (float)c->truncation;
+  k.tr15 = (float)(1.5 * c->truncation);
+  k.tr3 = (float)(3 * c->truncation);
+  k.tr04 = (float)(0.4 * c->truncation);
+  k.w_fs = (float)c->w_fs;
+  k.w_center = (float)c->w_center;
+  k.w_tail = (float)c->w_tail;
+  k.w_depth = (float)c->w_depth;
+  k.w_color = c->w_color;
+  return k;
+}
+
+static int check_samples(int n_strat, int n_imp) {
+  const int S = n_strat + n_imp;
+  if (n_strat < 2 || n_imp < 1 || n_imp > 16 || S > ESLAM_MAX_SAMPLES || n_strat > NP) return ESLAM_EUNSUPPORTED;
+  return 0;
+}
+
+template <typename K>
+static int set_smem(K kernel, size_t bytes) {
+  return (int)cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+}
+
+extern "C" {
+
+const char* eslam_last_error(void) { return g_err; }
+int eslam_abi_version(void) { return ESLAM_ABI_VERSION; }
+
+int eslam_plane_import(const float* nchw, float* arena, const eslam_plane_t* pl, eslam_stream_t s) {
+  REQUIRE(nchw && arena && pl && pl->H > 0 && pl->W > 0, "eslam_plane_import");
+  const int HW = pl->H * pl->W;
+  k_plane_layout<true><<<(HW + 31) / 32, 256, 0, S_(s)>>>(nchw, arena + pl->offset, HW);
+  CHECK_LAUNCH("eslam_plane_import");
+  return 0;
+}
+
+int eslam_plane_export(const float* arena, float* nchw, const eslam_plane_t* pl, eslam_stream_t s) {
+  REQUIRE(nchw && arena && pl && pl->H > 0 && pl->W > 0, "eslam_plane_export");
+  const int HW = pl->H * pl->W;
+  k_plane_layout<false><<<(HW + 31) / 32, 256, 0, S_(s)>>>(arena + pl->offset, nchw, HW);
+  CHECK_LAUNCH("eslam_plane_export");
+  return 0;
+}
+
+int eslam_bind_decoders(const float* dec, eslam_stream_t s) {
+  REQUIRE(dec, "eslam_bind_decoders");
+  cudaError_t e = cudaMemcpyToSymbolAsync(c_dec, dec, sizeof(float) * DEC_N, 0, cudaMemcpyDeviceToDevice, S_(s));
+  if (e != cudaSuccess) return fail((int)e, "eslam_bind_decoders");
+  return 0;
+}
+
+int eslam_decode_points(const eslam_field_t* f, const float* arena, const float* pts, int64_t n, float* raw,
+                        int flags, eslam_stream_t s) {
+  REQUIRE(f && arena && pts && raw && n >= 0, "eslam_decode_points");
+  if (n == 0) return 0;
+  DecodeArgs a;
+  memset(&a, 0, sizeof(a));
+  int rc = make_field_k(f, &a.fk);
+  if (rc) return fail(rc, "eslam_decode_points(field)");
+  a.arena4 = reinterpret_cast<const float4*>(arena);
+  a.pts = pts;
+  a.n = n;
+  a.raw = raw;
+  a.flags = flags & 7;
+  k_decode<<<(unsigned)((n + NP - 1) / NP), NP, 0, S_(s)>>>(a);
+  CHECK_LAUNCH("eslam_decode_points");
+  return 0;
+}
+
+int eslam_sample_plane_feature(const eslam_field_t* f, const float* arena, const float* p_nor, int64_t n, int which,
+                               float* feat, eslam_stream_t s) {
+  REQUIRE(f && arena && p_nor && feat && n >= 0 && (which == 0 || which == 1), "eslam_sample_plane_feature");
+  if (n == 0) return 0;
+  FeatArgs a;
+  int rc = make_field_k(f, &a.fk);
+  if (rc) return fail(rc, "eslam_sample_plane_feature(field)");
+  a.arena4 = reinterpret_cast<const float4*>(arena);
+  a.p_nor = p_nor;
+  a.n = n;
+  a.which = which;
+  a.feat4 = reinterpret_cast<float4*>(feat);
+  k_plane_feature<<<(unsigned)((n + NP - 1) / NP), NP, 0, S_(s)>>>(a);
+  CHECK_LAUNCH("eslam_sample_plane_feature");
+  return 0;
+}
+
+int eslam_grid_sdf(const eslam_field_t* f, const float* arena, const float* xs, const float* ys, const float* zs,
+                   int nx, int ny, int nz, int64_t start, int64_t count, float* sdf, eslam_stream_t s) {
+  REQUIRE(f && arena && xs && ys && zs && sdf && nx > 0 && ny > 0 && nz > 0 && start >= 0 && count >= 0 &&
+              start + count <= (int64_t)nx * ny * nz,
+          "eslam_grid_sdf");
+  if (count == 0) return 0;
+  DecodeArgs a;
+  memset(&a, 0, sizeof(a));
+  int rc = make_field_k(f, &a.fk);
+  if (rc) return fail(rc, "eslam_grid_sdf(field)");
+  a.arena4 = reinterpret_cast<const float4*>(arena);
+  a.n = count;
+  a.sdf_out = sdf;
+  a.flags = 1 | 2;
+  a.xs = xs;
+  a.ys = ys;
+  a.zs = zs;
+  a.nx = nx;
+  a.ny = ny;
+  a.nz = nz;
+  a.start = start;
+  k_decode<<<(unsigned)((count + NP - 1) / NP), NP, 0, S_(s)>>>(a);
+  CHECK_LAUNCH("eslam_grid_sdf");
+  return 0;
+}
+
+int eslam_sample_rays(const eslam_field_t* f, const eslam_camera_t* cam, const eslam_render_cfg_t* cfg,
+                      const int64_t* pix_idx, int n_img, int n_per_img, const float* c2w, const float* poses,
+                      int pose_first, const float* depth, const double* color, const float* u_depth,
+                      const float* t_uni, const float* t_surf, int need_depth, float* rays_o, float* rays_d,
+                      float* gt_depth, double* gt_color, int32_t* src, float* z, int32_t* dl_list, uint8_t* band,
+                      int32_t* counters, float* c2w_out, eslam_stream_t s) {
+  REQUIRE(f && cam && cfg && pix_idx && depth && color && t_uni && t_surf && rays_o && rays_d && gt_depth &&
+              gt_color && src && z && dl_list && band && counters && n_img > 0 && n_per_img > 0 && (c2w || poses),
+          "eslam_sample_rays");
+  REQUIRE(c2w || pose_first == 0, "eslam_sample_rays(c2w)");
+  int rc = check_samples(cfg->n_stratified, cfg->n_importance);
+  if (rc) return fail(rc, "eslam_sample_rays(samples)");
+  SampleArgs a;
+  memset(&a, 0, sizeof(a));
+  rc = make_field_k(f, &a.fk);
+  if (rc) return fail(rc, "eslam_sample_rays(field)");
+  const CfgK k = make_cfg(cfg);
+  a.H = cam->H;
+  a.W = cam->W;
+  a.H0 = cam->H0;
+  a.W0 = cam->W0;
+  a.Wc = cam->W1 - cam->W0;
+  a.HWc = a.Wc * (cam->H1 - cam->H0);
+  REQUIRE(a.Wc > 0 && cam->H1 > cam->H0 && cam->H1 <= cam->H && cam->W1 <= cam->W && cam->H0 >= 0 && cam->W0 >= 0,
+          "eslam_sample_rays(crop)");
+  a.fx = cam->fx;
+  a.fy = cam->fy;
+  a.cx = cam->cx;
+  a.cy = cam->cy;
+  a.n_strat = k.n_strat;
+  a.n_imp = k.n_imp;
+  a.tr = k.tr;
+  a.tr15 = k.tr15;
+  a.tr3 = k.tr3;
+  a.tr04 = k.tr04;
+  a.pix_idx = reinterpret_cast<const long long*>(pix_idx);
+  a.n_img = n_img;
+  a.n_per_img = n_per_img;
+  a.c2w = c2w;
+  a.poses = poses;
+  a.pose_first = pose_first;
+  a.depth = depth;
+  a.color = color;
+  a.u_depth = u_depth;
+  a.t_uni = t_uni;
+  a.t_surf = t_surf;
+  a.need_depth = need_depth;
+  a.rays_o = rays_o;
+  a.rays_d = rays_d;
+  a.gt_depth = gt_depth;
+  a.gt_color = gt_color;
+  a.src = src;
+  a.z = z;
+  a.dl_list = dl_list;
+  a.band = band;
+  a.counters = counters;
+  a.c2w_out = c2w_out;
+  cudaError_t e = cudaMemsetAsync(counters, 0, sizeof(int32_t) * ESLAM_N_COUNTERS, S_(s));
+  if (e != cudaSuccess) return fail((int)e, "eslam_sample_rays(memset)");
+  const int N = n_img * n_per_img;
+  k_sample_rays<<<(N + SB - 1) / SB, SB, 0, S_(s)>>>(a);
+  CHECK_LAUNCH("eslam_sample_rays");
+  return 0;
+}
+
+int eslam_depth_samples(const eslam_render_cfg_t* cfg, const float* gt_depth, int n_rays, const float* u_depth,
+                        const float* t_uni, const float* t_surf, float* z, int32_t* dl_list, int32_t* counters,
+                        eslam_stream_t s) {
+  REQUIRE(cfg && gt_depth && t_uni && t_surf && z && dl_list && counters && n_rays >= 0, "eslam_depth_samples");
+  int rc = check_samples(cfg->n_stratified, cfg->n_importance);
+  if (rc) return fail(rc, "eslam_depth_samples(samples)");
+  cudaError_t e = cudaMemsetAsync(counters, 0, sizeof(int32_t) * ESLAM_N_COUNTERS, S_(s));
+  if (e != cudaSuccess) return fail((int)e, "eslam_depth_samples(memset)");
+  if (n_rays == 0) return 0;
+  const CfgK k = make_cfg(cfg);
+  DepthSampleArgs a;
+  a.n_strat = k.n_strat;
+  a.n_imp = k.n_imp;
+  a.tr = k.tr;
+  a.tr15 = k.tr15;
+  a.tr3 = k.tr3;
+  a.tr04 = k.tr04;
+  a.gt_depth = gt_depth;
+  a.n_rays = n_rays;
+  a.u_depth = u_depth;
+  a.t_uni = t_uni;
+  a.t_surf = t_surf;
+  a.z = z;
+  a.dl_list = dl_list;
+  a.counters = counters;
+  k_depth_samples<<<(n_rays + SB - 1) / SB, SB, 0, S_(s)>>>(a);
+  CHECK_LAUNCH("eslam_depth_samples");
+  return 0;
+}
+
+int eslam_importance_samples(const eslam_field_t* f, const float* arena, const eslam_render_cfg_t* cfg,
+                             const float* rays_o, const float* rays_d, const int32_t* dl_list,
+                             const int32_t* counters, int max_rays, const float* u_coarse, const float* u_fine,
+                             const float* t_uni, float* z, eslam_stream_t s) {
+  REQUIRE(f && arena && cfg && rays_o && rays_d && dl_list && counters && u_coarse && u_fine && t_uni && z &&
+              max_rays >= 0,
+          "eslam_importance_samples");
+  if (max_rays == 0) return 0;
+  int rc = check_samples(cfg->n_stratified, cfg->n_importance);
+  if (rc) return fail(rc, "eslam_importance_samples(samples)");
+  ImportanceArgs a;
+  rc = make_field_k(f, &a.fk);
+  if (rc) return fail(rc, "eslam_importance_samples(field)");
+  a.arena4 = reinterpret_cast<const float4*>(arena);
+  a.n_strat = cfg->n_stratified;
+  a.n_imp = cfg->n_importance;
+  a.rays_o = rays_o;
+  a.rays_d = rays_d;
+  a.dl_list = dl_list;
+  a.counters = counters;
+  a.u_coarse = u_coarse;
+  a.u_fine = u_fine;
+  a.t_uni = t_uni;
+  a.z = z;
+  const int rpb = NP / a.n_strat;
+  k_importance<<<(max_rays + rpb - 1) / rpb, NP, 0, S_(s)>>>(a);
+  CHECK_LAUNCH("eslam_importance_samples");
+  return 0;
+}
+
+int eslam_render_forward(const eslam_field_t* f, const float* arena, const float* rays_o, const float* rays_d,
+                         const float* z, int n_rays, int n_samples, const int32_t* counters, float* depth, float* rgb,
+                         float* sdf, eslam_stream_t s) {
+  REQUIRE(f && arena && rays_o && rays_d && z && depth && rgb && n_rays >= 0, "eslam_render_forward");
+  REQUIRE(n_samples >= 1 && n_samples <= ESLAM_MAX_SAMPLES, "eslam_render_forward(n_samples)");
+  if (n_rays == 0) return 0;
+  RenderFwdArgs a;
+  int rc = make_field_k(f, &a.fk);
+  if (rc) return fail(rc, "eslam_render_forward(field)");
+  a.arena4 = reinterpret_cast<const float4*>(arena);
+  a.rays_o = rays_o;
+  a.rays_d = rays_d;
+  a.z = z;
+  a.n_rays = n_rays;
+  a.S = n_samples;
+  a.counters = counters;
+  a.depth = depth;
+  a.rgb = rgb;
+  a.sdf = sdf;
+  const int rpb = NP / n_samples;
+  k_render_fwd<<<(n_rays + rpb - 1) / rpb, NP, 0, S_(s)>>>(a);
+  CHECK_LAUNCH("eslam_render_forward");
+  return 0;
+}
+
+}  // extern "C"
+
+template <int MODE, bool GF, bool GR>
+static int launch_bwd(const BwdArgs& a, int n_rays, cudaStream_t st) {
+  static bool configured = false;
+  const size_t bytes = sizeof(SmemBwd<GF>);
+  if (!configured) {
+    int rc = set_smem(k_render_bwd<MODE, GF, GR>, bytes);
+    if (rc) return rc;
+    configured = true;
+  }
+  const int rpb = MODE == 2 ? NP : ((NP / a.S) < 16 ? (NP / a.S) : 16);
+  k_render_bwd<MODE, GF, GR><<<(n_rays + rpb - 1) / rpb, NP, bytes, st>>>(a);
+  return (int)cudaGetLastError();
+}
+
+extern "C" {
+
+int eslam_render_backward(const eslam_field_t* f, const float* arena, const float* rays_o, const float* rays_d,
+                          const float* z, int n_rays, int n_samples, const float* g_depth, const float* g_rgb,
+                          const float* g_sdf, float* grad_arena, float* g_rays_o, float* g_rays_d,
+                          eslam_stream_t s) {
+  REQUIRE(f && arena && rays_o && rays_d && z && g_depth && g_rgb && n_rays >= 0, "eslam_render_backward");
+  REQUIRE(n_samples >= 1 && n_samples <= ESLAM_MAX_SAMPLES, "eslam_render_backward(n_samples)");
+  REQUIRE((g_rays_o == nullptr) == (g_rays_d == nullptr), "eslam_render_backward(ray grads)");
+  if (n_rays == 0 || (!grad_arena && !g_rays_o)) return 0;
+  BwdArgs a;
+  memset(&a, 0, sizeof(a));
+  int rc = make_field_k(f, &a.fk);
+  if (rc) return fail(rc, "eslam_render_backward(field)");
+  a.arena4 = reinterpret_cast<const float4*>(arena);
+  a.rays_o = rays_o;
+  a.rays_d = rays_d;
+  a.z = z;
+  a.n_rays = n_rays;
+  a.S = n_samples;
+  a.g_depth = g_depth;
+  a.g_rgb = g_rgb;
+  a.g_sdf = g_sdf;
+  a.grad_arena = grad_arena;
+  a.g_rays_o = g_rays_o;
+  a.g_rays_d = g_rays_d;
+  if (grad_arena && g_rays_o)
+    rc = launch_bwd<0, true, true>(a, n_rays, S_(s));
+  else if (grad_arena)
+    rc = launch_bwd<0, true, false>(a, n_rays, S_(s));
+  else
+    rc = launch_bwd<0, false, true>(a, n_rays, S_(s));
+  if (rc) return fail(rc, "eslam_render_backward");
+  return 0;
+}
+
+int eslam_decode_backward(const eslam_field_t* f, const float* arena, const float* pts, int64_t n, const float* g_raw,
+                          float* grad_arena, float* g_pts, eslam_stream_t s) {
+  REQUIRE(f && arena && pts && g_raw && n >= 0 && n < 0x7fffffff / 4, "eslam_decode_backward");
+  if (n == 0 || (!grad_arena && !g_pts)) return 0;
+  BwdArgs a;
+  memset(&a, 0, sizeof(a));
+  int rc = make_field_k(f, &a.fk);
+  if (rc) return fail(rc, "eslam_decode_backward(field)");
+  a.arena4 = reinterpret_cast<const float4*>(arena);
+  a.rays_o = pts;
+  a.n_rays = (int)n;
+  a.S = 1;
+  a.g_sdf = g_raw;
+  a.grad_arena = grad_arena;
+  a.g_rays_o = g_pts;
+  if (grad_arena && g_pts)
+    rc = launch_bwd<2, true, true>(a, (int)n, S_(s));
+  else if (grad_arena)
+    rc = launch_bwd<2, true, false>(a, (int)n, S_(s));
+  else
+    rc = launch_bwd<2, false, true>(a, (int)n, S_(s));
+  if (rc) return fail(rc, "eslam_decode_backward");
+  return 0;
+}
+
+int eslam_track_mask(const float* gt_depth, const float* depth, const uint8_t* band, int max_rays, int32_t* counters,
+                     uint8_t* ray_mask, float* scratch, eslam_stream_t s) {
+  REQUIRE(gt_depth && depth && band && counters && ray_mask && scratch && max_rays > 0, "eslam_track_mask");
+  TrackMaskArgs a;
+  a.gt_depth = gt_depth;
+  a.depth = depth;
+  a.band = band;
+  a.max_rays = max_rays;
+  a.counters = counters;
+  a.ray_mask = ray_mask;
+  a.scratch = scratch;
+  k_track_mask<<<1, 1024, 0, S_(s)>>>(a);
+  CHECK_LAUNCH("eslam_track_mask");
+  return 0;
+}
+
+int eslam_loss_backward(const eslam_field_t* f, const float* arena, const eslam_camera_t* cam,
+                        const eslam_render_cfg_t* cfg, const float* rays_o, const float* rays_d, const float* z,
+                        const float* gt_depth, const double* gt_color, const int32_t* src, const int64_t* pix_idx,
+                        int n_per_img, const uint8_t* ray_mask, const int32_t* counters,
+                        const int32_t* norm_counters, int max_rays, float* grad_arena, float* pose_grad,
+                        double* loss_acc, eslam_stream_t s) {
+  REQUIRE(f && arena && cam && cfg && rays_o && rays_d && z && gt_depth && gt_color && counters && max_rays >= 0,
+          "eslam_loss_backward");
+  REQUIRE(!pose_grad || (src && pix_idx && n_per_img > 0), "eslam_loss_backward(pose)");
+  if (max_rays == 0) return 0;
+  int rc = check_samples(cfg->n_stratified, cfg->n_importance);
+  if (rc) return fail(rc, "eslam_loss_backward(samples)");
+  const CfgK k = make_cfg(cfg);
+  BwdArgs a;
+  memset(&a, 0, sizeof(a));
+  rc = make_field_k(f, &a.fk);
+  if (rc) return fail(rc, "eslam_loss_backward(field)");
+  a.arena4 = reinterpret_cast<const float4*>(arena);
+  a.rays_o = rays_o;
+  a.rays_d = rays_d;
+  a.z = z;
+  a.n_rays = max_rays;
+  a.S = k.n_strat + k.n_imp;
+  a.counters = counters;
+  a.norm = norm_counters ? norm_counters : counters;
+  a.gt_depth = gt_depth;
+  a.gt_color = gt_color;
+  a.src = src;
+  a.pix_idx = reinterpret_cast<const long long*>(pix_idx);
+  a.n_per_img = n_per_img;
+  a.ray_mask = ray_mask;
+  a.tr = k.tr;
+  a.tr04 = k.tr04;
+  a.w_fs = k.w_fs;
+  a.w_center = k.w_center;
+  a.w_tail = k.w_tail;
+  a.w_depth = k.w_depth;
+  a.w_color = k.w_color;
+  a.fx = cam->fx;
+  a.fy = cam->fy;
+  a.cx = cam->cx;
+  a.cy = cam->cy;
+  a.W0 = cam->W0;
+  a.H0 = cam->H0;
+  a.Wc = cam->W1 - cam->W0;
+  a.loss_acc = loss_acc;
+  a.grad_arena = grad_arena;
+  a.pose_grad = pose_grad;
+  if (grad_arena && pose_grad)
+    rc = launch_bwd<1, true, true>(a, max_rays, S_(s));
+  else if (grad_arena)
+    rc = launch_bwd<1, true, false>(a, max_rays, S_(s));
+  else if (pose_grad)
+    rc = launch_bwd<1, false, true>(a, max_rays, S_(s));
+  else
+    return fail(ESLAM_EINVAL, "eslam_loss_backward(no gradient requested)");
+  if (rc) return fail(rc, "eslam_loss_backward");
+  return 0;
+}
+
+int eslam_adam_step(float* param, float* grad, float* exp_avg, float* exp_avg_sq, int64_t n,
+                    const int64_t* seg_end, const double* seg_lr, int n_seg, int step, double beta1, double beta2,
+                    double eps, eslam_stream_t s) {
+  REQUIRE(param && grad && exp_avg && exp_avg_sq && seg_end && seg_lr && n > 0 && (n % 4) == 0 && n_seg >= 1 &&
+              n_seg <= 4 && step >= 1,
+          "eslam_adam_step");
+  AdamArgs a;
+  a.p = param;
+  a.g = grad;
+  a.m = exp_avg;
+  a.v = exp_avg_sq;
+  a.n = n;
+  a.n_seg = n_seg;
+  const double bc1 = 1.0 - pow(beta1, (double)step);
+  for (int i = 0; i < 4; ++i) {
+    a.seg_end[i] = i < n_seg ? seg_end[i] : n;
+    a.seg_step[i] = i < n_seg ? (float)(seg_lr[i] / bc1) : 0.f;
+    if (i < n_seg) REQUIRE(seg_end[i] % 4 == 0, "eslam_adam_step(segment alignment)");
+  }
+  a.beta1 = (float)beta1;
+  a.beta2 = (float)beta2;
+  a.one_m_beta1 = (float)(1.0 - beta1);
+  a.one_m_beta2 = (float)(1.0 - beta2);
+  a.bc2_sqrt = (float)sqrt(1.0 - pow(beta2, (double)step));
+  a.eps = (float)eps;
+  const long long n4 = n / 4;
+  long long blocks = (n4 + 255) / 256;
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  k_adam<<<(unsigned)blocks, 256, 0, S_(s)>>>(a);
+  CHECK_LAUNCH("eslam_adam_step");
+  return 0;
+}
+
+int eslam_pose_adam_step(float* poses, float* pose_grad, float* exp_avg, float* exp_avg_sq, int n, int first,
+                         double lr_q, double lr_t, int step, double beta1, double beta2, double eps, float* grad7,
+                         int apply, eslam_stream_t s) {
+  REQUIRE(poses && pose_grad && n > 0 && first >= 0 && first <= n, "eslam_pose_adam_step");
+  REQUIRE(!apply || (exp_avg && exp_avg_sq && step >= 1), "eslam_pose_adam_step(state)");
+  if (first == n) return 0;
+  PoseAdamArgs a;
+  a.poses = poses;
+  a.pose_grad = pose_grad;
+  a.m = exp_avg;
+  a.v = exp_avg_sq;
+  a.n = n;
+  a.first = first;
+  const double bc1 = 1.0 - pow(beta1, (double)(step < 1 ? 1 : step));
+  a.step_q = (float)(lr_q / bc1);
+  a.step_t = (float)(lr_t / bc1);
+  a.beta1 = (float)beta1;
+  a.beta2 = (float)beta2;
+  a.one_m_beta1 = (float)(1.0 - beta1);
+  a.one_m_beta2 = (float)(1.0 - beta2);
+  a.bc2_sqrt = (float)sqrt(1.0 - pow(beta2, (double)(step < 1 ? 1 : step)));
+  a.eps = (float)eps;
+  a.grad7 = grad7;
+  a.apply = apply;
+  const int cnt = n - first;
+  k_pose_adam<<<(cnt + 31) / 32, 32, 0, S_(s)>>>(a);
+  CHECK_LAUNCH("eslam_pose_adam_step");
+  return 0;
+}
+
+int eslam_finalize_loss(const eslam_render_cfg_t* cfg, const int32_t* counters, int tracker_rule, double* loss_acc,
+                        float* loss_out, eslam_stream_t s) {
+  // `counters` are the normalisers: pass the all-reduced ones (and all-reduced loss_acc) on several GPUs
+  REQUIRE(cfg && counters && loss_acc, "eslam_finalize_loss");
+  const CfgK k = make_cfg(cfg);
+  FinalizeArgs a;
+  a.counters = counters;
+  a.loss_acc = loss_acc;
+  a.loss_out = loss_out;
+  a.tracker_rule = tracker_rule;
+  a.w_fs = k.w_fs;
+  a.w_center = k.w_center;
+  a.w_tail = k.w_tail;
+  a.w_depth = k.w_depth;
+  a.w_color = k.w_color;
+  k_finalize_loss<<<1, 32, 0, S_(s)>>>(a);
+  CHECK_LAUNCH("eslam_finalize_loss");
+  return 0;
+}
+
+}  // extern "C"

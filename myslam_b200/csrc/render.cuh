@@ -1,0 +1,661 @@
+// Render family: point decode, ray forward (compositing) and the fused loss + backward.
+// Reference semantics: src/networks/decoders.py:64-146, src/utils/Renderer.py:136-153,
+// src/Tracker.py:114-148,192-208, src/Mapper.py:110-144,337-349.
+#pragma once
+#include "field.cuh"
+
+namespace eslam {
+
+// ---------------------------------------------------------------------------------------------------
+// shared-memory tiles
+// ---------------------------------------------------------------------------------------------------
+struct SmemFwd {
+  float4 F[NP * 16];   // feature tile of the decoder being evaluated
+  int ax_i[6][NP];     // axis set-ups of that decoder's two resolution groups: [scale*3+axis]
+  float ax_f[6][NP];
+  float one[NP], w[NP], z[NP], c[3][NP];
+};
+
+template <bool GF>
+struct SmemBwd {
+  float4 F0[NP * 16];  // sdf features, later d loss / d sdf features
+  float4 F1[NP * 16];  // rgb
+  int ax_i[12][NP];
+  float ax_f[12][NP];
+  float act0[GF ? NP * 20 : 4];  // activation / gradient staging for the weight-gradient products
+  float act1[GF ? NP * 20 : 4];
+  float one[NP], w[NP], z[NP], c[3][NP], gww[NP];
+  float gp[3][NP];     // d loss / d normalised coordinate
+  float rayv[4][16];   // per ray: rendered depth, r, g, b
+  float rayg[4][16];   // per ray: upstream g_depth, g_rgb
+  float rayd[16];      // per ray gt depth
+  int raym[16];        // per ray loss-mask flag
+  float rayod[6][16];  // per ray d loss / d (o, d)
+  float red[NWARP];
+  double redd[NWARP * 5];
+};
+
+// ---------------------------------------------------------------------------------------------------
+// common phases
+// ---------------------------------------------------------------------------------------------------
+
+// point layout: axis set-ups of resolution groups [g0, g0+NG) into ax rows [0, 3*NG)
+template <int NG>
+__device__ __forceinline__ void write_axis_setups(const FieldK& fk, int g0, const float (&pn)[3], int (*ax_i)[NP],
+                                                  float (*ax_f)[NP], int q) {
+#pragma unroll
+  for (int g = 0; g < NG; ++g) {
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+      int i0;
+      float fr;
+      axis_setup(pn[a], axis_size(fk, g0 + g, a), i0, fr);
+      ax_i[g * 3 + a][q] = i0;
+      ax_f[g * 3 + a][q] = fr;
+    }
+  }
+}
+
+// gather layout: fill the feature tile of decoder `field` for all NP slots of this CTA
+template <int AXBASE>
+__device__ __forceinline__ void gather_tile(const FieldK& fk, int field, const float4* __restrict__ arena4,
+                                            const int (*ax_i)[NP], const float (*ax_f)[NP], float4* F, int n_valid) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int grp = lane >> 3, sub = lane & 7;
+#pragma unroll 1
+  for (int it = 0; it < 8; ++it) {
+    const int qq = warp * 32 + it * 4 + grp;
+    float4 fc = f4_zero(), ff = f4_zero();
+    if (qq < n_valid) gather_features<AXBASE>(fk, field, arena4, ax_i, ax_f, qq, sub, fc, ff);
+    F[f_slot(qq, sub)] = fc;
+    F[f_slot(qq, 8 + sub)] = ff;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// decode points / grid sdf  (Decoders.forward; Mesher.eval_points)
+// ---------------------------------------------------------------------------------------------------
+struct DecodeArgs {
+  FieldK fk;
+  const float4* arena4;
+  const float* pts;  // [n][3] or NULL in grid mode
+  long long n;
+  float* raw;        // [n][4] (r,g,b,sdf) or NULL
+  float* sdf_out;    // [n] or NULL
+  int flags;         // bit0 sdf only, bit1 bound mask -> sdf=-1, bit2 pts are already normalised
+  const float *xs, *ys, *zs;
+  int nx, ny, nz;
+  long long start;
+};
+
+__global__ void __launch_bounds__(NP) k_decode(const __grid_constant__ DecodeArgs a) {
+  __shared__ SmemFwd sm;
+  const int q = threadIdx.x;
+  const long long base = (long long)blockIdx.x * NP;
+  const long long gi = base + q;
+  const int n_valid = (int)min((long long)NP, a.n - base);
+  const bool valid = q < n_valid;
+  float p[3] = {0.f, 0.f, 0.f}, pn[3];
+  if (valid) {
+    if (a.pts) {
+      p[0] = a.pts[gi * 3 + 0];
+      p[1] = a.pts[gi * 3 + 1];
+      p[2] = a.pts[gi * 3 + 2];
+    } else {
+      const long long f = a.start + gi;
+      const int iz = (int)(f % a.nz);
+      const long long t = f / a.nz;
+      const int ix = (int)(t % a.nx), iy = (int)(t / a.nx);
+      p[0] = a.xs[ix];
+      p[1] = a.ys[iy];
+      p[2] = a.zs[iz];
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < 3; ++k) pn[k] = (a.flags & 4) ? p[k] : normalize_axis(p[k], a.fk.lo[k], a.fk.hi[k]);
+  bool inside = true;
+  if (a.flags & 2) {
+#pragma unroll
+    for (int k = 0; k < 3; ++k) inside = inside && (p[k] < a.fk.hi[k]) && (p[k] > a.fk.lo[k]);
+  }
+  // sdf decoder
+  write_axis_setups<2>(a.fk, 0, pn, sm.ax_i, sm.ax_f, q);
+  __syncthreads();
+  gather_tile<0>(a.fk, 0, a.arena4, sm.ax_i, sm.ax_f, sm.F, n_valid);
+  __syncthreads();
+  float h1[16], h2[16], os[1];
+  mlp_forward<S_W1, S_B1, S_W2, S_B2, S_W3, S_B3, 1>(sm.F, q, h1, h2, os);
+  float sdf = tanhf(os[0]);
+  if (!inside) sdf = -1.0f;
+  if (valid) {
+    if (a.sdf_out) a.sdf_out[gi] = sdf;
+    if (a.raw) a.raw[gi * 4 + 3] = sdf;
+  }
+  if (a.flags & 1) return;
+  __syncthreads();
+  write_axis_setups<2>(a.fk, 2, pn, sm.ax_i, sm.ax_f, q);
+  __syncthreads();
+  gather_tile<0>(a.fk, 1, a.arena4, sm.ax_i, sm.ax_f, sm.F, n_valid);
+  __syncthreads();
+  float oc[3];
+  mlp_forward<C_W1, C_B1, C_W2, C_B2, C_W3, C_B3, 3>(sm.F, q, h1, h2, oc);
+  if (valid && a.raw) {
+    a.raw[gi * 4 + 0] = sigmoidf_(oc[0]);
+    a.raw[gi * 4 + 1] = sigmoidf_(oc[1]);
+    a.raw[gi * 4 + 2] = sigmoidf_(oc[2]);
+  }
+}
+
+// Decoders.sample_plane_feature: feat[n][64] from normalised coordinates
+struct FeatArgs {
+  FieldK fk;
+  const float4* arena4;
+  const float* p_nor;
+  long long n;
+  int which;
+  float4* feat4;
+};
+
+__global__ void __launch_bounds__(NP) k_plane_feature(const __grid_constant__ FeatArgs a) {
+  __shared__ int ax_i[6][NP];
+  __shared__ float ax_f[6][NP];
+  const int q = threadIdx.x;
+  const long long base = (long long)blockIdx.x * NP;
+  const int n_valid = (int)min((long long)NP, a.n - base);
+  float pn[3] = {0.f, 0.f, 0.f};
+  if (q < n_valid) {
+    pn[0] = a.p_nor[(base + q) * 3 + 0];
+    pn[1] = a.p_nor[(base + q) * 3 + 1];
+    pn[2] = a.p_nor[(base + q) * 3 + 2];
+  }
+  write_axis_setups<2>(a.fk, a.which * 2, pn, ax_i, ax_f, q);
+  __syncthreads();
+  const int warp = q >> 5, lane = q & 31, grp = lane >> 3, sub = lane & 7;
+  for (int it = 0; it < 8; ++it) {
+    const int qq = warp * 32 + it * 4 + grp;
+    if (qq < n_valid) {
+      float4 fc, ff;
+      gather_features<0>(a.fk, a.which, a.arena4, ax_i, ax_f, qq, sub, fc, ff);
+      a.feat4[(base + qq) * 16 + sub] = fc;
+      a.feat4[(base + qq) * 16 + 8 + sub] = ff;
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// ray forward  (Renderer.py:136-147)
+// ---------------------------------------------------------------------------------------------------
+struct RenderFwdArgs {
+  FieldK fk;
+  const float4* arena4;
+  const float *rays_o, *rays_d, *z;
+  int n_rays, S;
+  const int* counters;
+  float *depth, *rgb, *sdf;
+};
+
+__device__ __forceinline__ void sdf_to_alpha(float sdf, float beta, float& u, float& e, float& alpha) {
+  u = sigmoidf_(-sdf * beta);  // Renderer.py:149-153
+  e = expf(-beta * u);
+  alpha = 1.0f - e;
+}
+
+__global__ void __launch_bounds__(NP) k_render_fwd(const __grid_constant__ RenderFwdArgs a) {
+  __shared__ SmemFwd sm;
+  const int R = a.counters ? min(a.counters[0], a.n_rays) : a.n_rays;
+  const int S = a.S;
+  const int RPB = NP / S;
+  const int ray0 = blockIdx.x * RPB;
+  if (ray0 >= R) return;
+  const int rays_here = min(RPB, R - ray0);
+  const int n_valid = rays_here * S;
+  const int q = threadIdx.x;
+  const bool valid = q < n_valid;
+  const int rl = valid ? q / S : 0;
+  const int k = q - rl * S;
+  const int ray = ray0 + rl;
+  float pn[3] = {0.f, 0.f, 0.f}, zk = 0.f;
+  if (valid) {
+    zk = a.z[(long long)ray * S + k];
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      const float p = __fadd_rn(a.rays_o[ray * 3 + c], __fmul_rn(a.rays_d[ray * 3 + c], zk));
+      pn[c] = normalize_axis(p, a.fk.lo[c], a.fk.hi[c]);
+    }
+  }
+  write_axis_setups<2>(a.fk, 0, pn, sm.ax_i, sm.ax_f, q);
+  __syncthreads();
+  gather_tile<0>(a.fk, 0, a.arena4, sm.ax_i, sm.ax_f, sm.F, n_valid);
+  __syncthreads();
+  float h1[16], h2[16], os[1], oc[3];
+  mlp_forward<S_W1, S_B1, S_W2, S_B2, S_W3, S_B3, 1>(sm.F, q, h1, h2, os);
+  const float sdf = tanhf(os[0]);
+  __syncthreads();
+  write_axis_setups<2>(a.fk, 2, pn, sm.ax_i, sm.ax_f, q);
+  __syncthreads();
+  gather_tile<0>(a.fk, 1, a.arena4, sm.ax_i, sm.ax_f, sm.F, n_valid);
+  __syncthreads();
+  mlp_forward<C_W1, C_B1, C_W2, C_B2, C_W3, C_B3, 3>(sm.F, q, h1, h2, oc);
+  const float beta = c_dec[P_BETA];
+  float u, e, alpha;
+  sdf_to_alpha(sdf, beta, u, e, alpha);
+  sm.one[q] = __fadd_rn(__fsub_rn(1.0f, alpha), 1e-10f);
+  sm.z[q] = zk;
+#pragma unroll
+  for (int c = 0; c < 3; ++c) sm.c[c][q] = sigmoidf_(oc[c]);
+  __syncthreads();
+  float T = 1.0f;
+  for (int j = 0; j < k; ++j) T *= sm.one[rl * S + j];
+  sm.w[q] = valid ? alpha * T : 0.f;
+  if (valid && a.sdf) a.sdf[(long long)ray * S + k] = sdf;
+  __syncthreads();
+  if (valid && k < 4) {
+    const float* v = (k == 0) ? sm.z : sm.c[k - 1];
+    float acc = 0.f;
+    for (int j = 0; j < S; ++j) acc = fmaf(sm.w[rl * S + j], v[rl * S + j], acc);
+    if (k == 0)
+      a.depth[ray] = acc;
+    else
+      a.rgb[ray * 3 + (k - 1)] = acc;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// fused loss + backward
+// ---------------------------------------------------------------------------------------------------
+struct BwdArgs {
+  FieldK fk;
+  const float4* arena4;
+  const float *rays_o, *rays_d, *z;
+  int n_rays, S;
+  const int* counters;
+  const int* norm;  // loss normalisers (counters layout); == counters on one GPU, all-reduced sums on several
+  // upstream-gradient mode
+  const float *g_depth, *g_rgb, *g_sdf;
+  // fused-loss mode
+  const float* gt_depth;
+  const double* gt_color;
+  const int* src;
+  const long long* pix_idx;
+  int n_per_img;
+  const unsigned char* ray_mask;
+  float tr, tr04, w_fs, w_center, w_tail, w_depth;
+  double w_color;
+  float fx, fy, cx, cy;
+  int W0, H0, Wc;
+  double* loss_acc;
+  // outputs
+  float* grad_arena;
+  float *g_rays_o, *g_rays_d;
+  float* pose_grad;
+};
+
+// weight gradients of one decoder, accumulated into the gradient arena.  Point layout in, products over the
+// NP points of the tile with thread-owned outputs.
+template <int W1, int B1, int W2, int B2, int W3, int B3, int NOUT>
+__device__ __forceinline__ void weight_grads(float* act0, float* act1, const float4* F, float* gdec,
+                                             const float (&h1)[16], const float (&h2)[16], const float (&ga1)[16],
+                                             const float (&ga2)[16], const float (&gout)[NOUT]) {
+  const int t = threadIdx.x;
+  float4* a0 = reinterpret_cast<float4*>(act0 + t * 20);
+  float4* a1 = reinterpret_cast<float4*>(act1 + t * 20);
+  // --- output layer: dW3[o][i] = sum_q gout[o] h2[i]
+#pragma unroll
+  for (int v = 0; v < 4; ++v) a0[v] = make_float4(h2[v * 4], h2[v * 4 + 1], h2[v * 4 + 2], h2[v * 4 + 3]);
+  a1[0] = make_float4(gout[0], NOUT > 1 ? gout[NOUT > 1 ? 1 : 0] : 0.f, NOUT > 2 ? gout[NOUT > 2 ? 2 : 0] : 0.f, 0.f);
+  __syncthreads();
+  if (t < NOUT * 16 + NOUT) {
+    const bool bias = t >= NOUT * 16;
+    const int o = bias ? t - NOUT * 16 : t >> 4, i = t & 15;
+    float acc = 0.f;
+    for (int qq = 0; qq < NP; ++qq) acc = fmaf(act1[qq * 20 + o], bias ? 1.0f : act0[qq * 20 + i], acc);
+    atomicAdd(gdec + (bias ? B3 + o : W3 + o * 16 + i), acc);
+  }
+  __syncthreads();
+  // --- hidden layer: dW2[j][i] = sum_q ga2[j] h1[i]
+#pragma unroll
+  for (int v = 0; v < 4; ++v) {
+    a0[v] = make_float4(h1[v * 4], h1[v * 4 + 1], h1[v * 4 + 2], h1[v * 4 + 3]);
+    a1[v] = make_float4(ga2[v * 4], ga2[v * 4 + 1], ga2[v * 4 + 2], ga2[v * 4 + 3]);
+  }
+  __syncthreads();
+  {
+    const int i = t & 15, j0 = (t >> 4) * 2;
+    float acc0 = 0.f, acc1 = 0.f, accb = 0.f;
+    for (int qq = 0; qq < NP; ++qq) {
+      const float h = act0[qq * 20 + i];
+      acc0 = fmaf(act1[qq * 20 + j0], h, acc0);
+      acc1 = fmaf(act1[qq * 20 + j0 + 1], h, acc1);
+    }
+    atomicAdd(gdec + W2 + j0 * 16 + i, acc0);
+    atomicAdd(gdec + W2 + (j0 + 1) * 16 + i, acc1);
+    if (t < 16) {
+      for (int qq = 0; qq < NP; ++qq) accb += act1[qq * 20 + t];
+      atomicAdd(gdec + B2 + t, accb);
+    }
+  }
+  __syncthreads();
+  // --- input layer: dW1[j][c] = sum_q ga1[j] F[q][c]
+#pragma unroll
+  for (int v = 0; v < 4; ++v) a1[v] = make_float4(ga1[v * 4], ga1[v * 4 + 1], ga1[v * 4 + 2], ga1[v * 4 + 3]);
+  __syncthreads();
+  {
+    const int c = t & 63, j0 = (t >> 6) * 8;
+    float acc[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+    for (int qq = 0; qq < NP; ++qq) {
+      const float f = f_scalar(F, qq, c);
+      const float4 g0 = *reinterpret_cast<const float4*>(act1 + qq * 20 + j0);
+      const float4 g1 = *reinterpret_cast<const float4*>(act1 + qq * 20 + j0 + 4);
+      acc[0] = fmaf(g0.x, f, acc[0]);
+      acc[1] = fmaf(g0.y, f, acc[1]);
+      acc[2] = fmaf(g0.z, f, acc[2]);
+      acc[3] = fmaf(g0.w, f, acc[3]);
+      acc[4] = fmaf(g1.x, f, acc[4]);
+      acc[5] = fmaf(g1.y, f, acc[5]);
+      acc[6] = fmaf(g1.z, f, acc[6]);
+      acc[7] = fmaf(g1.w, f, acc[7]);
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) atomicAdd(gdec + W1 + (j0 + j) * 64 + c, acc[j]);
+    if (t < 16) {
+      float accb = 0.f;
+      for (int qq = 0; qq < NP; ++qq) accb += act1[qq * 20 + t];
+      atomicAdd(gdec + B1 + t, accb);
+    }
+  }
+  __syncthreads();
+}
+
+// gather layout: scatter d loss/d features of one decoder into the plane gradients and/or accumulate the
+// gradient with respect to the normalised coordinates.
+template <bool GF, bool GR, int AXBASE>
+__device__ __forceinline__ void scatter_point(const FieldK& fk, int field, const float4* __restrict__ arena4,
+                                              float4* __restrict__ garena4, const int (*ax_i)[NP],
+                                              const float (*ax_f)[NP], int q, int sub, float4 gC, float4 gF,
+                                              float (&gpn)[3]) {
+#pragma unroll
+  for (int s = 0; s < 2; ++s) {
+    const float4 g4 = s ? gF : gC;
+#pragma unroll
+    for (int p = 0; p < 3; ++p) {
+      const int au = AXBASE + s * 3 + pair_u(p), av = AXBASE + s * 3 + pair_v(p);
+      const PlaneK& pl = fk.pl[field * 6 + s * 3 + p];
+      const int u0 = ax_i[au][q], v0 = ax_i[av][q];
+      const Tap t = make_tap(pl, u0, ax_f[au][q], v0, ax_f[av][q], sub);
+      const float fu = t.fu, fv = t.fv;
+      if (GR) {
+        const float4 v00 = ldg4(arena4 + t.base), v01 = ldg4(arena4 + t.base + t.dx);
+        const float4 v10 = ldg4(arena4 + t.base + t.dy), v11 = ldg4(arena4 + t.base + t.dy + t.dx);
+        const float du = f4_dot(g4, f4_sub(v01, v00)) * (1.f - fv) + f4_dot(g4, f4_sub(v11, v10)) * fv;
+        const float dv = f4_dot(g4, f4_sub(v10, v00)) * (1.f - fu) + f4_dot(g4, f4_sub(v11, v01)) * fu;
+        gpn[pair_u(p)] = fmaf(du, axis_grad_mult(u0, fu, pl.W), gpn[pair_u(p)]);
+        gpn[pair_v(p)] = fmaf(dv, axis_grad_mult(v0, fv, pl.H), gpn[pair_v(p)]);
+      }
+      if (GF) {
+        red_add_v4(garena4 + t.base, f4_mul((1.f - fu) * (1.f - fv), g4));
+        red_add_v4(garena4 + t.base + t.dx, f4_mul(fu * (1.f - fv), g4));
+        red_add_v4(garena4 + t.base + t.dy, f4_mul((1.f - fu) * fv, g4));
+        red_add_v4(garena4 + t.base + t.dy + t.dx, f4_mul(fu * fv, g4));
+      }
+    }
+  }
+}
+
+// MODE 0: upstream gradients of (depth, rgb, sdf) per ray are read (autograd through render_batch_ray).
+// MODE 1 (FUSED): the five losses are evaluated in-kernel from gt data and device counters.
+// MODE 2 (POINTS): S == 1, "rays" are plain points (rays_o = points, rays_d unused) and the upstream gradient
+//         is g_raw[N][4] in g_sdf (autograd through Decoders.forward); g_rays_o receives d loss / d points.
+// GF: gradients for planes + decoders (+beta) into grad_arena.  GR: gradients for rays / points / poses.
+template <int MODE, bool GF, bool GR>
+__global__ void __launch_bounds__(NP, 2) k_render_bwd(const __grid_constant__ BwdArgs a) {
+  constexpr bool FUSED = MODE == 1;
+  constexpr bool POINTS = MODE == 2;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  SmemBwd<GF>& sm = *reinterpret_cast<SmemBwd<GF>*>(smem_raw);
+  const int R = a.counters ? min(a.counters[0], a.n_rays) : a.n_rays;
+  const int S = a.S;
+  const int RPB = POINTS ? NP : min(NP / S, 16);
+  const int ray0 = blockIdx.x * RPB;
+  if (ray0 >= R) return;
+  const int rays_here = min(RPB, R - ray0);
+  const int n_valid = rays_here * S;
+  const int q = threadIdx.x;
+  const int warp = q >> 5, lane = q & 31;
+  const bool valid = q < n_valid;
+  const int rl = valid ? q / S : 0;
+  const int k = q - rl * S;
+  const int ray = ray0 + rl;
+
+  // ---- P0/P1: points, normalised coordinates, axis set-ups
+  float pn[3] = {0.f, 0.f, 0.f}, zk = 0.f;
+  if (valid) {
+    zk = POINTS ? 0.f : a.z[(long long)ray * S + k];
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      const float p = POINTS ? a.rays_o[(long long)ray * 3 + c]
+                             : __fadd_rn(a.rays_o[ray * 3 + c], __fmul_rn(a.rays_d[ray * 3 + c], zk));
+      pn[c] = normalize_axis(p, a.fk.lo[c], a.fk.hi[c]);
+    }
+  }
+  write_axis_setups<4>(a.fk, 0, pn, sm.ax_i, sm.ax_f, q);
+#pragma unroll
+  for (int c = 0; c < 3; ++c) sm.gp[c][q] = 0.f;
+  __syncthreads();
+  // ---- P2: gather both decoders' features
+  gather_tile<0>(a.fk, 0, a.arena4, sm.ax_i, sm.ax_f, sm.F0, n_valid);
+  gather_tile<6>(a.fk, 1, a.arena4, sm.ax_i, sm.ax_f, sm.F1, n_valid);
+  __syncthreads();
+  // ---- P3: MLP forward
+  float h1s[16], h2s[16], os[1], h1c[16], h2c[16], oc[3];
+  mlp_forward<S_W1, S_B1, S_W2, S_B2, S_W3, S_B3, 1>(sm.F0, q, h1s, h2s, os);
+  mlp_forward<C_W1, C_B1, C_W2, C_B2, C_W3, C_B3, 3>(sm.F1, q, h1c, h2c, oc);
+  const float sdf = tanhf(os[0]);
+  float rgb[3];
+#pragma unroll
+  for (int c = 0; c < 3; ++c) rgb[c] = sigmoidf_(oc[c]);
+  // ---- P4: compositing
+  const float beta = c_dec[P_BETA];
+  float u, e, alpha;
+  sdf_to_alpha(sdf, beta, u, e, alpha);
+  const float one = __fadd_rn(__fsub_rn(1.0f, alpha), 1e-10f);
+  sm.one[q] = one;
+  sm.z[q] = zk;
+#pragma unroll
+  for (int c = 0; c < 3; ++c) sm.c[c][q] = rgb[c];
+  __syncthreads();
+  float T = 1.0f;
+  for (int j = 0; j < k; ++j) T *= sm.one[rl * S + j];
+  const float w = valid ? alpha * T : 0.f;
+  sm.w[q] = w;
+  __syncthreads();
+  if (!POINTS && valid && k < 4) {
+    const float* v = (k == 0) ? sm.z : sm.c[k - 1];
+    float acc = 0.f;
+    for (int j = 0; j < S; ++j) acc = fmaf(sm.w[rl * S + j], v[rl * S + j], acc);
+    sm.rayv[k][rl] = acc;
+  }
+  __syncthreads();
+  // ---- P5: upstream gradients of depth / rgb per ray, and the loss sums
+  double ls[5] = {0.0, 0.0, 0.0, 0.0, 0.0};  // fs, center, tail, depth, colour
+  float inv_f = 0.f, inv_c = 0.f, inv_t = 0.f;
+  if (FUSED) {
+    const int n_mask = a.norm[2];
+    inv_f = a.w_fs / (float)a.norm[3];
+    inv_c = a.w_center / (float)a.norm[4];
+    inv_t = a.w_tail / (float)a.norm[5];
+    if (valid && k == 0) {
+      const float d = a.gt_depth[ray];
+      const int m = a.ray_mask ? (int)a.ray_mask[ray] : (d > 0.f ? 1 : 0);
+      const float dr = sm.rayv[0][rl];
+      float gd = 0.f;
+      if (m) {
+        const float diff = d - dr;
+        gd = -2.0f * diff * (a.w_depth / (float)n_mask);
+        ls[3] = (double)(diff * diff);
+      }
+      sm.rayg[0][rl] = gd;
+      const bool col = a.ray_mask ? (m != 0) : true;
+      const double ncol = 3.0 * (double)(a.ray_mask ? n_mask : a.norm[0]);
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        float g = 0.f;
+        if (col) {
+          const double diff = a.gt_color[(long long)ray * 3 + c] - (double)sm.rayv[1 + c][rl];
+          g = (float)(-2.0 * diff * (a.w_color / ncol));
+          ls[4] += diff * diff;
+        }
+        sm.rayg[1 + c][rl] = g;
+      }
+      sm.rayd[rl] = d;
+      sm.raym[rl] = m;
+    }
+  } else if (!POINTS) {
+    if (valid && k < 4) sm.rayg[k][rl] = (k == 0) ? a.g_depth[ray] : a.g_rgb[ray * 3 + (k - 1)];
+  }
+  __syncthreads();
+  // ---- direct sdf gradient + compositing backward (point layout)
+  float g_sdf = 0.f, g_beta = 0.f, gout_s[1] = {0.f}, gout_c[3] = {0.f, 0.f, 0.f};
+  if (POINTS) {
+    if (valid) {
+      const float* gr = a.g_sdf + (long long)ray * 4;
+      gout_s[0] = gr[3] * (1.0f - sdf * sdf);
+#pragma unroll
+      for (int c = 0; c < 3; ++c) gout_c[c] = gr[c] * rgb[c] * (1.0f - rgb[c]);
+    }
+  } else {
+    float gdir = 0.f;
+    if (valid) {
+      if (FUSED) {
+        if (sm.raym[rl]) {
+          const float d = sm.rayd[rl];
+          const int band = sdf_band(zk, d, a.tr, a.tr04);
+          if (band == 0) {
+            const float r = sdf - 1.0f;
+            gdir = 2.0f * r * inv_f;
+            ls[0] = (double)(r * r);
+          } else if (band < 3) {
+            const float r = __fadd_rn(zk, __fmul_rn(sdf, a.tr)) - d;
+            gdir = 2.0f * r * a.tr * (band == 1 ? inv_c : inv_t);
+            ls[band] = (double)(r * r);
+          }
+        }
+      } else {
+        gdir = a.g_sdf ? a.g_sdf[(long long)ray * S + k] : 0.f;
+      }
+    }
+    const float gw = sm.rayg[0][rl] * zk + sm.rayg[1][rl] * rgb[0] + sm.rayg[2][rl] * rgb[1] + sm.rayg[3][rl] * rgb[2];
+    sm.gww[q] = valid ? gw * w : 0.f;
+    __syncthreads();
+    float B = 0.f;
+    if (valid)
+      for (int j = k + 1; j < S; ++j) B += sm.gww[rl * S + j];
+    const float g_alpha = valid ? (gw * T - B / one) : 0.f;
+    const float du = u * (1.0f - u);
+    g_sdf = gdir + g_alpha * (-beta * beta * e * du);
+    g_beta = g_alpha * e * (u - beta * sdf * du);
+    gout_s[0] = valid ? g_sdf * (1.0f - sdf * sdf) : 0.f;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) gout_c[c] = valid ? sm.rayg[1 + c][rl] * w * rgb[c] * (1.0f - rgb[c]) : 0.f;
+  }
+  // ---- P6: MLP backward
+  float ga1s[16], ga2s[16], ga1c[16], ga2c[16];
+  mlp_backward_hidden<S_W2, S_W3, 1>(gout_s, h1s, h2s, ga1s, ga2s);
+  mlp_backward_hidden<C_W2, C_W3, 3>(gout_c, h1c, h2c, ga1c, ga2c);
+  if (GF) {
+    float* gdec = a.grad_arena + a.fk.dec_off;
+    weight_grads<S_W1, S_B1, S_W2, S_B2, S_W3, S_B3, 1>(sm.act0, sm.act1, sm.F0, gdec, h1s, h2s, ga1s, ga2s, gout_s);
+    weight_grads<C_W1, C_B1, C_W2, C_B2, C_W3, C_B3, 3>(sm.act0, sm.act1, sm.F1, gdec, h1c, h2c, ga1c, ga2c, gout_c);
+    const float gb = warp_sum(g_beta);
+    if (lane == 0) sm.red[warp] = gb;
+  }
+  mlp_backward_input<S_W1>(ga1s, sm.F0, q);
+  mlp_backward_input<C_W1>(ga1c, sm.F1, q);
+  __syncthreads();
+  if (GF && q == 0) {
+    float gb = 0.f;
+    for (int i = 0; i < NWARP; ++i) gb += sm.red[i];
+    atomicAdd(a.grad_arena + a.fk.dec_off + P_BETA, gb);
+  }
+  // ---- P7: scatter to the planes / coordinate gradients (gather layout)
+  {
+    const int grp = lane >> 3, sub = lane & 7;
+    float4* garena4 = reinterpret_cast<float4*>(a.grad_arena);
+#pragma unroll 1
+    for (int it = 0; it < 8; ++it) {
+      const int qq = warp * 32 + it * 4 + grp;
+      float gpn[3] = {0.f, 0.f, 0.f};
+      if (qq < n_valid) {
+        scatter_point<GF, GR, 0>(a.fk, 0, a.arena4, garena4, sm.ax_i, sm.ax_f, qq, sub, sm.F0[f_slot(qq, sub)],
+                                 sm.F0[f_slot(qq, 8 + sub)], gpn);
+        scatter_point<GF, GR, 6>(a.fk, 1, a.arena4, garena4, sm.ax_i, sm.ax_f, qq, sub, sm.F1[f_slot(qq, sub)],
+                                 sm.F1[f_slot(qq, 8 + sub)], gpn);
+      }
+      if (GR) {
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+          float v = gpn[c];
+          v += __shfl_xor_sync(0xffffffffu, v, 1);
+          v += __shfl_xor_sync(0xffffffffu, v, 2);
+          v += __shfl_xor_sync(0xffffffffu, v, 4);
+          if (sub == 0) sm.gp[c][qq] = v;
+        }
+      }
+    }
+  }
+  // ---- P8: ray / pose gradients
+  if (GR) {
+    __syncthreads();
+    for (int t = q; t < rays_here * 6; t += NP) {
+      const int r2 = t / 6, comp = t - r2 * 6, ax = comp % 3;
+      const bool is_d = comp >= 3;
+      const float scale = 2.0f / (a.fk.hi[ax] - a.fk.lo[ax]);
+      float acc = 0.f;
+      for (int j = 0; j < S; ++j) {
+        const float g = sm.gp[ax][r2 * S + j] * scale;
+        acc += is_d ? g * sm.z[r2 * S + j] : g;
+      }
+      if (FUSED) {
+        sm.rayod[comp][r2] = acc;
+      } else if (!POINTS || !is_d) {
+        (is_d ? a.g_rays_d : a.g_rays_o)[(long long)(ray0 + r2) * 3 + ax] = acc;
+      }
+    }
+    if (FUSED && a.pose_grad) {
+      __syncthreads();
+      for (int t = q; t < rays_here * 12; t += NP) {
+        const int r2 = t / 12, el = t - r2 * 12, row = el >> 2, col = el & 3;
+        const int slot = a.src[ray0 + r2];
+        const int frame = slot / a.n_per_img;
+        float val;
+        if (col == 3) {
+          val = sm.rayod[row][r2];  // d loss / d t
+        } else {
+          const long long pix = a.pix_idx[slot];
+          const float pi = (float)(a.W0 + (int)(pix % a.Wc)), pj = (float)(a.H0 + (int)(pix / a.Wc));
+          const float dir = col == 0 ? __fdiv_rn(__fsub_rn(pi, a.cx), a.fx)
+                                     : (col == 1 ? -__fdiv_rn(__fsub_rn(pj, a.cy), a.fy) : -1.0f);
+          val = sm.rayod[3 + row][r2] * dir;  // d loss / d R[row][col]
+        }
+        atomicAdd(a.pose_grad + frame * 12 + el, val);
+      }
+    }
+  }
+  // ---- loss sums
+  if (FUSED && a.loss_acc) {
+#pragma unroll
+    for (int i = 0; i < 5; ++i) {
+      const double v = warp_sum_d(ls[i]);
+      if (lane == 0) sm.redd[warp * 5 + i] = v;
+    }
+    __syncthreads();
+    if (q < 5) {
+      double v = 0.0;
+      for (int i = 0; i < NWARP; ++i) v += sm.redd[i * 5 + q];
+      atomicAdd(a.loss_acc + q, v);
+    }
+  }
+}
+
+}  // namespace eslam

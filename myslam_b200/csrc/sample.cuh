@@ -1,0 +1,551 @@
+// Pixel pick -> rays -> bbox filter -> ordered compaction -> depth-guided samples, the importance
+// resampling of depth-less rays, and the tracker's median outlier mask.
+// Reference: src/common.py:41-153, src/Tracker.py:175-195, src/Mapper.py:322-332, src/utils/Renderer.py:46-134.
+// All arithmetic that decides which rays/samples exist uses explicit round-to-nearest intrinsics in the
+// reference's operation order (no FMA contraction), so ray selection and z_vals are bit-exact.
+#pragma once
+#include "field.cuh"
+#include "render.cuh"
+
+namespace eslam {
+
+constexpr int SB = 256;  // threads per block of the sampling kernels
+
+struct SampleArgs {
+  FieldK fk;
+  int H, W, H0, W0, Wc, HWc;
+  float fx, fy, cx, cy;
+  int n_strat, n_imp;
+  float tr, tr15, tr3, tr04;
+  const long long* pix_idx;
+  int n_img, n_per_img;
+  const float* c2w;
+  const float* poses;
+  int pose_first;
+  const float* depth;
+  const double* color;
+  const float* u_depth;
+  const float *t_uni, *t_surf;
+  int need_depth;
+  float *rays_o, *rays_d, *gt_depth;
+  double* gt_color;
+  int* src;
+  float* z;
+  int* dl_list;
+  unsigned char* band;
+  int* counters;
+  float* c2w_out;
+};
+
+// torch.max / torch.min propagate NaN
+__device__ __forceinline__ float max_nan(float a, float b) { return (a != a || b != b) ? __int_as_float(0x7fffffff) : fmaxf(a, b); }
+__device__ __forceinline__ float min_nan(float a, float b) { return (a != a || b != b) ? __int_as_float(0x7fffffff) : fminf(a, b); }
+
+// quaternion_to_matrix (pytorch3d 0.7.1) in the order torch evaluates it; row-major R[9]
+__device__ __forceinline__ void quat_to_rot(const float* q, float* R) {
+  const float r = q[0], i = q[1], j = q[2], k = q[3];
+  const float n = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(r, r), __fmul_rn(i, i)), __fmul_rn(j, j)), __fmul_rn(k, k));
+  const float s = __fdiv_rn(2.0f, n);
+#define MUL __fmul_rn
+#define ADD __fadd_rn
+#define SUB __fsub_rn
+  R[0] = SUB(1.0f, MUL(s, ADD(MUL(j, j), MUL(k, k))));
+  R[1] = MUL(s, SUB(MUL(i, j), MUL(k, r)));
+  R[2] = MUL(s, ADD(MUL(i, k), MUL(j, r)));
+  R[3] = MUL(s, ADD(MUL(i, j), MUL(k, r)));
+  R[4] = SUB(1.0f, MUL(s, ADD(MUL(i, i), MUL(k, k))));
+  R[5] = MUL(s, SUB(MUL(j, k), MUL(i, r)));
+  R[6] = MUL(s, SUB(MUL(i, k), MUL(j, r)));
+  R[7] = MUL(s, ADD(MUL(j, k), MUL(i, r)));
+  R[8] = SUB(1.0f, MUL(s, ADD(MUL(i, i), MUL(j, j))));
+#undef MUL
+#undef ADD
+#undef SUB
+}
+
+struct RayEval {
+  float o[3], d[3], depth;
+  bool keep;
+};
+
+// bbox exit distance: min over axes of max over {lo,hi} of (bound-o)/d  (Tracker.py:177-180)
+__device__ __forceinline__ float bbox_exit(const FieldK& fk, const float* o, const float* d) {
+  float t = 0.f;
+#pragma unroll
+  for (int a = 0; a < 3; ++a) {
+    const float tl = __fdiv_rn(__fsub_rn(fk.lo[a], o[a]), d[a]);
+    const float th = __fdiv_rn(__fsub_rn(fk.hi[a], o[a]), d[a]);
+    const float m = max_nan(tl, th);
+    t = (a == 0) ? m : min_nan(t, m);
+  }
+  return t;
+}
+
+__device__ __forceinline__ RayEval eval_ray(const SampleArgs& a, int slot) {
+  RayEval r;
+  const int frame = slot / a.n_per_img;
+  const long long pix = a.pix_idx[slot];
+  const int pr = (int)(pix / a.Wc), pc = (int)(pix - (long long)pr * a.Wc);
+  const float pi = (float)(a.W0 + pc), pj = (float)(a.H0 + pr);
+  r.depth = a.depth[((long long)frame * a.H + (a.H0 + pr)) * a.W + (a.W0 + pc)];
+  float Rm[9], t[3];
+  if (a.poses && frame >= a.pose_first) {
+    const float* p = a.poses + frame * 7;
+    quat_to_rot(p, Rm);
+    t[0] = p[4];
+    t[1] = p[5];
+    t[2] = p[6];
+  } else {
+    const float* m = a.c2w + frame * 16;
+#pragma unroll
+    for (int x = 0; x < 3; ++x) {
+      Rm[x * 3 + 0] = m[x * 4 + 0];
+      Rm[x * 3 + 1] = m[x * 4 + 1];
+      Rm[x * 3 + 2] = m[x * 4 + 2];
+      t[x] = m[x * 4 + 3];
+    }
+  }
+  const float d0 = __fdiv_rn(__fsub_rn(pi, a.cx), a.fx);
+  const float d1 = -__fdiv_rn(__fsub_rn(pj, a.cy), a.fy);
+  const float d2 = -1.0f;
+#pragma unroll
+  for (int x = 0; x < 3; ++x) {
+    r.d[x] = __fadd_rn(__fadd_rn(__fmul_rn(d0, Rm[x * 3 + 0]), __fmul_rn(d1, Rm[x * 3 + 1])), __fmul_rn(d2, Rm[x * 3 + 2]));
+    r.o[x] = t[x];
+  }
+  const float te = bbox_exit(a.fk, r.o, r.d);
+  r.keep = (te >= r.depth) && (!a.need_depth || r.depth > 0.f);
+  return r;
+}
+
+// block-wide exclusive scan of two small counts packed as (lo 16 bits | hi 16 bits); returns exclusive
+// prefix for this thread and the block total
+__device__ __forceinline__ void block_scan2(int f0, int f1, int& ex0, int& ex1, int& tot0, int& tot1, int* sh /*[2*SB/32+2]*/) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const unsigned b0 = __ballot_sync(0xffffffffu, f0), b1 = __ballot_sync(0xffffffffu, f1);
+  const unsigned lt = (1u << lane) - 1u;
+  if (lane == 0) {
+    sh[warp] = __popc(b0);
+    sh[SB / 32 + warp] = __popc(b1);
+  }
+  __syncthreads();
+  int base0 = 0, base1 = 0, t0 = 0, t1 = 0;
+  for (int w2 = 0; w2 < SB / 32; ++w2) {
+    const int c0 = sh[w2], c1 = sh[SB / 32 + w2];
+    if (w2 < warp) {
+      base0 += c0;
+      base1 += c1;
+    }
+    t0 += c0;
+    t1 += c1;
+  }
+  ex0 = base0 + __popc(b0 & lt);
+  ex1 = base1 + __popc(b1 & lt);
+  tot0 = t0;
+  tot1 = t1;
+  __syncthreads();
+}
+
+// depth-guided samples of one ray with depth>0: Renderer.py:94-106 + perturbation :46-61.
+// zout may be strided global memory; returns band counts.
+__device__ __forceinline__ void depth_guided_z(float d, int n_strat, int n_imp, const float* t_uni, const float* t_surf,
+                                               float tr15, float tr3, const float* u, float* zout, float tr, float tr04,
+                                               int& nf, int& nc, int& nt) {
+  float zs[ESLAM_MAX_SAMPLES];
+  const int S = n_strat + n_imp;
+  const float d12 = __fmul_rn(1.2f, d);
+  const float dsurf = __fsub_rn(d, tr15);
+  // merge of the two ascending lists == torch.sort of their concatenation (values only)
+  int ia = 0, ib = 0;
+  float va = __fmul_rn(d12, t_uni[0]);
+  float vb = __fadd_rn(dsurf, __fmul_rn(tr3, t_surf[0]));
+  for (int k = 0; k < S; ++k) {
+    const bool take_a = (ib >= n_imp) || (ia < n_strat && va <= vb);
+    if (take_a) {
+      zs[k] = va;
+      ++ia;
+      if (ia < n_strat) va = __fmul_rn(d12, t_uni[ia]);
+    } else {
+      zs[k] = vb;
+      ++ib;
+      if (ib < n_imp) vb = __fadd_rn(dsurf, __fmul_rn(tr3, t_surf[ib]));
+    }
+  }
+  nf = nc = nt = 0;
+  float lower = zs[0];
+  for (int k = 0; k < S; ++k) {
+    const float upper = (k < S - 1) ? __fmul_rn(0.5f, __fadd_rn(zs[k + 1], zs[k])) : zs[S - 1];
+    const float zp = u ? __fadd_rn(lower, __fmul_rn(__fsub_rn(upper, lower), u[k])) : zs[k];
+    zout[k] = zp;
+    const int b = sdf_band(zp, d, tr, tr04);
+    nf += (b == 0);
+    nc += (b == 1);
+    nt += (b == 2);
+    lower = upper;
+  }
+}
+
+__global__ void __launch_bounds__(SB) k_sample_rays(const __grid_constant__ SampleArgs a) {
+  __shared__ int sh[2 * SB / 32 + 2];
+  __shared__ int s_base[2];
+  __shared__ int s_cnt[4];
+  const int N = a.n_img * a.n_per_img;
+  const int start = blockIdx.x * SB;
+  const int slot = start + threadIdx.x;
+  if (threadIdx.x < 4) s_cnt[threadIdx.x] = 0;
+  // kept / depth-less counts of all preceding slots (recomputed, cheap; keeps the compaction ordered
+  // without a second launch or a look-back chain)
+  int pk = 0, pd = 0;
+  for (int j = threadIdx.x; j < start; j += SB) {
+    const RayEval e = eval_ray(a, j);
+    pk += e.keep;
+    pd += e.keep && !(e.depth > 0.f);
+  }
+  pk = (int)warp_sum((float)pk);  // counts < 2^24: exact in fp32
+  pd = (int)warp_sum((float)pd);
+  if ((threadIdx.x & 31) == 0) {
+    sh[threadIdx.x >> 5] = pk;
+    sh[SB / 32 + (threadIdx.x >> 5)] = pd;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    int t0 = 0, t1 = 0;
+    for (int w2 = 0; w2 < SB / 32; ++w2) {
+      t0 += sh[w2];
+      t1 += sh[SB / 32 + w2];
+    }
+    s_base[0] = t0;
+    s_base[1] = t1;
+  }
+  __syncthreads();
+  RayEval e;
+  e.keep = false;
+  e.depth = 0.f;
+  if (slot < N) e = eval_ray(a, slot);
+  const int fk_ = e.keep ? 1 : 0;
+  const int fd_ = (e.keep && !(e.depth > 0.f)) ? 1 : 0;
+  int ex0, ex1, tot0, tot1;
+  block_scan2(fk_, fd_, ex0, ex1, tot0, tot1, sh);
+  const int S = a.n_strat + a.n_imp;
+  if (e.keep) {
+    const int r = s_base[0] + ex0;
+    const int r0 = s_base[1] + ex1;  // ordinal among depth-less rays
+    const int r1 = r - r0;           // ordinal among depth>0 rays
+    const int frame = slot / a.n_per_img;
+    const long long pix = a.pix_idx[slot];
+    const int pr = (int)(pix / a.Wc), pc = (int)(pix - (long long)pr * a.Wc);
+#pragma unroll
+    for (int x = 0; x < 3; ++x) {
+      a.rays_o[r * 3 + x] = e.o[x];
+      a.rays_d[r * 3 + x] = e.d[x];
+    }
+    a.gt_depth[r] = e.depth;
+    const double* cp = a.color + (((long long)frame * a.H + (a.H0 + pr)) * a.W + (a.W0 + pc)) * 3;
+    a.gt_color[(long long)r * 3 + 0] = cp[0];
+    a.gt_color[(long long)r * 3 + 1] = cp[1];
+    a.gt_color[(long long)r * 3 + 2] = cp[2];
+    a.src[r] = slot;
+    int nf = 0, nc = 0, nt = 0;
+    if (e.depth > 0.f) {
+      depth_guided_z(e.depth, a.n_strat, a.n_imp, a.t_uni, a.t_surf, a.tr15, a.tr3,
+                     a.u_depth ? a.u_depth + (long long)r1 * S : nullptr, a.z + (long long)r * S, a.tr, a.tr04, nf,
+                     nc, nt);
+      atomicAdd(&s_cnt[0], 1);
+      atomicAdd(&s_cnt[1], nf);
+      atomicAdd(&s_cnt[2], nc);
+      atomicAdd(&s_cnt[3], nt);
+    } else {
+      a.dl_list[r0] = r;
+    }
+    a.band[r * 4 + 0] = (unsigned char)nf;
+    a.band[r * 4 + 1] = (unsigned char)nc;
+    a.band[r * 4 + 2] = (unsigned char)nt;
+    a.band[r * 4 + 3] = e.depth > 0.f ? 1 : 0;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    if (tot0) atomicAdd(a.counters + 0, tot0);
+    if (tot1) atomicAdd(a.counters + 1, tot1);
+    if (s_cnt[0]) atomicAdd(a.counters + 2, s_cnt[0]);
+    if (s_cnt[1]) atomicAdd(a.counters + 3, s_cnt[1]);
+    if (s_cnt[2]) atomicAdd(a.counters + 4, s_cnt[2]);
+    if (s_cnt[3]) atomicAdd(a.counters + 5, s_cnt[3]);
+  }
+  if (a.c2w_out && slot < N && (slot % a.n_per_img) == 0) {
+    const int frame = slot / a.n_per_img;
+    float Rm[9], t[3];
+    float* out = a.c2w_out + frame * 16;
+    if (a.poses && frame >= a.pose_first) {
+      const float* p = a.poses + frame * 7;
+      quat_to_rot(p, Rm);
+      t[0] = p[4];
+      t[1] = p[5];
+      t[2] = p[6];
+      for (int x = 0; x < 3; ++x) {
+        out[x * 4 + 0] = Rm[x * 3 + 0];
+        out[x * 4 + 1] = Rm[x * 3 + 1];
+        out[x * 4 + 2] = Rm[x * 3 + 2];
+        out[x * 4 + 3] = t[x];
+      }
+      out[12] = out[13] = out[14] = 0.f;
+      out[15] = 1.f;
+    } else {
+      for (int x = 0; x < 16; ++x) out[x] = a.c2w[frame * 16 + x];
+    }
+  }
+}
+
+// z_vals of an explicit, already compacted ray list (render_batch_ray through the reference's API)
+struct DepthSampleArgs {
+  int n_strat, n_imp;
+  float tr, tr15, tr3, tr04;
+  const float* gt_depth;
+  int n_rays;
+  const float* u_depth;
+  const float *t_uni, *t_surf;
+  float* z;
+  int* dl_list;
+  int* counters;
+};
+
+__global__ void __launch_bounds__(SB) k_depth_samples(const __grid_constant__ DepthSampleArgs a) {
+  __shared__ int sh[2 * SB / 32 + 2];
+  __shared__ int s_base;
+  const int start = blockIdx.x * SB;
+  const int r = start + threadIdx.x;
+  int pd = 0;
+  for (int j = threadIdx.x; j < start; j += SB) pd += !(a.gt_depth[j] > 0.f);
+  pd = (int)warp_sum((float)pd);
+  if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = pd;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    int t0 = 0;
+    for (int w2 = 0; w2 < SB / 32; ++w2) t0 += sh[w2];
+    s_base = t0;
+  }
+  __syncthreads();
+  const bool in = r < a.n_rays;
+  const float d = in ? a.gt_depth[r] : 1.f;
+  const int fd_ = (in && !(d > 0.f)) ? 1 : 0;
+  int ex0, ex1, tot0, tot1;
+  block_scan2(fd_, 0, ex0, ex1, tot0, tot1, sh);
+  const int S = a.n_strat + a.n_imp;
+  if (in) {
+    const int r0 = s_base + ex0;
+    if (d > 0.f) {
+      int nf, nc, nt;
+      depth_guided_z(d, a.n_strat, a.n_imp, a.t_uni, a.t_surf, a.tr15, a.tr3,
+                     a.u_depth ? a.u_depth + (long long)(r - r0) * S : nullptr, a.z + (long long)r * S, a.tr, a.tr04,
+                     nf, nc, nt);
+    } else {
+      a.dl_list[r0] = r;
+    }
+  }
+  if (threadIdx.x == 0) {
+    if (tot0) atomicAdd(a.counters + 1, tot0);
+    if (blockIdx.x == 0) a.counters[0] = a.n_rays;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// importance resampling of depth-less rays  (Renderer.py:108-134, common.py:41-77)
+// ---------------------------------------------------------------------------------------------------
+struct ImportanceArgs {
+  FieldK fk;
+  const float4* arena4;
+  int n_strat, n_imp;
+  const float *rays_o, *rays_d;
+  const int* dl_list;
+  const int* counters;
+  const float *u_coarse, *u_fine;
+  const float* t_uni;
+  float* z;
+};
+
+__global__ void __launch_bounds__(NP) k_importance(const __grid_constant__ ImportanceArgs a) {
+  __shared__ SmemFwd sm;
+  __shared__ float s_zi[NP];  // resampled depths, [rl*n_imp + i]
+  const int R0 = a.counters[1];
+  const int NS = a.n_strat;
+  const int RPB = NP / NS;
+  const int r00 = blockIdx.x * RPB;
+  if (r00 >= R0) return;
+  const int rays_here = min(RPB, R0 - r00);
+  const int n_valid = rays_here * NS;
+  const int q = threadIdx.x;
+  const bool valid = q < n_valid;
+  const int rl = valid ? q / NS : 0;
+  const int k = q - rl * NS;
+  const int r0 = r00 + rl;
+  const int ray = a.dl_list[r0];
+  float o[3], d[3];
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+    o[c] = a.rays_o[ray * 3 + c];
+    d[c] = a.rays_d[ray * 3 + c];
+  }
+  const float far = __fadd_rn(bbox_exit(a.fk, o, d), 0.01f);
+  float zp = 0.f, pn[3] = {0.f, 0.f, 0.f};
+  if (valid) {
+    // z_uni = 0*(1-t) + far*t == far*t; perturbation inside the midpoints' intervals
+    const float zc = __fmul_rn(far, a.t_uni[k]);
+    const float lower = k > 0 ? __fmul_rn(0.5f, __fadd_rn(zc, __fmul_rn(far, a.t_uni[k - 1]))) : zc;
+    const float upper = k < NS - 1 ? __fmul_rn(0.5f, __fadd_rn(__fmul_rn(far, a.t_uni[k + 1]), zc)) : zc;
+    zp = __fadd_rn(lower, __fmul_rn(__fsub_rn(upper, lower), a.u_coarse[(long long)r0 * NS + k]));
+#pragma unroll
+    for (int c = 0; c < 3; ++c) pn[c] = normalize_axis(__fadd_rn(o[c], __fmul_rn(d[c], zp)), a.fk.lo[c], a.fk.hi[c]);
+  }
+  write_axis_setups<2>(a.fk, 0, pn, sm.ax_i, sm.ax_f, q);
+  __syncthreads();
+  gather_tile<0>(a.fk, 0, a.arena4, sm.ax_i, sm.ax_f, sm.F, n_valid);
+  __syncthreads();
+  float h1[16], h2[16], os[1];
+  mlp_forward<S_W1, S_B1, S_W2, S_B2, S_W3, S_B3, 1>(sm.F, q, h1, h2, os);
+  const float sdf = tanhf(os[0]);
+  float u, e, alpha;
+  sdf_to_alpha(sdf, c_dec[P_BETA], u, e, alpha);
+  sm.one[q] = __fadd_rn(__fsub_rn(1.0f, alpha), 1e-10f);
+  sm.z[q] = zp;
+  __syncthreads();
+  float T = 1.0f;
+  for (int j = 0; j < k; ++j) T *= sm.one[rl * NS + j];
+  sm.w[q] = alpha * T;
+  __syncthreads();
+  // inverse cdf: pdf = w[1..NS-2] (un-normalised), bins = midpoints (NS-1 of them), cdf has NS-1 entries
+  if (valid && k < a.n_imp) {
+    const float* w = sm.w + rl * NS;
+    const float* zz = sm.z + rl * NS;
+    const float uu = a.u_fine[(long long)r0 * a.n_imp + k];
+    const int ncdf = NS - 1;
+    // searchsorted(cdf, u, right=True): number of cdf entries <= u
+    float c = 0.f;
+    int inds = 0;
+    float c_below = 0.f, c_above = 0.f;
+    {
+      float run = 0.f;
+      // entry 0 is 0, entry m is sum_{x<m} pdf[x] = sum w[1..m]
+      int cnt = 0;
+      for (int m = 0; m < ncdf; ++m) {
+        if (m > 0) run = __fadd_rn(run, w[m]);
+        if (run <= uu) ++cnt;
+      }
+      inds = cnt;
+      const int below = max(inds - 1, 0), above = min(inds, ncdf - 1);
+      run = 0.f;
+      for (int m = 0; m < ncdf; ++m) {
+        if (m > 0) run = __fadd_rn(run, w[m]);
+        if (m == below) c_below = run;
+        if (m == above) c_above = run;
+      }
+      const float b0 = __fmul_rn(0.5f, __fadd_rn(zz[below + 1], zz[below]));
+      const float b1 = __fmul_rn(0.5f, __fadd_rn(zz[above + 1], zz[above]));
+      float denom = __fsub_rn(c_above, c_below);
+      if (denom < 1e-5f) denom = 1.0f;
+      const float t = __fdiv_rn(__fsub_rn(uu, c_below), denom);
+      c = __fadd_rn(b0, __fmul_rn(t, __fsub_rn(b1, b0)));
+    }
+    s_zi[rl * a.n_imp + k] = c;
+  }
+  __syncthreads();
+  if (valid && k == 0) {
+    // sort the n_imp resampled depths, merge with the (ascending) coarse ones
+    float zi[16];
+    const int NI = a.n_imp;
+    for (int i = 0; i < NI; ++i) {
+      float v = s_zi[rl * NI + i];
+      int j = i;
+      while (j > 0 && zi[j - 1] > v) {
+        zi[j] = zi[j - 1];
+        --j;
+      }
+      zi[j] = v;
+    }
+    const float* zz = sm.z + rl * NS;
+    float* out = a.z + (long long)ray * (NS + NI);
+    int ia = 0, ib = 0;
+    for (int m = 0; m < NS + NI; ++m) {
+      const bool take_a = (ib >= NI) || (ia < NS && zz[ia] <= zi[ib]);
+      out[m] = take_a ? zz[ia++] : zi[ib++];
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// tracker outlier mask: lower median of |gt - rendered| by radix select  (Tracker.py:192-195)
+// ---------------------------------------------------------------------------------------------------
+struct TrackMaskArgs {
+  const float *gt_depth, *depth;
+  const unsigned char* band;
+  int max_rays;
+  int* counters;
+  unsigned char* ray_mask;
+  float* scratch;
+};
+
+__global__ void __launch_bounds__(1024) k_track_mask(const __grid_constant__ TrackMaskArgs a) {
+  __shared__ unsigned hist[256];
+  __shared__ unsigned s_prefix, s_rank;
+  __shared__ int s_tot[4];
+  const int R = min(a.counters[0], a.max_rays);
+  const int t = threadIdx.x;
+  unsigned* key = reinterpret_cast<unsigned*>(a.scratch);
+  for (int r = t; r < R; r += blockDim.x) key[r] = __float_as_uint(fabsf(__fsub_rn(a.gt_depth[r], a.depth[r])));
+  if (t == 0) {
+    s_prefix = 0u;
+    s_rank = R > 0 ? (unsigned)((R - 1) / 2) : 0u;
+  }
+  if (t < 4) s_tot[t] = 0;
+  __syncthreads();
+  for (int pass = 0; pass < 4; ++pass) {
+    const int shift = 24 - 8 * pass;
+    if (t < 256) hist[t] = 0u;
+    __syncthreads();
+    const unsigned prefix = s_prefix;
+    const unsigned himask = pass == 0 ? 0u : (0xffffffffu << (shift + 8));
+    for (int r = t; r < R; r += blockDim.x) {
+      const unsigned kk = key[r];
+      if ((kk & himask) == prefix) atomicAdd(&hist[(kk >> shift) & 255u], 1u);
+    }
+    __syncthreads();
+    if (t == 0) {
+      unsigned rank = s_rank, cum = 0u;
+      int b = 0;
+      for (; b < 256; ++b) {
+        if (cum + hist[b] > rank) break;
+        cum += hist[b];
+      }
+      if (b > 255) b = 255;
+      s_prefix = prefix | ((unsigned)b << shift);
+      s_rank = rank - cum;
+    }
+    __syncthreads();
+  }
+  const float median = __uint_as_float(s_prefix);
+  const float thr = __fmul_rn(10.0f, median);
+  int c0 = 0, c1 = 0, c2 = 0, c3 = 0;
+  for (int r = t; r < R; r += blockDim.x) {
+    const bool m = __uint_as_float(key[r]) < thr;
+    a.ray_mask[r] = m ? 1 : 0;
+    if (m) {
+      c0 += 1;
+      c1 += a.band[r * 4 + 0];
+      c2 += a.band[r * 4 + 1];
+      c3 += a.band[r * 4 + 2];
+    }
+  }
+  c0 = (int)warp_sum((float)c0);
+  c1 = (int)warp_sum((float)c1);
+  c2 = (int)warp_sum((float)c2);
+  c3 = (int)warp_sum((float)c3);
+  if ((t & 31) == 0) {
+    atomicAdd(&s_tot[0], c0);
+    atomicAdd(&s_tot[1], c1);
+    atomicAdd(&s_tot[2], c2);
+    atomicAdd(&s_tot[3], c3);
+  }
+  __syncthreads();
+  if (t < 4) a.counters[2 + t] = s_tot[t];
+  if (t == 0) a.scratch[a.max_rays] = median;
+}
+
+}  // namespace eslam

@@ -1,0 +1,189 @@
+"""The map as the kernels see it: ONE fp32 arena per process holding the 12 feature planes in
+channels-last [H][W][32] order followed by the packed decoders, plus same-layout gradient and Adam
+moment arenas.  The reference keeps the planes as 12 separate [1,32,H,W] tensors owned by
+`ESLAM` (src/ESLAM.py:175-218) and the decoders as an nn.Module (src/networks/decoders.py:39-62);
+`FieldStore.pull()` / `push()` convert between the two.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Dict, List, Optional, Sequence, Tuple
+
+import torch
+
+from . import _lib
+from ._lib import DEC_BETA, DEC_FLOATS, FieldDesc, call, ptr, stream
+
+# arena plane order: sdf coarse xy,xz,yz | sdf fine xy,xz,yz | rgb coarse ... | rgb fine ...
+# all_planes order (Tracker.py:164): (planes_xy, planes_xz, planes_yz, c_planes_xy, c_planes_xz, c_planes_yz),
+# each a list [coarse, fine]
+def arena_slot(group: int, scale: int) -> int:
+    """group = index into all_planes (0..5), scale 0/1 -> arena plane index."""
+    fld, pair = divmod(group, 3)
+    return fld * 6 + scale * 3 + pair
+
+
+# (state_dict key, offset, n) in the packed decoder block (include/eslam_b200.h)
+DEC_LAYOUT = (
+    ("linears.0.weight", 0, 1024), ("linears.0.bias", 1024, 16), ("linears.1.weight", 1040, 256),
+    ("linears.1.bias", 1296, 16), ("output_linear.weight", 1312, 16), ("output_linear.bias", 1328, 1),
+    ("c_linears.0.weight", 1332, 1024), ("c_linears.0.bias", 2356, 16), ("c_linears.1.weight", 2372, 256),
+    ("c_linears.1.bias", 2628, 16), ("c_output_linear.weight", 2644, 48), ("c_output_linear.bias", 2692, 3),
+    ("beta", DEC_BETA, 1),
+)
+
+
+def flatten_planes(all_planes) -> List[torch.Tensor]:
+    """The 12 plane tensors of an `all_planes` tuple in arena order."""
+    out: List[Optional[torch.Tensor]] = [None] * 12
+    for g, lst in enumerate(all_planes):
+        if len(lst) != 2:
+            raise RuntimeError("myslam_b200 supports exactly two plane scales (coarse, fine) per group")
+        for s, p in enumerate(lst):
+            out[arena_slot(g, s)] = p
+    return out  # type: ignore[return-value]
+
+
+class FieldStore:
+    """Arena + descriptor for one map.  Shapes are fixed at construction."""
+
+    def __init__(self, plane_shapes: Sequence[Tuple[int, int]], bound, device):
+        if len(plane_shapes) != 12:
+            raise RuntimeError("need 12 plane shapes in arena order")
+        self.device = torch.device(device)
+        if self.device.type != "cuda":
+            raise RuntimeError("FieldStore needs a CUDA device; myslam_b200 has no CPU path")
+        self.shapes = [(int(h), int(w)) for h, w in plane_shapes]
+        self.desc = FieldDesc()
+        off = 0
+        self.plane_off: List[int] = []
+        for i, (h, w) in enumerate(self.shapes):
+            self.desc.plane[i].offset = off
+            self.desc.plane[i].H = h
+            self.desc.plane[i].W = w
+            self.plane_off.append(off)
+            off += h * w * 32
+        self.n_sdf_end = self.plane_off[6]
+        self.n_planes_end = off
+        self.dec_off = off
+        off += DEC_FLOATS
+        self.n_floats = off
+        assert self.n_floats % 4 == 0
+        self.desc.dec_offset = self.dec_off
+        self.desc.n_floats = self.n_floats
+        b = torch.as_tensor(bound, dtype=torch.float32).cpu()
+        for a in range(3):
+            self.desc.bound[a][0] = float(b[a, 0])
+            self.desc.bound[a][1] = float(b[a, 1])
+        self.bound = b
+        self.arena = torch.zeros(self.n_floats, dtype=torch.float32, device=self.device)
+        self.grad: Optional[torch.Tensor] = None
+        self.exp_avg: Optional[torch.Tensor] = None
+        self.exp_avg_sq: Optional[torch.Tensor] = None
+        self._sig = None  # (data_ptr, version) of what was last pulled
+
+    # ------------------------------------------------------------------ construction helpers
+    @classmethod
+    def from_planes(cls, all_planes, bound, device=None) -> "FieldStore":
+        flat = flatten_planes(all_planes)
+        for p in flat:
+            if p.dim() != 4 or p.shape[0] != 1 or p.shape[1] != 32:
+                raise RuntimeError(f"planes must be [1,32,H,W] (model.c_dim=32), got {tuple(p.shape)}")
+        dev = device if device is not None else flat[0].device
+        return cls([(p.shape[2], p.shape[3]) for p in flat], bound, dev)
+
+    def matches(self, all_planes) -> bool:
+        flat = flatten_planes(all_planes)
+        return all((p.shape[2], p.shape[3]) == s for p, s in zip(flat, self.shapes))
+
+    def ref(self):
+        return C.byref(self.desc)
+
+    @property
+    def dec(self) -> torch.Tensor:
+        return self.arena[self.dec_off:self.dec_off + DEC_FLOATS]
+
+    def plane_view(self, i: int, which: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """[H,W,32] view of plane i in `which` arena (default: parameters)."""
+        a = self.arena if which is None else which
+        h, w = self.shapes[i]
+        return a[self.plane_off[i]:self.plane_off[i] + h * w * 32].view(h, w, 32)
+
+    # ------------------------------------------------------------------ reference layout -> arena
+    def pull_planes(self, all_planes) -> None:
+        for i, p in enumerate(flatten_planes(all_planes)):
+            _lib.require_cuda(p, "plane")
+            src = p.detach()
+            if src.dtype != torch.float32 or not src.is_contiguous():
+                src = src.float().contiguous()
+            call("eslam_plane_import", ptr(src), ptr(self.arena), C.byref(self.desc.plane[i]), stream())
+
+    def pull_decoders(self, state: Dict[str, torch.Tensor], beta) -> None:
+        dec = self.dec
+        for key, off, n in DEC_LAYOUT:
+            if key == "beta":
+                val = beta if torch.is_tensor(beta) else torch.tensor([float(beta)])
+                dec[off:off + 1].copy_(val.detach().reshape(1).to(self.device, torch.float32), non_blocking=True)
+            else:
+                dec[off:off + n].copy_(state[key].detach().reshape(-1), non_blocking=True)
+
+    def signature(self, all_planes, dec_tensors) -> tuple:
+        sig = [(p.data_ptr(), p._version) for p in flatten_planes(all_planes)]
+        sig += [(t.data_ptr(), t._version) if torch.is_tensor(t) else (0, float(t)) for t in dec_tensors]
+        return tuple(sig)
+
+    # ------------------------------------------------------------------ arena -> reference layout
+    def push_planes(self, all_planes, which: Optional[torch.Tensor] = None) -> None:
+        a = self.arena if which is None else which
+        for i, p in enumerate(flatten_planes(all_planes)):
+            dst = p.detach()
+            if not dst.is_contiguous() or dst.dtype != torch.float32:
+                raise RuntimeError("planes must be contiguous float32 to be updated in place")
+            call("eslam_plane_export", ptr(a), ptr(dst), C.byref(self.desc.plane[i]), stream())
+
+    def export_plane(self, i: int, which: torch.Tensor) -> torch.Tensor:
+        """NCHW copy of plane i of arena `which` (used for autograd gradients)."""
+        h, w = self.shapes[i]
+        out = torch.empty(1, 32, h, w, dtype=torch.float32, device=self.device)
+        call("eslam_plane_export", ptr(which), ptr(out), C.byref(self.desc.plane[i]), stream())
+        return out
+
+    def push_decoders(self, module) -> None:
+        dec = self.dec
+        with torch.no_grad():
+            sd = dict(module.named_parameters())
+            for key, off, n in DEC_LAYOUT:
+                if key in sd:
+                    sd[key].copy_(dec[off:off + n].view_as(sd[key]))
+
+    def dec_grad_dict(self, which: torch.Tensor) -> Dict[str, torch.Tensor]:
+        g = which[self.dec_off:self.dec_off + DEC_FLOATS]
+        return {key: g[off:off + n] for key, off, n in DEC_LAYOUT}
+
+    # ------------------------------------------------------------------ kernels' view
+    def bind(self) -> None:
+        """Make this map's decoders the ones the kernels read (constant memory)."""
+        call("eslam_bind_decoders", ptr(self.dec), stream())
+
+    def ensure_grad(self) -> torch.Tensor:
+        if self.grad is None:
+            self.grad = torch.zeros_like(self.arena)
+        return self.grad
+
+    def reset_adam(self) -> None:
+        """Fresh optimiser state, as Mapper.optimize_mapping builds a new Adam per call (Mapper.py:291-299)."""
+        if self.exp_avg is None:
+            self.exp_avg = torch.zeros_like(self.arena)
+            self.exp_avg_sq = torch.zeros_like(self.arena)
+        else:
+            self.exp_avg.zero_()
+            self.exp_avg_sq.zero_()
+        self.ensure_grad().zero_()
+
+    def adam_step(self, step: int, lr_dec: float, lr_planes: float, lr_cplanes: float, betas=(0.9, 0.999),
+                  eps=1e-8) -> None:
+        """One torch.optim.Adam step over planes (two lr groups) + decoders; zeroes the gradient arena."""
+        seg_end = (C.c_int64 * 3)(self.n_sdf_end, self.n_planes_end, self.n_floats)
+        seg_lr = (C.c_double * 3)(lr_planes, lr_cplanes, lr_dec)
+        call("eslam_adam_step", ptr(self.arena), ptr(self.grad), ptr(self.exp_avg), ptr(self.exp_avg_sq),
+             self.n_floats, seg_end, seg_lr, 3, step, betas[0], betas[1], eps, stream())

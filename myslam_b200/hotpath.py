@@ -1,0 +1,191 @@
+"""The fused per-iteration render-and-optimise step as a short
+sequence of kernel launches on the current stream, with no host synchronisation in the default
+mode:
+
+  tracking:  sample_rays -> render_forward -> track_mask -> loss_backward(pose) -> finalize -> pose Adam
+  mapping:   sample_rays -> importance_samples -> loss_backward(planes, decoders, poses) -> Adam -> pose Adam
+
+`strict_rng=True` reproduces the reference's random-draw SHAPES ([R1,S], [R0,n_strat], [R0,n_imp]),
+which costs one host sync per iteration (the reference has >= 12); it is what parity runs use.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass
+from typing import Optional
+
+import torch
+
+from ._lib import N_COUNTERS, N_LOSS, Camera, RenderCfg, call, ptr, stream
+from .field import FieldStore
+from .renderer import TorchDraws, linspace_table, make_cfg
+
+
+def make_camera(H, W, fx, fy, cx, cy, H0=0, H1=None, W0=0, W1=None) -> Camera:
+    c = Camera()
+    c.H, c.W = int(H), int(W)
+    c.fx, c.fy, c.cx, c.cy = float(fx), float(fy), float(cx), float(cy)
+    c.H0, c.H1 = int(H0), int(H if H1 is None else H1)
+    c.W0, c.W1 = int(W0), int(W if W1 is None else W1)
+    return c
+
+
+class Workspace:
+    """Per-process scratch for up to `max_rays` rays of `n_samples` samples and `max_frames` frames."""
+
+    def __init__(self, device, max_rays: int, n_samples: int, max_frames: int = 32):
+        dev = torch.device(device)
+        N, S = int(max_rays), int(n_samples)
+        f32, i32 = torch.float32, torch.int32
+        self.device, self.max_rays, self.n_samples, self.max_frames = dev, N, S, max_frames
+        self.rays_o = torch.empty(N, 3, dtype=f32, device=dev)
+        self.rays_d = torch.empty(N, 3, dtype=f32, device=dev)
+        self.gt_depth = torch.empty(N, dtype=f32, device=dev)
+        self.gt_color = torch.empty(N, 3, dtype=torch.float64, device=dev)
+        self.src = torch.empty(N, dtype=i32, device=dev)
+        self.z = torch.empty(N, S, dtype=f32, device=dev)
+        self.dl_list = torch.empty(N, dtype=i32, device=dev)
+        self.band = torch.empty(N, 4, dtype=torch.uint8, device=dev)
+        self.counters = torch.zeros(N_COUNTERS, dtype=i32, device=dev)
+        self.depth = torch.empty(N, dtype=f32, device=dev)
+        self.rgb = torch.empty(N, 3, dtype=f32, device=dev)
+        self.sdf = torch.empty(N, S, dtype=f32, device=dev)
+        self.ray_mask = torch.empty(N, dtype=torch.uint8, device=dev)
+        self.scratch = torch.empty(N + 1, dtype=f32, device=dev)
+        self.loss_acc = torch.zeros(N_LOSS, dtype=torch.float64, device=dev)
+        self.loss_out = torch.zeros(1, dtype=f32, device=dev)
+        self.pose_grad = torch.zeros(max_frames, 12, dtype=f32, device=dev)
+        self.grad7 = torch.zeros(max_frames, 7, dtype=f32, device=dev)
+        self.pose_m = torch.zeros(max_frames, 7, dtype=f32, device=dev)
+        self.pose_v = torch.zeros(max_frames, 7, dtype=f32, device=dev)
+        self.c2w_out = torch.zeros(max_frames, 16, dtype=f32, device=dev)
+
+    def fits(self, n_rays, n_samples, n_frames):
+        return n_rays <= self.max_rays and n_samples == self.n_samples and n_frames <= self.max_frames
+
+
+@dataclass
+class StepCfg:
+    """What one iteration needs besides the tensors: camera+crop, sampling and loss configuration."""
+    cam: Camera
+    render: RenderCfg
+    perturb: bool = True
+
+
+def _sample(ws: Workspace, store: FieldStore, sc: StepCfg, idx, n_img, n_per_img, c2w, poses, pose_first, depth,
+            color, u_depth, need_depth):
+    dev = ws.device
+    t_uni = linspace_table(sc.render.n_stratified, dev)
+    t_surf = linspace_table(sc.render.n_importance, dev)
+    call("eslam_sample_rays", store.ref(), C.byref(sc.cam), C.byref(sc.render), ptr(idx), n_img, n_per_img, ptr(c2w),
+         ptr(poses), pose_first, ptr(depth), ptr(color), ptr(u_depth), ptr(t_uni), ptr(t_surf), need_depth,
+         ptr(ws.rays_o), ptr(ws.rays_d), ptr(ws.gt_depth), ptr(ws.gt_color), ptr(ws.src), ptr(ws.z),
+         ptr(ws.dl_list), ptr(ws.band), ptr(ws.counters), ptr(ws.c2w_out), stream())
+
+
+def _check_frames(depth, color, n_img, cam):
+    if depth.dtype != torch.float32 or color.dtype != torch.float64:
+        raise RuntimeError("gt depth must be float32 and gt colour float64, as the reference's datasets produce "
+                           "(src/utils/datasets.py:90-92)")
+    if tuple(depth.shape) != (n_img, cam.H, cam.W) or tuple(color.shape) != (n_img, cam.H, cam.W, 3):
+        raise RuntimeError(f"frame stack shapes {tuple(depth.shape)} / {tuple(color.shape)} do not match the camera")
+    if not (depth.is_contiguous() and color.is_contiguous()):
+        raise RuntimeError("frame stacks must be contiguous")
+
+
+def tracking_iteration(ws: Workspace, store: FieldStore, sc: StepCfg, pose7: torch.Tensor, gt_color, gt_depth,
+                       n_pixels: int, draws=None, strict_rng: bool = False, apply_adam: Optional[dict] = None):
+    """One iteration of Tracker.optimize_tracking (Tracker.py:150-210) up to (and optionally including)
+    the Adam step.  pose7: [1,7] contiguous fp32 device tensor (quaternion, translation).
+    After the call: ws.loss_acc[5] = loss (float64), ws.grad7[0] = d loss / d pose.
+    apply_adam: dict(step=, lr_q=, lr_t=) -> fused Adam(betas .5,.999) on pose7 in place (ws.pose_m/v)."""
+    dev = ws.device
+    draws = draws or TorchDraws(dev)
+    cam, rc = sc.cam, sc.render
+    S = rc.n_stratified + rc.n_importance
+    n_crop = (cam.H1 - cam.H0) * (cam.W1 - cam.W0)
+    _check_frames(gt_depth, gt_color, 1, cam)
+    idx = draws.randint(n_crop, n_pixels)
+    store.bind()
+    if not sc.perturb:
+        u = None
+    elif strict_rng:
+        _sample(ws, store, sc, idx, 1, n_pixels, None, pose7, 0, gt_depth, gt_color, None, 1)
+        u = draws.rand(int(ws.counters[0].item()), S)
+    else:
+        u = draws.rand(n_pixels, S)
+    _sample(ws, store, sc, idx, 1, n_pixels, None, pose7, 0, gt_depth, gt_color, u, 1)
+    N = n_pixels
+    call("eslam_render_forward", store.ref(), ptr(store.arena), ptr(ws.rays_o), ptr(ws.rays_d), ptr(ws.z), N, S,
+         ptr(ws.counters), ptr(ws.depth), ptr(ws.rgb), ptr(ws.sdf), stream())
+    call("eslam_track_mask", ptr(ws.gt_depth), ptr(ws.depth), ptr(ws.band), N, ptr(ws.counters), ptr(ws.ray_mask),
+         ptr(ws.scratch), stream())
+    call("eslam_loss_backward", store.ref(), ptr(store.arena), C.byref(cam), C.byref(rc), ptr(ws.rays_o),
+         ptr(ws.rays_d), ptr(ws.z), ptr(ws.gt_depth), ptr(ws.gt_color), ptr(ws.src), ptr(idx), n_pixels,
+         ptr(ws.ray_mask), ptr(ws.counters), None, N, None, ptr(ws.pose_grad), ptr(ws.loss_acc), stream())
+    call("eslam_finalize_loss", C.byref(rc), ptr(ws.counters), 1, ptr(ws.loss_acc), ptr(ws.loss_out), stream())
+    if apply_adam is None:
+        call("eslam_pose_adam_step", ptr(pose7), ptr(ws.pose_grad), None, None, 1, 0, 0.0, 0.0, 1, 0.5, 0.999, 1e-8,
+             ptr(ws.grad7), 0, stream())
+    else:
+        call("eslam_pose_adam_step", ptr(pose7), ptr(ws.pose_grad), ptr(ws.pose_m), ptr(ws.pose_v), 1, 0,
+             apply_adam["lr_q"], apply_adam["lr_t"], apply_adam["step"], 0.5, 0.999, 1e-8, ptr(ws.grad7), 1, stream())
+
+
+def mapping_iteration(ws: Workspace, store: FieldStore, sc: StepCfg, c2ws, poses7, gt_colors, gt_depths,
+                      pix_per_image: int, step: int, lr_dec: float, lr_planes: float, lr_cplanes: float,
+                      lr_cam: float, draws=None, strict_rng: bool = False, want_loss: bool = False,
+                      apply_adam: bool = True, reduce_counters=None, reduce_grads=None):
+    """One iteration of the loop in Mapper.optimize_mapping (Mapper.py:308-350).
+    c2ws [b,4,4] fp32; poses7 [b,7] or None (joint_opt: frames 1.. are taken from poses7 and updated).
+    Planes/decoders live in `store` (Adam state in store.exp_avg*, reset by the caller per call).
+    reduce_counters(counters)->norm and reduce_grads(grad, pose_grad, loss_acc) are the two exchange
+    points of the ray-sharded multi-GPU mapping (myslam_b200.dist); None on one GPU."""
+    dev = ws.device
+    draws = draws or TorchDraws(dev)
+    cam, rc = sc.cam, sc.render
+    ns, ni = rc.n_stratified, rc.n_importance
+    S = ns + ni
+    b = c2ws.shape[0]
+    N = pix_per_image * b
+    _check_frames(gt_depths, gt_colors, b, cam)
+    n_crop = (cam.H1 - cam.H0) * (cam.W1 - cam.W0)
+    idx = draws.randint(n_crop, N)
+    store.bind()
+    c2w_flat = c2ws.reshape(b, 16).float().contiguous()
+    joint = poses7 is not None
+    if strict_rng:
+        _sample(ws, store, sc, idx, b, pix_per_image, c2w_flat, poses7, 1, gt_depths, gt_colors, None, 0)
+        cnt = ws.counters[:2].tolist()
+        r0 = cnt[1]
+        u = draws.rand(cnt[0] - r0, S) if sc.perturb else None
+    else:
+        r0 = N
+        u = draws.rand(N, S) if sc.perturb else None
+    _sample(ws, store, sc, idx, b, pix_per_image, c2w_flat, poses7, 1, gt_depths, gt_colors, u, 0)
+    if r0 > 0:
+        u_c = draws.rand(r0, ns)
+        u_f = draws.rand(r0, ni)
+        call("eslam_importance_samples", store.ref(), ptr(store.arena), C.byref(rc), ptr(ws.rays_o), ptr(ws.rays_d),
+             ptr(ws.dl_list), ptr(ws.counters), r0, ptr(u_c), ptr(u_f), ptr(linspace_table(ns, dev)), ptr(ws.z),
+             stream())
+    grad = store.ensure_grad()
+    norm = reduce_counters(ws.counters) if reduce_counters is not None else None
+    call("eslam_loss_backward", store.ref(), ptr(store.arena), C.byref(cam), C.byref(rc), ptr(ws.rays_o),
+         ptr(ws.rays_d), ptr(ws.z), ptr(ws.gt_depth), ptr(ws.gt_color), ptr(ws.src), ptr(idx), pix_per_image, None,
+         ptr(ws.counters), ptr(norm) if norm is not None else None, N, ptr(grad),
+         ptr(ws.pose_grad) if joint else None, ptr(ws.loss_acc) if want_loss else None, stream())
+    if reduce_grads is not None:
+        reduce_grads(grad, ws.pose_grad if joint else None, ws.loss_acc if want_loss else None)
+    if want_loss:
+        call("eslam_finalize_loss", C.byref(rc), ptr(norm if norm is not None else ws.counters), 0, ptr(ws.loss_acc),
+             ptr(ws.loss_out), stream())
+    if not apply_adam:
+        if joint:
+            call("eslam_pose_adam_step", ptr(poses7), ptr(ws.pose_grad), None, None, b, 1, 0.0, 0.0, 1, 0.9, 0.999,
+                 1e-8, ptr(ws.grad7), 0, stream())
+        return
+    store.adam_step(step, lr_dec, lr_planes, lr_cplanes)
+    if joint:
+        call("eslam_pose_adam_step", ptr(poses7), ptr(ws.pose_grad), ptr(ws.pose_m), ptr(ws.pose_v), b, 1, lr_cam,
+             lr_cam, step, 0.9, 0.999, 1e-8, ptr(ws.grad7), 1, stream())

@@ -1,0 +1,165 @@
+"""Drop-in for the hot half of `src/Mapper.py` (reference lines 110-144, 211-364):
+`optimize_mapping` with the reference's signature and side effects (planes and decoders updated in
+place in the storage `ESLAM` owns, `keyframe_dict[*]['est_c2w']` rewritten, `cur_c2w` returned).
+The per-iteration loop (sample, render, losses, backward, Adam) runs as fused kernels on the
+parameter arena; the arena is written back to the reference's [1,32,H,W] tensors once per call.
+"""
+from __future__ import annotations
+
+import os
+from typing import List, Optional
+
+import torch
+
+from .common import cam_pose_to_matrix, get_samples, matrix_to_cam_pose, random_select
+from .decoders import decoder_tensors, synced_store
+from .field import FieldStore
+from .hotpath import StepCfg, Workspace, make_camera, mapping_iteration
+from .renderer import make_cfg
+
+
+def _strict_default() -> bool:
+    return os.environ.get("ESLAM_B200_STRICT_RNG", "0") == "1"
+
+
+def map_window(store: FieldStore, ws: Workspace, sc: StepCfg, c2ws, gt_colors, gt_depths, n_pixels: int, iters: int,
+               lr_dec: float, lr_planes: float, lr_cplanes: float, joint_opt: bool, lr_cam: float, draws=None,
+               strict_rng: bool = False, losses: Optional[list] = None):
+    """The loop of Mapper.optimize_mapping (Mapper.py:288-350) for an already chosen window:
+    fresh Adam state, `iters` fused iterations on `store`.  Returns the window's c2ws [b,4,4] after the
+    call (frame 0 is held fixed, Mapper.py:314)."""
+    b = c2ws.shape[0]
+    pix = n_pixels // b
+    store.reset_adam()
+    poses7 = None
+    if joint_opt:
+        poses7 = torch.zeros(b, 7, dtype=torch.float32, device=c2ws.device)
+        if b > 1:
+            poses7[1:] = matrix_to_cam_pose(c2ws[1:])
+        ws.pose_m.zero_()
+        ws.pose_v.zero_()
+        ws.pose_grad.zero_()
+    c2ws = c2ws.float().contiguous()
+    for it in range(iters):
+        mapping_iteration(ws, store, sc, c2ws, poses7, gt_colors, gt_depths, pix, it + 1, lr_dec, lr_planes,
+                          lr_cplanes, lr_cam, draws=draws, strict_rng=strict_rng, want_loss=losses is not None)
+        if losses is not None:
+            losses.append(ws.loss_acc[5].clone())
+    if joint_opt and b > 1:
+        c2ws = torch.cat([c2ws[0:1], cam_pose_to_matrix(poses7[1:])], 0)
+    return c2ws
+
+
+def keyframe_selection_overlap(self, gt_color, gt_depth, c2w, num_keyframes, num_samples=8, num_rays=50):
+    """Keyframes whose frusta see the current view's surface (reference Mapper.py:146-209); torch ops,
+    once per mapped frame.  Returns a list of indices into keyframe_dict."""
+    device = self.device
+    H, W, fx, fy, cx, cy = self.H, self.W, self.fx, self.fy, self.cx, self.cy
+    rays_o, rays_d, d, _ = get_samples(0, H, 0, W, num_rays, H, W, fx, fy, cx, cy, c2w.unsqueeze(0),
+                                       gt_depth.unsqueeze(0), gt_color.unsqueeze(0), device)
+    ok = d > 0
+    rays_o, rays_d, d = rays_o[ok], rays_d[ok], d[ok].reshape(-1, 1).repeat(1, num_samples)
+    t = torch.linspace(0., 1., steps=num_samples).to(device)
+    z = (d * 0.8) * (1. - t) + (d + 0.5) * t
+    pts = (rays_o[:, None, :] + rays_d[:, None, :] * z[..., None]).reshape(1, -1, 3)
+    kf_c2w = torch.stack([self.estimate_c2w_list[i] for i in self.keyframe_list], dim=0)
+    w2c = torch.inverse(kf_c2w[:-2])  # the last two keyframes are always in the window
+    homo = torch.cat([pts, torch.ones_like(pts[..., :1])], -1).reshape(1, -1, 4, 1).expand(w2c.shape[0], -1, -1, -1)
+    cam = (w2c.unsqueeze(1).expand(-1, homo.shape[1], -1, -1) @ homo)[:, :, :3]
+    K = torch.tensor([[fx, .0, cx], [.0, fy, cy], [.0, .0, 1.0]], device=device)
+    cam[:, :, 0] *= -1
+    uv = K @ cam
+    zc = uv[:, :, -1:] + 1e-5
+    uv = uv[:, :, :2] / zc
+    edge = 20
+    inside = (uv[:, :, 0] < W - edge) * (uv[:, :, 0] > edge) * (uv[:, :, 1] < H - edge) * (uv[:, :, 1] > edge)
+    inside = (inside & (zc[:, :, 0] < 0)).squeeze(-1)
+    frac = inside.sum(dim=1) / uv.shape[1]
+    sel = torch.nonzero(frac).squeeze(-1)
+    sel = sel[torch.randperm(sel.shape[0])[:num_keyframes]]
+    return list(sel.cpu().numpy())
+
+
+def _mapper_state(mp, n_rays, b):
+    st = getattr(mp, "_b200", None)
+    rnd = mp.renderer
+    S = rnd.n_stratified + rnd.n_importance
+    if st is None or not st["ws"].fits(n_rays, S, b):
+        cam = make_camera(mp.H, mp.W, mp.fx, mp.fy, mp.cx, mp.cy)
+        rc = make_cfg(rnd.n_stratified, rnd.n_importance, mp.truncation,
+                      (mp.w_sdf_fs, mp.w_sdf_center, mp.w_sdf_tail, mp.w_depth, mp.w_color))
+        st = {"ws": Workspace(mp.device, max(n_rays, mp.mapping_pixels), S, max(32, b)),
+              "sc": StepCfg(cam, rc, bool(rnd.perturb))}
+        mp._b200 = st
+    return st
+
+
+def optimize_mapping(self, iters, lr_factor, idx, cur_gt_color, cur_gt_depth, gt_cur_c2w, keyframe_dict,
+                     keyframe_list, cur_c2w):
+    """Mapping iterations over a window of keyframes (reference Mapper.optimize_mapping, Mapper.py:211-364).
+    Returns the (possibly jointly optimised) cur_c2w."""
+    all_planes = (self.planes_xy, self.planes_xz, self.planes_yz, self.c_planes_xy, self.c_planes_xz, self.c_planes_yz)
+    cfg, device = self.cfg, self.device
+    # ---- window selection, as the reference (Mapper.py:235-247)
+    if len(keyframe_dict) == 0:
+        optimize_frame: List[int] = []
+    elif self.keyframe_selection_method == 'global':
+        optimize_frame = random_select(len(self.keyframe_dict) - 2, self.mapping_window_size - 1)
+    elif self.keyframe_selection_method == 'overlap':
+        optimize_frame = self.keyframe_selection_overlap(cur_gt_color, cur_gt_depth, cur_c2w,
+                                                         self.mapping_window_size - 1)
+    if len(keyframe_list) > 1:
+        optimize_frame = sorted(optimize_frame + [len(keyframe_list) - 1] + [len(keyframe_list) - 2])
+    optimize_frame += [-1]
+    b = len(optimize_frame)
+    # ---- stage the window (Mapper.py:268-286)
+    gt_depths = torch.stack([cur_gt_depth if f == -1 else keyframe_dict[f]['depth'].to(device)
+                             for f in optimize_frame], dim=0).contiguous()
+    gt_colors = torch.stack([cur_gt_color if f == -1 else keyframe_dict[f]['color'].to(device)
+                             for f in optimize_frame], dim=0).contiguous()
+    c2ws = torch.stack([cur_c2w if f == -1 else keyframe_dict[f]['est_c2w'] for f in optimize_frame], dim=0)
+    st = _mapper_state(self, (self.mapping_pixels // b) * b, b)
+    store = synced_store(all_planes, self.decoders, self.bound)
+    lr = cfg['mapping']['lr']
+    c2ws_new = map_window(store, st["ws"], st["sc"], c2ws, gt_colors, gt_depths, self.mapping_pixels, iters,
+                          lr['decoders_lr'] * lr_factor, lr['planes_lr'] * lr_factor, lr['c_planes_lr'] * lr_factor,
+                          bool(self.joint_opt), self.joint_opt_cam_lr, draws=getattr(self, "draws", None),
+                          strict_rng=getattr(self, "strict_rng", _strict_default()),
+                          losses=getattr(self, "loss_log", None))
+    # ---- write the map back into the storage ESLAM owns (shared with the tracker process)
+    store.push_planes(all_planes)
+    store.push_decoders(self.decoders)
+    store._sig = store.signature(all_planes, decoder_tensors(self.decoders))
+    if self.joint_opt:
+        k = 0
+        for f in optimize_frame[1:]:
+            if f != -1:
+                keyframe_dict[f]['est_c2w'] = c2ws_new[1 + k].clone()
+                k += 1
+            else:
+                cur_c2w = c2ws_new[-1].clone()
+    return cur_c2w
+
+
+class MapperStep:
+    """Standalone holder of exactly the attributes `optimize_mapping` reads (tests, bench)."""
+
+    def __init__(self, cfg, renderer, decoders, all_planes, bound, cam, device, estimate_c2w_list=None):
+        (self.planes_xy, self.planes_xz, self.planes_yz, self.c_planes_xy, self.c_planes_xz, self.c_planes_yz) = all_planes
+        self.cfg, self.renderer, self.decoders, self.bound, self.device = cfg, renderer, decoders, bound, device
+        self.H, self.W, self.fx, self.fy, self.cx, self.cy = cam
+        m = cfg['mapping']
+        self.truncation = cfg['model']['truncation']
+        self.w_sdf_fs, self.w_sdf_center, self.w_sdf_tail = m['w_sdf_fs'], m['w_sdf_center'], m['w_sdf_tail']
+        self.w_depth, self.w_color = m['w_depth'], m['w_color']
+        self.mapping_pixels = m['pixels']
+        self.mapping_window_size = m['mapping_window_size']
+        self.keyframe_selection_method = m['keyframe_selection_method']
+        self.joint_opt = False
+        self.joint_opt_cam_lr = m['joint_opt_cam_lr']
+        self.keyframe_dict: list = []
+        self.keyframe_list: list = []
+        self.estimate_c2w_list = estimate_c2w_list
+
+    optimize_mapping = optimize_mapping
+    keyframe_selection_overlap = keyframe_selection_overlap

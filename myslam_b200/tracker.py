@@ -1,0 +1,117 @@
+"""Drop-in for the hot half of `src/Tracker.py` (reference lines 114-210): `optimize_tracking`
+with the reference's signature, bound onto the reference's `Tracker` (or used through
+`TrackerStep` standalone), plus `track_frame`, the whole per-frame camera loop
+(Tracker.py:291-309) with the Adam step fused on the device.
+"""
+from __future__ import annotations
+
+import os
+from typing import Optional
+
+import torch
+
+from .common import cam_pose_to_matrix
+from .decoders import synced_store
+from .hotpath import StepCfg, Workspace, make_camera, tracking_iteration
+from .renderer import make_cfg
+
+
+def _strict_default() -> bool:
+    return os.environ.get("ESLAM_B200_STRICT_RNG", "0") == "1"
+
+
+def _tracker_state(trk, batch_size):
+    """Workspace + step configuration cached on the tracker object (built from the attributes the
+    reference's Tracker.__init__ sets, Tracker.py:44-112)."""
+    st = getattr(trk, "_b200", None)
+    rnd = trk.renderer
+    S = rnd.n_stratified + rnd.n_importance
+    if st is None or not st["ws"].fits(batch_size, S, 1):
+        cam = make_camera(trk.H, trk.W, trk.fx, trk.fy, trk.cx, trk.cy, trk.ignore_edge_H, trk.H - trk.ignore_edge_H,
+                          trk.ignore_edge_W, trk.W - trk.ignore_edge_W)
+        rc = make_cfg(rnd.n_stratified, rnd.n_importance, trk.truncation,
+                      (trk.w_sdf_fs, trk.w_sdf_center, trk.w_sdf_tail, trk.w_depth, trk.w_color))
+        st = {"ws": Workspace(trk.device, batch_size, S, 1), "sc": StepCfg(cam, rc, bool(rnd.perturb)),
+              "pulled_idx": None}
+        trk._b200 = st
+    return st
+
+
+def _tracker_store(trk, st):
+    all_planes = (trk.planes_xy, trk.planes_xz, trk.planes_yz, trk.c_planes_xy, trk.c_planes_xz, trk.c_planes_yz)
+    store = synced_store(all_planes, trk.decoders, trk.bound)
+    # the planes alias memory another PROCESS (the mapper) writes (Tracker.py:222-232): version counters
+    # cannot see that, so re-import whenever the tracker refreshed its parameters from the mapper
+    pm = getattr(trk, "prev_mapping_idx", None)
+    pm = int(pm) if pm is not None else None
+    if st["pulled_idx"] != pm:
+        store.pull_planes(all_planes)
+        st["pulled_idx"] = pm
+    return store
+
+
+def optimize_tracking(self, cam_pose, gt_color, gt_depth, batch_size, optimizer):
+    """One iteration of camera tracking (reference Tracker.optimize_tracking, Tracker.py:150-210):
+    sample pixels, render, losses, backward to the 7-dof pose, step the caller's optimizer.
+    Returns the loss as a python float."""
+    st = _tracker_state(self, batch_size)
+    store = _tracker_store(self, st)
+    ws = st["ws"]
+    pose7 = cam_pose.detach().float().contiguous()
+    tracking_iteration(ws, store, st["sc"], pose7, gt_color, gt_depth, batch_size,
+                       draws=getattr(self, "draws", None), strict_rng=getattr(self, "strict_rng", _strict_default()))
+    optimizer.zero_grad()
+    cam_pose.backward(ws.grad7[0:1].clone())
+    optimizer.step()
+    return ws.loss_acc[5].item()
+
+
+def track_frame(self, init_pose, gt_color, gt_depth, iters=None, batch_size=None, lr_T=None, lr_R=None):
+    """The camera loop of Tracker.run for one frame (Tracker.py:291-309) without leaving the device:
+    `iters` iterations with the fused Adam(betas=(0.5,0.999)) on (R,T); returns
+    (candidate_pose[1,7] = pose before the lowest-loss step, losses[iters] float64 tensor).
+    One host sync at the end instead of one per iteration."""
+    iters = self.num_cam_iters if iters is None else iters
+    batch_size = self.tracking_pixels if batch_size is None else batch_size
+    lr_T = self.cam_lr_T if lr_T is None else lr_T
+    lr_R = self.cam_lr_R if lr_R is None else lr_R
+    st = _tracker_state(self, batch_size)
+    store = _tracker_store(self, st)
+    ws = st["ws"]
+    pose = init_pose.detach().float().contiguous().clone()
+    ws.pose_m.zero_()
+    ws.pose_v.zero_()
+    dev = ws.device
+    losses = torch.empty(iters, dtype=torch.float64, device=dev)
+    trace = torch.empty(iters, 7, dtype=torch.float32, device=dev)
+    for it in range(iters):
+        trace[it].copy_(pose[0])
+        tracking_iteration(ws, store, st["sc"], pose, gt_color, gt_depth, batch_size,
+                           draws=getattr(self, "draws", None),
+                           strict_rng=getattr(self, "strict_rng", _strict_default()),
+                           apply_adam={"step": it + 1, "lr_q": lr_R, "lr_t": lr_T})
+        losses[it] = ws.loss_acc[5]
+    # first minimum, NaN losses never win (`loss < current_min_loss`, Tracker.py:305)
+    best = torch.argmin(torch.nan_to_num(losses, nan=float("inf")))
+    return trace[best][None].clone(), losses, pose
+
+
+class TrackerStep:
+    """Standalone holder of exactly the attributes `optimize_tracking` reads, for use without the
+    reference's Tracker (tests, bench)."""
+
+    def __init__(self, cfg, renderer, decoders, all_planes, bound, cam, device):
+        (self.planes_xy, self.planes_xz, self.planes_yz, self.c_planes_xy, self.c_planes_xz, self.c_planes_yz) = all_planes
+        self.renderer, self.decoders, self.bound, self.device = renderer, decoders, bound, device
+        self.H, self.W, self.fx, self.fy, self.cx, self.cy = cam
+        t = cfg['tracking']
+        self.truncation = cfg['model']['truncation']
+        self.ignore_edge_H, self.ignore_edge_W = t['ignore_edge_H'], t['ignore_edge_W']
+        self.w_sdf_fs, self.w_sdf_center, self.w_sdf_tail = t['w_sdf_fs'], t['w_sdf_center'], t['w_sdf_tail']
+        self.w_depth, self.w_color = t['w_depth'], t['w_color']
+        self.cam_lr_T, self.cam_lr_R = t['lr_T'], t['lr_R']
+        self.num_cam_iters, self.tracking_pixels = t['iters'], t['pixels']
+        self.prev_mapping_idx = -1
+
+    optimize_tracking = optimize_tracking
+    track_frame = track_frame

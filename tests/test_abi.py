@@ -1,0 +1,75 @@
+"""CPU: the C-ABI library loads and exports every symbol include/eslam_b200.h declares (no compute calls)."""
+import ctypes
+import os
+import re
+
+from conftest import ROOT
+
+
+def header_functions():
+    text = open(os.path.join(ROOT, "include", "eslam_b200.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(eslam_[a-z_0-9]+)\s*\(", text)))
+
+
+def test_library_exports_every_declared_symbol():
+    import myslam_b200._lib as L
+
+    lib = L.load()
+    names = header_functions()
+    assert len(names) >= 18
+    for n in names:
+        assert hasattr(lib, n), f"{n} declared in include/eslam_b200.h but not exported"
+    assert lib.eslam_abi_version() == L.ABI_VERSION
+
+
+def test_binding_covers_header_and_arity():
+    import myslam_b200._lib as L
+
+    text = open(os.path.join(ROOT, "include", "eslam_b200.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    for name in header_functions():
+        if name in ("eslam_last_error", "eslam_abi_version"):
+            continue
+        assert name in L.PROTOTYPES, f"{name} has no ctypes prototype"
+        m = re.search(name + r"\s*\((.*?)\)\s*;", text, flags=re.S)
+        n_args = len([a for a in m.group(1).split(",") if a.strip()])
+        assert n_args == len(L.PROTOTYPES[name]), (name, n_args, len(L.PROTOTYPES[name]))
+
+
+def test_struct_layouts_match_header():
+    import myslam_b200._lib as L
+
+    assert ctypes.sizeof(L.Plane) == 16
+    assert ctypes.sizeof(L.FieldDesc) == 12 * 16 + 8 + 8 + 24
+    assert ctypes.sizeof(L.Camera) == 40
+    assert ctypes.sizeof(L.RenderCfg) == 8 + 6 * 8
+    assert L.DEC_FLOATS % 4 == 0 and L.DEC_BETA < L.DEC_FLOATS
+
+
+def test_missing_library_fails_loudly(monkeypatch):
+    import myslam_b200._lib as L
+
+    monkeypatch.setattr(L, "_lib", None)
+    monkeypatch.setattr(L, "LIB_PATH", "/nonexistent/libeslam_b200.so")
+    try:
+        L.load()
+    except RuntimeError as e:
+        assert "no CPU or PyTorch fallback" in str(e)
+    else:
+        raise AssertionError("load() must raise when the library is missing")
+
+
+def test_cpu_tensors_are_rejected():
+    import torch
+    import myslam_b200 as M
+
+    planes = tuple([torch.zeros(1, 32, 4, 4), torch.zeros(1, 32, 8, 8)] for _ in range(6))
+    dec = M.Decoders()
+    dec.bound = torch.tensor([[0., 1.], [0., 1.], [0., 1.]])
+    try:
+        dec(torch.zeros(5, 3), planes)
+    except RuntimeError as e:
+        assert "CUDA" in str(e)
+    else:
+        raise AssertionError("CPU tensors must be rejected: there is no CPU path")

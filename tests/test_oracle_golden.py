@@ -1,0 +1,117 @@
+"""CPU: the oracle replays the golden vectors produced by the unmodified reference
+(tests/golden/make_golden.py) -- this is what pins the oracle when /root/reference is not around."""
+import numpy as np
+import torch
+
+import eslam_oracle as O
+from conftest import GOLDEN_CAM, TRUNC, golden_field, load_npz, recorded_draws, rel_err
+
+CAM = O.Camera(*GOLDEN_CAM)
+RC = O.RenderCfg(32, 8, TRUNC)
+
+
+def test_pose_conversions_golden():
+    d = load_npz("pose.npz")
+    poses = torch.from_numpy(d["poses"])
+    M = O.cam_pose_to_matrix(poses)
+    assert torch.equal(M, torch.from_numpy(d["mats"]))
+    assert torch.equal(O.matrix_to_cam_pose(M), torch.from_numpy(d["back"]))
+
+
+def test_quaternion_against_scipy():
+    from scipy.spatial.transform import Rotation
+
+    g = torch.Generator().manual_seed(5)
+    q = torch.randn(200, 4, generator=g) * 3.7
+    R = O.quaternion_to_matrix(q)
+    Rs = Rotation.from_quat(q[:, [1, 2, 3, 0]].numpy()).as_matrix()
+    assert rel_err(R, torch.from_numpy(Rs).float()) < 2e-6
+    back = O.matrix_to_quaternion(R)
+    qn = q / q.norm(dim=-1, keepdim=True)
+    sign = torch.sign((back * qn).sum(-1, keepdim=True))
+    assert rel_err(back * sign, qn) < 1e-5
+    # round trip identity
+    assert rel_err(O.quaternion_to_matrix(back), R) < 1e-5
+
+
+def test_decoders_golden():
+    fld, d = golden_field(), load_npz("decoders.npz")
+    pts = torch.from_numpy(d["pts"])
+    assert rel_err(O.decode(pts.clone(), fld), d["raw"]) < 1e-6
+    pn = O.normalize_pts(pts.clone(), fld.bound)
+    assert rel_err(O.plane_features(pn, *fld.planes[:3]), d["feat_sdf"]) < 1e-6
+
+
+def test_render_golden_forward_backward():
+    fld, d = golden_field().clone(requires_grad=True), load_npz("render.npz")
+    ro = torch.from_numpy(d["rays_o"]).requires_grad_(True)
+    rd = torch.from_numpy(d["rays_d"]).requires_grad_(True)
+    gt = torch.from_numpy(d["gt_depth"])
+    depth, rgb, sdf, z = O.render_rays(fld, ro, rd, gt, TRUNC, 32, 8, O.ReplayDraws(recorded_draws(d)))
+    has = gt > 0
+    assert torch.equal(z[has], torch.from_numpy(d["z"])[has])
+    assert rel_err(z, d["z"]) < 1e-6 and rel_err(depth, d["depth"]) < 1e-6 and rel_err(rgb, d["rgb"]) < 1e-6
+    (depth * torch.from_numpy(d["g_depth"])).sum().add((rgb * torch.from_numpy(d["g_rgb"])).sum()).add(
+        (sdf * torch.from_numpy(d["g_sdf"])).sum()).backward()
+    assert rel_err(ro.grad, d["d_rays_o"]) < 1e-5 and rel_err(rd.grad, d["d_rays_d"]) < 1e-5
+    for k, leaf in enumerate(fld.leaves()[:12]):
+        assert rel_err(leaf.grad, d[f"d_plane.{k}"]) < 1e-5
+    for name in O.DECODER_KEYS:
+        assert rel_err(fld.dec[name].grad, d[f"d_dec.{name}"]) < 1e-5
+    assert rel_err(fld.beta.grad, d["d_dec.beta"]) < 1e-5
+
+
+def test_tracking_golden():
+    fld, d = golden_field(), load_npz("tracking.npz")
+    best, final, losses = O.track_frame(fld, CAM, RC, O.TRACK_W, torch.from_numpy(d["pose0"]),
+                                        torch.from_numpy(d["gt_color"]), torch.from_numpy(d["gt_depth"]),
+                                        int(d["n_pix"]), int(d["edge_h"]), int(d["edge_w"]), int(d["iters"]),
+                                        float(d["lr_T"]), float(d["lr_R"]), O.ReplayDraws(recorded_draws(d)))
+    assert rel_err(torch.tensor(losses), d["losses"]) < 1e-6
+    assert rel_err(final, d["pose_trace"][-1:]) < 1e-6
+
+
+def test_mapping_golden():
+    fld, d = golden_field(), load_npz("mapping.npz")
+    c2ws, losses = O.map_window(fld, CAM, RC, O.MAP_W, torch.from_numpy(d["c2ws0"]), torch.from_numpy(d["gt_colors"]),
+                                torch.from_numpy(d["gt_depths"]), int(d["n_pixels"]), int(d["iters"]), 0.001, 0.005,
+                                0.005, True, 0.001, O.ReplayDraws(recorded_draws(d)))
+    assert rel_err(c2ws, d["c2ws_after"]) < 1e-6
+    names = ("xy", "xz", "yz", "c_xy", "c_xz", "c_yz")
+    for n, g in zip(names, fld.planes):
+        for s in range(2):
+            assert rel_err(g[s], d[f"after.plane.{n}.{s}"]) < 1e-6
+    for name in O.DECODER_KEYS:
+        assert rel_err(fld.dec[name], d[f"after.dec.{name}"]) < 1e-6
+    assert rel_err(fld.beta, d["after.beta"]) < 1e-6
+
+
+def test_mesh_grid_golden():
+    fld, d = golden_field(), load_npz("mesh.npz")
+    axes = O.grid_axes(d["mc_bound"], float(d["resolution"]))
+    assert [len(a) for a in axes] == list(d["n"])
+    ret = O.query_points(fld, O.grid_points(axes))
+    assert rel_err(ret[:, -1], d["sdf"]) < 1e-6 and rel_err(ret[:, :3], d["rgb"]) < 1e-6
+
+
+def test_adam_formula_matches_torch_optim():
+    g = torch.Generator().manual_seed(0)
+    p0 = torch.randn(1000, generator=g)
+    p_ref = torch.nn.Parameter(p0.clone())
+    opt = torch.optim.Adam([p_ref], lr=5e-3)
+    p, m, v = p0.clone(), torch.zeros(1000), torch.zeros(1000)
+    for step in range(1, 4):
+        grad = torch.randn(1000, generator=g) * 0.1
+        p_ref.grad = grad.clone()
+        opt.step()
+        O.adam_update(p, grad, m, v, step, 5e-3)
+    assert rel_err(p, p_ref) < 1e-6
+
+
+def test_empty_band_gives_nan_loss_but_finite_grads():
+    # mean over an empty mask is NaN in the loss value only
+    sdf = torch.zeros(4, 8, requires_grad=True)
+    z = torch.full((4, 8), 5.0)  # everything behind the surface: no front, no center samples
+    d = torch.ones(4)
+    loss = O.sdf_loss(sdf, z, d, 0.06, 10, 200, 50)
+    assert torch.isnan(loss)
