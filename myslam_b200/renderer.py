@@ -177,6 +177,10 @@ class Renderer(object):
         store = synced_store(all_planes, decoders, self.bound)
         ro = rays_o.reshape(-1, 3).float().contiguous()
         rd = rays_d.reshape(-1, 3).float().contiguous()
+        if ro.shape[0] == 0:
+            S = self.n_stratified + self.n_importance
+            z0 = lambda *shape: torch.zeros(*shape, dtype=torch.float32, device=ro.device)
+            return z0(0), z0(0, 3), z0(0, S), z0(0, S)
         with torch.no_grad():
             z = self.sample_z(store, ro.detach(), rd.detach(), gt_depth, truncation)
         dts = decoder_tensors(decoders)

@@ -96,3 +96,10 @@ def base_cfg(n_strat=32, n_imp=8, trunc=TRUNC):
                     "w_sdf_tail": 10, "w_depth": 0.1, "w_color": 5,
                     "lr": {"decoders_lr": 0.001, "planes_lr": 0.005, "c_planes_lr": 0.005}},
     }
+
+
+def arena_index(k):
+    """Index in the oracle's leaf order ([xy_c, xy_f, xz_c, xz_f, ...], group-major) -> arena plane slot."""
+    from myslam_b200.field import arena_slot
+
+    return arena_slot(k // 2, k % 2)

@@ -6,7 +6,7 @@ import pytest
 import torch
 
 import eslam_oracle as O
-from conftest import (GOLDEN_CAM, TRUNC, SimpleEslam, base_cfg, golden_field, load_npz, recorded_draws, rel_err,
+from conftest import (GOLDEN_CAM, TRUNC, SimpleEslam, arena_index, base_cfg, golden_field, load_npz, recorded_draws, rel_err,
                       to_device_scene)
 
 pytestmark = pytest.mark.gpu
@@ -70,8 +70,9 @@ def test_decoders_backward_vs_oracle():
     (dec(p_c, planes) * gr.to(DEV)).sum().backward()
     assert rel_err(p_c.grad, p_o.grad) < TOL_GRAD
     from myslam_b200.field import flatten_planes
-    for k, (a, b) in enumerate(zip(flatten_planes(planes), f2.leaves()[:12])):
-        assert rel_err(a.grad, b.grad) < TOL_GRAD, f"plane {k}"
+    flat = flatten_planes(planes)
+    for k, b in enumerate(f2.leaves()[:12]):
+        assert rel_err(flat[arena_index(k)].grad, b.grad) < TOL_GRAD, f"plane {k}"
     named = dict(dec.named_parameters())
     for name in O.DECODER_KEYS:
         assert rel_err(named[name].grad, f2.dec[name].grad) < TOL_GRAD, name
@@ -98,8 +99,9 @@ def test_render_batch_ray_golden():
         + (sdf * torch.from_numpy(d["g_sdf"]).to(DEV)).sum()
     loss.backward()
     assert rel_err(ro.grad, d["d_rays_o"]) < TOL_GRAD and rel_err(rd.grad, d["d_rays_d"]) < TOL_GRAD
-    for k, p in enumerate(flatten_planes(planes)):
-        assert rel_err(p.grad, d[f"d_plane.{k}"]) < TOL_GRAD, f"plane {k}"
+    flat = flatten_planes(planes)
+    for k in range(12):
+        assert rel_err(flat[arena_index(k)].grad, d[f"d_plane.{k}"]) < TOL_GRAD, f"plane {k}"
     named = dict(dec.named_parameters())
     for name in list(O.DECODER_KEYS) + ["beta"]:
         assert rel_err(named[name].grad, d[f"d_dec.{name}"]) < TOL_GRAD, name
@@ -245,12 +247,13 @@ def test_track_mask_median_rule():
         cnt[0] = R
         rm = torch.zeros(R, dtype=torch.uint8, device=DEV)
         scratch = torch.zeros(R + 1, device=DEV)
-        call("eslam_track_mask", ptr(gt.to(DEV)), ptr(dep.to(DEV)), ptr(band.to(DEV)), R, ptr(cnt), ptr(rm),
-             ptr(scratch), stream())
-        assert scratch[R].item() == med.item(), f"R={R}"
-        assert torch.equal(rm.cpu().bool(), mask)
+        gt_d, dep_d, band_d = gt.to(DEV), dep.to(DEV), band.to(DEV)  # keep alive: ptr() does not hold a reference
+        call("eslam_track_mask", ptr(gt_d), ptr(dep_d), ptr(band_d), R, ptr(cnt), ptr(rm), ptr(scratch), stream())
+        torch.cuda.synchronize()
+        assert scratch[R].item() == med.item(), f"R={R}: median {scratch[R].item()} vs {med.item()}"
+        assert torch.equal(rm.cpu().bool(), mask), f"R={R}: mask differs in {(rm.cpu().bool() != mask).sum()} rays"
         exp = [int(mask.sum())] + [int(band[mask][:, k].long().sum()) for k in range(3)]
-        assert cnt[2:6].tolist() == exp
+        assert cnt[2:6].tolist() == exp, f"R={R}: {cnt.tolist()} vs {exp}"
 
 
 # ------------------------------------------------------------------------------------------- mapping
@@ -295,7 +298,7 @@ def test_mapping_iteration_gradients_golden():
     assert rel_err(ws.z[:R], zg) < TOL_VAL
     assert abs(ws.loss_acc[5].item() - float(d["it0_loss"])) / abs(float(d["it0_loss"])) < TOL_VAL
     for k in range(12):
-        assert rel_err(store.export_plane(k, store.grad), d[f"it0_d_plane.{k}"]) < TOL_GRAD, f"plane {k}"
+        assert rel_err(store.export_plane(arena_index(k), store.grad), d[f"it0_d_plane.{k}"]) < TOL_GRAD, f"plane {k}"
     gdec = store.dec_grad_dict(store.grad)
     for name in O.DECODER_KEYS:
         assert rel_err(gdec[name].reshape(d[f"it0_d_dec.{name}"].shape), d[f"it0_d_dec.{name}"]) < TOL_GRAD, name
@@ -373,7 +376,8 @@ def test_grid_sdf_golden():
     assert torch.equal(sdf.cpu() == -1, out)
     # sharded query == whole query
     n = sdf.numel()
-    a, b = query_grid_sdf(planes, dec, axes, 0, n // 3), query_grid_sdf(planes, dec, axes, n // 3, n - n // 3)
+    a = query_grid_sdf(planes, dec, axes, start=0, count=n // 3)
+    b = query_grid_sdf(planes, dec, axes, start=n // 3, count=n - n // 3)
     assert torch.equal(torch.cat([a, b]), sdf)
     pts = O.grid_points(O.grid_axes(d["mc_bound"], float(d["resolution"]))).to(DEV)
     raw = eval_points(pts, planes, dec)
