@@ -322,7 +322,7 @@ static int launch_bwd(const BwdArgs& a, int n_rays, cudaStream_t st) {
     configured = true;
   }
   const int rpb = MODE == 2 ? NP : ((NP / a.S) < 16 ? (NP / a.S) : 16);
-  k_render_bwd<MODE, GF, GR><<<(n_rays + rpb - 1) / rpb, NP, bytes, st>>>(a);
+  k_render_bwd<MODE, GF, GR><<<(n_rays + rpb - 1) / rpb, NT_BWD, bytes, st>>>(a);
   return (int)cudaGetLastError();
 }
 

@@ -16,6 +16,8 @@ struct SmemFwd {
   float one[NP], w[NP], z[NP], c[3][NP];
 };
 
+constexpr int NT_BWD = 256;  // threads of the backward kernel: threads 0-127 own the sdf decoder, 128-255 the rgb one
+
 template <bool GF>
 struct SmemBwd {
   float4 F0[NP * 16];  // sdf features, later d loss / d sdf features
@@ -25,14 +27,14 @@ struct SmemBwd {
   float act0[GF ? NP * 20 : 4];  // activation / gradient staging for the weight-gradient products
   float act1[GF ? NP * 20 : 4];
   float one[NP], w[NP], z[NP], c[3][NP], gww[NP];
-  float gp[3][NP];     // d loss / d normalised coordinate
+  float gp[2][3][NP];  // d loss / d normalised coordinate, per decoder half
   float rayv[4][16];   // per ray: rendered depth, r, g, b
   float rayg[4][16];   // per ray: upstream g_depth, g_rgb
   float rayd[16];      // per ray gt depth
   int raym[16];        // per ray loss-mask flag
   float rayod[6][16];  // per ray d loss / d (o, d)
-  float red[NWARP];
-  double redd[NWARP * 5];
+  float red[NT_BWD / 32];
+  double redd[(NT_BWD / 32) * 5];
 };
 
 // ---------------------------------------------------------------------------------------------------
@@ -59,8 +61,9 @@ __device__ __forceinline__ void write_axis_setups(const FieldK& fk, int g0, cons
 // gather layout: fill the feature tile of decoder `field` for all NP slots of this CTA
 template <int AXBASE>
 __device__ __forceinline__ void gather_tile(const FieldK& fk, int field, const float4* __restrict__ arena4,
-                                            const int (*ax_i)[NP], const float (*ax_f)[NP], float4* F, int n_valid) {
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+                                            const int (*ax_i)[NP], const float (*ax_f)[NP], float4* F, int n_valid,
+                                            int tid = threadIdx.x) {
+  const int warp = tid >> 5, lane = tid & 31;
   const int grp = lane >> 3, sub = lane & 7;
 #pragma unroll 1
   for (int it = 0; it < 8; ++it) {
@@ -290,19 +293,22 @@ struct BwdArgs {
   float* pose_grad;
 };
 
-// weight gradients of one decoder, accumulated into the gradient arena.  Point layout in, products over the
-// NP points of the tile with thread-owned outputs.
+// weight gradients of one decoder, accumulated into the gradient arena.  The 128 threads that own the decoder
+// (`owner`) stage their activations / gradients; all NT_BWD threads then form the products over the NP points
+// of the tile with thread-owned outputs.  Contains __syncthreads: call from uniform control flow.
 template <int W1, int B1, int W2, int B2, int W3, int B3, int NOUT>
-__device__ __forceinline__ void weight_grads(float* act0, float* act1, const float4* F, float* gdec,
+__device__ __forceinline__ void weight_grads(float* act0, float* act1, const float4* F, float* gdec, bool owner, int q,
                                              const float (&h1)[16], const float (&h2)[16], const float (&ga1)[16],
-                                             const float (&ga2)[16], const float (&gout)[NOUT]) {
+                                             const float (&ga2)[16], const float (&gout)[3]) {
   const int t = threadIdx.x;
-  float4* a0 = reinterpret_cast<float4*>(act0 + t * 20);
-  float4* a1 = reinterpret_cast<float4*>(act1 + t * 20);
+  float4* a0 = reinterpret_cast<float4*>(act0 + q * 20);
+  float4* a1 = reinterpret_cast<float4*>(act1 + q * 20);
   // --- output layer: dW3[o][i] = sum_q gout[o] h2[i]
+  if (owner) {
 #pragma unroll
-  for (int v = 0; v < 4; ++v) a0[v] = make_float4(h2[v * 4], h2[v * 4 + 1], h2[v * 4 + 2], h2[v * 4 + 3]);
-  a1[0] = make_float4(gout[0], NOUT > 1 ? gout[NOUT > 1 ? 1 : 0] : 0.f, NOUT > 2 ? gout[NOUT > 2 ? 2 : 0] : 0.f, 0.f);
+    for (int v = 0; v < 4; ++v) a0[v] = make_float4(h2[v * 4], h2[v * 4 + 1], h2[v * 4 + 2], h2[v * 4 + 3]);
+    a1[0] = make_float4(gout[0], gout[1], gout[2], 0.f);
+  }
   __syncthreads();
   if (t < NOUT * 16 + NOUT) {
     const bool bias = t >= NOUT * 16;
@@ -313,52 +319,49 @@ __device__ __forceinline__ void weight_grads(float* act0, float* act1, const flo
   }
   __syncthreads();
   // --- hidden layer: dW2[j][i] = sum_q ga2[j] h1[i]
+  if (owner) {
 #pragma unroll
-  for (int v = 0; v < 4; ++v) {
-    a0[v] = make_float4(h1[v * 4], h1[v * 4 + 1], h1[v * 4 + 2], h1[v * 4 + 3]);
-    a1[v] = make_float4(ga2[v * 4], ga2[v * 4 + 1], ga2[v * 4 + 2], ga2[v * 4 + 3]);
+    for (int v = 0; v < 4; ++v) {
+      a0[v] = make_float4(h1[v * 4], h1[v * 4 + 1], h1[v * 4 + 2], h1[v * 4 + 3]);
+      a1[v] = make_float4(ga2[v * 4], ga2[v * 4 + 1], ga2[v * 4 + 2], ga2[v * 4 + 3]);
+    }
   }
   __syncthreads();
   {
-    const int i = t & 15, j0 = (t >> 4) * 2;
-    float acc0 = 0.f, acc1 = 0.f, accb = 0.f;
-    for (int qq = 0; qq < NP; ++qq) {
-      const float h = act0[qq * 20 + i];
-      acc0 = fmaf(act1[qq * 20 + j0], h, acc0);
-      acc1 = fmaf(act1[qq * 20 + j0 + 1], h, acc1);
-    }
-    atomicAdd(gdec + W2 + j0 * 16 + i, acc0);
-    atomicAdd(gdec + W2 + (j0 + 1) * 16 + i, acc1);
+    const int i = t & 15, j = t >> 4;  // 256 outputs, one per thread
+    float acc = 0.f;
+#pragma unroll 4
+    for (int qq = 0; qq < NP; ++qq) acc = fmaf(act1[qq * 20 + j], act0[qq * 20 + i], acc);
+    atomicAdd(gdec + W2 + j * 16 + i, acc);
     if (t < 16) {
+      float accb = 0.f;
       for (int qq = 0; qq < NP; ++qq) accb += act1[qq * 20 + t];
       atomicAdd(gdec + B2 + t, accb);
     }
   }
   __syncthreads();
   // --- input layer: dW1[j][c] = sum_q ga1[j] F[q][c]
+  if (owner) {
 #pragma unroll
-  for (int v = 0; v < 4; ++v) a1[v] = make_float4(ga1[v * 4], ga1[v * 4 + 1], ga1[v * 4 + 2], ga1[v * 4 + 3]);
+    for (int v = 0; v < 4; ++v) a1[v] = make_float4(ga1[v * 4], ga1[v * 4 + 1], ga1[v * 4 + 2], ga1[v * 4 + 3]);
+  }
   __syncthreads();
   {
-    const int c = t & 63, j0 = (t >> 6) * 8;
-    float acc[8];
-#pragma unroll
-    for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+    const int c = t & 63, j0 = (t >> 6) * 4;  // 1024 outputs, four per thread
+    float acc0 = 0.f, acc1 = 0.f, acc2 = 0.f, acc3 = 0.f;
+#pragma unroll 4
     for (int qq = 0; qq < NP; ++qq) {
       const float f = f_scalar(F, qq, c);
       const float4 g0 = *reinterpret_cast<const float4*>(act1 + qq * 20 + j0);
-      const float4 g1 = *reinterpret_cast<const float4*>(act1 + qq * 20 + j0 + 4);
-      acc[0] = fmaf(g0.x, f, acc[0]);
-      acc[1] = fmaf(g0.y, f, acc[1]);
-      acc[2] = fmaf(g0.z, f, acc[2]);
-      acc[3] = fmaf(g0.w, f, acc[3]);
-      acc[4] = fmaf(g1.x, f, acc[4]);
-      acc[5] = fmaf(g1.y, f, acc[5]);
-      acc[6] = fmaf(g1.z, f, acc[6]);
-      acc[7] = fmaf(g1.w, f, acc[7]);
+      acc0 = fmaf(g0.x, f, acc0);
+      acc1 = fmaf(g0.y, f, acc1);
+      acc2 = fmaf(g0.z, f, acc2);
+      acc3 = fmaf(g0.w, f, acc3);
     }
-#pragma unroll
-    for (int j = 0; j < 8; ++j) atomicAdd(gdec + W1 + (j0 + j) * 64 + c, acc[j]);
+    atomicAdd(gdec + W1 + (j0 + 0) * 64 + c, acc0);
+    atomicAdd(gdec + W1 + (j0 + 1) * 64 + c, acc1);
+    atomicAdd(gdec + W1 + (j0 + 2) * 64 + c, acc2);
+    atomicAdd(gdec + W1 + (j0 + 3) * 64 + c, acc3);
     if (t < 16) {
       float accb = 0.f;
       for (int qq = 0; qq < NP; ++qq) accb += act1[qq * 20 + t];
@@ -408,8 +411,12 @@ __device__ __forceinline__ void scatter_point(const FieldK& fk, int field, const
 // MODE 2 (POINTS): S == 1, "rays" are plain points (rays_o = points, rays_d unused) and the upstream gradient
 //         is g_raw[N][4] in g_sdf (autograd through Decoders.forward); g_rays_o receives d loss / d points.
 // GF: gradients for planes + decoders (+beta) into grad_arena.  GR: gradients for rays / points / poses.
+//
+// One CTA = NP points (whole rays) and NT_BWD = 2*NP threads: threads [0,NP) own the sdf decoder of point
+// q = tid, threads [NP,2NP) the rgb decoder of point q = tid-NP, so both decoders' gathers, MLPs and scatters
+// run side by side and every thread carries one decoder's activations only.
 template <int MODE, bool GF, bool GR>
-__global__ void __launch_bounds__(NP, 2) k_render_bwd(const __grid_constant__ BwdArgs a) {
+__global__ void __launch_bounds__(NT_BWD, 2) k_render_bwd(const __grid_constant__ BwdArgs a) {
   constexpr bool FUSED = MODE == 1;
   constexpr bool POINTS = MODE == 2;
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -421,14 +428,16 @@ __global__ void __launch_bounds__(NP, 2) k_render_bwd(const __grid_constant__ Bw
   if (ray0 >= R) return;
   const int rays_here = min(RPB, R - ray0);
   const int n_valid = rays_here * S;
-  const int q = threadIdx.x;
-  const int warp = q >> 5, lane = q & 31;
+  const int tid = threadIdx.x;
+  const int half = tid >> 7;  // 0: sdf decoder, 1: rgb decoder (warp-uniform)
+  const int q = tid & (NP - 1);
+  const int warp = tid >> 5, lane = tid & 31;
   const bool valid = q < n_valid;
   const int rl = valid ? q / S : 0;
   const int k = q - rl * S;
   const int ray = ray0 + rl;
 
-  // ---- P0/P1: points, normalised coordinates, axis set-ups
+  // ---- P0/P1: points, normalised coordinates, axis set-ups of this half's two resolution groups
   float pn[3] = {0.f, 0.f, 0.f}, zk = 0.f;
   if (valid) {
     zk = POINTS ? 0.f : a.z[(long long)ray * S + k];
@@ -439,44 +448,53 @@ __global__ void __launch_bounds__(NP, 2) k_render_bwd(const __grid_constant__ Bw
       pn[c] = normalize_axis(p, a.fk.lo[c], a.fk.hi[c]);
     }
   }
-  write_axis_setups<4>(a.fk, 0, pn, sm.ax_i, sm.ax_f, q);
-#pragma unroll
-  for (int c = 0; c < 3; ++c) sm.gp[c][q] = 0.f;
+  write_axis_setups<2>(a.fk, 2 * half, pn, sm.ax_i + 6 * half, sm.ax_f + 6 * half, q);
   __syncthreads();
-  // ---- P2: gather both decoders' features
-  gather_tile<0>(a.fk, 0, a.arena4, sm.ax_i, sm.ax_f, sm.F0, n_valid);
-  gather_tile<6>(a.fk, 1, a.arena4, sm.ax_i, sm.ax_f, sm.F1, n_valid);
+  // ---- P2: gather this half's decoder features
+  float4* Fh = half ? sm.F1 : sm.F0;
+  if (half == 0)
+    gather_tile<0>(a.fk, 0, a.arena4, sm.ax_i, sm.ax_f, sm.F0, n_valid, q);
+  else
+    gather_tile<6>(a.fk, 1, a.arena4, sm.ax_i, sm.ax_f, sm.F1, n_valid, q);
   __syncthreads();
-  // ---- P3: MLP forward
-  float h1s[16], h2s[16], os[1], h1c[16], h2c[16], oc[3];
-  mlp_forward<S_W1, S_B1, S_W2, S_B2, S_W3, S_B3, 1>(sm.F0, q, h1s, h2s, os);
-  mlp_forward<C_W1, C_B1, C_W2, C_B2, C_W3, C_B3, 3>(sm.F1, q, h1c, h2c, oc);
-  const float sdf = tanhf(os[0]);
-  float rgb[3];
-#pragma unroll
-  for (int c = 0; c < 3; ++c) rgb[c] = sigmoidf_(oc[c]);
-  // ---- P4: compositing
+  // ---- P3: MLP forward of this half's decoder
+  float h1[16], h2[16], out[3] = {0.f, 0.f, 0.f};
+  float sdf = 0.f, u = 0.f, e = 0.f, alpha = 0.f, one = 1.f, rgb[3] = {0.f, 0.f, 0.f};
   const float beta = c_dec[P_BETA];
-  float u, e, alpha;
-  sdf_to_alpha(sdf, beta, u, e, alpha);
-  const float one = __fadd_rn(__fsub_rn(1.0f, alpha), 1e-10f);
-  sm.one[q] = one;
-  sm.z[q] = zk;
+  if (half == 0) {
+    float os[1];
+    mlp_forward<S_W1, S_B1, S_W2, S_B2, S_W3, S_B3, 1>(sm.F0, q, h1, h2, os);
+    sdf = tanhf(os[0]);
+    sdf_to_alpha(sdf, beta, u, e, alpha);
+    one = __fadd_rn(__fsub_rn(1.0f, alpha), 1e-10f);
+    sm.one[q] = one;
+    sm.z[q] = zk;
+  } else {
+    mlp_forward<C_W1, C_B1, C_W2, C_B2, C_W3, C_B3, 3>(sm.F1, q, h1, h2, out);
 #pragma unroll
-  for (int c = 0; c < 3; ++c) sm.c[c][q] = rgb[c];
-  __syncthreads();
-  float T = 1.0f;
-  for (int j = 0; j < k; ++j) T *= sm.one[rl * S + j];
-  const float w = valid ? alpha * T : 0.f;
-  sm.w[q] = w;
-  __syncthreads();
-  if (!POINTS && valid && k < 4) {
-    const float* v = (k == 0) ? sm.z : sm.c[k - 1];
-    float acc = 0.f;
-    for (int j = 0; j < S; ++j) acc = fmaf(sm.w[rl * S + j], v[rl * S + j], acc);
-    sm.rayv[k][rl] = acc;
+    for (int c = 0; c < 3; ++c) {
+      rgb[c] = sigmoidf_(out[c]);
+      sm.c[c][q] = rgb[c];
+    }
   }
   __syncthreads();
+  // ---- P4: compositing (sdf half)
+  float T = 1.0f, w = 0.f;
+  if (!POINTS) {
+    if (half == 0) {
+      for (int j = 0; j < k; ++j) T *= sm.one[rl * S + j];
+      w = valid ? alpha * T : 0.f;
+      sm.w[q] = w;
+    }
+    __syncthreads();
+    if (half == 0 && valid && k < 4) {
+      const float* v = (k == 0) ? sm.z : sm.c[k - 1];
+      float acc = 0.f;
+      for (int j = 0; j < S; ++j) acc = fmaf(sm.w[rl * S + j], v[rl * S + j], acc);
+      sm.rayv[k][rl] = acc;
+    }
+    __syncthreads();
+  }
   // ---- P5: upstream gradients of depth / rgb per ray, and the loss sums
   double ls[5] = {0.0, 0.0, 0.0, 0.0, 0.0};  // fs, center, tail, depth, colour
   float inv_f = 0.f, inv_c = 0.f, inv_t = 0.f;
@@ -485,7 +503,7 @@ __global__ void __launch_bounds__(NP, 2) k_render_bwd(const __grid_constant__ Bw
     inv_f = a.w_fs / (float)a.norm[3];
     inv_c = a.w_center / (float)a.norm[4];
     inv_t = a.w_tail / (float)a.norm[5];
-    if (valid && k == 0) {
+    if (half == 0 && valid && k == 0) {
       const float d = a.gt_depth[ray];
       const int m = a.ray_mask ? (int)a.ray_mask[ray] : (d > 0.f ? 1 : 0);
       const float dr = sm.rayv[0][rl];
@@ -512,21 +530,34 @@ __global__ void __launch_bounds__(NP, 2) k_render_bwd(const __grid_constant__ Bw
       sm.raym[rl] = m;
     }
   } else if (!POINTS) {
-    if (valid && k < 4) sm.rayg[k][rl] = (k == 0) ? a.g_depth[ray] : a.g_rgb[ray * 3 + (k - 1)];
+    if (half == 0 && valid && k < 4) sm.rayg[k][rl] = (k == 0) ? a.g_depth[ray] : a.g_rgb[ray * 3 + (k - 1)];
   }
-  __syncthreads();
-  // ---- direct sdf gradient + compositing backward (point layout)
-  float g_sdf = 0.f, g_beta = 0.f, gout_s[1] = {0.f}, gout_c[3] = {0.f, 0.f, 0.f};
+  if (!POINTS) __syncthreads();
+  // ---- compositing backward -> gradient at this half's decoder outputs
+  float g_beta = 0.f, gout[3] = {0.f, 0.f, 0.f};
   if (POINTS) {
     if (valid) {
       const float* gr = a.g_sdf + (long long)ray * 4;
-      gout_s[0] = gr[3] * (1.0f - sdf * sdf);
+      if (half == 0) {
+        gout[0] = gr[3] * (1.0f - sdf * sdf);
+      } else {
 #pragma unroll
-      for (int c = 0; c < 3; ++c) gout_c[c] = gr[c] * rgb[c] * (1.0f - rgb[c]);
+        for (int c = 0; c < 3; ++c) gout[c] = gr[c] * rgb[c] * (1.0f - rgb[c]);
+      }
     }
   } else {
-    float gdir = 0.f;
-    if (valid) {
+    float gw = 0.f;
+    if (half == 0) {
+      gw = sm.rayg[0][rl] * zk + sm.rayg[1][rl] * sm.c[0][q] + sm.rayg[2][rl] * sm.c[1][q] + sm.rayg[3][rl] * sm.c[2][q];
+      sm.gww[q] = valid ? gw * w : 0.f;
+    } else if (valid) {
+      const float ww = sm.w[q];
+#pragma unroll
+      for (int c = 0; c < 3; ++c) gout[c] = sm.rayg[1 + c][rl] * ww * rgb[c] * (1.0f - rgb[c]);
+    }
+    __syncthreads();
+    if (half == 0 && valid) {
+      float gdir = 0.f;
       if (FUSED) {
         if (sm.raym[rl]) {
           const float d = sm.rayd[rl];
@@ -544,53 +575,55 @@ __global__ void __launch_bounds__(NP, 2) k_render_bwd(const __grid_constant__ Bw
       } else {
         gdir = a.g_sdf ? a.g_sdf[(long long)ray * S + k] : 0.f;
       }
-    }
-    const float gw = sm.rayg[0][rl] * zk + sm.rayg[1][rl] * rgb[0] + sm.rayg[2][rl] * rgb[1] + sm.rayg[3][rl] * rgb[2];
-    sm.gww[q] = valid ? gw * w : 0.f;
-    __syncthreads();
-    float B = 0.f;
-    if (valid)
+      float B = 0.f;
       for (int j = k + 1; j < S; ++j) B += sm.gww[rl * S + j];
-    const float g_alpha = valid ? (gw * T - B / one) : 0.f;
-    const float du = u * (1.0f - u);
-    g_sdf = gdir + g_alpha * (-beta * beta * e * du);
-    g_beta = g_alpha * e * (u - beta * sdf * du);
-    gout_s[0] = valid ? g_sdf * (1.0f - sdf * sdf) : 0.f;
-#pragma unroll
-    for (int c = 0; c < 3; ++c) gout_c[c] = valid ? sm.rayg[1 + c][rl] * w * rgb[c] * (1.0f - rgb[c]) : 0.f;
+      const float g_alpha = gw * T - B / one;
+      const float du = u * (1.0f - u);
+      const float g_sdf = gdir + g_alpha * (-beta * beta * e * du);
+      g_beta = g_alpha * e * (u - beta * sdf * du);
+      gout[0] = g_sdf * (1.0f - sdf * sdf);
+    }
   }
-  // ---- P6: MLP backward
-  float ga1s[16], ga2s[16], ga1c[16], ga2c[16];
-  mlp_backward_hidden<S_W2, S_W3, 1>(gout_s, h1s, h2s, ga1s, ga2s);
-  mlp_backward_hidden<C_W2, C_W3, 3>(gout_c, h1c, h2c, ga1c, ga2c);
+  // ---- P6: MLP backward of this half's decoder
+  float ga1[16], ga2[16];
+  if (half == 0) {
+    const float gs[1] = {gout[0]};
+    mlp_backward_hidden<S_W2, S_W3, 1>(gs, h1, h2, ga1, ga2);
+  } else {
+    mlp_backward_hidden<C_W2, C_W3, 3>(gout, h1, h2, ga1, ga2);
+  }
   if (GF) {
     float* gdec = a.grad_arena + a.fk.dec_off;
-    weight_grads<S_W1, S_B1, S_W2, S_B2, S_W3, S_B3, 1>(sm.act0, sm.act1, sm.F0, gdec, h1s, h2s, ga1s, ga2s, gout_s);
-    weight_grads<C_W1, C_B1, C_W2, C_B2, C_W3, C_B3, 3>(sm.act0, sm.act1, sm.F1, gdec, h1c, h2c, ga1c, ga2c, gout_c);
+    weight_grads<S_W1, S_B1, S_W2, S_B2, S_W3, S_B3, 1>(sm.act0, sm.act1, sm.F0, gdec, half == 0, q, h1, h2, ga1, ga2, gout);
+    weight_grads<C_W1, C_B1, C_W2, C_B2, C_W3, C_B3, 3>(sm.act0, sm.act1, sm.F1, gdec, half == 1, q, h1, h2, ga1, ga2, gout);
     const float gb = warp_sum(g_beta);
     if (lane == 0) sm.red[warp] = gb;
   }
-  mlp_backward_input<S_W1>(ga1s, sm.F0, q);
-  mlp_backward_input<C_W1>(ga1c, sm.F1, q);
+  if (half == 0)
+    mlp_backward_input<S_W1>(ga1, sm.F0, q);
+  else
+    mlp_backward_input<C_W1>(ga1, sm.F1, q);
   __syncthreads();
-  if (GF && q == 0) {
+  if (GF && tid == 0) {
     float gb = 0.f;
-    for (int i = 0; i < NWARP; ++i) gb += sm.red[i];
+    for (int i = 0; i < NP / 32; ++i) gb += sm.red[i];  // only the sdf half carries beta gradients
     atomicAdd(a.grad_arena + a.fk.dec_off + P_BETA, gb);
   }
-  // ---- P7: scatter to the planes / coordinate gradients (gather layout)
+  // ---- P7: scatter to the planes / coordinate gradients (gather layout, each half its own decoder)
   {
-    const int grp = lane >> 3, sub = lane & 7;
+    const int wl = (tid & (NP - 1)) >> 5, grp = lane >> 3, sub = lane & 7;
     float4* garena4 = reinterpret_cast<float4*>(a.grad_arena);
 #pragma unroll 1
     for (int it = 0; it < 8; ++it) {
-      const int qq = warp * 32 + it * 4 + grp;
+      const int qq = wl * 32 + it * 4 + grp;
       float gpn[3] = {0.f, 0.f, 0.f};
       if (qq < n_valid) {
-        scatter_point<GF, GR, 0>(a.fk, 0, a.arena4, garena4, sm.ax_i, sm.ax_f, qq, sub, sm.F0[f_slot(qq, sub)],
-                                 sm.F0[f_slot(qq, 8 + sub)], gpn);
-        scatter_point<GF, GR, 6>(a.fk, 1, a.arena4, garena4, sm.ax_i, sm.ax_f, qq, sub, sm.F1[f_slot(qq, sub)],
-                                 sm.F1[f_slot(qq, 8 + sub)], gpn);
+        if (half == 0)
+          scatter_point<GF, GR, 0>(a.fk, 0, a.arena4, garena4, sm.ax_i, sm.ax_f, qq, sub, sm.F0[f_slot(qq, sub)],
+                                   sm.F0[f_slot(qq, 8 + sub)], gpn);
+        else
+          scatter_point<GF, GR, 6>(a.fk, 1, a.arena4, garena4, sm.ax_i, sm.ax_f, qq, sub, sm.F1[f_slot(qq, sub)],
+                                   sm.F1[f_slot(qq, 8 + sub)], gpn);
       }
       if (GR) {
 #pragma unroll
@@ -599,21 +632,21 @@ __global__ void __launch_bounds__(NP, 2) k_render_bwd(const __grid_constant__ Bw
           v += __shfl_xor_sync(0xffffffffu, v, 1);
           v += __shfl_xor_sync(0xffffffffu, v, 2);
           v += __shfl_xor_sync(0xffffffffu, v, 4);
-          if (sub == 0) sm.gp[c][qq] = v;
+          if (sub == 0) sm.gp[half][c][qq] = v;
         }
       }
     }
   }
-  // ---- P8: ray / pose gradients
+  // ---- P8: ray / point / pose gradients
   if (GR) {
     __syncthreads();
-    for (int t = q; t < rays_here * 6; t += NP) {
+    for (int t = tid; t < rays_here * 6; t += NT_BWD) {
       const int r2 = t / 6, comp = t - r2 * 6, ax = comp % 3;
       const bool is_d = comp >= 3;
       const float scale = 2.0f / (a.fk.hi[ax] - a.fk.lo[ax]);
       float acc = 0.f;
       for (int j = 0; j < S; ++j) {
-        const float g = sm.gp[ax][r2 * S + j] * scale;
+        const float g = (sm.gp[0][ax][r2 * S + j] + sm.gp[1][ax][r2 * S + j]) * scale;
         acc += is_d ? g * sm.z[r2 * S + j] : g;
       }
       if (FUSED) {
@@ -624,7 +657,7 @@ __global__ void __launch_bounds__(NP, 2) k_render_bwd(const __grid_constant__ Bw
     }
     if (FUSED && a.pose_grad) {
       __syncthreads();
-      for (int t = q; t < rays_here * 12; t += NP) {
+      for (int t = tid; t < rays_here * 12; t += NT_BWD) {
         const int r2 = t / 12, el = t - r2 * 12, row = el >> 2, col = el & 3;
         const int slot = a.src[ray0 + r2];
         const int frame = slot / a.n_per_img;
@@ -650,12 +683,13 @@ __global__ void __launch_bounds__(NP, 2) k_render_bwd(const __grid_constant__ Bw
       if (lane == 0) sm.redd[warp * 5 + i] = v;
     }
     __syncthreads();
-    if (q < 5) {
+    if (tid < 5) {
       double v = 0.0;
-      for (int i = 0; i < NWARP; ++i) v += sm.redd[i * 5 + q];
-      atomicAdd(a.loss_acc + q, v);
+      for (int i = 0; i < NP / 32; ++i) v += sm.redd[i * 5 + tid];  // only the sdf half accumulates losses
+      atomicAdd(a.loss_acc + tid, v);
     }
   }
+  (void)Fh;
 }
 
 }  // namespace eslam
