@@ -130,6 +130,7 @@ int eslam_grid_sdf(const eslam_field_t* field_host, const float* arena, const fl
  * Outputs (capacity n_img*n_per_img rays, compacted in the reference's order):
  *   rays_o/rays_d[R][3], gt_depth[R], gt_color[R][3] f64, src[R] = original slot (frame = src / n_per_img),
  *   z[R][S] (filled for depth>0 rays), dl_list[R0] = compact index of each depth-less ray,
+ *   zord[R] = ordinal of the ray among the depth>0 kept rays (its row of u_depth) or -1,
  *   band[R][4] u8 = (#front,#center,#tail,depth>0) per ray, counters (see above; [2..5] filled with the
  *   mapper's depth>0 mask), c2w_out[n_img][16] (may be NULL).  need_depth=1 drops depth<=0 rays (tracker). */
 int eslam_sample_rays(const eslam_field_t* field_host, const eslam_camera_t* cam_host,
@@ -137,15 +138,15 @@ int eslam_sample_rays(const eslam_field_t* field_host, const eslam_camera_t* cam
                       const float* c2w, const float* poses, int pose_first, const float* depth,
                       const double* color, const float* u_depth, const float* t_uni, const float* t_surf,
                       int need_depth, float* rays_o, float* rays_d, float* gt_depth, double* gt_color,
-                      int32_t* src, float* z, int32_t* dl_list, uint8_t* band, int32_t* counters, float* c2w_out,
-                      eslam_stream_t s);
+                      int32_t* src, float* z, int32_t* dl_list, int32_t* zord, uint8_t* band, int32_t* counters,
+                      float* c2w_out, eslam_stream_t s);
 
 /* Depth-guided z_vals for an already compacted ray list with explicit gt_depth (the first half of
  * render_batch_ray when called through the reference's API, Renderer.py:88-106): fills the z rows of
  * depth>0 rays, lists the others in dl_list, counters[0]=n_rays, counters[1]=R0. */
 int eslam_depth_samples(const eslam_render_cfg_t* cfg_host, const float* gt_depth, int n_rays, const float* u_depth,
-                        const float* t_uni, const float* t_surf, float* z, int32_t* dl_list, int32_t* counters,
-                        eslam_stream_t s);
+                        const float* t_uni, const float* t_surf, float* z, int32_t* dl_list, int32_t* zord,
+                        int32_t* counters, eslam_stream_t s);
 
 /* The depth-less half of render_batch_ray's sampling (Renderer.py:108-134, common.py:41-77):
  * coarse SDF pass + inverse-cdf resampling for the rays in dl_list; fills their rows of z.

@@ -61,8 +61,8 @@ PROTOTYPES = {
     "eslam_sample_plane_feature": [_FP, _P, _P, _L, _I, _P, _P],
     "eslam_grid_sdf": [_FP, _P, _P, _P, _P, _I, _I, _I, _L, _L, _P, _P],
     "eslam_sample_rays": [_FP, _CP, _RP, _P, _I, _I, _P, _P, _I, _P, _P, _P, _P, _P, _I, _P, _P, _P, _P, _P, _P, _P,
-                          _P, _P, _P, _P],
-    "eslam_depth_samples": [_RP, _P, _I, _P, _P, _P, _P, _P, _P, _P],
+                          _P, _P, _P, _P, _P],
+    "eslam_depth_samples": [_RP, _P, _I, _P, _P, _P, _P, _P, _P, _P, _P],
     "eslam_importance_samples": [_FP, _P, _RP, _P, _P, _P, _P, _I, _P, _P, _P, _P, _P],
     "eslam_render_forward": [_FP, _P, _P, _P, _P, _I, _I, _P, _P, _P, _P, _P],
     "eslam_render_backward": [_FP, _P, _P, _P, _P, _I, _I, _P, _P, _P, _P, _P, _P, _P],

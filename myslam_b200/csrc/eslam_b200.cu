@@ -164,10 +164,11 @@ int eslam_sample_rays(const eslam_field_t* f, const eslam_camera_t* cam, const e
                       const int64_t* pix_idx, int n_img, int n_per_img, const float* c2w, const float* poses,
                       int pose_first, const float* depth, const double* color, const float* u_depth,
                       const float* t_uni, const float* t_surf, int need_depth, float* rays_o, float* rays_d,
-                      float* gt_depth, double* gt_color, int32_t* src, float* z, int32_t* dl_list, uint8_t* band,
-                      int32_t* counters, float* c2w_out, eslam_stream_t s) {
+                      float* gt_depth, double* gt_color, int32_t* src, float* z, int32_t* dl_list, int32_t* zord,
+                      uint8_t* band, int32_t* counters, float* c2w_out, eslam_stream_t s) {
   REQUIRE(f && cam && cfg && pix_idx && depth && color && t_uni && t_surf && rays_o && rays_d && gt_depth &&
-              gt_color && src && z && dl_list && band && counters && n_img > 0 && n_per_img > 0 && (c2w || poses),
+              gt_color && src && z && dl_list && zord && band && counters && n_img > 0 && n_per_img > 0 &&
+              (c2w || poses),
           "eslam_sample_rays");
   REQUIRE(c2w || pose_first == 0, "eslam_sample_rays(c2w)");
   int rc = check_samples(cfg->n_stratified, cfg->n_importance);
@@ -214,6 +215,7 @@ int eslam_sample_rays(const eslam_field_t* f, const eslam_camera_t* cam, const e
   a.src = src;
   a.z = z;
   a.dl_list = dl_list;
+  a.zord = zord;
   a.band = band;
   a.counters = counters;
   a.c2w_out = c2w_out;
@@ -221,37 +223,65 @@ int eslam_sample_rays(const eslam_field_t* f, const eslam_camera_t* cam, const e
   if (e != cudaSuccess) return fail((int)e, "eslam_sample_rays(memset)");
   const int N = n_img * n_per_img;
   k_sample_rays<<<(N + SB - 1) / SB, SB, 0, S_(s)>>>(a);
-  CHECK_LAUNCH("eslam_sample_rays");
+  CHECK_LAUNCH("eslam_sample_rays(select)");
+  RaySampleArgs b;
+  b.n_strat = k.n_strat;
+  b.n_imp = k.n_imp;
+  b.tr = k.tr;
+  b.tr15 = k.tr15;
+  b.tr3 = k.tr3;
+  b.tr04 = k.tr04;
+  b.gt_depth = gt_depth;
+  b.zord = zord;
+  b.max_rays = N;
+  b.u_depth = u_depth;
+  b.t_uni = t_uni;
+  b.t_surf = t_surf;
+  b.z = z;
+  b.band = band;
+  b.counters = counters;
+  k_ray_samples<<<(N + SB / 32 - 1) / (SB / 32), SB, 0, S_(s)>>>(b);
+  CHECK_LAUNCH("eslam_sample_rays(samples)");
   return 0;
 }
 
 int eslam_depth_samples(const eslam_render_cfg_t* cfg, const float* gt_depth, int n_rays, const float* u_depth,
-                        const float* t_uni, const float* t_surf, float* z, int32_t* dl_list, int32_t* counters,
-                        eslam_stream_t s) {
-  REQUIRE(cfg && gt_depth && t_uni && t_surf && z && dl_list && counters && n_rays >= 0, "eslam_depth_samples");
+                        const float* t_uni, const float* t_surf, float* z, int32_t* dl_list, int32_t* zord,
+                        int32_t* counters, eslam_stream_t s) {
+  REQUIRE(cfg && gt_depth && t_uni && t_surf && z && dl_list && zord && counters && n_rays >= 0,
+          "eslam_depth_samples");
   int rc = check_samples(cfg->n_stratified, cfg->n_importance);
   if (rc) return fail(rc, "eslam_depth_samples(samples)");
   cudaError_t e = cudaMemsetAsync(counters, 0, sizeof(int32_t) * ESLAM_N_COUNTERS, S_(s));
   if (e != cudaSuccess) return fail((int)e, "eslam_depth_samples(memset)");
   if (n_rays == 0) return 0;
   const CfgK k = make_cfg(cfg);
-  DepthSampleArgs a;
-  a.n_strat = k.n_strat;
-  a.n_imp = k.n_imp;
-  a.tr = k.tr;
-  a.tr15 = k.tr15;
-  a.tr3 = k.tr3;
-  a.tr04 = k.tr04;
-  a.gt_depth = gt_depth;
-  a.n_rays = n_rays;
-  a.u_depth = u_depth;
-  a.t_uni = t_uni;
-  a.t_surf = t_surf;
-  a.z = z;
-  a.dl_list = dl_list;
-  a.counters = counters;
-  k_depth_samples<<<(n_rays + SB - 1) / SB, SB, 0, S_(s)>>>(a);
-  CHECK_LAUNCH("eslam_depth_samples");
+  DepthOrdArgs o;
+  o.gt_depth = gt_depth;
+  o.n_rays = n_rays;
+  o.zord = zord;
+  o.dl_list = dl_list;
+  o.counters = counters;
+  k_depth_ordinals<<<(n_rays + SB - 1) / SB, SB, 0, S_(s)>>>(o);
+  CHECK_LAUNCH("eslam_depth_samples(ordinals)");
+  RaySampleArgs b;
+  b.n_strat = k.n_strat;
+  b.n_imp = k.n_imp;
+  b.tr = k.tr;
+  b.tr15 = k.tr15;
+  b.tr3 = k.tr3;
+  b.tr04 = k.tr04;
+  b.gt_depth = gt_depth;
+  b.zord = zord;
+  b.max_rays = n_rays;
+  b.u_depth = u_depth;
+  b.t_uni = t_uni;
+  b.t_surf = t_surf;
+  b.z = z;
+  b.band = nullptr;
+  b.counters = counters;
+  k_ray_samples<<<(n_rays + SB / 32 - 1) / (SB / 32), SB, 0, S_(s)>>>(b);
+  CHECK_LAUNCH("eslam_depth_samples(samples)");
   return 0;
 }
 

@@ -85,8 +85,9 @@ __device__ __forceinline__ float axis_grad_mult(int i0, float fr, int size) {
 __device__ __forceinline__ float4 ldg4(const float4* p) { return __ldg(p); }
 
 __device__ __forceinline__ void red_add_v4(float4* addr, float4 v) {
-  asm volatile("red.global.add.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(addr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w)
-               : "memory");
+  // no "memory" clobber: the gradient arena is never read by the kernels that reduce into it, and the clobber
+  // would pin every later corner load behind the reductions (exposing one L2 round trip per tap)
+  asm volatile("red.global.add.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(addr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w));
 }
 
 __device__ __forceinline__ float4 f4_zero() { return make_float4(0.f, 0.f, 0.f, 0.f); }

@@ -349,14 +349,21 @@ __device__ __forceinline__ void weight_grads(float* act0, float* act1, const flo
   {
     const int c = t & 63, j0 = (t >> 6) * 4;  // 1024 outputs, four per thread
     float acc0 = 0.f, acc1 = 0.f, acc2 = 0.f, acc3 = 0.f;
-#pragma unroll 4
-    for (int qq = 0; qq < NP; ++qq) {
-      const float f = f_scalar(F, qq, c);
-      const float4 g0 = *reinterpret_cast<const float4*>(act1 + qq * 20 + j0);
-      acc0 = fmaf(g0.x, f, acc0);
-      acc1 = fmaf(g0.y, f, acc1);
-      acc2 = fmaf(g0.z, f, acc2);
-      acc3 = fmaf(g0.w, f, acc3);
+    const float* Ff = reinterpret_cast<const float*>(F);
+    int off[8];  // swizzled float offset of column c within row (8m + r): depends on r only
+#pragma unroll
+    for (int r = 0; r < 8; ++r) off[r] = r * 64 + ((((c >> 2) ^ r) << 2) | (c & 3));
+#pragma unroll 2
+    for (int m = 0; m < NP / 8; ++m) {
+#pragma unroll
+      for (int r = 0; r < 8; ++r) {
+        const float f = Ff[m * 512 + off[r]];
+        const float4 g0 = *reinterpret_cast<const float4*>(act1 + (m * 8 + r) * 20 + j0);
+        acc0 = fmaf(g0.x, f, acc0);
+        acc1 = fmaf(g0.y, f, acc1);
+        acc2 = fmaf(g0.z, f, acc2);
+        acc3 = fmaf(g0.w, f, acc3);
+      }
     }
     atomicAdd(gdec + W1 + (j0 + 0) * 64 + c, acc0);
     atomicAdd(gdec + W1 + (j0 + 1) * 64 + c, acc1);
@@ -381,26 +388,46 @@ __device__ __forceinline__ void scatter_point(const FieldK& fk, int field, const
 #pragma unroll
   for (int s = 0; s < 2; ++s) {
     const float4 g4 = s ? gF : gC;
+    Tap tp[3];
+    int u0[3], v0[3];
 #pragma unroll
     for (int p = 0; p < 3; ++p) {
       const int au = AXBASE + s * 3 + pair_u(p), av = AXBASE + s * 3 + pair_v(p);
-      const PlaneK& pl = fk.pl[field * 6 + s * 3 + p];
-      const int u0 = ax_i[au][q], v0 = ax_i[av][q];
-      const Tap t = make_tap(pl, u0, ax_f[au][q], v0, ax_f[av][q], sub);
-      const float fu = t.fu, fv = t.fv;
-      if (GR) {
-        const float4 v00 = ldg4(arena4 + t.base), v01 = ldg4(arena4 + t.base + t.dx);
-        const float4 v10 = ldg4(arena4 + t.base + t.dy), v11 = ldg4(arena4 + t.base + t.dy + t.dx);
-        const float du = f4_dot(g4, f4_sub(v01, v00)) * (1.f - fv) + f4_dot(g4, f4_sub(v11, v10)) * fv;
-        const float dv = f4_dot(g4, f4_sub(v10, v00)) * (1.f - fu) + f4_dot(g4, f4_sub(v11, v01)) * fu;
-        gpn[pair_u(p)] = fmaf(du, axis_grad_mult(u0, fu, pl.W), gpn[pair_u(p)]);
-        gpn[pair_v(p)] = fmaf(dv, axis_grad_mult(v0, fv, pl.H), gpn[pair_v(p)]);
+      u0[p] = ax_i[au][q];
+      v0[p] = ax_i[av][q];
+      tp[p] = make_tap(fk.pl[field * 6 + s * 3 + p], u0[p], ax_f[au][q], v0[p], ax_f[av][q], sub);
+    }
+    if (GR) {
+      // all 12 corner loads of the scale in flight before the first use
+      float4 v[3][4];
+#pragma unroll
+      for (int p = 0; p < 3; ++p) {
+        v[p][0] = ldg4(arena4 + tp[p].base);
+        v[p][1] = ldg4(arena4 + tp[p].base + tp[p].dx);
+        v[p][2] = ldg4(arena4 + tp[p].base + tp[p].dy);
+        v[p][3] = ldg4(arena4 + tp[p].base + tp[p].dy + tp[p].dx);
       }
-      if (GF) {
-        red_add_v4(garena4 + t.base, f4_mul((1.f - fu) * (1.f - fv), g4));
-        red_add_v4(garena4 + t.base + t.dx, f4_mul(fu * (1.f - fv), g4));
-        red_add_v4(garena4 + t.base + t.dy, f4_mul((1.f - fu) * fv, g4));
-        red_add_v4(garena4 + t.base + t.dy + t.dx, f4_mul(fu * fv, g4));
+#pragma unroll
+      for (int p = 0; p < 3; ++p) {
+        const PlaneK& pl = fk.pl[field * 6 + s * 3 + p];
+        const float fu = tp[p].fu, fv = tp[p].fv;
+        // d tap/du = (v01-v00)(1-fv) + (v11-v10) fv, d tap/dv = (v10-v00)(1-fu) + (v11-v01) fu, contracted with g4
+        const float d00 = f4_dot(g4, v[p][0]), d01 = f4_dot(g4, v[p][1]);
+        const float d10 = f4_dot(g4, v[p][2]), d11 = f4_dot(g4, v[p][3]);
+        const float du = (d01 - d00) * (1.f - fv) + (d11 - d10) * fv;
+        const float dv = (d10 - d00) * (1.f - fu) + (d11 - d01) * fu;
+        gpn[pair_u(p)] = fmaf(du, axis_grad_mult(u0[p], fu, pl.W), gpn[pair_u(p)]);
+        gpn[pair_v(p)] = fmaf(dv, axis_grad_mult(v0[p], fv, pl.H), gpn[pair_v(p)]);
+      }
+    }
+    if (GF) {
+#pragma unroll
+      for (int p = 0; p < 3; ++p) {
+        const float fu = tp[p].fu, fv = tp[p].fv;
+        red_add_v4(garena4 + tp[p].base, f4_mul((1.f - fu) * (1.f - fv), g4));
+        red_add_v4(garena4 + tp[p].base + tp[p].dx, f4_mul(fu * (1.f - fv), g4));
+        red_add_v4(garena4 + tp[p].base + tp[p].dy, f4_mul((1.f - fu) * fv, g4));
+        red_add_v4(garena4 + tp[p].base + tp[p].dy + tp[p].dx, f4_mul(fu * fv, g4));
       }
     }
   }

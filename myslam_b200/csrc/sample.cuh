@@ -32,6 +32,7 @@ struct SampleArgs {
   int* src;
   float* z;
   int* dl_list;
+  int* zord;
   unsigned char* band;
   int* counters;
   float* c2w_out;
@@ -146,56 +147,84 @@ __device__ __forceinline__ void block_scan2(int f0, int f1, int& ex0, int& ex1, 
   __syncthreads();
 }
 
-// depth-guided samples of one ray with depth>0: Renderer.py:94-106 + perturbation :46-61.
-// zout may be strided global memory; returns band counts.
-__device__ __forceinline__ void depth_guided_z(float d, int n_strat, int n_imp, const float* t_uni, const float* t_surf,
-                                               float tr15, float tr3, const float* u, float* zout, float tr, float tr04,
-                                               int& nf, int& nc, int& nt) {
-  float zs[ESLAM_MAX_SAMPLES];
+// Depth-guided samples of one ray with depth>0 (Renderer.py:94-106 + perturbation :46-61), one WARP per ray:
+// lane l owns elements l and l+32 of the concatenated [free(n_strat) | surface(n_imp)] list, finds their
+// positions in the sorted order by counting (both lists are ascending, so torch.sort of the concatenation is a
+// merge; ties: free before surface), then jitters inside the midpoints' intervals and classifies the sdf band.
+// zs: this warp's 64-float shared scratch.  Returns band counts on every lane.
+__device__ __forceinline__ void depth_guided_z_warp(float d, int n_strat, int n_imp, const float* __restrict__ t_uni,
+                                                    const float* __restrict__ t_surf, float tr15, float tr3,
+                                                    bool has_u, float u_lo, float u_hi, float* __restrict__ zout,
+                                                    float tr, float tr04, float* zs, int& nf, int& nc, int& nt) {
+  const int lane = threadIdx.x & 31;
   const int S = n_strat + n_imp;
   const float d12 = __fmul_rn(1.2f, d);
   const float dsurf = __fsub_rn(d, tr15);
-  // merge of the two ascending lists == torch.sort of their concatenation (values only)
-  int ia = 0, ib = 0;
-  float va = __fmul_rn(d12, t_uni[0]);
-  float vb = __fadd_rn(dsurf, __fmul_rn(tr3, t_surf[0]));
-  for (int k = 0; k < S; ++k) {
-    const bool take_a = (ib >= n_imp) || (ia < n_strat && va <= vb);
-    if (take_a) {
-      zs[k] = va;
-      ++ia;
-      if (ia < n_strat) va = __fmul_rn(d12, t_uni[ia]);
-    } else {
-      zs[k] = vb;
-      ++ib;
-      if (ib < n_imp) vb = __fadd_rn(dsurf, __fmul_rn(tr3, t_surf[ib]));
+  float val[2];
+  bool is_free[2], live[2];
+  int idx[2];
+#pragma unroll
+  for (int h = 0; h < 2; ++h) {
+    const int e = lane + 32 * h;
+    live[h] = e < S;
+    is_free[h] = e < n_strat;
+    idx[h] = is_free[h] ? e : e - n_strat;
+    val[h] = 0.f;
+    if (live[h])
+      val[h] = is_free[h] ? __fmul_rn(d12, t_uni[idx[h]]) : __fadd_rn(dsurf, __fmul_rn(tr3, t_surf[idx[h]]));
+  }
+  int below[2] = {0, 0};  // free element: #surface < it ; surface element: filled from the ballots below
+  for (int j = 0; j < n_imp; ++j) {
+    const float sj = __fadd_rn(dsurf, __fmul_rn(tr3, t_surf[j]));
+    const unsigned b0 = __ballot_sync(0xffffffffu, live[0] && is_free[0] && val[0] <= sj);
+    const unsigned b1 = __ballot_sync(0xffffffffu, live[1] && is_free[1] && val[1] <= sj);
+    const int n_le = __popc(b0) + __popc(b1);  // #free <= surface_j
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      if (is_free[h]) {
+        below[h] += (sj < val[h]);
+      } else if (idx[h] == j) {
+        below[h] = n_le;
+      }
     }
   }
+#pragma unroll
+  for (int h = 0; h < 2; ++h)
+    if (live[h]) zs[idx[h] + below[h]] = val[h];
+  __syncwarp();
   nf = nc = nt = 0;
-  float lower = zs[0];
-  for (int k = 0; k < S; ++k) {
-    const float upper = (k < S - 1) ? __fmul_rn(0.5f, __fadd_rn(zs[k + 1], zs[k])) : zs[S - 1];
-    const float zp = u ? __fadd_rn(lower, __fmul_rn(__fsub_rn(upper, lower), u[k])) : zs[k];
-    zout[k] = zp;
-    const int b = sdf_band(zp, d, tr, tr04);
-    nf += (b == 0);
-    nc += (b == 1);
-    nt += (b == 2);
-    lower = upper;
+#pragma unroll
+  for (int h = 0; h < 2; ++h) {
+    const int k = lane + 32 * h;
+    bool f0 = false, f1 = false, f2 = false;
+    if (k < S) {
+      const float zc = zs[k];
+      const float lower = k > 0 ? __fmul_rn(0.5f, __fadd_rn(zc, zs[k - 1])) : zc;
+      const float upper = k < S - 1 ? __fmul_rn(0.5f, __fadd_rn(zs[k + 1], zc)) : zc;
+      const float zp = has_u ? __fadd_rn(lower, __fmul_rn(__fsub_rn(upper, lower), h ? u_hi : u_lo)) : zc;
+      zout[k] = zp;
+      const int b = sdf_band(zp, d, tr, tr04);
+      f0 = b == 0;
+      f1 = b == 1;
+      f2 = b == 2;
+    }
+    nf += __popc(__ballot_sync(0xffffffffu, f0));
+    nc += __popc(__ballot_sync(0xffffffffu, f1));
+    nt += __popc(__ballot_sync(0xffffffffu, f2));
   }
+  __syncwarp();
 }
 
 __global__ void __launch_bounds__(SB) k_sample_rays(const __grid_constant__ SampleArgs a) {
   __shared__ int sh[2 * SB / 32 + 2];
   __shared__ int s_base[2];
-  __shared__ int s_cnt[4];
   const int N = a.n_img * a.n_per_img;
   const int start = blockIdx.x * SB;
   const int slot = start + threadIdx.x;
-  if (threadIdx.x < 4) s_cnt[threadIdx.x] = 0;
   // kept / depth-less counts of all preceding slots (recomputed, cheap; keeps the compaction ordered
   // without a second launch or a look-back chain)
   int pk = 0, pd = 0;
+#pragma unroll 4
   for (int j = threadIdx.x; j < start; j += SB) {
     const RayEval e = eval_ray(a, j);
     pk += e.keep;
@@ -230,7 +259,6 @@ __global__ void __launch_bounds__(SB) k_sample_rays(const __grid_constant__ Samp
   if (e.keep) {
     const int r = s_base[0] + ex0;
     const int r0 = s_base[1] + ex1;  // ordinal among depth-less rays
-    const int r1 = r - r0;           // ordinal among depth>0 rays
     const int frame = slot / a.n_per_img;
     const long long pix = a.pix_idx[slot];
     const int pr = (int)(pix / a.Wc), pc = (int)(pix - (long long)pr * a.Wc);
@@ -245,31 +273,18 @@ __global__ void __launch_bounds__(SB) k_sample_rays(const __grid_constant__ Samp
     a.gt_color[(long long)r * 3 + 1] = cp[1];
     a.gt_color[(long long)r * 3 + 2] = cp[2];
     a.src[r] = slot;
-    int nf = 0, nc = 0, nt = 0;
     if (e.depth > 0.f) {
-      depth_guided_z(e.depth, a.n_strat, a.n_imp, a.t_uni, a.t_surf, a.tr15, a.tr3,
-                     a.u_depth ? a.u_depth + (long long)r1 * S : nullptr, a.z + (long long)r * S, a.tr, a.tr04, nf,
-                     nc, nt);
-      atomicAdd(&s_cnt[0], 1);
-      atomicAdd(&s_cnt[1], nf);
-      atomicAdd(&s_cnt[2], nc);
-      atomicAdd(&s_cnt[3], nt);
+      a.zord[r] = r - r0;  // ordinal among depth>0 kept rays = row of u_depth
     } else {
+      a.zord[r] = -1;
       a.dl_list[r0] = r;
+      *reinterpret_cast<uchar4*>(a.band + r * 4) = make_uchar4(0, 0, 0, 0);
     }
-    a.band[r * 4 + 0] = (unsigned char)nf;
-    a.band[r * 4 + 1] = (unsigned char)nc;
-    a.band[r * 4 + 2] = (unsigned char)nt;
-    a.band[r * 4 + 3] = e.depth > 0.f ? 1 : 0;
   }
-  __syncthreads();
   if (threadIdx.x == 0) {
     if (tot0) atomicAdd(a.counters + 0, tot0);
     if (tot1) atomicAdd(a.counters + 1, tot1);
-    if (s_cnt[0]) atomicAdd(a.counters + 2, s_cnt[0]);
-    if (s_cnt[1]) atomicAdd(a.counters + 3, s_cnt[1]);
-    if (s_cnt[2]) atomicAdd(a.counters + 4, s_cnt[2]);
-    if (s_cnt[3]) atomicAdd(a.counters + 5, s_cnt[3]);
+    if (tot0 - tot1) atomicAdd(a.counters + 2, tot0 - tot1);
   }
   if (a.c2w_out && slot < N && (slot % a.n_per_img) == 0) {
     const int frame = slot / a.n_per_img;
@@ -295,20 +310,70 @@ __global__ void __launch_bounds__(SB) k_sample_rays(const __grid_constant__ Samp
   }
 }
 
-// z_vals of an explicit, already compacted ray list (render_batch_ray through the reference's API)
-struct DepthSampleArgs {
+// Depth-guided z_vals, one warp per compact ray (grid covers an upper bound of rays; R is read on the device).
+// zord[r] = row of u_depth (ordinal among depth>0 rays) or -1 for a depth-less ray.  Fills z rows, band[r]
+// and adds the band totals to counters[3..5].
+struct RaySampleArgs {
   int n_strat, n_imp;
   float tr, tr15, tr3, tr04;
   const float* gt_depth;
-  int n_rays;
+  const int* zord;
+  int max_rays;
   const float* u_depth;
   const float *t_uni, *t_surf;
   float* z;
+  unsigned char* band;
+  int* counters;
+};
+
+__global__ void __launch_bounds__(SB) k_ray_samples(const __grid_constant__ RaySampleArgs a) {
+  __shared__ float s_zs[SB / 32][64];
+  __shared__ float s_tu[ESLAM_MAX_SAMPLES], s_ts[16];
+  __shared__ int s_cnt[3];
+  const int R = min(a.counters[0], a.max_rays);
+  if (blockIdx.x * (SB / 32) >= R) return;
+  if (threadIdx.x < a.n_strat) s_tu[threadIdx.x] = a.t_uni[threadIdx.x];
+  if (threadIdx.x < a.n_imp) s_ts[threadIdx.x] = a.t_surf[threadIdx.x];
+  if (threadIdx.x < 3) s_cnt[threadIdx.x] = 0;
+  __syncthreads();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int r = blockIdx.x * (SB / 32) + warp;
+  const int S = a.n_strat + a.n_imp;
+  if (r < R) {
+    const int ord = a.zord[r];
+    if (ord >= 0) {
+      float u_lo = 0.f, u_hi = 0.f;
+      if (a.u_depth) {
+        const float* up = a.u_depth + (long long)ord * S;
+        if (lane < S) u_lo = up[lane];
+        if (lane + 32 < S) u_hi = up[lane + 32];
+      }
+      int nf, nc, nt;
+      depth_guided_z_warp(a.gt_depth[r], a.n_strat, a.n_imp, s_tu, s_ts, a.tr15, a.tr3, a.u_depth != nullptr, u_lo,
+                          u_hi, a.z + (long long)r * S, a.tr, a.tr04, s_zs[warp], nf, nc, nt);
+      if (lane == 0) {
+        if (a.band) *reinterpret_cast<uchar4*>(a.band + r * 4) = make_uchar4(nf, nc, nt, 1);
+        atomicAdd(&s_cnt[0], nf);
+        atomicAdd(&s_cnt[1], nc);
+        atomicAdd(&s_cnt[2], nt);
+      }
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x < 3 && s_cnt[threadIdx.x]) atomicAdd(a.counters + 3 + threadIdx.x, s_cnt[threadIdx.x]);
+}
+
+// Ordinals for an explicit, already compacted ray list (render_batch_ray through the reference's API):
+// zord / dl_list / counters[0..2] from gt_depth alone.
+struct DepthOrdArgs {
+  const float* gt_depth;
+  int n_rays;
+  int* zord;
   int* dl_list;
   int* counters;
 };
 
-__global__ void __launch_bounds__(SB) k_depth_samples(const __grid_constant__ DepthSampleArgs a) {
+__global__ void __launch_bounds__(SB) k_depth_ordinals(const __grid_constant__ DepthOrdArgs a) {
   __shared__ int sh[2 * SB / 32 + 2];
   __shared__ int s_base;
   const int start = blockIdx.x * SB;
@@ -329,20 +394,19 @@ __global__ void __launch_bounds__(SB) k_depth_samples(const __grid_constant__ De
   const int fd_ = (in && !(d > 0.f)) ? 1 : 0;
   int ex0, ex1, tot0, tot1;
   block_scan2(fd_, 0, ex0, ex1, tot0, tot1, sh);
-  const int S = a.n_strat + a.n_imp;
   if (in) {
     const int r0 = s_base + ex0;
     if (d > 0.f) {
-      int nf, nc, nt;
-      depth_guided_z(d, a.n_strat, a.n_imp, a.t_uni, a.t_surf, a.tr15, a.tr3,
-                     a.u_depth ? a.u_depth + (long long)(r - r0) * S : nullptr, a.z + (long long)r * S, a.tr, a.tr04,
-                     nf, nc, nt);
+      a.zord[r] = r - r0;
     } else {
+      a.zord[r] = -1;
       a.dl_list[r0] = r;
     }
   }
   if (threadIdx.x == 0) {
     if (tot0) atomicAdd(a.counters + 1, tot0);
+    const int here = min(SB, a.n_rays - start);
+    if (here - tot0) atomicAdd(a.counters + 2, here - tot0);
     if (blockIdx.x == 0) a.counters[0] = a.n_rays;
   }
 }

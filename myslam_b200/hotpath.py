@@ -45,6 +45,7 @@ class Workspace:
         self.src = torch.empty(N, dtype=i32, device=dev)
         self.z = torch.empty(N, S, dtype=f32, device=dev)
         self.dl_list = torch.empty(N, dtype=i32, device=dev)
+        self.zord = torch.empty(N, dtype=i32, device=dev)
         self.band = torch.empty(N, 4, dtype=torch.uint8, device=dev)
         self.counters = torch.zeros(N_COUNTERS, dtype=i32, device=dev)
         self.depth = torch.empty(N, dtype=f32, device=dev)
@@ -80,7 +81,7 @@ def _sample(ws: Workspace, store: FieldStore, sc: StepCfg, idx, n_img, n_per_img
     call("eslam_sample_rays", store.ref(), C.byref(sc.cam), C.byref(sc.render), ptr(idx), n_img, n_per_img, ptr(c2w),
          ptr(poses), pose_first, ptr(depth), ptr(color), ptr(u_depth), ptr(t_uni), ptr(t_surf), need_depth,
          ptr(ws.rays_o), ptr(ws.rays_d), ptr(ws.gt_depth), ptr(ws.gt_color), ptr(ws.src), ptr(ws.z),
-         ptr(ws.dl_list), ptr(ws.band), ptr(ws.counters), ptr(ws.c2w_out), stream())
+         ptr(ws.dl_list), ptr(ws.zord), ptr(ws.band), ptr(ws.counters), ptr(ws.c2w_out), stream())
 
 
 def _check_frames(depth, color, n_img, cam):

@@ -153,11 +153,12 @@ class Renderer(object):
         r0 = R - r1
         z = torch.empty(R, S, dtype=torch.float32, device=dev)
         dl = torch.empty(max(R, 1), dtype=torch.int32, device=dev)
+        zord = torch.empty(max(R, 1), dtype=torch.int32, device=dev)
         cnt = torch.empty(N_COUNTERS, dtype=torch.int32, device=dev)
         u = draws.rand(r1, S) if self.perturb else None
         t_uni, t_surf = linspace_table(ns, dev), linspace_table(ni, dev)
         call("eslam_depth_samples", C.byref(cfg), ptr(d), R, ptr(u), ptr(t_uni), ptr(t_surf), ptr(z), ptr(dl),
-             ptr(cnt), stream())
+             ptr(zord), ptr(cnt), stream())
         if r0 > 0:
             if not self.perturb:
                 raise RuntimeError("rendering.perturb=False with depth-less rays is not supported by the kernels")
