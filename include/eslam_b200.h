@@ -85,6 +85,9 @@ typedef struct {
 
 const char* eslam_last_error(void);
 int eslam_abi_version(void);
+/* Profiling aid only (0 in production): bit0 skips the plane-gradient reductions and bit1 the decoder weight
+ * gradients inside eslam_loss_backward, to time the phases of the fused kernel separately. */
+void eslam_set_debug(int flags);
 
 /* ---- layout: the reference's NCHW planes <-> the channels-last arena ------------------------ */
 /* replaces nothing in the reference; it is the price of keeping ESLAM.py's [1,32,H,W] storage. */

@@ -13,6 +13,7 @@
 using namespace eslam;
 
 static thread_local char g_err[512] = "";
+static int g_debug = 0;
 
 static int fail(int code, const char* what) {
   if (code > 0)
@@ -75,6 +76,7 @@ extern "C" {
 
 const char* eslam_last_error(void) { return g_err; }
 int eslam_abi_version(void) { return ESLAM_ABI_VERSION; }
+void eslam_set_debug(int flags) { g_debug = flags; }
 
 int eslam_plane_import(const float* nchw, float* arena, const eslam_plane_t* pl, eslam_stream_t s) {
   REQUIRE(nchw && arena && pl && pl->H > 0 && pl->W > 0, "eslam_plane_import");
@@ -457,6 +459,7 @@ int eslam_loss_backward(const eslam_field_t* f, const float* arena, const eslam_
   a.n_rays = max_rays;
   a.S = k.n_strat + k.n_imp;
   a.counters = counters;
+  a.dbg = g_debug;
   a.norm = norm_counters ? norm_counters : counters;
   a.gt_depth = gt_depth;
   a.gt_color = gt_color;

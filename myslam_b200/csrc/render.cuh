@@ -272,6 +272,7 @@ struct BwdArgs {
   const float *rays_o, *rays_d, *z;
   int n_rays, S;
   const int* counters;
+  int dbg;          // profiling aid (eslam_set_debug): bit0 skip plane reductions, bit1 skip weight gradients
   const int* norm;  // loss normalisers (counters layout); == counters on one GPU, all-reduced sums on several
   // upstream-gradient mode
   const float *g_depth, *g_rgb, *g_sdf;
@@ -380,54 +381,128 @@ __device__ __forceinline__ void weight_grads(float* act0, float* act1, const flo
 
 // gather layout: scatter d loss/d features of one decoder into the plane gradients and/or accumulate the
 // gradient with respect to the normalised coordinates.
+// Scatter of one decoder's feature gradients (tile F, overwritten with d loss / d features) for the 8 consecutive
+// points [qb, qb+8) owned by this 8-lane group, plus the gradient with respect to the normalised coordinates.
+//
+// The plane-gradient reductions are the one phase of the iteration that sits on a hardware limit
+// (red.global.add.v4.f32 peaks at ~6.2 TB/s on B200, tools/microbench/l2_gather_red.cu), so the bytes are what
+// must shrink: consecutive samples of a ray stay ~3 samples in the same 24 cm coarse cell, therefore the coarse
+// taps run tap-major over the group's consecutive points and keep the four corner contributions in registers
+// until the cell changes (run-length merging).  Fine taps (6 cm / 3 cm cells) rarely repeat and go point-major
+// with all 12 corner loads of the scale in flight.
 template <bool GF, bool GR, int AXBASE>
-__device__ __forceinline__ void scatter_point(const FieldK& fk, int field, const float4* __restrict__ arena4,
+__device__ __forceinline__ void scatter_group(const FieldK& fk, int field, const float4* __restrict__ arena4,
                                               float4* __restrict__ garena4, const int (*ax_i)[NP],
-                                              const float (*ax_f)[NP], int q, int sub, float4 gC, float4 gF,
-                                              float (&gpn)[3]) {
-#pragma unroll
-  for (int s = 0; s < 2; ++s) {
-    const float4 g4 = s ? gF : gC;
-    Tap tp[3];
-    int u0[3], v0[3];
+                                              const float (*ax_f)[NP], const float4* F, int qb, int n_valid, int sub,
+                                              float (*gp)[NP], int dbg) {
+  const bool do_red = GF && !(dbg & 1);
+  // ---- pass 1, coarse scale, reductions only: tap-major over the consecutive points, merged per cell
+  if (do_red) {
 #pragma unroll
     for (int p = 0; p < 3; ++p) {
-      const int au = AXBASE + s * 3 + pair_u(p), av = AXBASE + s * 3 + pair_v(p);
-      u0[p] = ax_i[au][q];
-      v0[p] = ax_i[av][q];
-      tp[p] = make_tap(fk.pl[field * 6 + s * 3 + p], u0[p], ax_f[au][q], v0[p], ax_f[av][q], sub);
+      const PlaneK& pl = fk.pl[field * 6 + p];
+      const int au = AXBASE + pair_u(p), av = AXBASE + pair_v(p);
+      int cur = -1, cdx = 0, cdy = 0;
+      float4 a00 = f4_zero(), a01 = f4_zero(), a10 = f4_zero(), a11 = f4_zero();
+#pragma unroll
+      for (int it = 0; it < 8; ++it) {
+        const int q = qb + it;
+        if (q < n_valid) {
+          const Tap t = make_tap(pl, ax_i[au][q], ax_f[au][q], ax_i[av][q], ax_f[av][q], sub);
+          const float fu = t.fu, fv = t.fv;
+          const float4 g4 = F[f_slot(q, sub)];
+          const float w00 = (1.f - fu) * (1.f - fv), w01 = fu * (1.f - fv), w10 = (1.f - fu) * fv, w11 = fu * fv;
+          if (t.base != cur) {
+            if (cur >= 0) {
+              red_add_v4(garena4 + cur, a00);
+              red_add_v4(garena4 + cur + cdx, a01);
+              red_add_v4(garena4 + cur + cdy, a10);
+              red_add_v4(garena4 + cur + cdy + cdx, a11);
+            }
+            cur = t.base;
+            cdx = t.dx;
+            cdy = t.dy;
+            a00 = f4_mul(w00, g4);
+            a01 = f4_mul(w01, g4);
+            a10 = f4_mul(w10, g4);
+            a11 = f4_mul(w11, g4);
+          } else {
+            a00 = f4_fma(w00, g4, a00);
+            a01 = f4_fma(w01, g4, a01);
+            a10 = f4_fma(w10, g4, a10);
+            a11 = f4_fma(w11, g4, a11);
+          }
+        }
+      }
+      if (cur >= 0) {
+        red_add_v4(garena4 + cur, a00);
+        red_add_v4(garena4 + cur + cdx, a01);
+        red_add_v4(garena4 + cur + cdy, a10);
+        red_add_v4(garena4 + cur + cdy + cdx, a11);
+      }
+    }
+  }
+  // ---- pass 2, point-major: coordinate gradients of both scales (12 corner loads in flight per scale) and
+  //      the fine-scale reductions
+#pragma unroll 1
+  for (int it = 0; it < 8; ++it) {
+    const int q = qb + it;
+    float gpn[3] = {0.f, 0.f, 0.f};
+    if (q < n_valid) {
+#pragma unroll
+      for (int sc = 0; sc < 2; ++sc) {
+        if (!GR && sc == 0) continue;
+        const float4 g4 = F[f_slot(q, sc * 8 + sub)];
+        Tap tp[3];
+        int u0[3], v0[3];
+#pragma unroll
+        for (int p = 0; p < 3; ++p) {
+          const int au = AXBASE + sc * 3 + pair_u(p), av = AXBASE + sc * 3 + pair_v(p);
+          u0[p] = ax_i[au][q];
+          v0[p] = ax_i[av][q];
+          tp[p] = make_tap(fk.pl[field * 6 + sc * 3 + p], u0[p], ax_f[au][q], v0[p], ax_f[av][q], sub);
+        }
+        if (GR) {
+          float4 v[3][4];
+#pragma unroll
+          for (int p = 0; p < 3; ++p) {
+            v[p][0] = ldg4(arena4 + tp[p].base);
+            v[p][1] = ldg4(arena4 + tp[p].base + tp[p].dx);
+            v[p][2] = ldg4(arena4 + tp[p].base + tp[p].dy);
+            v[p][3] = ldg4(arena4 + tp[p].base + tp[p].dy + tp[p].dx);
+          }
+#pragma unroll
+          for (int p = 0; p < 3; ++p) {
+            const PlaneK& pl = fk.pl[field * 6 + sc * 3 + p];
+            const float fu = tp[p].fu, fv = tp[p].fv;
+            const float d00 = f4_dot(g4, v[p][0]), d01 = f4_dot(g4, v[p][1]);
+            const float d10 = f4_dot(g4, v[p][2]), d11 = f4_dot(g4, v[p][3]);
+            const float du = (d01 - d00) * (1.f - fv) + (d11 - d10) * fv;
+            const float dv = (d10 - d00) * (1.f - fu) + (d11 - d01) * fu;
+            gpn[pair_u(p)] = fmaf(du, axis_grad_mult(u0[p], fu, pl.W), gpn[pair_u(p)]);
+            gpn[pair_v(p)] = fmaf(dv, axis_grad_mult(v0[p], fv, pl.H), gpn[pair_v(p)]);
+          }
+        }
+        if (do_red && sc == 1) {
+#pragma unroll
+          for (int p = 0; p < 3; ++p) {
+            const float fu = tp[p].fu, fv = tp[p].fv;
+            red_add_v4(garena4 + tp[p].base, f4_mul((1.f - fu) * (1.f - fv), g4));
+            red_add_v4(garena4 + tp[p].base + tp[p].dx, f4_mul(fu * (1.f - fv), g4));
+            red_add_v4(garena4 + tp[p].base + tp[p].dy, f4_mul((1.f - fu) * fv, g4));
+            red_add_v4(garena4 + tp[p].base + tp[p].dy + tp[p].dx, f4_mul(fu * fv, g4));
+          }
+        }
+      }
     }
     if (GR) {
-      // all 12 corner loads of the scale in flight before the first use
-      float4 v[3][4];
 #pragma unroll
-      for (int p = 0; p < 3; ++p) {
-        v[p][0] = ldg4(arena4 + tp[p].base);
-        v[p][1] = ldg4(arena4 + tp[p].base + tp[p].dx);
-        v[p][2] = ldg4(arena4 + tp[p].base + tp[p].dy);
-        v[p][3] = ldg4(arena4 + tp[p].base + tp[p].dy + tp[p].dx);
-      }
-#pragma unroll
-      for (int p = 0; p < 3; ++p) {
-        const PlaneK& pl = fk.pl[field * 6 + s * 3 + p];
-        const float fu = tp[p].fu, fv = tp[p].fv;
-        // d tap/du = (v01-v00)(1-fv) + (v11-v10) fv, d tap/dv = (v10-v00)(1-fu) + (v11-v01) fu, contracted with g4
-        const float d00 = f4_dot(g4, v[p][0]), d01 = f4_dot(g4, v[p][1]);
-        const float d10 = f4_dot(g4, v[p][2]), d11 = f4_dot(g4, v[p][3]);
-        const float du = (d01 - d00) * (1.f - fv) + (d11 - d10) * fv;
-        const float dv = (d10 - d00) * (1.f - fu) + (d11 - d01) * fu;
-        gpn[pair_u(p)] = fmaf(du, axis_grad_mult(u0[p], fu, pl.W), gpn[pair_u(p)]);
-        gpn[pair_v(p)] = fmaf(dv, axis_grad_mult(v0[p], fv, pl.H), gpn[pair_v(p)]);
-      }
-    }
-    if (GF) {
-#pragma unroll
-      for (int p = 0; p < 3; ++p) {
-        const float fu = tp[p].fu, fv = tp[p].fv;
-        red_add_v4(garena4 + tp[p].base, f4_mul((1.f - fu) * (1.f - fv), g4));
-        red_add_v4(garena4 + tp[p].base + tp[p].dx, f4_mul(fu * (1.f - fv), g4));
-        red_add_v4(garena4 + tp[p].base + tp[p].dy, f4_mul((1.f - fu) * fv, g4));
-        red_add_v4(garena4 + tp[p].base + tp[p].dy + tp[p].dx, f4_mul(fu * fv, g4));
+      for (int c = 0; c < 3; ++c) {
+        float v = gpn[c];
+        v += __shfl_xor_sync(0xffffffffu, v, 1);
+        v += __shfl_xor_sync(0xffffffffu, v, 2);
+        v += __shfl_xor_sync(0xffffffffu, v, 4);
+        if (sub == 0) gp[c][q] = v;
       }
     }
   }
@@ -619,7 +694,7 @@ __global__ void __launch_bounds__(NT_BWD, 2) k_render_bwd(const __grid_constant_
   } else {
     mlp_backward_hidden<C_W2, C_W3, 3>(gout, h1, h2, ga1, ga2);
   }
-  if (GF) {
+  if (GF && !(a.dbg & 2)) {
     float* gdec = a.grad_arena + a.fk.dec_off;
     weight_grads<S_W1, S_B1, S_W2, S_B2, S_W3, S_B3, 1>(sm.act0, sm.act1, sm.F0, gdec, half == 0, q, h1, h2, ga1, ga2, gout);
     weight_grads<C_W1, C_B1, C_W2, C_B2, C_W3, C_B3, 3>(sm.act0, sm.act1, sm.F1, gdec, half == 1, q, h1, h2, ga1, ga2, gout);
@@ -631,7 +706,7 @@ __global__ void __launch_bounds__(NT_BWD, 2) k_render_bwd(const __grid_constant_
   else
     mlp_backward_input<C_W1>(ga1, sm.F1, q);
   __syncthreads();
-  if (GF && tid == 0) {
+  if (GF && !(a.dbg & 2) && tid == 0) {
     float gb = 0.f;
     for (int i = 0; i < NP / 32; ++i) gb += sm.red[i];  // only the sdf half carries beta gradients
     atomicAdd(a.grad_arena + a.fk.dec_off + P_BETA, gb);
@@ -639,30 +714,12 @@ __global__ void __launch_bounds__(NT_BWD, 2) k_render_bwd(const __grid_constant_
   // ---- P7: scatter to the planes / coordinate gradients (gather layout, each half its own decoder)
   {
     const int wl = (tid & (NP - 1)) >> 5, grp = lane >> 3, sub = lane & 7;
+    const int qb = wl * 32 + grp * 8;  // 8 consecutive points (samples along a ray) per 8-lane group
     float4* garena4 = reinterpret_cast<float4*>(a.grad_arena);
-#pragma unroll 1
-    for (int it = 0; it < 8; ++it) {
-      const int qq = wl * 32 + it * 4 + grp;
-      float gpn[3] = {0.f, 0.f, 0.f};
-      if (qq < n_valid) {
-        if (half == 0)
-          scatter_point<GF, GR, 0>(a.fk, 0, a.arena4, garena4, sm.ax_i, sm.ax_f, qq, sub, sm.F0[f_slot(qq, sub)],
-                                   sm.F0[f_slot(qq, 8 + sub)], gpn);
-        else
-          scatter_point<GF, GR, 6>(a.fk, 1, a.arena4, garena4, sm.ax_i, sm.ax_f, qq, sub, sm.F1[f_slot(qq, sub)],
-                                   sm.F1[f_slot(qq, 8 + sub)], gpn);
-      }
-      if (GR) {
-#pragma unroll
-        for (int c = 0; c < 3; ++c) {
-          float v = gpn[c];
-          v += __shfl_xor_sync(0xffffffffu, v, 1);
-          v += __shfl_xor_sync(0xffffffffu, v, 2);
-          v += __shfl_xor_sync(0xffffffffu, v, 4);
-          if (sub == 0) sm.gp[half][c][qq] = v;
-        }
-      }
-    }
+    if (half == 0)
+      scatter_group<GF, GR, 0>(a.fk, 0, a.arena4, garena4, sm.ax_i, sm.ax_f, sm.F0, qb, n_valid, sub, sm.gp[0], a.dbg);
+    else
+      scatter_group<GF, GR, 6>(a.fk, 1, a.arena4, garena4, sm.ax_i, sm.ax_f, sm.F1, qb, n_valid, sub, sm.gp[1], a.dbg);
   }
   // ---- P8: ray / point / pose gradients
   if (GR) {

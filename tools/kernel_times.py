@@ -67,6 +67,11 @@ def main():
     timeit("map.loss_backward planes+poses", bwd(True, True))
     timeit("map.loss_backward planes only", bwd(True, False))
     timeit("map.loss_backward poses only", bwd(False, True))
+    from myslam_b200 import _lib
+    for flags, name in ((1, "no plane reductions"), (2, "no weight grads"), (3, "no reductions, no weight grads")):
+        _lib.load().eslam_set_debug(flags)
+        timeit(f"map.loss_backward planes+poses [{name}]", bwd(True, True))
+    _lib.load().eslam_set_debug(0)
     timeit("map.sample_rays", lambda: _sample(ws, store, sc, idx, nf, pix, c2w, poses7, 1, deps, cols, u, 0))
     timeit("map.importance", lambda: call(
         "eslam_importance_samples", store.ref(), ptr(store.arena), C.byref(sc.render), ptr(ws.rays_o), ptr(ws.rays_d),
