@@ -563,7 +563,23 @@ __global__ void __launch_bounds__(NT_BWD, 2) k_render_bwd(const __grid_constant_
   float h1[16], h2[16], out[3] = {0.f, 0.f, 0.f};
   float sdf = 0.f, u = 0.f, e = 0.f, alpha = 0.f, one = 1.f, rgb[3] = {0.f, 0.f, 0.f};
   const float beta = c_dec[P_BETA];
-  if (half == 0) {
+  if (a.dbg & 4) {  // profiling: skip the MLP arithmetic (results are meaningless)
+#pragma unroll
+    for (int j = 0; j < 16; ++j) h1[j] = h2[j] = sm.F0[q * 16].x * 0.f + (float)j;
+    if (half == 0) {
+      sdf = 0.1f;
+      sdf_to_alpha(sdf, beta, u, e, alpha);
+      one = __fadd_rn(__fsub_rn(1.0f, alpha), 1e-10f);
+      sm.one[q] = one;
+      sm.z[q] = zk;
+    } else {
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        rgb[c] = 0.5f;
+        sm.c[c][q] = rgb[c];
+      }
+    }
+  } else if (half == 0) {
     float os[1];
     mlp_forward<S_W1, S_B1, S_W2, S_B2, S_W3, S_B3, 1>(sm.F0, q, h1, h2, os);
     sdf = tanhf(os[0]);
@@ -688,7 +704,10 @@ __global__ void __launch_bounds__(NT_BWD, 2) k_render_bwd(const __grid_constant_
   }
   // ---- P6: MLP backward of this half's decoder
   float ga1[16], ga2[16];
-  if (half == 0) {
+  if (a.dbg & 4) {
+#pragma unroll
+    for (int j = 0; j < 16; ++j) ga1[j] = ga2[j] = gout[0] + gout[1] * (float)j;
+  } else if (half == 0) {
     const float gs[1] = {gout[0]};
     mlp_backward_hidden<S_W2, S_W3, 1>(gs, h1, h2, ga1, ga2);
   } else {
@@ -701,7 +720,9 @@ __global__ void __launch_bounds__(NT_BWD, 2) k_render_bwd(const __grid_constant_
     const float gb = warp_sum(g_beta);
     if (lane == 0) sm.red[warp] = gb;
   }
-  if (half == 0)
+  if (a.dbg & 4) {
+    Fh[q * 16] = make_float4(ga1[0], ga1[1], ga1[2], ga1[3]);
+  } else if (half == 0)
     mlp_backward_input<S_W1>(ga1, sm.F0, q);
   else
     mlp_backward_input<C_W1>(ga1, sm.F1, q);

@@ -68,7 +68,8 @@ def main():
     timeit("map.loss_backward planes only", bwd(True, False))
     timeit("map.loss_backward poses only", bwd(False, True))
     from myslam_b200 import _lib
-    for flags, name in ((1, "no plane reductions"), (2, "no weight grads"), (3, "no reductions, no weight grads")):
+    for flags, name in ((1, "no plane reductions"), (2, "no weight grads"), (3, "no reductions, no weight grads"),
+                        (4, "no MLP arithmetic"), (6, "no MLP, no weight grads"), (7, "gather+scan+corner loads only")):
         _lib.load().eslam_set_debug(flags)
         timeit(f"map.loss_backward planes+poses [{name}]", bwd(True, True))
     _lib.load().eslam_set_debug(0)
