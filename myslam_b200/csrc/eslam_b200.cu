@@ -68,6 +68,14 @@ static int check_samples(int n_strat, int n_imp) {
 }
 
 template <typename K>
+static int ensure_smem(K kernel, size_t bytes, bool* done) {
+  if (*done) return 0;
+  int rc = (int)cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+  if (rc == 0) *done = true;
+  return rc;
+}
+
+template <typename K>
 static int set_smem(K kernel, size_t bytes) {
   return (int)cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
 }
@@ -348,6 +356,7 @@ template <int MODE, bool GF, bool GR>
 static int launch_bwd(const BwdArgs& a, int n_rays, cudaStream_t st) {
   static bool configured = false;
   const size_t bytes = sizeof(SmemBwd<GF>);
+  static_assert(sizeof(SmemBwd<true>) <= 113 * 1024, "two CTAs of the backward kernel must fit one SM's shared memory");
   if (!configured) {
     int rc = set_smem(k_render_bwd<MODE, GF, GR>, bytes);
     if (rc) return rc;

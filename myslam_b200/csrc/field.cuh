@@ -1,6 +1,6 @@
 // Device-side building blocks shared by every kernel of the hot path: the plane table, the
 // bilinear tap set-up of grid_sample(border, align_corners=True), the 8-lanes-per-point gather,
-// and the two register-resident decoder MLPs reading their weights from constant memory.
+// and the two register-resident decoder MLPs reading their weights from a shared-memory copy.
 //
 // Thread layouts used throughout (one CTA = NP points = whole rays):
 //   "point layout":  thread q owns point q (MLPs, compositing, losses)
@@ -17,15 +17,13 @@ namespace eslam {
 
 constexpr int NP = 128;      // points per CTA (= threads per CTA)
 constexpr int NWARP = NP / 32;
+typedef short ax_t;          // texel index along one axis (plane extents are far below 32768)
 
 // ---- packed decoder offsets (include/eslam_b200.h) -------------------------------------------------
 constexpr int S_W1 = 0, S_B1 = 1024, S_W2 = 1040, S_B2 = 1296, S_W3 = 1312, S_B3 = 1328;
 constexpr int C_W1 = 1332, C_B1 = 2356, C_W2 = 2372, C_B2 = 2628, C_W3 = 2644, C_B3 = 2692;
 constexpr int P_BETA = ESLAM_DEC_BETA;
 constexpr int DEC_N = ESLAM_DEC_FLOATS;
-
-// decoder weights, filled by eslam_bind_decoders (single translation unit: defined here)
-__constant__ float c_dec[DEC_N];
 
 struct PlaneK {
   int off4;  // float4 offset of texel (0,0) in the arena
@@ -41,6 +39,7 @@ struct FieldK {
 inline int make_field_k(const eslam_field_t* f, FieldK* out) {
   for (int i = 0; i < 12; ++i) {
     if (f->plane[i].offset % 4 != 0 || f->plane[i].H < 1 || f->plane[i].W < 1) return ESLAM_EINVAL;
+    if (f->plane[i].H > 32767 || f->plane[i].W > 32767) return ESLAM_EUNSUPPORTED;
     if (f->plane[i].offset / 4 + (long long)f->plane[i].H * f->plane[i].W * 8 > 0x7fffffffLL) return ESLAM_EUNSUPPORTED;
     out->pl[i].off4 = (int)(f->plane[i].offset / 4);
     out->pl[i].H = f->plane[i].H;
@@ -135,7 +134,7 @@ __device__ __forceinline__ int pair_v(int p) { return p == 0 ? 1 : 2; }
 // (scale*3+axis) + AXBASE.
 template <int AXBASE>
 __device__ __forceinline__ void gather_features(const FieldK& fk, int field, const float4* __restrict__ arena4,
-                                                const int (*ax_i)[NP], const float (*ax_f)[NP], int q, int sub,
+                                                const ax_t (*ax_i)[NP], const float (*ax_f)[NP], int q, int sub,
                                                 float4& out_coarse, float4& out_fine) {
   Tap tp[6];
 #pragma unroll
@@ -175,7 +174,14 @@ __device__ __forceinline__ void gather_features(const FieldK& fk, int field, con
   out_fine = acc[1];
 }
 
-// ---- MLPs (point layout, weights from constant memory, fully unrolled) --------------------------------
+// decoder weights for the forward-only kernels, filled by eslam_bind_decoders (one translation unit)
+__constant__ float c_dec[DEC_N];
+
+// ---- forward MLP, weights as constant-memory operands, fully unrolled -----------------------------------
+// Used by the forward-only kernels (decode, render forward, importance): there the ~4 k straight-line
+// instructions stay resident in the instruction cache and no shared-memory bandwidth is spent on weights
+// (84 us vs 139 us for 4000 rays with the shared-memory form below).  The fused backward kernel, whose code is
+// three times larger, uses the looped shared-memory form instead (441 -> 358 us).
 
 template <int W1, int B1, int W2, int B2, int W3, int B3, int NOUT>
 __device__ __forceinline__ void mlp_forward(const float4* __restrict__ F, int q, float (&h1)[16], float (&h2)[16],
@@ -213,41 +219,123 @@ __device__ __forceinline__ void mlp_forward(const float4* __restrict__ F, int q,
   }
 }
 
-// Backward to the pre-activation gradients ga2, ga1 (relu masks from the stored activations).
-template <int W2, int W3, int NOUT>
-__device__ __forceinline__ void mlp_backward_hidden(const float (&gout)[NOUT], const float (&h1)[16],
-                                                    const float (&h2)[16], float (&ga1)[16], float (&ga2)[16]) {
-#pragma unroll
-  for (int i = 0; i < 16; ++i) {
-    float g = 0.f;
-#pragma unroll
-    for (int o = 0; o < NOUT; ++o) g = fmaf(c_dec[W3 + o * 16 + i], gout[o], g);
-    ga2[i] = h2[i] > 0.f ? g : 0.f;
-  }
-#pragma unroll
-  for (int i = 0; i < 16; ++i) {
-    float g = 0.f;
-#pragma unroll
-    for (int j = 0; j < 16; ++j) g = fmaf(c_dec[W2 + j * 16 + i], ga2[j], g);
-    ga1[i] = h1[i] > 0.f ? g : 0.f;
+// ---- MLPs with the weights in shared memory (point layout) ------------------------------------------------
+// One symmetric block per decoder, DW_STRIDE floats: W1[16][64] b1[16] W2[16][16] b2[16] W3[3][16] b3[3] (+pad);
+// the sdf decoder's W3 rows 1-2 and b3[1..2] are zero, so both decoders run the SAME code with a different base
+// pointer.  Loops over the 16 float4 feature chunks keep the code ~20x smaller than the fully unrolled
+// constant-operand form (which stalled on instruction fetch, profiles/r01_bwd_full_summary.txt).
+constexpr int DW_W1 = 0, DW_B1 = 1024, DW_W2 = 1040, DW_B2 = 1296, DW_W3 = 1312, DW_B3 = 1360, DW_STRIDE = 1364;
+constexpr int DW_BETA = 2 * DW_STRIDE, DW_TOTAL = 2 * DW_STRIDE + 4;
+
+// packed arena block (include/eslam_b200.h) -> symmetric shared block; all threads of the CTA cooperate
+__device__ __forceinline__ void load_decoder_weights(float* sW, const float* __restrict__ dec, int tid, int nthreads) {
+  for (int i = tid; i < DW_TOTAL; i += nthreads) {
+    float v = 0.f;
+    if (i < DW_STRIDE) {  // sdf block: arena offsets 0..1328 are laid out identically up to W3 row 0
+      if (i < DW_W3 + 16) v = dec[i];
+      else if (i == DW_B3) v = dec[S_B3];
+    } else if (i < 2 * DW_STRIDE) {
+      const int k = i - DW_STRIDE;
+      if (k < DW_B3 + 3) v = dec[C_W1 + k];  // rgb block is contiguous in the arena with the same inner layout
+    } else if (i == DW_BETA) {
+      v = dec[P_BETA];
+    }
+    sW[i] = v;
   }
 }
 
-// g_feat = W1^T ga1, written over the point's feature row.
-template <int W1>
-__device__ __forceinline__ void mlp_backward_input(const float (&ga1)[16], float4* __restrict__ F, int q) {
-  const int swz = q & 7;
-  float4* row = F + q * 16;
+__device__ __forceinline__ float4 lds4(const float* p) { return *reinterpret_cast<const float4*>(p); }
+
+__device__ __forceinline__ void mlp_forward_s(const float* __restrict__ W, const float4* __restrict__ F, int q,
+                                              float (&h1)[16], float (&h2)[16], float (&out)[3]) {
 #pragma unroll
+  for (int j4 = 0; j4 < 4; ++j4) {
+    const float4 b = lds4(W + DW_B1 + j4 * 4);
+    h1[j4 * 4 + 0] = b.x;
+    h1[j4 * 4 + 1] = b.y;
+    h1[j4 * 4 + 2] = b.z;
+    h1[j4 * 4 + 3] = b.w;
+  }
+  const int swz = q & 7;
+  const float4* row = F + q * 16;
+#pragma unroll 1
   for (int c4 = 0; c4 < 16; ++c4) {
-    float4 g = f4_zero();
+    const float4 f = row[c4 ^ swz];
+    const float* w = W + DW_W1 + c4 * 4;
 #pragma unroll
     for (int j = 0; j < 16; ++j) {
-      g.x = fmaf(c_dec[W1 + j * 64 + c4 * 4 + 0], ga1[j], g.x);
-      g.y = fmaf(c_dec[W1 + j * 64 + c4 * 4 + 1], ga1[j], g.y);
-      g.z = fmaf(c_dec[W1 + j * 64 + c4 * 4 + 2], ga1[j], g.z);
-      g.w = fmaf(c_dec[W1 + j * 64 + c4 * 4 + 3], ga1[j], g.w);
+      const float4 wj = lds4(w + j * 64);
+      h1[j] = fmaf(wj.x, f.x, h1[j]);
+      h1[j] = fmaf(wj.y, f.y, h1[j]);
+      h1[j] = fmaf(wj.z, f.z, h1[j]);
+      h1[j] = fmaf(wj.w, f.w, h1[j]);
     }
+  }
+#pragma unroll
+  for (int j = 0; j < 16; ++j) h1[j] = fmaxf(h1[j], 0.f);
+#pragma unroll
+  for (int j = 0; j < 16; ++j) {
+    float a = W[DW_B2 + j];
+#pragma unroll
+    for (int i4 = 0; i4 < 4; ++i4) {
+      const float4 w = lds4(W + DW_W2 + j * 16 + i4 * 4);
+      a = fmaf(w.x, h1[i4 * 4 + 0], a);
+      a = fmaf(w.y, h1[i4 * 4 + 1], a);
+      a = fmaf(w.z, h1[i4 * 4 + 2], a);
+      a = fmaf(w.w, h1[i4 * 4 + 3], a);
+    }
+    h2[j] = fmaxf(a, 0.f);
+  }
+#pragma unroll
+  for (int o = 0; o < 3; ++o) {
+    float a = W[DW_B3 + o];
+#pragma unroll
+    for (int i4 = 0; i4 < 4; ++i4) {
+      const float4 w = lds4(W + DW_W3 + o * 16 + i4 * 4);
+      a = fmaf(w.x, h2[i4 * 4 + 0], a);
+      a = fmaf(w.y, h2[i4 * 4 + 1], a);
+      a = fmaf(w.z, h2[i4 * 4 + 2], a);
+      a = fmaf(w.w, h2[i4 * 4 + 3], a);
+    }
+    out[o] = a;
+  }
+}
+
+__device__ __forceinline__ void mlp_backward_hidden_s(const float* __restrict__ W, const float (&gout)[3],
+                                                      const float (&h1)[16], const float (&h2)[16], float (&ga1)[16],
+                                                      float (&ga2)[16]) {
+#pragma unroll
+  for (int i4 = 0; i4 < 4; ++i4) {
+    float4 g = f4_zero();
+#pragma unroll
+    for (int o = 0; o < 3; ++o) g = f4_fma(gout[o], lds4(W + DW_W3 + o * 16 + i4 * 4), g);
+    ga2[i4 * 4 + 0] = h2[i4 * 4 + 0] > 0.f ? g.x : 0.f;
+    ga2[i4 * 4 + 1] = h2[i4 * 4 + 1] > 0.f ? g.y : 0.f;
+    ga2[i4 * 4 + 2] = h2[i4 * 4 + 2] > 0.f ? g.z : 0.f;
+    ga2[i4 * 4 + 3] = h2[i4 * 4 + 3] > 0.f ? g.w : 0.f;
+  }
+#pragma unroll
+  for (int i4 = 0; i4 < 4; ++i4) {
+    float4 g = f4_zero();
+#pragma unroll
+    for (int j = 0; j < 16; ++j) g = f4_fma(ga2[j], lds4(W + DW_W2 + j * 16 + i4 * 4), g);
+    ga1[i4 * 4 + 0] = h1[i4 * 4 + 0] > 0.f ? g.x : 0.f;
+    ga1[i4 * 4 + 1] = h1[i4 * 4 + 1] > 0.f ? g.y : 0.f;
+    ga1[i4 * 4 + 2] = h1[i4 * 4 + 2] > 0.f ? g.z : 0.f;
+    ga1[i4 * 4 + 3] = h1[i4 * 4 + 3] > 0.f ? g.w : 0.f;
+  }
+}
+
+__device__ __forceinline__ void mlp_backward_input_s(const float* __restrict__ W, const float (&ga1)[16],
+                                                     float4* __restrict__ F, int q) {
+  const int swz = q & 7;
+  float4* row = F + q * 16;
+#pragma unroll 1
+  for (int c4 = 0; c4 < 16; ++c4) {
+    float4 g = f4_zero();
+    const float* w = W + DW_W1 + c4 * 4;
+#pragma unroll
+    for (int j = 0; j < 16; ++j) g = f4_fma(ga1[j], lds4(w + j * 64), g);
     row[c4 ^ swz] = g;
   }
 }

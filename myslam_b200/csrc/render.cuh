@@ -11,7 +11,7 @@ namespace eslam {
 // ---------------------------------------------------------------------------------------------------
 struct SmemFwd {
   float4 F[NP * 16];   // feature tile of the decoder being evaluated
-  int ax_i[6][NP];     // axis set-ups of that decoder's two resolution groups: [scale*3+axis]
+  ax_t ax_i[6][NP];     // axis set-ups of that decoder's two resolution groups: [scale*3+axis]
   float ax_f[6][NP];
   float one[NP], w[NP], z[NP], c[3][NP];
 };
@@ -22,8 +22,9 @@ template <bool GF>
 struct SmemBwd {
   float4 F0[NP * 16];  // sdf features, later d loss / d sdf features
   float4 F1[NP * 16];  // rgb
-  int ax_i[12][NP];
+  ax_t ax_i[12][NP];
   float ax_f[12][NP];
+  float W[DW_TOTAL];   // both decoders' weights, symmetric blocks (field.cuh)
   float act0[GF ? NP * 20 : 4];  // activation / gradient staging for the weight-gradient products
   float act1[GF ? NP * 20 : 4];
   float one[NP], w[NP], z[NP], c[3][NP], gww[NP];
@@ -43,7 +44,7 @@ struct SmemBwd {
 
 // point layout: axis set-ups of resolution groups [g0, g0+NG) into ax rows [0, 3*NG)
 template <int NG>
-__device__ __forceinline__ void write_axis_setups(const FieldK& fk, int g0, const float (&pn)[3], int (*ax_i)[NP],
+__device__ __forceinline__ void write_axis_setups(const FieldK& fk, int g0, const float (&pn)[3], ax_t (*ax_i)[NP],
                                                   float (*ax_f)[NP], int q) {
 #pragma unroll
   for (int g = 0; g < NG; ++g) {
@@ -52,7 +53,7 @@ __device__ __forceinline__ void write_axis_setups(const FieldK& fk, int g0, cons
       int i0;
       float fr;
       axis_setup(pn[a], axis_size(fk, g0 + g, a), i0, fr);
-      ax_i[g * 3 + a][q] = i0;
+      ax_i[g * 3 + a][q] = (ax_t)i0;
       ax_f[g * 3 + a][q] = fr;
     }
   }
@@ -61,7 +62,7 @@ __device__ __forceinline__ void write_axis_setups(const FieldK& fk, int g0, cons
 // gather layout: fill the feature tile of decoder `field` for all NP slots of this CTA
 template <int AXBASE>
 __device__ __forceinline__ void gather_tile(const FieldK& fk, int field, const float4* __restrict__ arena4,
-                                            const int (*ax_i)[NP], const float (*ax_f)[NP], float4* F, int n_valid,
+                                            const ax_t (*ax_i)[NP], const float (*ax_f)[NP], float4* F, int n_valid,
                                             int tid = threadIdx.x) {
   const int warp = tid >> 5, lane = tid & 31;
   const int grp = lane >> 3, sub = lane & 7;
@@ -160,7 +161,7 @@ struct FeatArgs {
 };
 
 __global__ void __launch_bounds__(NP) k_plane_feature(const __grid_constant__ FeatArgs a) {
-  __shared__ int ax_i[6][NP];
+  __shared__ ax_t ax_i[6][NP];
   __shared__ float ax_f[6][NP];
   const int q = threadIdx.x;
   const long long base = (long long)blockIdx.x * NP;
@@ -392,7 +393,7 @@ __device__ __forceinline__ void weight_grads(float* act0, float* act1, const flo
 // with all 12 corner loads of the scale in flight.
 template <bool GF, bool GR, int AXBASE>
 __device__ __forceinline__ void scatter_group(const FieldK& fk, int field, const float4* __restrict__ arena4,
-                                              float4* __restrict__ garena4, const int (*ax_i)[NP],
+                                              float4* __restrict__ garena4, const ax_t (*ax_i)[NP],
                                               const float (*ax_f)[NP], const float4* F, int qb, int n_valid, int sub,
                                               float (*gp)[NP], int dbg) {
   const bool do_red = GF && !(dbg & 1);
@@ -551,6 +552,7 @@ __global__ void __launch_bounds__(NT_BWD, 2) k_render_bwd(const __grid_constant_
     }
   }
   write_axis_setups<2>(a.fk, 2 * half, pn, sm.ax_i + 6 * half, sm.ax_f + 6 * half, q);
+  load_decoder_weights(sm.W, reinterpret_cast<const float*>(a.arena4) + a.fk.dec_off, tid, NT_BWD);
   __syncthreads();
   // ---- P2: gather this half's decoder features
   float4* Fh = half ? sm.F1 : sm.F0;
@@ -562,7 +564,8 @@ __global__ void __launch_bounds__(NT_BWD, 2) k_render_bwd(const __grid_constant_
   // ---- P3: MLP forward of this half's decoder
   float h1[16], h2[16], out[3] = {0.f, 0.f, 0.f};
   float sdf = 0.f, u = 0.f, e = 0.f, alpha = 0.f, one = 1.f, rgb[3] = {0.f, 0.f, 0.f};
-  const float beta = c_dec[P_BETA];
+  const float beta = sm.W[DW_BETA];
+  const float* Wh = sm.W + half * DW_STRIDE;
   if (a.dbg & 4) {  // profiling: skip the MLP arithmetic (results are meaningless)
 #pragma unroll
     for (int j = 0; j < 16; ++j) h1[j] = h2[j] = sm.F0[q * 16].x * 0.f + (float)j;
@@ -579,20 +582,20 @@ __global__ void __launch_bounds__(NT_BWD, 2) k_render_bwd(const __grid_constant_
         sm.c[c][q] = rgb[c];
       }
     }
-  } else if (half == 0) {
-    float os[1];
-    mlp_forward<S_W1, S_B1, S_W2, S_B2, S_W3, S_B3, 1>(sm.F0, q, h1, h2, os);
-    sdf = tanhf(os[0]);
-    sdf_to_alpha(sdf, beta, u, e, alpha);
-    one = __fadd_rn(__fsub_rn(1.0f, alpha), 1e-10f);
-    sm.one[q] = one;
-    sm.z[q] = zk;
   } else {
-    mlp_forward<C_W1, C_B1, C_W2, C_B2, C_W3, C_B3, 3>(sm.F1, q, h1, h2, out);
+    mlp_forward_s(Wh, Fh, q, h1, h2, out);
+    if (half == 0) {
+      sdf = tanhf(out[0]);
+      sdf_to_alpha(sdf, beta, u, e, alpha);
+      one = __fadd_rn(__fsub_rn(1.0f, alpha), 1e-10f);
+      sm.one[q] = one;
+      sm.z[q] = zk;
+    } else {
 #pragma unroll
-    for (int c = 0; c < 3; ++c) {
-      rgb[c] = sigmoidf_(out[c]);
-      sm.c[c][q] = rgb[c];
+      for (int c = 0; c < 3; ++c) {
+        rgb[c] = sigmoidf_(out[c]);
+        sm.c[c][q] = rgb[c];
+      }
     }
   }
   __syncthreads();
@@ -707,11 +710,8 @@ __global__ void __launch_bounds__(NT_BWD, 2) k_render_bwd(const __grid_constant_
   if (a.dbg & 4) {
 #pragma unroll
     for (int j = 0; j < 16; ++j) ga1[j] = ga2[j] = gout[0] + gout[1] * (float)j;
-  } else if (half == 0) {
-    const float gs[1] = {gout[0]};
-    mlp_backward_hidden<S_W2, S_W3, 1>(gs, h1, h2, ga1, ga2);
   } else {
-    mlp_backward_hidden<C_W2, C_W3, 3>(gout, h1, h2, ga1, ga2);
+    mlp_backward_hidden_s(Wh, gout, h1, h2, ga1, ga2);  // sdf: gout[1] = gout[2] = 0
   }
   if (GF && !(a.dbg & 2)) {
     float* gdec = a.grad_arena + a.fk.dec_off;
@@ -722,10 +722,9 @@ __global__ void __launch_bounds__(NT_BWD, 2) k_render_bwd(const __grid_constant_
   }
   if (a.dbg & 4) {
     Fh[q * 16] = make_float4(ga1[0], ga1[1], ga1[2], ga1[3]);
-  } else if (half == 0)
-    mlp_backward_input<S_W1>(ga1, sm.F0, q);
-  else
-    mlp_backward_input<C_W1>(ga1, sm.F1, q);
+  } else {
+    mlp_backward_input_s(Wh, ga1, Fh, q);
+  }
   __syncthreads();
   if (GF && !(a.dbg & 2) && tid == 0) {
     float gb = 0.f;
