@@ -405,7 +405,7 @@ __device__ __forceinline__ void scatter_group(const FieldK& fk, int field, const
       const int au = AXBASE + pair_u(p), av = AXBASE + pair_v(p);
       int cur = -1, cdx = 0, cdy = 0;
       float4 a00 = f4_zero(), a01 = f4_zero(), a10 = f4_zero(), a11 = f4_zero();
-#pragma unroll
+#pragma unroll 1
       for (int it = 0; it < 8; ++it) {
         const int q = qb + it;
         if (q < n_valid) {
