@@ -7,6 +7,7 @@ moment arenas.  The reference keeps the planes as 12 separate [1,32,H,W] tensors
 from __future__ import annotations
 
 import ctypes as C
+import weakref
 from typing import Dict, List, Optional, Sequence, Tuple
 
 import torch
@@ -42,6 +43,35 @@ def flatten_planes(all_planes) -> List[torch.Tensor]:
         for s, p in enumerate(lst):
             out[arena_slot(g, s)] = p
     return out  # type: ignore[return-value]
+
+
+class Signature:
+    """Identity + version of the tensors a store mirrors.  Equal only if every tensor is the SAME live object
+    (weak reference, so a new tensor that happens to reuse the address does not match), at the same address and
+    autograd version."""
+
+    def __init__(self, tensors):
+        self.items = []
+        for t in tensors:
+            if torch.is_tensor(t):
+                self.items.append((weakref.ref(t), t.data_ptr(), t._version))
+            else:
+                self.items.append((None, 0, float(t)))
+
+    def __eq__(self, other):
+        if not isinstance(other, Signature) or len(self.items) != len(other.items):
+            return False
+        for (ra, pa, va), (rb, pb, vb) in zip(self.items, other.items):
+            if pa != pb or va != vb:
+                return False
+            if (ra is None) != (rb is None):
+                return False
+            if ra is not None and (ra() is None or ra() is not rb()):
+                return False
+        return True
+
+    def __ne__(self, other):
+        return not self.__eq__(other)
 
 
 class FieldStore:
@@ -127,10 +157,8 @@ class FieldStore:
             else:
                 dec[off:off + n].copy_(state[key].detach().reshape(-1), non_blocking=True)
 
-    def signature(self, all_planes, dec_tensors) -> tuple:
-        sig = [(p.data_ptr(), p._version) for p in flatten_planes(all_planes)]
-        sig += [(t.data_ptr(), t._version) if torch.is_tensor(t) else (0, float(t)) for t in dec_tensors]
-        return tuple(sig)
+    def signature(self, all_planes, dec_tensors) -> "Signature":
+        return Signature(flatten_planes(all_planes) + list(dec_tensors))
 
     # ------------------------------------------------------------------ arena -> reference layout
     def push_planes(self, all_planes, which: Optional[torch.Tensor] = None) -> None:
