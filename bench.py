@@ -218,7 +218,7 @@ def main():
     import myslam_b200 as M
     from myslam_b200 import _lib
     from myslam_b200.decoders import synced_store
-    from myslam_b200.dist import MappingExchange
+    from myslam_b200.dist import MappingExchange, PeerExchange
     from myslam_b200.hotpath import mapping_iteration
     from myslam_b200.mapper import _mapper_state, map_window
     from myslam_b200.common import matrix_to_cam_pose
@@ -255,8 +255,15 @@ def main():
     mp = M.MapperStep(cfg, rnd, scene.decoders, scene.all_planes, scene.bound, scene.cam, dev)
     st = _mapper_state(mp, m["pixels"], n_frames)
     store = synced_store(scene.all_planes, scene.decoders, scene.bound)
-    ex = MappingExchange() if dist_on else None
     ws, sc = st["ws"], st["sc"]
+    ex, exchange_name = None, "none (1 GPU)"
+    if dist_on:
+        if os.environ.get("ESLAM_B200_EXCHANGE", "peer") == "nccl":
+            ex, exchange_name = MappingExchange(), "NCCL all-reduce of the gradient arena + replicated Adam"
+        else:
+            ex = PeerExchange(store, ws)
+            exchange_name = ("one kernel over symmetric peer memory: reduce-scatter + Adam + all-gather + zero_grad ("
+                             + ("multimem.ld_reduce/st through NVSwitch" if ex.multimem else "P2P loads/stores") + ")")
     lr = m["lr"]
     pix = m["pixels"] // n_frames
 
@@ -269,9 +276,7 @@ def main():
         ws.pose_v.zero_()
         for it in range(m["iters"]):
             mapping_iteration(ws, store, sc, poses, poses7, cols, deps, pix, it + 1, lr["decoders_lr"],
-                              lr["planes_lr"], lr["c_planes_lr"], m["joint_opt_cam_lr"],
-                              reduce_counters=ex.reduce_counters if ex else None,
-                              reduce_grads=ex.reduce_grads if ex else None)
+                              lr["planes_lr"], lr["c_planes_lr"], m["joint_opt_cam_lr"], exchange=ex)
 
     sampler = ClockSampler(local).start() if rank == 0 else None
     l0 = _lib.LAUNCHES
@@ -365,6 +370,10 @@ def main():
     h_dep = deps[-1].cpu().pin_memory()
     h_c2w = poses[-1].cpu().pin_memory()
     kf_list = list(range(0, 4 * (n_frames - 1), 4))
+    if dist_on:
+        dist.barrier()  # rank 0 has been timing the tracker; line the ranks up before kernels that wait on peers
+    mp.exchange = ex  # N > 1: every rank stages the same window from its own host memory and draws its own rays
+
     def mapping_e2e():
         gc = h_col.to(dev, non_blocking=True)
         gd = h_dep.to(dev, non_blocking=True)
@@ -372,17 +381,16 @@ def main():
         out = mp.optimize_mapping(m["iters"], 1.0, torch.tensor(4 * n_frames), gc, gd, cw, kf, kf_list, cw)
         out.cpu()
 
-    if not dist_on:
-        ms_e2e = time_region(mapping_e2e, max(args.steps // 2, 2), 2, False)
-        e2e_val = rays_per_step * max(args.steps // 2, 2) / (ms_e2e * 1e-3)
-        e2e = {"value": e2e_val, "unit": "rays*iters/s",
-               "h2d_bytes_per_step": h_col.numel() * 8 + h_dep.numel() * 4 + 64, "d2h_bytes_per_step": 64,
-               "ms_per_step": ms_e2e / max(args.steps // 2, 2),
-               "api": "MapperStep.optimize_mapping (reference signature): window selection + staging of 20 frames + "
-                      "15 fused iterations + write-back of planes/decoders to the reference's NCHW tensors"}
-    else:
-        e2e = {"value": None, "unit": "rays*iters/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0,
-               "note": "e2e is measured at N=1; the multi-GPU line times the sharded per-call loop"}
+    n_e2e = max(args.steps // 2, 2)
+    ms_e2e = time_region(mapping_e2e, n_e2e, 2, dist_on)
+    e2e = {"value": world * rays_per_step * n_e2e / (ms_e2e * 1e-3), "unit": "rays*iters/s",
+           "h2d_bytes_per_step": h_col.numel() * 8 + h_dep.numel() * 4 + 64, "d2h_bytes_per_step": 64,
+           "ms_per_step": ms_e2e / n_e2e,
+           "api": "MapperStep.optimize_mapping (reference signature): window selection + staging of 20 frames + "
+                  "15 fused iterations + write-back of planes/decoders to the reference's NCHW tensors"
+                  + ("; per rank, bytes are per rank" if dist_on else "")}
+    if hasattr(ex, "check"):
+        ex.check()
     clocks = sampler.stop() if sampler else None
 
     # ------------------------------------------------------------------ baselines (rank 0, N=1 only)
@@ -418,7 +426,7 @@ def main():
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": "replica-room0-shaped 1200x680, 20-keyframe window, 4000 rays/iter per GPU, "
                                    "15 iterations per optimize_mapping call, ESLAM.yaml defaults, joint pose optimisation",
-                       "rays_per_iter_total": world * pix * n_frames, "l2": "inputs larger than L2 (471 MB frame stack "
+                       "rays_per_iter_total": world * pix * n_frames, "exchange": exchange_name, "l2": "inputs larger than L2 (471 MB frame stack "
                        "+ 109 MB parameter/optimiser arenas); no flush", "seed": 0},
             "e2e": e2e, "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu_baseline,
             "torch_gpu_baseline": torch_gpu, "tracking": tracking, "clocks": clocks,

@@ -34,6 +34,8 @@ extern "C" {
 #define ESLAM_N_PLANES 12
 #define ESLAM_DEC_FLOATS 2700 /* 1329 (sdf, padded to 1332) + 1363 (rgb, padded to 1364) + beta, padded */
 #define ESLAM_MAX_SAMPLES 64  /* n_stratified + n_importance per ray */
+#define ESLAM_MAX_PEERS 8    /* GPUs of one NVLink/NVSwitch box */
+#define ESLAM_EXCH_CTAS 592   /* grid of eslam_adam_exchange (4 CTAs per SM), identical on every rank */
 
 #define ESLAM_EINVAL (-1)
 #define ESLAM_EUNSUPPORTED (-2)
@@ -217,6 +219,51 @@ int eslam_pose_adam_step(float* poses, float* pose_grad, float* exp_avg, float* 
  * loss_acc[0..4] are reset to 0. */
 int eslam_finalize_loss(const eslam_render_cfg_t* cfg_host, const int32_t* counters, int tracker_rule,
                         double* loss_acc, float* loss_out, eslam_stream_t s);
+
+/* ---- multi-GPU mapping over peer memory (new in this build; the reference is single-GPU) ---------------------
+ * One process per GPU; every rank owns ONE symmetric (NVLink peer-mapped) allocation holding, at identical
+ * offsets: the parameter arena, a gradient staging block of eslam_exchange_stage_floats(n, world) floats, two
+ * published copies of the aux blocks and counters, and a zero-initialised flag block of
+ * eslam_exchange_flag_words() uint32.  The gradient arena stays in ordinary device memory.  Pointer tables
+ * `x_host[r]` are rank r's copies as mapped into THIS process (index `rank` = local).
+ * `epoch` must increase by one with every exchange call (either kind) and be the same on every rank;
+ * `adam_seq` counts the eslam_adam_exchange calls (1-based); `local_sync` is a local zero-initialised
+ * uint64[2]; `status` is a local int32 that becomes non-zero if a peer did not arrive within 4 s. */
+typedef struct {
+  int32_t rank, world;
+  uint32_t epoch;
+  uint32_t pad_;
+  uint32_t* flags[ESLAM_MAX_PEERS];
+  int32_t* status;
+  uint64_t* local_sync;
+  uint64_t adam_seq;
+} eslam_peers_t;
+
+int eslam_exchange_flag_words(void);
+
+/* norm[i] = sum over ranks of counters[i], i < n <= 8: the all-reduce of the loss normalisers
+ * (front/center/tail/depth/ray counts) that makes every rank differentiate the global-batch loss
+ * (Mapper.py:110-144,337-346 evaluated over the union of the ranks' rays).  `counters` is this rank's block,
+ * pub_host[r] rank r's published copy (alternate between two copies from call to call). */
+int eslam_exchange_counters(const eslam_peers_t* peers_host, const int32_t* counters, int32_t* const* pub_host,
+                            int n, int32_t* norm, eslam_stream_t s);
+
+int64_t eslam_exchange_stage_floats(int64_t n, int world);
+
+/* Reduce-scatter + torch.optim.Adam + all-gather + zero_grad over peer memory, replacing `optimizer.step()` /
+ * `zero_grad()` of Mapper.py:348-350 plus a gradient all-reduce.  Two kernels: (1) every rank stores slice q of
+ * its gradient arena `grad` into rank q's staging (P2P stores) and zeroes it; (2) after a handshake rank r sums
+ * its own slice and the staged rows in rank order, applies the Adam update of eslam_adam_step to slice r
+ * (exp_avg / exp_avg_sq are local, only slice r is touched), zeroes its slice of `grad`, and stores the new
+ * parameters into every rank's arena (P2P stores, or one multimem.st when mc_param != NULL); a closing handshake
+ * makes the stores visible.  The local aux (float, pose gradients) / auxd (double, loss terms) blocks are
+ * published, zeroed, and summed over all ranks into aux_sum / auxd_sum.  The call is identical on every rank. */
+int eslam_adam_exchange(const eslam_peers_t* peers_host, float* const* param_host, float* const* stage_host,
+                        float* grad, float* mc_param, float* exp_avg, float* exp_avg_sq, int64_t n,
+                        const int64_t* seg_end_host, const double* seg_lr_host, int n_seg, int step, double beta1,
+                        double beta2, double eps, float* aux_local, float* const* aux_pub_host, float* aux_sum,
+                        int n_aux, double* auxd_local, double* const* auxd_pub_host, double* auxd_sum, int n_auxd,
+                        eslam_stream_t s);
 
 #ifdef __cplusplus
 }

@@ -42,6 +42,16 @@ class RenderCfg(C.Structure):
                 ("w_color", C.c_double)]
 
 
+MAX_PEERS = 8
+EXCH_CTAS = 592
+
+
+class Peers(C.Structure):
+    _fields_ = [("rank", C.c_int32), ("world", C.c_int32), ("epoch", C.c_uint32), ("pad_", C.c_uint32),
+                ("flags", C.c_void_p * MAX_PEERS), ("status", C.c_void_p), ("local_sync", C.c_void_p),
+                ("adam_seq", C.c_uint64)]
+
+
 _P = C.c_void_p
 _I = C.c_int
 _L = C.c_int64
@@ -71,6 +81,10 @@ PROTOTYPES = {
     "eslam_adam_step": [_P, _P, _P, _P, _L, C.POINTER(C.c_int64), C.POINTER(C.c_double), _I, _I, _D, _D, _D, _P],
     "eslam_pose_adam_step": [_P, _P, _P, _P, _I, _I, _D, _D, _I, _D, _D, _D, _P, _I, _P],
     "eslam_finalize_loss": [_RP, _P, _I, _P, _P, _P],
+    "eslam_exchange_counters": [C.POINTER(Peers), _P, C.POINTER(C.c_void_p), _I, _P, _P],
+    "eslam_adam_exchange": [C.POINTER(Peers), C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), _P, _P, _P, _P, _L,
+                            C.POINTER(C.c_int64), C.POINTER(C.c_double), _I, _I, _D, _D, _D, _P, C.POINTER(C.c_void_p),
+                            _P, _I, _P, C.POINTER(C.c_void_p), _P, _I, _P],
 }
 
 _lib = None
@@ -90,6 +104,10 @@ def load():
     lib.eslam_last_error.argtypes = []
     lib.eslam_abi_version.restype = C.c_int
     lib.eslam_abi_version.argtypes = []
+    lib.eslam_exchange_flag_words.restype = C.c_int
+    lib.eslam_exchange_flag_words.argtypes = []
+    lib.eslam_exchange_stage_floats.restype = C.c_int64
+    lib.eslam_exchange_stage_floats.argtypes = [C.c_int64, C.c_int]
     for name, argtypes in PROTOTYPES.items():
         fn = getattr(lib, name)  # AttributeError if the symbol is not exported
         fn.restype = C.c_int

@@ -9,6 +9,7 @@
 #include "render.cuh"
 #include "sample.cuh"
 #include "optim.cuh"
+#include "exchange.cuh"
 
 using namespace eslam;
 
@@ -505,24 +506,16 @@ int eslam_loss_backward(const eslam_field_t* f, const float* arena, const eslam_
   return 0;
 }
 
-int eslam_adam_step(float* param, float* grad, float* exp_avg, float* exp_avg_sq, int64_t n,
-                    const int64_t* seg_end, const double* seg_lr, int n_seg, int step, double beta1, double beta2,
-                    double eps, eslam_stream_t s) {
-  REQUIRE(param && grad && exp_avg && exp_avg_sq && seg_end && seg_lr && n > 0 && (n % 4) == 0 && n_seg >= 1 &&
-              n_seg <= 4 && step >= 1,
-          "eslam_adam_step");
-  AdamArgs a;
-  a.p = param;
-  a.g = grad;
-  a.m = exp_avg;
-  a.v = exp_avg_sq;
+static int fill_adam(AdamArgs& a, int64_t n, const int64_t* seg_end, const double* seg_lr, int n_seg, int step,
+                     double beta1, double beta2, double eps) {
+  if (!(seg_end && seg_lr && n > 0 && (n % 4) == 0 && n_seg >= 1 && n_seg <= 4 && step >= 1)) return ESLAM_EINVAL;
   a.n = n;
   a.n_seg = n_seg;
   const double bc1 = 1.0 - pow(beta1, (double)step);
   for (int i = 0; i < 4; ++i) {
     a.seg_end[i] = i < n_seg ? seg_end[i] : n;
     a.seg_step[i] = i < n_seg ? (float)(seg_lr[i] / bc1) : 0.f;
-    if (i < n_seg) REQUIRE(seg_end[i] % 4 == 0, "eslam_adam_step(segment alignment)");
+    if (i < n_seg && seg_end[i] % 4 != 0) return ESLAM_EINVAL;
   }
   a.beta1 = (float)beta1;
   a.beta2 = (float)beta2;
@@ -530,11 +523,112 @@ int eslam_adam_step(float* param, float* grad, float* exp_avg, float* exp_avg_sq
   a.one_m_beta2 = (float)(1.0 - beta2);
   a.bc2_sqrt = (float)sqrt(1.0 - pow(beta2, (double)step));
   a.eps = (float)eps;
+  return 0;
+}
+
+int eslam_adam_step(float* param, float* grad, float* exp_avg, float* exp_avg_sq, int64_t n,
+                    const int64_t* seg_end, const double* seg_lr, int n_seg, int step, double beta1, double beta2,
+                    double eps, eslam_stream_t s) {
+  REQUIRE(param && grad && exp_avg && exp_avg_sq, "eslam_adam_step");
+  AdamArgs a;
+  a.p = param;
+  a.g = grad;
+  a.m = exp_avg;
+  a.v = exp_avg_sq;
+  if (fill_adam(a, n, seg_end, seg_lr, n_seg, step, beta1, beta2, eps)) return fail(ESLAM_EINVAL, "eslam_adam_step");
   const long long n4 = n / 4;
   long long blocks = (n4 + 255) / 256;
   if (blocks > 148 * 8) blocks = 148 * 8;
   k_adam<<<(unsigned)blocks, 256, 0, S_(s)>>>(a);
   CHECK_LAUNCH("eslam_adam_step");
+  return 0;
+}
+
+static int fill_peers(PeerSync& ps, const eslam_peers_t* p) {
+  if (!p || p->world < 1 || p->world > MAX_PEERS || p->rank < 0 || p->rank >= p->world || !p->status || !p->local_sync)
+    return ESLAM_EINVAL;
+  ps.rank = p->rank;
+  ps.world = p->world;
+  ps.epoch = p->epoch;
+  ps.status = p->status;
+  ps.local = reinterpret_cast<unsigned long long*>(p->local_sync);
+  ps.done_target = (unsigned long long)p->adam_seq * ESLAM_EXCH_CTAS;
+  for (int r = 0; r < MAX_PEERS; ++r) {
+    ps.flags[r] = r < p->world ? p->flags[r] : nullptr;
+    if (r < p->world && !p->flags[r]) return ESLAM_EINVAL;
+  }
+  return 0;
+}
+
+int eslam_exchange_flag_words(void) { return N_SLOTS * MAX_PEERS; }
+
+int eslam_exchange_counters(const eslam_peers_t* peers, const int32_t* counters, int32_t* const* pub, int n,
+                            int32_t* norm, eslam_stream_t s) {
+  REQUIRE(counters && pub && norm && n >= 1 && n <= 32, "eslam_exchange_counters");
+  CounterExchArgs a;
+  memset(&a, 0, sizeof(a));
+  if (fill_peers(a.ps, peers)) return fail(ESLAM_EINVAL, "eslam_exchange_counters(peers)");
+  for (int r = 0; r < a.ps.world; ++r) {
+    REQUIRE(pub[r], "eslam_exchange_counters(pub)");
+    a.pub[r] = pub[r];
+  }
+  a.local = counters;
+  a.norm = norm;
+  a.n = n;
+  k_exchange_counters<<<1, 32, 0, S_(s)>>>(a);
+  CHECK_LAUNCH("eslam_exchange_counters");
+  return 0;
+}
+
+int64_t eslam_exchange_stage_floats(int64_t n, int world) {
+  if (n <= 0 || world < 1) return 0;
+  const int64_t n4 = n / 4;
+  return 4 * world * ((n4 + world - 1) / world);
+}
+
+int eslam_adam_exchange(const eslam_peers_t* peers, float* const* param, float* const* stage, float* grad,
+                        float* mc_param, float* exp_avg, float* exp_avg_sq, int64_t n, const int64_t* seg_end,
+                        const double* seg_lr, int n_seg, int step, double beta1, double beta2, double eps,
+                        float* aux_local, float* const* aux_pub, float* aux_sum, int n_aux, double* auxd_local,
+                        double* const* auxd_pub, double* auxd_sum, int n_auxd, eslam_stream_t s) {
+  REQUIRE(param && stage && grad && exp_avg && exp_avg_sq && n_aux >= 0 && n_auxd >= 0, "eslam_adam_exchange");
+  REQUIRE(n_aux == 0 || (aux_local && aux_pub && aux_sum), "eslam_adam_exchange(aux)");
+  REQUIRE(n_auxd == 0 || (auxd_local && auxd_pub && auxd_sum), "eslam_adam_exchange(auxd)");
+  AdamExchArgs a;
+  memset(&a, 0, sizeof(a));
+  if (fill_peers(a.ps, peers)) return fail(ESLAM_EINVAL, "eslam_adam_exchange(peers)");
+  REQUIRE(peers->adam_seq >= 1, "eslam_adam_exchange(adam_seq)");
+  if (fill_adam(a.adam, n, seg_end, seg_lr, n_seg, step, beta1, beta2, eps))
+    return fail(ESLAM_EINVAL, "eslam_adam_exchange(adam)");
+  for (int r = 0; r < a.ps.world; ++r) {
+    REQUIRE(param[r] && stage[r], "eslam_adam_exchange(arenas)");
+    a.p[r] = reinterpret_cast<float4*>(param[r]);
+    a.stage[r] = reinterpret_cast<float4*>(stage[r]);
+    if (n_aux) a.aux_pub[r] = aux_pub[r];
+    if (n_auxd) a.auxd_pub[r] = auxd_pub[r];
+  }
+  a.g = reinterpret_cast<float4*>(grad);
+  a.mc_p = reinterpret_cast<float4*>(mc_param);
+  a.m = reinterpret_cast<float4*>(exp_avg);
+  a.v = reinterpret_cast<float4*>(exp_avg_sq);
+  a.aux_local = aux_local;
+  a.aux_sum = aux_sum;
+  a.n_aux = n_aux;
+  a.auxd_local = auxd_local;
+  a.auxd_sum = auxd_sum;
+  a.n_auxd = n_auxd;
+  a.dbg = g_debug;
+  k_grad_push<<<ESLAM_EXCH_CTAS, EXCH_THREADS, 0, S_(s)>>>(a);
+  CHECK_LAUNCH("eslam_adam_exchange(push)");
+  if (mc_param)
+    k_adam_exchange<true, 8><<<ESLAM_EXCH_CTAS, EXCH_THREADS, 0, S_(s)>>>(a);
+  else if (a.ps.world <= 2)
+    k_adam_exchange<false, 2><<<ESLAM_EXCH_CTAS, EXCH_THREADS, 0, S_(s)>>>(a);
+  else if (a.ps.world <= 4)
+    k_adam_exchange<false, 4><<<ESLAM_EXCH_CTAS, EXCH_THREADS, 0, S_(s)>>>(a);
+  else
+    k_adam_exchange<false, 8><<<ESLAM_EXCH_CTAS, EXCH_THREADS, 0, S_(s)>>>(a);
+  CHECK_LAUNCH("eslam_adam_exchange");
   return 0;
 }
 

@@ -6,9 +6,18 @@ batch, and two exchanges per iteration make all ranks differentiate the SAME glo
   2. all-reduce (sum, fp32) of the gradient arena (12 planes + decoders, one contiguous buffer) and of
      the [frames,12] pose-gradient block, over NCCL (NVLink 5 / NVSwitch), then the identical Adam step.
 
-The same code runs on CPU tensors with the gloo backend for the world_size-2 tests.
+`MappingExchange` does both with NCCL collectives (and with gloo on CPU tensors for the world_size-2 tests).
+`PeerExchange` is the B200 path: parameters, two alternating gradient arenas, published pose-gradient / loss /
+counter blocks and a flag block live in ONE symmetric (NVLink peer-mapped) allocation per rank, the normalisers
+are summed by a one-CTA kernel over peer loads, and `eslam_adam_exchange` does reduce-scatter + Adam + all-gather
++ zero_grad in a single kernel over peer memory (P2P loads/stores, or multimem.ld_reduce / multimem.st through
+the NVSwitch).
+No NCCL call is left on the per-iteration path; torch.distributed only sets the allocation up.
 """
 from __future__ import annotations
+
+import ctypes as C
+import os
 
 import torch
 import torch.distributed as dist
@@ -36,6 +45,146 @@ class MappingExchange:
             dist.all_reduce(pose_grad, op=dist.ReduceOp.SUM, group=self.group)
         if loss_acc is not None:
             dist.all_reduce(loss_acc, op=dist.ReduceOp.SUM, group=self.group)
+
+
+class PeerExchange(MappingExchange):
+    """Symmetric-memory exchange for one FieldStore.  Construct it on every rank at the same point (it is
+    collective); afterwards `store.arena` is a view of the symmetric allocation.  The gradient arena stays in
+    ordinary device memory (reductions into peer-mapped memory are slower); peers receive it through a staging
+    block."""
+
+    def __init__(self, store, ws=None, group=None, multimem=None, max_frames=None):
+        super().__init__(group)
+        import torch.distributed._symmetric_memory as symm
+
+        from . import _lib
+
+        if not dist.is_initialized() or self.world < 2:
+            raise RuntimeError("PeerExchange needs an initialised process group with at least 2 ranks")
+        if self.world > _lib.MAX_PEERS:
+            raise RuntimeError(f"PeerExchange supports up to {_lib.MAX_PEERS} GPUs of one box")
+        dev = store.device
+        self.store, self._side = store, None
+        n = store.n_floats
+        frames = max_frames or (ws.max_frames if ws is not None else 32)
+        self.n_pose = frames * 12
+        pose_blk = ((self.n_pose + 3) // 4) * 4
+        flag_words = _lib.load().eslam_exchange_flag_words()
+        n_stage = int(_lib.load().eslam_exchange_stage_floats(n, self.world))
+        self.off_stage = n
+        o = n + n_stage
+        self.off_pose = [o, o + pose_blk]
+        o += 2 * pose_blk
+        self.off_loss = [o, o + 2 * _lib.N_LOSS]  # 16-byte aligned, so the float64 view is aligned
+        o += 4 * _lib.N_LOSS
+        self.off_cnt = [o, o + _lib.N_COUNTERS]
+        o += 2 * _lib.N_COUNTERS
+        self.off_flags = o
+        total = o + flag_words
+        grp = group if group is not None else dist.group.WORLD
+        self.buf = symm.empty(total, dtype=torch.float32, device=dev)
+        self.buf.zero_()
+        self.handle = symm.rendezvous(self.buf, grp.group_name)
+        self.rank = dist.get_rank(group)
+        bases = [int(b) for b in self.handle.buffer_ptrs]
+        mc = int(getattr(self.handle, "multicast_ptr", 0) or 0)
+        if multimem is None:
+            # P2P stores by default; ESLAM_B200_MULTIMEM=1 broadcasts the parameters with one multimem.st per
+            # element through the NVSwitch instead of world_size point-to-point stores
+            multimem = os.environ.get("ESLAM_B200_MULTIMEM", "0") == "1"
+        self.multimem = bool(multimem and mc)
+        self._mc = mc
+
+        def table(off_floats):
+            arr = (C.c_void_p * _lib.MAX_PEERS)()
+            for r in range(self.world):
+                arr[r] = bases[r] + 4 * off_floats
+            return arr
+
+        self._param = table(0)
+        self._stage = table(self.off_stage)
+        self._pose = [table(o_) for o_ in self.off_pose]
+        self._loss = [table(o_) for o_ in self.off_loss]
+        self._cnt = [table(o_) for o_ in self.off_cnt]
+        self.peers = _lib.Peers()
+        self.peers.rank, self.peers.world, self.peers.epoch, self.peers.adam_seq = self.rank, self.world, 0, 0
+        for r in range(self.world):
+            self.peers.flags[r] = bases[r] + 4 * self.off_flags
+        self.status = torch.zeros(1, dtype=torch.int32, device=dev)
+        self.local_sync = torch.zeros(2, dtype=torch.int64, device=dev)
+        self.peers.status = self.status.data_ptr()
+        self.peers.local_sync = self.local_sync.data_ptr()
+        self.norm = torch.zeros(_lib.N_COUNTERS, dtype=torch.int32, device=dev)
+        self.pose_sum = torch.zeros(frames, 12, dtype=torch.float32, device=dev)
+        self.loss_sum = torch.zeros(_lib.N_LOSS, dtype=torch.float64, device=dev)
+        self._n_cnt = 0
+        # move the store's arenas into the symmetric allocation
+        arena = self.buf[:n]
+        arena.copy_(store.arena)
+        store.arena = arena
+        store.ensure_grad()
+        torch.cuda.synchronize(dev)
+        dist.barrier(group)  # nobody signals into a flag block that is not zeroed yet
+
+    def _next_epoch(self):
+        self.peers.epoch = (self.peers.epoch + 1) & 0x7FFFFFFF
+        return C.byref(self.peers)
+
+    def _counters_call(self, counters, cuda_stream):
+        from ._lib import N_COUNTERS, call, ptr
+
+        par = self._n_cnt & 1
+        self._n_cnt += 1
+        call("eslam_exchange_counters", self._next_epoch(), ptr(counters), self._cnt[par], N_COUNTERS, ptr(self.norm),
+             cuda_stream)
+        return self.norm
+
+    def reduce_counters(self, counters: torch.Tensor) -> torch.Tensor:
+        from ._lib import stream
+
+        return self._counters_call(counters, stream())
+
+    def begin_counters(self, counters: torch.Tensor) -> torch.Tensor:
+        """reduce_counters on a side stream, so the peer round trip overlaps the kernels launched until
+        end_counters() (the importance sampling of depth-less rays, which only reads the LOCAL counters)."""
+        if self._side is None:
+            self._side = torch.cuda.Stream(device=self.store.device)
+            self._ev_fork, self._ev_join = torch.cuda.Event(), torch.cuda.Event()
+        self._ev_fork.record()
+        self._side.wait_event(self._ev_fork)
+        norm = self._counters_call(counters, self._side.cuda_stream)
+        self._ev_join.record(self._side)
+        return norm
+
+    def end_counters(self) -> None:
+        torch.cuda.current_stream().wait_event(self._ev_join)
+
+    def adam_exchange(self, step: int, lr_dec: float, lr_planes: float, lr_cplanes: float, pose_grad=None,
+                      n_pose_frames: int = 0, loss_acc=None, betas=(0.9, 0.999), eps=1e-8):
+        """The fused optimiser step of the ray-sharded mapping on `store.grad` (this iteration's gradient arena).
+        pose_grad [frames,12] / loss_acc float64[>=5] are this rank's local blocks: published, zeroed and summed
+        over the ranks.  Returns (pose_grad_sum, loss_sum).  store.grad is zero afterwards."""
+        from ._lib import call, ptr, stream
+
+        st = self.store
+        if n_pose_frames * 12 > self.n_pose:
+            raise RuntimeError("PeerExchange: more frames than the published pose block was sized for")
+        par = self.peers.adam_seq & 1
+        self.peers.adam_seq += 1
+        seg_end = (C.c_int64 * 3)(st.n_sdf_end, st.n_planes_end, st.n_floats)
+        seg_lr = (C.c_double * 3)(lr_planes, lr_cplanes, lr_dec)
+        n_aux = n_pose_frames * 12 if pose_grad is not None else 0
+        n_auxd = 5 if loss_acc is not None else 0
+        call("eslam_adam_exchange", self._next_epoch(), self._param, self._stage, ptr(st.grad),
+             self._mc if self.multimem else None, ptr(st.exp_avg), ptr(st.exp_avg_sq), st.n_floats, seg_end, seg_lr, 3,
+             step, betas[0], betas[1], eps, ptr(pose_grad) if n_aux else None, self._pose[par], ptr(self.pose_sum),
+             n_aux, ptr(loss_acc) if n_auxd else None, self._loss[par], ptr(self.loss_sum), n_auxd, stream())
+        return self.pose_sum, self.loss_sum
+
+    def check(self) -> None:
+        """Raise if a peer ever failed to arrive at a barrier (host sync)."""
+        if int(self.status.item()) != 0:
+            raise RuntimeError("PeerExchange: a peer did not reach an exchange barrier within 4 s")
 
 
 def shard_range(total: int, rank: int, world: int):

@@ -136,13 +136,17 @@ def tracking_iteration(ws: Workspace, store: FieldStore, sc: StepCfg, pose7: tor
 def mapping_iteration(ws: Workspace, store: FieldStore, sc: StepCfg, c2ws, poses7, gt_colors, gt_depths,
                       pix_per_image: int, step: int, lr_dec: float, lr_planes: float, lr_cplanes: float,
                       lr_cam: float, draws=None, strict_rng: bool = False, want_loss: bool = False,
-                      apply_adam: bool = True, reduce_counters=None, reduce_grads=None):
+                      apply_adam: bool = True, reduce_counters=None, reduce_grads=None, exchange=None):
     """One iteration of the loop in Mapper.optimize_mapping (Mapper.py:308-350).
     c2ws [b,4,4] fp32; poses7 [b,7] or None (joint_opt: frames 1.. are taken from poses7 and updated).
     Planes/decoders live in `store` (Adam state in store.exp_avg*, reset by the caller per call).
     reduce_counters(counters)->norm and reduce_grads(grad, pose_grad, loss_acc) are the two exchange
-    points of the ray-sharded multi-GPU mapping (myslam_b200.dist); None on one GPU."""
+    points of the ray-sharded multi-GPU mapping (myslam_b200.dist); None on one GPU.  `exchange` is an object
+    providing both; a dist.PeerExchange additionally replaces all-reduce + Adam by the fused peer-memory kernel."""
     dev = ws.device
+    if exchange is not None:
+        reduce_counters, reduce_grads = exchange.reduce_counters, exchange.reduce_grads
+    fused_exchange = apply_adam and exchange is not None and hasattr(exchange, "adam_exchange")
     draws = draws or TorchDraws(dev)
     cam, rc = sc.cam, sc.render
     ns, ni = rc.n_stratified, rc.n_importance
@@ -164,6 +168,9 @@ def mapping_iteration(ws: Workspace, store: FieldStore, sc: StepCfg, c2ws, poses
         r0 = N
         u = draws.rand(N, S) if sc.perturb else None
     _sample(ws, store, sc, idx, b, pix_per_image, c2w_flat, poses7, 1, gt_depths, gt_colors, u, 0)
+    norm, overlapped = None, exchange is not None and hasattr(exchange, "begin_counters")
+    if overlapped:  # the counters are final here; their exchange overlaps the importance sampling below
+        norm = exchange.begin_counters(ws.counters)
     if r0 > 0:
         u_c = draws.rand(r0, ns)
         u_f = draws.rand(r0, ni)
@@ -171,11 +178,25 @@ def mapping_iteration(ws: Workspace, store: FieldStore, sc: StepCfg, c2ws, poses
              ptr(ws.dl_list), ptr(ws.counters), r0, ptr(u_c), ptr(u_f), ptr(linspace_table(ns, dev)), ptr(ws.z),
              stream())
     grad = store.ensure_grad()
-    norm = reduce_counters(ws.counters) if reduce_counters is not None else None
+    if overlapped:
+        exchange.end_counters()
+    elif reduce_counters is not None:
+        norm = reduce_counters(ws.counters)
     call("eslam_loss_backward", store.ref(), ptr(store.arena), C.byref(cam), C.byref(rc), ptr(ws.rays_o),
          ptr(ws.rays_d), ptr(ws.z), ptr(ws.gt_depth), ptr(ws.gt_color), ptr(ws.src), ptr(idx), pix_per_image, None,
          ptr(ws.counters), ptr(norm) if norm is not None else None, N, ptr(grad),
          ptr(ws.pose_grad) if joint else None, ptr(ws.loss_acc) if want_loss else None, stream())
+    if fused_exchange:
+        # reduce-scatter + Adam + all-gather + zero_grad in one kernel over peer memory (csrc/exchange.cuh)
+        pose_sum, loss_sum = exchange.adam_exchange(step, lr_dec, lr_planes, lr_cplanes, ws.pose_grad if joint else None,
+                                                    b, ws.loss_acc if want_loss else None)
+        if want_loss:
+            call("eslam_finalize_loss", C.byref(rc), ptr(norm), 0, ptr(loss_sum), ptr(ws.loss_out), stream())
+            ws.loss_acc[5:7].copy_(loss_sum[5:7])
+        if joint:
+            call("eslam_pose_adam_step", ptr(poses7), ptr(pose_sum), ptr(ws.pose_m), ptr(ws.pose_v), b, 1, lr_cam,
+                 lr_cam, step, 0.9, 0.999, 1e-8, ptr(ws.grad7), 1, stream())
+        return
     if reduce_grads is not None:
         reduce_grads(grad, ws.pose_grad if joint else None, ws.loss_acc if want_loss else None)
     if want_loss:

@@ -24,10 +24,11 @@ def _strict_default() -> bool:
 
 def map_window(store: FieldStore, ws: Workspace, sc: StepCfg, c2ws, gt_colors, gt_depths, n_pixels: int, iters: int,
                lr_dec: float, lr_planes: float, lr_cplanes: float, joint_opt: bool, lr_cam: float, draws=None,
-               strict_rng: bool = False, losses: Optional[list] = None):
+               strict_rng: bool = False, losses: Optional[list] = None, exchange=None):
     """The loop of Mapper.optimize_mapping (Mapper.py:288-350) for an already chosen window:
     fresh Adam state, `iters` fused iterations on `store`.  Returns the window's c2ws [b,4,4] after the
-    call (frame 0 is held fixed, Mapper.py:314)."""
+    call (frame 0 is held fixed, Mapper.py:314).  `exchange` (myslam_b200.dist) makes the call one rank of a
+    ray-sharded multi-GPU mapping: every rank passes the same window and draws its own `n_pixels` rays."""
     b = c2ws.shape[0]
     pix = n_pixels // b
     store.reset_adam()
@@ -42,7 +43,8 @@ def map_window(store: FieldStore, ws: Workspace, sc: StepCfg, c2ws, gt_colors, g
     c2ws = c2ws.float().contiguous()
     for it in range(iters):
         mapping_iteration(ws, store, sc, c2ws, poses7, gt_colors, gt_depths, pix, it + 1, lr_dec, lr_planes,
-                          lr_cplanes, lr_cam, draws=draws, strict_rng=strict_rng, want_loss=losses is not None)
+                          lr_cplanes, lr_cam, draws=draws, strict_rng=strict_rng, want_loss=losses is not None,
+                          exchange=exchange)
         if losses is not None:
             losses.append(ws.loss_acc[5].clone())
     if joint_opt and b > 1:
@@ -125,7 +127,7 @@ def optimize_mapping(self, iters, lr_factor, idx, cur_gt_color, cur_gt_depth, gt
                           lr['decoders_lr'] * lr_factor, lr['planes_lr'] * lr_factor, lr['c_planes_lr'] * lr_factor,
                           bool(self.joint_opt), self.joint_opt_cam_lr, draws=getattr(self, "draws", None),
                           strict_rng=getattr(self, "strict_rng", _strict_default()),
-                          losses=getattr(self, "loss_log", None))
+                          losses=getattr(self, "loss_log", None), exchange=getattr(self, "exchange", None))
     # ---- write the map back into the storage ESLAM owns (shared with the tracker process)
     store.push_planes(all_planes)
     store.push_decoders(self.decoders)

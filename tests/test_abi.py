@@ -29,7 +29,8 @@ def test_binding_covers_header_and_arity():
     text = open(os.path.join(ROOT, "include", "eslam_b200.h")).read()
     text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
     for name in header_functions():
-        if name in ("eslam_last_error", "eslam_abi_version", "eslam_set_debug"):
+        if name in ("eslam_last_error", "eslam_abi_version", "eslam_set_debug", "eslam_exchange_flag_words",
+                    "eslam_exchange_stage_floats"):
             continue
         assert name in L.PROTOTYPES, f"{name} has no ctypes prototype"
         m = re.search(name + r"\s*\((.*?)\)\s*;", text, flags=re.S)
@@ -45,6 +46,8 @@ def test_struct_layouts_match_header():
     assert ctypes.sizeof(L.Camera) == 40
     assert ctypes.sizeof(L.RenderCfg) == 8 + 6 * 8
     assert L.DEC_FLOATS % 4 == 0 and L.DEC_BETA < L.DEC_FLOATS
+    assert ctypes.sizeof(L.Peers) == 16 + 8 * L.MAX_PEERS + 8 + 8 + 8
+    assert L.load().eslam_exchange_flag_words() == 4 * L.MAX_PEERS
 
 
 def test_missing_library_fails_loudly(monkeypatch):
