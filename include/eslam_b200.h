@@ -146,6 +146,19 @@ int eslam_sample_rays(const eslam_field_t* field_host, const eslam_camera_t* cam
                       int32_t* src, float* z, int32_t* dl_list, int32_t* zord, uint8_t* band, int32_t* counters,
                       float* c2w_out, eslam_stream_t s);
 
+/* eslam_sample_rays with the window's frames given as two DEVICE tables of n_img per-frame pointers
+ * (depth_frames[k] -> [H][W] f32, color_frames[k] -> [H][W][3] f64) instead of one stacked tensor, so the
+ * keyframes of a window are read where they live and Mapper.py:268-286's torch.stack of up to 20 full frames
+ * (457 MB per call at Replica size) is not needed. */
+int eslam_sample_rays_frames(const eslam_field_t* field_host, const eslam_camera_t* cam_host,
+                             const eslam_render_cfg_t* cfg_host, const int64_t* pix_idx, int n_img, int n_per_img,
+                             const float* c2w, const float* poses, int pose_first,
+                             const float* const* depth_frames, const double* const* color_frames,
+                             const float* u_depth, const float* t_uni, const float* t_surf, int need_depth,
+                             float* rays_o, float* rays_d, float* gt_depth, double* gt_color, int32_t* src, float* z,
+                             int32_t* dl_list, int32_t* zord, uint8_t* band, int32_t* counters, float* c2w_out,
+                             eslam_stream_t s);
+
 /* Depth-guided z_vals for an already compacted ray list with explicit gt_depth (the first half of
  * render_batch_ray when called through the reference's API, Renderer.py:88-106): fills the z rows of
  * depth>0 rays, lists the others in dl_list, counters[0]=n_rays, counters[1]=R0. */
@@ -219,6 +232,16 @@ int eslam_pose_adam_step(float* poses, float* pose_grad, float* exp_avg, float* 
  * loss_acc[0..4] are reset to 0. */
 int eslam_finalize_loss(const eslam_render_cfg_t* cfg_host, const int32_t* counters, int tracker_rule,
                         double* loss_acc, float* loss_out, eslam_stream_t s);
+
+/* Mapper.keyframe_selection_overlap (Mapper.py:146-203) up to `percent_inside`: the n_rays pixels pix_idx
+ * (draws of randint(H*W), common.py:108) of the current frame that have depth > 0 are lifted to n_samples points
+ * each between 0.8*d and d+0.5 (t_vals = linspace(0,1,n_samples)), projected into every keyframe kf_c2w[k]
+ * (row-major 4x4 c2w, inverted here) and counted when they fall inside the image with a 20-pixel margin, in
+ * front of the camera.  inside[k] = count for keyframe k, n_pts[0] = points tested; the reference's
+ * percent_inside[k] = inside[k] / n_pts.  The caller keeps nonzero(inside) in randperm order (Mapper.py:205-209). */
+int eslam_keyframe_overlap(const eslam_camera_t* cam_host, const float* c2w, const float* depth,
+                           const int64_t* pix_idx, int n_rays, const float* t_vals, int n_samples,
+                           const float* kf_c2w, int n_keyframes, int32_t* inside, int32_t* n_pts, eslam_stream_t s);
 
 /* ---- multi-GPU mapping over peer memory (new in this build; the reference is single-GPU) ---------------------
  * One process per GPU; every rank owns ONE symmetric (NVLink peer-mapped) allocation holding, at identical

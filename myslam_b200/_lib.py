@@ -11,7 +11,7 @@ import os
 import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libeslam_b200.so")
+LIB_PATH = os.environ.get("ESLAM_B200_LIB") or os.path.join(_HERE, "libeslam_b200.so")  # override: kernel experiments
 
 N_PLANES = 12
 DEC_FLOATS = 2700
@@ -72,6 +72,8 @@ PROTOTYPES = {
     "eslam_grid_sdf": [_FP, _P, _P, _P, _P, _I, _I, _I, _L, _L, _P, _P],
     "eslam_sample_rays": [_FP, _CP, _RP, _P, _I, _I, _P, _P, _I, _P, _P, _P, _P, _P, _I, _P, _P, _P, _P, _P, _P, _P,
                           _P, _P, _P, _P, _P],
+    "eslam_sample_rays_frames": [_FP, _CP, _RP, _P, _I, _I, _P, _P, _I, _P, _P, _P, _P, _P, _I, _P, _P, _P, _P, _P, _P,
+                                 _P, _P, _P, _P, _P, _P],
     "eslam_depth_samples": [_RP, _P, _I, _P, _P, _P, _P, _P, _P, _P, _P],
     "eslam_importance_samples": [_FP, _P, _RP, _P, _P, _P, _P, _I, _P, _P, _P, _P, _P],
     "eslam_render_forward": [_FP, _P, _P, _P, _P, _I, _I, _P, _P, _P, _P, _P],
@@ -81,6 +83,7 @@ PROTOTYPES = {
     "eslam_adam_step": [_P, _P, _P, _P, _L, C.POINTER(C.c_int64), C.POINTER(C.c_double), _I, _I, _D, _D, _D, _P],
     "eslam_pose_adam_step": [_P, _P, _P, _P, _I, _I, _D, _D, _I, _D, _D, _D, _P, _I, _P],
     "eslam_finalize_loss": [_RP, _P, _I, _P, _P, _P],
+    "eslam_keyframe_overlap": [_CP, _P, _P, _P, _I, _P, _I, _P, _I, _P, _P, _P],
     "eslam_exchange_counters": [C.POINTER(Peers), _P, C.POINTER(C.c_void_p), _I, _P, _P],
     "eslam_adam_exchange": [C.POINTER(Peers), C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), _P, _P, _P, _P, _L,
                             C.POINTER(C.c_int64), C.POINTER(C.c_double), _I, _I, _D, _D, _D, _P, C.POINTER(C.c_void_p),

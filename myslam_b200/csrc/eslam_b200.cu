@@ -10,6 +10,7 @@
 #include "sample.cuh"
 #include "optim.cuh"
 #include "exchange.cuh"
+#include "keyframes.cuh"
 
 using namespace eslam;
 
@@ -171,12 +172,13 @@ int eslam_grid_sdf(const eslam_field_t* f, const float* arena, const float* xs, 
   return 0;
 }
 
-int eslam_sample_rays(const eslam_field_t* f, const eslam_camera_t* cam, const eslam_render_cfg_t* cfg,
-                      const int64_t* pix_idx, int n_img, int n_per_img, const float* c2w, const float* poses,
-                      int pose_first, const float* depth, const double* color, const float* u_depth,
-                      const float* t_uni, const float* t_surf, int need_depth, float* rays_o, float* rays_d,
-                      float* gt_depth, double* gt_color, int32_t* src, float* z, int32_t* dl_list, int32_t* zord,
-                      uint8_t* band, int32_t* counters, float* c2w_out, eslam_stream_t s) {
+static int sample_rays_impl(const eslam_field_t* f, const eslam_camera_t* cam, const eslam_render_cfg_t* cfg,
+                            const int64_t* pix_idx, int n_img, int n_per_img, const float* c2w, const float* poses,
+                            int pose_first, const float* depth, const double* color, bool frame_table,
+                            const float* u_depth, const float* t_uni, const float* t_surf, int need_depth,
+                            float* rays_o, float* rays_d, float* gt_depth, double* gt_color, int32_t* src, float* z,
+                            int32_t* dl_list, int32_t* zord, uint8_t* band, int32_t* counters, float* c2w_out,
+                            eslam_stream_t s) {
   REQUIRE(f && cam && cfg && pix_idx && depth && color && t_uni && t_surf && rays_o && rays_d && gt_depth &&
               gt_color && src && z && dl_list && zord && band && counters && n_img > 0 && n_per_img > 0 &&
               (c2w || poses),
@@ -213,8 +215,13 @@ int eslam_sample_rays(const eslam_field_t* f, const eslam_camera_t* cam, const e
   a.c2w = c2w;
   a.poses = poses;
   a.pose_first = pose_first;
-  a.depth = depth;
-  a.color = color;
+  if (frame_table) {
+    a.depth_tab = reinterpret_cast<const float* const*>(depth);
+    a.color_tab = reinterpret_cast<const double* const*>(color);
+  } else {
+    a.depth = depth;
+    a.color = color;
+  }
   a.u_depth = u_depth;
   a.t_uni = t_uni;
   a.t_surf = t_surf;
@@ -254,6 +261,31 @@ int eslam_sample_rays(const eslam_field_t* f, const eslam_camera_t* cam, const e
   k_ray_samples<<<(N + SB / 32 - 1) / (SB / 32), SB, 0, S_(s)>>>(b);
   CHECK_LAUNCH("eslam_sample_rays(samples)");
   return 0;
+}
+
+
+int eslam_sample_rays(const eslam_field_t* f, const eslam_camera_t* cam, const eslam_render_cfg_t* cfg,
+                      const int64_t* pix_idx, int n_img, int n_per_img, const float* c2w, const float* poses,
+                      int pose_first, const float* depth, const double* color, const float* u_depth,
+                      const float* t_uni, const float* t_surf, int need_depth, float* rays_o, float* rays_d,
+                      float* gt_depth, double* gt_color, int32_t* src, float* z, int32_t* dl_list, int32_t* zord,
+                      uint8_t* band, int32_t* counters, float* c2w_out, eslam_stream_t s) {
+  return sample_rays_impl(f, cam, cfg, pix_idx, n_img, n_per_img, c2w, poses, pose_first, depth, color, false, u_depth,
+                          t_uni, t_surf, need_depth, rays_o, rays_d, gt_depth, gt_color, src, z, dl_list, zord, band,
+                          counters, c2w_out, s);
+}
+
+int eslam_sample_rays_frames(const eslam_field_t* f, const eslam_camera_t* cam, const eslam_render_cfg_t* cfg,
+                             const int64_t* pix_idx, int n_img, int n_per_img, const float* c2w, const float* poses,
+                             int pose_first, const float* const* depth_frames, const double* const* color_frames,
+                             const float* u_depth, const float* t_uni, const float* t_surf, int need_depth,
+                             float* rays_o, float* rays_d, float* gt_depth, double* gt_color, int32_t* src, float* z,
+                             int32_t* dl_list, int32_t* zord, uint8_t* band, int32_t* counters, float* c2w_out,
+                             eslam_stream_t s) {
+  return sample_rays_impl(f, cam, cfg, pix_idx, n_img, n_per_img, c2w, poses, pose_first,
+                          reinterpret_cast<const float*>(depth_frames), reinterpret_cast<const double*>(color_frames),
+                          true, u_depth, t_uni, t_surf, need_depth, rays_o, rays_d, gt_depth, gt_color, src, z, dl_list,
+                          zord, band, counters, c2w_out, s);
 }
 
 int eslam_depth_samples(const eslam_render_cfg_t* cfg, const float* gt_depth, int n_rays, const float* u_depth,
@@ -659,6 +691,35 @@ int eslam_pose_adam_step(float* poses, float* pose_grad, float* exp_avg, float* 
   const int cnt = n - first;
   k_pose_adam<<<(cnt + 31) / 32, 32, 0, S_(s)>>>(a);
   CHECK_LAUNCH("eslam_pose_adam_step");
+  return 0;
+}
+
+int eslam_keyframe_overlap(const eslam_camera_t* cam, const float* c2w, const float* depth, const int64_t* pix_idx,
+                           int n_rays, const float* t_vals, int n_samples, const float* kf_c2w, int n_keyframes,
+                           int32_t* inside, int32_t* n_pts, eslam_stream_t s) {
+  REQUIRE(cam && c2w && depth && pix_idx && t_vals && kf_c2w && inside && n_pts && n_rays > 0 && n_samples > 0 &&
+              n_keyframes >= 0,
+          "eslam_keyframe_overlap");
+  if (n_keyframes == 0) return 0;
+  OverlapArgs a;
+  a.c2w = c2w;
+  a.depth = depth;
+  a.pix_idx = reinterpret_cast<const long long*>(pix_idx);
+  a.t_vals = t_vals;
+  a.kf_c2w = kf_c2w;
+  a.n_rays = n_rays;
+  a.n_samples = n_samples;
+  a.K = n_keyframes;
+  a.H = cam->H;
+  a.W = cam->W;
+  a.fx = cam->fx;
+  a.fy = cam->fy;
+  a.cx = cam->cx;
+  a.cy = cam->cy;
+  a.inside = inside;
+  a.n_pts = n_pts;
+  k_keyframe_overlap<<<n_keyframes, OVERLAP_THREADS, 0, S_(s)>>>(a);
+  CHECK_LAUNCH("eslam_keyframe_overlap");
   return 0;
 }
 

@@ -175,7 +175,7 @@ __device__ __forceinline__ void gather_features(const FieldK& fk, int field, con
 }
 
 // decoder weights for the forward-only kernels, filled by eslam_bind_decoders (one translation unit)
-__constant__ float c_dec[DEC_N];
+__constant__ __align__(16) float c_dec[DEC_N];
 
 // ---- forward MLP, weights as constant-memory operands, fully unrolled -----------------------------------
 // Used by the forward-only kernels (decode, render forward, importance): there the ~4 k straight-line

@@ -22,8 +22,10 @@ struct SampleArgs {
   const float* c2w;
   const float* poses;
   int pose_first;
-  const float* depth;
-  const double* color;
+  const float* depth;               // [n_img][H][W], or NULL when the per-frame tables below are used
+  const double* color;              // [n_img][H][W][3]
+  const float* const* depth_tab;    // [n_img] device pointers to [H][W] frames (keyframes stay where they are)
+  const double* const* color_tab;   // [n_img] device pointers to [H][W][3] frames
   const float* u_depth;
   const float *t_uni, *t_surf;
   int need_depth;
@@ -88,7 +90,8 @@ __device__ __forceinline__ RayEval eval_ray(const SampleArgs& a, int slot) {
   const long long pix = a.pix_idx[slot];
   const int pr = (int)(pix / a.Wc), pc = (int)(pix - (long long)pr * a.Wc);
   const float pi = (float)(a.W0 + pc), pj = (float)(a.H0 + pr);
-  r.depth = a.depth[((long long)frame * a.H + (a.H0 + pr)) * a.W + (a.W0 + pc)];
+  const float* dframe = a.depth_tab ? a.depth_tab[frame] : a.depth + (long long)frame * a.H * a.W;
+  r.depth = dframe[(long long)(a.H0 + pr) * a.W + (a.W0 + pc)];
   float Rm[9], t[3];
   if (a.poses && frame >= a.pose_first) {
     const float* p = a.poses + frame * 7;
@@ -268,7 +271,8 @@ __global__ void __launch_bounds__(SB) k_sample_rays(const __grid_constant__ Samp
       a.rays_d[r * 3 + x] = e.d[x];
     }
     a.gt_depth[r] = e.depth;
-    const double* cp = a.color + (((long long)frame * a.H + (a.H0 + pr)) * a.W + (a.W0 + pc)) * 3;
+    const double* cframe = a.color_tab ? a.color_tab[frame] : a.color + (long long)frame * a.H * a.W * 3;
+    const double* cp = cframe + ((long long)(a.H0 + pr) * a.W + (a.W0 + pc)) * 3;
     a.gt_color[(long long)r * 3 + 0] = cp[0];
     a.gt_color[(long long)r * 3 + 1] = cp[1];
     a.gt_color[(long long)r * 3 + 2] = cp[2];

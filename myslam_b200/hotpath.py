@@ -73,18 +73,50 @@ class StepCfg:
     perturb: bool = True
 
 
+class FrameTable:
+    """The frames of a mapping window, read by the sampling kernel WHERE THEY LIVE through a device table of
+    per-frame pointers, instead of the reference's torch.stack of up to 20 full frames per call
+    (Mapper.py:268-286: 457 MB of copies at Replica size).  colors[k]: [H,W,3] float64, depths[k]: [H,W] float32,
+    contiguous CUDA tensors; the table keeps them alive."""
+
+    def __init__(self, colors, depths, cam: Camera, device):
+        if len(colors) != len(depths) or len(depths) == 0:
+            raise RuntimeError("FrameTable: need the same (non-zero) number of colour and depth frames")
+        dev = torch.device(device)
+        for c, d in zip(colors, depths):
+            if not (c.is_cuda and d.is_cuda) or c.device != d.device:
+                raise RuntimeError("FrameTable: frames must be CUDA tensors of one device; there is no CPU path")
+            if d.dtype != torch.float32 or c.dtype != torch.float64:
+                raise RuntimeError("gt depth must be float32 and gt colour float64, as the reference's datasets "
+                                   "produce (src/utils/datasets.py:90-92)")
+            if tuple(d.shape) != (cam.H, cam.W) or tuple(c.shape) != (cam.H, cam.W, 3):
+                raise RuntimeError(f"frame shapes {tuple(d.shape)} / {tuple(c.shape)} do not match the camera")
+            if not (d.is_contiguous() and c.is_contiguous()):
+                raise RuntimeError("frames must be contiguous")
+        self.colors, self.depths, self.n = list(colors), list(depths), len(depths)
+        host = torch.tensor([[d.data_ptr() for d in depths], [c.data_ptr() for c in colors]], dtype=torch.int64)
+        self.table = host.to(dev)  # [2][n] device pointers
+
+
 def _sample(ws: Workspace, store: FieldStore, sc: StepCfg, idx, n_img, n_per_img, c2w, poses, pose_first, depth,
             color, u_depth, need_depth):
     dev = ws.device
     t_uni = linspace_table(sc.render.n_stratified, dev)
     t_surf = linspace_table(sc.render.n_importance, dev)
-    call("eslam_sample_rays", store.ref(), C.byref(sc.cam), C.byref(sc.render), ptr(idx), n_img, n_per_img, ptr(c2w),
+    entry = "eslam_sample_rays"
+    if isinstance(depth, FrameTable):
+        entry, color, depth = "eslam_sample_rays_frames", depth.table[1], depth.table[0]
+    call(entry, store.ref(), C.byref(sc.cam), C.byref(sc.render), ptr(idx), n_img, n_per_img, ptr(c2w),
          ptr(poses), pose_first, ptr(depth), ptr(color), ptr(u_depth), ptr(t_uni), ptr(t_surf), need_depth,
          ptr(ws.rays_o), ptr(ws.rays_d), ptr(ws.gt_depth), ptr(ws.gt_color), ptr(ws.src), ptr(ws.z),
          ptr(ws.dl_list), ptr(ws.zord), ptr(ws.band), ptr(ws.counters), ptr(ws.c2w_out), stream())
 
 
 def _check_frames(depth, color, n_img, cam):
+    if isinstance(depth, FrameTable):
+        if color is not depth or depth.n != n_img:
+            raise RuntimeError("pass the same FrameTable as gt_colors and gt_depths, one frame per camera")
+        return
     if depth.dtype != torch.float32 or color.dtype != torch.float64:
         raise RuntimeError("gt depth must be float32 and gt colour float64, as the reference's datasets produce "
                            "(src/utils/datasets.py:90-92)")
@@ -139,6 +171,7 @@ def mapping_iteration(ws: Workspace, store: FieldStore, sc: StepCfg, c2ws, poses
                       apply_adam: bool = True, reduce_counters=None, reduce_grads=None, exchange=None):
     """One iteration of the loop in Mapper.optimize_mapping (Mapper.py:308-350).
     c2ws [b,4,4] fp32; poses7 [b,7] or None (joint_opt: frames 1.. are taken from poses7 and updated).
+    gt_colors / gt_depths: stacked [b,H,W,3] f64 / [b,H,W] f32 tensors, or one FrameTable passed as both.
     Planes/decoders live in `store` (Adam state in store.exp_avg*, reset by the caller per call).
     reduce_counters(counters)->norm and reduce_grads(grad, pose_grad, loss_acc) are the two exchange
     points of the ray-sharded multi-GPU mapping (myslam_b200.dist); None on one GPU.  `exchange` is an object

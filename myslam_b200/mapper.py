@@ -6,6 +6,7 @@ parameter arena; the arena is written back to the reference's [1,32,H,W] tensors
 """
 from __future__ import annotations
 
+import ctypes as C
 import os
 from typing import List, Optional
 
@@ -14,7 +15,9 @@ import torch
 from .common import cam_pose_to_matrix, get_samples, matrix_to_cam_pose, random_select
 from .decoders import decoder_tensors, synced_store
 from .field import FieldStore
-from .hotpath import StepCfg, Workspace, make_camera, mapping_iteration
+from ._lib import call, ptr, stream
+from .hotpath import FrameTable, StepCfg, Workspace, make_camera, mapping_iteration
+from .renderer import TorchDraws, linspace_table
 from .renderer import make_cfg
 
 
@@ -53,33 +56,46 @@ def map_window(store: FieldStore, ws: Workspace, sc: StepCfg, c2ws, gt_colors, g
 
 
 def keyframe_selection_overlap(self, gt_color, gt_depth, c2w, num_keyframes, num_samples=8, num_rays=50):
-    """Keyframes whose frusta see the current view's surface (reference Mapper.py:146-209); torch ops,
-    once per mapped frame.  Returns a list of indices into keyframe_dict."""
+    """Keyframes whose frusta see the current view's surface (reference Mapper.py:146-209): one kernel projects the
+    50 x 8 sample points into every keyframe (eslam_keyframe_overlap); the pixel draw (randint, common.py:108),
+    the nonzero + CPU randperm pick (Mapper.py:205-209) and the returned list are the reference's."""
     device = self.device
-    H, W, fx, fy, cx, cy = self.H, self.W, self.fx, self.fy, self.cx, self.cy
-    rays_o, rays_d, d, _ = get_samples(0, H, 0, W, num_rays, H, W, fx, fy, cx, cy, c2w.unsqueeze(0),
-                                       gt_depth.unsqueeze(0), gt_color.unsqueeze(0), device)
-    ok = d > 0
-    rays_o, rays_d, d = rays_o[ok], rays_d[ok], d[ok].reshape(-1, 1).repeat(1, num_samples)
-    t = torch.linspace(0., 1., steps=num_samples).to(device)
-    z = (d * 0.8) * (1. - t) + (d + 0.5) * t
-    pts = (rays_o[:, None, :] + rays_d[:, None, :] * z[..., None]).reshape(1, -1, 3)
-    kf_c2w = torch.stack([self.estimate_c2w_list[i] for i in self.keyframe_list], dim=0)
-    w2c = torch.inverse(kf_c2w[:-2])  # the last two keyframes are always in the window
-    homo = torch.cat([pts, torch.ones_like(pts[..., :1])], -1).reshape(1, -1, 4, 1).expand(w2c.shape[0], -1, -1, -1)
-    cam = (w2c.unsqueeze(1).expand(-1, homo.shape[1], -1, -1) @ homo)[:, :, :3]
-    K = torch.tensor([[fx, .0, cx], [.0, fy, cy], [.0, .0, 1.0]], device=device)
-    cam[:, :, 0] *= -1
-    uv = K @ cam
-    zc = uv[:, :, -1:] + 1e-5
-    uv = uv[:, :, :2] / zc
-    edge = 20
-    inside = (uv[:, :, 0] < W - edge) * (uv[:, :, 0] > edge) * (uv[:, :, 1] < H - edge) * (uv[:, :, 1] > edge)
-    inside = (inside & (zc[:, :, 0] < 0)).squeeze(-1)
-    frac = inside.sum(dim=1) / uv.shape[1]
-    sel = torch.nonzero(frac).squeeze(-1)
+    draws = getattr(self, "draws", None) or TorchDraws(device)
+    idx = draws.randint(self.H * self.W, num_rays)
+    kf_c2w = torch.stack([self.estimate_c2w_list[i] for i in self.keyframe_list], dim=0)[:-2]  # last two: always in
+    K = kf_c2w.shape[0]
+    if K == 0:
+        return []
+    kf_c2w = kf_c2w.to(device=device, dtype=torch.float32).reshape(K, 16).contiguous()
+    depth = gt_depth.to(device=device, dtype=torch.float32).contiguous()
+    cur = c2w.to(device=device, dtype=torch.float32).reshape(-1)[:16].contiguous()
+    inside = torch.empty(K, dtype=torch.int32, device=device)
+    n_pts = torch.zeros(1, dtype=torch.int32, device=device)
+    cam = make_camera(self.H, self.W, self.fx, self.fy, self.cx, self.cy)
+    call("eslam_keyframe_overlap", C.byref(cam), ptr(cur), ptr(depth), ptr(idx), num_rays,
+         ptr(linspace_table(num_samples, device)), num_samples, ptr(kf_c2w), K, ptr(inside), ptr(n_pts), stream())
+    self._last_overlap = (inside, n_pts)  # percent_inside = inside / n_pts (tests)
+    sel = torch.nonzero(inside).squeeze(-1)
     sel = sel[torch.randperm(sel.shape[0])[:num_keyframes]]
     return list(sel.cpu().numpy())
+
+
+def _device_frame(self, t: torch.Tensor, dtype) -> torch.Tensor:
+    """A contiguous device copy of a keyframe image, cached across optimize_mapping calls (`keyframe_device: cpu`
+    makes the reference re-upload every window frame on every call, Mapper.py:276-277)."""
+    dev = torch.device(self.device)
+    if t.device == dev and t.dtype == dtype and t.is_contiguous():
+        return t
+    cache = self.__dict__.setdefault("_kf_cache", {})
+    ent = cache.get(id(t))
+    if ent is not None and ent[0] is t and ent[2] == t._version:
+        return ent[1]
+    limit = int(os.environ.get("ESLAM_B200_KF_CACHE", "512"))
+    while len(cache) >= limit:
+        cache.pop(next(iter(cache)))
+    out = t.to(device=dev, dtype=dtype).contiguous()
+    cache[id(t)] = (t, out, t._version)
+    return out
 
 
 def _mapper_state(mp, n_rays, b):
@@ -115,12 +131,14 @@ def optimize_mapping(self, iters, lr_factor, idx, cur_gt_color, cur_gt_depth, gt
     optimize_frame += [-1]
     b = len(optimize_frame)
     # ---- stage the window (Mapper.py:268-286)
-    gt_depths = torch.stack([cur_gt_depth if f == -1 else keyframe_dict[f]['depth'].to(device)
-                             for f in optimize_frame], dim=0).contiguous()
-    gt_colors = torch.stack([cur_gt_color if f == -1 else keyframe_dict[f]['color'].to(device)
-                             for f in optimize_frame], dim=0).contiguous()
+    # (no torch.stack of the frames: the sampling kernel reads each frame where it lives)
+    depths = [_device_frame(self, cur_gt_depth if f == -1 else keyframe_dict[f]['depth'], torch.float32)
+              for f in optimize_frame]
+    colors = [_device_frame(self, cur_gt_color if f == -1 else keyframe_dict[f]['color'], torch.float64)
+              for f in optimize_frame]
     c2ws = torch.stack([cur_c2w if f == -1 else keyframe_dict[f]['est_c2w'] for f in optimize_frame], dim=0)
     st = _mapper_state(self, (self.mapping_pixels // b) * b, b)
+    gt_colors = gt_depths = FrameTable(colors, depths, st["sc"].cam, device)
     store = synced_store(all_planes, self.decoders, self.bound)
     lr = cfg['mapping']['lr']
     c2ws_new = map_window(store, st["ws"], st["sc"], c2ws, gt_colors, gt_depths, self.mapping_pixels, iters,

@@ -685,3 +685,36 @@ def query_points(fld: Field, p):
         ret = decode(p, fld)
     ret[~inside, -1] = -1
     return ret
+
+
+# ---------------------------------------------------------------------------------------
+# keyframe selection by view overlap
+# ---------------------------------------------------------------------------------------
+def keyframe_overlap(cam: Camera, c2w, gt_depth, gt_color, kf_c2ws, draws, num_samples=8, num_rays=50):
+    """Mapper.keyframe_selection_overlap (Mapper.py:146-203) up to `percent_inside`: `num_rays` random pixels of
+    the current frame with depth > 0, `num_samples` points per ray between 0.8*d and d+0.5, projected into every
+    keyframe of kf_c2ws [K,4,4] (the caller drops the last two keyframes, Mapper.py:180); fraction of points that
+    land inside the image with a 20-pixel margin and in front of the camera.  The reference then keeps
+    nonzero(percent_inside) in a random (CPU randperm) order (Mapper.py:205-209)."""
+    H, W, fx, fy, cx, cy = cam.H, cam.W, cam.fx, cam.fy, cam.cx, cam.cy
+    rays_o, rays_d, d, _, _ = sample_rays(0, H, 0, W, num_rays, fx, fy, cx, cy, c2w.unsqueeze(0),
+                                          gt_depth.unsqueeze(0), gt_color.unsqueeze(0), draws)
+    d = d.reshape(-1, 1)
+    ok = d[:, 0] > 0
+    rays_o, rays_d, d = rays_o[ok], rays_d[ok], d[ok].repeat(1, num_samples)
+    t = torch.linspace(0., 1., steps=num_samples).to(d.device)
+    z = (d * 0.8) * (1. - t) + (d + 0.5) * t
+    pts = (rays_o[..., None, :] + rays_d[..., None, :] * z[..., :, None]).reshape(1, -1, 3)
+    w2cs = torch.inverse(kf_c2ws)
+    ones = torch.ones_like(pts[..., 0]).reshape(1, -1, 1)
+    homo = torch.cat([pts, ones], dim=-1).reshape(1, -1, 4, 1).expand(w2cs.shape[0], -1, -1, -1)
+    cam_pts = (w2cs.unsqueeze(1).expand(-1, homo.shape[1], -1, -1) @ homo)[:, :, :3]
+    K = torch.tensor([[fx, .0, cx], [.0, fy, cy], [.0, .0, 1.0]], device=d.device).reshape(3, 3)
+    cam_pts[:, :, 0] *= -1
+    uv = K @ cam_pts
+    zc = uv[:, :, -1:] + 1e-5
+    uv = uv[:, :, :2] / zc
+    edge = 20
+    mask = (uv[:, :, 0] < W - edge) * (uv[:, :, 0] > edge) * (uv[:, :, 1] < H - edge) * (uv[:, :, 1] > edge)
+    mask = (mask & (zc[:, :, 0] < 0)).squeeze(-1)
+    return mask.sum(dim=1) / uv.shape[1], mask.sum(dim=1), uv.shape[1]

@@ -1,0 +1,128 @@
+"""GPU: SURVEY.md 8(f)-1 -- keyframe selection by view overlap (one projection kernel) and the frame table that
+replaces the reference's per-call torch.stack of the window's frames."""
+import numpy as np
+import pytest
+import torch
+
+import eslam_oracle as O
+from conftest import GOLDEN_CAM, SimpleEslam, base_cfg, golden_field, load_npz, rel_err, to_device_scene
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+
+
+def _mapper(cam, dev=DEV):
+    import myslam_b200 as M
+
+    fld = golden_field()
+    planes, dec = to_device_scene(fld, dev)
+    cfg = base_cfg()
+    rnd = M.Renderer(cfg, SimpleEslam(fld.bound.clone(), cam, dev))
+    return M.MapperStep(cfg, rnd, dec, planes, fld.bound.clone(), cam, dev), fld
+
+
+def test_keyframe_overlap_counts_golden(monkeypatch):
+    """Counts per keyframe equal the unmodified reference's percent_inside * n_pts on the committed fixture, and the
+    drop-in method returns the reference's list (randperm replaced by the identity, as in the generator)."""
+    import myslam_b200 as M
+
+    d = load_npz("kfsel.npz")
+    cam = (int(d["H"]), int(d["W"]), float(d["fx"]), float(d["fy"]), float(d["cx"]), float(d["cy"]))
+    mp, _ = _mapper(cam)
+    kfs = torch.from_numpy(d["kf_c2ws"]).to(DEV)
+    mp.keyframe_list = list(range(kfs.shape[0]))
+    mp.estimate_c2w_list = kfs
+    mp.draws = M.ReplayDraws([torch.from_numpy(d["idx"])], DEV)
+    monkeypatch.setattr(torch, "randperm", lambda n, *a, **k: torch.arange(n))
+    sel = mp.keyframe_selection_overlap(torch.from_numpy(d["color"]).to(DEV), torch.from_numpy(d["depth"]).to(DEV),
+                                        torch.from_numpy(d["cur_c2w"]).to(DEV), kfs.shape[0])
+    inside, n_pts = mp._last_overlap
+    assert int(n_pts) == int(d["n_pts"])
+    assert inside.cpu().tolist() == d["counts"].tolist()
+    assert [int(s) for s in sel] == d["selected"].tolist()
+    frac = inside.float() / n_pts.float()
+    assert torch.equal(frac.cpu(), torch.from_numpy(d["percent_inside"]))
+
+
+@pytest.mark.parametrize("seed", [0, 1, 2])
+def test_keyframe_overlap_counts_vs_oracle_random(seed):
+    """Seeded random cameras at Replica image size; counts may differ from the oracle only for points within float
+    rounding of the 20-pixel margin (the oracle inverts with LU, the kernel with cofactors)."""
+    import myslam_b200 as M
+
+    g = torch.Generator().manual_seed(seed)
+    H, W = 340, 600
+    cam = (H, W, 300.0, 300.0, 299.5, 169.5)
+    mp, _ = _mapper(cam)
+    K = 40
+    q = torch.randn(K + 2, 4, generator=g) * 0.3 + torch.tensor([1.0, 0, 0, 0])
+    t = torch.randn(K + 2, 3, generator=g) * 1.5
+    kfs = O.cam_pose_to_matrix(torch.cat([q, t], -1))
+    cur = O.cam_pose_to_matrix(torch.tensor([[1.0, 0.02, 0.01, -0.03, 0.1, 0.2, -0.1]]))[0]
+    depth = 1.0 + 3.0 * torch.rand(H, W, generator=g)
+    depth[torch.rand(H, W, generator=g) < 0.2] = 0.0
+    color = torch.zeros(H, W, 3, dtype=torch.float64)
+    idx = torch.randint(H * W, (50,), generator=g)
+    ocam = O.Camera(*cam)
+    frac, cnt, n_pts = O.keyframe_overlap(ocam, cur, depth, color, kfs[:-2], O.ReplayDraws([idx]))
+    mp.keyframe_list = list(range(K + 2))
+    mp.estimate_c2w_list = kfs.to(DEV)
+    mp.draws = M.ReplayDraws([idx], DEV)
+    mp.keyframe_selection_overlap(color.to(DEV), depth.to(DEV), cur.to(DEV), K)
+    inside, n = mp._last_overlap
+    assert int(n) == int(n_pts)
+    diff = (inside.cpu().long() - cnt.long()).abs()
+    assert int(diff.max()) <= 1 and int((diff > 0).sum()) <= 2, diff.tolist()
+    assert int(cnt.sum()) > 0
+
+
+def test_frame_table_equals_stacked_frames():
+    """The same mapping iteration with the window given as a FrameTable (frames read where they live) and as the
+    reference's stacked tensors: identical kept rays, gradients and loss."""
+    from myslam_b200 import ReplayDraws
+    from myslam_b200.decoders import synced_store
+    from myslam_b200.hotpath import FrameTable, mapping_iteration
+    from myslam_b200.mapper import _mapper_state
+
+    mp, fld = _mapper(GOLDEN_CAM)
+    d = load_npz("mapping.npz")
+    st = _mapper_state(mp, 400, 4)
+    store = synced_store((mp.planes_xy, mp.planes_xz, mp.planes_yz, mp.c_planes_xy, mp.c_planes_xz, mp.c_planes_yz),
+                         mp.decoders, fld.bound)
+    c2ws = torch.from_numpy(d["c2ws0"]).to(DEV)
+    cols, deps = torch.from_numpy(d["gt_colors"]).to(DEV), torch.from_numpy(d["gt_depths"]).to(DEV)
+    draws = [torch.from_numpy(d[f"draw.{k}"]) for k in range(int(d["n_draws"]))]
+    outs = []
+    for mode in ("stack", "table"):
+        store.reset_adam()
+        if mode == "stack":
+            gc, gd = cols, deps
+        else:  # separate allocations in a shuffled order of creation: nothing contiguous about them
+            frames = [(cols[k].clone(), deps[k].clone()) for k in (2, 0, 3, 1)]
+            frames = [frames[[2, 0, 3, 1].index(k)] for k in range(4)]
+            gc = gd = FrameTable([f[0] for f in frames], [f[1] for f in frames], st["sc"].cam, DEV)
+        mapping_iteration(st["ws"], store, st["sc"], c2ws, None, gc, gd, 100, 1, 1e-3, 5e-3, 5e-3, 1e-3,
+                          draws=ReplayDraws(draws, DEV), strict_rng=True, want_loss=True, apply_adam=False)
+        ws = st["ws"]
+        R = int(ws.counters[0])
+        outs.append((R, ws.src[:R].clone(), ws.gt_color[:R].clone(), ws.gt_depth[:R].clone(), store.grad.clone(),
+                     ws.loss_acc[5].item()))
+    a, b = outs
+    assert a[0] == b[0] and torch.equal(a[1], b[1]) and torch.equal(a[2], b[2]) and torch.equal(a[3], b[3])
+    assert rel_err(b[4], a[4]) < 1e-5 and abs(a[5] - b[5]) <= 1e-6 * abs(a[5])
+
+
+def test_keyframe_device_cache():
+    """`keyframe_device: cpu` keyframes are uploaded once and re-used across optimize_mapping calls."""
+    from myslam_b200.mapper import _device_frame
+
+    mp, _ = _mapper(GOLDEN_CAM)
+    t = torch.rand(GOLDEN_CAM[0], GOLDEN_CAM[1])
+    a = _device_frame(mp, t, torch.float32)
+    b = _device_frame(mp, t, torch.float32)
+    assert a.is_cuda and a.data_ptr() == b.data_ptr() and torch.equal(a.cpu(), t)
+    t.add_(1.0)  # in-place change -> new version -> re-upload
+    c = _device_frame(mp, t, torch.float32)
+    assert torch.equal(c.cpu(), t)
+    g = torch.rand(4, 4, device=DEV)
+    assert _device_frame(mp, g, torch.float32) is g

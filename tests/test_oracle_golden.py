@@ -115,3 +115,16 @@ def test_empty_band_gives_nan_loss_but_finite_grads():
     d = torch.ones(4)
     loss = O.sdf_loss(sdf, z, d, 0.06, 10, 200, 50)
     assert torch.isnan(loss)
+
+
+def test_keyframe_overlap_golden():
+    """Oracle restatement of Mapper.keyframe_selection_overlap (Mapper.py:146-203) against the fixture the
+    unmodified reference produced (tests/golden/make_golden_kfsel.py)."""
+    d = load_npz("kfsel.npz")
+    cam = O.Camera(int(d["H"]), int(d["W"]), float(d["fx"]), float(d["fy"]), float(d["cx"]), float(d["cy"]))
+    frac, cnt, n_pts = O.keyframe_overlap(cam, torch.from_numpy(d["cur_c2w"]), torch.from_numpy(d["depth"]),
+                                          torch.from_numpy(d["color"]), torch.from_numpy(d["kf_c2ws"])[:-2],
+                                          O.ReplayDraws([torch.from_numpy(d["idx"])]))
+    assert torch.equal(frac, torch.from_numpy(d["percent_inside"]))
+    assert torch.nonzero(frac).squeeze(-1).tolist() == d["selected"].tolist()
+    assert int(n_pts) == int(d["n_pts"]) and cnt.tolist() == d["counts"].tolist()
