@@ -233,6 +233,12 @@ int eslam_pose_adam_step(float* poses, float* pose_grad, float* exp_avg, float* 
 int eslam_finalize_loss(const eslam_render_cfg_t* cfg_host, const int32_t* counters, int tracker_rule,
                         double* loss_acc, float* loss_out, eslam_stream_t s);
 
+/* matrix_to_cam_pose / cam_pose_to_matrix (common.py:155-181 over pytorch3d 0.7.1 matrix_to_quaternion /
+ * quaternion_to_matrix) for n cameras: c2w[n][16] row-major <-> poses[n][7] = (qw,qx,qy,qz,tx,ty,tz), evaluated in
+ * torch's operation order.  Used once per optimize_mapping call for the window's poses (Mapper.py:289,352-362). */
+int eslam_matrix_to_pose(const float* c2w, float* poses, int n, eslam_stream_t s);
+int eslam_pose_to_matrix(const float* poses, float* c2w, int n, eslam_stream_t s);
+
 /* Mapper.keyframe_selection_overlap (Mapper.py:146-203) up to `percent_inside`: the n_rays pixels pix_idx
  * (draws of randint(H*W), common.py:108) of the current frame that have depth > 0 are lifted to n_samples points
  * each between 0.8*d and d+0.5 (t_vals = linspace(0,1,n_samples)), projected into every keyframe kf_c2w[k]

@@ -83,6 +83,8 @@ PROTOTYPES = {
     "eslam_adam_step": [_P, _P, _P, _P, _L, C.POINTER(C.c_int64), C.POINTER(C.c_double), _I, _I, _D, _D, _D, _P],
     "eslam_pose_adam_step": [_P, _P, _P, _P, _I, _I, _D, _D, _I, _D, _D, _D, _P, _I, _P],
     "eslam_finalize_loss": [_RP, _P, _I, _P, _P, _P],
+    "eslam_matrix_to_pose": [_P, _P, _I, _P],
+    "eslam_pose_to_matrix": [_P, _P, _I, _P],
     "eslam_keyframe_overlap": [_CP, _P, _P, _P, _I, _P, _I, _P, _I, _P, _P, _P],
     "eslam_exchange_counters": [C.POINTER(Peers), _P, C.POINTER(C.c_void_p), _I, _P, _P],
     "eslam_adam_exchange": [C.POINTER(Peers), C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), _P, _P, _P, _P, _L,

@@ -694,6 +694,22 @@ int eslam_pose_adam_step(float* poses, float* pose_grad, float* exp_avg, float* 
   return 0;
 }
 
+int eslam_matrix_to_pose(const float* c2w, float* poses, int n, eslam_stream_t s) {
+  REQUIRE(c2w && poses && n >= 0, "eslam_matrix_to_pose");
+  if (n == 0) return 0;
+  k_matrix_to_pose<<<(n + 31) / 32, 32, 0, S_(s)>>>(c2w, poses, n);
+  CHECK_LAUNCH("eslam_matrix_to_pose");
+  return 0;
+}
+
+int eslam_pose_to_matrix(const float* poses, float* c2w, int n, eslam_stream_t s) {
+  REQUIRE(c2w && poses && n >= 0, "eslam_pose_to_matrix");
+  if (n == 0) return 0;
+  k_pose_to_matrix<<<(n + 31) / 32, 32, 0, S_(s)>>>(poses, c2w, n);
+  CHECK_LAUNCH("eslam_pose_to_matrix");
+  return 0;
+}
+
 int eslam_keyframe_overlap(const eslam_camera_t* cam, const float* c2w, const float* depth, const int64_t* pix_idx,
                            int n_rays, const float* t_vals, int n_samples, const float* kf_c2w, int n_keyframes,
                            int32_t* inside, int32_t* n_pts, eslam_stream_t s) {

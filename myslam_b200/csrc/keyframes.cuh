@@ -2,6 +2,7 @@
 // (src/Mapper.py:146-203), one CTA per keyframe.  SURVEY.md section 8(f)-1.
 #pragma once
 #include "field.cuh"
+#include "sample.cuh"
 
 namespace eslam {
 
@@ -90,6 +91,60 @@ __global__ void __launch_bounds__(OVERLAP_THREADS) k_keyframe_overlap(const __gr
     a.inside[k] = s_cnt;
     if (k == 0) a.n_pts[0] = s_tested;
   }
+}
+
+// ---- pose <-> matrix for a window of cameras (common.py:155-181 over pytorch3d 0.7.1's quaternion functions), one
+//      thread per camera, in torch's evaluation order (bit-exact with the host mirror myslam_b200/common.py).
+//      Replaces ~60 tiny ATen launches at the start and end of every optimize_mapping call.
+__global__ void k_matrix_to_pose(const float* __restrict__ c2w, float* __restrict__ poses, int n) {
+  const int f = blockIdx.x * blockDim.x + threadIdx.x;
+  if (f >= n) return;
+  const float* m = c2w + f * 16;
+  const float m00 = m[0], m01 = m[1], m02 = m[2], m10 = m[4], m11 = m[5], m12 = m[6], m20 = m[8], m21 = m[9], m22 = m[10];
+  float sq[4], qa[4];
+  sq[0] = __fadd_rn(__fadd_rn(__fadd_rn(1.0f, m00), m11), m22);
+  sq[1] = __fsub_rn(__fsub_rn(__fadd_rn(1.0f, m00), m11), m22);
+  sq[2] = __fsub_rn(__fadd_rn(__fsub_rn(1.0f, m00), m11), m22);
+  sq[3] = __fadd_rn(__fsub_rn(__fsub_rn(1.0f, m00), m11), m22);
+  int best = 0;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    qa[i] = sq[i] > 0.f ? __fsqrt_rn(sq[i]) : 0.f;
+    if (qa[i] > qa[best]) best = i;  // torch.argmax: first maximum
+  }
+  float c[4];
+  const float d = __fmul_rn(qa[best], qa[best]);
+  switch (best) {
+    case 0: c[0] = d; c[1] = __fsub_rn(m21, m12); c[2] = __fsub_rn(m02, m20); c[3] = __fsub_rn(m10, m01); break;
+    case 1: c[0] = __fsub_rn(m21, m12); c[1] = d; c[2] = __fadd_rn(m10, m01); c[3] = __fadd_rn(m02, m20); break;
+    case 2: c[0] = __fsub_rn(m02, m20); c[1] = __fadd_rn(m10, m01); c[2] = d; c[3] = __fadd_rn(m12, m21); break;
+    default: c[0] = __fsub_rn(m10, m01); c[1] = __fadd_rn(m20, m02); c[2] = __fadd_rn(m21, m12); c[3] = d; break;
+  }
+  const float den = __fmul_rn(2.0f, fmaxf(qa[best], 0.1f));
+#pragma unroll
+  for (int i = 0; i < 4; ++i) poses[f * 7 + i] = __fdiv_rn(c[i], den);
+  poses[f * 7 + 4] = m[3];
+  poses[f * 7 + 5] = m[7];
+  poses[f * 7 + 6] = m[11];
+}
+
+__global__ void k_pose_to_matrix(const float* __restrict__ poses, float* __restrict__ c2w, int n) {
+  const int f = blockIdx.x * blockDim.x + threadIdx.x;
+  if (f >= n) return;
+  float R[9];
+  quat_to_rot(poses + f * 7, R);
+  float* m = c2w + f * 16;
+#pragma unroll
+  for (int x = 0; x < 3; ++x) {
+    m[x * 4 + 0] = R[x * 3 + 0];
+    m[x * 4 + 1] = R[x * 3 + 1];
+    m[x * 4 + 2] = R[x * 3 + 2];
+    m[x * 4 + 3] = poses[f * 7 + 4 + x];
+  }
+  m[12] = 0.f;
+  m[13] = 0.f;
+  m[14] = 0.f;
+  m[15] = 1.f;
 }
 
 }  // namespace eslam

@@ -36,22 +36,24 @@ def map_window(store: FieldStore, ws: Workspace, sc: StepCfg, c2ws, gt_colors, g
     pix = n_pixels // b
     store.reset_adam()
     poses7 = None
+    c2ws = c2ws.float().contiguous()
     if joint_opt:
         poses7 = torch.zeros(b, 7, dtype=torch.float32, device=c2ws.device)
-        if b > 1:
-            poses7[1:] = matrix_to_cam_pose(c2ws[1:])
+        if b > 1:  # matrix_to_cam_pose(c2ws[1:]) (Mapper.py:289) as one launch
+            call("eslam_matrix_to_pose", ptr(c2ws[1:]), ptr(poses7[1:]), b - 1, stream())
         ws.pose_m.zero_()
         ws.pose_v.zero_()
         ws.pose_grad.zero_()
-    c2ws = c2ws.float().contiguous()
     for it in range(iters):
         mapping_iteration(ws, store, sc, c2ws, poses7, gt_colors, gt_depths, pix, it + 1, lr_dec, lr_planes,
                           lr_cplanes, lr_cam, draws=draws, strict_rng=strict_rng, want_loss=losses is not None,
                           exchange=exchange)
         if losses is not None:
             losses.append(ws.loss_acc[5].clone())
-    if joint_opt and b > 1:
-        c2ws = torch.cat([c2ws[0:1], cam_pose_to_matrix(poses7[1:])], 0)
+    if joint_opt and b > 1:  # cam_pose_to_matrix of the optimised poses (Mapper.py:352-362) as one launch
+        out = c2ws.clone()
+        call("eslam_pose_to_matrix", ptr(poses7[1:]), ptr(out[1:]), b - 1, stream())
+        c2ws = out
     return c2ws
 
 
@@ -154,10 +156,10 @@ def optimize_mapping(self, iters, lr_factor, idx, cur_gt_color, cur_gt_depth, gt
         k = 0
         for f in optimize_frame[1:]:
             if f != -1:
-                keyframe_dict[f]['est_c2w'] = c2ws_new[1 + k].clone()
+                keyframe_dict[f]['est_c2w'] = c2ws_new[1 + k]  # rows of one fresh [b,4,4] tensor nobody else holds
                 k += 1
             else:
-                cur_c2w = c2ws_new[-1].clone()
+                cur_c2w = c2ws_new[-1]
     return cur_c2w
 
 

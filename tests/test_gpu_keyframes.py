@@ -126,3 +126,30 @@ def test_keyframe_device_cache():
     assert torch.equal(c.cpu(), t)
     g = torch.rand(4, 4, device=DEV)
     assert _device_frame(mp, g, torch.float32) is g
+
+
+def test_pose_conversion_kernels_match_host_mirror():
+    """eslam_matrix_to_pose / eslam_pose_to_matrix == common.matrix_to_cam_pose / cam_pose_to_matrix (which the CPU
+    tests pin against the reference's functions through the golden pose fixture), bit for bit on the device."""
+    from myslam_b200._lib import call, ptr, stream
+    from myslam_b200.common import cam_pose_to_matrix, matrix_to_cam_pose
+
+    d = load_npz("pose.npz")
+    poses = torch.from_numpy(d["poses"]).to(DEV)
+    mats = torch.from_numpy(d["mats"]).to(DEV).contiguous()
+    n = poses.shape[0]
+    out_p = torch.empty(n, 7, device=DEV)
+    call("eslam_matrix_to_pose", ptr(mats), ptr(out_p), n, stream())
+    assert torch.equal(out_p, matrix_to_cam_pose(mats))
+    assert rel_err(out_p, d["back"]) < 1e-6  # the fixture was computed by torch on the CPU
+    out_m = torch.empty(n, 4, 4, device=DEV)
+    call("eslam_pose_to_matrix", ptr(poses.contiguous()), ptr(out_m), n, stream())
+    # (torch's device reduction adds |q|^2 in a different order than its CPU loop, which the kernel follows)
+    assert rel_err(out_m, cam_pose_to_matrix(poses)) < 1e-6
+    assert rel_err(out_m, d["mats"]) < 1e-6
+    # every branch of the argmax: rotations by ~180 degrees about each axis
+    q = torch.tensor([[1e-3, 1, 0, 0], [1e-3, 0, 1, 0], [1e-3, 0, 0, 1], [1, 0, 0, 0], [0.5, 0.5, 0.5, 0.5]], device=DEV)
+    m = cam_pose_to_matrix(torch.cat([q, torch.zeros(5, 3, device=DEV)], -1)).contiguous()
+    o = torch.empty(5, 7, device=DEV)
+    call("eslam_matrix_to_pose", ptr(m), ptr(o), 5, stream())
+    assert torch.equal(o, matrix_to_cam_pose(m))
