@@ -197,6 +197,86 @@ class OracleRun:
                                                  iters, t["lr_T"], t["lr_R"], self.draws)) / iters
 
 
+def extras(scene, rnd, spec, dev, rank, world, dist_on, poses, deps, hbm_peak):
+    """Secondary workloads of BASELINE.json (configs 3 and 5) and the full-frame render, each a few launches."""
+    import torch.distributed as dist
+    import myslam_b200 as M
+    from myslam_b200 import synthetic as S
+    from myslam_b200.dist import shard_range
+    from myslam_b200.mesher import grid_axes, query_grid_sdf
+
+    out = {}
+    # ---- config 5: marching-cubes SDF query at 1 cm over the room0 bound, flat lattice ranges sharded over ranks
+    axes = grid_axes(spec["bound"], 0.01)
+    total = len(axes[0]) * len(axes[1]) * len(axes[2])
+    start, count = shard_range(total, rank, world)
+    buf = torch.empty(count, dtype=torch.float32, device=dev)
+    fn = lambda: query_grid_sdf(scene.all_planes, scene.decoders, axes, scene.bound, start=start, count=count, out=buf)
+    ms = time_region(fn, 3, 1, dist_on) / 3
+    out["mesh_query"] = {"value": total / (ms * 1e-3), "unit": "points/s", "ms": ms, "points": total,
+                         "lattice": [len(a) for a in axes], "n_gpus": world, "scaling": "strong",
+                         "algorithmic_GBps_per_gpu": count * 3076 / (ms * 1e-3) / 1e9,
+                         "frac_of_hbm_peak": count * 3076 / (ms * 1e-3) / 1e9 / hbm_peak,
+                         "what": "Mesher.get_grid_uniform + eval_points (Mesher.py:130-186), SDF head only, coordinates "
+                                 "generated in-kernel, 3072 B gathered + 4 B written per point"}
+    del buf
+    if rank != 0:
+        return out
+    # ---- full-frame inference (Renderer.render_img, 1200x680 = 816 k rays, one pass)
+    fn = lambda: rnd.render_img(scene.all_planes, scene.decoders, poses[0], spec["truncation"], dev, gt_depth=deps[0])
+    ms = time_region(fn, 3, 1, False) / 3
+    out["render_img"] = {"ms": ms, "rays": spec["H"] * spec["W"], "rays_per_s": spec["H"] * spec["W"] / (ms * 1e-3),
+                         "what": "Renderer.render_img (Renderer.py:155-204) in one sampling + one render launch "
+                                 "(the reference: 82 chunks of 10 k rays)"}
+    # ---- config 3: ScanNet scene0000 shape (620x460 after crop, S = 48 + 8, 70.5 MB of planes)
+    sp = S.SCANNET_0000
+    sc3 = S.make_scene(sp, dev, seed=0)
+    cfg3 = S.run_cfg(sp)
+
+    class E:
+        pass
+
+    e = E()
+    e.bound, e.device = sc3.bound, dev
+    e.H, e.W, e.fx, e.fy, e.cx, e.cy = sc3.cam
+    rnd3 = M.Renderer(cfg3, e)
+    m3, t3 = sp["mapping"], sp["tracking"]
+    nf = m3["mapping_window_size"]
+    p3, c3, d3 = build_inputs(sp, dev, nf, seed=2)
+    p3 = p3.to(dev)
+    from myslam_b200.common import matrix_to_cam_pose
+    from myslam_b200.decoders import synced_store
+    from myslam_b200.mapper import _mapper_state, map_window
+
+    mp3 = M.MapperStep(cfg3, rnd3, sc3.decoders, sc3.all_planes, sc3.bound, sc3.cam, dev)
+    st3 = _mapper_state(mp3, m3["pixels"], nf)
+    store3 = synced_store(sc3.all_planes, sc3.decoders, sc3.bound)
+    lr = m3["lr"]
+    iters = 15
+    fn = lambda: map_window(store3, st3["ws"], st3["sc"], p3, c3, d3, m3["pixels"], iters, lr["decoders_lr"],
+                            lr["planes_lr"], lr["c_planes_lr"], True, m3["joint_opt_cam_lr"])
+    ms = time_region(fn, 3, 1, False) / 3
+    trk3 = M.TrackerStep(cfg3, rnd3, sc3.decoders, sc3.all_planes, sc3.bound, sc3.cam, dev)
+    pose0 = matrix_to_cam_pose(p3[:1])
+    col1, dep1 = c3[:1].contiguous(), d3[:1].contiguous()
+    ms_t = time_region(lambda: trk3.track_frame(pose0, col1, dep1), 3, 1, False) / 3
+    S56 = sp["n_stratified"] + sp["n_importance"]
+    out["scannet_scene0000_shape"] = {
+        "mapping_rays_iters_per_s": iters * (m3["pixels"] // nf) * nf / (ms * 1e-3), "mapping_ms_per_iter": ms / iters,
+        "tracking_frames_per_s": 1.0 / (ms_t * 1e-3), "tracking_iters_per_frame": t3["iters"], "samples_per_ray": S56,
+        "plane_MB": store3.n_floats * 4 / 1e6,
+        "mapping_frac_of_hbm_peak": iters * (m3["pixels"] // nf) * nf * S56 * 6144 * 2 / (ms * 1e-3) / 1e9 / hbm_peak}
+    return out
+
+
+def workload_config(world, pix, n_frames, exchange_name):
+    return {"workload": "replica-room0-shaped 1200x680, 20-keyframe window, 4000 rays/iter per GPU, "
+                        "15 iterations per optimize_mapping call, ESLAM.yaml defaults, joint pose optimisation",
+            "rays_per_iter_total": world * pix * n_frames, "exchange": exchange_name,
+            "l2": "inputs larger than L2 (471 MB of window frames + 109 MB parameter/optimiser arenas); no flush",
+            "seed": 0}
+
+
 def run_reference(args, spec):
     """--impl reference: the reference's CPU implementation of the path (oracle port) on the host cores."""
     rank = int(os.environ.get("RANK", "0"))
@@ -219,8 +299,8 @@ def run_reference(args, spec):
         "unit": "rays*iters/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": 1e3 * s_iter, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "replica-room0-shaped 1200x680, 20-keyframe window, 4000 rays/iter, ESLAM.yaml defaults",
-                   "step": "1 mapping iteration (bounded sample of the 15-iteration call)"},
+        "config": {**workload_config(1, m["pixels"] // n_frames, n_frames, "none (host cores)"),
+                   "step": "1 mapping iteration of the same window (bounded sample of the 15-iteration call)"},
         "cpu_baseline": {"value": value, "unit": "rays*iters/s", "cores": cores, "kind": "port",
                          "sample": f"{len(per_iter)} x 1 mapping iteration of 4000 rays, torch CPU, {cores} threads"},
         "e2e": {"value": value, "unit": "rays*iters/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -450,6 +530,12 @@ def main():
     if hasattr(ex, "check"):
         ex.check()
     clocks = sampler.stop() if sampler else None
+    extra = {}
+    if not args.profile_only:
+        try:
+            extra = extras(scene, rnd, spec, dev, rank, world, dist_on, poses, deps, hbm_peak)
+        except Exception as exc:  # secondary numbers never take the headline line down
+            extra = {"error": repr(exc)}
 
     # ------------------------------------------------------------------ baselines (rank 0, N=1 only)
     cpu_baseline = None
@@ -482,12 +568,9 @@ def main():
             "metric": "mapping rays*iters/s (Replica room0 shape)", "value": value, "unit": "rays*iters/s",
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_map / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": "replica-room0-shaped 1200x680, 20-keyframe window, 4000 rays/iter per GPU, "
-                                   "15 iterations per optimize_mapping call, ESLAM.yaml defaults, joint pose optimisation",
-                       "rays_per_iter_total": world * pix * n_frames, "exchange": exchange_name, "l2": "inputs larger than L2 (471 MB frame stack "
-                       "+ 109 MB parameter/optimiser arenas); no flush", "seed": 0},
+            "config": workload_config(world, pix, n_frames, exchange_name),
             "e2e": e2e, "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu_baseline,
-            "torch_gpu_baseline": torch_gpu, "tracking": tracking, "clocks": clocks,
+            "torch_gpu_baseline": torch_gpu, "tracking": tracking, "clocks": clocks, **extra,
         }
         print(json.dumps(line))
     if dist_on:

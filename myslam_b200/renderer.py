@@ -5,6 +5,7 @@ signatures; sampling, decoding and compositing run in the sm_100a kernels and
 from __future__ import annotations
 
 import ctypes as C
+import os
 from typing import Optional
 
 import torch
@@ -190,18 +191,22 @@ class Renderer(object):
         return depth, rgb, sdf, z
 
     def render_img(self, all_planes, decoders, c2w, truncation, device, gt_depth=None):
-        """Full-image inference (Renderer.py:155-204): depth[H,W] float64, colour[H,W,3]; perturbation on,
-        chunks of ray_batch_size rays like the reference so the random stream has the same shapes."""
+        """Full-image inference (Renderer.py:155-204): depth[H,W] float64, colour[H,W,3]; perturbation on.
+        All H*W rays go through the kernels in ONE pass (one sampling launch, one render launch: SURVEY.md 8f-3);
+        with `strict_rng` (ESLAM_B200_STRICT_RNG=1) the reference's chunks of ray_batch_size rays are kept so the
+        random stream is consumed in the reference's shapes."""
         from .common import get_rays
         with torch.no_grad():
             H, W = self.H, self.W
+            strict = getattr(self, "strict_rng", os.environ.get("ESLAM_B200_STRICT_RNG", "0") == "1")
+            chunk = self.ray_batch_size if strict else H * W
             rays_o, rays_d = get_rays(H, W, self.fx, self.fy, self.cx, self.cy, c2w, device)
             rays_o = rays_o.reshape(-1, 3).contiguous()
             rays_d = rays_d.reshape(-1, 3).contiguous()
             gt_depth = gt_depth.reshape(-1)
             depth_list, color_list = [], []
-            for i in range(0, rays_d.shape[0], self.ray_batch_size):
-                sl = slice(i, i + self.ray_batch_size)
+            for i in range(0, rays_d.shape[0], chunk):
+                sl = slice(i, i + chunk)
                 depth, color, _, _ = self.render_batch_ray(all_planes, decoders, rays_d[sl], rays_o[sl], device,
                                                            truncation, gt_depth=gt_depth[sl])
                 depth_list.append(depth.double())

@@ -22,7 +22,8 @@ REPLICA_ROOM0 = dict(
                  lr=dict(decoders_lr=0.001, planes_lr=0.005, c_planes_lr=0.005)))
 
 SCANNET_0000 = dict(
-    bound=[[-0.2, 8.6], [-0.2, 8.9], [-0.2, 3.2]], H=460, W=620, fx=577.590698, fy=578.729797, cx=308.906342,
+    bound=[[-2.0, 11.0], [-2.0, 11.5], [-2.0, 5.5]], H=460, W=620,  # configs/ScanNet/scene0000.yaml:3
+    fx=577.590698, fy=578.729797, cx=308.906342,
     cy=232.683609, planes_res=(0.24, 0.06), c_planes_res=(0.24, 0.03), bound_dividable=0.24, truncation=0.06,
     n_stratified=48, n_importance=8, room=[[0.2, 8.2], [0.2, 8.5], [0.1, 2.9]],
     tracking=dict(pixels=2000, iters=30, lr_T=0.0005, lr_R=0.0025, ignore_edge_W=75, ignore_edge_H=75,

@@ -718,3 +718,32 @@ def keyframe_overlap(cam: Camera, c2w, gt_depth, gt_color, kf_c2ws, draws, num_s
     mask = (uv[:, :, 0] < W - edge) * (uv[:, :, 0] > edge) * (uv[:, :, 1] < H - edge) * (uv[:, :, 1] > edge)
     mask = (mask & (zc[:, :, 0] < 0)).squeeze(-1)
     return mask.sum(dim=1) / uv.shape[1], mask.sum(dim=1), uv.shape[1]
+
+
+# ---------------------------------------------------------------------------------------
+# full-image inference
+# ---------------------------------------------------------------------------------------
+def image_rays(cam: Camera, c2w):
+    """get_rays (common.py:183-201): rays of every pixel, row-major, [H*W,3] each."""
+    i, j = torch.meshgrid(torch.linspace(0, cam.W - 1, cam.W), torch.linspace(0, cam.H - 1, cam.H), indexing="ij")
+    i, j = i.t(), j.t()
+    dirs = torch.stack([(i - cam.cx) / cam.fx, -(j - cam.cy) / cam.fy, -torch.ones_like(i)], -1).to(c2w.device)
+    dirs = dirs.reshape(cam.H, cam.W, 1, 3)
+    rays_d = torch.sum(dirs * c2w[:3, :3], -1)
+    rays_o = c2w[:3, -1].expand(rays_d.shape)
+    return rays_o.reshape(-1, 3), rays_d.reshape(-1, 3)
+
+
+def render_image(fld: Field, cam: Camera, c2w, gt_depth, truncation, n_strat, n_imp, draws, ray_batch_size=10000):
+    """Renderer.render_img (Renderer.py:155-204): chunks of ray_batch_size rays through render_batch_ray with the
+    perturbation ON (ESLAM.yaml:74); depth [H,W] float64, colour [H,W,3] float32."""
+    with torch.no_grad():
+        ro, rd = image_rays(cam, c2w)
+        d = gt_depth.reshape(-1)
+        depths, colors = [], []
+        for i in range(0, rd.shape[0], ray_batch_size):
+            dep, col, _, _ = render_rays(fld, ro[i:i + ray_batch_size], rd[i:i + ray_batch_size],
+                                         d[i:i + ray_batch_size], truncation, n_strat, n_imp, draws)
+            depths.append(dep.double())
+            colors.append(col)
+        return torch.cat(depths, 0).reshape(cam.H, cam.W), torch.cat(colors, 0).reshape(cam.H, cam.W, 3)

@@ -128,3 +128,17 @@ def test_keyframe_overlap_golden():
     assert torch.equal(frac, torch.from_numpy(d["percent_inside"]))
     assert torch.nonzero(frac).squeeze(-1).tolist() == d["selected"].tolist()
     assert int(n_pts) == int(d["n_pts"]) and cnt.tolist() == d["counts"].tolist()
+
+
+def test_render_img_golden():
+    """Oracle restatement of Renderer.render_img (Renderer.py:155-204) against the reference's output
+    (tests/golden/make_golden_img.py), replaying its random draws."""
+    from conftest import GOLDEN_CAM, TRUNC, golden_field
+
+    d = load_npz("img.npz")
+    draws = [torch.from_numpy(d[f"draw.{k}"]) for k in range(int(d["n_draws"]))]
+    dep, col = O.render_image(golden_field(), O.Camera(*GOLDEN_CAM), torch.from_numpy(d["c2w"]),
+                              torch.from_numpy(d["gt_depth"]), TRUNC, 32, 8, O.ReplayDraws(draws),
+                              ray_batch_size=int(d["ray_batch_size"]))
+    assert dep.dtype == torch.float64
+    assert rel_err(dep, d["depth"]) < 1e-6 and rel_err(col, d["color"]) < 1e-6
