@@ -349,6 +349,8 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device(dev))
     if args.profile_only:
         args.no_baselines = True
+    if os.environ.get("ESLAM_B200_DEBUG"):
+        _lib.load().eslam_set_debug(int(os.environ["ESLAM_B200_DEBUG"]))
     m, t = spec["mapping"], spec["tracking"]
     n_frames = m["mapping_window_size"]
 
@@ -384,14 +386,8 @@ def main():
 
     def mapping_call():
         # Mapper.optimize_mapping's per-call loop (fresh Adam, joint pose optimisation, 15 iterations)
-        store.reset_adam()
-        poses7 = torch.zeros(n_frames, 7, device=dev)
-        poses7[1:] = matrix_to_cam_pose(poses[1:])
-        ws.pose_m.zero_()
-        ws.pose_v.zero_()
-        for it in range(m["iters"]):
-            mapping_iteration(ws, store, sc, poses, poses7, cols, deps, pix, it + 1, lr["decoders_lr"],
-                              lr["planes_lr"], lr["c_planes_lr"], m["joint_opt_cam_lr"], exchange=ex)
+        map_window(store, ws, sc, poses, cols, deps, m["pixels"], m["iters"], lr["decoders_lr"], lr["planes_lr"],
+                   lr["c_planes_lr"], True, m["joint_opt_cam_lr"], exchange=ex)
 
     sampler = ClockSampler(local).start() if rank == 0 else None
     l0 = _lib.LAUNCHES

@@ -153,3 +153,4 @@ def test_pose_conversion_kernels_match_host_mirror():
     o = torch.empty(5, 7, device=DEV)
     call("eslam_matrix_to_pose", ptr(m), ptr(o), 5, stream())
     assert torch.equal(o, matrix_to_cam_pose(m))
+
