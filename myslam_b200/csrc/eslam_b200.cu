@@ -87,6 +87,16 @@ extern "C" {
 const char* eslam_last_error(void) { return g_err; }
 int eslam_abi_version(void) { return ESLAM_ABI_VERSION; }
 void eslam_set_debug(int flags) { g_debug = flags; }
+#ifdef ESLAM_PROFILE_PHASES
+// profiling build only (tools/phase_profile.py): read and clear the per-phase clock sums of the backward kernel
+int eslam_phase_counters(unsigned long long* out_host) {
+  cudaDeviceSynchronize();
+  cudaMemcpyFromSymbol(out_host, g_phase, sizeof(unsigned long long) * 32);
+  unsigned long long z[32] = {0};
+  cudaMemcpyToSymbol(g_phase, z, sizeof(z));
+  return 0;
+}
+#endif
 
 int eslam_plane_import(const float* nchw, float* arena, const eslam_plane_t* pl, eslam_stream_t s) {
   REQUIRE(nchw && arena && pl && pl->H > 0 && pl->W > 0, "eslam_plane_import");

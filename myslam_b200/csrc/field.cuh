@@ -227,22 +227,35 @@ __device__ __forceinline__ void mlp_forward(const float4* __restrict__ F, int q,
 constexpr int DW_W1 = 0, DW_B1 = 1024, DW_W2 = 1040, DW_B2 = 1296, DW_W3 = 1312, DW_B3 = 1360, DW_STRIDE = 1364;
 constexpr int DW_BETA = 2 * DW_STRIDE, DW_TOTAL = 2 * DW_STRIDE + 4;
 
-// packed arena block (include/eslam_b200.h) -> symmetric shared block; all threads of the CTA cooperate
-__device__ __forceinline__ void load_decoder_weights(float* sW, const float* __restrict__ dec, int tid, int nthreads) {
-  for (int i = tid; i < DW_TOTAL; i += nthreads) {
-    float v = 0.f;
-    if (i < DW_STRIDE) {  // sdf block: arena offsets 0..1328 are laid out identically up to W3 row 0
-      if (i < DW_W3 + 16) v = dec[i];
-      else if (i == DW_B3) v = dec[S_B3];
-    } else if (i < 2 * DW_STRIDE) {
-      const int k = i - DW_STRIDE;
-      if (k < DW_B3 + 3) v = dec[C_W1 + k];  // rgb block is contiguous in the arena with the same inner layout
-    } else if (i == DW_BETA) {
-      v = dec[P_BETA];
-    }
-    sW[i] = v;
-  }
+// packed arena block (include/eslam_b200.h) -> symmetric shared block; all threads of the CTA cooperate.
+// Asynchronous 16-byte copies (cp.async): issued at the top of the kernel, they land while the points are set up and
+// the features gathered; decoder_weights_wait() + __syncthreads() must precede the first use.
+// Both blocks start on 16-byte boundaries in the arena (offsets 0 and 1332 floats) and in shared memory (0, 1364).
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src) {
+  const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gmem_src) : "memory");
 }
+__device__ __forceinline__ void load_decoder_weights(float* sW, const float* __restrict__ dec, int tid, int nthreads) {
+  constexpr int SDF4 = (DW_W3 + 16) / 4;  // 332 float4: W1 b1 W2 b2 W3[0]
+  constexpr int RGB4 = (DW_B3 + 3) / 4;   // 340 float4: W1 b1 W2 b2 W3[0..2] (b3 is the 3-float tail)
+  for (int i = tid; i < SDF4 + RGB4; i += nthreads) {
+    if (i < SDF4)
+      cp_async16(sW + 4 * i, dec + 4 * i);
+    else
+      cp_async16(sW + DW_STRIDE + 4 * (i - SDF4), dec + C_W1 + 4 * (i - SDF4));
+  }
+  asm volatile("cp.async.commit_group;" ::: "memory");
+  // the few scalars outside the 16-byte pattern
+  if (tid < 32) sW[DW_W3 + 16 + tid] = 0.f;  // sdf W3 rows 1-2 (the sdf decoder has one output)
+  if (tid == 32) sW[DW_B3] = dec[S_B3];
+  if (tid == 33) sW[DW_B3 + 1] = 0.f;
+  if (tid == 34) sW[DW_B3 + 2] = 0.f;
+  if (tid == 35) sW[DW_B3 + 3] = 0.f;
+  if (tid >= 36 && tid < 39) sW[DW_STRIDE + DW_B3 + (tid - 36)] = dec[C_B3 + (tid - 36)];
+  if (tid == 39) sW[DW_STRIDE + DW_B3 + 3] = 0.f;
+  if (tid == 40) sW[DW_BETA] = dec[P_BETA];
+}
+__device__ __forceinline__ void decoder_weights_wait() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
 
 __device__ __forceinline__ float4 lds4(const float* p) { return *reinterpret_cast<const float4*>(p); }
 

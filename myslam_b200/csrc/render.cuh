@@ -16,6 +16,24 @@ struct SmemFwd {
   float one[NP], w[NP], z[NP], c[3][NP];
 };
 
+#ifdef ESLAM_PROFILE_PHASES
+// per-phase wall clocks of the backward kernel, summed over (CTA, warp 0 / warp 4) into g_phase[half][phase]
+__device__ unsigned long long g_phase[2][16];
+#define PHASE_MARK(i)                                                                         \
+  do {                                                                                        \
+    if ((threadIdx.x & 127) == 0) {                                                           \
+      const long long now_ = clock64();                                                       \
+      atomicAdd(&g_phase[threadIdx.x >> 7][i], (unsigned long long)(now_ - phase_t0_));       \
+      phase_t0_ = now_;                                                                       \
+    }                                                                                         \
+  } while (0)
+#define PHASE_INIT() long long phase_t0_ = clock64()
+#else
+#define PHASE_MARK(i) do {} while (0)
+#define PHASE_INIT() do {} while (0)
+#endif
+
+constexpr int WG_STRIDE = 20;  // floats per point in the staging buffers: 16 values + the output-layer gradients
 constexpr int NT_BWD = 256;  // threads of the backward kernel: threads 0-127 own the sdf decoder, 128-255 the rgb one
 
 template <bool GF>
@@ -25,8 +43,8 @@ struct SmemBwd {
   ax_t ax_i[12][NP];
   float ax_f[12][NP];
   float W[DW_TOTAL];   // both decoders' weights, symmetric blocks (field.cuh)
-  float act0[GF ? NP * 20 : 4];  // activation / gradient staging for the weight-gradient products
-  float act1[GF ? NP * 20 : 4];
+  float act0[GF ? NP * WG_STRIDE : 4];  // gradient / activation staging for the weight-gradient products
+  float act1[GF ? NP * WG_STRIDE : 4];
   float one[NP], w[NP], z[NP], c[3][NP], gww[NP];
   float gp[2][3][NP];  // d loss / d normalised coordinate, per decoder half
   float rayv[4][16];   // per ray: rendered depth, r, g, b
@@ -295,87 +313,157 @@ struct BwdArgs {
   float* pose_grad;
 };
 
-// weight gradients of one decoder, accumulated into the gradient arena.  The 128 threads that own the decoder
-// (`owner`) stage their activations / gradients; all NT_BWD threads then form the products over the NP points
-// of the tile with thread-owned outputs.  Contains __syncthreads: call from uniform control flow.
+// ---- weight gradients on the tensor cores ----------------------------------------------------------------------
+// dW[m][n] = sum over the tile's 128 points of grad[q][m] * act[q][n] is a 16 x N x 128 contraction per layer: dense,
+// batched over points, and as scalar FMAs (two shared-memory loads each) it took 15 % of the kernel's issue slots
+// (profiles/r01_bwd_full_summary.txt).  It runs as mma.sync m16n8k8 TF32 with the operands split into a TF32 head
+// and a TF32 tail (x = hi + lo; hi*hi + lo*hi + hi*lo: ~2^-21 relative, inside the 1e-3 gradient bar where a
+// single TF32 product would not be).  One warp owns one 16 x 8 output tile over all 16 k-steps, so there is no
+// cross-warp reduction; the bias gradients are the same contraction against a column of ones.
+__device__ __forceinline__ void split_tf32(float x, uint32_t& hi, uint32_t& lo) {
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(hi) : "f"(x));
+  const float r = x - __uint_as_float(hi);
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(lo) : "f"(r));
+}
+
+__device__ __forceinline__ void mma_tf32(float (&d)[4], const uint32_t (&a)[4], const uint32_t (&b)[2]) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+      : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]));
+}
+
+// B-operand sources: B[k][n] for point row k of the tile and output column n of this warp's 8-wide tile
+struct BFromBuf {  // staging buffer [NP][WG_STRIDE]
+  const float* buf;
+  int n0;
+  __device__ __forceinline__ float operator()(int q, int n) const { return buf[q * WG_STRIDE + n0 + n]; }
+};
+struct BFromTile {  // swizzled feature tile F[NP][64]
+  const float4* F;
+  int n0;
+  __device__ __forceinline__ float operator()(int q, int n) const { return f_scalar(F, q, n0 + n); }
+};
+struct BOnes {  // column 0 = 1: the bias gradient
+  __device__ __forceinline__ float operator()(int, int n) const { return n == 0 ? 1.0f : 0.0f; }
+};
+
+// acc (m16n8 fragment: rows g, g+8; columns 2t, 2t+1) = A^T B over the NP points; A[q][m] = abuf[q*WG_STRIDE + m]
+// for m < A_ROWS (4 or 16), zero above.  The three split products of two interleaved k-steps go to six independent
+// accumulators (dependent chains of 8 instead of 48 mma.sync).
+template <int A_ROWS, typename BLoad>
+__device__ __forceinline__ void wgrad_tile(const float* __restrict__ abuf, BLoad bload, int lane, float (&acc)[4]) {
+  const int g = lane >> 2, t = lane & 3;
+  float part[6][4];
+#pragma unroll
+  for (int i = 0; i < 6; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) part[i][j] = 0.f;
+#pragma unroll 1
+  for (int q0 = 0; q0 < NP; q0 += 16) {
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const int qa = q0 + h * 8 + t;
+      float af[4], bf[2];
+      af[0] = (g < A_ROWS) ? abuf[qa * WG_STRIDE + g] : 0.f;
+      af[2] = (g < A_ROWS) ? abuf[(qa + 4) * WG_STRIDE + g] : 0.f;
+      af[1] = (A_ROWS > 8) ? abuf[qa * WG_STRIDE + g + 8] : 0.f;
+      af[3] = (A_ROWS > 8) ? abuf[(qa + 4) * WG_STRIDE + g + 8] : 0.f;
+      bf[0] = bload(qa, g);
+      bf[1] = bload(qa + 4, g);
+      uint32_t ah[4], al[4], bh[2], bl[2];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) split_tf32(af[i], ah[i], al[i]);
+#pragma unroll
+      for (int i = 0; i < 2; ++i) split_tf32(bf[i], bh[i], bl[i]);
+      mma_tf32(part[h * 3 + 0], al, bh);
+      mma_tf32(part[h * 3 + 1], ah, bl);
+      mma_tf32(part[h * 3 + 2], ah, bh);
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < 4; ++j)
+    acc[j] = ((part[0][j] + part[3][j]) + (part[1][j] + part[4][j])) + (part[2][j] + part[5][j]);
+}
+
+// fragment -> gradient arena: dst[m * ld + n0 + n] for the fragment's (m, n); rows m >= m_valid are dropped.
+// Every CTA of the grid adds into the same 2700 floats, and same-line reductions serialise in L2, so lane pairs
+// (t, t^1) swap halves and each lane issues one 16-byte red.global.add.v4 (even t: row g, odd t: row g+8, four
+// consecutive columns) instead of four scalar atomics.
+__device__ __forceinline__ void wgrad_store(float* dst, int ld, int n0, int m_valid, int lane, const float (&acc)[4]) {
+  const int g = lane >> 2, t = lane & 3;
+  const bool even = (t & 1) == 0;
+  const float r0 = __shfl_xor_sync(0xffffffffu, even ? acc[2] : acc[0], 1);
+  const float r1 = __shfl_xor_sync(0xffffffffu, even ? acc[3] : acc[1], 1);
+  const int row = even ? g : g + 8;
+  const int col = n0 + 2 * (t & 2);
+  const float4 v = even ? make_float4(acc[0], acc[1], r0, r1) : make_float4(r0, r1, acc[2], acc[3]);
+  if (row < m_valid) red_add_v4(reinterpret_cast<float4*>(dst + row * ld + col), v);
+}
+__device__ __forceinline__ void wgrad_store_bias(float* dst, int m_valid, int lane, const float (&acc)[4]) {
+  const int g = lane >> 2, t = lane & 3;
+  if (t == 0) {  // column 0 of the ones tile
+    if (g < m_valid) atomicAdd(dst + g, acc[0]);
+    if (g + 8 < m_valid) atomicAdd(dst + g + 8, acc[2]);
+  }
+}
+
+// Weight gradients of one decoder, accumulated into the gradient arena.  The 128 threads that own the decoder
+// (`owner`) stage their activations / gradients; all 8 warps then take output tiles.  Contains __syncthreads: call
+// from uniform control flow.
 template <int W1, int B1, int W2, int B2, int W3, int B3, int NOUT>
 __device__ __forceinline__ void weight_grads(float* act0, float* act1, const float4* F, float* gdec, bool owner, int q,
                                              const float (&h1)[16], const float (&h2)[16], const float (&ga1)[16],
                                              const float (&ga2)[16], const float (&gout)[3]) {
-  const int t = threadIdx.x;
-  float4* a0 = reinterpret_cast<float4*>(act0 + q * 20);
-  float4* a1 = reinterpret_cast<float4*>(act1 + q * 20);
-  // --- output layer: dW3[o][i] = sum_q gout[o] h2[i]
-  if (owner) {
-#pragma unroll
-    for (int v = 0; v < 4; ++v) a0[v] = make_float4(h2[v * 4], h2[v * 4 + 1], h2[v * 4 + 2], h2[v * 4 + 3]);
-    a1[0] = make_float4(gout[0], gout[1], gout[2], 0.f);
-  }
-  __syncthreads();
-  if (t < NOUT * 16 + NOUT) {
-    const bool bias = t >= NOUT * 16;
-    const int o = bias ? t - NOUT * 16 : t >> 4, i = t & 15;
-    float acc = 0.f;
-    for (int qq = 0; qq < NP; ++qq) acc = fmaf(act1[qq * 20 + o], bias ? 1.0f : act0[qq * 20 + i], acc);
-    atomicAdd(gdec + (bias ? B3 + o : W3 + o * 16 + i), acc);
-  }
-  __syncthreads();
-  // --- hidden layer: dW2[j][i] = sum_q ga2[j] h1[i]
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  float4* a0 = reinterpret_cast<float4*>(act0 + q * WG_STRIDE);
+  float4* a1 = reinterpret_cast<float4*>(act1 + q * WG_STRIDE);
+  // ---- round 1: input layer (A = ga1, B = features) on all warps; output layer (A = gout, B = h2) on warps 0-2
   if (owner) {
 #pragma unroll
     for (int v = 0; v < 4; ++v) {
-      a0[v] = make_float4(h1[v * 4], h1[v * 4 + 1], h1[v * 4 + 2], h1[v * 4 + 3]);
-      a1[v] = make_float4(ga2[v * 4], ga2[v * 4 + 1], ga2[v * 4 + 2], ga2[v * 4 + 3]);
+      a0[v] = make_float4(ga1[v * 4], ga1[v * 4 + 1], ga1[v * 4 + 2], ga1[v * 4 + 3]);
+      a1[v] = make_float4(h2[v * 4], h2[v * 4 + 1], h2[v * 4 + 2], h2[v * 4 + 3]);
     }
+    a0[4] = make_float4(gout[0], gout[1], gout[2], 0.f);  // columns 16-19 of the gradient buffer
   }
   __syncthreads();
   {
-    const int i = t & 15, j = t >> 4;  // 256 outputs, one per thread
-    float acc = 0.f;
-#pragma unroll 4
-    for (int qq = 0; qq < NP; ++qq) acc = fmaf(act1[qq * 20 + j], act0[qq * 20 + i], acc);
-    atomicAdd(gdec + W2 + j * 16 + i, acc);
-    if (t < 16) {
-      float accb = 0.f;
-      for (int qq = 0; qq < NP; ++qq) accb += act1[qq * 20 + t];
-      atomicAdd(gdec + B2 + t, accb);
-    }
+    float acc[4];
+    wgrad_tile<16>(act0, BFromTile{F, warp * 8}, lane, acc);  // dW1[:, 8 warp .. 8 warp + 7]
+    wgrad_store(gdec + W1, 64, warp * 8, 16, lane, acc);
+  }
+  if (warp < 2) {
+    float acc[4];
+    wgrad_tile<4>(act0 + 16, BFromBuf{act1, warp * 8}, lane, acc);  // dW3[:, 8 warp ..]
+    wgrad_store(gdec + W3, 16, warp * 8, NOUT, lane, acc);
+  } else if (warp == 2) {
+    float acc[4];
+    wgrad_tile<4>(act0 + 16, BOnes{}, lane, acc);  // db3
+    wgrad_store_bias(gdec + B3, NOUT, lane, acc);
+  } else if (warp == 3) {
+    float acc[4];
+    wgrad_tile<16>(act0, BOnes{}, lane, acc);  // db1
+    wgrad_store_bias(gdec + B1, 16, lane, acc);
   }
   __syncthreads();
-  // --- input layer: dW1[j][c] = sum_q ga1[j] F[q][c]
+  // ---- round 2: hidden layer (A = ga2, B = h1) on warps 0-2
   if (owner) {
 #pragma unroll
-    for (int v = 0; v < 4; ++v) a1[v] = make_float4(ga1[v * 4], ga1[v * 4 + 1], ga1[v * 4 + 2], ga1[v * 4 + 3]);
+    for (int v = 0; v < 4; ++v) {
+      a0[v] = make_float4(ga2[v * 4], ga2[v * 4 + 1], ga2[v * 4 + 2], ga2[v * 4 + 3]);
+      a1[v] = make_float4(h1[v * 4], h1[v * 4 + 1], h1[v * 4 + 2], h1[v * 4 + 3]);
+    }
   }
   __syncthreads();
-  {
-    const int c = t & 63, j0 = (t >> 6) * 4;  // 1024 outputs, four per thread
-    float acc0 = 0.f, acc1 = 0.f, acc2 = 0.f, acc3 = 0.f;
-    const float* Ff = reinterpret_cast<const float*>(F);
-    int off[8];  // swizzled float offset of column c within row (8m + r): depends on r only
-#pragma unroll
-    for (int r = 0; r < 8; ++r) off[r] = r * 64 + ((((c >> 2) ^ r) << 2) | (c & 3));
-#pragma unroll 2
-    for (int m = 0; m < NP / 8; ++m) {
-#pragma unroll
-      for (int r = 0; r < 8; ++r) {
-        const float f = Ff[m * 512 + off[r]];
-        const float4 g0 = *reinterpret_cast<const float4*>(act1 + (m * 8 + r) * 20 + j0);
-        acc0 = fmaf(g0.x, f, acc0);
-        acc1 = fmaf(g0.y, f, acc1);
-        acc2 = fmaf(g0.z, f, acc2);
-        acc3 = fmaf(g0.w, f, acc3);
-      }
-    }
-    atomicAdd(gdec + W1 + (j0 + 0) * 64 + c, acc0);
-    atomicAdd(gdec + W1 + (j0 + 1) * 64 + c, acc1);
-    atomicAdd(gdec + W1 + (j0 + 2) * 64 + c, acc2);
-    atomicAdd(gdec + W1 + (j0 + 3) * 64 + c, acc3);
-    if (t < 16) {
-      float accb = 0.f;
-      for (int qq = 0; qq < NP; ++qq) accb += act1[qq * 20 + t];
-      atomicAdd(gdec + B1 + t, accb);
-    }
+  if (warp < 2) {
+    float acc[4];
+    wgrad_tile<16>(act0, BFromBuf{act1, warp * 8}, lane, acc);  // dW2[:, 8 warp ..]
+    wgrad_store(gdec + W2, 16, warp * 8, 16, lane, acc);
+  } else if (warp == 2) {
+    float acc[4];
+    wgrad_tile<16>(act0, BOnes{}, lane, acc);  // db2
+    wgrad_store_bias(gdec + B2, 16, lane, acc);
   }
   __syncthreads();
 }
@@ -540,6 +628,7 @@ __global__ void __launch_bounds__(NT_BWD, 2) k_render_bwd(const __grid_constant_
   const int k = q - rl * S;
   const int ray = ray0 + rl;
 
+  PHASE_INIT();
   // ---- P0/P1: points, normalised coordinates, axis set-ups of this half's two resolution groups
   float pn[3] = {0.f, 0.f, 0.f}, zk = 0.f;
   if (valid) {
@@ -554,13 +643,17 @@ __global__ void __launch_bounds__(NT_BWD, 2) k_render_bwd(const __grid_constant_
   write_axis_setups<2>(a.fk, 2 * half, pn, sm.ax_i + 6 * half, sm.ax_f + 6 * half, q);
   load_decoder_weights(sm.W, reinterpret_cast<const float*>(a.arena4) + a.fk.dec_off, tid, NT_BWD);
   __syncthreads();
+  PHASE_MARK(0);
   // ---- P2: gather this half's decoder features
   float4* Fh = half ? sm.F1 : sm.F0;
   if (half == 0)
     gather_tile<0>(a.fk, 0, a.arena4, sm.ax_i, sm.ax_f, sm.F0, n_valid, q);
   else
     gather_tile<6>(a.fk, 1, a.arena4, sm.ax_i, sm.ax_f, sm.F1, n_valid, q);
+  PHASE_MARK(1);
+  decoder_weights_wait();
   __syncthreads();
+  PHASE_MARK(2);
   // ---- P3: MLP forward of this half's decoder
   float h1[16], h2[16], out[3] = {0.f, 0.f, 0.f};
   float sdf = 0.f, u = 0.f, e = 0.f, alpha = 0.f, one = 1.f, rgb[3] = {0.f, 0.f, 0.f};
@@ -598,7 +691,9 @@ __global__ void __launch_bounds__(NT_BWD, 2) k_render_bwd(const __grid_constant_
       }
     }
   }
+  PHASE_MARK(3);
   __syncthreads();
+  PHASE_MARK(4);
   // ---- P4: compositing (sdf half)
   float T = 1.0f, w = 0.f;
   if (!POINTS) {
@@ -705,6 +800,7 @@ __global__ void __launch_bounds__(NT_BWD, 2) k_render_bwd(const __grid_constant_
       gout[0] = g_sdf * (1.0f - sdf * sdf);
     }
   }
+  PHASE_MARK(5);
   // ---- P6: MLP backward of this half's decoder
   float ga1[16], ga2[16];
   if (a.dbg & 4) {
@@ -713,6 +809,7 @@ __global__ void __launch_bounds__(NT_BWD, 2) k_render_bwd(const __grid_constant_
   } else {
     mlp_backward_hidden_s(Wh, gout, h1, h2, ga1, ga2);  // sdf: gout[1] = gout[2] = 0
   }
+  PHASE_MARK(6);
   if (GF && !(a.dbg & 2)) {
     float* gdec = a.grad_arena + a.fk.dec_off;
     weight_grads<S_W1, S_B1, S_W2, S_B2, S_W3, S_B3, 1>(sm.act0, sm.act1, sm.F0, gdec, half == 0, q, h1, h2, ga1, ga2, gout);
@@ -720,6 +817,7 @@ __global__ void __launch_bounds__(NT_BWD, 2) k_render_bwd(const __grid_constant_
     const float gb = warp_sum(g_beta);
     if (lane == 0) sm.red[warp] = gb;
   }
+  PHASE_MARK(7);
   if (a.dbg & 4) {
     Fh[q * 16] = make_float4(ga1[0], ga1[1], ga1[2], ga1[3]);
   } else {
@@ -731,6 +829,7 @@ __global__ void __launch_bounds__(NT_BWD, 2) k_render_bwd(const __grid_constant_
     for (int i = 0; i < NP / 32; ++i) gb += sm.red[i];  // only the sdf half carries beta gradients
     atomicAdd(a.grad_arena + a.fk.dec_off + P_BETA, gb);
   }
+  PHASE_MARK(8);
   // ---- P7: scatter to the planes / coordinate gradients (gather layout, each half its own decoder)
   {
     const int wl = (tid & (NP - 1)) >> 5, grp = lane >> 3, sub = lane & 7;
@@ -741,6 +840,7 @@ __global__ void __launch_bounds__(NT_BWD, 2) k_render_bwd(const __grid_constant_
     else
       scatter_group<GF, GR, 6>(a.fk, 1, a.arena4, garena4, sm.ax_i, sm.ax_f, sm.F1, qb, n_valid, sub, sm.gp[1], a.dbg);
   }
+  PHASE_MARK(9);
   // ---- P8: ray / point / pose gradients
   if (GR) {
     __syncthreads();
@@ -779,6 +879,7 @@ __global__ void __launch_bounds__(NT_BWD, 2) k_render_bwd(const __grid_constant_
       }
     }
   }
+  PHASE_MARK(10);
   // ---- loss sums
   if (FUSED && a.loss_acc) {
 #pragma unroll
