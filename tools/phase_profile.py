@@ -47,6 +47,7 @@ def main():
     store = synced_store(scene.all_planes, scene.decoders, scene.bound)
     lr = m["lr"]
     lib = load()
+    lib.eslam_set_debug(int(os.environ.get("ESLAM_B200_DEBUG", "0")))
     buf = (C.c_ulonglong * 32)()
     run = lambda: map_window(store, st["ws"], st["sc"], poses, cols, deps, m["pixels"], m["iters"], lr["decoders_lr"],
                              lr["planes_lr"], lr["c_planes_lr"], True, m["joint_opt_cam_lr"])
