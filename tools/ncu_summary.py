@@ -41,9 +41,10 @@ def launches(path):
         a[1] += v
     mine = {k: v for k, v in agg.items() if "eslam::" in k}
     tot = sum(a[1] for a in mine.values())
-    print("# ncu --metrics gpu__time_duration.sum --clock-control none  python tools/profile_step.py")
-    print("# (2 x [15 mapping iterations of 4000 rays] + 2 x [8 tracking iterations of 2000 rays]; cold-cache, serialised:")
-    print("#  compare SHARES, not absolutes).  Only this repo's kernels are listed; torch's RNG/fill kernels are excluded.")
+    print("# ncu --metrics gpu__time_duration.sum --clock-control none -c 2500 --csv  python bench.py --steps 2 --warmup 1 --profile-only")
+    print("# (the bench's own launch sequence: device-resident mapping calls, the backward kernel alone, tracking, the e2e")
+    print("#  drop-in calls; cold-cache and serialised under ncu: compare SHARES, not absolutes).  Only this repo's kernels")
+    print("#  are listed one by one; torch's kernels (scene synthesis, RNG draws, fills, copies) are summed in the last line.")
     print(f"{'us total':>10} {'launches':>8} {'us/launch':>10} {'share':>7}  kernel")
     for n, (c, t) in sorted(mine.items(), key=lambda x: -x[1][1]):
         print(f"{t:10.1f} {c:8d} {t / c:10.1f} {100 * t / tot:6.1f}%  {n}")
