@@ -315,11 +315,11 @@ struct BwdArgs {
 
 // ---- weight gradients on the tensor cores ----------------------------------------------------------------------
 // dW[m][n] = sum over the tile's 128 points of grad[q][m] * act[q][n] is a 16 x N x 128 contraction per layer: dense,
-// batched over points, and as scalar FMAs (two shared-memory loads each) it took 15 % of the kernel's issue slots
-// (profiles/r01_bwd_full_summary.txt).  It runs as mma.sync m16n8k8 TF32 with the operands split into a TF32 head
-// and a TF32 tail (x = hi + lo; hi*hi + lo*hi + hi*lo: ~2^-21 relative, inside the 1e-3 gradient bar where a
-// single TF32 product would not be).  One warp owns one 16 x 8 output tile over all 16 k-steps, so there is no
-// cross-warp reduction; the bias gradients are the same contraction against a column of ones.
+// batched over points, and as scalar FMAs (two shared-memory loads each) it took 15 % of the kernel's issue slots.
+// It runs as mma.sync m16n8k8 TF32 with the operands split into a TF32 head and a TF32 tail (x = hi + lo;
+// hi*hi + lo*hi + hi*lo: ~2^-21 relative, inside the 1e-3 gradient bar where a single TF32 product would not be).
+// A warp owns whole output tiles over all the points it is given; the bias gradients are the same contraction
+// against a column of ones.
 __device__ __forceinline__ void split_tf32(float x, uint32_t& hi, uint32_t& lo) {
   asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(hi) : "f"(x));
   const float r = x - __uint_as_float(hi);
@@ -333,57 +333,83 @@ __device__ __forceinline__ void mma_tf32(float (&d)[4], const uint32_t (&a)[4], 
       : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]));
 }
 
-// B-operand sources: B[k][n] for point row k of the tile and output column n of this warp's 8-wide tile
-struct BFromBuf {  // staging buffer [NP][WG_STRIDE]
+// Operand sources: element (point row q, channel c) of a staging buffer [NP][WG_STRIDE] or of a swizzled tile F[NP][64]
+struct FromBuf {
   const float* buf;
-  int n0;
-  __device__ __forceinline__ float operator()(int q, int n) const { return buf[q * WG_STRIDE + n0 + n]; }
+  int c0;
+  __device__ __forceinline__ float operator()(int q, int c) const { return buf[q * WG_STRIDE + c0 + c]; }
 };
-struct BFromTile {  // swizzled feature tile F[NP][64]
+struct FromTile {
   const float4* F;
-  int n0;
-  __device__ __forceinline__ float operator()(int q, int n) const { return f_scalar(F, q, n0 + n); }
-};
-struct BOnes {  // column 0 = 1: the bias gradient
-  __device__ __forceinline__ float operator()(int, int n) const { return n == 0 ? 1.0f : 0.0f; }
+  int c0;
+  __device__ __forceinline__ float operator()(int q, int c) const { return f_scalar(F, q, c0 + c); }
 };
 
-// acc (m16n8 fragment: rows g, g+8; columns 2t, 2t+1) = A^T B over the NP points; A[q][m] = abuf[q*WG_STRIDE + m]
-// for m < A_ROWS (4 or 16), zero above.  The three split products of two interleaved k-steps go to six independent
-// accumulators (dependent chains of 8 instead of 48 mma.sync).
-template <int A_ROWS, typename BLoad>
-__device__ __forceinline__ void wgrad_tile(const float* __restrict__ abuf, BLoad bload, int lane, float (&acc)[4]) {
+// acc[i] (m16n8 fragments: rows g, g+8; columns 2t, 2t+1) = A^T B_i over the points [q_lo, q_hi) of the tile, for NB
+// B operands that share the A fragments; A[q][m] = aload(q, m) for m < A_ROWS (4 or 16), zero above.  Loading and
+// splitting the fragments is most of the work, so a warp that owns two tiles pays for the A side once; with
+// NB == 1 two k-steps are interleaved to keep two independent mma chains in flight.
+template <int A_ROWS, int NB, typename ALoad, typename BLoad>
+__device__ __forceinline__ void wgrad_tiles(ALoad aload, const BLoad (&bload)[NB], int q_lo, int q_hi, int lane,
+                                            float (&acc)[NB][4]) {
   const int g = lane >> 2, t = lane & 3;
-  float part[6][4];
+  float lo_acc[NB][4];  // the two cross terms (small) accumulate apart from the head product
 #pragma unroll
-  for (int i = 0; i < 6; ++i)
+  for (int i = 0; i < NB; ++i)
 #pragma unroll
-    for (int j = 0; j < 4; ++j) part[i][j] = 0.f;
-#pragma unroll 1
-  for (int q0 = 0; q0 < NP; q0 += 16) {
+    for (int j = 0; j < 4; ++j) acc[i][j] = lo_acc[i][j] = 0.f;
+#pragma unroll 2
+  for (int q0 = q_lo; q0 < q_hi; q0 += 8) {
+    const int qa = q0 + t;
+    float af[4];
+    af[0] = (g < A_ROWS) ? aload(qa, g) : 0.f;
+    af[2] = (g < A_ROWS) ? aload(qa + 4, g) : 0.f;
+    af[1] = (A_ROWS > 8) ? aload(qa, g + 8) : 0.f;
+    af[3] = (A_ROWS > 8) ? aload(qa + 4, g + 8) : 0.f;
+    uint32_t ah[4], al[4];
 #pragma unroll
-    for (int h = 0; h < 2; ++h) {
-      const int qa = q0 + h * 8 + t;
-      float af[4], bf[2];
-      af[0] = (g < A_ROWS) ? abuf[qa * WG_STRIDE + g] : 0.f;
-      af[2] = (g < A_ROWS) ? abuf[(qa + 4) * WG_STRIDE + g] : 0.f;
-      af[1] = (A_ROWS > 8) ? abuf[qa * WG_STRIDE + g + 8] : 0.f;
-      af[3] = (A_ROWS > 8) ? abuf[(qa + 4) * WG_STRIDE + g + 8] : 0.f;
-      bf[0] = bload(qa, g);
-      bf[1] = bload(qa + 4, g);
-      uint32_t ah[4], al[4], bh[2], bl[2];
+    for (int i = 0; i < 4; ++i) split_tf32(af[i], ah[i], al[i]);
 #pragma unroll
-      for (int i = 0; i < 4; ++i) split_tf32(af[i], ah[i], al[i]);
-#pragma unroll
-      for (int i = 0; i < 2; ++i) split_tf32(bf[i], bh[i], bl[i]);
-      mma_tf32(part[h * 3 + 0], al, bh);
-      mma_tf32(part[h * 3 + 1], ah, bl);
-      mma_tf32(part[h * 3 + 2], ah, bh);
+    for (int b = 0; b < NB; ++b) {
+      uint32_t bh[2], bl[2];
+      split_tf32(bload[b](qa, g), bh[0], bl[0]);
+      split_tf32(bload[b](qa + 4, g), bh[1], bl[1]);
+      mma_tf32(lo_acc[b], al, bh);
+      mma_tf32(lo_acc[b], ah, bl);
+      mma_tf32(acc[b], ah, bh);
     }
   }
 #pragma unroll
-  for (int j = 0; j < 4; ++j)
-    acc[j] = ((part[0][j] + part[3][j]) + (part[1][j] + part[4][j])) + (part[2][j] + part[5][j]);
+  for (int i = 0; i < NB; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] += lo_acc[i][j];
+}
+
+// the bias gradients: A^T 1 (column 0 of a tile whose B is one column of ones; 1.0 is exact in TF32)
+template <int A_ROWS, typename ALoad>
+__device__ __forceinline__ void wgrad_bias(ALoad aload, int lane, float (&acc)[4]) {
+  const int g = lane >> 2, t = lane & 3;
+  float lo_acc[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) acc[j] = lo_acc[j] = 0.f;
+  uint32_t bh[2];
+  bh[0] = bh[1] = __float_as_uint(g == 0 ? 1.0f : 0.0f);
+#pragma unroll 2
+  for (int q0 = 0; q0 < NP; q0 += 8) {
+    const int qa = q0 + t;
+    float af[4];
+    af[0] = (g < A_ROWS) ? aload(qa, g) : 0.f;
+    af[2] = (g < A_ROWS) ? aload(qa + 4, g) : 0.f;
+    af[1] = (A_ROWS > 8) ? aload(qa, g + 8) : 0.f;
+    af[3] = (A_ROWS > 8) ? aload(qa + 4, g + 8) : 0.f;
+    uint32_t ah[4], al[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) split_tf32(af[i], ah[i], al[i]);
+    mma_tf32(lo_acc, al, bh);
+    mma_tf32(acc, ah, bh);
+  }
+#pragma unroll
+  for (int j = 0; j < 4; ++j) acc[j] += lo_acc[j];
 }
 
 // fragment -> gradient arena: dst[m * ld + n0 + n] for the fragment's (m, n); rows m >= m_valid are dropped.
@@ -408,62 +434,74 @@ __device__ __forceinline__ void wgrad_store_bias(float* dst, int m_valid, int la
   }
 }
 
-// Weight gradients of one decoder, accumulated into the gradient arena.  The 128 threads that own the decoder
-// (`owner`) stage their activations / gradients; all 8 warps then take output tiles.  Contains __syncthreads: call
-// from uniform control flow.
-template <int W1, int B1, int W2, int B2, int W3, int B3, int NOUT>
-__device__ __forceinline__ void weight_grads(float* act0, float* act1, const float4* F, float* gdec, bool owner, int q,
-                                             const float (&h1)[16], const float (&h2)[16], const float (&ga1)[16],
+// Weight gradients of BOTH decoders, accumulated into the gradient arena, in two CTA-wide rounds.  Warps 0-3 work
+// on the sdf decoder, warps 4-7 on the rgb decoder (the same split as the thread halves, so `half` is also the
+// decoder a warp computes for).  Contains __syncthreads: call from uniform control flow.
+//   round 1  input layer  dW1 = ga1^T F : ga1 staged in act0 (sdf) / act1 (rgb); warp w of a half owns feature
+//            columns 16w..16w+15 (two tiles sharing the A fragments); warp 0 of a half also takes db1
+//   round 2  hidden and output layers: every owner thread parks (ga2 | h1 | h2 | gout) in ITS OWN row of the feature
+//            tile, which is dead after round 1 and is only rewritten by mlp_backward_input afterwards; per half:
+//            warps 0,1 dW2 (half of the points each, two tiles), warp 2 dW3 (two tiles), warp 3 db2 and db3
+__device__ __forceinline__ void weight_grads(float* act0, float* act1, float4* F0, float4* F1, float* gdec, int half,
+                                             int q, const float (&h1)[16], const float (&h2)[16], const float (&ga1)[16],
                                              const float (&ga2)[16], const float (&gout)[3]) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  float4* a0 = reinterpret_cast<float4*>(act0 + q * WG_STRIDE);
-  float4* a1 = reinterpret_cast<float4*>(act1 + q * WG_STRIDE);
-  // ---- round 1: input layer (A = ga1, B = features) on all warps; output layer (A = gout, B = h2) on warps 0-2
-  if (owner) {
+  const int wl = warp & 3;
+  float* abuf = half ? act1 : act0;
+  float4* F = half ? F1 : F0;
+  const int nout = half ? 3 : 1;
+  float* gW1 = gdec + (half ? C_W1 : S_W1);
+  float* gB1 = gdec + (half ? C_B1 : S_B1);
+  float* gW2 = gdec + (half ? C_W2 : S_W2);
+  float* gB2 = gdec + (half ? C_B2 : S_B2);
+  float* gW3 = gdec + (half ? C_W3 : S_W3);
+  float* gB3 = gdec + (half ? C_B3 : S_B3);
+  // ---- round 1
+  {
+    float4* a0 = reinterpret_cast<float4*>(abuf + q * WG_STRIDE);
 #pragma unroll
-    for (int v = 0; v < 4; ++v) {
-      a0[v] = make_float4(ga1[v * 4], ga1[v * 4 + 1], ga1[v * 4 + 2], ga1[v * 4 + 3]);
-      a1[v] = make_float4(h2[v * 4], h2[v * 4 + 1], h2[v * 4 + 2], h2[v * 4 + 3]);
-    }
-    a0[4] = make_float4(gout[0], gout[1], gout[2], 0.f);  // columns 16-19 of the gradient buffer
+    for (int v = 0; v < 4; ++v) a0[v] = make_float4(ga1[v * 4], ga1[v * 4 + 1], ga1[v * 4 + 2], ga1[v * 4 + 3]);
   }
   __syncthreads();
   {
-    float acc[4];
-    wgrad_tile<16>(act0, BFromTile{F, warp * 8}, lane, acc);  // dW1[:, 8 warp .. 8 warp + 7]
-    wgrad_store(gdec + W1, 64, warp * 8, 16, lane, acc);
-  }
-  if (warp < 2) {
-    float acc[4];
-    wgrad_tile<4>(act0 + 16, BFromBuf{act1, warp * 8}, lane, acc);  // dW3[:, 8 warp ..]
-    wgrad_store(gdec + W3, 16, warp * 8, NOUT, lane, acc);
-  } else if (warp == 2) {
-    float acc[4];
-    wgrad_tile<4>(act0 + 16, BOnes{}, lane, acc);  // db3
-    wgrad_store_bias(gdec + B3, NOUT, lane, acc);
-  } else if (warp == 3) {
-    float acc[4];
-    wgrad_tile<16>(act0, BOnes{}, lane, acc);  // db1
-    wgrad_store_bias(gdec + B1, 16, lane, acc);
-  }
-  __syncthreads();
-  // ---- round 2: hidden layer (A = ga2, B = h1) on warps 0-2
-  if (owner) {
-#pragma unroll
-    for (int v = 0; v < 4; ++v) {
-      a0[v] = make_float4(ga2[v * 4], ga2[v * 4 + 1], ga2[v * 4 + 2], ga2[v * 4 + 3]);
-      a1[v] = make_float4(h1[v * 4], h1[v * 4 + 1], h1[v * 4 + 2], h1[v * 4 + 3]);
+    float acc[2][4];
+    const FromTile b[2] = {{F, wl * 16}, {F, wl * 16 + 8}};
+    wgrad_tiles<16, 2>(FromBuf{abuf, 0}, b, 0, NP, lane, acc);
+    wgrad_store(gW1, 64, wl * 16, 16, lane, acc[0]);
+    wgrad_store(gW1, 64, wl * 16 + 8, 16, lane, acc[1]);
+    if (wl == 0) {
+      wgrad_bias<16>(FromBuf{abuf, 0}, lane, acc[0]);
+      wgrad_store_bias(gB1, 16, lane, acc[0]);
     }
   }
   __syncthreads();
-  if (warp < 2) {
+  // ---- round 2: columns 0-15 ga2, 16-31 h1, 32-47 h2, 48-51 gout of the thread's own feature-tile row
+#pragma unroll
+  for (int v = 0; v < 4; ++v) {
+    F[f_slot(q, v)] = make_float4(ga2[v * 4], ga2[v * 4 + 1], ga2[v * 4 + 2], ga2[v * 4 + 3]);
+    F[f_slot(q, 4 + v)] = make_float4(h1[v * 4], h1[v * 4 + 1], h1[v * 4 + 2], h1[v * 4 + 3]);
+    F[f_slot(q, 8 + v)] = make_float4(h2[v * 4], h2[v * 4 + 1], h2[v * 4 + 2], h2[v * 4 + 3]);
+  }
+  F[f_slot(q, 12)] = make_float4(gout[0], gout[1], gout[2], 0.f);
+  __syncthreads();
+  if (wl < 2) {
+    float acc[2][4];
+    const FromTile b[2] = {{F, 16}, {F, 24}};
+    wgrad_tiles<16, 2>(FromTile{F, 0}, b, wl * (NP / 2), (wl + 1) * (NP / 2), lane, acc);
+    wgrad_store(gW2, 16, 0, 16, lane, acc[0]);
+    wgrad_store(gW2, 16, 8, 16, lane, acc[1]);
+  } else if (wl == 2) {
+    float acc[2][4];
+    const FromTile b[2] = {{F, 32}, {F, 40}};
+    wgrad_tiles<4, 2>(FromTile{F, 48}, b, 0, NP, lane, acc);
+    wgrad_store(gW3, 16, 0, nout, lane, acc[0]);
+    wgrad_store(gW3, 16, 8, nout, lane, acc[1]);
+  } else {
     float acc[4];
-    wgrad_tile<16>(act0, BFromBuf{act1, warp * 8}, lane, acc);  // dW2[:, 8 warp ..]
-    wgrad_store(gdec + W2, 16, warp * 8, 16, lane, acc);
-  } else if (warp == 2) {
-    float acc[4];
-    wgrad_tile<16>(act0, BOnes{}, lane, acc);  // db2
-    wgrad_store_bias(gdec + B2, 16, lane, acc);
+    wgrad_bias<16>(FromTile{F, 0}, lane, acc);
+    wgrad_store_bias(gB2, 16, lane, acc);
+    wgrad_bias<4>(FromTile{F, 48}, lane, acc);
+    wgrad_store_bias(gB3, nout, lane, acc);
   }
   __syncthreads();
 }
@@ -812,8 +850,7 @@ __global__ void __launch_bounds__(NT_BWD, 2) k_render_bwd(const __grid_constant_
   PHASE_MARK(6);
   if (GF && !(a.dbg & 2)) {
     float* gdec = a.grad_arena + a.fk.dec_off;
-    weight_grads<S_W1, S_B1, S_W2, S_B2, S_W3, S_B3, 1>(sm.act0, sm.act1, sm.F0, gdec, half == 0, q, h1, h2, ga1, ga2, gout);
-    weight_grads<C_W1, C_B1, C_W2, C_B2, C_W3, C_B3, 3>(sm.act0, sm.act1, sm.F1, gdec, half == 1, q, h1, h2, ga1, ga2, gout);
+    weight_grads(sm.act0, sm.act1, sm.F0, sm.F1, gdec, half, q, h1, h2, ga1, ga2, gout);
     const float gb = warp_sum(g_beta);
     if (lane == 0) sm.red[warp] = gb;
   }
