@@ -333,26 +333,36 @@ __device__ __forceinline__ void mma_tf32(float (&d)[4], const uint32_t (&a)[4], 
       : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]));
 }
 
-// Operand sources: element (point row q, channel c) of a staging buffer [NP][WG_STRIDE] or of a swizzled tile F[NP][64]
-struct FromBuf {
-  const float* buf;
-  int c0;
-  __device__ __forceinline__ float operator()(int q, int c) const { return buf[q * WG_STRIDE + c0 + c]; }
+// Operand sources for the mma fragments.  A lane always reads channel c of the point rows q0 + t and q0 + t + 4 with
+// q0 a multiple of 8, so everything but q0 folds into two per-lane offsets computed once (for the swizzled feature
+// tile the XOR term depends on q & 7 = t or t + 4 only).
+struct FromBuf {  // staging buffer [NP][WG_STRIDE]
+  const float* base;
+  int o0, o1;
+  __device__ __forceinline__ FromBuf(const float* buf, int c, int t)
+      : base(buf), o0(t * WG_STRIDE + c), o1((t + 4) * WG_STRIDE + c) {}
+  __device__ __forceinline__ float lo(int q0) const { return base[q0 * WG_STRIDE + o0]; }
+  __device__ __forceinline__ float hi(int q0) const { return base[q0 * WG_STRIDE + o1]; }
 };
-struct FromTile {
-  const float4* F;
-  int c0;
-  __device__ __forceinline__ float operator()(int q, int c) const { return f_scalar(F, q, c0 + c); }
+struct FromTile {  // swizzled tile F[NP][64]
+  const float* base;
+  int o0, o1;
+  __device__ __forceinline__ FromTile(const float4* F, int c, int t)
+      : base(reinterpret_cast<const float*>(F)),
+        o0((t * 16 + ((c >> 2) ^ t)) * 4 + (c & 3)),
+        o1(((t + 4) * 16 + ((c >> 2) ^ (t + 4))) * 4 + (c & 3)) {}
+  __device__ __forceinline__ float lo(int q0) const { return base[q0 * 64 + o0]; }
+  __device__ __forceinline__ float hi(int q0) const { return base[q0 * 64 + o1]; }
 };
 
-// acc[i] (m16n8 fragments: rows g, g+8; columns 2t, 2t+1) = A^T B_i over the points [q_lo, q_hi) of the tile, for NB
-// B operands that share the A fragments; A[q][m] = aload(q, m) for m < A_ROWS (4 or 16), zero above.  Loading and
-// splitting the fragments is most of the work, so a warp that owns two tiles pays for the A side once; with
-// NB == 1 two k-steps are interleaved to keep two independent mma chains in flight.
-template <int A_ROWS, int NB, typename ALoad, typename BLoad>
-__device__ __forceinline__ void wgrad_tiles(ALoad aload, const BLoad (&bload)[NB], int q_lo, int q_hi, int lane,
-                                            float (&acc)[NB][4]) {
-  const int g = lane >> 2, t = lane & 3;
+// acc[i] (m16n8 fragments: rows g, g+8; columns 2t, 2t+1) = A^T B_i over the points [q_lo, q_hi) of the tile (multiples
+// of 8), for NB B operands that share the A fragments.  a_lo / a_hi read gradient channels g and g + 8 (A_ROWS = 4:
+// channels >= 4 are zero and a_hi is not read); b[i] reads activation channel n0_i + g.  Loading and splitting the
+// fragments is most of the work, so a warp that owns two tiles pays for the A side once.
+template <int A_ROWS, int NB, typename AFrag, typename BFrag>
+__device__ __forceinline__ void wgrad_tiles(const AFrag& a_lo, const AFrag& a_hi, const BFrag (&b)[NB], int q_lo, int q_hi,
+                                            int lane, float (&acc)[NB][4]) {
+  const int g = lane >> 2;
   float lo_acc[NB][4];  // the two cross terms (small) accumulate apart from the head product
 #pragma unroll
   for (int i = 0; i < NB; ++i)
@@ -360,23 +370,22 @@ __device__ __forceinline__ void wgrad_tiles(ALoad aload, const BLoad (&bload)[NB
     for (int j = 0; j < 4; ++j) acc[i][j] = lo_acc[i][j] = 0.f;
 #pragma unroll 2
   for (int q0 = q_lo; q0 < q_hi; q0 += 8) {
-    const int qa = q0 + t;
     float af[4];
-    af[0] = (g < A_ROWS) ? aload(qa, g) : 0.f;
-    af[2] = (g < A_ROWS) ? aload(qa + 4, g) : 0.f;
-    af[1] = (A_ROWS > 8) ? aload(qa, g + 8) : 0.f;
-    af[3] = (A_ROWS > 8) ? aload(qa + 4, g + 8) : 0.f;
+    af[0] = (g < A_ROWS) ? a_lo.lo(q0) : 0.f;
+    af[2] = (g < A_ROWS) ? a_lo.hi(q0) : 0.f;
+    af[1] = (A_ROWS > 8) ? a_hi.lo(q0) : 0.f;
+    af[3] = (A_ROWS > 8) ? a_hi.hi(q0) : 0.f;
     uint32_t ah[4], al[4];
 #pragma unroll
     for (int i = 0; i < 4; ++i) split_tf32(af[i], ah[i], al[i]);
 #pragma unroll
-    for (int b = 0; b < NB; ++b) {
+    for (int i = 0; i < NB; ++i) {
       uint32_t bh[2], bl[2];
-      split_tf32(bload[b](qa, g), bh[0], bl[0]);
-      split_tf32(bload[b](qa + 4, g), bh[1], bl[1]);
-      mma_tf32(lo_acc[b], al, bh);
-      mma_tf32(lo_acc[b], ah, bl);
-      mma_tf32(acc[b], ah, bh);
+      split_tf32(b[i].lo(q0), bh[0], bl[0]);
+      split_tf32(b[i].hi(q0), bh[1], bl[1]);
+      mma_tf32(lo_acc[i], al, bh);
+      mma_tf32(lo_acc[i], ah, bl);
+      mma_tf32(acc[i], ah, bh);
     }
   }
 #pragma unroll
@@ -386,9 +395,9 @@ __device__ __forceinline__ void wgrad_tiles(ALoad aload, const BLoad (&bload)[NB
 }
 
 // the bias gradients: A^T 1 (column 0 of a tile whose B is one column of ones; 1.0 is exact in TF32)
-template <int A_ROWS, typename ALoad>
-__device__ __forceinline__ void wgrad_bias(ALoad aload, int lane, float (&acc)[4]) {
-  const int g = lane >> 2, t = lane & 3;
+template <int A_ROWS, typename AFrag>
+__device__ __forceinline__ void wgrad_bias(const AFrag& a_lo, const AFrag& a_hi, int lane, float (&acc)[4]) {
+  const int g = lane >> 2;
   float lo_acc[4];
 #pragma unroll
   for (int j = 0; j < 4; ++j) acc[j] = lo_acc[j] = 0.f;
@@ -396,12 +405,11 @@ __device__ __forceinline__ void wgrad_bias(ALoad aload, int lane, float (&acc)[4
   bh[0] = bh[1] = __float_as_uint(g == 0 ? 1.0f : 0.0f);
 #pragma unroll 2
   for (int q0 = 0; q0 < NP; q0 += 8) {
-    const int qa = q0 + t;
     float af[4];
-    af[0] = (g < A_ROWS) ? aload(qa, g) : 0.f;
-    af[2] = (g < A_ROWS) ? aload(qa + 4, g) : 0.f;
-    af[1] = (A_ROWS > 8) ? aload(qa, g + 8) : 0.f;
-    af[3] = (A_ROWS > 8) ? aload(qa + 4, g + 8) : 0.f;
+    af[0] = (g < A_ROWS) ? a_lo.lo(q0) : 0.f;
+    af[2] = (g < A_ROWS) ? a_lo.hi(q0) : 0.f;
+    af[1] = (A_ROWS > 8) ? a_hi.lo(q0) : 0.f;
+    af[3] = (A_ROWS > 8) ? a_hi.hi(q0) : 0.f;
     uint32_t ah[4], al[4];
 #pragma unroll
     for (int i = 0; i < 4; ++i) split_tf32(af[i], ah[i], al[i]);
@@ -463,14 +471,16 @@ __device__ __forceinline__ void weight_grads(float* act0, float* act1, float4* F
     for (int v = 0; v < 4; ++v) a0[v] = make_float4(ga1[v * 4], ga1[v * 4 + 1], ga1[v * 4 + 2], ga1[v * 4 + 3]);
   }
   __syncthreads();
+  const int g = lane >> 2, t = lane & 3;
   {
     float acc[2][4];
-    const FromTile b[2] = {{F, wl * 16}, {F, wl * 16 + 8}};
-    wgrad_tiles<16, 2>(FromBuf{abuf, 0}, b, 0, NP, lane, acc);
+    const FromBuf a_lo(abuf, g, t), a_hi(abuf, g + 8, t);
+    const FromTile b[2] = {FromTile(F, wl * 16 + g, t), FromTile(F, wl * 16 + 8 + g, t)};
+    wgrad_tiles<16, 2>(a_lo, a_hi, b, 0, NP, lane, acc);
     wgrad_store(gW1, 64, wl * 16, 16, lane, acc[0]);
     wgrad_store(gW1, 64, wl * 16 + 8, 16, lane, acc[1]);
     if (wl == 0) {
-      wgrad_bias<16>(FromBuf{abuf, 0}, lane, acc[0]);
+      wgrad_bias<16>(a_lo, a_hi, lane, acc[0]);
       wgrad_store_bias(gB1, 16, lane, acc[0]);
     }
   }
@@ -484,23 +494,25 @@ __device__ __forceinline__ void weight_grads(float* act0, float* act1, float4* F
   }
   F[f_slot(q, 12)] = make_float4(gout[0], gout[1], gout[2], 0.f);
   __syncthreads();
+  const FromTile g2_lo(F, g, t), g2_hi(F, 8 + g, t);  // ga2 channels g, g + 8
+  const FromTile g3_lo(F, 48 + (g & 3), t);           // gout channel g (< 4; lanes with g >= 4 contribute zeros)
   if (wl < 2) {
     float acc[2][4];
-    const FromTile b[2] = {{F, 16}, {F, 24}};
-    wgrad_tiles<16, 2>(FromTile{F, 0}, b, wl * (NP / 2), (wl + 1) * (NP / 2), lane, acc);
+    const FromTile b[2] = {FromTile(F, 16 + g, t), FromTile(F, 24 + g, t)};
+    wgrad_tiles<16, 2>(g2_lo, g2_hi, b, wl * (NP / 2), (wl + 1) * (NP / 2), lane, acc);
     wgrad_store(gW2, 16, 0, 16, lane, acc[0]);
     wgrad_store(gW2, 16, 8, 16, lane, acc[1]);
   } else if (wl == 2) {
     float acc[2][4];
-    const FromTile b[2] = {{F, 32}, {F, 40}};
-    wgrad_tiles<4, 2>(FromTile{F, 48}, b, 0, NP, lane, acc);
+    const FromTile b[2] = {FromTile(F, 32 + g, t), FromTile(F, 40 + g, t)};
+    wgrad_tiles<4, 2>(g3_lo, g3_lo, b, 0, NP, lane, acc);
     wgrad_store(gW3, 16, 0, nout, lane, acc[0]);
     wgrad_store(gW3, 16, 8, nout, lane, acc[1]);
   } else {
     float acc[4];
-    wgrad_bias<16>(FromTile{F, 0}, lane, acc);
+    wgrad_bias<16>(g2_lo, g2_hi, lane, acc);
     wgrad_store_bias(gB2, 16, lane, acc);
-    wgrad_bias<4>(FromTile{F, 48}, lane, acc);
+    wgrad_bias<4>(g3_lo, g3_lo, lane, acc);
     wgrad_store_bias(gB3, nout, lane, acc);
   }
   __syncthreads();
