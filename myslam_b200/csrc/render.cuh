@@ -316,108 +316,123 @@ struct BwdArgs {
 // ---- weight gradients on the tensor cores ----------------------------------------------------------------------
 // dW[m][n] = sum over the tile's 128 points of grad[q][m] * act[q][n] is a 16 x N x 128 contraction per layer: dense,
 // batched over points, and as scalar FMAs (two shared-memory loads each) it took 15 % of the kernel's issue slots.
-// It runs as mma.sync m16n8k8 TF32 with the operands split into a TF32 head and a TF32 tail (x = hi + lo;
-// hi*hi + lo*hi + hi*lo: ~2^-21 relative, inside the 1e-3 gradient bar where a single TF32 product would not be).
+// It runs as mma.sync m16n8k16 bf16 with every operand split into a bf16 head and middle (x = h + m + O(2^-16 x);
+// h*h + m*h + h*m: ~2^-15 relative, inside the 1e-3 gradient bar where a single bf16 or TF32 product is not).
 // A warp owns whole output tiles over all the points it is given; the bias gradients are the same contraction
 // against a column of ones.
-__device__ __forceinline__ void split_tf32(float x, uint32_t& hi, uint32_t& lo) {
-  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(hi) : "f"(x));
-  const float r = x - __uint_as_float(hi);
-  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(lo) : "f"(r));
+// x0, x1 -> packed bf16 pairs (low half = x0): head = bf16(x), middle = bf16(x - head)
+__device__ __forceinline__ void split_bf16x2(float x0, float x1, uint32_t& hi, uint32_t& mid) {
+  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(hi) : "f"(x1), "f"(x0));
+  const float h0 = __uint_as_float(hi << 16), h1 = __uint_as_float(hi & 0xffff0000u);
+  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(mid) : "f"(x1 - h1), "f"(x0 - h0));
 }
 
-__device__ __forceinline__ void mma_tf32(float (&d)[4], const uint32_t (&a)[4], const uint32_t (&b)[2]) {
+__device__ __forceinline__ void mma_bf16(float (&d)[4], const uint32_t (&a)[4], const uint32_t (&b)[2]) {
   asm volatile(
-      "mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+      "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
       : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
       : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]));
 }
 
-// Operand sources for the mma fragments.  A lane always reads channel c of the point rows q0 + t and q0 + t + 4 with
-// q0 a multiple of 8, so everything but q0 folds into two per-lane offsets computed once (for the swizzled feature
-// tile the XOR term depends on q & 7 = t or t + 4 only).
+// Operand sources for the mma fragments.  In a k-step of 16 points starting at q0 (a multiple of 16) a lane reads
+// channel c of the point rows q0 + {2t, 2t+1, 2t+8, 2t+9}, so everything but q0 folds into four per-lane offsets
+// computed once (for the swizzled feature tile the XOR term depends on the row's low 3 bits only).
 struct FromBuf {  // staging buffer [NP][WG_STRIDE]
   const float* base;
-  int o0, o1;
-  __device__ __forceinline__ FromBuf(const float* buf, int c, int t)
-      : base(buf), o0(t * WG_STRIDE + c), o1((t + 4) * WG_STRIDE + c) {}
-  __device__ __forceinline__ float lo(int q0) const { return base[q0 * WG_STRIDE + o0]; }
-  __device__ __forceinline__ float hi(int q0) const { return base[q0 * WG_STRIDE + o1]; }
+  int o[4];
+  __device__ __forceinline__ FromBuf(const float* buf, int c, int t) : base(buf) {
+    const int r[4] = {2 * t, 2 * t + 1, 2 * t + 8, 2 * t + 9};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) o[i] = r[i] * WG_STRIDE + c;
+  }
+  __device__ __forceinline__ float at(int q0, int i) const { return base[q0 * WG_STRIDE + o[i]]; }
 };
 struct FromTile {  // swizzled tile F[NP][64]
   const float* base;
-  int o0, o1;
-  __device__ __forceinline__ FromTile(const float4* F, int c, int t)
-      : base(reinterpret_cast<const float*>(F)),
-        o0((t * 16 + ((c >> 2) ^ t)) * 4 + (c & 3)),
-        o1(((t + 4) * 16 + ((c >> 2) ^ (t + 4))) * 4 + (c & 3)) {}
-  __device__ __forceinline__ float lo(int q0) const { return base[q0 * 64 + o0]; }
-  __device__ __forceinline__ float hi(int q0) const { return base[q0 * 64 + o1]; }
+  int o[4];
+  __device__ __forceinline__ FromTile(const float4* F, int c, int t) : base(reinterpret_cast<const float*>(F)) {
+    const int r[4] = {2 * t, 2 * t + 1, 2 * t + 8, 2 * t + 9};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) o[i] = (r[i] * 16 + ((c >> 2) ^ (r[i] & 7))) * 4 + (c & 3);
+  }
+  __device__ __forceinline__ float at(int q0, int i) const { return base[q0 * 64 + o[i]]; }
 };
 
 // acc[i] (m16n8 fragments: rows g, g+8; columns 2t, 2t+1) = A^T B_i over the points [q_lo, q_hi) of the tile (multiples
-// of 8), for NB B operands that share the A fragments.  a_lo / a_hi read gradient channels g and g + 8 (A_ROWS = 4:
-// channels >= 4 are zero and a_hi is not read); b[i] reads activation channel n0_i + g.  Loading and splitting the
-// fragments is most of the work, so a warp that owns two tiles pays for the A side once.
+// of 16), for NB B operands that share the A fragments.  a_lo / a_hi read gradient channels g and g + 8 (A_ROWS = 4:
+// channels >= 4 are zero and a_hi is not read); b[i] reads activation channel n0_i + g.
+// Every operand is split x = head + middle (+ a dropped 2^-16 tail) in bf16 and three products are accumulated:
+// head*head, middle*head, head*middle.  The legacy mma.sync pipe, not instruction issue, bounds this phase on
+// sm_100a (a TF32 m16n8k8 head/tail split, 6 mma per 16 points, measured 10.4 us per CTA; this form needs 3).
 template <int A_ROWS, int NB, typename AFrag, typename BFrag>
 __device__ __forceinline__ void wgrad_tiles(const AFrag& a_lo, const AFrag& a_hi, const BFrag (&b)[NB], int q_lo, int q_hi,
                                             int lane, float (&acc)[NB][4]) {
   const int g = lane >> 2;
-  float lo_acc[NB][4];  // the two cross terms (small) accumulate apart from the head product
+  float x_acc[NB][4];  // the two cross terms (small) accumulate apart from the head product
 #pragma unroll
   for (int i = 0; i < NB; ++i)
 #pragma unroll
-    for (int j = 0; j < 4; ++j) acc[i][j] = lo_acc[i][j] = 0.f;
+    for (int j = 0; j < 4; ++j) acc[i][j] = x_acc[i][j] = 0.f;
 #pragma unroll 2
-  for (int q0 = q_lo; q0 < q_hi; q0 += 8) {
-    float af[4];
-    af[0] = (g < A_ROWS) ? a_lo.lo(q0) : 0.f;
-    af[2] = (g < A_ROWS) ? a_lo.hi(q0) : 0.f;
-    af[1] = (A_ROWS > 8) ? a_hi.lo(q0) : 0.f;
-    af[3] = (A_ROWS > 8) ? a_hi.hi(q0) : 0.f;
-    uint32_t ah[4], al[4];
-#pragma unroll
-    for (int i = 0; i < 4; ++i) split_tf32(af[i], ah[i], al[i]);
+  for (int q0 = q_lo; q0 < q_hi; q0 += 16) {
+    uint32_t ah[4], am[4];
+    if (g < A_ROWS) {
+      split_bf16x2(a_lo.at(q0, 0), a_lo.at(q0, 1), ah[0], am[0]);
+      split_bf16x2(a_lo.at(q0, 2), a_lo.at(q0, 3), ah[2], am[2]);
+    } else {
+      ah[0] = am[0] = ah[2] = am[2] = 0u;
+    }
+    if (A_ROWS > 8) {
+      split_bf16x2(a_hi.at(q0, 0), a_hi.at(q0, 1), ah[1], am[1]);
+      split_bf16x2(a_hi.at(q0, 2), a_hi.at(q0, 3), ah[3], am[3]);
+    } else {
+      ah[1] = am[1] = ah[3] = am[3] = 0u;
+    }
 #pragma unroll
     for (int i = 0; i < NB; ++i) {
-      uint32_t bh[2], bl[2];
-      split_tf32(b[i].lo(q0), bh[0], bl[0]);
-      split_tf32(b[i].hi(q0), bh[1], bl[1]);
-      mma_tf32(lo_acc[i], al, bh);
-      mma_tf32(lo_acc[i], ah, bl);
-      mma_tf32(acc[i], ah, bh);
+      uint32_t bh[2], bm[2];
+      split_bf16x2(b[i].at(q0, 0), b[i].at(q0, 1), bh[0], bm[0]);
+      split_bf16x2(b[i].at(q0, 2), b[i].at(q0, 3), bh[1], bm[1]);
+      mma_bf16(x_acc[i], am, bh);
+      mma_bf16(x_acc[i], ah, bm);
+      mma_bf16(acc[i], ah, bh);
     }
   }
 #pragma unroll
   for (int i = 0; i < NB; ++i)
 #pragma unroll
-    for (int j = 0; j < 4; ++j) acc[i][j] += lo_acc[i][j];
+    for (int j = 0; j < 4; ++j) acc[i][j] += x_acc[i][j];
 }
 
-// the bias gradients: A^T 1 (column 0 of a tile whose B is one column of ones; 1.0 is exact in TF32)
+// the bias gradients: A^T 1 (column 0 of a tile whose B is one column of ones; 1.0 is exact in bf16)
 template <int A_ROWS, typename AFrag>
 __device__ __forceinline__ void wgrad_bias(const AFrag& a_lo, const AFrag& a_hi, int lane, float (&acc)[4]) {
   const int g = lane >> 2;
-  float lo_acc[4];
+  float x_acc[4];
 #pragma unroll
-  for (int j = 0; j < 4; ++j) acc[j] = lo_acc[j] = 0.f;
+  for (int j = 0; j < 4; ++j) acc[j] = x_acc[j] = 0.f;
   uint32_t bh[2];
-  bh[0] = bh[1] = __float_as_uint(g == 0 ? 1.0f : 0.0f);
+  bh[0] = bh[1] = (g == 0) ? 0x3f803f80u : 0u;
 #pragma unroll 2
-  for (int q0 = 0; q0 < NP; q0 += 8) {
-    float af[4];
-    af[0] = (g < A_ROWS) ? a_lo.lo(q0) : 0.f;
-    af[2] = (g < A_ROWS) ? a_lo.hi(q0) : 0.f;
-    af[1] = (A_ROWS > 8) ? a_hi.lo(q0) : 0.f;
-    af[3] = (A_ROWS > 8) ? a_hi.hi(q0) : 0.f;
-    uint32_t ah[4], al[4];
-#pragma unroll
-    for (int i = 0; i < 4; ++i) split_tf32(af[i], ah[i], al[i]);
-    mma_tf32(lo_acc, al, bh);
-    mma_tf32(acc, ah, bh);
+  for (int q0 = 0; q0 < NP; q0 += 16) {
+    uint32_t ah[4], am[4];
+    if (g < A_ROWS) {
+      split_bf16x2(a_lo.at(q0, 0), a_lo.at(q0, 1), ah[0], am[0]);
+      split_bf16x2(a_lo.at(q0, 2), a_lo.at(q0, 3), ah[2], am[2]);
+    } else {
+      ah[0] = am[0] = ah[2] = am[2] = 0u;
+    }
+    if (A_ROWS > 8) {
+      split_bf16x2(a_hi.at(q0, 0), a_hi.at(q0, 1), ah[1], am[1]);
+      split_bf16x2(a_hi.at(q0, 2), a_hi.at(q0, 3), ah[3], am[3]);
+    } else {
+      ah[1] = am[1] = ah[3] = am[3] = 0u;
+    }
+    mma_bf16(x_acc, am, bh);
+    mma_bf16(acc, ah, bh);
   }
 #pragma unroll
-  for (int j = 0; j < 4; ++j) acc[j] += lo_acc[j];
+  for (int j = 0; j < 4; ++j) acc[j] += x_acc[j];
 }
 
 // fragment -> gradient arena: dst[m * ld + n0 + n] for the fragment's (m, n); rows m >= m_valid are dropped.
