@@ -183,6 +183,15 @@ int eslam_render_forward(const eslam_field_t* field_host, const float* arena, co
                          const float* rays_d, const float* z, int n_rays, int n_samples, const int32_t* counters,
                          float* depth, float* rgb, float* sdf, eslam_stream_t s);
 
+/* eslam_render_forward that also keeps what a pose-only backward pass needs of the forward: act4[R][S][4] =
+ * (r, g, b, bit pattern of the sdf decoder's ReLU masks) and actm[R][S] = the rgb decoder's ReLU masks (bit j:
+ * hidden-1 unit j active, bit 16+j: hidden-2 unit j active); sdf is required.  24 bytes per sample instead of a
+ * second gather of 6 KB and two forward MLPs in eslam_pose_backward_act. */
+int eslam_render_forward_act(const eslam_field_t* field_host, const float* arena, const float* rays_o,
+                             const float* rays_d, const float* z, int n_rays, int n_samples,
+                             const int32_t* counters, float* depth, float* rgb, float* sdf, float* act4,
+                             uint32_t* actm, eslam_stream_t s);
+
 /* Backward of the above for arbitrary upstream gradients (autograd through render_batch_ray):
  * g_depth[R], g_rgb[R][3], g_sdf[R][S] (may be NULL) -> grad_arena (+=, planes and decoders incl. beta; may
  * be NULL), g_rays_o/g_rays_d[R][3] (=, both or neither). */
@@ -212,6 +221,17 @@ int eslam_loss_backward(const eslam_field_t* field_host, const float* arena, con
                         const int64_t* pix_idx, int n_per_img, const uint8_t* ray_mask, const int32_t* counters,
                         const int32_t* norm_counters, int max_rays, float* grad_arena, float* pose_grad,
                         double* loss_acc, eslam_stream_t s);
+
+/* The tracker's half of eslam_loss_backward (Tracker.py:192-208: losses over the outlier-masked rays, gradient to
+ * the 7-dof pose only) on the activations eslam_render_forward_act left for the SAME rays and samples: no feature
+ * gather and no forward MLPs, only compositing, the losses, the MLPs' backward-to-input pass and the bilinear
+ * coordinate gradients. */
+int eslam_pose_backward_act(const eslam_field_t* field_host, const float* arena, const eslam_camera_t* cam_host,
+                            const eslam_render_cfg_t* cfg_host, const float* rays_o, const float* rays_d,
+                            const float* z, const float* gt_depth, const double* gt_color, const int32_t* src,
+                            const int64_t* pix_idx, int n_per_img, const uint8_t* ray_mask, const int32_t* counters,
+                            int max_rays, const float* sdf, const float* act4, const uint32_t* actm,
+                            float* pose_grad, double* loss_acc, eslam_stream_t s);
 
 /* torch.optim.Adam single-tensor update (torch/optim/adam.py) over a flat arena with up to 4 lr segments
  * [seg_end[i-1], seg_end[i]) (multiples of 4 floats); zeroes the gradient afterwards (the zero_grad of the

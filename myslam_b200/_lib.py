@@ -77,9 +77,11 @@ PROTOTYPES = {
     "eslam_depth_samples": [_RP, _P, _I, _P, _P, _P, _P, _P, _P, _P, _P],
     "eslam_importance_samples": [_FP, _P, _RP, _P, _P, _P, _P, _I, _P, _P, _P, _P, _P],
     "eslam_render_forward": [_FP, _P, _P, _P, _P, _I, _I, _P, _P, _P, _P, _P],
+    "eslam_render_forward_act": [_FP, _P, _P, _P, _P, _I, _I, _P, _P, _P, _P, _P, _P, _P],
     "eslam_render_backward": [_FP, _P, _P, _P, _P, _I, _I, _P, _P, _P, _P, _P, _P, _P],
     "eslam_track_mask": [_P, _P, _P, _I, _P, _P, _P, _P],
     "eslam_loss_backward": [_FP, _P, _CP, _RP, _P, _P, _P, _P, _P, _P, _P, _I, _P, _P, _P, _I, _P, _P, _P, _P],
+    "eslam_pose_backward_act": [_FP, _P, _CP, _RP, _P, _P, _P, _P, _P, _P, _P, _I, _P, _P, _I, _P, _P, _P, _P, _P, _P],
     "eslam_adam_step": [_P, _P, _P, _P, _L, C.POINTER(C.c_int64), C.POINTER(C.c_double), _I, _I, _D, _D, _D, _P],
     "eslam_pose_adam_step": [_P, _P, _P, _P, _I, _I, _D, _D, _I, _D, _D, _D, _P, _I, _P],
     "eslam_finalize_loss": [_RP, _P, _I, _P, _P, _P],

@@ -368,10 +368,11 @@ int eslam_importance_samples(const eslam_field_t* f, const float* arena, const e
   return 0;
 }
 
-int eslam_render_forward(const eslam_field_t* f, const float* arena, const float* rays_o, const float* rays_d,
-                         const float* z, int n_rays, int n_samples, const int32_t* counters, float* depth, float* rgb,
-                         float* sdf, eslam_stream_t s) {
+static int render_forward_impl(const eslam_field_t* f, const float* arena, const float* rays_o, const float* rays_d,
+                               const float* z, int n_rays, int n_samples, const int32_t* counters, float* depth,
+                               float* rgb, float* sdf, float* act4, uint32_t* actm, eslam_stream_t s) {
   REQUIRE(f && arena && rays_o && rays_d && z && depth && rgb && n_rays >= 0, "eslam_render_forward");
+  REQUIRE((act4 == nullptr) == (actm == nullptr) && (!act4 || sdf), "eslam_render_forward(activations)");
   REQUIRE(n_samples >= 1 && n_samples <= ESLAM_MAX_SAMPLES, "eslam_render_forward(n_samples)");
   if (n_rays == 0) return 0;
   RenderFwdArgs a;
@@ -387,10 +388,26 @@ int eslam_render_forward(const eslam_field_t* f, const float* arena, const float
   a.depth = depth;
   a.rgb = rgb;
   a.sdf = sdf;
+  a.act4 = reinterpret_cast<float4*>(act4);
+  a.actm = actm;
   const int rpb = NP / n_samples;
   k_render_fwd<<<(n_rays + rpb - 1) / rpb, NP, 0, S_(s)>>>(a);
   CHECK_LAUNCH("eslam_render_forward");
   return 0;
+}
+
+int eslam_render_forward(const eslam_field_t* f, const float* arena, const float* rays_o, const float* rays_d,
+                         const float* z, int n_rays, int n_samples, const int32_t* counters, float* depth, float* rgb,
+                         float* sdf, eslam_stream_t s) {
+  return render_forward_impl(f, arena, rays_o, rays_d, z, n_rays, n_samples, counters, depth, rgb, sdf, nullptr, nullptr,
+                             s);
+}
+
+int eslam_render_forward_act(const eslam_field_t* f, const float* arena, const float* rays_o, const float* rays_d,
+                             const float* z, int n_rays, int n_samples, const int32_t* counters, float* depth,
+                             float* rgb, float* sdf, float* act4, uint32_t* actm, eslam_stream_t s) {
+  REQUIRE(act4 && actm && sdf, "eslam_render_forward_act");
+  return render_forward_impl(f, arena, rays_o, rays_d, z, n_rays, n_samples, counters, depth, rgb, sdf, act4, actm, s);
 }
 
 }  // extern "C"
@@ -487,12 +504,13 @@ int eslam_track_mask(const float* gt_depth, const float* depth, const uint8_t* b
   return 0;
 }
 
-int eslam_loss_backward(const eslam_field_t* f, const float* arena, const eslam_camera_t* cam,
-                        const eslam_render_cfg_t* cfg, const float* rays_o, const float* rays_d, const float* z,
-                        const float* gt_depth, const double* gt_color, const int32_t* src, const int64_t* pix_idx,
-                        int n_per_img, const uint8_t* ray_mask, const int32_t* counters,
-                        const int32_t* norm_counters, int max_rays, float* grad_arena, float* pose_grad,
-                        double* loss_acc, eslam_stream_t s) {
+static int loss_backward_impl(const eslam_field_t* f, const float* arena, const eslam_camera_t* cam,
+                              const eslam_render_cfg_t* cfg, const float* rays_o, const float* rays_d, const float* z,
+                              const float* gt_depth, const double* gt_color, const int32_t* src,
+                              const int64_t* pix_idx, int n_per_img, const uint8_t* ray_mask, const int32_t* counters,
+                              const int32_t* norm_counters, int max_rays, float* grad_arena, float* pose_grad,
+                              double* loss_acc, const float* sdf, const float* act4, const uint32_t* actm,
+                              eslam_stream_t s) {
   REQUIRE(f && arena && cam && cfg && rays_o && rays_d && z && gt_depth && gt_color && counters && max_rays >= 0,
           "eslam_loss_backward");
   REQUIRE(!pose_grad || (src && pix_idx && n_per_img > 0), "eslam_loss_backward(pose)");
@@ -536,6 +554,9 @@ int eslam_loss_backward(const eslam_field_t* f, const float* arena, const eslam_
   a.loss_acc = loss_acc;
   a.grad_arena = grad_arena;
   a.pose_grad = pose_grad;
+  a.sdf_in = sdf;
+  a.act4 = reinterpret_cast<const float4*>(act4);
+  a.actm = actm;
   if (grad_arena && pose_grad)
     rc = launch_bwd<1, true, true>(a, max_rays, S_(s));
   else if (grad_arena)
@@ -546,6 +567,28 @@ int eslam_loss_backward(const eslam_field_t* f, const float* arena, const eslam_
     return fail(ESLAM_EINVAL, "eslam_loss_backward(no gradient requested)");
   if (rc) return fail(rc, "eslam_loss_backward");
   return 0;
+}
+
+int eslam_loss_backward(const eslam_field_t* f, const float* arena, const eslam_camera_t* cam,
+                        const eslam_render_cfg_t* cfg, const float* rays_o, const float* rays_d, const float* z,
+                        const float* gt_depth, const double* gt_color, const int32_t* src, const int64_t* pix_idx,
+                        int n_per_img, const uint8_t* ray_mask, const int32_t* counters,
+                        const int32_t* norm_counters, int max_rays, float* grad_arena, float* pose_grad,
+                        double* loss_acc, eslam_stream_t s) {
+  return loss_backward_impl(f, arena, cam, cfg, rays_o, rays_d, z, gt_depth, gt_color, src, pix_idx, n_per_img, ray_mask,
+                            counters, norm_counters, max_rays, grad_arena, pose_grad, loss_acc, nullptr, nullptr,
+                            nullptr, s);
+}
+
+int eslam_pose_backward_act(const eslam_field_t* f, const float* arena, const eslam_camera_t* cam,
+                            const eslam_render_cfg_t* cfg, const float* rays_o, const float* rays_d, const float* z,
+                            const float* gt_depth, const double* gt_color, const int32_t* src, const int64_t* pix_idx,
+                            int n_per_img, const uint8_t* ray_mask, const int32_t* counters, int max_rays,
+                            const float* sdf, const float* act4, const uint32_t* actm, float* pose_grad,
+                            double* loss_acc, eslam_stream_t s) {
+  REQUIRE(sdf && act4 && actm && pose_grad, "eslam_pose_backward_act");
+  return loss_backward_impl(f, arena, cam, cfg, rays_o, rays_d, z, gt_depth, gt_color, src, pix_idx, n_per_img, ray_mask,
+                            counters, nullptr, max_rays, nullptr, pose_grad, loss_acc, sdf, act4, actm, s);
 }
 
 static int fill_adam(AdamArgs& a, int64_t n, const int64_t* seg_end, const double* seg_lr, int n_seg, int step,

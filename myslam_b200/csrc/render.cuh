@@ -214,7 +214,18 @@ struct RenderFwdArgs {
   int n_rays, S;
   const int* counters;
   float *depth, *rgb, *sdf;
+  float4* act4;    // optional [R][S]: (r, g, b, bits of the sdf decoder's ReLU masks) per sample, for the cached backward
+  unsigned* actm;  // optional [R][S]: the rgb decoder's ReLU masks (bit j: h1[j] > 0, bit 16 + j: h2[j] > 0)
 };
+
+// bit j: h1[j] > 0, bit 16 + j: h2[j] > 0 -- all the backward pass needs of the hidden activations when no weight
+// gradients are wanted
+__device__ __forceinline__ unsigned relu_mask(const float (&h1)[16], const float (&h2)[16]) {
+  unsigned m = 0u;
+#pragma unroll
+  for (int j = 0; j < 16; ++j) m |= (h1[j] > 0.f ? 1u << j : 0u) | (h2[j] > 0.f ? 1u << (16 + j) : 0u);
+  return m;
+}
 
 __device__ __forceinline__ void sdf_to_alpha(float sdf, float beta, float& u, float& e, float& alpha) {
   u = sigmoidf_(-sdf * beta);  // Renderer.py:149-153
@@ -252,12 +263,15 @@ __global__ void __launch_bounds__(NP) k_render_fwd(const __grid_constant__ Rende
   float h1[16], h2[16], os[1], oc[3];
   mlp_forward<S_W1, S_B1, S_W2, S_B2, S_W3, S_B3, 1>(sm.F, q, h1, h2, os);
   const float sdf = tanhf(os[0]);
+  unsigned mask_s = 0u, mask_c = 0u;
+  if (a.act4) mask_s = relu_mask(h1, h2);
   __syncthreads();
   write_axis_setups<2>(a.fk, 2, pn, sm.ax_i, sm.ax_f, q);
   __syncthreads();
   gather_tile<0>(a.fk, 1, a.arena4, sm.ax_i, sm.ax_f, sm.F, n_valid);
   __syncthreads();
   mlp_forward<C_W1, C_B1, C_W2, C_B2, C_W3, C_B3, 3>(sm.F, q, h1, h2, oc);
+  if (a.act4) mask_c = relu_mask(h1, h2);
   const float beta = c_dec[P_BETA];
   float u, e, alpha;
   sdf_to_alpha(sdf, beta, u, e, alpha);
@@ -265,6 +279,10 @@ __global__ void __launch_bounds__(NP) k_render_fwd(const __grid_constant__ Rende
   sm.z[q] = zk;
 #pragma unroll
   for (int c = 0; c < 3; ++c) sm.c[c][q] = sigmoidf_(oc[c]);
+  if (a.act4 && valid) {
+    a.act4[(long long)ray * S + k] = make_float4(sm.c[0][q], sm.c[1][q], sm.c[2][q], __uint_as_float(mask_s));
+    a.actm[(long long)ray * S + k] = mask_c;
+  }
   __syncthreads();
   float T = 1.0f;
   for (int j = 0; j < k; ++j) T *= sm.one[rl * S + j];
@@ -307,6 +325,10 @@ struct BwdArgs {
   float fx, fy, cx, cy;
   int W0, H0, Wc;
   double* loss_acc;
+  // cached forward (tracking): written by k_render_fwd for the same rays / samples; replaces gather + forward MLPs
+  const float* sdf_in;
+  const float4* act4;
+  const unsigned* actm;
   // outputs
   float* grad_arena;
   float *g_rays_o, *g_rays_d;
@@ -709,8 +731,50 @@ __global__ void __launch_bounds__(NT_BWD, 2) k_render_bwd(const __grid_constant_
   load_decoder_weights(sm.W, reinterpret_cast<const float*>(a.arena4) + a.fk.dec_off, tid, NT_BWD);
   __syncthreads();
   PHASE_MARK(0);
-  // ---- P2: gather this half's decoder features
+  // ---- P2/P3 from the cache: the tracker has just run k_render_fwd on these rays (it needs the rendered depth
+  //      for its outlier mask before any gradient), which left sdf, rgb and the ReLU masks of every sample.
+  //      Without weight gradients that is all the backward pass needs, so the gather and both forward MLPs go.
+  const bool cached = !GF && FUSED && a.act4 != nullptr;
   float4* Fh = half ? sm.F1 : sm.F0;
+  float h1[16], h2[16], out[3] = {0.f, 0.f, 0.f};
+  float sdf = 0.f, u = 0.f, e = 0.f, alpha = 0.f, one = 1.f, rgb[3] = {0.f, 0.f, 0.f};
+  const float* Wh = sm.W + half * DW_STRIDE;
+  float beta;
+  if (cached) {
+    PHASE_MARK(1);
+    decoder_weights_wait();
+    __syncthreads();
+    PHASE_MARK(2);
+    beta = sm.W[DW_BETA];
+    unsigned m = 0u;
+    if (valid) {
+      const float4 c4 = a.act4[(long long)ray * S + k];
+      if (half == 0) {
+        m = __float_as_uint(c4.w);
+        sdf = a.sdf_in[(long long)ray * S + k];
+      } else {
+        m = a.actm[(long long)ray * S + k];
+        rgb[0] = c4.x;
+        rgb[1] = c4.y;
+        rgb[2] = c4.z;
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+      h1[j] = (m >> j) & 1u ? 1.f : 0.f;
+      h2[j] = (m >> (16 + j)) & 1u ? 1.f : 0.f;
+    }
+    if (half == 0) {
+      sdf_to_alpha(sdf, beta, u, e, alpha);
+      one = __fadd_rn(__fsub_rn(1.0f, alpha), 1e-10f);
+      sm.one[q] = one;
+      sm.z[q] = zk;
+    } else {
+#pragma unroll
+      for (int c = 0; c < 3; ++c) sm.c[c][q] = rgb[c];
+    }
+  } else {
+  // ---- P2: gather this half's decoder features
   if (half == 0)
     gather_tile<0>(a.fk, 0, a.arena4, sm.ax_i, sm.ax_f, sm.F0, n_valid, q);
   else
@@ -720,10 +784,7 @@ __global__ void __launch_bounds__(NT_BWD, 2) k_render_bwd(const __grid_constant_
   __syncthreads();
   PHASE_MARK(2);
   // ---- P3: MLP forward of this half's decoder
-  float h1[16], h2[16], out[3] = {0.f, 0.f, 0.f};
-  float sdf = 0.f, u = 0.f, e = 0.f, alpha = 0.f, one = 1.f, rgb[3] = {0.f, 0.f, 0.f};
-  const float beta = sm.W[DW_BETA];
-  const float* Wh = sm.W + half * DW_STRIDE;
+  beta = sm.W[DW_BETA];
   if (a.dbg & 4) {  // profiling: skip the MLP arithmetic (results are meaningless)
 #pragma unroll
     for (int j = 0; j < 16; ++j) h1[j] = h2[j] = sm.F0[q * 16].x * 0.f + (float)j;
@@ -755,6 +816,7 @@ __global__ void __launch_bounds__(NT_BWD, 2) k_render_bwd(const __grid_constant_
         sm.c[c][q] = rgb[c];
       }
     }
+  }
   }
   PHASE_MARK(3);
   __syncthreads();

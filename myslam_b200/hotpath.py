@@ -51,6 +51,8 @@ class Workspace:
         self.depth = torch.empty(N, dtype=f32, device=dev)
         self.rgb = torch.empty(N, 3, dtype=f32, device=dev)
         self.sdf = torch.empty(N, S, dtype=f32, device=dev)
+        self.act4 = torch.empty(N, S, 4, dtype=f32, device=dev)   # forward activations kept for the tracker's
+        self.actm = torch.empty(N, S, dtype=i32, device=dev)      # pose-only backward (eslam_render_forward_act)
         self.ray_mask = torch.empty(N, dtype=torch.uint8, device=dev)
         self.scratch = torch.empty(N + 1, dtype=f32, device=dev)
         self.loss_acc = torch.zeros(N_LOSS, dtype=torch.float64, device=dev)
@@ -149,13 +151,17 @@ def tracking_iteration(ws: Workspace, store: FieldStore, sc: StepCfg, pose7: tor
         u = draws.rand(n_pixels, S)
     _sample(ws, store, sc, idx, 1, n_pixels, None, pose7, 0, gt_depth, gt_color, u, 1)
     N = n_pixels
-    call("eslam_render_forward", store.ref(), ptr(store.arena), ptr(ws.rays_o), ptr(ws.rays_d), ptr(ws.z), N, S,
-         ptr(ws.counters), ptr(ws.depth), ptr(ws.rgb), ptr(ws.sdf), stream())
+    # the forward pass (needed first: the outlier mask is a median over the rendered depth, Tracker.py:192-195)
+    # keeps sdf, rgb and the ReLU masks of every sample, so the backward pass neither gathers features nor
+    # re-runs the forward MLPs
+    call("eslam_render_forward_act", store.ref(), ptr(store.arena), ptr(ws.rays_o), ptr(ws.rays_d), ptr(ws.z), N, S,
+         ptr(ws.counters), ptr(ws.depth), ptr(ws.rgb), ptr(ws.sdf), ptr(ws.act4), ptr(ws.actm), stream())
     call("eslam_track_mask", ptr(ws.gt_depth), ptr(ws.depth), ptr(ws.band), N, ptr(ws.counters), ptr(ws.ray_mask),
          ptr(ws.scratch), stream())
-    call("eslam_loss_backward", store.ref(), ptr(store.arena), C.byref(cam), C.byref(rc), ptr(ws.rays_o),
+    call("eslam_pose_backward_act", store.ref(), ptr(store.arena), C.byref(cam), C.byref(rc), ptr(ws.rays_o),
          ptr(ws.rays_d), ptr(ws.z), ptr(ws.gt_depth), ptr(ws.gt_color), ptr(ws.src), ptr(idx), n_pixels,
-         ptr(ws.ray_mask), ptr(ws.counters), None, N, None, ptr(ws.pose_grad), ptr(ws.loss_acc), stream())
+         ptr(ws.ray_mask), ptr(ws.counters), N, ptr(ws.sdf), ptr(ws.act4), ptr(ws.actm), ptr(ws.pose_grad),
+         ptr(ws.loss_acc), stream())
     call("eslam_finalize_loss", C.byref(rc), ptr(ws.counters), 1, ptr(ws.loss_acc), ptr(ws.loss_out), stream())
     if apply_adam is None:
         call("eslam_pose_adam_step", ptr(pose7), ptr(ws.pose_grad), None, None, 1, 0, 0.0, 0.0, 1, 0.5, 0.999, 1e-8,

@@ -382,3 +382,36 @@ def test_grid_sdf_golden():
     pts = O.grid_points(O.grid_axes(d["mc_bound"], float(d["resolution"]))).to(DEV)
     raw = eval_points(pts, planes, dec)
     assert rel_err(raw[:, 3], d["sdf"]) < TOL_VAL and rel_err(raw[:, :3], d["rgb"]) < TOL_VAL
+
+
+def test_cached_pose_backward_equals_recomputing_backward():
+    """The tracker's backward pass on the activations the forward kernel kept (eslam_pose_backward_act: no gather,
+    no forward MLPs) gives the pose gradient and loss of the recomputing kernel (eslam_loss_backward) on the same
+    rays, samples and outlier mask."""
+    import ctypes as C
+    from myslam_b200 import ReplayDraws
+    from myslam_b200._lib import call, ptr, stream
+    from myslam_b200.hotpath import tracking_iteration
+    from myslam_b200.tracker import _tracker_state, _tracker_store
+
+    fld, d = golden_field(), load_npz("tracking.npz")
+    trk = make_tracker(fld, d)
+    draws = recorded_draws(d)
+    n_pix = int(d["n_pix"])
+    st = _tracker_state(trk, n_pix)
+    store = _tracker_store(trk, st)
+    pose = torch.from_numpy(d["pose0"]).to(DEV).contiguous()
+    gc, gd = torch.from_numpy(d["gt_color"]).to(DEV), torch.from_numpy(d["gt_depth"]).to(DEV)
+    tracking_iteration(st["ws"], store, st["sc"], pose, gc, gd, n_pix, draws=ReplayDraws(draws[:2], DEV), strict_rng=True)
+    ws, sc = st["ws"], st["sc"]
+    g_cached, loss_cached = ws.grad7[0].clone(), ws.loss_acc[5].item()
+    idx = draws[0].to(DEV)
+    ws.loss_acc.zero_()
+    call("eslam_loss_backward", store.ref(), ptr(store.arena), C.byref(sc.cam), C.byref(sc.render), ptr(ws.rays_o),
+         ptr(ws.rays_d), ptr(ws.z), ptr(ws.gt_depth), ptr(ws.gt_color), ptr(ws.src), ptr(idx), n_pix, ptr(ws.ray_mask),
+         ptr(ws.counters), None, n_pix, None, ptr(ws.pose_grad), ptr(ws.loss_acc), stream())
+    call("eslam_finalize_loss", C.byref(sc.render), ptr(ws.counters), 1, ptr(ws.loss_acc), ptr(ws.loss_out), stream())
+    call("eslam_pose_adam_step", ptr(pose), ptr(ws.pose_grad), None, None, 1, 0, 0.0, 0.0, 1, 0.5, 0.999, 1e-8,
+         ptr(ws.grad7), 0, stream())
+    assert rel_err(g_cached, ws.grad7[0]) < 1e-5
+    assert abs(loss_cached - ws.loss_acc[5].item()) <= 1e-6 * abs(loss_cached)
