@@ -82,6 +82,11 @@ typedef struct {
  * [0] R rays kept  [1] R0 depth-less rays among them  [2] rays in the loss mask
  * [3] front samples [4] center samples [5] tail samples (over masked rays)  [6],[7] reserved */
 #define ESLAM_N_COUNTERS 8
+/* The counters BUFFER handed to eslam_sample_rays* / eslam_depth_samples must hold ESLAM_COUNTER_WORDS int32
+ * (8-byte aligned): the 8 counters, then one 64-bit word per CTA of the compaction kernel (its totals, published
+ * for the CTAs after it).  Everything else only reads the first ESLAM_N_COUNTERS. */
+#define ESLAM_MAX_COMPACT_BLOCKS 4096 /* x 256 slots: up to 1 048 576 rays per call */
+#define ESLAM_COUNTER_WORDS (ESLAM_N_COUNTERS + 2 * ESLAM_MAX_COMPACT_BLOCKS)
 /* Device-side loss accumulators (double[8]): fs, center, tail, depth, colour sums; [5] = loss */
 #define ESLAM_N_LOSS 8
 

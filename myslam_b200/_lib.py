@@ -17,6 +17,8 @@ N_PLANES = 12
 DEC_FLOATS = 2700
 DEC_BETA = 2696
 N_COUNTERS = 8
+MAX_COMPACT_BLOCKS = 4096
+COUNTER_WORDS = N_COUNTERS + 2 * MAX_COMPACT_BLOCKS  # allocation size of a counters buffer (include/eslam_b200.h)
 N_LOSS = 8
 MAX_SAMPLES = 64
 ABI_VERSION = 1

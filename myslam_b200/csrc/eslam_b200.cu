@@ -247,9 +247,12 @@ static int sample_rays_impl(const eslam_field_t* f, const eslam_camera_t* cam, c
   a.band = band;
   a.counters = counters;
   a.c2w_out = c2w_out;
-  cudaError_t e = cudaMemsetAsync(counters, 0, sizeof(int32_t) * ESLAM_N_COUNTERS, S_(s));
-  if (e != cudaSuccess) return fail((int)e, "eslam_sample_rays(memset)");
   const int N = n_img * n_per_img;
+  const int n_blocks = (N + SB - 1) / SB;
+  if (n_blocks > ESLAM_MAX_COMPACT_BLOCKS) return fail(ESLAM_EUNSUPPORTED, "eslam_sample_rays(too many rays per call)");
+  a.agg = reinterpret_cast<unsigned long long*>(counters + ESLAM_N_COUNTERS);
+  cudaError_t e = cudaMemsetAsync(counters, 0, sizeof(int32_t) * (ESLAM_N_COUNTERS + 2 * n_blocks), S_(s));
+  if (e != cudaSuccess) return fail((int)e, "eslam_sample_rays(memset)");
   k_sample_rays<<<(N + SB - 1) / SB, SB, 0, S_(s)>>>(a);
   CHECK_LAUNCH("eslam_sample_rays(select)");
   RaySampleArgs b;
@@ -305,7 +308,9 @@ int eslam_depth_samples(const eslam_render_cfg_t* cfg, const float* gt_depth, in
           "eslam_depth_samples");
   int rc = check_samples(cfg->n_stratified, cfg->n_importance);
   if (rc) return fail(rc, "eslam_depth_samples(samples)");
-  cudaError_t e = cudaMemsetAsync(counters, 0, sizeof(int32_t) * ESLAM_N_COUNTERS, S_(s));
+  const int n_blocks = (n_rays + SB - 1) / SB;
+  if (n_blocks > ESLAM_MAX_COMPACT_BLOCKS) return fail(ESLAM_EUNSUPPORTED, "eslam_depth_samples(too many rays per call)");
+  cudaError_t e = cudaMemsetAsync(counters, 0, sizeof(int32_t) * (ESLAM_N_COUNTERS + 2 * n_blocks), S_(s));
   if (e != cudaSuccess) return fail((int)e, "eslam_depth_samples(memset)");
   if (n_rays == 0) return 0;
   const CfgK k = make_cfg(cfg);
@@ -315,6 +320,7 @@ int eslam_depth_samples(const eslam_render_cfg_t* cfg, const float* gt_depth, in
   o.zord = zord;
   o.dl_list = dl_list;
   o.counters = counters;
+  o.agg = reinterpret_cast<unsigned long long*>(counters + ESLAM_N_COUNTERS);
   k_depth_ordinals<<<(n_rays + SB - 1) / SB, SB, 0, S_(s)>>>(o);
   CHECK_LAUNCH("eslam_depth_samples(ordinals)");
   RaySampleArgs b;

@@ -37,6 +37,7 @@ struct SampleArgs {
   int* zord;
   unsigned char* band;
   int* counters;
+  unsigned long long* agg;  // per-CTA totals for the look-back (counters + ESLAM_N_COUNTERS, zeroed per launch)
   float* c2w_out;
 };
 
@@ -150,6 +151,42 @@ __device__ __forceinline__ void block_scan2(int f0, int f1, int& ex0, int& ex1, 
   __syncthreads();
 }
 
+// Ordered compaction across CTAs without re-evaluating the preceding slots: CTA b publishes its two totals in
+// agg[b] (one 64-bit word, bit 0 = ready; zeroed by the host entry point before the launch) and sums the words of
+// the CTAs before it, spinning on those not yet published.  CTAs are dispatched in index order and never wait for
+// a later one, so the chain cannot deadlock even when the grid exceeds what is resident.
+__device__ __forceinline__ void lookback2(unsigned long long* agg, int tot0, int tot1, int* sh /*[2*SB/32+2]*/,
+                                          int& base0, int& base1) {
+  const int b = blockIdx.x;
+  if (threadIdx.x == 0) {
+    const unsigned long long w = ((unsigned long long)(unsigned)tot0 << 32) | ((unsigned long long)(unsigned)tot1 << 1) | 1ull;
+    __threadfence();
+    atomicExch(agg + b, w);
+  }
+  int p0 = 0, p1 = 0;
+  for (int j = threadIdx.x; j < b; j += SB) {
+    unsigned long long w;
+    do {
+      w = *reinterpret_cast<volatile unsigned long long*>(agg + j);
+    } while (!(w & 1ull));
+    p0 += (int)(w >> 32);
+    p1 += (int)((w & 0xffffffffull) >> 1);
+  }
+  p0 = (int)warp_sum((float)p0);  // counts < 2^24: exact in fp32
+  p1 = (int)warp_sum((float)p1);
+  if ((threadIdx.x & 31) == 0) {
+    sh[threadIdx.x >> 5] = p0;
+    sh[SB / 32 + (threadIdx.x >> 5)] = p1;
+  }
+  __syncthreads();
+  base0 = base1 = 0;
+  for (int w2 = 0; w2 < SB / 32; ++w2) {
+    base0 += sh[w2];
+    base1 += sh[SB / 32 + w2];
+  }
+  __syncthreads();
+}
+
 // Depth-guided samples of one ray with depth>0 (Renderer.py:94-106 + perturbation :46-61), one WARP per ray:
 // lane l owns elements l and l+32 of the concatenated [free(n_strat) | surface(n_imp)] list, finds their
 // positions in the sorted order by counting (both lists are ascending, so torch.sort of the concatenation is a
@@ -220,48 +257,23 @@ __device__ __forceinline__ void depth_guided_z_warp(float d, int n_strat, int n_
 
 __global__ void __launch_bounds__(SB) k_sample_rays(const __grid_constant__ SampleArgs a) {
   __shared__ int sh[2 * SB / 32 + 2];
-  __shared__ int s_base[2];
   const int N = a.n_img * a.n_per_img;
   const int start = blockIdx.x * SB;
   const int slot = start + threadIdx.x;
-  // kept / depth-less counts of all preceding slots (recomputed, cheap; keeps the compaction ordered
-  // without a second launch or a look-back chain)
-  int pk = 0, pd = 0;
-#pragma unroll 4
-  for (int j = threadIdx.x; j < start; j += SB) {
-    const RayEval e = eval_ray(a, j);
-    pk += e.keep;
-    pd += e.keep && !(e.depth > 0.f);
-  }
-  pk = (int)warp_sum((float)pk);  // counts < 2^24: exact in fp32
-  pd = (int)warp_sum((float)pd);
-  if ((threadIdx.x & 31) == 0) {
-    sh[threadIdx.x >> 5] = pk;
-    sh[SB / 32 + (threadIdx.x >> 5)] = pd;
-  }
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    int t0 = 0, t1 = 0;
-    for (int w2 = 0; w2 < SB / 32; ++w2) {
-      t0 += sh[w2];
-      t1 += sh[SB / 32 + w2];
-    }
-    s_base[0] = t0;
-    s_base[1] = t1;
-  }
-  __syncthreads();
   RayEval e;
   e.keep = false;
   e.depth = 0.f;
   if (slot < N) e = eval_ray(a, slot);
   const int fk_ = e.keep ? 1 : 0;
   const int fd_ = (e.keep && !(e.depth > 0.f)) ? 1 : 0;
-  int ex0, ex1, tot0, tot1;
+  int ex0, ex1, tot0, tot1, base0, base1;
   block_scan2(fk_, fd_, ex0, ex1, tot0, tot1, sh);
-  const int S = a.n_strat + a.n_imp;
+  // kept / depth-less counts of all preceding slots: the order-preserving compaction of Tracker.py:184-187 /
+  // Mapper.py:329-332 (boolean indexing) across CTAs
+  lookback2(a.agg, tot0, tot1, sh, base0, base1);
   if (e.keep) {
-    const int r = s_base[0] + ex0;
-    const int r0 = s_base[1] + ex1;  // ordinal among depth-less rays
+    const int r = base0 + ex0;
+    const int r0 = base1 + ex1;  // ordinal among depth-less rays
     const int frame = slot / a.n_per_img;
     const long long pix = a.pix_idx[slot];
     const int pr = (int)(pix / a.Wc), pc = (int)(pix - (long long)pr * a.Wc);
@@ -375,31 +387,21 @@ struct DepthOrdArgs {
   int* zord;
   int* dl_list;
   int* counters;
+  unsigned long long* agg;
 };
 
 __global__ void __launch_bounds__(SB) k_depth_ordinals(const __grid_constant__ DepthOrdArgs a) {
   __shared__ int sh[2 * SB / 32 + 2];
-  __shared__ int s_base;
   const int start = blockIdx.x * SB;
   const int r = start + threadIdx.x;
-  int pd = 0;
-  for (int j = threadIdx.x; j < start; j += SB) pd += !(a.gt_depth[j] > 0.f);
-  pd = (int)warp_sum((float)pd);
-  if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = pd;
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    int t0 = 0;
-    for (int w2 = 0; w2 < SB / 32; ++w2) t0 += sh[w2];
-    s_base = t0;
-  }
-  __syncthreads();
   const bool in = r < a.n_rays;
   const float d = in ? a.gt_depth[r] : 1.f;
   const int fd_ = (in && !(d > 0.f)) ? 1 : 0;
-  int ex0, ex1, tot0, tot1;
+  int ex0, ex1, tot0, tot1, base0, base1;
   block_scan2(fd_, 0, ex0, ex1, tot0, tot1, sh);
+  lookback2(a.agg, tot0, tot1, sh, base0, base1);
   if (in) {
-    const int r0 = s_base + ex0;
+    const int r0 = base0 + ex0;
     if (d > 0.f) {
       a.zord[r] = r - r0;
     } else {

@@ -16,7 +16,7 @@ from typing import Optional
 
 import torch
 
-from ._lib import N_COUNTERS, N_LOSS, Camera, RenderCfg, call, ptr, stream
+from ._lib import COUNTER_WORDS, N_COUNTERS, N_LOSS, Camera, RenderCfg, call, ptr, stream
 from .field import FieldStore
 from .renderer import TorchDraws, linspace_table, make_cfg
 
@@ -47,7 +47,8 @@ class Workspace:
         self.dl_list = torch.empty(N, dtype=i32, device=dev)
         self.zord = torch.empty(N, dtype=i32, device=dev)
         self.band = torch.empty(N, 4, dtype=torch.uint8, device=dev)
-        self.counters = torch.zeros(N_COUNTERS, dtype=i32, device=dev)
+        self._counter_buf = torch.zeros(COUNTER_WORDS, dtype=i32, device=dev)  # counters + per-CTA look-back words
+        self.counters = self._counter_buf[:N_COUNTERS]
         self.depth = torch.empty(N, dtype=f32, device=dev)
         self.rgb = torch.empty(N, 3, dtype=f32, device=dev)
         self.sdf = torch.empty(N, S, dtype=f32, device=dev)

@@ -11,7 +11,7 @@ from typing import Optional
 import torch
 
 from . import _lib
-from ._lib import N_COUNTERS, RenderCfg, call, ptr, stream
+from ._lib import COUNTER_WORDS, MAX_COMPACT_BLOCKS, N_COUNTERS, RenderCfg, call, ptr, stream
 from .decoders import decoder_tensors, split_arena_grads, synced_store
 from .field import flatten_planes
 
@@ -155,7 +155,7 @@ class Renderer(object):
         z = torch.empty(R, S, dtype=torch.float32, device=dev)
         dl = torch.empty(max(R, 1), dtype=torch.int32, device=dev)
         zord = torch.empty(max(R, 1), dtype=torch.int32, device=dev)
-        cnt = torch.empty(N_COUNTERS, dtype=torch.int32, device=dev)
+        cnt = torch.empty(COUNTER_WORDS, dtype=torch.int32, device=dev)
         u = draws.rand(r1, S) if self.perturb else None
         t_uni, t_surf = linspace_table(ns, dev), linspace_table(ni, dev)
         call("eslam_depth_samples", C.byref(cfg), ptr(d), R, ptr(u), ptr(t_uni), ptr(t_surf), ptr(z), ptr(dl),
@@ -199,7 +199,7 @@ class Renderer(object):
         with torch.no_grad():
             H, W = self.H, self.W
             strict = getattr(self, "strict_rng", os.environ.get("ESLAM_B200_STRICT_RNG", "0") == "1")
-            chunk = self.ray_batch_size if strict else H * W
+            chunk = self.ray_batch_size if strict else min(H * W, MAX_COMPACT_BLOCKS * 256)
             rays_o, rays_d = get_rays(H, W, self.fx, self.fy, self.cx, self.cy, c2w, device)
             rays_o = rays_o.reshape(-1, 3).contiguous()
             rays_d = rays_d.reshape(-1, 3).contiguous()
