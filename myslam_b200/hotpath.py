@@ -206,14 +206,19 @@ def mapping_iteration(ws: Workspace, store: FieldStore, sc: StepCfg, c2ws, poses
         u = draws.rand(cnt[0] - r0, S) if sc.perturb else None
     else:
         r0 = N
-        u = draws.rand(N, S) if sc.perturb else None
+        u = u_c = u_f = None
+        if sc.perturb and hasattr(draws, "rand_many"):  # one generator launch for the three uniform blocks
+            u, u_c, u_f = draws.rand_many([(N, S), (N, ns), (N, ni)])
+        elif sc.perturb:
+            u = draws.rand(N, S)
     _sample(ws, store, sc, idx, b, pix_per_image, c2w_flat, poses7, 1, gt_depths, gt_colors, u, 0)
     norm, overlapped = None, exchange is not None and hasattr(exchange, "begin_counters")
     if overlapped:  # the counters are final here; their exchange overlaps the importance sampling below
         norm = exchange.begin_counters(ws.counters)
     if r0 > 0:
-        u_c = draws.rand(r0, ns)
-        u_f = draws.rand(r0, ni)
+        if strict_rng or u_c is None:
+            u_c = draws.rand(r0, ns)
+            u_f = draws.rand(r0, ni)
         call("eslam_importance_samples", store.ref(), ptr(store.arena), C.byref(rc), ptr(ws.rays_o), ptr(ws.rays_d),
              ptr(ws.dl_list), ptr(ws.counters), r0, ptr(u_c), ptr(u_f), ptr(linspace_table(ns, dev)), ptr(ws.z),
              stream())

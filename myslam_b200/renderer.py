@@ -29,6 +29,17 @@ class TorchDraws:
     def rand(self, rows, cols):
         return torch.rand(rows, cols, device=self.device)
 
+    def rand_many(self, shapes):
+        """Several uniform blocks from ONE generator call (fewer launches); only used where the reference's draw
+        shapes are not reproduced anyway (strict_rng off)."""
+        sizes = [r * c for r, c in shapes]
+        flat = torch.rand(sum(sizes), device=self.device)
+        out, o = [], 0
+        for (r, c), n in zip(shapes, sizes):
+            out.append(flat[o:o + n].view(r, c))
+            o += n
+        return out
+
 
 class ReplayDraws:
     """Replays recorded draws (tests / parity runs); tensors are moved to the device."""
