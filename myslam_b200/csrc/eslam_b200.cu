@@ -114,10 +114,27 @@ int eslam_plane_export(const float* arena, float* nchw, const eslam_plane_t* pl,
   return 0;
 }
 
+// The constant bank is backed by device memory: a one-CTA kernel stores the packed block through the symbol's
+// address, which keeps the update on the compute engine (a cudaMemcpyToSymbolAsync between two kernels costs a
+// copy-engine hand-off in both directions on every mapping iteration).  Kernels launched afterwards read the new
+// values: the constant caches are invalidated at kernel boundaries.
+__global__ void __launch_bounds__(256) k_bind_decoders(const float* __restrict__ dec, float* __restrict__ dst) {
+  for (int i = threadIdx.x; i < DEC_N; i += 256) dst[i] = dec[i];
+}
+
 int eslam_bind_decoders(const float* dec, eslam_stream_t s) {
   REQUIRE(dec, "eslam_bind_decoders");
-  cudaError_t e = cudaMemcpyToSymbolAsync(c_dec, dec, sizeof(float) * DEC_N, 0, cudaMemcpyDeviceToDevice, S_(s));
-  if (e != cudaSuccess) return fail((int)e, "eslam_bind_decoders");
+  static thread_local float* sym = nullptr;
+  static thread_local int sym_dev = -1;
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (!sym || sym_dev != dev) {
+    cudaError_t e = cudaGetSymbolAddress(reinterpret_cast<void**>(&sym), c_dec);
+    if (e != cudaSuccess) return fail((int)e, "eslam_bind_decoders(symbol)");
+    sym_dev = dev;
+  }
+  k_bind_decoders<<<1, 256, 0, S_(s)>>>(dec, sym);
+  CHECK_LAUNCH("eslam_bind_decoders");
   return 0;
 }
 
