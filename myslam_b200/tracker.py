@@ -12,7 +12,7 @@ import torch
 
 from .common import cam_pose_to_matrix
 from .decoders import synced_store
-from .hotpath import StepCfg, Workspace, make_camera, tracking_iteration
+from .hotpath import FrameTable, StepCfg, Workspace, make_camera, tracking_iteration
 from .renderer import make_cfg
 
 
@@ -66,11 +66,70 @@ def optimize_tracking(self, cam_pose, gt_color, gt_depth, batch_size, optimizer)
     return ws.loss_acc[5].item()
 
 
+def _check_track_frames(gt_color, gt_depth, cam):
+    if gt_depth.dtype != torch.float32 or gt_color.dtype != torch.float64:
+        raise RuntimeError("gt depth must be float32 and gt colour float64, as the reference's datasets produce "
+                           "(src/utils/datasets.py:90-92)")
+    if tuple(gt_depth.shape) != (1, cam.H, cam.W) or tuple(gt_color.shape) != (1, cam.H, cam.W, 3):
+        raise RuntimeError(f"frame shapes {tuple(gt_depth.shape)} / {tuple(gt_color.shape)} do not match the camera")
+    if not (gt_depth.is_cuda and gt_color.is_cuda and gt_depth.is_contiguous() and gt_color.is_contiguous()):
+        raise RuntimeError("frames must be contiguous CUDA tensors; there is no CPU path")
+
+
+class _FrameGraph:
+    """The `iters` iterations of one tracked frame captured once as a CUDA graph (launch-bound inner loop: ~10
+    small launches per iteration, each a ctypes call).  Everything the kernels address is persistent: the workspace,
+    the parameter arena, a pose / loss / trace buffer, and a one-entry frame table whose two pointers are rewritten
+    before every replay.  The random draws are torch's (its CUDA generator is graph safe)."""
+
+    def __init__(self, trk, st, store, gt_color, gt_depth, iters, batch_size, lr_T, lr_R):
+        ws, sc = st["ws"], st["sc"]
+        dev = ws.device
+        self.key = (iters, batch_size, lr_T, lr_R, store.arena.data_ptr(), id(ws))
+        self.pose = torch.zeros(1, 7, dtype=torch.float32, device=dev)
+        self.losses = torch.zeros(iters, dtype=torch.float64, device=dev)
+        self.trace = torch.zeros(iters, 7, dtype=torch.float32, device=dev)
+        self.frames = FrameTable([gt_color[0]], [gt_depth[0]], sc.cam, dev)
+
+        def body():
+            ws.pose_m.zero_()
+            ws.pose_v.zero_()
+            for it in range(iters):
+                self.trace[it].copy_(self.pose[0])
+                tracking_iteration(ws, store, sc, self.pose, self.frames, self.frames, batch_size,
+                                   apply_adam={"step": it + 1, "lr_q": lr_R, "lr_t": lr_T})
+                self.losses[it].copy_(ws.loss_acc[5])
+
+        side = torch.cuda.Stream(device=dev)  # one eager pass first: lazy initialisations must not be captured
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            body()
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize(dev)
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph):
+            body()
+
+    def run(self, init_pose, gt_color, gt_depth):
+        c, d = gt_color[0], gt_depth[0]
+        self.frames.colors, self.frames.depths = [c], [d]  # keep the frame alive while the graph reads it
+        self.frames.table.copy_(torch.tensor([[d.data_ptr()], [c.data_ptr()]], dtype=torch.int64))  # 16 bytes, staged
+        self.pose.copy_(init_pose.detach().float().reshape(1, 7))
+        self.graph.replay()
+        return self.trace, self.losses, self.pose
+
+
+def _use_graph(trk) -> bool:
+    return (os.environ.get("ESLAM_B200_GRAPH", "1") == "1" and getattr(trk, "draws", None) is None
+            and not getattr(trk, "strict_rng", _strict_default()))
+
+
 def track_frame(self, init_pose, gt_color, gt_depth, iters=None, batch_size=None, lr_T=None, lr_R=None):
     """The camera loop of Tracker.run for one frame (Tracker.py:291-309) without leaving the device:
     `iters` iterations with the fused Adam(betas=(0.5,0.999)) on (R,T); returns
-    (candidate_pose[1,7] = pose before the lowest-loss step, losses[iters] float64 tensor).
-    One host sync at the end instead of one per iteration."""
+    (candidate_pose[1,7] = pose before the lowest-loss step, losses[iters] float64 tensor, final pose).
+    One host sync at the end instead of one per iteration; the iterations replay as one CUDA graph
+    (ESLAM_B200_GRAPH=0, injected draws or strict_rng fall back to launching them one by one)."""
     iters = self.num_cam_iters if iters is None else iters
     batch_size = self.tracking_pixels if batch_size is None else batch_size
     lr_T = self.cam_lr_T if lr_T is None else lr_T
@@ -78,6 +137,17 @@ def track_frame(self, init_pose, gt_color, gt_depth, iters=None, batch_size=None
     st = _tracker_state(self, batch_size)
     store = _tracker_store(self, st)
     ws = st["ws"]
+    if _use_graph(self) and st["sc"].perturb:
+        key = (iters, batch_size, lr_T, lr_R, store.arena.data_ptr(), id(ws))
+        fg = st.get("graph")
+        if fg is None or fg.key != key:
+            _check_track_frames(gt_color, gt_depth, st["sc"].cam)
+            fg = _FrameGraph(self, st, store, gt_color, gt_depth, iters, batch_size, lr_T, lr_R)
+            st["graph"] = fg
+        _check_track_frames(gt_color, gt_depth, st["sc"].cam)
+        trace, losses, pose = fg.run(init_pose, gt_color, gt_depth)
+        best = torch.argmin(torch.nan_to_num(losses, nan=float("inf")))
+        return trace[best][None].clone(), losses.clone(), pose.clone()
     pose = init_pose.detach().float().contiguous().clone()
     ws.pose_m.zero_()
     ws.pose_v.zero_()
