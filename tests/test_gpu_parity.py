@@ -420,7 +420,7 @@ def test_cached_pose_backward_equals_recomputing_backward():
 def test_track_frame_graph_replay_matches_eager_loop(monkeypatch):
     """track_frame replays its iterations as one CUDA graph; with the same map, frame and initial pose it must
     behave like the launch-by-launch loop: finite, decreasing-on-average losses of the same size and a best pose
-    within the step size of the eager one (the random pixels differ, so not bit for bit), and a second replay on a
+    within the step size of the eager one (the random pixels differ, so not bit for bit), and a replay on a
     DIFFERENT frame tensor must read the new frame (pointer table rewritten)."""
     fld, d = golden_field(), load_npz("tracking.npz")
     pose0 = torch.from_numpy(d["pose0"]).to(DEV)
@@ -437,9 +437,11 @@ def test_track_frame_graph_replay_matches_eager_loop(monkeypatch):
     l0, l1 = res["0"][1], res["1"][1]
     assert abs(l0.mean().item() - l1.mean().item()) < 0.25 * abs(l0.mean().item())
     assert (res["0"][2] - res["1"][2]).abs().max().item() < 6 * 2e-3 * 2  # both within iters x lr of the start
-    # replay on another frame object (shifted depth): the loss level must change, i.e. the new frame was read
+    # replay on another frame object whose depth is all zero: the tracker keeps depth > 0 rays only (Tracker.py:182), so
+    # if the rewritten pointer table is what the graph reads, no ray survives
     trk = res["1"][3]
-    gd2 = (gd * 1.3).contiguous()
-    _, losses2, _ = trk.track_frame(pose0, gc.clone(), gd2, iters=6, batch_size=int(d["n_pix"]), lr_T=2e-3, lr_R=1e-3)
-    assert torch.isfinite(losses2).all()
-    assert abs(losses2.mean().item() - l1.mean().item()) > 0.05 * abs(l1.mean().item())
+    assert int(trk._b200["ws"].counters[0]) > 0
+    trk.track_frame(pose0, gc.clone(), torch.zeros_like(gd), iters=6, batch_size=int(d["n_pix"]), lr_T=2e-3, lr_R=1e-3)
+    assert int(trk._b200["ws"].counters[0]) == 0
+    _, losses3, _ = trk.track_frame(pose0, gc, gd, iters=6, batch_size=int(d["n_pix"]), lr_T=2e-3, lr_R=1e-3)
+    assert torch.isfinite(losses3).all() and int(trk._b200["ws"].counters[0]) > 0
