@@ -128,6 +128,14 @@ int eslam_grid_sdf(const eslam_field_t* field_host, const float* arena, const fl
                    const float* zs, int nx, int ny, int nz, int64_t start, int64_t count, float* sdf,
                    eslam_stream_t s);
 
+/* eslam_grid_sdf with the mesh bound of Mesher.get_mesh (Mesher.py:206-217: points outside the convex hull of the
+ * observed region get sdf = -1) applied in the same pass: hull_planes[n_planes][4] = (nx, ny, nz, d) per hull
+ * face with the normal pointing outwards, a point is inside iff n.p + d <= 0 for every face (the geometric
+ * predicate `mesh_bound.contains` evaluates for a convex mesh).  Tiles that lie outside entirely are not decoded. */
+int eslam_grid_sdf_hull(const eslam_field_t* field_host, const float* arena, const float* xs, const float* ys,
+                        const float* zs, int nx, int ny, int nz, int64_t start, int64_t count,
+                        const float* hull_planes, int n_planes, float* sdf, eslam_stream_t s);
+
 /* ---- pixel pick, rays, bbox filter, depth-guided samples --------------------------------------- */
 /* get_samples + the bbox pre-filter + the depth>0 half of render_batch_ray's sampling
  * (src/common.py:87-153, src/Tracker.py:175-187, src/Mapper.py:322-332, src/utils/Renderer.py:81-106).
@@ -257,6 +265,14 @@ int eslam_pose_adam_step(float* poses, float* pose_grad, float* exp_avg, float* 
  * loss_acc[0..4] are reset to 0. */
 int eslam_finalize_loss(const eslam_render_cfg_t* cfg_host, const int32_t* counters, int tracker_rule,
                         double* loss_acc, float* loss_out, eslam_stream_t s);
+
+/* The arithmetic of BaseDataset.__getitem__ (src/utils/datasets.py:88-95,108-112) after cv2 has decoded the two
+ * files and when colour and depth have the same size (Replica; no undistortion, no resize): bgr[H][W][3] uint8 ->
+ * color[H-2e][W-2e][3] float64 RGB / 255, depth_u16[H][W] -> depth[H-2e][W-2e] float32 = u16 / png_depth_scale *
+ * scale (both in float32, as numpy and torch evaluate them), e = crop_edge.  Bit-exact with the reference's loader;
+ * the host ships 8 bytes per pixel instead of 28. */
+int eslam_ingest_frame(const uint8_t* bgr, const uint16_t* depth_u16, int H, int W, int crop_edge,
+                       double png_depth_scale, double scale, double* color, float* depth, eslam_stream_t s);
 
 /* matrix_to_cam_pose / cam_pose_to_matrix (common.py:155-181 over pytorch3d 0.7.1 matrix_to_quaternion /
  * quaternion_to_matrix) for n cameras: c2w[n][16] row-major <-> poses[n][7] = (qw,qx,qy,qz,tx,ty,tz), evaluated in

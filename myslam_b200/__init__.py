@@ -8,7 +8,8 @@ from .renderer import Renderer, ReplayDraws, TorchDraws  # noqa: F401
 from .field import FieldStore  # noqa: F401
 from .tracker import TrackerStep, optimize_tracking, track_frame  # noqa: F401
 from .mapper import MapperStep, map_window, optimize_mapping  # noqa: F401
-from .mesher import eval_points, grid_axes, query_grid_sdf  # noqa: F401
+from .mesher import eval_points, grid_axes, hull_planes, query_grid_sdf  # noqa: F401
+from .ingest import ingest_frame  # noqa: F401
 from .install import install  # noqa: F401
 
 __version__ = "0.1.0"

@@ -72,6 +72,7 @@ PROTOTYPES = {
     "eslam_decode_backward": [_FP, _P, _P, _L, _P, _P, _P, _P],
     "eslam_sample_plane_feature": [_FP, _P, _P, _L, _I, _P, _P],
     "eslam_grid_sdf": [_FP, _P, _P, _P, _P, _I, _I, _I, _L, _L, _P, _P],
+    "eslam_grid_sdf_hull": [_FP, _P, _P, _P, _P, _I, _I, _I, _L, _L, _P, _I, _P, _P],
     "eslam_sample_rays": [_FP, _CP, _RP, _P, _I, _I, _P, _P, _I, _P, _P, _P, _P, _P, _I, _P, _P, _P, _P, _P, _P, _P,
                           _P, _P, _P, _P, _P],
     "eslam_sample_rays_frames": [_FP, _CP, _RP, _P, _I, _I, _P, _P, _I, _P, _P, _P, _P, _P, _I, _P, _P, _P, _P, _P, _P,
@@ -87,6 +88,7 @@ PROTOTYPES = {
     "eslam_adam_step": [_P, _P, _P, _P, _L, C.POINTER(C.c_int64), C.POINTER(C.c_double), _I, _I, _D, _D, _D, _P],
     "eslam_pose_adam_step": [_P, _P, _P, _P, _I, _I, _D, _D, _I, _D, _D, _D, _P, _I, _P],
     "eslam_finalize_loss": [_RP, _P, _I, _P, _P, _P],
+    "eslam_ingest_frame": [_P, _P, _I, _I, _I, _D, _D, _P, _P, _P],
     "eslam_matrix_to_pose": [_P, _P, _I, _P],
     "eslam_pose_to_matrix": [_P, _P, _I, _P],
     "eslam_keyframe_overlap": [_CP, _P, _P, _P, _I, _P, _I, _P, _I, _P, _P, _P],

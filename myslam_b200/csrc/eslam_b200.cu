@@ -11,6 +11,7 @@
 #include "optim.cuh"
 #include "exchange.cuh"
 #include "keyframes.cuh"
+#include "ingest.cuh"
 
 using namespace eslam;
 
@@ -173,10 +174,11 @@ int eslam_sample_plane_feature(const eslam_field_t* f, const float* arena, const
   return 0;
 }
 
-int eslam_grid_sdf(const eslam_field_t* f, const float* arena, const float* xs, const float* ys, const float* zs,
-                   int nx, int ny, int nz, int64_t start, int64_t count, float* sdf, eslam_stream_t s) {
+static int grid_sdf_impl(const eslam_field_t* f, const float* arena, const float* xs, const float* ys, const float* zs,
+                         int nx, int ny, int nz, int64_t start, int64_t count, const float* hull, int n_hull,
+                         float* sdf, eslam_stream_t s) {
   REQUIRE(f && arena && xs && ys && zs && sdf && nx > 0 && ny > 0 && nz > 0 && start >= 0 && count >= 0 &&
-              start + count <= (int64_t)nx * ny * nz,
+              start + count <= (int64_t)nx * ny * nz && n_hull >= 0 && (n_hull == 0 || hull),
           "eslam_grid_sdf");
   if (count == 0) return 0;
   DecodeArgs a;
@@ -186,7 +188,9 @@ int eslam_grid_sdf(const eslam_field_t* f, const float* arena, const float* xs, 
   a.arena4 = reinterpret_cast<const float4*>(arena);
   a.n = count;
   a.sdf_out = sdf;
-  a.flags = 1 | 2;
+  a.flags = 1 | 2 | (n_hull > 0 ? 8 : 0);
+  a.hull = reinterpret_cast<const float4*>(hull);
+  a.n_hull = n_hull;
   a.xs = xs;
   a.ys = ys;
   a.zs = zs;
@@ -197,6 +201,18 @@ int eslam_grid_sdf(const eslam_field_t* f, const float* arena, const float* xs, 
   k_decode<<<(unsigned)((count + NP - 1) / NP), NP, 0, S_(s)>>>(a);
   CHECK_LAUNCH("eslam_grid_sdf");
   return 0;
+}
+
+int eslam_grid_sdf(const eslam_field_t* f, const float* arena, const float* xs, const float* ys, const float* zs,
+                   int nx, int ny, int nz, int64_t start, int64_t count, float* sdf, eslam_stream_t s) {
+  return grid_sdf_impl(f, arena, xs, ys, zs, nx, ny, nz, start, count, nullptr, 0, sdf, s);
+}
+
+int eslam_grid_sdf_hull(const eslam_field_t* f, const float* arena, const float* xs, const float* ys, const float* zs,
+                        int nx, int ny, int nz, int64_t start, int64_t count, const float* hull_planes, int n_planes,
+                        float* sdf, eslam_stream_t s) {
+  REQUIRE(hull_planes && n_planes > 0, "eslam_grid_sdf_hull");
+  return grid_sdf_impl(f, arena, xs, ys, zs, nx, ny, nz, start, count, hull_planes, n_planes, sdf, s);
 }
 
 static int sample_rays_impl(const eslam_field_t* f, const eslam_camera_t* cam, const eslam_render_cfg_t* cfg,
@@ -767,6 +783,28 @@ int eslam_pose_adam_step(float* poses, float* pose_grad, float* exp_avg, float* 
   const int cnt = n - first;
   k_pose_adam<<<(cnt + 31) / 32, 32, 0, S_(s)>>>(a);
   CHECK_LAUNCH("eslam_pose_adam_step");
+  return 0;
+}
+
+int eslam_ingest_frame(const uint8_t* bgr, const uint16_t* depth_u16, int H, int W, int crop_edge,
+                       double png_depth_scale, double scale, double* color, float* depth, eslam_stream_t s) {
+  REQUIRE(bgr && depth_u16 && color && depth && H > 0 && W > 0 && crop_edge >= 0 && 2 * crop_edge < H && 2 * crop_edge < W,
+          "eslam_ingest_frame");
+  IngestArgs a;
+  a.bgr = bgr;
+  a.depth = depth_u16;
+  a.H = H;
+  a.W = W;
+  a.edge = crop_edge;
+  a.png_depth_scale = (float)png_depth_scale;
+  a.scale = (float)scale;
+  a.color = color;
+  a.out_depth = depth;
+  const long long n = (long long)(H - 2 * crop_edge) * (W - 2 * crop_edge);
+  long long blocks = (n + 255) / 256;
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  k_ingest_frame<<<(unsigned)blocks, 256, 0, S_(s)>>>(a);
+  CHECK_LAUNCH("eslam_ingest_frame");
   return 0;
 }
 

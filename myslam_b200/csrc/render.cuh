@@ -108,6 +108,8 @@ struct DecodeArgs {
   const float *xs, *ys, *zs;
   int nx, ny, nz;
   long long start;
+  const float4* hull;  // flags bit3: n_hull half-spaces (nx, ny, nz, d), inside iff n.p + d <= 0 for all of them
+  int n_hull;
 };
 
 __global__ void __launch_bounds__(NP) k_decode(const __grid_constant__ DecodeArgs a) {
@@ -139,6 +141,17 @@ __global__ void __launch_bounds__(NP) k_decode(const __grid_constant__ DecodeArg
   if (a.flags & 2) {
 #pragma unroll
     for (int k = 0; k < 3; ++k) inside = inside && (p[k] < a.fk.hi[k]) && (p[k] > a.fk.lo[k]);
+  }
+  if (a.flags & 8) {  // convex mesh bound of the seen region (Mesher.py:210-217: mesh_bound.contains -> sdf = -1)
+    for (int k = 0; k < a.n_hull && inside; ++k) {
+      const float4 h = __ldg(a.hull + k);
+      inside = fmaf(h.x, p[0], fmaf(h.y, p[1], fmaf(h.z, p[2], h.w))) <= 0.f;
+    }
+  }
+  if ((a.flags & (2 | 8)) && (a.flags & 1) && !__syncthreads_or(valid && inside)) {
+    if (valid && a.sdf_out) a.sdf_out[gi] = -1.0f;  // the whole tile lies outside: nothing to decode
+    if (valid && a.raw) a.raw[gi * 4 + 3] = -1.0f;
+    return;
   }
   // sdf decoder
   write_axis_setups<2>(a.fk, 0, pn, sm.ax_i, sm.ax_f, q);

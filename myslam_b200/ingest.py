@@ -1,0 +1,42 @@
+"""Frame ingest on the device: the arithmetic half of the reference's
+`BaseDataset.__getitem__` (src/utils/datasets.py:79-115) after cv2 has decoded the colour and depth files.
+
+    color_u8 = cv2.imread(color_path)                              # [H,W,3] uint8, BGR   (host, unchanged)
+    depth_u16 = cv2.imread(depth_path, cv2.IMREAD_UNCHANGED)       # [H,W]   uint16       (host, unchanged)
+    color, depth = ingest_frame(color_u8, depth_u16, png_depth_scale, crop_edge, device)
+
+returns exactly what the reference's loader followed by `.to(device)` returns -- colour [H',W',3] float64 RGB in
+[0,1], depth [H',W'] float32 -- but moves 8 bytes per pixel over PCIe instead of 28.  Same-size colour and depth
+only (Replica); datasets that undistort or resize the colour image (ScanNet, TUM) keep the reference's host path.
+"""
+from __future__ import annotations
+
+import numpy as np
+import torch
+
+from ._lib import call, ptr, stream
+
+
+def ingest_frame(color_u8, depth_u16, png_depth_scale: float, crop_edge: int = 0, device="cuda", scale: float = 1.0):
+    dev = torch.device(device)
+    if dev.type != "cuda":
+        raise RuntimeError("ingest_frame needs a CUDA device; myslam_b200 has no CPU path")
+    if isinstance(color_u8, np.ndarray):
+        color_u8 = torch.from_numpy(np.ascontiguousarray(color_u8))
+    if isinstance(depth_u16, np.ndarray):
+        if depth_u16.dtype != np.uint16:
+            raise RuntimeError(f"depth must be the 16-bit png as decoded (uint16), got {depth_u16.dtype}")
+        depth_u16 = torch.from_numpy(np.ascontiguousarray(depth_u16).view(np.int16))  # same bits; torch-friendly dtype
+    if color_u8.dtype != torch.uint8 or color_u8.dim() != 3 or color_u8.shape[2] != 3:
+        raise RuntimeError("colour must be [H,W,3] uint8 (BGR, as cv2.imread returns it)")
+    if depth_u16.dtype not in (torch.int16, torch.uint16) or tuple(depth_u16.shape) != tuple(color_u8.shape[:2]):
+        raise RuntimeError("depth must be [H,W] 16-bit with the colour image's size (no resize on this path)")
+    H, W = int(color_u8.shape[0]), int(color_u8.shape[1])
+    e = int(crop_edge)
+    c = color_u8.contiguous().to(dev, non_blocking=True)
+    d = depth_u16.contiguous().to(dev, non_blocking=True)
+    color = torch.empty(H - 2 * e, W - 2 * e, 3, dtype=torch.float64, device=dev)
+    depth = torch.empty(H - 2 * e, W - 2 * e, dtype=torch.float32, device=dev)
+    call("eslam_ingest_frame", ptr(c), ptr(d), H, W, e, float(png_depth_scale), float(scale), ptr(color), ptr(depth),
+         stream())
+    return color, depth

@@ -30,10 +30,26 @@ def eval_points(p, all_planes, decoders, bound=None):
     return raw
 
 
-def query_grid_sdf(all_planes, decoders, axes, bound=None, start=0, count=None, chunk=1 << 24, out=None):
+def hull_planes(vertices, faces) -> torch.Tensor:
+    """Outward half-spaces [F,4] = (n, d) with n.p + d <= 0 inside, of a CONVEX triangle mesh (the convex hull
+    Mesher.get_bound_from_frames builds with Open3D, Mesher.py:63-128).  float64 numpy in, float32 tensor out."""
+    v = np.asarray(vertices, dtype=np.float64)
+    f = np.asarray(faces, dtype=np.int64)
+    n = np.cross(v[f[:, 1]] - v[f[:, 0]], v[f[:, 2]] - v[f[:, 0]])
+    n /= np.linalg.norm(n, axis=1, keepdims=True).clip(1e-30)
+    d = -(n * v[f[:, 0]]).sum(1)
+    centre = v.mean(0)
+    flip = (n @ centre + d) > 0  # orient every face away from the centroid
+    n[flip] *= -1
+    d[flip] *= -1
+    return torch.from_numpy(np.concatenate([n, d[:, None]], 1).astype(np.float32))
+
+
+def query_grid_sdf(all_planes, decoders, axes, bound=None, start=0, count=None, chunk=1 << 24, out=None, hull=None):
     """SDF on the flat index range [start, start+count) of the marching-cubes lattice
     (flat = (iy*nx + ix)*nz + iz, Mesher.py:179-184), coordinates generated in-kernel.
-    Shard over GPUs by giving each rank its own [start, count)."""
+    Shard over GPUs by giving each rank its own [start, count).  hull: optional [F,4] half-spaces (hull_planes) of
+    the mesh bound; points outside get sdf = -1 in the same pass (Mesher.py:210-217)."""
     store = synced_store(all_planes, decoders, bound)
     dev = store.device
     xs, ys, zs = (torch.from_numpy(np.asarray(a)).float().to(dev) for a in axes)
@@ -42,10 +58,16 @@ def query_grid_sdf(all_planes, decoders, axes, bound=None, start=0, count=None, 
     count = total - start if count is None else count
     if out is None:
         out = torch.empty(count, dtype=torch.float32, device=dev)
+    if hull is not None:
+        hull = hull.to(device=dev, dtype=torch.float32).contiguous()
     done = 0
     while done < count:
         n = min(chunk, count - done)
-        call("eslam_grid_sdf", store.ref(), ptr(store.arena), ptr(xs), ptr(ys), ptr(zs), nx, ny, nz, start + done, n,
-             out[done:done + n].data_ptr(), stream())
+        if hull is None:
+            call("eslam_grid_sdf", store.ref(), ptr(store.arena), ptr(xs), ptr(ys), ptr(zs), nx, ny, nz, start + done,
+                 n, out[done:done + n].data_ptr(), stream())
+        else:
+            call("eslam_grid_sdf_hull", store.ref(), ptr(store.arena), ptr(xs), ptr(ys), ptr(zs), nx, ny, nz,
+                 start + done, n, ptr(hull), hull.shape[0], out[done:done + n].data_ptr(), stream())
         done += n
     return out

@@ -747,3 +747,21 @@ def render_image(fld: Field, cam: Camera, c2w, gt_depth, truncation, n_strat, n_
             depths.append(dep.double())
             colors.append(col)
         return torch.cat(depths, 0).reshape(cam.H, cam.W), torch.cat(colors, 0).reshape(cam.H, cam.W, 3)
+
+
+# ---------------------------------------------------------------------------------------
+# frame ingest
+# ---------------------------------------------------------------------------------------
+def ingest_frame(color_u8_bgr, depth_u16, png_depth_scale, crop_edge=0, scale=1.0):
+    """The arithmetic of BaseDataset.__getitem__ (datasets.py:88-112) after cv2.imread, for same-size colour and
+    depth (no undistortion / resize): numpy arrays in, (colour [H',W',3] float64 RGB, depth [H',W'] float32) out."""
+    import numpy as np
+
+    color = color_u8_bgr[:, :, ::-1] / 255.                       # cvtColor(BGR2RGB); uint8 / float -> float64
+    depth = depth_u16.astype(np.float32) / png_depth_scale
+    color = torch.from_numpy(np.ascontiguousarray(color))
+    depth = torch.from_numpy(depth) * scale
+    if crop_edge > 0:
+        color = color[crop_edge:-crop_edge, crop_edge:-crop_edge]
+        depth = depth[crop_edge:-crop_edge, crop_edge:-crop_edge]
+    return color.contiguous(), depth.contiguous()

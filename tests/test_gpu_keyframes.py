@@ -154,3 +154,53 @@ def test_pose_conversion_kernels_match_host_mirror():
     call("eslam_matrix_to_pose", ptr(m), ptr(o), 5, stream())
     assert torch.equal(o, matrix_to_cam_pose(m))
 
+
+
+def test_ingest_frame_bit_exact():
+    """eslam_ingest_frame == the reference's Replica loader on the fixture frame, bit for bit."""
+    from myslam_b200.ingest import ingest_frame
+
+    d = load_npz("ingest.npz")
+    color, depth = ingest_frame(d["bgr"], d["depth_u16"], float(d["png_depth_scale"]), int(d["crop_edge"]), DEV)
+    assert color.dtype == torch.float64 and depth.dtype == torch.float32
+    assert torch.equal(color.cpu(), torch.from_numpy(d["color"]))
+    assert torch.equal(depth.cpu(), torch.from_numpy(d["depth"]))
+    # no crop, large values, full uint16 range
+    rng = np.random.default_rng(3)
+    bgr = rng.integers(0, 256, size=(33, 47, 3), dtype=np.uint8)
+    dep = rng.integers(0, 65536, size=(33, 47), dtype=np.uint16)
+    c2, d2 = ingest_frame(bgr, dep, 1000.0, 0, DEV)
+    oc, od = O.ingest_frame(bgr, dep, 1000.0, 0)
+    assert torch.equal(c2.cpu(), oc) and torch.equal(d2.cpu(), od)
+
+
+def test_grid_query_with_convex_mesh_bound():
+    """Mesher.get_mesh forces sdf = -1 outside the convex hull of the observed region (Mesher.py:206-217); here the
+    half-space test runs inside the grid query.  Against the plain query + a float64 half-space mask, away from the
+    faces' rounding band."""
+    from scipy.spatial import ConvexHull
+    from myslam_b200 import grid_axes, hull_planes, query_grid_sdf
+
+    mp, fld = _mapper(GOLDEN_CAM)
+    planes = (mp.planes_xy, mp.planes_xz, mp.planes_yz, mp.c_planes_xy, mp.c_planes_xz, mp.c_planes_yz)
+    b = fld.bound.numpy().astype(np.float64)
+    rng = np.random.default_rng(1)
+    pts = b[:, 0] + (b[:, 1] - b[:, 0]) * (0.15 + 0.7 * rng.random((40, 3)))  # a blob strictly inside the bound
+    hull = ConvexHull(pts)
+    hp = hull_planes(pts, hull.simplices)
+    assert hp.shape == (len(hull.simplices), 4)
+    axes = grid_axes(b, 0.03)
+    plain = query_grid_sdf(planes, mp.decoders, axes, fld.bound).cpu()
+    bounded = query_grid_sdf(planes, mp.decoders, axes, fld.bound, hull=hp).cpu()
+    gx, gy, gz = np.meshgrid(*axes, indexing="xy")  # Mesher.get_grid_uniform's point order
+    p = np.stack([gx.reshape(-1), gy.reshape(-1), gz.reshape(-1)], 1)
+    margin = (p @ hp[:, :3].double().numpy().T + hp[:, 3].double().numpy()).max(1)  # <= 0 inside
+    sure_in, sure_out = torch.from_numpy(margin < -1e-4), torch.from_numpy(margin > 1e-4)
+    assert int(sure_in.sum()) > 100 and int(sure_out.sum()) > 100
+    assert torch.equal(bounded[sure_in], plain[sure_in])
+    assert (bounded[sure_out] == -1.0).all()
+    # sharded ranges give the same lattice values
+    n = bounded.numel()
+    parts = [query_grid_sdf(planes, mp.decoders, axes, fld.bound, start=s, count=c, hull=hp).cpu()
+             for s, c in ((0, n // 3), (n // 3, n - n // 3))]
+    assert torch.equal(torch.cat(parts), bounded)

@@ -142,3 +142,12 @@ def test_render_img_golden():
                               ray_batch_size=int(d["ray_batch_size"]))
     assert dep.dtype == torch.float64
     assert rel_err(dep, d["depth"]) < 1e-6 and rel_err(col, d["color"]) < 1e-6
+
+
+def test_ingest_golden():
+    """Oracle restatement of BaseDataset.__getitem__'s arithmetic (datasets.py:88-112) against what the reference's
+    Replica loader returned for the fixture frame (tests/golden/make_golden_ingest.py)."""
+    d = load_npz("ingest.npz")
+    color, depth = O.ingest_frame(d["bgr"], d["depth_u16"], float(d["png_depth_scale"]), int(d["crop_edge"]))
+    assert color.dtype == torch.float64 and depth.dtype == torch.float32
+    assert torch.equal(color, torch.from_numpy(d["color"])) and torch.equal(depth, torch.from_numpy(d["depth"]))
