@@ -492,9 +492,16 @@ __device__ __forceinline__ void wgrad_store_bias(float* dst, int m_valid, int la
   }
 }
 
-// Weight gradients of BOTH decoders, accumulated into the gradient arena, in two CTA-wide rounds.  Warps 0-3 work
+// barrier over the 128 threads that own one decoder (hardware barriers 1 and 2; 0 is __syncthreads): from the MLP
+// backward to the end of the scatter a half only touches its own staging buffer and feature tile, so the two
+// halves need not wait for each other and their reduction-bound and FMA-bound phases can overlap
+__device__ __forceinline__ void half_sync(int half) {
+  asm volatile("bar.sync %0, %1;" ::"r"(1 + half), "r"(NP) : "memory");
+}
+
+// Weight gradients of BOTH decoders, accumulated into the gradient arena, in two rounds per half.  Warps 0-3 work
 // on the sdf decoder, warps 4-7 on the rgb decoder (the same split as the thread halves, so `half` is also the
-// decoder a warp computes for).  Contains __syncthreads: call from uniform control flow.
+// decoder a warp computes for).  Contains barriers over each half: call from uniform control flow.
 //   round 1  input layer  dW1 = ga1^T F : ga1 staged in act0 (sdf) / act1 (rgb); warp w of a half owns feature
 //            columns 16w..16w+15 (two tiles sharing the A fragments); warp 0 of a half also takes db1
 //   round 2  hidden and output layers: every owner thread parks (ga2 | h1 | h2 | gout) in ITS OWN row of the feature
@@ -520,7 +527,7 @@ __device__ __forceinline__ void weight_grads(float* act0, float* act1, float4* F
 #pragma unroll
     for (int v = 0; v < 4; ++v) a0[v] = make_float4(ga1[v * 4], ga1[v * 4 + 1], ga1[v * 4 + 2], ga1[v * 4 + 3]);
   }
-  __syncthreads();
+  half_sync(half);
   const int g = lane >> 2, t = lane & 3;
   {
     float acc[2][4];
@@ -534,7 +541,7 @@ __device__ __forceinline__ void weight_grads(float* act0, float* act1, float4* F
       wgrad_store_bias(gB1, 16, lane, acc[0]);
     }
   }
-  __syncthreads();
+  half_sync(half);
   // ---- round 2: columns 0-15 ga2, 16-31 h1, 32-47 h2, 48-51 gout of the thread's own feature-tile row
 #pragma unroll
   for (int v = 0; v < 4; ++v) {
@@ -543,7 +550,7 @@ __device__ __forceinline__ void weight_grads(float* act0, float* act1, float4* F
     F[f_slot(q, 8 + v)] = make_float4(h2[v * 4], h2[v * 4 + 1], h2[v * 4 + 2], h2[v * 4 + 3]);
   }
   F[f_slot(q, 12)] = make_float4(gout[0], gout[1], gout[2], 0.f);
-  __syncthreads();
+  half_sync(half);
   const FromTile g2_lo(F, g, t), g2_hi(F, 8 + g, t);  // ga2 channels g, g + 8
   const FromTile g3_lo(F, 48 + (g & 3), t);           // gout channel g (< 4; lanes with g >= 4 contribute zeros)
   if (wl < 2) {
@@ -565,7 +572,7 @@ __device__ __forceinline__ void weight_grads(float* act0, float* act1, float4* F
     wgrad_bias<4>(g3_lo, g3_lo, lane, acc);
     wgrad_store_bias(gB3, nout, lane, acc);
   }
-  __syncthreads();
+  half_sync(half);
 }
 
 // gather layout: scatter d loss/d features of one decoder into the plane gradients and/or accumulate the
@@ -962,7 +969,7 @@ __global__ void __launch_bounds__(NT_BWD, 2) k_render_bwd(const __grid_constant_
   } else {
     mlp_backward_input_s(Wh, ga1, Fh, q);
   }
-  __syncthreads();
+  half_sync(half);
   if (GF && !(a.dbg & 2) && tid == 0) {
     float gb = 0.f;
     for (int i = 0; i < NP / 32; ++i) gb += sm.red[i];  // only the sdf half carries beta gradients
