@@ -134,7 +134,8 @@ def tracking_iteration(ws: Workspace, store: FieldStore, sc: StepCfg, pose7: tor
     """One iteration of Tracker.optimize_tracking (Tracker.py:150-210) up to (and optionally including)
     the Adam step.  pose7: [1,7] contiguous fp32 device tensor (quaternion, translation).
     After the call: ws.loss_acc[5] = loss (float64), ws.grad7[0] = d loss / d pose.
-    apply_adam: dict(step=, lr_q=, lr_t=) -> fused Adam(betas .5,.999) on pose7 in place (ws.pose_m/v)."""
+    apply_adam: dict(step=, lr_q=, lr_t=[, m=, v=, betas=, eps=]) -> fused Adam (default betas .5,.999) on pose7 in
+    place, on the workspace's moments or on the given [1,7] rows."""
     dev = ws.device
     draws = draws or TorchDraws(dev)
     cam, rc = sc.cam, sc.render
@@ -168,8 +169,11 @@ def tracking_iteration(ws: Workspace, store: FieldStore, sc: StepCfg, pose7: tor
         call("eslam_pose_adam_step", ptr(pose7), ptr(ws.pose_grad), None, None, 1, 0, 0.0, 0.0, 1, 0.5, 0.999, 1e-8,
              ptr(ws.grad7), 0, stream())
     else:
-        call("eslam_pose_adam_step", ptr(pose7), ptr(ws.pose_grad), ptr(ws.pose_m), ptr(ws.pose_v), 1, 0,
-             apply_adam["lr_q"], apply_adam["lr_t"], apply_adam["step"], 0.5, 0.999, 1e-8, ptr(ws.grad7), 1, stream())
+        # moments: the workspace's, or the caller's (the rows of a torch.optim.Adam's own state, tracker.py)
+        m, v = apply_adam.get("m", ws.pose_m), apply_adam.get("v", ws.pose_v)
+        b1, b2 = apply_adam.get("betas", (0.5, 0.999))
+        call("eslam_pose_adam_step", ptr(pose7), ptr(ws.pose_grad), ptr(m), ptr(v), 1, 0, apply_adam["lr_q"],
+             apply_adam["lr_t"], apply_adam["step"], b1, b2, apply_adam.get("eps", 1e-8), ptr(ws.grad7), 1, stream())
 
 
 def mapping_iteration(ws: Workspace, store: FieldStore, sc: StepCfg, c2ws, poses7, gt_colors, gt_depths,

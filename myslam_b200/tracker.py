@@ -50,19 +50,87 @@ def _tracker_store(trk, st):
     return store
 
 
+def _fused_adam_plan(cam_pose, optimizer):
+    """If `cam_pose` is torch.cat([R, T], -1) of two leaf parameters R [1,4] and T [1,3] that are the only parameters
+    of a plain torch.optim.Adam (what Tracker.run builds, Tracker.py:282-299), return what is needed to take the
+    optimizer's step with the fused pose-Adam kernel ON THE OPTIMIZER'S OWN STATE; otherwise None (generic path:
+    autograd + optimizer.step())."""
+    fn = cam_pose.grad_fn
+    if type(optimizer) is not torch.optim.Adam or fn is None or type(fn).__name__ != "CatBackward0":
+        return None
+    nxt = fn.next_functions
+    if len(nxt) != 2 or any(n[0] is None or not hasattr(n[0], "variable") for n in nxt):
+        return None
+    Rq, T = nxt[0][0].variable, nxt[1][0].variable
+    if tuple(Rq.shape) != (1, 4) or tuple(T.shape) != (1, 3) or tuple(cam_pose.shape) != (1, 7):
+        return None
+    groups = optimizer.param_groups
+    if len(groups) != 2 or any(len(g["params"]) != 1 for g in groups):
+        return None
+    by_param = {id(g["params"][0]): g for g in groups}
+    if id(Rq) not in by_param or id(T) not in by_param:
+        return None
+    gR, gT = by_param[id(Rq)], by_param[id(T)]
+    for g in (gR, gT):
+        if g.get("amsgrad") or g.get("maximize") or g.get("weight_decay", 0) != 0 or g.get("capturable") \
+                or g.get("differentiable") or g.get("fused"):
+            return None
+    if gR["betas"] != gT["betas"] or gR["eps"] != gT["eps"]:
+        return None
+    sR, sT = optimizer.state[Rq], optimizer.state[T]
+    if len(sR) == 0 and len(sT) == 0:
+        # first step: create the optimizer's state the way torch does, with both parameters' moments in ONE [1,7]
+        # row each so the kernel can address them as a pose
+        m7 = torch.zeros(1, 7, dtype=torch.float32, device=Rq.device)
+        v7 = torch.zeros(1, 7, dtype=torch.float32, device=Rq.device)
+        for st_, sl in ((sR, slice(0, 4)), (sT, slice(4, 7))):
+            st_["step"] = torch.tensor(0.0, dtype=torch.float32)
+            st_["exp_avg"] = m7[:, sl]
+            st_["exp_avg_sq"] = v7[:, sl]
+    try:
+        mR, mT, vR, vT = sR["exp_avg"], sT["exp_avg"], sR["exp_avg_sq"], sT["exp_avg_sq"]
+    except KeyError:
+        return None
+    adjacent = (mT.data_ptr() == mR.data_ptr() + 16 and vT.data_ptr() == vR.data_ptr() + 16
+                and mR.dtype == torch.float32 and mR.device == Rq.device and float(sR["step"]) == float(sT["step"]))
+    if not adjacent:
+        return None  # state created elsewhere: leave it to torch
+    return Rq, T, gR, gT, sR, sT
+
+
 def optimize_tracking(self, cam_pose, gt_color, gt_depth, batch_size, optimizer):
     """One iteration of camera tracking (reference Tracker.optimize_tracking, Tracker.py:150-210):
     sample pixels, render, losses, backward to the 7-dof pose, step the caller's optimizer.
-    Returns the loss as a python float."""
+    Returns the loss as a python float.
+
+    When the caller's optimizer is the plain Adam over (R, T) that Tracker.run builds and `cam_pose` is their
+    concatenation, the step is taken by the fused pose-Adam kernel directly on the optimizer's state (same update
+    rule, `.grad` of both parameters set, step counters advanced) instead of through autograd and ~30 ATen launches;
+    anything else goes through `cam_pose.backward` + `optimizer.step()`."""
     st = _tracker_state(self, batch_size)
     store = _tracker_store(self, st)
     ws = st["ws"]
-    pose7 = cam_pose.detach().float().contiguous()
-    tracking_iteration(ws, store, st["sc"], pose7, gt_color, gt_depth, batch_size,
-                       draws=getattr(self, "draws", None), strict_rng=getattr(self, "strict_rng", _strict_default()))
-    optimizer.zero_grad()
-    cam_pose.backward(ws.grad7[0:1].clone())
-    optimizer.step()
+    plan = _fused_adam_plan(cam_pose, optimizer) if os.environ.get("ESLAM_B200_FUSED_OPT", "1") == "1" else None
+    draws, strict = getattr(self, "draws", None), getattr(self, "strict_rng", _strict_default())
+    if plan is None:
+        pose7 = cam_pose.detach().float().contiguous()
+        tracking_iteration(ws, store, st["sc"], pose7, gt_color, gt_depth, batch_size, draws=draws, strict_rng=strict)
+        optimizer.zero_grad()
+        cam_pose.backward(ws.grad7[0:1].clone())
+        optimizer.step()
+        return ws.loss_acc[5].item()
+    Rq, T, gR, gT, sR, sT = plan
+    pose7 = cam_pose.detach().float().clone().contiguous()
+    tracking_iteration(ws, store, st["sc"], pose7, gt_color, gt_depth, batch_size, draws=draws, strict_rng=strict,
+                       apply_adam={"step": int(float(sR["step"])) + 1, "lr_q": float(gR["lr"]), "lr_t": float(gT["lr"]),
+                                   "m": sR["exp_avg"], "v": sR["exp_avg_sq"], "betas": gR["betas"], "eps": gR["eps"]})
+    g7 = ws.grad7[0:1].clone()
+    with torch.no_grad():
+        Rq.copy_(pose7[:, :4])
+        T.copy_(pose7[:, 4:])
+    Rq.grad, T.grad = g7[:, :4], g7[:, 4:]
+    sR["step"] += 1
+    sT["step"] += 1
     return ws.loss_acc[5].item()
 
 

@@ -445,3 +445,39 @@ def test_track_frame_graph_replay_matches_eager_loop(monkeypatch):
     assert int(trk._b200["ws"].counters[0]) == 0
     _, losses3, _ = trk.track_frame(pose0, gc, gd, iters=6, batch_size=int(d["n_pix"]), lr_T=2e-3, lr_R=1e-3)
     assert torch.isfinite(losses3).all() and int(trk._b200["ws"].counters[0]) > 0
+
+
+def test_optimize_tracking_fused_step_keeps_the_callers_optimizer_consistent(monkeypatch):
+    """optimize_tracking takes the step of the caller's torch.optim.Adam with the fused kernel when it recognises the
+    (R, T) set-up of Tracker.run; parameters, .grad, moments and step counters must end up where autograd +
+    optimizer.step() (ESLAM_B200_FUSED_OPT=0) puts them, and an optimizer it does not recognise goes the generic way."""
+    from myslam_b200 import ReplayDraws
+    from myslam_b200.tracker import _fused_adam_plan
+
+    fld, d = golden_field(), load_npz("tracking.npz")
+    pose0 = torch.from_numpy(d["pose0"]).to(DEV)
+    gc, gd = torch.from_numpy(d["gt_color"]).to(DEV), torch.from_numpy(d["gt_depth"]).to(DEV)
+    out = {}
+    for mode in ("0", "1"):
+        monkeypatch.setenv("ESLAM_B200_FUSED_OPT", mode)
+        trk = make_tracker(fld, d)
+        trk.draws = ReplayDraws(recorded_draws(d), DEV)
+        T = torch.nn.Parameter(pose0[:, -3:].clone())
+        Rq = torch.nn.Parameter(pose0[:, :4].clone())
+        opt = torch.optim.Adam([{"params": [T], "lr": float(d["lr_T"]), "betas": (0.5, 0.999)},
+                                {"params": [Rq], "lr": float(d["lr_R"]), "betas": (0.5, 0.999)}])
+        for _ in range(int(d["iters"])):
+            pose = torch.cat([Rq, T], -1)
+            if mode == "1":
+                assert _fused_adam_plan(pose, opt) is not None
+            trk.optimize_tracking(pose, gc, gd, int(d["n_pix"]), opt)
+        out[mode] = (Rq.detach().clone(), T.detach().clone(), Rq.grad.clone(), T.grad.clone(),
+                     opt.state[Rq]["exp_avg"].clone(), opt.state[T]["exp_avg_sq"].clone(), float(opt.state[Rq]["step"]),
+                     float(opt.state[T]["step"]))
+    for a, b in zip(out["0"][:6], out["1"][:6]):
+        assert rel_err(b, a) < 1e-5
+    assert out["0"][6:] == out["1"][6:] == (float(d["iters"]), float(d["iters"]))
+    # not the (R, T) pattern: a single [1,7] parameter, SGD -> generic path
+    P = torch.nn.Parameter(pose0.clone())
+    assert _fused_adam_plan(P * 1.0, torch.optim.SGD([P], lr=1e-3)) is None
+    assert _fused_adam_plan(torch.cat([P[:, :4], P[:, 4:]], -1), torch.optim.Adam([P], lr=1e-3)) is None
