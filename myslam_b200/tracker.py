@@ -50,7 +50,45 @@ def _tracker_store(trk, st):
     return store
 
 
-def _fused_adam_plan(cam_pose, optimizer):
+class _IterGraphs:
+    """One CUDA graph per Adam step index for the per-iteration drop-in (`optimize_tracking`): draws + ray sampling +
+    forward + outlier mask + backward + loss + pose Adam, i.e. one replay instead of ~10 launches per iteration.
+    Persistent buffers the graphs address: the [1,7] pose, the two [1,7] moment rows (lent to the caller's optimizer
+    as its own state, see _fused_adam_plan) and a one-entry frame table."""
+
+    def __init__(self, dev):
+        self.pose = torch.zeros(1, 7, dtype=torch.float32, device=dev)
+        self.m7 = torch.zeros(1, 7, dtype=torch.float32, device=dev)
+        self.v7 = torch.zeros(1, 7, dtype=torch.float32, device=dev)
+        self.frames = None
+        self.frame_key = None
+        self.graphs = {}
+        self.owner = None  # weakref to the optimizer whose state currently lives in m7 / v7
+
+    def lend(self, optimizer):
+        """The moment rows for a NEW optimizer state, or None if another live optimizer still uses them."""
+        import weakref
+
+        cur = self.owner() if self.owner is not None else None
+        if cur is not None and cur is not optimizer:
+            return None
+        self.owner = weakref.ref(optimizer)
+        self.m7.zero_()
+        self.v7.zero_()
+        return self.m7, self.v7
+
+    def set_frame(self, gt_color, gt_depth, cam, dev):
+        c, d = gt_color[0], gt_depth[0]
+        key = (c.data_ptr(), d.data_ptr())
+        if self.frames is None:
+            self.frames = FrameTable([c], [d], cam, dev)
+        elif key != self.frame_key:
+            self.frames.colors, self.frames.depths = [c], [d]
+            self.frames.table.copy_(torch.tensor([[d.data_ptr()], [c.data_ptr()]], dtype=torch.int64))
+        self.frame_key = key
+
+
+def _fused_adam_plan(cam_pose, optimizer, ig=None):
     """If `cam_pose` is torch.cat([R, T], -1) of two leaf parameters R [1,4] and T [1,3] that are the only parameters
     of a plain torch.optim.Adam (what Tracker.run builds, Tracker.py:282-299), return what is needed to take the
     optimizer's step with the fused pose-Adam kernel ON THE OPTIMIZER'S OWN STATE; otherwise None (generic path:
@@ -81,8 +119,12 @@ def _fused_adam_plan(cam_pose, optimizer):
     if len(sR) == 0 and len(sT) == 0:
         # first step: create the optimizer's state the way torch does, with both parameters' moments in ONE [1,7]
         # row each so the kernel can address them as a pose
-        m7 = torch.zeros(1, 7, dtype=torch.float32, device=Rq.device)
-        v7 = torch.zeros(1, 7, dtype=torch.float32, device=Rq.device)
+        lent = ig.lend(optimizer) if ig is not None else None
+        if lent is not None:
+            m7, v7 = lent
+        else:
+            m7 = torch.zeros(1, 7, dtype=torch.float32, device=Rq.device)
+            v7 = torch.zeros(1, 7, dtype=torch.float32, device=Rq.device)
         for st_, sl in ((sR, slice(0, 4)), (sT, slice(4, 7))):
             st_["step"] = torch.tensor(0.0, dtype=torch.float32)
             st_["exp_avg"] = m7[:, sl]
@@ -110,7 +152,12 @@ def optimize_tracking(self, cam_pose, gt_color, gt_depth, batch_size, optimizer)
     st = _tracker_state(self, batch_size)
     store = _tracker_store(self, st)
     ws = st["ws"]
-    plan = _fused_adam_plan(cam_pose, optimizer) if os.environ.get("ESLAM_B200_FUSED_OPT", "1") == "1" else None
+    fused = os.environ.get("ESLAM_B200_FUSED_OPT", "1") == "1"
+    graphs_on = fused and _use_graph(self) and st["sc"].perturb
+    ig = st.get("iter_graphs")
+    if graphs_on and ig is None:
+        ig = st["iter_graphs"] = _IterGraphs(ws.device)
+    plan = _fused_adam_plan(cam_pose, optimizer, ig if graphs_on else None) if fused else None
     draws, strict = getattr(self, "draws", None), getattr(self, "strict_rng", _strict_default())
     if plan is None:
         pose7 = cam_pose.detach().float().contiguous()
@@ -120,10 +167,37 @@ def optimize_tracking(self, cam_pose, gt_color, gt_depth, batch_size, optimizer)
         optimizer.step()
         return ws.loss_acc[5].item()
     Rq, T, gR, gT, sR, sT = plan
-    pose7 = cam_pose.detach().float().clone().contiguous()
-    tracking_iteration(ws, store, st["sc"], pose7, gt_color, gt_depth, batch_size, draws=draws, strict_rng=strict,
-                       apply_adam={"step": int(float(sR["step"])) + 1, "lr_q": float(gR["lr"]), "lr_t": float(gT["lr"]),
-                                   "m": sR["exp_avg"], "v": sR["exp_avg_sq"], "betas": gR["betas"], "eps": gR["eps"]})
+    step = int(float(sR["step"])) + 1
+    adam = {"step": step, "lr_q": float(gR["lr"]), "lr_t": float(gT["lr"]), "m": sR["exp_avg"], "v": sR["exp_avg_sq"],
+            "betas": tuple(gR["betas"]), "eps": float(gR["eps"])}
+    replay = (graphs_on and st.get("eager_done") and sR["exp_avg"].data_ptr() == ig.m7.data_ptr()
+              and sR["exp_avg_sq"].data_ptr() == ig.v7.data_ptr())
+    if replay:
+        # one graph per Adam step index (the bias corrections are host-side constants of the launch)
+        _check_track_frames(gt_color, gt_depth, st["sc"].cam)
+        ig.set_frame(gt_color, gt_depth, st["sc"].cam, ws.device)
+        ig.pose.copy_(cam_pose.detach().float().reshape(1, 7))
+        key = (step, adam["lr_q"], adam["lr_t"], adam["betas"], adam["eps"], batch_size, store.arena.data_ptr(), id(ws))
+        ent = ig.graphs.get(key)
+        if ent is None:
+            from . import _lib
+
+            g = torch.cuda.CUDAGraph()
+            l0 = _lib.LAUNCHES
+            with torch.cuda.graph(g):
+                tracking_iteration(ws, store, st["sc"], ig.pose, ig.frames, ig.frames, batch_size,
+                                   apply_adam={**adam, "m": ig.m7, "v": ig.v7})
+            ent = ig.graphs[key] = (g, _lib.LAUNCHES - l0)
+        ent[0].replay()
+        from . import _lib
+
+        _lib.LAUNCHES += ent[1]
+        pose7 = ig.pose
+    else:
+        pose7 = cam_pose.detach().float().clone().contiguous()
+        tracking_iteration(ws, store, st["sc"], pose7, gt_color, gt_depth, batch_size, draws=draws, strict_rng=strict,
+                           apply_adam=adam)
+        st["eager_done"] = True
     g7 = ws.grad7[0:1].clone()
     with torch.no_grad():
         Rq.copy_(pose7[:, :4])

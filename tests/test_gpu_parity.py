@@ -429,10 +429,12 @@ def test_track_frame_graph_replay_matches_eager_loop(monkeypatch):
     for mode in ("0", "1"):
         monkeypatch.setenv("ESLAM_B200_GRAPH", mode)
         trk = make_tracker(fld, d)
+        trk.strict_rng = False  # graphs need fixed draw shapes
         torch.manual_seed(5)
         best, losses, final = trk.track_frame(pose0, gc, gd, iters=6, batch_size=int(d["n_pix"]), lr_T=2e-3, lr_R=1e-3)
         torch.cuda.synchronize()
         assert torch.isfinite(losses).all() and torch.isfinite(final).all()
+        assert (trk._b200.get("graph") is not None) == (mode == "1")
         res[mode] = (best.clone(), losses.clone(), final.clone(), trk)
     l0, l1 = res["0"][1], res["1"][1]
     assert abs(l0.mean().item() - l1.mean().item()) < 0.25 * abs(l0.mean().item())
@@ -481,3 +483,46 @@ def test_optimize_tracking_fused_step_keeps_the_callers_optimizer_consistent(mon
     P = torch.nn.Parameter(pose0.clone())
     assert _fused_adam_plan(P * 1.0, torch.optim.SGD([P], lr=1e-3)) is None
     assert _fused_adam_plan(torch.cat([P[:, :4], P[:, 4:]], -1), torch.optim.Adam([P], lr=1e-3)) is None
+
+
+def test_optimize_tracking_iteration_graphs(monkeypatch):
+    """Without injected draws the drop-in replays one CUDA graph per Adam step index.  Driven like Tracker.run (a new
+    Adam per frame): the optimizer's state advances, the graphs captured for the first frame are re-used for the next,
+    the losses are those of the launch-by-launch path on average, and a frame of zero depth really is read."""
+    fld, d = golden_field(), load_npz("tracking.npz")
+    pose0 = torch.from_numpy(d["pose0"]).to(DEV)
+    gc, gd = torch.from_numpy(d["gt_color"]).to(DEV), torch.from_numpy(d["gt_depth"]).to(DEV)
+    iters, n_pix = 6, int(d["n_pix"])
+
+    def run_frame(trk, color, depth):
+        T = torch.nn.Parameter(pose0[:, -3:].clone())
+        Rq = torch.nn.Parameter(pose0[:, :4].clone())
+        opt = torch.optim.Adam([{"params": [T], "lr": 2e-3, "betas": (0.5, 0.999)},
+                                {"params": [Rq], "lr": 1e-3, "betas": (0.5, 0.999)}])
+        losses = [trk.optimize_tracking(torch.cat([Rq, T], -1), color, depth, n_pix, opt) for _ in range(iters)]
+        return torch.tensor(losses), torch.cat([Rq, T], -1).detach().clone(), opt, Rq, T
+
+    means = {}
+    for mode in ("0", "1"):
+        monkeypatch.setenv("ESLAM_B200_GRAPH", mode)
+        trk = make_tracker(fld, d)
+        trk.strict_rng = False  # graphs need fixed draw shapes
+        torch.manual_seed(9)
+        l_a, pose_a, opt, Rq, T = run_frame(trk, gc, gd)
+        assert torch.isfinite(l_a).all() and torch.isfinite(pose_a).all()
+        assert float(opt.state[Rq]["step"]) == iters and float(opt.state[T]["step"]) == iters
+        assert opt.state[Rq]["exp_avg"].abs().sum() > 0 and torch.isfinite(Rq.grad).all()
+        assert (pose_a - pose0).abs().max() > 0
+        means[mode] = l_a.mean().item()
+        if mode == "1":
+            ig = trk._b200["iter_graphs"]
+            n_graphs = len(ig.graphs)
+            assert n_graphs == iters - 1  # the first iteration of the first frame ran launch by launch
+            del opt
+            l_b, _, opt2, Rq2, _ = run_frame(trk, gc.clone(), gd.clone())  # next frame: new optimizer, new tensors
+            assert len(ig.graphs) == iters and torch.isfinite(l_b).all()
+            assert opt2.state[Rq2]["exp_avg"].data_ptr() == ig.m7.data_ptr()
+            del opt2
+            run_frame(trk, gc, torch.zeros_like(gd))
+            assert int(trk._b200["ws"].counters[0]) == 0  # depth > 0 rays only: the new frame was read
+    assert abs(means["0"] - means["1"]) < 0.25 * abs(means["0"])
