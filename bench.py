@@ -378,9 +378,23 @@ def main():
         if os.environ.get("ESLAM_B200_EXCHANGE", "peer") == "nccl":
             ex, exchange_name = MappingExchange(), "NCCL all-reduce of the gradient arena + replicated Adam"
         else:
-            ex = PeerExchange(store, ws)
-            exchange_name = ("one kernel over symmetric peer memory: reduce-scatter + Adam + all-gather + zero_grad ("
-                             + ("multimem.ld_reduce/st through NVSwitch" if ex.multimem else "P2P loads/stores") + ")")
+            # symmetric (peer-mapped) memory needs P2P between all GPUs of the job: agree on it, and measure the NCCL
+            # path (saying so) rather than nothing if the box does not offer it
+            err = None
+            try:
+                ex = PeerExchange(store, ws)
+            except Exception as exc:  # noqa: BLE001
+                err = repr(exc)
+            ok = torch.tensor([0 if err else 1], device=dev)
+            dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+            if int(ok.item()) == 1:
+                exchange_name = ("own kernels over symmetric peer memory: push reduce-scatter + Adam + all-gather + "
+                                 "zero_grad (" + ("multimem.st parameter broadcast" if ex.multimem else "P2P stores")
+                                 + "), normalisers summed over peer loads; no NCCL call per iteration")
+            else:
+                ex = MappingExchange()
+                exchange_name = ("NCCL all-reduce of the gradient arena + replicated Adam (symmetric memory "
+                                 f"unavailable: {err})")
     lr = m["lr"]
     pix = m["pixels"] // n_frames
 
