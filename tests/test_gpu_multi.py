@@ -169,3 +169,66 @@ def test_fused_peer_exchange_equals_nccl_allreduce_plus_adam(tmp_path, world):
             assert rel_err(c2w, ref_c2w) < tol
             assert rel_err(loss, ref_loss) < tol
     print("multimem used:", res[0]["peer"][4])
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# the drop-in call itself on several ranks: Mapper.optimize_mapping with `mapper.exchange` attached
+# ---------------------------------------------------------------------------------------------------------------
+def _worker_dropin(rank, world, port, out):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    for p in (ROOT, os.path.join(ROOT, "oracle"), os.path.join(ROOT, "tests")):
+        if p not in sys.path:
+            sys.path.insert(0, p)
+    torch.cuda.set_device(rank)
+    dev = f"cuda:{rank}"
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device(dev))
+    from myslam_b200 import MapperStep, Renderer
+    from myslam_b200.decoders import _STORES, synced_store
+    from myslam_b200.dist import MappingExchange, PeerExchange
+
+    res = {}
+    for kind in ("nccl", "peer"):
+        _STORES.clear()
+        fld, d = golden_field(), load_npz("mapping.npz")
+        planes, dec = to_device_scene(fld, dev)
+        cfg = base_cfg()
+        rnd = Renderer(cfg, SimpleEslam(fld.bound.clone(), GOLDEN_CAM, dev))
+        mp_ = MapperStep(cfg, rnd, dec, planes, fld.bound.clone(), GOLDEN_CAM, dev)
+        mp_.joint_opt = True
+        store = synced_store(planes, dec, fld.bound)
+        mp_.exchange = MappingExchange() if kind == "nccl" else PeerExchange(store)
+        c2ws = torch.from_numpy(d["c2ws0"]).to(dev)
+        cols, deps = torch.from_numpy(d["gt_colors"]).to(dev), torch.from_numpy(d["gt_depths"]).to(dev)
+        kf = [{"gt_c2w": c2ws[k], "idx": torch.tensor(4 * k), "color": cols[k], "depth": deps[k],
+               "est_c2w": c2ws[k].clone()} for k in range(3)]
+        mp_.keyframe_dict = kf
+        import numpy as np
+
+        np.random.seed(3)              # identical window on every rank
+        torch.manual_seed(200 + rank)  # own rays per rank
+        cur = mp_.optimize_mapping(3, 1.0, torch.tensor(12), cols[3], deps[3], c2ws[3].clone(), kf, [0, 4, 8],
+                                   c2ws[3].clone())
+        torch.cuda.synchronize()
+        if hasattr(mp_.exchange, "check"):
+            mp_.exchange.check()
+        flat = torch.cat([p.detach().reshape(-1) for g in planes for p in g]).cpu()
+        sd = torch.cat([v.detach().reshape(-1) for v in dec.state_dict().values()]).cpu()
+        res[kind] = (flat, sd, cur.cpu(), torch.stack([k["est_c2w"] for k in kf]).cpu())
+    torch.save(res, f"{out}.{rank}")
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
+def test_optimize_mapping_dropin_with_peer_exchange(tmp_path):
+    """The reference-facing call on 2 ranks: planes and decoders written back to the reference's tensors, keyframe and
+    current poses -- identical on both ranks and equal to the NCCL all-reduce path."""
+    out = str(tmp_path / "d.pt")
+    mp.spawn(_worker_dropin, args=(2, 30100 + os.getpid() % 200, out), nprocs=2, join=True)
+    r0, r1 = torch.load(out + ".0"), torch.load(out + ".1")
+    for kind in ("nccl", "peer"):
+        for a, b in zip(r0[kind], r1[kind]):
+            assert torch.equal(a, b), f"{kind}: ranks differ"
+    for a, b in zip(r0["peer"], r0["nccl"]):
+        assert torch.isfinite(a).all() and rel_err(a, b) < 1e-6
