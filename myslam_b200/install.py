@@ -31,3 +31,4 @@ def install(src_package: str = "src") -> None:
     trk_mod.Tracker.track_frame = tracker.track_frame
     map_mod = importlib.import_module(f"{src_package}.Mapper")
     map_mod.Mapper.optimize_mapping = mapper.optimize_mapping
+    map_mod.Mapper.keyframe_selection_overlap = mapper.keyframe_selection_overlap

@@ -65,3 +65,51 @@ def test_plane_shapes_room0_float32_truncation():
     assert O.plane_shapes(b, 0.06) == ((111, 164), (84, 164), (84, 111))
     assert O.plane_shapes(b, 0.24) == ((27, 41), (21, 41), (21, 27))
     assert O.plane_shapes(b, 0.03) == ((223, 328), (168, 328), (168, 223))
+
+
+def test_install_patches_the_reference_package():
+    """`myslam_b200.install("src")` on the UNMODIFIED reference (only where /root/reference exists: the build
+    container): the four redirections of INTEGRATION.md land on the reference's own classes and keep their
+    signatures."""
+    import inspect
+    import os
+    import sys
+
+    import pytest
+
+    ref = os.environ.get("ESLAM_REFERENCE", "/root/reference")
+    if not os.path.isdir(os.path.join(ref, "src")):
+        pytest.skip("the reference tree is not available here")
+    from conftest import ROOT
+
+    standins = os.path.join(ROOT, "oracle", "standins")
+    added = [p for p in (standins, ref) if p not in sys.path]
+    for p in added:
+        sys.path.insert(0, p)
+    try:
+        import src.Mapper as RM
+        import src.Tracker as RT
+        import src.networks.decoders as RD
+        import src.utils.Renderer as RR
+
+        ref_sigs = {"ot": inspect.signature(RT.Tracker.optimize_tracking), "om": inspect.signature(RM.Mapper.optimize_mapping),
+                    "ks": inspect.signature(RM.Mapper.keyframe_selection_overlap),
+                    "rb": inspect.signature(RR.Renderer.render_batch_ray), "ri": inspect.signature(RR.Renderer.render_img),
+                    "fw": inspect.signature(RD.Decoders.forward), "di": inspect.signature(RD.Decoders.__init__)}
+        import myslam_b200 as M
+
+        M.install("src")
+        assert RD.Decoders is M.Decoders and RR.Renderer is M.Renderer
+        assert RT.Tracker.optimize_tracking is M.tracker.optimize_tracking
+        assert RM.Mapper.optimize_mapping is M.mapper.optimize_mapping
+        new_sigs = {"ot": inspect.signature(RT.Tracker.optimize_tracking), "om": inspect.signature(RM.Mapper.optimize_mapping),
+                    "ks": inspect.signature(RM.Mapper.keyframe_selection_overlap),
+                    "rb": inspect.signature(M.Renderer.render_batch_ray), "ri": inspect.signature(M.Renderer.render_img),
+                    "fw": inspect.signature(M.Decoders.forward), "di": inspect.signature(M.Decoders.__init__)}
+        for k in ref_sigs:
+            assert list(ref_sigs[k].parameters) == list(new_sigs[k].parameters), (k, ref_sigs[k], new_sigs[k])
+    finally:
+        for p in added:
+            sys.path.remove(p)
+        for name in [n for n in sys.modules if n == "src" or n.startswith("src.")]:
+            del sys.modules[name]
