@@ -577,16 +577,39 @@ __global__ void __launch_bounds__(1024) k_track_mask(const __grid_constant__ Tra
       if ((kk & himask) == prefix) atomicAdd(&hist[(kk >> shift) & 255u], 1u);
     }
     __syncthreads();
-    if (t == 0) {
-      unsigned rank = s_rank, cum = 0u;
-      int b = 0;
-      for (; b < 256; ++b) {
-        if (cum + hist[b] > rank) break;
-        cum += hist[b];
+    if (t < 32) {  // warp 0: lane l owns bins 8l..8l+7; a warp scan finds the bin that holds rank s_rank
+      unsigned h[8], sum = 0u;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        h[i] = hist[t * 8 + i];
+        sum += h[i];
       }
-      if (b > 255) b = 255;
-      s_prefix = prefix | ((unsigned)b << shift);
-      s_rank = rank - cum;
+      unsigned incl = sum;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const unsigned n = __shfl_up_sync(0xffffffffu, incl, o);
+        if (t >= o) incl += n;
+      }
+      const unsigned excl = incl - sum, rank = s_rank;
+      const bool mine = rank >= excl && rank < incl;  // exactly one lane unless R == 0
+      const unsigned who = __ballot_sync(0xffffffffu, mine);
+      if (who == 0u) {
+        if (t == 31) {
+          s_prefix = prefix | (255u << shift);
+          s_rank = 0u;
+        }
+      } else if (mine) {
+        unsigned cum = excl;
+        int b = 0;
+#pragma unroll
+        for (; b < 8; ++b) {
+          if (cum + h[b] > rank) break;
+          cum += h[b];
+        }
+        if (b > 7) b = 7;
+        s_prefix = prefix | ((unsigned)(t * 8 + b) << shift);
+        s_rank = rank - cum;
+      }
     }
     __syncthreads();
   }
