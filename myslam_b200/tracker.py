@@ -224,11 +224,11 @@ class _FrameGraph:
     the parameter arena, a pose / loss / trace buffer, and a one-entry frame table whose two pointers are rewritten
     before every replay.  The random draws are torch's (its CUDA generator is graph safe)."""
 
-    def __init__(self, trk, st, store, gt_color, gt_depth, iters, batch_size, lr_T, lr_R):
+    def __init__(self, trk, st, store, init_pose, gt_color, gt_depth, iters, batch_size, lr_T, lr_R):
         ws, sc = st["ws"], st["sc"]
         dev = ws.device
         self.key = (iters, batch_size, lr_T, lr_R, store.arena.data_ptr(), id(ws))
-        self.pose = torch.zeros(1, 7, dtype=torch.float32, device=dev)
+        self.pose = init_pose.detach().float().reshape(1, 7).clone().contiguous()  # a valid pose for the warm-up pass
         self.losses = torch.zeros(iters, dtype=torch.float64, device=dev)
         self.trace = torch.zeros(iters, 7, dtype=torch.float32, device=dev)
         self.frames = FrameTable([gt_color[0]], [gt_depth[0]], sc.cam, dev)
@@ -291,7 +291,7 @@ def track_frame(self, init_pose, gt_color, gt_depth, iters=None, batch_size=None
         fg = st.get("graph")
         if fg is None or fg.key != key:
             _check_track_frames(gt_color, gt_depth, st["sc"].cam)
-            fg = _FrameGraph(self, st, store, gt_color, gt_depth, iters, batch_size, lr_T, lr_R)
+            fg = _FrameGraph(self, st, store, init_pose, gt_color, gt_depth, iters, batch_size, lr_T, lr_R)
             st["graph"] = fg
         _check_track_frames(gt_color, gt_depth, st["sc"].cam)
         trace, losses, pose = fg.run(init_pose, gt_color, gt_depth)

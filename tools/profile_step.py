@@ -54,6 +54,13 @@ def main():
     for rep in range(2):
         trk.track_frame(pose0, cols[:1].contiguous(), deps[:1].contiguous())
         torch.cuda.synchronize()
+    # a 16 M-point slab of the 1 cm marching-cubes lattice (config 5) for the grid-query kernel
+    from myslam_b200.mesher import grid_axes, query_grid_sdf
+
+    axes = grid_axes(spec["bound"], 0.01)
+    for rep in range(2):
+        query_grid_sdf(scene.all_planes, scene.decoders, axes, scene.bound, start=100_000_000, count=1 << 24)
+        torch.cuda.synchronize()
     print("profile_step done")
 
 
