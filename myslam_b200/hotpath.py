@@ -130,7 +130,8 @@ def _check_frames(depth, color, n_img, cam):
 
 
 def tracking_iteration(ws: Workspace, store: FieldStore, sc: StepCfg, pose7: torch.Tensor, gt_color, gt_depth,
-                       n_pixels: int, draws=None, strict_rng: bool = False, apply_adam: Optional[dict] = None):
+                       n_pixels: int, draws=None, strict_rng: bool = False, apply_adam: Optional[dict] = None,
+                       bind: bool = True):
     """One iteration of Tracker.optimize_tracking (Tracker.py:150-210) up to (and optionally including)
     the Adam step.  pose7: [1,7] contiguous fp32 device tensor (quaternion, translation).
     After the call: ws.loss_acc[5] = loss (float64), ws.grad7[0] = d loss / d pose.
@@ -143,7 +144,8 @@ def tracking_iteration(ws: Workspace, store: FieldStore, sc: StepCfg, pose7: tor
     n_crop = (cam.H1 - cam.H0) * (cam.W1 - cam.W0)
     _check_frames(gt_depth, gt_color, 1, cam)
     idx = draws.randint(n_crop, n_pixels)
-    store.bind()
+    if bind:  # the decoders are frozen while a frame is tracked: a caller looping over iterations binds once
+        store.bind()
     if not sc.perturb:
         u = None
     elif strict_rng:

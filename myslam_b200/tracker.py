@@ -236,10 +236,11 @@ class _FrameGraph:
         def body():
             ws.pose_m.zero_()
             ws.pose_v.zero_()
+            store.bind()
             for it in range(iters):
                 self.trace[it].copy_(self.pose[0])
                 tracking_iteration(ws, store, sc, self.pose, self.frames, self.frames, batch_size,
-                                   apply_adam={"step": it + 1, "lr_q": lr_R, "lr_t": lr_T})
+                                   apply_adam={"step": it + 1, "lr_q": lr_R, "lr_t": lr_T}, bind=False)
                 self.losses[it].copy_(ws.loss_acc[5])
 
         side = torch.cuda.Stream(device=dev)  # one eager pass first: lazy initialisations must not be captured
