@@ -253,6 +253,15 @@ int eslam_adam_step(float* param, float* grad, float* exp_avg, float* exp_avg_sq
                     const int64_t* seg_end_host, const double* seg_lr_host, int n_seg, int step, double beta1,
                     double beta2, double eps, eslam_stream_t s);
 
+/* eslam_adam_step that skips what torch's update leaves unchanged: touched[(n + 127) / 128] (zeroed by the caller
+ * together with the moments whenever the optimiser state is re-created) holds one flag per group of 128
+ * parameters, raised the first time any gradient of the group is non-zero.  Until then m = v = 0 and
+ * p - lr * 0 / (0 + eps) = p, so parameters, moments and the zero gradient of the group are neither read (beyond
+ * the gradient) nor written.  Bit-identical to eslam_adam_step. */
+int eslam_adam_step_sparse(float* param, float* grad, float* exp_avg, float* exp_avg_sq, int64_t n,
+                           const int64_t* seg_end_host, const double* seg_lr_host, int n_seg, int step,
+                           double beta1, double beta2, double eps, uint8_t* touched, eslam_stream_t s);
+
 /* cam_pose_to_matrix backward (common.py:169-181 with pytorch3d quaternion_to_matrix) for frames
  * [first, n): pose_grad[n][12] (d loss / d c2w[:3,:4]) -> grad7[n][7] = d loss / d (q,t) (may be NULL);
  * if apply: Adam step on poses[n][7] with lr_q / lr_t and state exp_avg/exp_avg_sq[n][7]; zeroes pose_grad. */

@@ -86,6 +86,8 @@ PROTOTYPES = {
     "eslam_loss_backward": [_FP, _P, _CP, _RP, _P, _P, _P, _P, _P, _P, _P, _I, _P, _P, _P, _I, _P, _P, _P, _P],
     "eslam_pose_backward_act": [_FP, _P, _CP, _RP, _P, _P, _P, _P, _P, _P, _P, _I, _P, _P, _I, _P, _P, _P, _P, _P, _P],
     "eslam_adam_step": [_P, _P, _P, _P, _L, C.POINTER(C.c_int64), C.POINTER(C.c_double), _I, _I, _D, _D, _D, _P],
+    "eslam_adam_step_sparse": [_P, _P, _P, _P, _L, C.POINTER(C.c_int64), C.POINTER(C.c_double), _I, _I, _D, _D, _D, _P,
+                               _P],
     "eslam_pose_adam_step": [_P, _P, _P, _P, _I, _I, _D, _D, _I, _D, _D, _D, _P, _I, _P],
     "eslam_finalize_loss": [_RP, _P, _I, _P, _P, _P],
     "eslam_ingest_frame": [_P, _P, _I, _I, _I, _D, _D, _P, _P, _P],

@@ -650,11 +650,12 @@ static int fill_adam(AdamArgs& a, int64_t n, const int64_t* seg_end, const doubl
   return 0;
 }
 
-int eslam_adam_step(float* param, float* grad, float* exp_avg, float* exp_avg_sq, int64_t n,
-                    const int64_t* seg_end, const double* seg_lr, int n_seg, int step, double beta1, double beta2,
-                    double eps, eslam_stream_t s) {
+static int adam_step_impl(float* param, float* grad, float* exp_avg, float* exp_avg_sq, int64_t n,
+                          const int64_t* seg_end, const double* seg_lr, int n_seg, int step, double beta1, double beta2,
+                          double eps, uint8_t* touched, eslam_stream_t s) {
   REQUIRE(param && grad && exp_avg && exp_avg_sq, "eslam_adam_step");
   AdamArgs a;
+  a.touched = touched;
   a.p = param;
   a.g = grad;
   a.m = exp_avg;
@@ -666,6 +667,19 @@ int eslam_adam_step(float* param, float* grad, float* exp_avg, float* exp_avg_sq
   k_adam<<<(unsigned)blocks, 256, 0, S_(s)>>>(a);
   CHECK_LAUNCH("eslam_adam_step");
   return 0;
+}
+
+int eslam_adam_step(float* param, float* grad, float* exp_avg, float* exp_avg_sq, int64_t n,
+                    const int64_t* seg_end, const double* seg_lr, int n_seg, int step, double beta1, double beta2,
+                    double eps, eslam_stream_t s) {
+  return adam_step_impl(param, grad, exp_avg, exp_avg_sq, n, seg_end, seg_lr, n_seg, step, beta1, beta2, eps, nullptr, s);
+}
+
+int eslam_adam_step_sparse(float* param, float* grad, float* exp_avg, float* exp_avg_sq, int64_t n,
+                           const int64_t* seg_end, const double* seg_lr, int n_seg, int step, double beta1,
+                           double beta2, double eps, uint8_t* touched, eslam_stream_t s) {
+  REQUIRE(touched, "eslam_adam_step_sparse");
+  return adam_step_impl(param, grad, exp_avg, exp_avg_sq, n, seg_end, seg_lr, n_seg, step, beta1, beta2, eps, touched, s);
 }
 
 static int fill_peers(PeerSync& ps, const eslam_peers_t* p) {

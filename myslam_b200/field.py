@@ -110,6 +110,7 @@ class FieldStore:
         self.grad: Optional[torch.Tensor] = None
         self.exp_avg: Optional[torch.Tensor] = None
         self.exp_avg_sq: Optional[torch.Tensor] = None
+        self.touched: Optional[torch.Tensor] = None  # one flag per 128 parameters: any non-zero gradient since reset
         self._sig = None  # (data_ptr, version) of what was last pulled
 
     # ------------------------------------------------------------------ construction helpers
@@ -203,9 +204,11 @@ class FieldStore:
         if self.exp_avg is None:
             self.exp_avg = torch.zeros_like(self.arena)
             self.exp_avg_sq = torch.zeros_like(self.arena)
+            self.touched = torch.zeros((self.n_floats + 127) // 128, dtype=torch.uint8, device=self.device)
         else:
             self.exp_avg.zero_()
             self.exp_avg_sq.zero_()
+            self.touched.zero_()
         self.ensure_grad().zero_()
 
     def adam_step(self, step: int, lr_dec: float, lr_planes: float, lr_cplanes: float, betas=(0.9, 0.999),
@@ -213,5 +216,5 @@ class FieldStore:
         """One torch.optim.Adam step over planes (two lr groups) + decoders; zeroes the gradient arena."""
         seg_end = (C.c_int64 * 3)(self.n_sdf_end, self.n_planes_end, self.n_floats)
         seg_lr = (C.c_double * 3)(lr_planes, lr_cplanes, lr_dec)
-        call("eslam_adam_step", ptr(self.arena), ptr(self.grad), ptr(self.exp_avg), ptr(self.exp_avg_sq),
-             self.n_floats, seg_end, seg_lr, 3, step, betas[0], betas[1], eps, stream())
+        call("eslam_adam_step_sparse", ptr(self.arena), ptr(self.grad), ptr(self.exp_avg), ptr(self.exp_avg_sq),
+             self.n_floats, seg_end, seg_lr, 3, step, betas[0], betas[1], eps, ptr(self.touched), stream())

@@ -526,3 +526,41 @@ def test_optimize_tracking_iteration_graphs(monkeypatch):
             run_frame(trk, gc, torch.zeros_like(gd))
             assert int(trk._b200["ws"].counters[0]) == 0  # depth > 0 rays only: the new frame was read
     assert abs(means["0"] - means["1"]) < 0.25 * abs(means["0"])
+
+
+def test_sparse_adam_is_bit_identical_to_dense():
+    """eslam_adam_step_sparse skips groups of 128 parameters whose gradient has been zero since the optimiser was
+    created (torch's update leaves them unchanged); everything else -- parameters, moments, the zeroed gradient -- must
+    equal the dense kernel bit for bit, over steps in which groups wake up at different times."""
+    import ctypes as C
+    from myslam_b200._lib import call, ptr, stream
+
+    n = 128 * 700 + 64  # a ragged last group
+    g = torch.Generator().manual_seed(3)
+    p0 = torch.randn(n, generator=g)
+    seg_end, seg_lr = (C.c_int64 * 2)(128 * 300 + 4, n), (C.c_double * 2)(5e-3, 1e-3)
+    state = {k: [p0.clone().to(DEV), torch.zeros(n, device=DEV), torch.zeros(n, device=DEV)] for k in ("dense", "sparse")}
+    touched = torch.zeros((n + 127) // 128, dtype=torch.uint8, device=DEV)
+    awake = torch.zeros(n // 128 + 1, dtype=torch.bool)
+    for step in range(1, 7):
+        awake |= torch.rand(awake.shape, generator=g) < 0.2      # more groups receive gradients over time
+        grad = torch.randn(n, generator=g) * 0.1
+        grad[~awake.repeat_interleave(128)[:n]] = 0
+        grad[torch.rand(n, generator=g) < 0.3] = 0                  # zeros inside live groups too
+        if step == 4:
+            grad.zero_()                                            # a step without any gradient: momentum only
+        for kind in ("dense", "sparse"):
+            p, m, v = state[kind]
+            gd = grad.clone().to(DEV)
+            if kind == "dense":
+                call("eslam_adam_step", ptr(p), ptr(gd), ptr(m), ptr(v), n, seg_end, seg_lr, 2, step, 0.9, 0.999, 1e-8,
+                     stream())
+            else:
+                call("eslam_adam_step_sparse", ptr(p), ptr(gd), ptr(m), ptr(v), n, seg_end, seg_lr, 2, step, 0.9, 0.999,
+                     1e-8, ptr(touched), stream())
+            assert float(gd.abs().max()) == 0.0
+        for a, b in zip(state["dense"], state["sparse"]):
+            assert torch.equal(a, b), f"step {step}"
+    t = touched.cpu().bool()
+    assert 0 < int(t.sum()) < t.numel()
+    assert torch.equal(state["sparse"][0].cpu()[~t.repeat_interleave(128)[:n]], p0[~t.repeat_interleave(128)[:n]])
