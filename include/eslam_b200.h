@@ -336,13 +336,16 @@ int64_t eslam_exchange_stage_floats(int64_t n, int world);
  * (exp_avg / exp_avg_sq are local, only slice r is touched), zeroes its slice of `grad`, and stores the new
  * parameters into every rank's arena (P2P stores, or one multimem.st when mc_param != NULL); a closing handshake
  * makes the stores visible.  The local aux (float, pose gradients) / auxd (double, loss terms) blocks are
- * published, zeroed, and summed over all ranks into aux_sum / auxd_sum.  The call is identical on every rank. */
+ * published, zeroed, and summed over all ranks into aux_sum / auxd_sum.  The call is identical on every rank.
+ * Groups of 128 parameters whose gradient is zero on a rank are not sent (the staging must start zeroed; the
+ * owner clears what it consumes), and with `touched` (as in eslam_adam_step_sparse, local, may be NULL) groups no
+ * rank has touched since the optimiser was created are neither updated nor broadcast. */
 int eslam_adam_exchange(const eslam_peers_t* peers_host, float* const* param_host, float* const* stage_host,
                         float* grad, float* mc_param, float* exp_avg, float* exp_avg_sq, int64_t n,
                         const int64_t* seg_end_host, const double* seg_lr_host, int n_seg, int step, double beta1,
                         double beta2, double eps, float* aux_local, float* const* aux_pub_host, float* aux_sum,
                         int n_aux, double* auxd_local, double* const* auxd_pub_host, double* auxd_sum, int n_auxd,
-                        eslam_stream_t s);
+                        uint8_t* touched, eslam_stream_t s);
 
 #ifdef __cplusplus
 }

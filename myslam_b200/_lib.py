@@ -97,7 +97,7 @@ PROTOTYPES = {
     "eslam_exchange_counters": [C.POINTER(Peers), _P, C.POINTER(C.c_void_p), _I, _P, _P],
     "eslam_adam_exchange": [C.POINTER(Peers), C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), _P, _P, _P, _P, _L,
                             C.POINTER(C.c_int64), C.POINTER(C.c_double), _I, _I, _D, _D, _D, _P, C.POINTER(C.c_void_p),
-                            _P, _I, _P, C.POINTER(C.c_void_p), _P, _I, _P],
+                            _P, _I, _P, C.POINTER(C.c_void_p), _P, _I, _P, _P],
 }
 
 _lib = None

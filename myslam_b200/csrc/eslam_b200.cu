@@ -728,7 +728,7 @@ int eslam_adam_exchange(const eslam_peers_t* peers, float* const* param, float* 
                         float* mc_param, float* exp_avg, float* exp_avg_sq, int64_t n, const int64_t* seg_end,
                         const double* seg_lr, int n_seg, int step, double beta1, double beta2, double eps,
                         float* aux_local, float* const* aux_pub, float* aux_sum, int n_aux, double* auxd_local,
-                        double* const* auxd_pub, double* auxd_sum, int n_auxd, eslam_stream_t s) {
+                        double* const* auxd_pub, double* auxd_sum, int n_auxd, uint8_t* touched, eslam_stream_t s) {
   REQUIRE(param && stage && grad && exp_avg && exp_avg_sq && n_aux >= 0 && n_auxd >= 0, "eslam_adam_exchange");
   REQUIRE(n_aux == 0 || (aux_local && aux_pub && aux_sum), "eslam_adam_exchange(aux)");
   REQUIRE(n_auxd == 0 || (auxd_local && auxd_pub && auxd_sum), "eslam_adam_exchange(auxd)");
@@ -746,6 +746,7 @@ int eslam_adam_exchange(const eslam_peers_t* peers, float* const* param, float* 
     if (n_auxd) a.auxd_pub[r] = auxd_pub[r];
   }
   a.g = reinterpret_cast<float4*>(grad);
+  a.adam.touched = touched;
   a.mc_p = reinterpret_cast<float4*>(mc_param);
   a.m = reinterpret_cast<float4*>(exp_avg);
   a.v = reinterpret_cast<float4*>(exp_avg_sq);

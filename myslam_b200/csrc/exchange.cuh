@@ -178,16 +178,18 @@ __global__ void __launch_bounds__(EXCH_THREADS) k_grad_push(const __grid_constan
     long long lo, hi;
     slice_of(n4, world, q, lo, hi);
     float4* dst = a.stage[q] + (long long)rank * smax - lo;
-    for (long long i = lo + first; i < hi; i += 2 * stride) {
-      const long long i2 = i + stride;
-      const float4 v0 = a.g[i];
-      float4 v1 = z;
-      if (i2 < hi) v1 = a.g[i2];
-      dst[i] = v0;
-      a.g[i] = z;
-      if (i2 < hi) {
-        dst[i2] = v1;
-        a.g[i2] = z;
+    // Whole, globally aligned groups of 32 float4 (128 parameters) per warp and trip.  A group whose gradient is all
+    // zero on this rank is not sent: the owner keeps its staging rows zero (it clears what it consumes), and a
+    // mapping window only ever touches part of the planes, so most of the NVLink volume disappears.
+    const long long lo_a = lo & ~31ll, hi_r = (hi + 31) & ~31ll;
+    for (long long i = lo_a + first; i < hi_r; i += stride) {
+      const bool in = i >= lo && i < hi;
+      const float4 v = in ? a.g[i] : z;
+      const bool nz = v.x != 0.f || v.y != 0.f || v.z != 0.f || v.w != 0.f;
+      if (__ballot_sync(0xffffffffu, nz) == 0u) continue;
+      if (in) {
+        dst[i] = v;
+        a.g[i] = z;
       }
     }
   }
@@ -224,15 +226,35 @@ __global__ void __launch_bounds__(EXCH_THREADS) k_adam_exchange(const __grid_con
   slice_of(n4, world, rank, lo, hi);
   if (a.dbg & 8) hi = lo;
   float4* const p_own = a.p[rank];
-  const float4* const st_own = a.stage[rank] - lo;
+  float4* const st_own = a.stage[rank] - lo;
   const float4 z = f4_zero();
-  for (long long i = lo + first; i < hi; i += stride) {
+  unsigned char* const touched = a.adam.touched;
+  // Whole, globally aligned groups of 128 parameters per warp and trip (see k_grad_push).  A group in which no rank
+  // has had a non-zero gradient since the optimiser was created still has m = v = 0: torch's update leaves p as it
+  // is on every replica, so nothing is read beyond the gradients and nothing is stored or broadcast (k_adam).
+  const long long lo_a = lo & ~31ll, hi_r = (hi + 31) & ~31ll;
+  for (long long i = lo_a + first; i < hi_r; i += stride) {
+    const bool in = i >= lo && i < hi;
     float4 part[WMAX];
+    bool nz = false;
 #pragma unroll
     for (int q = 0; q < WMAX; ++q)
-      if (q < world) part[q] = (q == rank) ? a.g[i] : ld_sys_v4(st_own + q * smax + i);
+      if (q < world) {
+        part[q] = !in ? z : (q == rank) ? a.g[i] : ld_sys_v4(st_own + q * smax + i);
+        nz = nz || part[q].x != 0.f || part[q].y != 0.f || part[q].z != 0.f || part[q].w != 0.f;
+      }
+    const bool any = __ballot_sync(0xffffffffu, nz) != 0u;
+    const bool was = touched ? touched[i >> 5] != 0 : true;
+    if (!any && !was) continue;
+    if (touched && !was && (threadIdx.x & 31) == 0) touched[i >> 5] = 1;
+    if (!in) continue;
+    if (any) {  // consumed: the gradient arena and the staging rows go back to zero
+      a.g[i] = z;
+#pragma unroll
+      for (int q = 0; q < WMAX; ++q)
+        if (q < world && q != rank) st_own[q * smax + i] = z;
+    }
     float4 p = p_own[i], m = a.m[i], v = a.v[i];
-    a.g[i] = z;
     float4 g = part[0];
 #pragma unroll
     for (int q = 1; q < WMAX; ++q)

@@ -178,7 +178,8 @@ class PeerExchange(MappingExchange):
         call("eslam_adam_exchange", self._next_epoch(), self._param, self._stage, ptr(st.grad),
              self._mc if self.multimem else None, ptr(st.exp_avg), ptr(st.exp_avg_sq), st.n_floats, seg_end, seg_lr, 3,
              step, betas[0], betas[1], eps, ptr(pose_grad) if n_aux else None, self._pose[par], ptr(self.pose_sum),
-             n_aux, ptr(loss_acc) if n_auxd else None, self._loss[par], ptr(self.loss_sum), n_auxd, stream())
+             n_aux, ptr(loss_acc) if n_auxd else None, self._loss[par], ptr(self.loss_sum), n_auxd,
+             ptr(st.touched) if getattr(st, "touched", None) is not None else None, stream())
         return self.pose_sum, self.loss_sum
 
     def check(self) -> None:
