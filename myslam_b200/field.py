@@ -216,5 +216,7 @@ class FieldStore:
         """One torch.optim.Adam step over planes (two lr groups) + decoders; zeroes the gradient arena."""
         seg_end = (C.c_int64 * 3)(self.n_sdf_end, self.n_planes_end, self.n_floats)
         seg_lr = (C.c_double * 3)(lr_planes, lr_cplanes, lr_dec)
+        if self.exp_avg is None:
+            raise RuntimeError("FieldStore.adam_step before reset_adam(): there is no optimiser state")
         call("eslam_adam_step_sparse", ptr(self.arena), ptr(self.grad), ptr(self.exp_avg), ptr(self.exp_avg_sq),
              self.n_floats, seg_end, seg_lr, 3, step, betas[0], betas[1], eps, ptr(self.touched), stream())
