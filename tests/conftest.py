@@ -17,6 +17,12 @@ torch.backends.cudnn.allow_tf32 = False
 
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box)")
+    # the shared library is a build artefact (git-ignored): build it in-tree if this checkout does not have it yet
+    # (nvcc cross-compiles sm_100a without a GPU, ~35 s); the tests themselves never fall back to anything else
+    from myslam_b200.build import OUT, build_library
+
+    if not os.path.exists(OUT):
+        build_library()
 
 
 def pytest_collection_modifyitems(config, items):
