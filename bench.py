@@ -218,7 +218,9 @@ def extras(scene, rnd, spec, dev, rank, world, dist_on, poses, deps, hbm_peak):
                          "algorithmic_GBps_per_gpu": count * 3076 / (ms * 1e-3) / 1e9,
                          "frac_of_hbm_peak": count * 3076 / (ms * 1e-3) / 1e9 / hbm_peak,
                          "what": "Mesher.get_grid_uniform + eval_points (Mesher.py:130-186), SDF head only, coordinates "
-                                 "generated in-kernel, 3072 B gathered + 4 B written per point"}
+                                 "generated in-kernel; algorithmic bytes = 3072 B gathered + 4 B written per point "
+                                 "(the separable form resamples the planes once on the lattice's faces and reads "
+                                 "768 B per point)"}
     del buf
     if rank != 0:
         return out

@@ -136,6 +136,20 @@ int eslam_grid_sdf_hull(const eslam_field_t* field_host, const float* arena, con
                         const float* zs, int nx, int ny, int nz, int64_t start, int64_t count,
                         const float* hull_planes, int n_planes, float* sdf, eslam_stream_t s);
 
+/* Separable form of the lattice query: on the regular marching-cubes lattice every bilinear tap depends on two
+ * lattice indices only, feat(ix,iy,iz) = (Fxy[iy][ix] + Fxz[iz][ix]) + Fyz[iz][iy] per scale (decoders.py:82's
+ * order).  eslam_grid_features resamples the sdf decoder's three plane pairs ONCE on the lattice's faces with the
+ * arithmetic of the direct query (fxy[ny][nx][64], fxz[nz][nx][64], fyz[nz][ny][64] floats, caller-owned);
+ * eslam_grid_sdf_separable then evaluates [start, start+count) from them (three 256-byte reads per voxel instead
+ * of 24 corner fetches) and returns values bit-identical to eslam_grid_sdf / eslam_grid_sdf_hull (n_planes may
+ * be 0).  The features must be recomputed after the parameters change. */
+int eslam_grid_features(const eslam_field_t* field_host, const float* arena, const float* xs, const float* ys,
+                        const float* zs, int nx, int ny, int nz, float* fxy, float* fxz, float* fyz, eslam_stream_t s);
+int eslam_grid_sdf_separable(const eslam_field_t* field_host, const float* arena, const float* xs, const float* ys,
+                             const float* zs, int nx, int ny, int nz, int64_t start, int64_t count, const float* fxy,
+                             const float* fxz, const float* fyz, const float* hull_planes, int n_planes, float* sdf,
+                             eslam_stream_t s);
+
 /* ---- pixel pick, rays, bbox filter, depth-guided samples --------------------------------------- */
 /* get_samples + the bbox pre-filter + the depth>0 half of render_batch_ray's sampling
  * (src/common.py:87-153, src/Tracker.py:175-187, src/Mapper.py:322-332, src/utils/Renderer.py:81-106).

@@ -73,6 +73,8 @@ PROTOTYPES = {
     "eslam_sample_plane_feature": [_FP, _P, _P, _L, _I, _P, _P],
     "eslam_grid_sdf": [_FP, _P, _P, _P, _P, _I, _I, _I, _L, _L, _P, _P],
     "eslam_grid_sdf_hull": [_FP, _P, _P, _P, _P, _I, _I, _I, _L, _L, _P, _I, _P, _P],
+    "eslam_grid_features": [_FP, _P, _P, _P, _P, _I, _I, _I, _P, _P, _P, _P],
+    "eslam_grid_sdf_separable": [_FP, _P, _P, _P, _P, _I, _I, _I, _L, _L, _P, _P, _P, _P, _I, _P, _P],
     "eslam_sample_rays": [_FP, _CP, _RP, _P, _I, _I, _P, _P, _I, _P, _P, _P, _P, _P, _I, _P, _P, _P, _P, _P, _P, _P,
                           _P, _P, _P, _P, _P],
     "eslam_sample_rays_frames": [_FP, _CP, _RP, _P, _I, _I, _P, _P, _I, _P, _P, _P, _P, _P, _I, _P, _P, _P, _P, _P, _P,

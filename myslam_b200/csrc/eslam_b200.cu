@@ -176,7 +176,7 @@ int eslam_sample_plane_feature(const eslam_field_t* f, const float* arena, const
 
 static int grid_sdf_impl(const eslam_field_t* f, const float* arena, const float* xs, const float* ys, const float* zs,
                          int nx, int ny, int nz, int64_t start, int64_t count, const float* hull, int n_hull,
-                         float* sdf, eslam_stream_t s) {
+                         const float* fxy, const float* fxz, const float* fyz, float* sdf, eslam_stream_t s) {
   REQUIRE(f && arena && xs && ys && zs && sdf && nx > 0 && ny > 0 && nz > 0 && start >= 0 && count >= 0 &&
               start + count <= (int64_t)nx * ny * nz && n_hull >= 0 && (n_hull == 0 || hull),
           "eslam_grid_sdf");
@@ -188,7 +188,10 @@ static int grid_sdf_impl(const eslam_field_t* f, const float* arena, const float
   a.arena4 = reinterpret_cast<const float4*>(arena);
   a.n = count;
   a.sdf_out = sdf;
-  a.flags = 1 | 2 | (n_hull > 0 ? 8 : 0);
+  a.flags = 1 | 2 | (n_hull > 0 ? 8 : 0) | (fxy ? 16 : 0);
+  a.fxy = reinterpret_cast<const float4*>(fxy);
+  a.fxz = reinterpret_cast<const float4*>(fxz);
+  a.fyz = reinterpret_cast<const float4*>(fyz);
   a.hull = reinterpret_cast<const float4*>(hull);
   a.n_hull = n_hull;
   a.xs = xs;
@@ -205,14 +208,52 @@ static int grid_sdf_impl(const eslam_field_t* f, const float* arena, const float
 
 int eslam_grid_sdf(const eslam_field_t* f, const float* arena, const float* xs, const float* ys, const float* zs,
                    int nx, int ny, int nz, int64_t start, int64_t count, float* sdf, eslam_stream_t s) {
-  return grid_sdf_impl(f, arena, xs, ys, zs, nx, ny, nz, start, count, nullptr, 0, sdf, s);
+  return grid_sdf_impl(f, arena, xs, ys, zs, nx, ny, nz, start, count, nullptr, 0, nullptr, nullptr, nullptr, sdf, s);
 }
 
 int eslam_grid_sdf_hull(const eslam_field_t* f, const float* arena, const float* xs, const float* ys, const float* zs,
                         int nx, int ny, int nz, int64_t start, int64_t count, const float* hull_planes, int n_planes,
                         float* sdf, eslam_stream_t s) {
   REQUIRE(hull_planes && n_planes > 0, "eslam_grid_sdf_hull");
-  return grid_sdf_impl(f, arena, xs, ys, zs, nx, ny, nz, start, count, hull_planes, n_planes, sdf, s);
+  return grid_sdf_impl(f, arena, xs, ys, zs, nx, ny, nz, start, count, hull_planes, n_planes, nullptr, nullptr, nullptr,
+                       sdf, s);
+}
+
+int eslam_grid_features(const eslam_field_t* f, const float* arena, const float* xs, const float* ys, const float* zs,
+                        int nx, int ny, int nz, float* fxy, float* fxz, float* fyz, eslam_stream_t s) {
+  REQUIRE(f && arena && xs && ys && zs && fxy && fxz && fyz && nx > 0 && ny > 0 && nz > 0, "eslam_grid_features");
+  REQUIRE(nx <= 32767 && ny <= 32767 && nz <= 32767, "eslam_grid_features(lattice size)");
+  GridFeatArgs a;
+  memset(&a, 0, sizeof(a));
+  int rc = make_field_k(f, &a.fk);
+  if (rc) return fail(rc, "eslam_grid_features(field)");
+  a.arena4 = reinterpret_cast<const float4*>(arena);
+  const float* us[3] = {xs, xs, ys};
+  const float* vs[3] = {ys, zs, zs};
+  const int na[3] = {nx, nx, ny}, nb[3] = {ny, nz, nz}, ua[3] = {0, 0, 1}, va[3] = {1, 2, 2};
+  float* out[3] = {fxy, fxz, fyz};
+  for (int p = 0; p < 3; ++p) {
+    a.us = us[p];
+    a.vs = vs[p];
+    a.na = na[p];
+    a.nb = nb[p];
+    a.plane = p;
+    a.ua = ua[p];
+    a.va = va[p];
+    a.out = reinterpret_cast<float4*>(out[p]);
+    const long long n = (long long)na[p] * nb[p];
+    k_grid_features<<<(unsigned)((n + 31) / 32), 256, 0, S_(s)>>>(a);
+    CHECK_LAUNCH("eslam_grid_features");
+  }
+  return 0;
+}
+
+int eslam_grid_sdf_separable(const eslam_field_t* f, const float* arena, const float* xs, const float* ys,
+                             const float* zs, int nx, int ny, int nz, int64_t start, int64_t count, const float* fxy,
+                             const float* fxz, const float* fyz, const float* hull_planes, int n_planes, float* sdf,
+                             eslam_stream_t s) {
+  REQUIRE(fxy && fxz && fyz && nx <= 32767 && ny <= 32767 && nz <= 32767, "eslam_grid_sdf_separable");
+  return grid_sdf_impl(f, arena, xs, ys, zs, nx, ny, nz, start, count, hull_planes, n_planes, fxy, fxz, fyz, sdf, s);
 }
 
 static int sample_rays_impl(const eslam_field_t* f, const eslam_camera_t* cam, const eslam_render_cfg_t* cfg,

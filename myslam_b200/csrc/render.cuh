@@ -110,7 +110,51 @@ struct DecodeArgs {
   long long start;
   const float4* hull;  // flags bit3: n_hull half-spaces (nx, ny, nz, d), inside iff n.p + d <= 0 for all of them
   int n_hull;
+  // flags bit4 (grid mode, sdf only): per-plane features resampled once on the lattice's three faces (k_grid_features)
+  const float4 *fxy, *fxz, *fyz;  // [ny][nx][16], [nz][nx][16], [nz][ny][16] float4 (coarse | fine)
 };
+
+// ---------------------------------------------------------------------------------------------------
+// separable lattice query ("mesh query separability")
+// ---------------------------------------------------------------------------------------------------
+// On the regular marching-cubes lattice every bilinear tap depends on two lattice indices only:
+//   feat(ix, iy, iz) = (Fxy[iy][ix] + Fxz[iz][ix]) + Fyz[iz][iy]      per scale, in decoders.py:82's order,
+// so the three planes are resampled ONCE on the lattice's faces (this kernel: the same tap arithmetic as
+// gather_features, hence bit-identical features) and a voxel costs three 256-byte reads and two adds per channel
+// instead of 24 corner fetches and their interpolation.
+struct GridFeatArgs {
+  FieldK fk;
+  const float4* arena4;
+  const float *us, *vs;  // lattice coordinates along the plane's first (W) and second (H) axis
+  int na, nb, plane, ua, va;
+  float4* out;           // [nb][na][16]
+};
+
+__global__ void __launch_bounds__(256) k_grid_features(const __grid_constant__ GridFeatArgs a) {
+  const long long idx = (long long)blockIdx.x * 32 + (threadIdx.x >> 3);
+  const int sub = threadIdx.x & 7;
+  if (idx >= (long long)a.na * a.nb) return;
+  const int ia = (int)(idx % a.na), ib = (int)(idx / a.na);
+  const float pu = normalize_axis(a.us[ia], a.fk.lo[a.ua], a.fk.hi[a.ua]);
+  const float pv = normalize_axis(a.vs[ib], a.fk.lo[a.va], a.fk.hi[a.va]);
+#pragma unroll
+  for (int s = 0; s < 2; ++s) {
+    int u0, v0;
+    float fu, fv;
+    axis_setup(pu, axis_size(a.fk, s, a.ua), u0, fu);
+    axis_setup(pv, axis_size(a.fk, s, a.va), v0, fv);
+    const Tap t = make_tap(a.fk.pl[s * 3 + a.plane], u0, fu, v0, fv, sub);
+    const float4 v00 = ldg4(a.arena4 + t.base), v01 = ldg4(a.arena4 + t.base + t.dx);
+    const float4 v10 = ldg4(a.arena4 + t.base + t.dy), v11 = ldg4(a.arena4 + t.base + t.dy + t.dx);
+    const float w00 = (1.f - fu) * (1.f - fv), w01 = fu * (1.f - fv), w10 = (1.f - fu) * fv, w11 = fu * fv;
+    float4 tap = f4_mul(w00, v00);
+    tap = f4_fma(w01, v01, tap);
+    tap = f4_fma(w10, v10, tap);
+    tap = f4_fma(w11, v11, tap);
+    a.out[idx * 16 + s * 8 + sub] = tap;
+  }
+}
+
 
 __global__ void __launch_bounds__(NP) k_decode(const __grid_constant__ DecodeArgs a) {
   __shared__ SmemFwd sm;
@@ -154,9 +198,34 @@ __global__ void __launch_bounds__(NP) k_decode(const __grid_constant__ DecodeArg
     return;
   }
   // sdf decoder
-  write_axis_setups<2>(a.fk, 0, pn, sm.ax_i, sm.ax_f, q);
-  __syncthreads();
-  gather_tile<0>(a.fk, 0, a.arena4, sm.ax_i, sm.ax_f, sm.F, n_valid);
+  if (a.flags & 16) {  // separable lattice: sum the three resampled faces (k_grid_features)
+    const long long f = a.start + gi;
+    const long long t = f / a.nz;
+    sm.ax_i[0][q] = (ax_t)(valid ? (int)(t % a.nx) : 0);
+    sm.ax_i[1][q] = (ax_t)(valid ? (int)(t / a.nx) : 0);
+    sm.ax_i[2][q] = (ax_t)(valid ? (int)(f % a.nz) : 0);
+    __syncthreads();
+    const int warp = q >> 5, lane = q & 31, grp = lane >> 3, sub = lane & 7;
+#pragma unroll 2
+    for (int it = 0; it < 8; ++it) {
+      const int qq = warp * 32 + it * 4 + grp;
+      float4 fc = f4_zero(), ff = f4_zero();
+      if (qq < n_valid) {
+        const int ix = sm.ax_i[0][qq], iy = sm.ax_i[1][qq], iz = sm.ax_i[2][qq];
+        const float4* pxy = a.fxy + ((long long)iy * a.nx + ix) * 16 + sub;
+        const float4* pxz = a.fxz + ((long long)iz * a.nx + ix) * 16 + sub;
+        const float4* pyz = a.fyz + ((long long)iz * a.ny + iy) * 16 + sub;
+        fc = f4_add(f4_add(ldg4(pxy), ldg4(pxz)), ldg4(pyz));  // (xy + xz) + yz, decoders.py:82
+        ff = f4_add(f4_add(ldg4(pxy + 8), ldg4(pxz + 8)), ldg4(pyz + 8));
+      }
+      sm.F[f_slot(qq, sub)] = fc;
+      sm.F[f_slot(qq, 8 + sub)] = ff;
+    }
+  } else {
+    write_axis_setups<2>(a.fk, 0, pn, sm.ax_i, sm.ax_f, q);
+    __syncthreads();
+    gather_tile<0>(a.fk, 0, a.arena4, sm.ax_i, sm.ax_f, sm.F, n_valid);
+  }
   __syncthreads();
   float h1[16], h2[16], os[1];
   mlp_forward<S_W1, S_B1, S_W2, S_B2, S_W3, S_B3, 1>(sm.F, q, h1, h2, os);

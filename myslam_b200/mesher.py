@@ -4,6 +4,8 @@ coordinates generated on the device and only the SDF head evaluated for the volu
 """
 from __future__ import annotations
 
+import os
+
 import numpy as np
 import torch
 
@@ -45,11 +47,14 @@ def hull_planes(vertices, faces) -> torch.Tensor:
     return torch.from_numpy(np.concatenate([n, d[:, None]], 1).astype(np.float32))
 
 
-def query_grid_sdf(all_planes, decoders, axes, bound=None, start=0, count=None, chunk=1 << 24, out=None, hull=None):
+def query_grid_sdf(all_planes, decoders, axes, bound=None, start=0, count=None, chunk=1 << 24, out=None, hull=None,
+                   separable=None):
     """SDF on the flat index range [start, start+count) of the marching-cubes lattice
     (flat = (iy*nx + ix)*nz + iz, Mesher.py:179-184), coordinates generated in-kernel.
     Shard over GPUs by giving each rank its own [start, count).  hull: optional [F,4] half-spaces (hull_planes) of
-    the mesh bound; points outside get sdf = -1 in the same pass (Mesher.py:210-217)."""
+    the mesh bound; points outside get sdf = -1 in the same pass (Mesher.py:210-217).
+    separable (default: on when the three resampled faces fit 4 GB): the plane features are resampled once on the
+    lattice's faces and each voxel sums three of them (bit-identical values, eslam_grid_sdf_separable)."""
     store = synced_store(all_planes, decoders, bound)
     dev = store.device
     xs, ys, zs = (torch.from_numpy(np.asarray(a)).float().to(dev) for a in axes)
@@ -60,10 +65,22 @@ def query_grid_sdf(all_planes, decoders, axes, bound=None, start=0, count=None, 
         out = torch.empty(count, dtype=torch.float32, device=dev)
     if hull is not None:
         hull = hull.to(device=dev, dtype=torch.float32).contiguous()
+    face_bytes = 256 * (nx * ny + nx * nz + ny * nz)
+    if separable is None:
+        separable = face_bytes <= (4 << 30) and os.environ.get("ESLAM_B200_SEPARABLE", "1") == "1"
+    faces = None
+    if separable and max(nx, ny, nz) <= 32767:
+        faces = [torch.empty(b, a, 64, dtype=torch.float32, device=dev) for a, b in ((nx, ny), (nx, nz), (ny, nz))]
+        call("eslam_grid_features", store.ref(), ptr(store.arena), ptr(xs), ptr(ys), ptr(zs), nx, ny, nz, ptr(faces[0]),
+             ptr(faces[1]), ptr(faces[2]), stream())
     done = 0
     while done < count:
         n = min(chunk, count - done)
-        if hull is None:
+        if faces is not None:
+            call("eslam_grid_sdf_separable", store.ref(), ptr(store.arena), ptr(xs), ptr(ys), ptr(zs), nx, ny, nz,
+                 start + done, n, ptr(faces[0]), ptr(faces[1]), ptr(faces[2]), ptr(hull) if hull is not None else None,
+                 hull.shape[0] if hull is not None else 0, out[done:done + n].data_ptr(), stream())
+        elif hull is None:
             call("eslam_grid_sdf", store.ref(), ptr(store.arena), ptr(xs), ptr(ys), ptr(zs), nx, ny, nz, start + done,
                  n, out[done:done + n].data_ptr(), stream())
         else:

@@ -190,8 +190,11 @@ def test_grid_query_with_convex_mesh_bound():
     hp = hull_planes(pts, hull.simplices)
     assert hp.shape == (len(hull.simplices), 4)
     axes = grid_axes(b, 0.03)
-    plain = query_grid_sdf(planes, mp.decoders, axes, fld.bound).cpu()
-    bounded = query_grid_sdf(planes, mp.decoders, axes, fld.bound, hull=hp).cpu()
+    plain = query_grid_sdf(planes, mp.decoders, axes, fld.bound, separable=False).cpu()
+    bounded = query_grid_sdf(planes, mp.decoders, axes, fld.bound, hull=hp, separable=False).cpu()
+    # the separable form (plane features resampled once on the lattice's faces) is bit-identical to the direct one
+    assert torch.equal(query_grid_sdf(planes, mp.decoders, axes, fld.bound, separable=True).cpu(), plain)
+    assert torch.equal(query_grid_sdf(planes, mp.decoders, axes, fld.bound, hull=hp, separable=True).cpu(), bounded)
     gx, gy, gz = np.meshgrid(*axes, indexing="xy")  # Mesher.get_grid_uniform's point order
     p = np.stack([gx.reshape(-1), gy.reshape(-1), gz.reshape(-1)], 1)
     margin = (p @ hp[:, :3].double().numpy().T + hp[:, 3].double().numpy()).max(1)  # <= 0 inside
