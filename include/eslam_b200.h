@@ -150,6 +150,22 @@ int eslam_grid_sdf_separable(const eslam_field_t* field_host, const float* arena
                              const float* fxz, const float* fyz, const float* hull_planes, int n_planes, float* sdf,
                              eslam_stream_t s);
 
+/* Factored form of the lattice query (Mesher.py:159-186 with decoders.py:109-118's first layer pulled through the
+ * sum of decoders.py:82): the first layer is linear in the summed feature, so
+ *   W1 (Fxy + Fxz + Fyz) + b1 = (W1 Fxy + b1) + W1 Fxz + W1 Fyz.
+ * eslam_grid_preact resamples the sdf decoder's plane pairs on the lattice's faces and applies W1 there
+ * (caller-owned pxy[ny][nx][16], pxz[nx][4][nz][4], pyz[ny][4][nz][4] floats: 16 values per face texel, the z-major
+ * faces split into four float4 components so a warp walking z reads coalesced rows); eslam_grid_sdf_factored then
+ * evaluates [start, start+count): three 64-byte reads, 32 adds and the 16 -> 16 -> 1 tail per voxel.  Values agree with
+ * eslam_grid_sdf / _hull to a few ulp of the first layer's pre-activation (re-associated sum: NOT bit-identical;
+ * the tests hold 1e-5 against the direct form and 1e-4 against the reference).  n_planes may be 0.  The faces must
+ * be recomputed after the parameters change; layers 2-3 read the decoders bound by eslam_bind_decoders. */
+int eslam_grid_preact(const eslam_field_t* field_host, const float* arena, const float* xs, const float* ys,
+                      const float* zs, int nx, int ny, int nz, float* pxy, float* pxz, float* pyz, eslam_stream_t s);
+int eslam_grid_sdf_factored(const eslam_field_t* field_host, const float* xs, const float* ys, const float* zs, int nx,
+                            int ny, int nz, int64_t start, int64_t count, const float* pxy, const float* pxz,
+                            const float* pyz, const float* hull_planes, int n_planes, float* sdf, eslam_stream_t s);
+
 /* ---- pixel pick, rays, bbox filter, depth-guided samples --------------------------------------- */
 /* get_samples + the bbox pre-filter + the depth>0 half of render_batch_ray's sampling
  * (src/common.py:87-153, src/Tracker.py:175-187, src/Mapper.py:322-332, src/utils/Renderer.py:81-106).

@@ -256,6 +256,71 @@ int eslam_grid_sdf_separable(const eslam_field_t* f, const float* arena, const f
   return grid_sdf_impl(f, arena, xs, ys, zs, nx, ny, nz, start, count, hull_planes, n_planes, fxy, fxz, fyz, sdf, s);
 }
 
+int eslam_grid_preact(const eslam_field_t* f, const float* arena, const float* xs, const float* ys, const float* zs,
+                      int nx, int ny, int nz, float* pxy, float* pxz, float* pyz, eslam_stream_t s) {
+  REQUIRE(f && arena && xs && ys && zs && pxy && pxz && pyz && nx > 0 && ny > 0 && nz > 0, "eslam_grid_preact");
+  REQUIRE(nx <= 32767 && ny <= 32767 && nz <= 32767, "eslam_grid_preact(lattice size)");
+  GridPreArgs a;
+  memset(&a, 0, sizeof(a));
+  int rc = make_field_k(f, &a.fk);
+  if (rc) return fail(rc, "eslam_grid_preact(field)");
+  a.arena4 = reinterpret_cast<const float4*>(arena);
+  a.w1 = arena + f->dec_offset + S_W1;
+  const float* us[3] = {xs, xs, ys};
+  const float* vs[3] = {ys, zs, zs};
+  const int na[3] = {nx, nx, ny}, nb[3] = {ny, nz, nz}, ua[3] = {0, 0, 1}, va[3] = {1, 2, 2};
+  float* out[3] = {pxy, pxz, pyz};
+  for (int p = 0; p < 3; ++p) {
+    a.us = us[p];
+    a.vs = vs[p];
+    a.na = na[p];
+    a.nb = nb[p];
+    a.plane = p;
+    a.ua = ua[p];
+    a.va = va[p];
+    a.zmajor = p > 0;
+    a.out = reinterpret_cast<float4*>(out[p]);
+    const long long n = (long long)na[p] * nb[p];
+    const long long want = (n + 127) / 128;  // >= 4 trips per CTA amortise the 4 KB copy of W1
+    k_grid_preact<<<(unsigned)(want < 1 ? 1 : want), 256, 0, S_(s)>>>(a);
+    CHECK_LAUNCH("eslam_grid_preact");
+  }
+  return 0;
+}
+
+int eslam_grid_sdf_factored(const eslam_field_t* f, const float* xs, const float* ys, const float* zs, int nx, int ny,
+                            int nz, int64_t start, int64_t count, const float* pxy, const float* pxz, const float* pyz,
+                            const float* hull_planes, int n_planes, float* sdf, eslam_stream_t s) {
+  REQUIRE(f && xs && ys && zs && pxy && pxz && pyz && sdf && nx > 0 && ny > 0 && nz > 0 && start >= 0 && count >= 0 &&
+              nx <= 32767 && ny <= 32767 && nz <= 32767 && start + count <= (int64_t)nx * ny * nz && n_planes >= 0 &&
+              (n_planes == 0 || hull_planes),
+          "eslam_grid_sdf_factored");
+  if (count == 0) return 0;
+  GridFacArgs a;
+  memset(&a, 0, sizeof(a));
+  for (int k = 0; k < 3; ++k) {
+    a.lo[k] = f->bound[k][0];
+    a.hi[k] = f->bound[k][1];
+  }
+  a.xs = xs;
+  a.ys = ys;
+  a.zs = zs;
+  a.nx = nx;
+  a.ny = ny;
+  a.nz = nz;
+  a.start = start;
+  a.n = count;
+  a.pxy = reinterpret_cast<const float4*>(pxy);
+  a.pxz = reinterpret_cast<const float4*>(pxz);
+  a.pyz = reinterpret_cast<const float4*>(pyz);
+  a.hull = reinterpret_cast<const float4*>(hull_planes);
+  a.n_hull = n_planes;
+  a.sdf_out = sdf;
+  k_grid_sdf_factored<<<(unsigned)((count + FAC_THREADS - 1) / FAC_THREADS), FAC_THREADS, 0, S_(s)>>>(a);
+  CHECK_LAUNCH("eslam_grid_sdf_factored");
+  return 0;
+}
+
 static int sample_rays_impl(const eslam_field_t* f, const eslam_camera_t* cam, const eslam_render_cfg_t* cfg,
                             const int64_t* pix_idx, int n_img, int n_per_img, const float* c2w, const float* poses,
                             int pose_first, const float* depth, const double* color, bool frame_table,

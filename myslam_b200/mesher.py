@@ -48,13 +48,21 @@ def hull_planes(vertices, faces) -> torch.Tensor:
 
 
 def query_grid_sdf(all_planes, decoders, axes, bound=None, start=0, count=None, chunk=1 << 24, out=None, hull=None,
-                   separable=None):
+                   separable=None, factored=None):
     """SDF on the flat index range [start, start+count) of the marching-cubes lattice
     (flat = (iy*nx + ix)*nz + iz, Mesher.py:179-184), coordinates generated in-kernel.
     Shard over GPUs by giving each rank its own [start, count).  hull: optional [F,4] half-spaces (hull_planes) of
     the mesh bound; points outside get sdf = -1 in the same pass (Mesher.py:210-217).
-    separable (default: on when the three resampled faces fit 4 GB): the plane features are resampled once on the
-    lattice's faces and each voxel sums three of them (bit-identical values, eslam_grid_sdf_separable)."""
+
+    Three forms of the same query:
+      direct     every voxel gathers its 24 plane corners (eslam_grid_sdf / _hull);
+      separable  the plane features are resampled once on the lattice's faces and a voxel sums three of them:
+                 bit-identical to the direct form (eslam_grid_features + eslam_grid_sdf_separable);
+      factored   the decoder's (linear) first layer is applied on the faces as well, a voxel adds three 16-vectors and
+                 runs the 16->16->1 tail: equal to the direct form up to the re-association of the first layer's sum
+                 (tests: 1e-5; eslam_grid_preact + eslam_grid_sdf_factored).
+    Default: factored (ESLAM_B200_FACTORED=0 selects separable, ESLAM_B200_SEPARABLE=0 as well selects direct);
+    an explicit separable=True/False asks for that bit-exact form."""
     store = synced_store(all_planes, decoders, bound)
     dev = store.device
     xs, ys, zs = (torch.from_numpy(np.asarray(a)).float().to(dev) for a in axes)
@@ -65,26 +73,41 @@ def query_grid_sdf(all_planes, decoders, axes, bound=None, start=0, count=None, 
         out = torch.empty(count, dtype=torch.float32, device=dev)
     if hull is not None:
         hull = hull.to(device=dev, dtype=torch.float32).contiguous()
-    face_bytes = 256 * (nx * ny + nx * nz + ny * nz)
+    hull_p = ptr(hull) if hull is not None else None
+    hull_n = hull.shape[0] if hull is not None else 0
+    fits = max(nx, ny, nz) <= 32767 and 256 * (nx * ny + nx * nz + ny * nz) <= (4 << 30)
+    if factored is None:
+        factored = separable is None and os.environ.get("ESLAM_B200_FACTORED", "1") == "1"
     if separable is None:
-        separable = face_bytes <= (4 << 30) and os.environ.get("ESLAM_B200_SEPARABLE", "1") == "1"
+        separable = os.environ.get("ESLAM_B200_SEPARABLE", "1") == "1"
     faces = None
-    if separable and max(nx, ny, nz) <= 32767:
+    if factored and fits:
+        mode = "factored"
+        faces = [torch.empty(n, dtype=torch.float32, device=dev) for n in (ny * nx * 16, nx * nz * 16, ny * nz * 16)]
+        call("eslam_grid_preact", store.ref(), ptr(store.arena), ptr(xs), ptr(ys), ptr(zs), nx, ny, nz, ptr(faces[0]),
+             ptr(faces[1]), ptr(faces[2]), stream())
+    elif separable and fits:
+        mode = "separable"
         faces = [torch.empty(b, a, 64, dtype=torch.float32, device=dev) for a, b in ((nx, ny), (nx, nz), (ny, nz))]
         call("eslam_grid_features", store.ref(), ptr(store.arena), ptr(xs), ptr(ys), ptr(zs), nx, ny, nz, ptr(faces[0]),
              ptr(faces[1]), ptr(faces[2]), stream())
+    else:
+        mode = "direct" if hull is None else "hull"
     done = 0
     while done < count:
         n = min(chunk, count - done)
-        if faces is not None:
+        dst = out[done:done + n].data_ptr()
+        if mode == "factored":
+            call("eslam_grid_sdf_factored", store.ref(), ptr(xs), ptr(ys), ptr(zs), nx, ny, nz, start + done, n,
+                 ptr(faces[0]), ptr(faces[1]), ptr(faces[2]), hull_p, hull_n, dst, stream())
+        elif mode == "separable":
             call("eslam_grid_sdf_separable", store.ref(), ptr(store.arena), ptr(xs), ptr(ys), ptr(zs), nx, ny, nz,
-                 start + done, n, ptr(faces[0]), ptr(faces[1]), ptr(faces[2]), ptr(hull) if hull is not None else None,
-                 hull.shape[0] if hull is not None else 0, out[done:done + n].data_ptr(), stream())
-        elif hull is None:
+                 start + done, n, ptr(faces[0]), ptr(faces[1]), ptr(faces[2]), hull_p, hull_n, dst, stream())
+        elif mode == "direct":
             call("eslam_grid_sdf", store.ref(), ptr(store.arena), ptr(xs), ptr(ys), ptr(zs), nx, ny, nz, start + done,
-                 n, out[done:done + n].data_ptr(), stream())
+                 n, dst, stream())
         else:
             call("eslam_grid_sdf_hull", store.ref(), ptr(store.arena), ptr(xs), ptr(ys), ptr(zs), nx, ny, nz,
-                 start + done, n, ptr(hull), hull.shape[0], out[done:done + n].data_ptr(), stream())
+                 start + done, n, hull_p, hull_n, dst, stream())
         done += n
     return out

@@ -204,6 +204,15 @@ def test_grid_query_with_convex_mesh_bound():
     assert (bounded[sure_out] == -1.0).all()
     # sharded ranges give the same lattice values
     n = bounded.numel()
-    parts = [query_grid_sdf(planes, mp.decoders, axes, fld.bound, start=s, count=c, hull=hp).cpu()
+    parts = [query_grid_sdf(planes, mp.decoders, axes, fld.bound, start=s, count=c, hull=hp, separable=True).cpu()
              for s, c in ((0, n // 3), (n // 3, n - n // 3))]
     assert torch.equal(torch.cat(parts), bounded)
+    # the factored form (first layer applied on the faces) re-associates one sum: same mask, values within 1e-5
+    fac = query_grid_sdf(planes, mp.decoders, axes, fld.bound, factored=True).cpu()
+    fac_b = query_grid_sdf(planes, mp.decoders, axes, fld.bound, hull=hp, factored=True).cpu()
+    assert (fac - plain).abs().max().item() < 1e-5 and (fac_b - bounded).abs().max().item() < 1e-5
+    assert torch.equal(fac_b == -1.0, bounded == -1.0)
+    cuts = (0, 77, n // 3 + 5, n - 300, n)  # ragged ranges: CTAs straddle z columns and range ends
+    parts = [query_grid_sdf(planes, mp.decoders, axes, fld.bound, start=a, count=b - a, hull=hp, factored=True).cpu()
+             for a, b in zip(cuts[:-1], cuts[1:])]
+    assert torch.equal(torch.cat(parts), fac_b)
