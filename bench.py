@@ -218,11 +218,11 @@ def extras(scene, rnd, spec, dev, rank, world, dist_on, poses, deps, hbm_peak):
              "direct_ms": time_region(q(separable=False), 3, 1, dist_on) / 3}
     out["mesh_query"] = {"value": total / (ms * 1e-3), "unit": "points/s", "ms": ms, "points": total,
                          "lattice": [len(a) for a in axes], "n_gpus": world, "scaling": "strong", "forms": forms,
-                         "algorithmic_GBps_per_gpu": count * 3076 / (ms * 1e-3) / 1e9,
-                         "frac_of_hbm_peak": count * 3076 / (ms * 1e-3) / 1e9 / hbm_peak,
+                         "bytes_per_point": {"reference_gather": 3076, "separable": 772, "factored": 196},
+                         "factored_GBps_per_gpu": count * 196 / (ms * 1e-3) / 1e9,  # served by L2 (faces: 95 MB)
+                         "hbm_write_GBps_per_gpu": count * 4 / (ms * 1e-3) / 1e9,
                          "what": "Mesher.get_grid_uniform + eval_points (Mesher.py:130-186), SDF head only, coordinates "
-                                 "generated in-kernel; algorithmic bytes = the reference's 3072 B gathered + 4 B "
-                                 "written per point.  direct: every voxel gathers its 24 corners; separable: the "
+                                 "generated in-kernel.  direct: every voxel gathers its 24 corners; separable: the "
                                  "planes are resampled once on the lattice's faces (768 B per point, bit-identical); "
                                  "factored (default): the first decoder layer is applied on the faces too (192 B and "
                                  "272 FMA per point, equal to 1e-5).  Face resampling is inside every timed call."}
