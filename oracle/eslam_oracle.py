@@ -687,6 +687,42 @@ def query_points(fld: Field, p):
     return ret
 
 
+def query_lattice_factored(fld: Field, axes):
+    """CPU restatement of the product's FACTORED lattice query (csrc/render.cuh: k_grid_preact + k_grid_sdf_factored),
+    kept here so the algebra is pinned against the reference's golden lattice values without a GPU.
+    On the regular lattice of Mesher.py:159-186 every tap of decoders.py:64-85 depends on two lattice indices, and the
+    first layer of decoders.py:87-105 is linear in the summed feature, so
+        W1 (Fxy + Fxz + Fyz) + b1 = (W1 Fxy + b1) + W1 Fxz + W1 Fyz
+    with each term resampled once on a face of the lattice.  Returns sdf in the flat order of grid_points."""
+    b = fld.bound
+    t = [torch.from_numpy(np.asarray(a)).float() for a in axes]
+    nor = [((t[a] - b[a, 0]) / (b[a, 1] - b[a, 0])) * 2 - 1.0 for a in range(3)]
+    W1, b1 = fld.dec["linears.0.weight"], fld.dec["linears.0.bias"]
+
+    def face(planes, u, v):  # [len(v), len(u), 16]; u runs along the plane's W axis, v along H
+        gu, gv = torch.meshgrid(u, v, indexing="xy")
+        grid = torch.stack([gu, gv], -1)[None]
+        acc = 0
+        for s, plane in enumerate(planes):
+            f = F.grid_sample(plane, grid, padding_mode="border", align_corners=True, mode="bilinear")[0]
+            acc = acc + torch.einsum("oc,chw->hwo", W1[:, s * 32:(s + 1) * 32], f)
+        return acc
+
+    with torch.no_grad():
+        pxy = face(fld.planes[0], nor[0], nor[1]) + b1  # [ny, nx, 16]
+        pxz = face(fld.planes[1], nor[0], nor[2])       # [nz, nx, 16]
+        pyz = face(fld.planes[2], nor[1], nor[2])       # [nz, ny, 16]
+        pre = (pxy[:, :, None] + pxz.permute(1, 0, 2)[None]) + pyz.permute(1, 0, 2)[:, None]  # [ny, nx, nz, 16]
+        h = F.relu(pre)
+        h = F.relu(F.linear(h, fld.dec["linears.1.weight"], fld.dec["linears.1.bias"]))
+        sdf = torch.tanh(F.linear(h, fld.dec["output_linear.weight"], fld.dec["output_linear.bias"])).reshape(-1)
+    p = grid_points(axes)
+    inside = ((p[:, 0] < b[0][1]) & (p[:, 0] > b[0][0]) & (p[:, 1] < b[1][1]) & (p[:, 1] > b[1][0])
+              & (p[:, 2] < b[2][1]) & (p[:, 2] > b[2][0]))
+    sdf[~inside] = -1
+    return sdf
+
+
 # ---------------------------------------------------------------------------------------
 # keyframe selection by view overlap (SURVEY.md 8f-1)
 # ---------------------------------------------------------------------------------------

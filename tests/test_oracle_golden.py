@@ -94,6 +94,17 @@ def test_mesh_grid_golden():
     assert rel_err(ret[:, -1], d["sdf"]) < 1e-6 and rel_err(ret[:, :3], d["rgb"]) < 1e-6
 
 
+def test_factored_lattice_query_matches_the_reference_lattice():
+    """The algebra behind eslam_grid_preact + eslam_grid_sdf_factored (first decoder layer applied on the lattice's
+    faces) against the reference's own lattice values: same -1 mask, values within 1e-5."""
+    fld, d = golden_field(), load_npz("mesh.npz")
+    axes = O.grid_axes(d["mc_bound"], float(d["resolution"]))
+    sdf = O.query_lattice_factored(fld, axes)
+    ref = torch.from_numpy(d["sdf"])
+    assert torch.equal(sdf == -1, ref == -1)
+    assert (sdf - ref).abs().max().item() < 1e-5
+
+
 def test_adam_formula_matches_torch_optim():
     g = torch.Generator().manual_seed(0)
     p0 = torch.randn(1000, generator=g)
