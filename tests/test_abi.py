@@ -76,3 +76,37 @@ def test_cpu_tensors_are_rejected():
         assert "CUDA" in str(e)
     else:
         raise AssertionError("CPU tensors must be rejected: there is no CPU path")
+
+
+def test_every_entry_point_rejects_null_arguments_before_touching_the_device():
+    """Error behaviour of the boundary (include/eslam_b200.h: negative ESLAM_E* code + eslam_last_error, no exception,
+    no device work): every entry point called with NULL pointers and zero sizes returns ESLAM_EINVAL and names itself.
+    Run in a child process so that a missing check shows up as a crash of the child, not of the test session."""
+    import subprocess
+    import sys
+
+    code = r"""
+import ctypes as C, sys
+sys.path.insert(0, %r)
+import myslam_b200._lib as L
+lib = L.load()
+bad = []
+for name, argtypes in L.PROTOTYPES.items():
+    args = []
+    for t in argtypes:
+        if t in (C.c_int, C.c_int64):
+            args.append(0)
+        elif t is C.c_double:
+            args.append(0.0)
+        else:
+            args.append(None)
+    rc = getattr(lib, name)(*args)
+    msg = lib.eslam_last_error().decode()
+    stem = name.replace("_frames", "").replace("_act", "").replace("_sparse", "")
+    if rc != -1 or not (name in msg or stem in msg or name.rsplit("_", 1)[0] in msg):
+        bad.append((name, rc, msg))
+print("BAD", bad)
+sys.exit(1 if bad else 0)
+""" % ROOT
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
