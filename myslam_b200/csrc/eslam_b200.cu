@@ -316,7 +316,8 @@ int eslam_grid_sdf_factored(const eslam_field_t* f, const float* xs, const float
   a.hull = reinterpret_cast<const float4*>(hull_planes);
   a.n_hull = n_planes;
   a.sdf_out = sdf;
-  k_grid_sdf_factored<<<(unsigned)((count + FAC_THREADS - 1) / FAC_THREADS), FAC_THREADS, 0, S_(s)>>>(a);
+  const int64_t per_cta = FAC_THREADS * FAC_PT;
+  k_grid_sdf_factored<<<(unsigned)((count + per_cta - 1) / per_cta), FAC_THREADS, 0, S_(s)>>>(a);
   CHECK_LAUNCH("eslam_grid_sdf_factored");
   return 0;
 }

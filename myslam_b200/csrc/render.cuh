@@ -257,66 +257,99 @@ struct GridFacArgs {
 };
 
 constexpr int FAC_THREADS = 256;
+constexpr int FAC_PT = 2;  // voxels per thread (FAC_THREADS apart, so every load stays a coalesced row): the uniform
+                           // loads of the layer-2/3 weights and the CTA's index set-up are shared between them
 
 __global__ void __launch_bounds__(FAC_THREADS) k_grid_sdf_factored(const __grid_constant__ GridFacArgs a) {
-  __shared__ long long s_t0;
-  __shared__ int s_iz0;
-  const long long base = (long long)blockIdx.x * FAC_THREADS;
+  __shared__ int s_idx[3];
+  const long long base = (long long)blockIdx.x * (FAC_THREADS * FAC_PT);
   if (threadIdx.x == 0) {  // one 64-bit division per CTA; the per-thread index math below is 32-bit
     const long long f0 = a.start + base;
     const long long t0 = f0 / a.nz;
-    s_t0 = t0;
-    s_iz0 = (int)(f0 - t0 * a.nz);
+    const int iy0 = (int)(t0 / a.nx);
+    s_idx[0] = (int)(t0 - (long long)iy0 * a.nx);
+    s_idx[1] = iy0;
+    s_idx[2] = (int)(f0 - t0 * a.nz);
   }
   __syncthreads();
-  const long long gi = base + threadIdx.x;
-  const bool valid = gi < a.n;
-  int ix = 0, iy = 0, iz = 0;
-  if (valid) {
-    const unsigned zq = (unsigned)s_iz0 + threadIdx.x;
-    const unsigned wrap = zq / (unsigned)a.nz;
-    iz = (int)(zq - wrap * (unsigned)a.nz);
-    const unsigned t = (unsigned)s_t0 + wrap;  // < nx*ny <= 2^30
-    iy = (int)(t / (unsigned)a.nx);
-    ix = (int)(t - (unsigned)iy * (unsigned)a.nx);
-  }
-  const float p[3] = {a.xs[ix], a.ys[iy], a.zs[iz]};
-  bool inside = valid;
+  const unsigned nx = (unsigned)a.nx, nz = (unsigned)a.nz;
+  long long gi[FAC_PT];
+  bool valid[FAC_PT], inside[FAC_PT];
+  const float4 *qxy[FAC_PT], *qxz[FAC_PT], *qyz[FAC_PT];
+  bool any_inside = false;
 #pragma unroll
-  for (int k = 0; k < 3; ++k) inside = inside && (p[k] < a.hi[k]) && (p[k] > a.lo[k]);  // Mesher.py:214-215
-  for (int k = 0; k < a.n_hull && inside; ++k) {  // Mesher.py:210-217: mesh_bound.contains -> sdf = -1
-    const float4 h = __ldg(a.hull + k);
-    inside = fmaf(h.x, p[0], fmaf(h.y, p[1], fmaf(h.z, p[2], h.w))) <= 0.f;
+  for (int k = 0; k < FAC_PT; ++k) {
+    gi[k] = base + k * FAC_THREADS + threadIdx.x;
+    valid[k] = gi[k] < a.n;
+    unsigned x = (unsigned)s_idx[0], y = (unsigned)s_idx[1], z = (unsigned)s_idx[2] + k * FAC_THREADS + threadIdx.x;
+    if (z >= nz) {  // the CTA's range runs over the end of a z column (and possibly of an x row)
+      const unsigned w = z / nz;
+      z -= w * nz;
+      x += w;
+      if (x >= nx) {
+        const unsigned d = x / nx;
+        x -= d * nx;
+        y += d;
+      }
+    }
+    if (!valid[k]) x = y = z = 0u;
+    const float p[3] = {a.xs[x], a.ys[y], a.zs[z]};
+    bool in = valid[k];
+#pragma unroll
+    for (int c = 0; c < 3; ++c) in = in && (p[c] < a.hi[c]) && (p[c] > a.lo[c]);  // Mesher.py:214-215
+    for (int h = 0; h < a.n_hull && in; ++h) {  // Mesher.py:210-217: mesh_bound.contains -> sdf = -1
+      const float4 hp = __ldg(a.hull + h);
+      in = fmaf(hp.x, p[0], fmaf(hp.y, p[1], fmaf(hp.z, p[2], hp.w))) <= 0.f;
+    }
+    inside[k] = in;
+    any_inside = any_inside || in;
+    qxy[k] = a.pxy + ((long long)y * nx + x) * 4;
+    qxz[k] = a.pxz + (long long)x * 4 * nz + z;
+    qyz[k] = a.pyz + (long long)y * 4 * nz + z;
   }
-  if (!__syncthreads_or(inside)) {
-    if (valid) a.sdf_out[gi] = -1.0f;  // the whole tile lies outside: nothing to decode
+  if (!__syncthreads_or(any_inside)) {  // the whole tile lies outside: nothing to decode
+#pragma unroll
+    for (int k = 0; k < FAC_PT; ++k)
+      if (valid[k]) a.sdf_out[gi[k]] = -1.0f;
     return;
   }
-  const float4* qxy = a.pxy + ((long long)iy * a.nx + ix) * 4;
-  const float4* qxz = a.pxz + (long long)ix * 4 * a.nz + iz;
-  const float4* qyz = a.pyz + (long long)iy * 4 * a.nz + iz;
-  float h1[16];
+  float h1[FAC_PT][16];
 #pragma unroll
-  for (int c = 0; c < 4; ++c) {
-    const float4 v = f4_add(f4_add(ldg4(qxy + c), ldg4(qxz + (long long)c * a.nz)), ldg4(qyz + (long long)c * a.nz));
-    h1[c * 4 + 0] = fmaxf(v.x, 0.f);
-    h1[c * 4 + 1] = fmaxf(v.y, 0.f);
-    h1[c * 4 + 2] = fmaxf(v.z, 0.f);
-    h1[c * 4 + 3] = fmaxf(v.w, 0.f);
+  for (int k = 0; k < FAC_PT; ++k) {
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      const float4 v = f4_add(f4_add(ldg4(qxy[k] + c), ldg4(qxz[k] + (long long)c * nz)), ldg4(qyz[k] + (long long)c * nz));
+      h1[k][c * 4 + 0] = fmaxf(v.x, 0.f);
+      h1[k][c * 4 + 1] = fmaxf(v.y, 0.f);
+      h1[k][c * 4 + 2] = fmaxf(v.z, 0.f);
+      h1[k][c * 4 + 3] = fmaxf(v.w, 0.f);
+    }
   }
-  float o = c_dec[S_B3];
+  float o[FAC_PT];
+#pragma unroll
+  for (int k = 0; k < FAC_PT; ++k) o[k] = c_dec[S_B3];
 #pragma unroll
   for (int j = 0; j < 16; ++j) {
-    float acc = c_dec[S_B2 + j];
+    float acc[FAC_PT];
 #pragma unroll
-    for (int i = 0; i < 16; ++i) acc = fmaf(c_dec[S_W2 + j * 16 + i], h1[i], acc);
-    o = fmaf(c_dec[S_W3 + j], fmaxf(acc, 0.f), o);
+    for (int k = 0; k < FAC_PT; ++k) acc[k] = c_dec[S_B2 + j];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+      const float w = c_dec[S_W2 + j * 16 + i];
+#pragma unroll
+      for (int k = 0; k < FAC_PT; ++k) acc[k] = fmaf(w, h1[k][i], acc[k]);
+    }
+    const float w3 = c_dec[S_W3 + j];
+#pragma unroll
+    for (int k = 0; k < FAC_PT; ++k) o[k] = fmaf(w3, fmaxf(acc[k], 0.f), o[k]);
   }
-  float sdf = tanhf(o);
-  if (!inside) sdf = -1.0f;
-  if (valid) a.sdf_out[gi] = sdf;
+#pragma unroll
+  for (int k = 0; k < FAC_PT; ++k) {
+    float sdf = tanhf(o[k]);
+    if (!inside[k]) sdf = -1.0f;
+    if (valid[k]) a.sdf_out[gi[k]] = sdf;
+  }
 }
-
 
 __global__ void __launch_bounds__(NP) k_decode(const __grid_constant__ DecodeArgs a) {
   __shared__ SmemFwd sm;
