@@ -166,6 +166,18 @@ int eslam_grid_sdf_factored(const eslam_field_t* field_host, const float* xs, co
                             int ny, int nz, int64_t start, int64_t count, const float* pxy, const float* pxz,
                             const float* pyz, const float* hull_planes, int n_planes, float* sdf, eslam_stream_t s);
 
+/* ---- EXPERIMENTAL: pre-activated planes ------------------------------------------------
+ * Not used by the Python mirror yet and not validated on hardware (tests/test_gpu_experimental.py runs only with
+ * ESLAM_B200_EXPERIMENTAL=1); the signatures may change.  The first layer of decoders.py:87-125 commutes with the
+ * bilinear fetch of decoders.py:64-85, so it can be applied to the planes once instead of to every sample:
+ * eslam_q_build writes Q = W1_half . plane for the 12 planes as 16-channel channels-last images (q_arena: half the
+ * plane floats of the parameter arena, plane i at half its float offset; decoders read from the arena);
+ * eslam_render_forward_q is eslam_render_forward / _act on q_arena (layers 2-3 read the bound decoders). */
+int eslam_q_build(const eslam_field_t* field_host, const float* arena, float* q_arena, eslam_stream_t s);
+int eslam_render_forward_q(const eslam_field_t* field_host, const float* q_arena, const float* rays_o,
+                           const float* rays_d, const float* z, int n_rays, int n_samples, const int32_t* counters,
+                           float* depth, float* rgb, float* sdf, float* act4, uint32_t* actm, eslam_stream_t s);
+
 /* ---- pixel pick, rays, bbox filter, depth-guided samples --------------------------------------- */
 /* get_samples + the bbox pre-filter + the depth>0 half of render_batch_ray's sampling
  * (src/common.py:87-153, src/Tracker.py:175-187, src/Mapper.py:322-332, src/utils/Renderer.py:81-106).

@@ -77,6 +77,8 @@ PROTOTYPES = {
     "eslam_grid_sdf_separable": [_FP, _P, _P, _P, _P, _I, _I, _I, _L, _L, _P, _P, _P, _P, _I, _P, _P],
     "eslam_grid_preact": [_FP, _P, _P, _P, _P, _I, _I, _I, _P, _P, _P, _P],
     "eslam_grid_sdf_factored": [_FP, _P, _P, _P, _I, _I, _I, _L, _L, _P, _P, _P, _P, _I, _P, _P],
+    "eslam_q_build": [_FP, _P, _P, _P],
+    "eslam_render_forward_q": [_FP, _P, _P, _P, _P, _I, _I, _P, _P, _P, _P, _P, _P, _P],
     "eslam_sample_rays": [_FP, _CP, _RP, _P, _I, _I, _P, _P, _I, _P, _P, _P, _P, _P, _I, _P, _P, _P, _P, _P, _P, _P,
                           _P, _P, _P, _P, _P],
     "eslam_sample_rays_frames": [_FP, _CP, _RP, _P, _I, _I, _P, _P, _I, _P, _P, _P, _P, _P, _I, _P, _P, _P, _P, _P, _P,

@@ -1,5 +1,6 @@
 // C ABI of the B200-native ESLAM hot path (include/eslam_b200.h).  One translation unit: the constant
 // decoder block is shared by every kernel.  Host side: argument checks, kernel-argument packing, launches.
+#include <algorithm>
 #include <cstdio>
 #include <cstring>
 #include <cmath>
@@ -12,6 +13,7 @@
 #include "exchange.cuh"
 #include "keyframes.cuh"
 #include "ingest.cuh"
+#include "qplane.cuh"
 
 using namespace eslam;
 
@@ -972,6 +974,53 @@ int eslam_keyframe_overlap(const eslam_camera_t* cam, const float* c2w, const fl
   a.n_pts = n_pts;
   k_keyframe_overlap<<<n_keyframes, OVERLAP_THREADS, 0, S_(s)>>>(a);
   CHECK_LAUNCH("eslam_keyframe_overlap");
+  return 0;
+}
+
+// ---- experimental: pre-activated planes (qplane.cuh) ---------------------------------------
+int eslam_q_build(const eslam_field_t* f, const float* arena, float* q_arena, eslam_stream_t s) {
+  REQUIRE(f && arena && q_arena, "eslam_q_build");
+  QBuildArgs a;
+  memset(&a, 0, sizeof(a));
+  int rc = make_field_k(f, &a.fk);
+  if (rc) return fail(rc, "eslam_q_build(field)");
+  for (int i = 0; i < 12; ++i) REQUIRE(f->plane[i].offset % 32 == 0, "eslam_q_build(plane offset)");
+  a.arena4 = reinterpret_cast<const float4*>(arena);
+  a.dec = arena + f->dec_offset;
+  a.q4 = reinterpret_cast<float4*>(q_arena);
+  long long most = 1;
+  for (int i = 0; i < 12; ++i) most = std::max(most, (long long)f->plane[i].H * f->plane[i].W);
+  const long long want = (most + 127) / 128;  // >= 4 trips per CTA of the largest plane amortise the 2 KB copy of W1
+  k_q_build<<<dim3((unsigned)std::min(want, 4096ll), 12), 256, 0, S_(s)>>>(a);
+  CHECK_LAUNCH("eslam_q_build");
+  return 0;
+}
+
+int eslam_render_forward_q(const eslam_field_t* f, const float* q_arena, const float* rays_o, const float* rays_d,
+                           const float* z, int n_rays, int n_samples, const int32_t* counters, float* depth,
+                           float* rgb, float* sdf, float* act4, uint32_t* actm, eslam_stream_t s) {
+  REQUIRE(f && q_arena && rays_o && rays_d && z && depth && rgb && n_rays >= 0, "eslam_render_forward_q");
+  REQUIRE((act4 == nullptr) == (actm == nullptr) && (!act4 || sdf), "eslam_render_forward_q(activations)");
+  REQUIRE(n_samples >= 1 && n_samples <= ESLAM_MAX_SAMPLES, "eslam_render_forward_q(n_samples)");
+  if (n_rays == 0) return 0;
+  RenderFwdQArgs a;
+  int rc = make_field_k(f, &a.fk);
+  if (rc) return fail(rc, "eslam_render_forward_q(field)");
+  a.q4 = reinterpret_cast<const float4*>(q_arena);
+  a.rays_o = rays_o;
+  a.rays_d = rays_d;
+  a.z = z;
+  a.n_rays = n_rays;
+  a.S = n_samples;
+  a.counters = counters;
+  a.depth = depth;
+  a.rgb = rgb;
+  a.sdf = sdf;
+  a.act4 = reinterpret_cast<float4*>(act4);
+  a.actm = actm;
+  const int rpb = NP / n_samples;
+  k_render_fwd_q<<<(n_rays + rpb - 1) / rpb, NP, 0, S_(s)>>>(a);
+  CHECK_LAUNCH("eslam_render_forward_q");
   return 0;
 }
 
