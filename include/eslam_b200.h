@@ -167,8 +167,8 @@ int eslam_grid_sdf_factored(const eslam_field_t* field_host, const float* xs, co
                             const float* pyz, const float* hull_planes, int n_planes, float* sdf, eslam_stream_t s);
 
 /* ---- EXPERIMENTAL: pre-activated planes ------------------------------------------------
- * Not used by the Python mirror yet and not validated on hardware (tests/test_gpu_experimental.py runs only with
- * ESLAM_B200_EXPERIMENTAL=1); the signatures may change.  The first layer of decoders.py:87-125 commutes with the
+ * Not used by the Python mirror yet (tests/test_gpu_experimental.py holds them to 1e-5 of eslam_render_forward_act);
+ * the signatures may change.  The first layer of decoders.py:87-125 commutes with the
  * bilinear fetch of decoders.py:64-85, so it can be applied to the planes once instead of to every sample:
  * eslam_q_build writes Q = W1_half . plane for the 12 planes as 16-channel channels-last images (q_arena: half the
  * plane floats of the parameter arena, plane i at half its float offset; decoders read from the arena);

@@ -1,6 +1,6 @@
 // EXPERIMENTAL -- pre-activated planes ("apply the first decoder layer on the planes").
-// Not wired into the product path yet: the Python mirror never calls these entry points, and their GPU tests
-// (tests/test_gpu_experimental.py) only run with ESLAM_B200_EXPERIMENTAL=1 until they have been validated on hardware.
+// Not wired into the product path yet: the Python mirror never calls these entry points; tests/test_gpu_experimental.py
+// holds them to 1e-5 of the product's render forward.
 //
 // Bilinear interpolation is linear, so the first decoder layer of decoders.py:87-125 commutes with the plane fetch
 // of decoders.py:64-85:
