@@ -100,6 +100,15 @@ def main():
     timeit("trk.render_forward", lambda: call(
         "eslam_render_forward", tstore.ref(), ptr(tstore.arena), ptr(tws.rays_o), ptr(tws.rays_d), ptr(tws.z), 2000, 40,
         ptr(tws.counters), ptr(tws.depth), ptr(tws.rgb), ptr(tws.sdf), stream()))
+    # experimental: the same forward on pre-activated plane images, and the image rebuild
+    q_arena = torch.zeros(tstore.n_planes_end // 2, dtype=torch.float32, device=dev)
+    timeit("q_build (12 planes)", lambda: call("eslam_q_build", tstore.ref(), ptr(tstore.arena), ptr(q_arena), stream()))
+    timeit("trk.render_forward_q", lambda: call(
+        "eslam_render_forward_q", tstore.ref(), ptr(q_arena), ptr(tws.rays_o), ptr(tws.rays_d), ptr(tws.z), 2000, 40,
+        ptr(tws.counters), ptr(tws.depth), ptr(tws.rgb), ptr(tws.sdf), None, None, stream()))
+    timeit("map.render_forward_q 4000 rays", lambda: call(
+        "eslam_render_forward_q", store.ref(), ptr(q_arena), ptr(ws.rays_o), ptr(ws.rays_d), ptr(ws.z), N, 40,
+        ptr(ws.counters), ptr(ws.depth), ptr(ws.rgb), ptr(ws.sdf), None, None, stream()))
     timeit("trk.track_mask", lambda: call("eslam_track_mask", ptr(tws.gt_depth), ptr(tws.depth), ptr(tws.band), 2000,
                                           ptr(tws.counters), ptr(tws.ray_mask), ptr(tws.scratch), stream()))
     timeit("trk.loss_backward poses", lambda: call(
