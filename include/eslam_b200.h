@@ -177,6 +177,15 @@ int eslam_q_build(const eslam_field_t* field_host, const float* arena, float* q_
 int eslam_render_forward_q(const eslam_field_t* field_host, const float* q_arena, const float* rays_o,
                            const float* rays_d, const float* z, int n_rays, int n_samples, const int32_t* counters,
                            float* depth, float* rgb, float* sdf, float* act4, uint32_t* actm, eslam_stream_t s);
+/* eslam_pose_backward_act on q_arena: the cached activations must come from eslam_render_forward_q; `arena` still
+ * supplies the decoders.  The backward-to-input pass of the first layer disappears (the taps need the 16 pre-activation
+ * gradients only) and the coordinate-gradient re-gather reads 64 instead of 128 bytes per corner. */
+int eslam_pose_backward_q(const eslam_field_t* field_host, const float* arena, const float* q_arena,
+                          const eslam_camera_t* cam, const eslam_render_cfg_t* cfg, const float* rays_o,
+                          const float* rays_d, const float* z, const float* gt_depth, const double* gt_color,
+                          const int32_t* src, const int64_t* pix_idx, int n_per_img, const uint8_t* ray_mask,
+                          const int32_t* counters, int max_rays, const float* sdf, const float* act4,
+                          const uint32_t* actm, float* pose_grad, double* loss_acc, eslam_stream_t s);
 
 /* ---- pixel pick, rays, bbox filter, depth-guided samples --------------------------------------- */
 /* get_samples + the bbox pre-filter + the depth>0 half of render_batch_ray's sampling

@@ -658,7 +658,7 @@ static int loss_backward_impl(const eslam_field_t* f, const float* arena, const 
                               const int64_t* pix_idx, int n_per_img, const uint8_t* ray_mask, const int32_t* counters,
                               const int32_t* norm_counters, int max_rays, float* grad_arena, float* pose_grad,
                               double* loss_acc, const float* sdf, const float* act4, const uint32_t* actm,
-                              eslam_stream_t s) {
+                              const float* q_arena, eslam_stream_t s) {
   REQUIRE(f && arena && cam && cfg && rays_o && rays_d && z && gt_depth && gt_color && counters && max_rays >= 0,
           "eslam_loss_backward");
   REQUIRE(!pose_grad || (src && pix_idx && n_per_img > 0), "eslam_loss_backward(pose)");
@@ -705,7 +705,20 @@ static int loss_backward_impl(const eslam_field_t* f, const float* arena, const 
   a.sdf_in = sdf;
   a.act4 = reinterpret_cast<const float4*>(act4);
   a.actm = actm;
-  if (grad_arena && pose_grad)
+  a.g_depth = q_arena;  // the Q form reads its images through the (otherwise unused) upstream-gradient slot
+  if (q_arena) {
+    REQUIRE(!grad_arena && pose_grad && sdf && act4 && actm, "eslam_pose_backward_q");
+    static bool configured = false;
+    const size_t bytes = sizeof(SmemBwd<false>);
+    if (!configured) {
+      rc = set_smem(k_pose_bwd_q, bytes);
+      if (rc) return fail(rc, "eslam_pose_backward_q(shared memory)");
+      configured = true;
+    }
+    const int S = a.S, rpb = (NP / S) < 16 ? (NP / S) : 16;
+    k_pose_bwd_q<<<(max_rays + rpb - 1) / rpb, NT_BWD, bytes, S_(s)>>>(a);
+    rc = (int)cudaGetLastError();
+  } else if (grad_arena && pose_grad)
     rc = launch_bwd<1, true, true>(a, max_rays, S_(s));
   else if (grad_arena)
     rc = launch_bwd<1, true, false>(a, max_rays, S_(s));
@@ -725,7 +738,7 @@ int eslam_loss_backward(const eslam_field_t* f, const float* arena, const eslam_
                         double* loss_acc, eslam_stream_t s) {
   return loss_backward_impl(f, arena, cam, cfg, rays_o, rays_d, z, gt_depth, gt_color, src, pix_idx, n_per_img, ray_mask,
                             counters, norm_counters, max_rays, grad_arena, pose_grad, loss_acc, nullptr, nullptr,
-                            nullptr, s);
+                            nullptr, nullptr, s);
 }
 
 int eslam_pose_backward_act(const eslam_field_t* f, const float* arena, const eslam_camera_t* cam,
@@ -736,7 +749,20 @@ int eslam_pose_backward_act(const eslam_field_t* f, const float* arena, const es
                             double* loss_acc, eslam_stream_t s) {
   REQUIRE(sdf && act4 && actm && pose_grad, "eslam_pose_backward_act");
   return loss_backward_impl(f, arena, cam, cfg, rays_o, rays_d, z, gt_depth, gt_color, src, pix_idx, n_per_img, ray_mask,
-                            counters, nullptr, max_rays, nullptr, pose_grad, loss_acc, sdf, act4, actm, s);
+                            counters, nullptr, max_rays, nullptr, pose_grad, loss_acc, sdf, act4, actm, nullptr, s);
+}
+
+// experimental (qplane.cuh): eslam_pose_backward_act on the pre-activated plane images; the cached activations must
+// come from eslam_render_forward_q on the same q_arena
+int eslam_pose_backward_q(const eslam_field_t* f, const float* arena, const float* q_arena, const eslam_camera_t* cam,
+                          const eslam_render_cfg_t* cfg, const float* rays_o, const float* rays_d, const float* z,
+                          const float* gt_depth, const double* gt_color, const int32_t* src, const int64_t* pix_idx,
+                          int n_per_img, const uint8_t* ray_mask, const int32_t* counters, int max_rays,
+                          const float* sdf, const float* act4, const uint32_t* actm, float* pose_grad,
+                          double* loss_acc, eslam_stream_t s) {
+  REQUIRE(q_arena && sdf && act4 && actm && pose_grad, "eslam_pose_backward_q");
+  return loss_backward_impl(f, arena, cam, cfg, rays_o, rays_d, z, gt_depth, gt_color, src, pix_idx, n_per_img, ray_mask,
+                            counters, nullptr, max_rays, nullptr, pose_grad, loss_acc, sdf, act4, actm, q_arena, s);
 }
 
 static int fill_adam(AdamArgs& a, int64_t n, const int64_t* seg_end, const double* seg_lr, int n_seg, int step,

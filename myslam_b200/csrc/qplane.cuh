@@ -59,10 +59,6 @@ __global__ void __launch_bounds__(256) k_q_build(const __grid_constant__ QBuildA
   }
 }
 
-// pre-activation tile: row q holds 4 float4; physical slot = c ^ ((q >> 1) & 3), conflict-free both for the 4-lane
-// writers (two consecutive rows per quarter warp) and for the point-layout readers (eight consecutive rows)
-__device__ __forceinline__ int p_slot(int q, int c) { return q * 4 + (c ^ ((q >> 1) & 3)); }
-
 struct SmemFwdQ {
   float4 P[2][NP * 4];  // first-layer pre-activations (without bias) of the sdf / rgb decoder
   ax_t ax_i[12][NP];    // axis set-ups of the four resolution groups: [group*3 + axis]

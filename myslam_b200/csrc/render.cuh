@@ -968,6 +968,61 @@ __device__ __forceinline__ void scatter_group(const FieldK& fk, int field, const
   }
 }
 
+// Experimental Q form (qplane.cuh) of the coordinate-gradient half of scatter_group: P holds the
+// gradient at the first layer's pre-activations (16 per point, p_slot layout); 4 lanes per point fetch the corners of
+// the 16-channel Q images and the coordinate gradient is d/du of bilinear(Q) . g, with the clip rule of scatter_group.
+template <int FIELD>
+__device__ __forceinline__ void coord_grads_q(const FieldK& fk, const float4* __restrict__ q4, const ax_t (*ax_i)[NP],
+                                              const float (*ax_f)[NP], const float4* P, int wl, int grp, int sub,
+                                              int n_valid, float (*gp)[NP]) {
+#pragma unroll 1
+  for (int it = 0; it < 4; ++it) {
+    const int q = wl * 32 + it * 8 + grp;
+    float gpn[3] = {0.f, 0.f, 0.f};
+    if (q < n_valid) {
+      const float4 g4 = P[p_slot(q, sub)];
+#pragma unroll
+      for (int sc = 0; sc < 2; ++sc) {
+        float4 v[3][4];
+        int u0[3], v0[3];
+        float fu[3], fv[3];
+#pragma unroll
+        for (int p = 0; p < 3; ++p) {
+          const int au = FIELD * 6 + sc * 3 + pair_u(p), av = FIELD * 6 + sc * 3 + pair_v(p);
+          const PlaneK& pl = fk.pl[FIELD * 6 + sc * 3 + p];
+          u0[p] = ax_i[au][q];
+          v0[p] = ax_i[av][q];
+          fu[p] = ax_f[au][q];
+          fv[p] = ax_f[av][q];
+          const int base = (pl.off4 >> 1) + (v0[p] * pl.W + u0[p]) * 4 + sub;
+          const int dx = (u0[p] + 1 < pl.W) ? 4 : 0, dy = (v0[p] + 1 < pl.H) ? pl.W * 4 : 0;
+          v[p][0] = ldg4(q4 + base);
+          v[p][1] = ldg4(q4 + base + dx);
+          v[p][2] = ldg4(q4 + base + dy);
+          v[p][3] = ldg4(q4 + base + dy + dx);
+        }
+#pragma unroll
+        for (int p = 0; p < 3; ++p) {
+          const PlaneK& pl = fk.pl[FIELD * 6 + sc * 3 + p];
+          const float d00 = f4_dot(g4, v[p][0]), d01 = f4_dot(g4, v[p][1]);
+          const float d10 = f4_dot(g4, v[p][2]), d11 = f4_dot(g4, v[p][3]);
+          const float du = (d01 - d00) * (1.f - fv[p]) + (d11 - d10) * fv[p];
+          const float dv = (d10 - d00) * (1.f - fu[p]) + (d11 - d01) * fu[p];
+          gpn[pair_u(p)] = fmaf(du, axis_grad_mult(u0[p], fu[p], pl.W), gpn[pair_u(p)]);
+          gpn[pair_v(p)] = fmaf(dv, axis_grad_mult(v0[p], fv[p], pl.H), gpn[pair_v(p)]);
+        }
+      }
+    }
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      float v = gpn[c];
+      v += __shfl_xor_sync(0xffffffffu, v, 1);
+      v += __shfl_xor_sync(0xffffffffu, v, 2);
+      if (sub == 0) gp[c][q] = v;
+    }
+  }
+}
+
 // MODE 0: upstream gradients of (depth, rgb, sdf) per ray are read (autograd through render_batch_ray).
 // MODE 1 (FUSED): the five losses are evaluated in-kernel from gt data and device counters.
 // MODE 2 (POINTS): S == 1, "rays" are plain points (rays_o = points, rays_d unused) and the upstream gradient
@@ -977,8 +1032,11 @@ __device__ __forceinline__ void scatter_group(const FieldK& fk, int field, const
 // One CTA = NP points (whole rays) and NT_BWD = 2*NP threads: threads [0,NP) own the sdf decoder of point
 // q = tid, threads [NP,2NP) the rgb decoder of point q = tid-NP, so both decoders' gathers, MLPs and scatters
 // run side by side and every thread carries one decoder's activations only.
-template <int MODE, bool GF, bool GR>
-__global__ void __launch_bounds__(NT_BWD, 2) k_render_bwd(const __grid_constant__ BwdArgs a) {
+// QF (experimental, qplane.cuh): pose-only backward of the tracker on the pre-activated plane images; the forward
+//         must have been k_render_fwd_q with activations (cached branch below).
+template <int MODE, bool GF, bool GR, bool QF>
+__device__ __forceinline__ void render_bwd_body(const BwdArgs& a) {
+  static_assert(!QF || (MODE == 1 && !GF && GR), "the Q form exists for the tracker's pose-only backward");
   constexpr bool FUSED = MODE == 1;
   constexpr bool POINTS = MODE == 2;
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -1228,7 +1286,10 @@ __global__ void __launch_bounds__(NT_BWD, 2) k_render_bwd(const __grid_constant_
     if (lane == 0) sm.red[warp] = gb;
   }
   PHASE_MARK(7);
-  if (a.dbg & 4) {
+  if constexpr (QF) {  // the first layer lives in the Q images: its pre-activation gradient is what the taps need
+#pragma unroll
+    for (int c = 0; c < 4; ++c) Fh[p_slot(q, c)] = make_float4(ga1[c * 4], ga1[c * 4 + 1], ga1[c * 4 + 2], ga1[c * 4 + 3]);
+  } else if (a.dbg & 4) {
     Fh[q * 16] = make_float4(ga1[0], ga1[1], ga1[2], ga1[3]);
   } else {
     mlp_backward_input_s(Wh, ga1, Fh, q);
@@ -1241,7 +1302,13 @@ __global__ void __launch_bounds__(NT_BWD, 2) k_render_bwd(const __grid_constant_
   }
   PHASE_MARK(8);
   // ---- P7: scatter to the planes / coordinate gradients (gather layout, each half its own decoder)
-  {
+  if constexpr (QF) {
+    const int wl = (tid & (NP - 1)) >> 5;
+    if (half == 0)
+      coord_grads_q<0>(a.fk, reinterpret_cast<const float4*>(a.g_depth), sm.ax_i, sm.ax_f, sm.F0, wl, lane >> 2, lane & 3, n_valid, sm.gp[0]);
+    else
+      coord_grads_q<1>(a.fk, reinterpret_cast<const float4*>(a.g_depth), sm.ax_i, sm.ax_f, sm.F1, wl, lane >> 2, lane & 3, n_valid, sm.gp[1]);
+  } else {
     const int wl = (tid & (NP - 1)) >> 5, grp = lane >> 3, sub = lane & 7;
     const int qb = wl * 32 + grp * 8;  // 8 consecutive points (samples along a ray) per 8-lane group
     float4* garena4 = reinterpret_cast<float4*>(a.grad_arena);
@@ -1305,6 +1372,18 @@ __global__ void __launch_bounds__(NT_BWD, 2) k_render_bwd(const __grid_constant_
     }
   }
   (void)Fh;
+}
+
+// The kernels proper.  The body is shared through render_bwd_body; the Q form is a separate __global__ function (not a
+// fourth template argument of k_render_bwd) because the mangled name of a kernel feeds the compiler's heuristics:
+// adding the argument changed the register allocation of every existing instantiation.
+template <int MODE, bool GF, bool GR>
+__global__ void __launch_bounds__(NT_BWD, 2) k_render_bwd(const __grid_constant__ BwdArgs a) {
+  render_bwd_body<MODE, GF, GR, false>(a);
+}
+
+__global__ void __launch_bounds__(NT_BWD, 2) k_pose_bwd_q(const __grid_constant__ BwdArgs a) {
+  render_bwd_body<1, false, true, true>(a);
 }
 
 }  // namespace eslam

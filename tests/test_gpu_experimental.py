@@ -49,3 +49,53 @@ def test_render_forward_on_preactivated_planes_matches_render_forward(S):
     # ReLU masks may flip only where a pre-activation sits within rounding of zero
     flips = (out["q"]["actm"] != out["ref"]["actm"]).float().mean().item()
     assert flips < 1e-3, flips
+
+
+@pytest.mark.skipif(__import__("os").environ.get("ESLAM_B200_EXPERIMENTAL", "0") != "1",
+                    reason="eslam_pose_backward_q has not run on hardware yet: set ESLAM_B200_EXPERIMENTAL=1")
+def test_pose_backward_on_preactivated_planes_matches_the_cached_backward():
+    """Tracker iteration on the golden frame twice: product path (eslam_render_forward_act + eslam_pose_backward_act)
+    and Q path (eslam_render_forward_q + eslam_pose_backward_q) on the same rays, samples and outlier mask; the
+    pose gradient and the loss must agree to the re-association of the first layer's sums."""
+    import ctypes as C
+
+    from conftest import load_npz, recorded_draws, rel_err
+    from myslam_b200 import ReplayDraws
+    from myslam_b200._lib import call, ptr, stream
+    from myslam_b200.hotpath import tracking_iteration
+    from myslam_b200.tracker import _tracker_state, _tracker_store
+    from test_gpu_parity import make_tracker
+
+    fld, d = golden_field(), load_npz("tracking.npz")
+    trk = make_tracker(fld, d)
+    draws = recorded_draws(d)
+    n_pix = int(d["n_pix"])
+    st = _tracker_state(trk, n_pix)
+    store = _tracker_store(trk, st)
+    pose = torch.from_numpy(d["pose0"]).to(DEV).contiguous()
+    gc, gd = torch.from_numpy(d["gt_color"]).to(DEV), torch.from_numpy(d["gt_depth"]).to(DEV)
+    tracking_iteration(st["ws"], store, st["sc"], pose, gc, gd, n_pix, draws=ReplayDraws(draws[:2], DEV), strict_rng=True)
+    ws, sc = st["ws"], st["sc"]
+    g_ref, loss_ref = ws.grad7[0].clone(), ws.loss_acc[5].item()
+    mask_ref = ws.ray_mask.clone()
+    idx = draws[0].to(DEV)
+    S = sc.render.n_stratified + sc.render.n_importance
+    # the same iteration on the Q images: forward (keeps activations), outlier mask, pose-only backward
+    q_arena = torch.zeros(store.n_planes_end // 2, dtype=torch.float32, device=DEV)
+    call("eslam_q_build", store.ref(), ptr(store.arena), ptr(q_arena), stream())
+    ws.loss_acc.zero_()
+    call("eslam_render_forward_q", store.ref(), ptr(q_arena), ptr(ws.rays_o), ptr(ws.rays_d), ptr(ws.z), n_pix, S,
+         ptr(ws.counters), ptr(ws.depth), ptr(ws.rgb), ptr(ws.sdf), ptr(ws.act4), ptr(ws.actm), stream())
+    call("eslam_track_mask", ptr(ws.gt_depth), ptr(ws.depth), ptr(ws.band), n_pix, ptr(ws.counters), ptr(ws.ray_mask),
+         ptr(ws.scratch), stream())
+    call("eslam_pose_backward_q", store.ref(), ptr(store.arena), ptr(q_arena), C.byref(sc.cam), C.byref(sc.render),
+         ptr(ws.rays_o), ptr(ws.rays_d), ptr(ws.z), ptr(ws.gt_depth), ptr(ws.gt_color), ptr(ws.src), ptr(idx), n_pix,
+         ptr(ws.ray_mask), ptr(ws.counters), n_pix, ptr(ws.sdf), ptr(ws.act4), ptr(ws.actm), ptr(ws.pose_grad),
+         ptr(ws.loss_acc), stream())
+    call("eslam_finalize_loss", C.byref(sc.render), ptr(ws.counters), 1, ptr(ws.loss_acc), ptr(ws.loss_out), stream())
+    call("eslam_pose_adam_step", ptr(pose), ptr(ws.pose_grad), None, None, 1, 0, 0.0, 0.0, 1, 0.5, 0.999, 1e-8,
+         ptr(ws.grad7), 0, stream())
+    torch.cuda.synchronize()
+    assert torch.equal(ws.ray_mask, mask_ref), "the outlier mask must not depend on the form of the forward"
+    assert rel_err(ws.grad7[0], g_ref) < 1e-4
+    assert abs(ws.loss_acc[5].item() - loss_ref) <= 1e-5 * abs(loss_ref)
