@@ -112,6 +112,10 @@ class FieldStore:
         self.exp_avg_sq: Optional[torch.Tensor] = None
         self.touched: Optional[torch.Tensor] = None  # one flag per 128 parameters: any non-zero gradient since reset
         self._sig = None  # (data_ptr, version) of what was last pulled
+        # EXPERIMENTAL: 16-channel pre-activated plane images for the tracker's Q path; kept in
+        # step with the parameters by bind() while want_q is set (ESLAM_B200_QTRACK=1, see tracker._tracker_store)
+        self.want_q = False
+        self.q_arena: Optional[torch.Tensor] = None
 
     # ------------------------------------------------------------------ construction helpers
     @classmethod
@@ -193,6 +197,10 @@ class FieldStore:
     def bind(self) -> None:
         """Make this map's decoders the ones the kernels read (constant memory)."""
         call("eslam_bind_decoders", ptr(self.dec), stream())
+        if self.want_q:
+            if self.q_arena is None:
+                self.q_arena = torch.zeros(self.n_planes_end // 2, dtype=torch.float32, device=self.device)
+            call("eslam_q_build", self.ref(), ptr(self.arena), ptr(self.q_arena), stream())
 
     def ensure_grad(self) -> torch.Tensor:
         if self.grad is None:

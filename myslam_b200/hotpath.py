@@ -158,14 +158,25 @@ def tracking_iteration(ws: Workspace, store: FieldStore, sc: StepCfg, pose7: tor
     # the forward pass (needed first: the outlier mask is a median over the rendered depth, Tracker.py:192-195)
     # keeps sdf, rgb and the ReLU masks of every sample, so the backward pass neither gathers features nor
     # re-runs the forward MLPs
-    call("eslam_render_forward_act", store.ref(), ptr(store.arena), ptr(ws.rays_o), ptr(ws.rays_d), ptr(ws.z), N, S,
-         ptr(ws.counters), ptr(ws.depth), ptr(ws.rgb), ptr(ws.sdf), ptr(ws.act4), ptr(ws.actm), stream())
+    q = store.q_arena if store.want_q else None  # EXPERIMENTAL opt-in: the same two kernels on the Q images
+    if q is None:
+        call("eslam_render_forward_act", store.ref(), ptr(store.arena), ptr(ws.rays_o), ptr(ws.rays_d), ptr(ws.z), N, S,
+             ptr(ws.counters), ptr(ws.depth), ptr(ws.rgb), ptr(ws.sdf), ptr(ws.act4), ptr(ws.actm), stream())
+    else:
+        call("eslam_render_forward_q", store.ref(), ptr(q), ptr(ws.rays_o), ptr(ws.rays_d), ptr(ws.z), N, S,
+             ptr(ws.counters), ptr(ws.depth), ptr(ws.rgb), ptr(ws.sdf), ptr(ws.act4), ptr(ws.actm), stream())
     call("eslam_track_mask", ptr(ws.gt_depth), ptr(ws.depth), ptr(ws.band), N, ptr(ws.counters), ptr(ws.ray_mask),
          ptr(ws.scratch), stream())
-    call("eslam_pose_backward_act", store.ref(), ptr(store.arena), C.byref(cam), C.byref(rc), ptr(ws.rays_o),
-         ptr(ws.rays_d), ptr(ws.z), ptr(ws.gt_depth), ptr(ws.gt_color), ptr(ws.src), ptr(idx), n_pixels,
-         ptr(ws.ray_mask), ptr(ws.counters), N, ptr(ws.sdf), ptr(ws.act4), ptr(ws.actm), ptr(ws.pose_grad),
-         ptr(ws.loss_acc), stream())
+    if q is None:
+        call("eslam_pose_backward_act", store.ref(), ptr(store.arena), C.byref(cam), C.byref(rc), ptr(ws.rays_o),
+             ptr(ws.rays_d), ptr(ws.z), ptr(ws.gt_depth), ptr(ws.gt_color), ptr(ws.src), ptr(idx), n_pixels,
+             ptr(ws.ray_mask), ptr(ws.counters), N, ptr(ws.sdf), ptr(ws.act4), ptr(ws.actm), ptr(ws.pose_grad),
+             ptr(ws.loss_acc), stream())
+    else:
+        call("eslam_pose_backward_q", store.ref(), ptr(store.arena), ptr(q), C.byref(cam), C.byref(rc), ptr(ws.rays_o),
+             ptr(ws.rays_d), ptr(ws.z), ptr(ws.gt_depth), ptr(ws.gt_color), ptr(ws.src), ptr(idx), n_pixels,
+             ptr(ws.ray_mask), ptr(ws.counters), N, ptr(ws.sdf), ptr(ws.act4), ptr(ws.actm), ptr(ws.pose_grad),
+             ptr(ws.loss_acc), stream())
     call("eslam_finalize_loss", C.byref(rc), ptr(ws.counters), 1, ptr(ws.loss_acc), ptr(ws.loss_out), stream())
     if apply_adam is None:
         call("eslam_pose_adam_step", ptr(pose7), ptr(ws.pose_grad), None, None, 1, 0, 0.0, 0.0, 1, 0.5, 0.999, 1e-8,
