@@ -705,7 +705,7 @@ static int loss_backward_impl(const eslam_field_t* f, const float* arena, const 
   a.sdf_in = sdf;
   a.act4 = reinterpret_cast<const float4*>(act4);
   a.actm = actm;
-  a.g_depth = q_arena;  // the Q form reads its images through the (otherwise unused) upstream-gradient slot
+  a.q4 = reinterpret_cast<const float4*>(q_arena);
   if (q_arena) {
     REQUIRE(!grad_arena && pose_grad && sdf && act4 && actm, "eslam_pose_backward_q");
     static bool configured = false;

@@ -610,6 +610,8 @@ struct BwdArgs {
   float* grad_arena;
   float *g_rays_o, *g_rays_d;
   float* pose_grad;
+  // experimental Q form (k_pose_bwd_q): the pre-activated plane images; last, so that no other member moves
+  const float4* q4;
 };
 
 // ---- weight gradients on the tensor cores ----------------------------------------------------------------------
@@ -1305,9 +1307,9 @@ __device__ __forceinline__ void render_bwd_body(const BwdArgs& a) {
   if constexpr (QF) {
     const int wl = (tid & (NP - 1)) >> 5;
     if (half == 0)
-      coord_grads_q<0>(a.fk, reinterpret_cast<const float4*>(a.g_depth), sm.ax_i, sm.ax_f, sm.F0, wl, lane >> 2, lane & 3, n_valid, sm.gp[0]);
+      coord_grads_q<0>(a.fk, a.q4, sm.ax_i, sm.ax_f, sm.F0, wl, lane >> 2, lane & 3, n_valid, sm.gp[0]);
     else
-      coord_grads_q<1>(a.fk, reinterpret_cast<const float4*>(a.g_depth), sm.ax_i, sm.ax_f, sm.F1, wl, lane >> 2, lane & 3, n_valid, sm.gp[1]);
+      coord_grads_q<1>(a.fk, a.q4, sm.ax_i, sm.ax_f, sm.F1, wl, lane >> 2, lane & 3, n_valid, sm.gp[1]);
   } else {
     const int wl = (tid & (NP - 1)) >> 5, grp = lane >> 3, sub = lane & 7;
     const int qb = wl * 32 + grp * 8;  // 8 consecutive points (samples along a ray) per 8-lane group
@@ -1374,9 +1376,7 @@ __device__ __forceinline__ void render_bwd_body(const BwdArgs& a) {
   (void)Fh;
 }
 
-// The kernels proper.  The body is shared through render_bwd_body; the Q form is a separate __global__ function (not a
-// fourth template argument of k_render_bwd) because the mangled name of a kernel feeds the compiler's heuristics:
-// adding the argument changed the register allocation of every existing instantiation.
+// The kernels proper: the body is shared through render_bwd_body; the experimental Q form is its own __global__ function.
 template <int MODE, bool GF, bool GR>
 __global__ void __launch_bounds__(NT_BWD, 2) k_render_bwd(const __grid_constant__ BwdArgs a) {
   render_bwd_body<MODE, GF, GR, false>(a);
