@@ -27,7 +27,10 @@ def build_library(force: bool = False, verbose: bool = False) -> str:
     if not force and up_to_date():
         return OUT
     cmd = [nvcc_path(), "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
-           "--split-compile", "0", "-Xcompiler", "-fPIC", "-shared", "-o", OUT, SRC]
+           "--split-compile", "4", "-Xcompiler", "-fPIC", "-shared", "-o", OUT, SRC]
+    # A fixed thread count on purpose: the optimiser partitions the module by the number of split-compile threads, and
+    # the partitioning changes the code of nearly every kernel (8 threads, 2-4 threads and 1 thread give three different
+    # builds of the same source; "0" = "as many as there are CPUs right now" made that vary from build to build).
     if verbose:
         cmd.insert(1, "-Xptxas")
         cmd.insert(2, "-v")
