@@ -187,6 +187,17 @@ int eslam_pose_backward_q(const eslam_field_t* field_host, const float* arena, c
                           const int32_t* counters, int max_rays, const float* sdf, const float* act4,
                           const uint32_t* actm, float* pose_grad, double* loss_acc, eslam_stream_t s);
 
+/* Dense tail of a mapping iteration in the Q form (not used yet: the backward kernel that fills gq_arena is not
+ * written).  gq_arena holds d loss / d (first-layer pre-activation) reduced per texel, in the layout of q_arena.
+ * Per texel: d loss / d plane = W1_half^T . GQ (consumed in registers by torch.optim.Adam's update of the planes,
+ * Mapper.py:288-306,348-350, with the moments in parameter-arena layout), d loss / d W1_half += GQ (x) plane (added
+ * into grad_arena's decoder block, so the decoders then take the ordinary eslam_adam_step), gq_arena zeroed where
+ * consumed.  touched_q: eslam_q_touched_bytes() flags (one per 4 texels), zeroed together with the moments. */
+int eslam_q_touched_bytes(const eslam_field_t* field_host);
+int eslam_q_adam_planes(const eslam_field_t* field_host, float* arena, float* gq_arena, float* exp_avg,
+                        float* exp_avg_sq, float* grad_arena, uint8_t* touched_q, double lr_planes, double lr_cplanes,
+                        int step, double beta1, double beta2, double eps, eslam_stream_t s);
+
 /* ---- pixel pick, rays, bbox filter, depth-guided samples --------------------------------------- */
 /* get_samples + the bbox pre-filter + the depth>0 half of render_batch_ray's sampling
  * (src/common.py:87-153, src/Tracker.py:175-187, src/Mapper.py:322-332, src/utils/Renderer.py:81-106).

@@ -78,6 +78,7 @@ PROTOTYPES = {
     "eslam_grid_preact": [_FP, _P, _P, _P, _P, _I, _I, _I, _P, _P, _P, _P],
     "eslam_grid_sdf_factored": [_FP, _P, _P, _P, _I, _I, _I, _L, _L, _P, _P, _P, _P, _I, _P, _P],
     "eslam_q_build": [_FP, _P, _P, _P],
+    "eslam_q_adam_planes": [_FP, _P, _P, _P, _P, _P, _P, _D, _D, _I, _D, _D, _D, _P],
     "eslam_render_forward_q": [_FP, _P, _P, _P, _P, _I, _I, _P, _P, _P, _P, _P, _P, _P],
     "eslam_sample_rays": [_FP, _CP, _RP, _P, _I, _I, _P, _P, _I, _P, _P, _P, _P, _P, _I, _P, _P, _P, _P, _P, _P, _P,
                           _P, _P, _P, _P, _P],
@@ -128,6 +129,8 @@ def load():
     lib.eslam_exchange_flag_words.argtypes = []
     lib.eslam_exchange_stage_floats.restype = C.c_int64
     lib.eslam_exchange_stage_floats.argtypes = [C.c_int64, C.c_int]
+    lib.eslam_q_touched_bytes.restype = C.c_int
+    lib.eslam_q_touched_bytes.argtypes = [C.POINTER(FieldDesc)]
     for name, argtypes in PROTOTYPES.items():
         fn = getattr(lib, name)  # AttributeError if the symbol is not exported
         fn.restype = C.c_int

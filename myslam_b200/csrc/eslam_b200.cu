@@ -1022,6 +1022,49 @@ int eslam_q_build(const eslam_field_t* f, const float* arena, float* q_arena, es
   return 0;
 }
 
+int eslam_q_touched_bytes(const eslam_field_t* f) {
+  if (!f) return 0;
+  long long total = 0;
+  for (int i = 0; i < 12; ++i) total += ((long long)f->plane[i].H * f->plane[i].W + 3) / 4;
+  return (int)total;
+}
+
+int eslam_q_adam_planes(const eslam_field_t* f, float* arena, float* gq_arena, float* exp_avg, float* exp_avg_sq,
+                        float* grad_arena, uint8_t* touched_q, double lr_planes, double lr_cplanes, int step,
+                        double beta1, double beta2, double eps, eslam_stream_t s) {
+  REQUIRE(f && arena && gq_arena && exp_avg && exp_avg_sq && grad_arena && touched_q && step >= 1,
+          "eslam_q_adam_planes");
+  QAdamArgs a;
+  memset(&a, 0, sizeof(a));
+  int rc = make_field_k(f, &a.fk);
+  if (rc) return fail(rc, "eslam_q_adam_planes(field)");
+  int base = 0;
+  for (int i = 0; i < 12; ++i) {
+    REQUIRE(f->plane[i].offset % 32 == 0, "eslam_q_adam_planes(plane offset)");
+    a.tq_base[i] = base;
+    base += (int)(((long long)f->plane[i].H * f->plane[i].W + 3) / 4);
+  }
+  a.arena4 = reinterpret_cast<float4*>(arena);
+  a.gq4 = reinterpret_cast<float4*>(gq_arena);
+  a.m4 = reinterpret_cast<float4*>(exp_avg);
+  a.v4 = reinterpret_cast<float4*>(exp_avg_sq);
+  a.gdec = grad_arena + f->dec_offset;
+  a.dec = arena + f->dec_offset;
+  a.touched = touched_q;
+  const double bc1 = 1.0 - pow(beta1, (double)step);
+  a.step_sdf = (float)(lr_planes / bc1);
+  a.step_rgb = (float)(lr_cplanes / bc1);
+  a.adam.beta1 = (float)beta1;
+  a.adam.beta2 = (float)beta2;
+  a.adam.one_m_beta1 = (float)(1.0 - beta1);
+  a.adam.one_m_beta2 = (float)(1.0 - beta2);
+  a.adam.bc2_sqrt = (float)sqrt(1.0 - pow(beta2, (double)step));
+  a.adam.eps = (float)eps;
+  k_q_adam_planes<<<dim3(74, 12), 256, 0, S_(s)>>>(a);  // 888 CTAs = 6 per SM, grid-stride over each plane's texels
+  CHECK_LAUNCH("eslam_q_adam_planes");
+  return 0;
+}
+
 int eslam_render_forward_q(const eslam_field_t* f, const float* q_arena, const float* rays_o, const float* rays_d,
                            const float* z, int n_rays, int n_samples, const int32_t* counters, float* depth,
                            float* rgb, float* sdf, float* act4, uint32_t* actm, eslam_stream_t s) {

@@ -11,6 +11,7 @@
 // 64 -> 16 layer (1 024 of the 1 300 FMA per sample and decoder) gone.  Values differ from k_render_fwd by the
 // re-association of that one sum.
 #pragma once
+#include "optim.cuh"
 #include "render.cuh"
 
 namespace eslam {
@@ -65,6 +66,108 @@ struct SmemFwdQ {
   float ax_f[12][NP];
   float one[NP], w[NP], z[NP], c[3][NP];
 };
+
+// ---- dense tail of a mapping iteration in the Q form -------------------------------------------------------------
+// The backward kernel of the Q form reduces the 16-channel gradient of the first layer's pre-activations into GQ
+// images (layout of the Q arena).  Per texel the chain rule back to the parameters is dense and tiny:
+//     d loss / d plane[texel][c]   = sum_j W1[j][scale*32 + c] * GQ[texel][j]
+//     d loss / d W1[j][scale*32+c] = sum over the three planes of that scale and all texels of GQ[texel][j] * plane[texel][c]
+// so it is fused with the plane half of Adam: the plane gradient lives in registers only.  grid (x, 12): blockIdx.y =
+// plane; 8 lanes per texel, lane `sub` owns channels 4*sub..4*sub+3 of the texel (p, m, v) and the matching 16 x 4
+// slice of dW1, accumulated in registers over the CTA's texels and reduced once per CTA into the gradient arena's
+// decoder block (the decoders then take the ordinary Adam step, and k_q_build follows with the new W1).
+// Exact skip as in k_adam: a group of 4 texels whose GQ has been zero since the optimiser was created has m = v = 0
+// and a zero update; `touched` here is one flag per 4 texels of a plane (tq_base[plane] + texel / 4).
+struct QAdamArgs {
+  FieldK fk;
+  float4* arena4;  // parameters; the planes are updated in place
+  float4* gq4;     // gradient images, zeroed where consumed
+  float4 *m4, *v4; // Adam moments in parameter-arena layout
+  float* gdec;     // gradient arena's decoder block: dW1 is added here
+  const float* dec;
+  unsigned char* touched;
+  int tq_base[12];
+  float step_sdf, step_rgb;  // lr / (1 - beta1^t) of the sdf / rgb planes
+  AdamArgs adam;             // scalars only
+};
+
+__global__ void __launch_bounds__(256) k_q_adam_planes(const __grid_constant__ QAdamArgs a) {
+  __shared__ __align__(16) float sW[16 * 32];
+  __shared__ float sdW[16 * 32];
+  const int pi = blockIdx.y;
+  const int field = pi / 6, scale = (pi % 6) / 3;
+  const int off4 = a.fk.pl[pi].off4;
+  const long long n = (long long)a.fk.pl[pi].H * a.fk.pl[pi].W;
+  const float* w1 = a.dec + (field ? C_W1 : S_W1) + scale * 32;
+  for (int i = threadIdx.x; i < 16 * 32; i += 256) {
+    sW[i] = w1[(i >> 5) * 64 + (i & 31)];
+    sdW[i] = 0.f;
+  }
+  __syncthreads();
+  const int lane = threadIdx.x & 31, sub = threadIdx.x & 7;
+  const float ss = field ? a.step_rgb : a.step_sdf;
+  float acc[16][4];
+#pragma unroll
+  for (int j = 0; j < 16; ++j)
+#pragma unroll
+    for (int e = 0; e < 4; ++e) acc[j][e] = 0.f;
+  const float4 z4 = f4_zero();
+  const long long n4 = (n + 3) & ~3ll;  // whole warps (4 texels = one touched group) per trip
+  for (long long idx = (long long)blockIdx.x * 32 + (threadIdx.x >> 3); idx < n4; idx += (long long)gridDim.x * 32) {
+    const bool in = idx < n;
+    const long long id = in ? idx : n - 1;
+    float4* gq = a.gq4 + (long long)(off4 >> 1) + id * 4;
+    float4 g4[4];
+    bool nz = false;
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      g4[c] = in ? gq[c] : z4;
+      nz = nz || g4[c].x != 0.f || g4[c].y != 0.f || g4[c].z != 0.f || g4[c].w != 0.f;
+    }
+    const bool any = __ballot_sync(0xffffffffu, nz) != 0u;
+    unsigned char* flag = a.touched + a.tq_base[pi] + (idx >> 2);  // same byte for the whole warp
+    const bool was = *flag != 0;
+    if (!any && !was) continue;
+    if (!was && lane == 0) *flag = 1;
+    if (!in) continue;
+    const long long at = (long long)off4 + id * 8 + sub;
+    float4 p = a.arena4[at], m = a.m4[at], v = a.v4[at];
+    const float gj[16] = {g4[0].x, g4[0].y, g4[0].z, g4[0].w, g4[1].x, g4[1].y, g4[1].z, g4[1].w,
+                          g4[2].x, g4[2].y, g4[2].z, g4[2].w, g4[3].x, g4[3].y, g4[3].z, g4[3].w};
+    float4 g = z4;
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+      const float4 wj = lds4(sW + j * 32 + sub * 4);
+      g = f4_fma(gj[j], wj, g);
+      acc[j][0] = fmaf(gj[j], p.x, acc[j][0]);
+      acc[j][1] = fmaf(gj[j], p.y, acc[j][1]);
+      acc[j][2] = fmaf(gj[j], p.z, acc[j][2]);
+      acc[j][3] = fmaf(gj[j], p.w, acc[j][3]);
+    }
+    adam_one(p.x, g.x, m.x, v.x, a.adam, ss);
+    adam_one(p.y, g.y, m.y, v.y, a.adam, ss);
+    adam_one(p.z, g.z, m.z, v.z, a.adam, ss);
+    adam_one(p.w, g.w, m.w, v.w, a.adam, ss);
+    a.arena4[at] = p;
+    a.m4[at] = m;
+    a.v4[at] = v;
+    if (any && sub < 4) gq[sub] = z4;
+  }
+  // dW1: lanes with the same `sub` (the 4 texels of a warp) first, then the CTA's warps, then one reduction per element
+#pragma unroll
+  for (int j = 0; j < 16; ++j)
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      float v = acc[j][e];
+      v += __shfl_xor_sync(0xffffffffu, v, 8);
+      v += __shfl_xor_sync(0xffffffffu, v, 16);
+      if (lane < 8 && v != 0.f) atomicAdd(&sdW[j * 32 + sub * 4 + e], v);
+    }
+  __syncthreads();
+  float* dst = a.gdec + (field ? C_W1 : S_W1) + scale * 32;
+  for (int i = threadIdx.x; i < 16 * 32; i += 256)
+    if (sdW[i] != 0.f) atomicAdd(dst + (i >> 5) * 64 + (i & 31), sdW[i]);
+}
 
 // Sum over the 6 planes of decoder FIELD of the bilinear fetch from its Q images; this lane's 4 pre-activations.
 template <int FIELD>

@@ -99,3 +99,59 @@ def test_pose_backward_on_preactivated_planes_matches_the_cached_backward():
     assert torch.equal(ws.ray_mask, mask_ref), "the outlier mask must not depend on the form of the forward"
     assert rel_err(ws.grad7[0], g_ref) < 1e-4
     assert abs(ws.loss_acc[5].item() - loss_ref) <= 1e-5 * abs(loss_ref)
+
+
+@pytest.mark.skipif(__import__("os").environ.get("ESLAM_B200_EXPERIMENTAL", "0") != "1",
+                    reason="eslam_q_adam_planes has not run on hardware yet: set ESLAM_B200_EXPERIMENTAL=1")
+def test_q_adam_planes_matches_the_dense_chain_rule_and_adam():
+    """Two optimiser steps of the Q form's dense tail on sparse gradient images against plain torch:
+    dplane = GQ . W1_half, dW1_half = sum GQ (x) plane, Adam on the planes (oracle formula = torch.optim.Adam), gradient
+    images zeroed, untouched texels bit-identical."""
+    import eslam_oracle as O
+    from myslam_b200._lib import call, load, ptr, stream
+    from myslam_b200.decoders import synced_store
+
+    fld = golden_field()
+    planes, dec = to_device_scene(fld)
+    store = synced_store(planes, dec, fld.bound)
+    store.reset_adam()
+    lib = load()
+    touched = torch.zeros(lib.eslam_q_touched_bytes(store.ref()), dtype=torch.uint8, device=DEV)
+    gq = torch.zeros(store.n_planes_end // 2, dtype=torch.float32, device=DEV)
+    W1 = {0: store.dec[0:1024].view(16, 64).clone(), 1: store.dec[1332:1332 + 1024].view(16, 64).clone()}
+    ref_p = [store.plane_view(i).clone() for i in range(12)]
+    ref_m = [torch.zeros_like(p) for p in ref_p]
+    ref_v = [torch.zeros_like(p) for p in ref_p]
+    arena0 = store.arena.clone()
+    g = torch.Generator(device="cpu").manual_seed(3)
+    lr = (5e-3, 2e-3)
+    hit = [torch.zeros(p.shape[:2], dtype=torch.bool, device=DEV) for p in ref_p]
+    for step in (1, 2):
+        dW1 = {0: torch.zeros(16, 64, device=DEV), 1: torch.zeros(16, 64, device=DEV)}
+        for i in range(12):
+            h, w = store.shapes[i]
+            view = gq[store.plane_off[i] // 2: store.plane_off[i] // 2 + h * w * 16].view(h, w, 16)
+            mask = (torch.rand(h, w, generator=g) < (0.2 if step == 1 else 0.1)).to(DEV)
+            view[mask] = torch.randn(int(mask.sum()), 16, generator=g).to(DEV) * 1e-2
+            hit[i] |= mask
+            fld_i, sc = i // 6, (i % 6) // 3
+            Wh = W1[fld_i][:, sc * 32:(sc + 1) * 32]
+            grad = view @ Wh
+            dW1[fld_i][:, sc * 32:(sc + 1) * 32] += torch.einsum("hwj,hwc->jc", view, ref_p[i])
+            O.adam_update(ref_p[i], grad, ref_m[i], ref_v[i], step, lr[fld_i])
+        store.grad.zero_()
+        call("eslam_q_adam_planes", store.ref(), ptr(store.arena), ptr(gq), ptr(store.exp_avg), ptr(store.exp_avg_sq),
+             ptr(store.grad), ptr(touched), lr[0], lr[1], step, 0.9, 0.999, 1e-8, stream())
+        torch.cuda.synchronize()
+        assert float(gq.abs().max()) == 0.0, "consumed gradient images must be zeroed"
+        gdec = store.grad[store.dec_off:]
+        for fld_i, off in ((0, 0), (1, 1332)):
+            got = gdec[off:off + 1024].view(16, 64)
+            assert (got - dW1[fld_i]).abs().max().item() <= 1e-5 * dW1[fld_i].abs().max().item()
+    for i in range(12):
+        assert (store.plane_view(i) - ref_p[i]).abs().max().item() <= 1e-5 * ref_p[i].abs().max().item()
+        assert (store.plane_view(i, store.exp_avg) - ref_m[i]).abs().max().item() <= 1e-5 * ref_m[i].abs().max().item()
+        assert (store.plane_view(i, store.exp_avg_sq) - ref_v[i]).abs().max().item() <= 1e-5 * ref_v[i].abs().max().item()
+        # texels never hit keep their initial bits (exact skip)
+        before = arena0[store.plane_off[i]: store.plane_off[i] + ref_p[i].numel()].view_as(ref_p[i])
+        assert torch.equal(store.plane_view(i)[~hit[i]], before[~hit[i]])
