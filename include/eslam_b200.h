@@ -187,8 +187,17 @@ int eslam_pose_backward_q(const eslam_field_t* field_host, const float* arena, c
                           const int32_t* counters, int max_rays, const float* sdf, const float* act4,
                           const uint32_t* actm, float* pose_grad, double* loss_acc, eslam_stream_t s);
 
-/* Dense tail of a mapping iteration in the Q form (not used yet: the backward kernel that fills gq_arena is not
- * written).  gq_arena holds d loss / d (first-layer pre-activation) reduced per texel, in the layout of q_arena.
+/* eslam_loss_backward (planes + decoders, poses if pose_grad) in the Q form: the forward recompute gathers q_arena, the
+ * plane gradients are reduced as 16-channel pre-activation gradients into gq_arena (layout of q_arena, +=), grad_arena
+ * receives the decoder gradients except dW1 (which eslam_q_adam_planes forms from gq_arena) and beta. */
+int eslam_loss_backward_q(const eslam_field_t* field_host, const float* arena, const float* q_arena, float* gq_arena,
+                          const eslam_camera_t* cam, const eslam_render_cfg_t* cfg, const float* rays_o,
+                          const float* rays_d, const float* z, const float* gt_depth, const double* gt_color,
+                          const int32_t* src, const int64_t* pix_idx, int n_per_img, const uint8_t* ray_mask,
+                          const int32_t* counters, const int32_t* norm_counters, int max_rays, float* grad_arena,
+                          float* pose_grad, double* loss_acc, eslam_stream_t s);
+
+/* Dense tail of a mapping iteration in the Q form (gq_arena is filled by eslam_loss_backward_q).  gq_arena holds d loss / d (first-layer pre-activation) reduced per texel, in the layout of q_arena.
  * Per texel: d loss / d plane = W1_half^T . GQ (consumed in registers by torch.optim.Adam's update of the planes,
  * Mapper.py:288-306,348-350, with the moments in parameter-arena layout), d loss / d W1_half += GQ (x) plane (added
  * into grad_arena's decoder block, so the decoders then take the ordinary eslam_adam_step), gq_arena zeroed where

@@ -658,7 +658,7 @@ static int loss_backward_impl(const eslam_field_t* f, const float* arena, const 
                               const int64_t* pix_idx, int n_per_img, const uint8_t* ray_mask, const int32_t* counters,
                               const int32_t* norm_counters, int max_rays, float* grad_arena, float* pose_grad,
                               double* loss_acc, const float* sdf, const float* act4, const uint32_t* actm,
-                              const float* q_arena, eslam_stream_t s) {
+                              const float* q_arena, float* gq_arena, eslam_stream_t s) {
   REQUIRE(f && arena && cam && cfg && rays_o && rays_d && z && gt_depth && gt_color && counters && max_rays >= 0,
           "eslam_loss_backward");
   REQUIRE(!pose_grad || (src && pix_idx && n_per_img > 0), "eslam_loss_backward(pose)");
@@ -706,7 +706,25 @@ static int loss_backward_impl(const eslam_field_t* f, const float* arena, const 
   a.act4 = reinterpret_cast<const float4*>(act4);
   a.actm = actm;
   a.q4 = reinterpret_cast<const float4*>(q_arena);
-  if (q_arena) {
+  a.gq4 = reinterpret_cast<float4*>(gq_arena);
+  if (q_arena && grad_arena) {  // mapping iteration in the Q form
+    REQUIRE(gq_arena && !act4, "eslam_loss_backward_q");
+    static bool configured[2] = {false, false};
+    const size_t bytes = sizeof(SmemBwd<true>);
+    const int gr = pose_grad ? 1 : 0;
+    if (!configured[gr]) {
+      rc = gr ? set_smem(k_map_bwd_q<true>, bytes) : set_smem(k_map_bwd_q<false>, bytes);
+      if (rc) return fail(rc, "eslam_loss_backward_q(shared memory)");
+      configured[gr] = true;
+    }
+    const int S = a.S, rpb = (NP / S) < 16 ? (NP / S) : 16;
+    const unsigned grid = (unsigned)((max_rays + rpb - 1) / rpb);
+    if (gr)
+      k_map_bwd_q<true><<<grid, NT_BWD, bytes, S_(s)>>>(a);
+    else
+      k_map_bwd_q<false><<<grid, NT_BWD, bytes, S_(s)>>>(a);
+    rc = (int)cudaGetLastError();
+  } else if (q_arena) {
     REQUIRE(!grad_arena && pose_grad && sdf && act4 && actm, "eslam_pose_backward_q");
     static bool configured = false;
     const size_t bytes = sizeof(SmemBwd<false>);
@@ -738,7 +756,7 @@ int eslam_loss_backward(const eslam_field_t* f, const float* arena, const eslam_
                         double* loss_acc, eslam_stream_t s) {
   return loss_backward_impl(f, arena, cam, cfg, rays_o, rays_d, z, gt_depth, gt_color, src, pix_idx, n_per_img, ray_mask,
                             counters, norm_counters, max_rays, grad_arena, pose_grad, loss_acc, nullptr, nullptr,
-                            nullptr, nullptr, s);
+                            nullptr, nullptr, nullptr, s);
 }
 
 int eslam_pose_backward_act(const eslam_field_t* f, const float* arena, const eslam_camera_t* cam,
@@ -749,7 +767,7 @@ int eslam_pose_backward_act(const eslam_field_t* f, const float* arena, const es
                             double* loss_acc, eslam_stream_t s) {
   REQUIRE(sdf && act4 && actm && pose_grad, "eslam_pose_backward_act");
   return loss_backward_impl(f, arena, cam, cfg, rays_o, rays_d, z, gt_depth, gt_color, src, pix_idx, n_per_img, ray_mask,
-                            counters, nullptr, max_rays, nullptr, pose_grad, loss_acc, sdf, act4, actm, nullptr, s);
+                            counters, nullptr, max_rays, nullptr, pose_grad, loss_acc, sdf, act4, actm, nullptr, nullptr, s);
 }
 
 // experimental (qplane.cuh): eslam_pose_backward_act on the pre-activated plane images; the cached activations must
@@ -762,7 +780,23 @@ int eslam_pose_backward_q(const eslam_field_t* f, const float* arena, const floa
                           double* loss_acc, eslam_stream_t s) {
   REQUIRE(q_arena && sdf && act4 && actm && pose_grad, "eslam_pose_backward_q");
   return loss_backward_impl(f, arena, cam, cfg, rays_o, rays_d, z, gt_depth, gt_color, src, pix_idx, n_per_img, ray_mask,
-                            counters, nullptr, max_rays, nullptr, pose_grad, loss_acc, sdf, act4, actm, q_arena, s);
+                            counters, nullptr, max_rays, nullptr, pose_grad, loss_acc, sdf, act4, actm, q_arena, nullptr,
+                            s);
+}
+
+// experimental (qplane.cuh): eslam_loss_backward with planes + decoders (+ poses) in the Q form.  The plane gradients
+// arrive as 16-channel reductions in gq_arena (layout of q_arena); grad_arena receives the decoder gradients except
+// dW1 (formed by eslam_q_adam_planes from gq_arena) and beta.
+int eslam_loss_backward_q(const eslam_field_t* f, const float* arena, const float* q_arena, float* gq_arena,
+                          const eslam_camera_t* cam, const eslam_render_cfg_t* cfg, const float* rays_o,
+                          const float* rays_d, const float* z, const float* gt_depth, const double* gt_color,
+                          const int32_t* src, const int64_t* pix_idx, int n_per_img, const uint8_t* ray_mask,
+                          const int32_t* counters, const int32_t* norm_counters, int max_rays, float* grad_arena,
+                          float* pose_grad, double* loss_acc, eslam_stream_t s) {
+  REQUIRE(q_arena && gq_arena && grad_arena, "eslam_loss_backward_q");
+  return loss_backward_impl(f, arena, cam, cfg, rays_o, rays_d, z, gt_depth, gt_color, src, pix_idx, n_per_img, ray_mask,
+                            counters, norm_counters, max_rays, grad_arena, pose_grad, loss_acc, nullptr, nullptr,
+                            nullptr, q_arena, gq_arena, s);
 }
 
 static int fill_adam(AdamArgs& a, int64_t n, const int64_t* seg_end, const double* seg_lr, int n_seg, int step,

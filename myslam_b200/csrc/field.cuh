@@ -104,9 +104,6 @@ __device__ __forceinline__ float f4_dot(float4 a, float4 b) { return a.x * b.x +
 
 // swizzled feature tile: row q holds 16 float4; physical slot = c4 ^ (q & 7)
 __device__ __forceinline__ int f_slot(int q, int c4) { return q * 16 + (c4 ^ (q & 7)); }
-// pre-activation tile of the experimental Q form (qplane.cuh): row q holds 4 float4; physical slot = c ^ ((q >> 1) & 3),
-// conflict-free both for 4-lane writers (two consecutive rows per quarter warp) and point-layout readers
-__device__ __forceinline__ int p_slot(int q, int c) { return q * 4 + (c ^ ((q >> 1) & 3)); }
 __device__ __forceinline__ float f_scalar(const float4* F, int q, int c) {
   return reinterpret_cast<const float*>(F)[f_slot(q, c >> 2) * 4 + (c & 3)];
 }

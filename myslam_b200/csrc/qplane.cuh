@@ -169,50 +169,6 @@ __global__ void __launch_bounds__(256) k_q_adam_planes(const __grid_constant__ Q
     if (sdW[i] != 0.f) atomicAdd(dst + (i >> 5) * 64 + (i & 31), sdW[i]);
 }
 
-// Sum over the 6 planes of decoder FIELD of the bilinear fetch from its Q images; this lane's 4 pre-activations.
-template <int FIELD>
-__device__ __forceinline__ float4 gather_preact(const FieldK& fk, const float4* __restrict__ q4, const ax_t (*ax_i)[NP],
-                                                const float (*ax_f)[NP], int qq, int sub) {
-  float4 v[6][4];
-  float fu[6], fv[6];
-#pragma unroll
-  for (int s = 0; s < 2; ++s) {
-#pragma unroll
-    for (int p = 0; p < 3; ++p) {
-      const int t = s * 3 + p;
-      const int au = FIELD * 6 + s * 3 + pair_u(p), av = FIELD * 6 + s * 3 + pair_v(p);
-      const PlaneK& pl = fk.pl[FIELD * 6 + t];
-      const int u0 = ax_i[au][qq], v0 = ax_i[av][qq];
-      fu[t] = ax_f[au][qq];
-      fv[t] = ax_f[av][qq];
-      const int base = (pl.off4 >> 1) + (v0 * pl.W + u0) * 4 + sub;
-      const int dx = (u0 + 1 < pl.W) ? 4 : 0, dy = (v0 + 1 < pl.H) ? pl.W * 4 : 0;
-      v[t][0] = ldg4(q4 + base);
-      v[t][1] = ldg4(q4 + base + dx);
-      v[t][2] = ldg4(q4 + base + dy);
-      v[t][3] = ldg4(q4 + base + dy + dx);
-    }
-  }
-  float4 acc[2];
-#pragma unroll
-  for (int s = 0; s < 2; ++s) {
-    float4 sum = f4_zero();
-#pragma unroll
-    for (int p = 0; p < 3; ++p) {
-      const int t = s * 3 + p;
-      const float w00 = (1.f - fu[t]) * (1.f - fv[t]), w01 = fu[t] * (1.f - fv[t]), w10 = (1.f - fu[t]) * fv[t],
-                  w11 = fu[t] * fv[t];
-      float4 tap = f4_mul(w00, v[t][0]);
-      tap = f4_fma(w01, v[t][1], tap);
-      tap = f4_fma(w10, v[t][2], tap);
-      tap = f4_fma(w11, v[t][3], tap);
-      sum = (p == 0) ? tap : f4_add(sum, tap);  // (xy + xz) + yz, decoders.py:82
-    }
-    acc[s] = sum;
-  }
-  return f4_add(acc[0], acc[1]);  // coarse + fine
-}
-
 // layers 2 and 3 on h1 = relu(pre + b1), weights as constant-memory operands (field.cuh mlp_forward, minus layer 1)
 template <int B1, int W2, int B2, int W3, int B3, int NOUT>
 __device__ __forceinline__ void mlp_tail(const float4* __restrict__ P, int q, float (&h1)[16], float (&h2)[16],

@@ -3,6 +3,7 @@
 // src/Tracker.py:114-148,192-208, src/Mapper.py:110-144,337-349.
 #pragma once
 #include "field.cuh"
+#include "qform.cuh"
 
 namespace eslam {
 
@@ -610,8 +611,10 @@ struct BwdArgs {
   float* grad_arena;
   float *g_rays_o, *g_rays_d;
   float* pose_grad;
-  // experimental Q form (k_pose_bwd_q): the pre-activated plane images; last, so that no other member moves
+  // experimental Q form (k_pose_bwd_q, k_map_bwd_q): the pre-activated plane images and, for the mapper, the gradient
+  // images the plane reductions go to; last, so that no other member moves
   const float4* q4;
+  float4* gq4;
 };
 
 // ---- weight gradients on the tensor cores ----------------------------------------------------------------------
@@ -773,6 +776,9 @@ __device__ __forceinline__ void half_sync(int half) {
 //   round 2  hidden and output layers: every owner thread parks (ga2 | h1 | h2 | gout) in ITS OWN row of the feature
 //            tile, which is dead after round 1 and is only rewritten by mlp_backward_input afterwards; per half:
 //            warps 0,1 dW2 (half of the points each, two tiles), warp 2 dW3 (two tiles), warp 3 db2 and db3
+// QF (experimental Q form): the input layer's weight gradient is formed per texel by the optimiser tail
+// (k_q_adam_planes), so round 1 only takes db1 and the feature tile is not read.
+template <bool QF = false>
 __device__ __forceinline__ void weight_grads(float* act0, float* act1, float4* F0, float4* F1, float* gdec, int half,
                                              int q, const float (&h1)[16], const float (&h2)[16], const float (&ga1)[16],
                                              const float (&ga2)[16], const float (&gout)[3]) {
@@ -795,7 +801,15 @@ __device__ __forceinline__ void weight_grads(float* act0, float* act1, float4* F
   }
   half_sync(half);
   const int g = lane >> 2, t = lane & 3;
-  {
+  if constexpr (QF) {
+    if (wl == 0) {
+      float acc[4];
+      const FromBuf a_lo(abuf, g, t), a_hi(abuf, g + 8, t);
+      wgrad_bias<16>(a_lo, a_hi, lane, acc);
+      wgrad_store_bias(gB1, 16, lane, acc);
+    }
+    (void)gW1;
+  } else {
     float acc[2][4];
     const FromBuf a_lo(abuf, g, t), a_hi(abuf, g + 8, t);
     const FromTile b[2] = {FromTile(F, wl * 16 + g, t), FromTile(F, wl * 16 + 8 + g, t)};
@@ -970,61 +984,6 @@ __device__ __forceinline__ void scatter_group(const FieldK& fk, int field, const
   }
 }
 
-// Experimental Q form (qplane.cuh) of the coordinate-gradient half of scatter_group: P holds the
-// gradient at the first layer's pre-activations (16 per point, p_slot layout); 4 lanes per point fetch the corners of
-// the 16-channel Q images and the coordinate gradient is d/du of bilinear(Q) . g, with the clip rule of scatter_group.
-template <int FIELD>
-__device__ __forceinline__ void coord_grads_q(const FieldK& fk, const float4* __restrict__ q4, const ax_t (*ax_i)[NP],
-                                              const float (*ax_f)[NP], const float4* P, int wl, int grp, int sub,
-                                              int n_valid, float (*gp)[NP]) {
-#pragma unroll 1
-  for (int it = 0; it < 4; ++it) {
-    const int q = wl * 32 + it * 8 + grp;
-    float gpn[3] = {0.f, 0.f, 0.f};
-    if (q < n_valid) {
-      const float4 g4 = P[p_slot(q, sub)];
-#pragma unroll
-      for (int sc = 0; sc < 2; ++sc) {
-        float4 v[3][4];
-        int u0[3], v0[3];
-        float fu[3], fv[3];
-#pragma unroll
-        for (int p = 0; p < 3; ++p) {
-          const int au = FIELD * 6 + sc * 3 + pair_u(p), av = FIELD * 6 + sc * 3 + pair_v(p);
-          const PlaneK& pl = fk.pl[FIELD * 6 + sc * 3 + p];
-          u0[p] = ax_i[au][q];
-          v0[p] = ax_i[av][q];
-          fu[p] = ax_f[au][q];
-          fv[p] = ax_f[av][q];
-          const int base = (pl.off4 >> 1) + (v0[p] * pl.W + u0[p]) * 4 + sub;
-          const int dx = (u0[p] + 1 < pl.W) ? 4 : 0, dy = (v0[p] + 1 < pl.H) ? pl.W * 4 : 0;
-          v[p][0] = ldg4(q4 + base);
-          v[p][1] = ldg4(q4 + base + dx);
-          v[p][2] = ldg4(q4 + base + dy);
-          v[p][3] = ldg4(q4 + base + dy + dx);
-        }
-#pragma unroll
-        for (int p = 0; p < 3; ++p) {
-          const PlaneK& pl = fk.pl[FIELD * 6 + sc * 3 + p];
-          const float d00 = f4_dot(g4, v[p][0]), d01 = f4_dot(g4, v[p][1]);
-          const float d10 = f4_dot(g4, v[p][2]), d11 = f4_dot(g4, v[p][3]);
-          const float du = (d01 - d00) * (1.f - fv[p]) + (d11 - d10) * fv[p];
-          const float dv = (d10 - d00) * (1.f - fu[p]) + (d11 - d01) * fu[p];
-          gpn[pair_u(p)] = fmaf(du, axis_grad_mult(u0[p], fu[p], pl.W), gpn[pair_u(p)]);
-          gpn[pair_v(p)] = fmaf(dv, axis_grad_mult(v0[p], fv[p], pl.H), gpn[pair_v(p)]);
-        }
-      }
-    }
-#pragma unroll
-    for (int c = 0; c < 3; ++c) {
-      float v = gpn[c];
-      v += __shfl_xor_sync(0xffffffffu, v, 1);
-      v += __shfl_xor_sync(0xffffffffu, v, 2);
-      if (sub == 0) gp[c][q] = v;
-    }
-  }
-}
-
 // MODE 0: upstream gradients of (depth, rgb, sdf) per ray are read (autograd through render_batch_ray).
 // MODE 1 (FUSED): the five losses are evaluated in-kernel from gt data and device counters.
 // MODE 2 (POINTS): S == 1, "rays" are plain points (rays_o = points, rays_d unused) and the upstream gradient
@@ -1038,7 +997,7 @@ __device__ __forceinline__ void coord_grads_q(const FieldK& fk, const float4* __
 //         must have been k_render_fwd_q with activations (cached branch below).
 template <int MODE, bool GF, bool GR, bool QF>
 __device__ __forceinline__ void render_bwd_body(const BwdArgs& a) {
-  static_assert(!QF || (MODE == 1 && !GF && GR), "the Q form exists for the tracker's pose-only backward");
+  static_assert(!QF || MODE == 1, "the Q form exists for the fused-loss mode (tracker and mapper iterations)");
   constexpr bool FUSED = MODE == 1;
   constexpr bool POINTS = MODE == 2;
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -1119,7 +1078,12 @@ __device__ __forceinline__ void render_bwd_body(const BwdArgs& a) {
     }
   } else {
   // ---- P2: gather this half's decoder features
-  if (half == 0)
+  if constexpr (QF) {  // first-layer pre-activations (without bias) from the Q images, p_slot layout
+    if (half == 0)
+      gather_preact_tile<0>(a.fk, a.q4, sm.ax_i, sm.ax_f, sm.F0, n_valid, q);
+    else
+      gather_preact_tile<1>(a.fk, a.q4, sm.ax_i, sm.ax_f, sm.F1, n_valid, q);
+  } else if (half == 0)
     gather_tile<0>(a.fk, 0, a.arena4, sm.ax_i, sm.ax_f, sm.F0, n_valid, q);
   else
     gather_tile<6>(a.fk, 1, a.arena4, sm.ax_i, sm.ax_f, sm.F1, n_valid, q);
@@ -1146,7 +1110,10 @@ __device__ __forceinline__ void render_bwd_body(const BwdArgs& a) {
       }
     }
   } else {
-    mlp_forward_s(Wh, Fh, q, h1, h2, out);
+    if constexpr (QF)
+      mlp_tail_s(Wh, Fh, q, h1, h2, out);
+    else
+      mlp_forward_s(Wh, Fh, q, h1, h2, out);
     if (half == 0) {
       sdf = tanhf(out[0]);
       sdf_to_alpha(sdf, beta, u, e, alpha);
@@ -1283,7 +1250,7 @@ __device__ __forceinline__ void render_bwd_body(const BwdArgs& a) {
   PHASE_MARK(6);
   if (GF && !(a.dbg & 2)) {
     float* gdec = a.grad_arena + a.fk.dec_off;
-    weight_grads(sm.act0, sm.act1, sm.F0, sm.F1, gdec, half, q, h1, h2, ga1, ga2, gout);
+    weight_grads<QF>(sm.act0, sm.act1, sm.F0, sm.F1, gdec, half, q, h1, h2, ga1, ga2, gout);
     const float gb = warp_sum(g_beta);
     if (lane == 0) sm.red[warp] = gb;
   }
@@ -1304,7 +1271,14 @@ __device__ __forceinline__ void render_bwd_body(const BwdArgs& a) {
   }
   PHASE_MARK(8);
   // ---- P7: scatter to the planes / coordinate gradients (gather layout, each half its own decoder)
-  if constexpr (QF) {
+  if constexpr (QF && GF) {
+    const int wl = (tid & (NP - 1)) >> 5;
+    const int qb = wl * 32 + (lane >> 3) * 8;  // 8 consecutive points per 8-lane group, as below
+    if (half == 0)
+      scatter_q<GF, GR, 0>(a.fk, a.q4, a.gq4, sm.ax_i, sm.ax_f, sm.F0, qb, n_valid, lane & 7, sm.gp[0], a.dbg);
+    else
+      scatter_q<GF, GR, 1>(a.fk, a.q4, a.gq4, sm.ax_i, sm.ax_f, sm.F1, qb, n_valid, lane & 7, sm.gp[1], a.dbg);
+  } else if constexpr (QF) {
     const int wl = (tid & (NP - 1)) >> 5;
     if (half == 0)
       coord_grads_q<0>(a.fk, a.q4, sm.ax_i, sm.ax_f, sm.F0, wl, lane >> 2, lane & 3, n_valid, sm.gp[0]);
@@ -1384,6 +1358,13 @@ __global__ void __launch_bounds__(NT_BWD, 2) k_render_bwd(const __grid_constant_
 
 __global__ void __launch_bounds__(NT_BWD, 2) k_pose_bwd_q(const __grid_constant__ BwdArgs a) {
   render_bwd_body<1, false, true, true>(a);
+}
+
+// mapping iteration in the Q form: plane gradients as 16-channel reductions into the GQ images (a.gq4), decoder
+// gradients except dW1 into the gradient arena; the optimiser tail (k_q_adam_planes) turns GQ into dplane and dW1
+template <bool GR>
+__global__ void __launch_bounds__(NT_BWD, 2) k_map_bwd_q(const __grid_constant__ BwdArgs a) {
+  render_bwd_body<1, true, GR, true>(a);
 }
 
 }  // namespace eslam

@@ -155,3 +155,77 @@ def test_q_adam_planes_matches_the_dense_chain_rule_and_adam():
         # texels never hit keep their initial bits (exact skip)
         before = arena0[store.plane_off[i]: store.plane_off[i] + ref_p[i].numel()].view_as(ref_p[i])
         assert torch.equal(store.plane_view(i)[~hit[i]], before[~hit[i]])
+
+
+@pytest.mark.skipif(__import__("os").environ.get("ESLAM_B200_EXPERIMENTAL", "0") != "1",
+                    reason="eslam_loss_backward_q has not run on hardware yet: set ESLAM_B200_EXPERIMENTAL=1")
+def test_mapping_backward_in_the_q_form_matches_the_reference_gradients():
+    """The golden mapping iteration (reference gradients from tests/golden/mapping.npz) through the Q form:
+    eslam_q_build -> eslam_loss_backward_q.  Plane gradients are recovered from the gradient images as GQ . W1_half,
+    dW1 as sum GQ (x) plane (what eslam_q_adam_planes consumes), the other decoder gradients, beta, poses and the loss
+    come out of the kernel directly; all held to the product path's bars (1e-4 loss, 1e-3 gradients)."""
+    import ctypes as C
+
+    import eslam_oracle as O
+    from conftest import arena_index, load_npz, recorded_draws, rel_err
+    from myslam_b200 import ReplayDraws
+    from myslam_b200._lib import call, ptr, stream
+    from myslam_b200.common import matrix_to_cam_pose
+    from myslam_b200.decoders import synced_store
+    from myslam_b200.hotpath import mapping_iteration
+    from myslam_b200.mapper import _mapper_state
+    from test_gpu_parity import make_mapper
+
+    fld, d = golden_field(), load_npz("mapping.npz")
+    mp = make_mapper(fld, d)
+    all_planes = (mp.planes_xy, mp.planes_xz, mp.planes_yz, mp.c_planes_xy, mp.c_planes_xz, mp.c_planes_yz)
+    st = _mapper_state(mp, 400, 4)
+    store = synced_store(all_planes, mp.decoders, mp.bound)
+    store.reset_adam()
+    c2ws = torch.from_numpy(d["c2ws0"]).to(DEV)
+    poses7 = torch.zeros(4, 7, device=DEV)
+    poses7[1:] = matrix_to_cam_pose(c2ws[1:])
+    gc, gd = torch.from_numpy(d["gt_colors"]).to(DEV), torch.from_numpy(d["gt_depths"]).to(DEV)
+    draws = recorded_draws(d)
+    # the product path first: it leaves the compacted rays, samples and counters of the iteration in the workspace
+    mapping_iteration(st["ws"], store, st["sc"], c2ws, poses7, gc, gd, 100, 1, 1e-3, 5e-3, 5e-3, 1e-3,
+                      draws=ReplayDraws(draws[:4], DEV), strict_rng=True, want_loss=True, apply_adam=False)
+    ws, sc = st["ws"], st["sc"]
+    idx = draws[0].to(DEV)
+    N = 400
+    q_arena = torch.zeros(store.n_planes_end // 2, dtype=torch.float32, device=DEV)
+    gq = torch.zeros_like(q_arena)
+    call("eslam_q_build", store.ref(), ptr(store.arena), ptr(q_arena), stream())
+    store.grad.zero_()
+    ws.pose_grad.zero_()
+    ws.loss_acc.zero_()
+    call("eslam_loss_backward_q", store.ref(), ptr(store.arena), ptr(q_arena), ptr(gq), C.byref(sc.cam),
+         C.byref(sc.render), ptr(ws.rays_o), ptr(ws.rays_d), ptr(ws.z), ptr(ws.gt_depth), ptr(ws.gt_color), ptr(ws.src),
+         ptr(idx), 100, None, ptr(ws.counters), None, N, ptr(store.grad), ptr(ws.pose_grad), ptr(ws.loss_acc), stream())
+    call("eslam_finalize_loss", C.byref(sc.render), ptr(ws.counters), 0, ptr(ws.loss_acc), ptr(ws.loss_out), stream())
+    call("eslam_pose_adam_step", ptr(poses7), ptr(ws.pose_grad), None, None, 4, 1, 0.0, 0.0, 1, 0.9, 0.999, 1e-8,
+         ptr(ws.grad7), 0, stream())
+    torch.cuda.synchronize()
+    assert abs(ws.loss_acc[5].item() - float(d["it0_loss"])) / abs(float(d["it0_loss"])) < 1e-4
+    W1 = {0: store.dec[0:1024].view(16, 64), 1: store.dec[1332:1332 + 1024].view(16, 64)}
+    dW1 = {0: torch.zeros(16, 64, device=DEV), 1: torch.zeros(16, 64, device=DEV)}
+    for k in range(12):
+        i = arena_index(k)
+        h, w = store.shapes[i]
+        G = gq[store.plane_off[i] // 2: store.plane_off[i] // 2 + h * w * 16].view(h, w, 16)
+        f_i, s_i = i // 6, (i % 6) // 3
+        dplane = (G @ W1[f_i][:, s_i * 32:(s_i + 1) * 32]).permute(2, 0, 1)[None]  # NCHW like the reference's gradient
+        assert rel_err(dplane, d[f"it0_d_plane.{k}"]) < 1e-3, f"plane {k}"
+        dW1[f_i][:, s_i * 32:(s_i + 1) * 32] += torch.einsum("hwj,hwc->jc", G, store.plane_view(i))
+    gdec = store.dec_grad_dict(store.grad)
+    for name in O.DECODER_KEYS:
+        ref = d[f"it0_d_dec.{name}"]
+        if name == "linears.0.weight":
+            got = dW1[0]
+        elif name == "c_linears.0.weight":
+            got = dW1[1]
+        else:
+            got = gdec[name].reshape(ref.shape)
+        assert rel_err(got, ref) < 1e-3, name
+    assert rel_err(gdec["beta"], d["it0_beta_grad"]) < 1e-3
+    assert rel_err(ws.grad7[1:4], d["it0_pose_grad"]) < 1e-3
