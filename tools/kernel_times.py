@@ -73,6 +73,22 @@ def main():
         _lib.load().eslam_set_debug(flags)
         timeit(f"map.loss_backward planes+poses [{name}]", bwd(True, True))
     _lib.load().eslam_set_debug(0)
+    # experimental Q form of the mapping iteration: backward into gradient images, dense tail
+    if os.environ.get("ESLAM_B200_EXPERIMENTAL", "0") == "1":
+        mq = torch.zeros(store.n_planes_end // 2, dtype=torch.float32, device=dev)
+        mgq = torch.zeros_like(mq)
+        tq = torch.zeros(_lib.load().eslam_q_touched_bytes(store.ref()), dtype=torch.uint8, device=dev)
+        call("eslam_q_build", store.ref(), ptr(store.arena), ptr(mq), stream())
+        timeit("map.loss_backward_q planes+poses", lambda: call(
+            "eslam_loss_backward_q", store.ref(), ptr(store.arena), ptr(mq), ptr(mgq), C.byref(sc.cam),
+            C.byref(sc.render), ptr(ws.rays_o), ptr(ws.rays_d), ptr(ws.z), ptr(ws.gt_depth), ptr(ws.gt_color),
+            ptr(ws.src), ptr(idx), pix, None, ptr(ws.counters), None, N, ptr(store.grad), ptr(ws.pose_grad), None,
+            stream()))
+        timeit("map.q_adam_planes (tail)", lambda: call(
+            "eslam_q_adam_planes", store.ref(), ptr(store.arena), ptr(mgq), ptr(store.exp_avg), ptr(store.exp_avg_sq),
+            ptr(store.grad), ptr(tq), 5e-3, 5e-3, 1, 0.9, 0.999, 1e-8, stream()))
+        timeit("map.q_build", lambda: call("eslam_q_build", store.ref(), ptr(store.arena), ptr(mq), stream()))
+        store.grad.zero_()
     timeit("map.sample_rays", lambda: _sample(ws, store, sc, idx, nf, pix, c2w, poses7, 1, deps, cols, u, 0))
     timeit("map.importance", lambda: call(
         "eslam_importance_samples", store.ref(), ptr(store.arena), C.byref(sc.render), ptr(ws.rays_o), ptr(ws.rays_d),
