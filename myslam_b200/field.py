@@ -116,6 +116,8 @@ class FieldStore:
         # step with the parameters by bind() while want_q is set (ESLAM_B200_QTRACK=1, see tracker._tracker_store)
         self.want_q = False
         self.q_arena: Optional[torch.Tensor] = None
+        self.gq_arena: Optional[torch.Tensor] = None   # gradient images of the Q-form mapping backward
+        self.touched_q: Optional[torch.Tensor] = None  # exact-skip flags of eslam_q_adam_planes (one per 4 texels)
 
     # ------------------------------------------------------------------ construction helpers
     @classmethod
@@ -218,6 +220,29 @@ class FieldStore:
             self.exp_avg_sq.zero_()
             self.touched.zero_()
         self.ensure_grad().zero_()
+        if self.gq_arena is not None:
+            self.gq_arena.zero_()
+            self.touched_q.zero_()
+
+    def adam_step_q(self, step: int, lr_dec: float, lr_planes: float, lr_cplanes: float, betas=(0.9, 0.999),
+                    eps=1e-8) -> None:
+        """EXPERIMENTAL optimiser step of the Q form: the planes from the gradient images (which also yields dW1),
+        then the decoders with the ordinary kernel; zeroes the gradient images and the decoder gradients."""
+        call("eslam_q_adam_planes", self.ref(), ptr(self.arena), ptr(self.gq_arena), ptr(self.exp_avg),
+             ptr(self.exp_avg_sq), ptr(self.grad), ptr(self.touched_q), lr_planes, lr_cplanes, step, betas[0], betas[1],
+             eps, stream())
+        seg_end = (C.c_int64 * 1)(DEC_FLOATS)
+        seg_lr = (C.c_double * 1)(lr_dec)
+        o = self.dec_off
+        call("eslam_adam_step", ptr(self.arena[o:]), ptr(self.grad[o:]), ptr(self.exp_avg[o:]), ptr(self.exp_avg_sq[o:]),
+             DEC_FLOATS, seg_end, seg_lr, 1, step, betas[0], betas[1], eps, stream())
+
+    def ensure_q_grad(self) -> torch.Tensor:
+        if self.gq_arena is None:
+            self.gq_arena = torch.zeros(self.n_planes_end // 2, dtype=torch.float32, device=self.device)
+            n = _lib.load().eslam_q_touched_bytes(self.ref())
+            self.touched_q = torch.zeros(n, dtype=torch.uint8, device=self.device)
+        return self.gq_arena
 
     def adam_step(self, step: int, lr_dec: float, lr_planes: float, lr_cplanes: float, betas=(0.9, 0.999),
                   eps=1e-8) -> None:

@@ -11,6 +11,7 @@ which costs one host sync per iteration (the reference has >= 12); it is what pa
 from __future__ import annotations
 
 import ctypes as C
+import os
 from dataclasses import dataclass
 from typing import Optional
 
@@ -213,6 +214,11 @@ def mapping_iteration(ws: Workspace, store: FieldStore, sc: StepCfg, c2ws, poses
     _check_frames(gt_depths, gt_colors, b, cam)
     n_crop = (cam.H1 - cam.H0) * (cam.W1 - cam.W0)
     idx = draws.randint(n_crop, N)
+    # EXPERIMENTAL opt-in (ESLAM_B200_QMAP=1, one GPU): the iteration on the pre-activated plane
+    # images; bind() then also rebuilds them from the parameters of this step
+    q_form = os.environ.get("ESLAM_B200_QMAP", "0") == "1" and exchange is None and reduce_grads is None
+    if q_form:
+        store.want_q = True
     store.bind()
     c2w_flat = c2ws.reshape(b, 16).float().contiguous()
     joint = poses7 is not None
@@ -244,6 +250,18 @@ def mapping_iteration(ws: Workspace, store: FieldStore, sc: StepCfg, c2ws, poses
         exchange.end_counters()
     elif reduce_counters is not None:
         norm = reduce_counters(ws.counters)
+    if q_form and apply_adam:
+        call("eslam_loss_backward_q", store.ref(), ptr(store.arena), ptr(store.q_arena), ptr(store.ensure_q_grad()),
+             C.byref(cam), C.byref(rc), ptr(ws.rays_o), ptr(ws.rays_d), ptr(ws.z), ptr(ws.gt_depth), ptr(ws.gt_color),
+             ptr(ws.src), ptr(idx), pix_per_image, None, ptr(ws.counters), None, N, ptr(grad),
+             ptr(ws.pose_grad) if joint else None, ptr(ws.loss_acc) if want_loss else None, stream())
+        if want_loss:
+            call("eslam_finalize_loss", C.byref(rc), ptr(ws.counters), 0, ptr(ws.loss_acc), ptr(ws.loss_out), stream())
+        store.adam_step_q(step, lr_dec, lr_planes, lr_cplanes)
+        if joint:
+            call("eslam_pose_adam_step", ptr(poses7), ptr(ws.pose_grad), ptr(ws.pose_m), ptr(ws.pose_v), b, 1, lr_cam,
+                 lr_cam, step, 0.9, 0.999, 1e-8, ptr(ws.grad7), 1, stream())
+        return
     call("eslam_loss_backward", store.ref(), ptr(store.arena), C.byref(cam), C.byref(rc), ptr(ws.rays_o),
          ptr(ws.rays_d), ptr(ws.z), ptr(ws.gt_depth), ptr(ws.gt_color), ptr(ws.src), ptr(idx), pix_per_image, None,
          ptr(ws.counters), ptr(norm) if norm is not None else None, N, ptr(grad),
