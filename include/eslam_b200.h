@@ -167,8 +167,10 @@ int eslam_grid_sdf_factored(const eslam_field_t* field_host, const float* xs, co
                             const float* pyz, const float* hull_planes, int n_planes, float* sdf, eslam_stream_t s);
 
 /* ---- EXPERIMENTAL: pre-activated planes ------------------------------------------------
- * Not used by the Python mirror yet (tests/test_gpu_experimental.py holds them to 1e-5 of eslam_render_forward_act);
- * the signatures may change.  The first layer of decoders.py:87-125 commutes with the
+ * Everything from here to the next section is opt-in only (ESLAM_B200_QTRACK / ESLAM_B200_QMAP in the Python
+ * mirror) and may change.  Validated on hardware so far: eslam_q_build + eslam_render_forward_q (1e-5 of
+ * eslam_render_forward_act, tests/test_gpu_experimental.py); the backward and optimiser entry points below have
+ * compiled but not run yet.  The first layer of decoders.py:87-125 commutes with the
  * bilinear fetch of decoders.py:64-85, so it can be applied to the planes once instead of to every sample:
  * eslam_q_build writes Q = W1_half . plane for the 12 planes as 16-channel channels-last images (q_arena: half the
  * plane floats of the parameter arena, plane i at half its float offset; decoders read from the arena);
