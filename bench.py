@@ -428,16 +428,18 @@ def main():
     idx = torch.randint(spec["H"] * spec["W"], (pix * n_frames,), device=dev)
     R = int(ws.counters[0])
 
-    def bwd_kernel():
-        call("eslam_loss_backward", store.ref(), ptr(store.arena), C.byref(sc.cam), C.byref(sc.render),
-             ptr(ws.rays_o), ptr(ws.rays_d), ptr(ws.z), ptr(ws.gt_depth), ptr(ws.gt_color), ptr(ws.src), ptr(idx),
-             pix, None, ptr(ws.counters), None, pix * n_frames, ptr(store.grad), ptr(ws.pose_grad), None, stream())
+    q_img, gq_img = store.ensure_q(), store.ensure_q_grad()
 
-    store.bind()
+    def bwd_kernel():
+        call("eslam_loss_backward_q", store.ref(), ptr(store.arena), ptr(q_img), ptr(gq_img), C.byref(sc.cam),
+             C.byref(sc.render), ptr(ws.rays_o), ptr(ws.rays_d), ptr(ws.z), ptr(ws.gt_depth), ptr(ws.gt_color),
+             ptr(ws.src), ptr(idx), pix, None, ptr(ws.counters), None, pix * n_frames, ptr(store.grad),
+             ptr(ws.pose_grad), None, stream())
+
     ms_k = time_region(bwd_kernel, 50, 5, False) / 50
     hbm_peak, peak_src, _ = measured_peaks()
     achieved = R * ALGO_BYTES_PER_RAY_ITER / (ms_k * 1e-3) / 1e9
-    roofline = {"bound": "hbm", "kernel": "k_render_bwd<fused,planes,poses> (eslam_loss_backward)",
+    roofline = {"bound": "hbm", "kernel": "k_map_bwd_q<poses> (eslam_loss_backward_q)",
                 "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
                 "traffic": None, "peak_source": peak_src, "us_per_launch": 1e3 * ms_k, "rays_per_launch": R,
                 "note": "algorithmic bytes = rays x 40 samples x 6144 B x (gather+scatter); the 27 MB plane set is "

@@ -14,6 +14,7 @@
 #include "keyframes.cuh"
 #include "ingest.cuh"
 #include "qplane.cuh"
+#include "qbwd.cuh"
 
 using namespace eslam;
 
@@ -117,27 +118,14 @@ int eslam_plane_export(const float* arena, float* nchw, const eslam_plane_t* pl,
   return 0;
 }
 
-// The constant bank is backed by device memory: a one-CTA kernel stores the packed block through the symbol's
-// address, which keeps the update on the compute engine (a cudaMemcpyToSymbolAsync between two kernels costs a
-// copy-engine hand-off in both directions on every mapping iteration).  Kernels launched afterwards read the new
-// values: the constant caches are invalidated at kernel boundaries.
-__global__ void __launch_bounds__(256) k_bind_decoders(const float* __restrict__ dec, float* __restrict__ dst) {
-  for (int i = threadIdx.x; i < DEC_N; i += 256) dst[i] = dec[i];
-}
-
+// The forward-only kernels read the decoders as constant-bank operands (c_dec, field.cuh).  The block is refreshed
+// with the documented device-to-device cudaMemcpyToSymbolAsync on the caller's stream: the runtime orders it with the
+// kernels around it and takes care of the constant caches (a kernel storing through cudaGetSymbolAddress's pointer
+// would rely on undocumented invalidation at kernel boundaries).  Inside a CUDA graph it is captured as a memcpy node.
 int eslam_bind_decoders(const float* dec, eslam_stream_t s) {
   REQUIRE(dec, "eslam_bind_decoders");
-  static thread_local float* sym = nullptr;
-  static thread_local int sym_dev = -1;
-  int dev = 0;
-  cudaGetDevice(&dev);
-  if (!sym || sym_dev != dev) {
-    cudaError_t e = cudaGetSymbolAddress(reinterpret_cast<void**>(&sym), c_dec);
-    if (e != cudaSuccess) return fail((int)e, "eslam_bind_decoders(symbol)");
-    sym_dev = dev;
-  }
-  k_bind_decoders<<<1, 256, 0, S_(s)>>>(dec, sym);
-  CHECK_LAUNCH("eslam_bind_decoders");
+  cudaError_t e = cudaMemcpyToSymbolAsync(c_dec, dec, sizeof(float) * DEC_N, 0, cudaMemcpyDeviceToDevice, S_(s));
+  if (e != cudaSuccess) return fail((int)e, "eslam_bind_decoders");
   return 0;
 }
 
@@ -710,7 +698,8 @@ static int loss_backward_impl(const eslam_field_t* f, const float* arena, const 
   if (q_arena && grad_arena) {  // mapping iteration in the Q form
     REQUIRE(gq_arena && !act4, "eslam_loss_backward_q");
     static bool configured[2] = {false, false};
-    const size_t bytes = sizeof(SmemBwd<true>);
+    const size_t bytes = sizeof(SmemBwdQ<true>);
+    static_assert(sizeof(SmemBwdQ<true>) <= 113 * 1024, "two CTAs of the Q backward must fit one SM's shared memory");
     const int gr = pose_grad ? 1 : 0;
     if (!configured[gr]) {
       rc = gr ? set_smem(k_map_bwd_q<true>, bytes) : set_smem(k_map_bwd_q<false>, bytes);
@@ -727,7 +716,7 @@ static int loss_backward_impl(const eslam_field_t* f, const float* arena, const 
   } else if (q_arena) {
     REQUIRE(!grad_arena && pose_grad && sdf && act4 && actm, "eslam_pose_backward_q");
     static bool configured = false;
-    const size_t bytes = sizeof(SmemBwd<false>);
+    const size_t bytes = sizeof(SmemBwdQ<false>);
     if (!configured) {
       rc = set_smem(k_pose_bwd_q, bytes);
       if (rc) return fail(rc, "eslam_pose_backward_q(shared memory)");
@@ -1042,16 +1031,12 @@ int eslam_q_build(const eslam_field_t* f, const float* arena, float* q_arena, es
   REQUIRE(f && arena && q_arena, "eslam_q_build");
   QBuildArgs a;
   memset(&a, 0, sizeof(a));
-  int rc = make_field_k(f, &a.fk);
-  if (rc) return fail(rc, "eslam_q_build(field)");
-  for (int i = 0; i < 12; ++i) REQUIRE(f->plane[i].offset % 32 == 0, "eslam_q_build(plane offset)");
+  int rc = make_q_groups(f, QB_TPC, &a.qg);
+  if (rc) return fail(rc, "eslam_q_build(plane layout)");
   a.arena4 = reinterpret_cast<const float4*>(arena);
   a.dec = arena + f->dec_offset;
-  a.q4 = reinterpret_cast<float4*>(q_arena);
-  long long most = 1;
-  for (int i = 0; i < 12; ++i) most = std::max(most, (long long)f->plane[i].H * f->plane[i].W);
-  const long long want = (most + 127) / 128;  // >= 4 trips per CTA of the largest plane amortise the 2 KB copy of W1
-  k_q_build<<<dim3((unsigned)std::min(want, 4096ll), 12), 256, 0, S_(s)>>>(a);
+  a.q2 = reinterpret_cast<float2*>(q_arena);
+  k_q_build<<<a.qg.unit0[4], 256, 0, S_(s)>>>(a);
   CHECK_LAUNCH("eslam_q_build");
   return 0;
 }
@@ -1059,8 +1044,8 @@ int eslam_q_build(const eslam_field_t* f, const float* arena, float* q_arena, es
 int eslam_q_touched_bytes(const eslam_field_t* f) {
   if (!f) return 0;
   long long total = 0;
-  for (int i = 0; i < 12; ++i) total += ((long long)f->plane[i].H * f->plane[i].W + 3) / 4;
-  return (int)total;
+  for (int i = 0; i < 12; ++i) total = std::max(total, f->plane[i].offset / 32 + (long long)f->plane[i].H * f->plane[i].W);
+  return (int)total;  // one flag per texel, indexed by the texel's arena position
 }
 
 int eslam_q_adam_planes(const eslam_field_t* f, float* arena, float* gq_arena, float* exp_avg, float* exp_avg_sq,
@@ -1070,14 +1055,8 @@ int eslam_q_adam_planes(const eslam_field_t* f, float* arena, float* gq_arena, f
           "eslam_q_adam_planes");
   QAdamArgs a;
   memset(&a, 0, sizeof(a));
-  int rc = make_field_k(f, &a.fk);
-  if (rc) return fail(rc, "eslam_q_adam_planes(field)");
-  int base = 0;
-  for (int i = 0; i < 12; ++i) {
-    REQUIRE(f->plane[i].offset % 32 == 0, "eslam_q_adam_planes(plane offset)");
-    a.tq_base[i] = base;
-    base += (int)(((long long)f->plane[i].H * f->plane[i].W + 3) / 4);
-  }
+  int rc = make_q_groups(f, QA_TILE, &a.qg);
+  if (rc) return fail(rc, "eslam_q_adam_planes(plane layout)");
   a.arena4 = reinterpret_cast<float4*>(arena);
   a.gq4 = reinterpret_cast<float4*>(gq_arena);
   a.m4 = reinterpret_cast<float4*>(exp_avg);
@@ -1094,7 +1073,7 @@ int eslam_q_adam_planes(const eslam_field_t* f, float* arena, float* gq_arena, f
   a.adam.one_m_beta2 = (float)(1.0 - beta2);
   a.adam.bc2_sqrt = (float)sqrt(1.0 - pow(beta2, (double)step));
   a.adam.eps = (float)eps;
-  k_q_adam_planes<<<dim3(74, 12), 256, 0, S_(s)>>>(a);  // 888 CTAs = 6 per SM, grid-stride over each plane's texels
+  k_q_adam_planes<<<a.qg.unit0[4], QA_TILE, 0, S_(s)>>>(a);
   CHECK_LAUNCH("eslam_q_adam_planes");
   return 0;
 }

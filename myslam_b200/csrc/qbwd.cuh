@@ -1,0 +1,545 @@
+// Fused loss + backward of both loops ON THE Q IMAGES: the first decoder layer lives in the
+// 16-channel images Q = W1_slice . plane, so a sample gathers 64 instead of 128 bytes per corner, the 64 -> 16 layer
+// is gone from forward, backward and the weight-gradient contraction, and the plane gradients leave the kernel as
+// 16-channel reductions into gradient images (the optimiser tail, qplane.cuh, turns them into d loss / d plane and dW1).
+// Reference semantics: src/networks/decoders.py:64-146, src/utils/Renderer.py:136-153, src/Tracker.py:114-148,192-208,
+// src/Mapper.py:110-144,337-349.
+//
+// One CTA = NP points (whole rays), 2 * NP threads: threads [0, NP) own the sdf decoder of point tid, threads [NP, 2 NP)
+// the rgb decoder of point tid - NP (render.cuh's split).  Differences from render_bwd_body beyond the Q form:
+//   * the gather also forms J = d pre-activation / d normalised coordinate (3 x 16 per point and decoder: the corner
+//     differences it has in registers anyway), parked in a row tile; the coordinate gradient is then J^T g in point
+//     layout and the backward never fetches a corner twice (the parameter form re-gathers all 48 lines per sample)
+//   * one staging round for the weight gradients: the row tile is overwritten in place by (ga2 | h1 | h2 | gout), the
+//     pre-activation tile by ga1, one barrier, then dW2 / dW3 / db1 / db2 / db3 on the tensor cores
+//   * everything a ray needs from global memory late in the kernel (gt depth / colour, outlier mask, loss normalisers,
+//     source pixel of the pose gradient) is fetched at the top, so no L2 round trip is exposed behind a barrier
+#pragma once
+#include "render.cuh"
+
+namespace eslam {
+
+constexpr int RS = 52;                          // floats per point of the row tile: J (3 x 16) or (ga2 | h1 | h2 | gout)
+constexpr int QW_STRIDE = DW_STRIDE - DW_B1;    // b1 W2 b2 W3 b3 of one decoder (field.cuh's block minus W1): 340 floats
+constexpr int QW_TOTAL = 2 * QW_STRIDE + 4;
+
+template <bool ROWS>
+struct SmemBwdQ {
+  float4 P[2][NP * 4];                 // pre-activations, later their gradient (p_slot layout)
+  float R[2][ROWS ? NP * RS : 4];      // row tile per decoder
+  ax_t ax_i[12][NP];
+  float ax_f[12][NP];
+  float W[QW_TOTAL];
+  float one[NP], w[NP], z[NP], c[3][NP], gww[NP];
+  float gp[2][3][NP];  // d loss / d normalised coordinate, per decoder half
+  float rayv[4][16];   // per ray: rendered depth, r, g, b
+  float rayg[4][16];   // per ray: upstream g_depth, g_rgb
+  float rayd[16];      // per ray gt depth
+  int raym[16];        // per ray loss-mask flag
+  double rayc[3][16];  // per ray gt colour
+  int norm[8];         // loss normalisers (counters layout)
+  float rayod[6][16];  // per ray d loss / d (o, d)
+  float red[NT_BWD / 32];
+  double redd[(NT_BWD / 32) * 5];
+};
+
+template <int BYTES>
+__device__ __forceinline__ void cp_async_small(void* smem_dst, const void* gmem_src) {
+  const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.ca.shared.global [%0], [%1], %2;" ::"r"(d), "l"(gmem_src), "n"(BYTES) : "memory");
+}
+
+// b1 W2 b2 W3 b3 of both decoders -> shared memory (cp.async; decoder_weights_wait() + barrier before first use).
+// The packed arena block (include/eslam_b200.h) holds them contiguously: sdf floats [1024, 1329), rgb [2356, 2695).
+__device__ __forceinline__ void load_tail_weights(float* sW, const float* __restrict__ dec, int tid, int nthreads) {
+  constexpr int SDF4 = 304 / 4;  // b1 W2 b2 W3[0]
+  constexpr int RGB4 = 336 / 4;  // b1 W2 b2 W3[0..2]
+  for (int i = tid; i < SDF4 + RGB4; i += nthreads) {
+    if (i < SDF4)
+      cp_async16(sW + 4 * i, dec + S_B1 + 4 * i);
+    else
+      cp_async16(sW + QW_STRIDE + 4 * (i - SDF4), dec + C_B1 + 4 * (i - SDF4));
+  }
+  asm volatile("cp.async.commit_group;" ::: "memory");
+  if (tid < 32) sW[304 + tid] = 0.f;  // sdf W3 rows 1-2 (the sdf decoder has one output)
+  if (tid == 32) sW[336] = dec[S_B3];
+  if (tid >= 33 && tid < 36) sW[336 + (tid - 32)] = 0.f;
+  if (tid >= 36 && tid < 39) sW[QW_STRIDE + 336 + (tid - 36)] = dec[C_B3 + (tid - 36)];
+  if (tid == 39) sW[QW_STRIDE + 339] = 0.f;
+  if (tid == 40) sW[2 * QW_STRIDE] = dec[P_BETA];
+}
+
+// Sum over the 6 planes of decoder FIELD of the bilinear fetch from its Q images (this lane's 4 pre-activations) and,
+// with WJ, its derivative with respect to the three normalised coordinates (grid_sample's grid gradient: corner
+// differences times (size-1)/2, zero where the coordinate is clipped, GridSampler.h).
+template <int FIELD, bool WJ>
+__device__ __forceinline__ void gather_preact_j(const FieldK& fk, const float4* __restrict__ q4, const ax_t (*ax_i)[NP],
+                                                const float (*ax_f)[NP], int qq, int sub, float4& pre,
+                                                float4 (&J)[3]) {
+  float4 v[6][4];
+  float fu[6], fv[6], mu[6], mv[6];
+#pragma unroll
+  for (int s = 0; s < 2; ++s) {
+#pragma unroll
+    for (int p = 0; p < 3; ++p) {
+      const int t = s * 3 + p;
+      const int au = FIELD * 6 + s * 3 + pair_u(p), av = FIELD * 6 + s * 3 + pair_v(p);
+      const PlaneK& pl = fk.pl[FIELD * 6 + t];
+      const int u0 = ax_i[au][qq], v0 = ax_i[av][qq];
+      fu[t] = ax_f[au][qq];
+      fv[t] = ax_f[av][qq];
+      if (WJ) {
+        mu[t] = axis_grad_mult(u0, fu[t], pl.W);
+        mv[t] = axis_grad_mult(v0, fv[t], pl.H);
+      }
+      const int base = (pl.off4 >> 1) + (v0 * pl.W + u0) * 4 + sub;
+      const int dx = (u0 + 1 < pl.W) ? 4 : 0, dy = (v0 + 1 < pl.H) ? pl.W * 4 : 0;
+      v[t][0] = ldg4(q4 + base);
+      v[t][1] = ldg4(q4 + base + dx);
+      v[t][2] = ldg4(q4 + base + dy);
+      v[t][3] = ldg4(q4 + base + dy + dx);
+    }
+  }
+  if (WJ) J[0] = J[1] = J[2] = f4_zero();
+  float4 acc[2];
+#pragma unroll
+  for (int s = 0; s < 2; ++s) {
+    float4 sum = f4_zero();
+#pragma unroll
+    for (int p = 0; p < 3; ++p) {
+      const int t = s * 3 + p;
+      const float w00 = (1.f - fu[t]) * (1.f - fv[t]), w01 = fu[t] * (1.f - fv[t]), w10 = (1.f - fu[t]) * fv[t],
+                  w11 = fu[t] * fv[t];
+      float4 tap = f4_mul(w00, v[t][0]);
+      tap = f4_fma(w01, v[t][1], tap);
+      tap = f4_fma(w10, v[t][2], tap);
+      tap = f4_fma(w11, v[t][3], tap);
+      sum = (p == 0) ? tap : f4_add(sum, tap);  // (xy + xz) + yz, decoders.py:82
+      if (WJ) {
+        const float4 a = f4_sub(v[t][1], v[t][0]), b = f4_sub(v[t][3], v[t][2]);  // d/du on the lower / upper row
+        const float4 c = f4_sub(v[t][2], v[t][0]), d = f4_sub(v[t][3], v[t][1]);  // d/dv on the left / right column
+        const float4 du = f4_fma(fv[t], f4_sub(b, a), a);
+        const float4 dv = f4_fma(fu[t], f4_sub(d, c), c);
+        J[pair_u(p)] = f4_fma(mu[t], du, J[pair_u(p)]);
+        J[pair_v(p)] = f4_fma(mv[t], dv, J[pair_v(p)]);
+      }
+    }
+    acc[s] = sum;
+  }
+  pre = f4_add(acc[0], acc[1]);  // coarse + fine
+}
+
+// pre-activation tile and (WJ) the J rows of decoder FIELD for the NP slots of one half of the CTA
+template <int FIELD, bool WJ>
+__device__ __forceinline__ void gather_preact_rows(const FieldK& fk, const float4* __restrict__ q4,
+                                                   const ax_t (*ax_i)[NP], const float (*ax_f)[NP], float4* P, float* R,
+                                                   int n_valid, int tid) {
+  const int warp = tid >> 5, lane = tid & 31, grp = lane >> 2, sub = lane & 3;
+#pragma unroll 1
+  for (int it = 0; it < 4; ++it) {
+    const int qq = warp * 32 + it * 8 + grp;
+    float4 p = f4_zero(), J[3];
+    J[0] = J[1] = J[2] = f4_zero();
+    if (qq < n_valid) gather_preact_j<FIELD, WJ>(fk, q4, ax_i, ax_f, qq, sub, p, J);
+    P[p_slot(qq, sub)] = p;
+    if (WJ) {
+      float4* row = reinterpret_cast<float4*>(R + qq * RS);
+#pragma unroll
+      for (int a = 0; a < 3; ++a) row[a * 4 + sub] = J[a];
+    }
+  }
+}
+
+// operand sources of the weight-gradient mma fragments (see render.cuh FromBuf / FromTile)
+struct FromRow {  // row tile [NP][RS]
+  const float* base;
+  int o[4];
+  __device__ __forceinline__ FromRow(const float* buf, int c, int t) : base(buf) {
+    const int r[4] = {2 * t, 2 * t + 1, 2 * t + 8, 2 * t + 9};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) o[i] = r[i] * RS + c;
+  }
+  __device__ __forceinline__ float at(int q0, int i) const { return base[q0 * RS + o[i]]; }
+};
+struct FromP {  // pre-activation tile, p_slot layout (q0 is a multiple of 16, so the swizzle term depends on r only)
+  const float* base;
+  int o[4];
+  __device__ __forceinline__ FromP(const float4* P, int c, int t) : base(reinterpret_cast<const float*>(P)) {
+    const int r[4] = {2 * t, 2 * t + 1, 2 * t + 8, 2 * t + 9};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) o[i] = (r[i] * 4 + ((c >> 2) ^ ((r[i] >> 1) & 3))) * 4 + (c & 3);
+  }
+  __device__ __forceinline__ float at(int q0, int i) const { return base[q0 * 16 + o[i]]; }
+};
+
+// Weight gradients of one decoder's layers 2 and 3 and of all three biases (dW1 is formed per texel by the optimiser
+// tail).  Every owner thread parks (ga2 | h1 | h2 | gout) in ITS OWN row of the row tile (whose J it has just consumed)
+// and ga1 in its row of the pre-activation tile; after one barrier over the half: warps 0,1 dW2 (half of the points
+// each), warp 2 dW3, warp 3 the biases.  Contains a barrier over the half: call from uniform control flow.
+__device__ __forceinline__ void weight_grads_q(float* R, float4* P, float* gdec, int half, int q, const float (&h1)[16],
+                                               const float (&h2)[16], const float (&ga1)[16], const float (&ga2)[16],
+                                               const float (&gout)[3], bool with_wgrads) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int wl = warp & 3;
+  const int nout = half ? 3 : 1;
+#pragma unroll
+  for (int c = 0; c < 4; ++c) P[p_slot(q, c)] = make_float4(ga1[c * 4], ga1[c * 4 + 1], ga1[c * 4 + 2], ga1[c * 4 + 3]);
+  if (with_wgrads) {
+    float4* row = reinterpret_cast<float4*>(R + q * RS);
+#pragma unroll
+    for (int v = 0; v < 4; ++v) {
+      row[v] = make_float4(ga2[v * 4], ga2[v * 4 + 1], ga2[v * 4 + 2], ga2[v * 4 + 3]);
+      row[4 + v] = make_float4(h1[v * 4], h1[v * 4 + 1], h1[v * 4 + 2], h1[v * 4 + 3]);
+      row[8 + v] = make_float4(h2[v * 4], h2[v * 4 + 1], h2[v * 4 + 2], h2[v * 4 + 3]);
+    }
+    row[12] = make_float4(gout[0], gout[1], gout[2], 0.f);
+  }
+  half_sync(half);
+  if (!with_wgrads) return;
+  float* gB1 = gdec + (half ? C_B1 : S_B1);
+  float* gW2 = gdec + (half ? C_W2 : S_W2);
+  float* gB2 = gdec + (half ? C_B2 : S_B2);
+  float* gW3 = gdec + (half ? C_W3 : S_W3);
+  float* gB3 = gdec + (half ? C_B3 : S_B3);
+  const int g = lane >> 2, t = lane & 3;
+  const FromRow g2_lo(R, g, t), g2_hi(R, 8 + g, t);  // ga2 channels g, g + 8
+  const FromRow g3_lo(R, 48 + (g & 3), t);           // gout channel g (< 4; lanes with g >= 4 contribute zeros)
+  if (wl < 2) {
+    float acc[2][4];
+    const FromRow b[2] = {FromRow(R, 16 + g, t), FromRow(R, 24 + g, t)};
+    wgrad_tiles<16, 2>(g2_lo, g2_hi, b, wl * (NP / 2), (wl + 1) * (NP / 2), lane, acc);
+    wgrad_store(gW2, 16, 0, 16, lane, acc[0]);
+    wgrad_store(gW2, 16, 8, 16, lane, acc[1]);
+  } else if (wl == 2) {
+    float acc[2][4];
+    const FromRow b[2] = {FromRow(R, 32 + g, t), FromRow(R, 40 + g, t)};
+    wgrad_tiles<4, 2>(g3_lo, g3_lo, b, 0, NP, lane, acc);
+    wgrad_store(gW3, 16, 0, nout, lane, acc[0]);
+    wgrad_store(gW3, 16, 8, nout, lane, acc[1]);
+  } else {
+    float acc[4];
+    const FromP g1_lo(P, g, t), g1_hi(P, 8 + g, t);
+    wgrad_bias<16>(g1_lo, g1_hi, lane, acc);
+    wgrad_store_bias(gB1, 16, lane, acc);
+    wgrad_bias<16>(g2_lo, g2_hi, lane, acc);
+    wgrad_store_bias(gB2, 16, lane, acc);
+    wgrad_bias<4>(g3_lo, g3_lo, lane, acc);
+    wgrad_store_bias(gB3, nout, lane, acc);
+  }
+}
+
+// GF: gradients for the planes (gradient images a.gq4) and the decoders (a.grad_arena's decoder block, except dW1).
+// GR: gradients for the poses.  CACHED (tracker, !GF): sdf, rgb and the ReLU masks of every sample come from
+// k_render_fwd_q on the same rays, so neither the gather nor the forward MLPs run; the coordinate gradients then
+// fetch the Q corners once (coord_grads_q).
+template <bool GF, bool GR, bool CACHED>
+__device__ __forceinline__ void render_bwd_q_body(const BwdArgs& a) {
+  static_assert(!(GF && CACHED), "the cached form has no activations for weight gradients");
+  constexpr bool ROWS = !CACHED;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  SmemBwdQ<ROWS>& sm = *reinterpret_cast<SmemBwdQ<ROWS>*>(smem_raw);
+  const int R = a.counters ? min(a.counters[0], a.n_rays) : a.n_rays;
+  const int S = a.S;
+  const int RPB = min(NP / S, 16);
+  const int ray0 = blockIdx.x * RPB;
+  if (ray0 >= R) return;
+  const int rays_here = min(RPB, R - ray0);
+  const int n_valid = rays_here * S;
+  const int tid = threadIdx.x;
+  const int half = tid >> 7;  // 0: sdf decoder, 1: rgb decoder (warp-uniform)
+  const int q = tid & (NP - 1);
+  const int warp = tid >> 5, lane = tid & 31;
+  const bool valid = q < n_valid;
+  const int rl = valid ? q / S : 0;
+  const int k = q - rl * S;
+  const int ray = ray0 + rl;
+
+  PHASE_INIT();
+  // ---- P0: points, normalised coordinates, axis set-ups of this half's two resolution groups; early fetches
+  float pn[3] = {0.f, 0.f, 0.f}, zk = 0.f;
+  if (valid) {
+    zk = a.z[(long long)ray * S + k];
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      const float p = __fadd_rn(a.rays_o[ray * 3 + c], __fmul_rn(a.rays_d[ray * 3 + c], zk));
+      pn[c] = normalize_axis(p, a.fk.lo[c], a.fk.hi[c]);
+    }
+  }
+  load_tail_weights(sm.W, reinterpret_cast<const float*>(a.arena4) + a.fk.dec_off, tid, NT_BWD);
+  // per-ray inputs of the loss (owner: sample 0 of the ray, sdf half) and the normalisers travel global -> shared
+  // asynchronously in the weights' copy group; the outlier mask (a byte) goes through a register
+  const bool ray_owner = half == 0 && valid && k == 0;
+  int pre_m = 1;
+  if (ray_owner) {
+    cp_async_small<4>(&sm.rayd[rl], a.gt_depth + ray);
+#pragma unroll
+    for (int c = 0; c < 3; ++c) cp_async_small<8>(&sm.rayc[c][rl], a.gt_color + (long long)ray * 3 + c);
+    if (a.ray_mask) pre_m = (int)a.ray_mask[ray];
+  }
+  if (tid < 2) cp_async16(&sm.norm[4 * tid], a.norm + 4 * tid);
+  asm volatile("cp.async.commit_group;" ::: "memory");
+  int pose_frame = 0;
+  float pose_dir = 0.f;
+  if (GR && a.pose_grad && tid < rays_here * 12) {
+    const int r2 = tid / 12, el = tid - r2 * 12, col = el & 3;
+    const int slot = a.src[ray0 + r2];
+    pose_frame = slot / a.n_per_img;
+    if (col < 3) {
+      const long long pix = a.pix_idx[slot];
+      const float pi = (float)(a.W0 + (int)(pix % a.Wc)), pj = (float)(a.H0 + (int)(pix / a.Wc));
+      pose_dir = col == 0 ? __fdiv_rn(__fsub_rn(pi, a.cx), a.fx) : (col == 1 ? -__fdiv_rn(__fsub_rn(pj, a.cy), a.fy) : -1.0f);
+    }
+  }
+  if (!CACHED || GR) write_axis_setups<2>(a.fk, 2 * half, pn, sm.ax_i + 6 * half, sm.ax_f + 6 * half, q);
+  __syncthreads();
+  PHASE_MARK(0);
+  float h1[16], h2[16], out[3] = {0.f, 0.f, 0.f};
+  float sdf = 0.f, u = 0.f, e = 0.f, alpha = 0.f, one = 1.f, rgb[3] = {0.f, 0.f, 0.f};
+  const float* Wh = sm.W + half * QW_STRIDE - DW_B1;  // field.cuh's DW_* offsets minus the absent W1
+  float4* Ph = sm.P[half];
+  float* Rh = sm.R[half];
+  float beta;
+  if (CACHED) {
+    PHASE_MARK(1);
+    decoder_weights_wait();
+    __syncthreads();
+    PHASE_MARK(2);
+    beta = sm.W[2 * QW_STRIDE];
+    unsigned m = 0u;
+    if (valid) {
+      const float4 c4 = a.act4[(long long)ray * S + k];
+      if (half == 0) {
+        m = __float_as_uint(c4.w);
+        sdf = a.sdf_in[(long long)ray * S + k];
+      } else {
+        m = a.actm[(long long)ray * S + k];
+        rgb[0] = c4.x;
+        rgb[1] = c4.y;
+        rgb[2] = c4.z;
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+      h1[j] = (m >> j) & 1u ? 1.f : 0.f;
+      h2[j] = (m >> (16 + j)) & 1u ? 1.f : 0.f;
+    }
+  } else {
+    // ---- P2: first-layer pre-activations (without bias) from the Q images, and J
+    if (half == 0)
+      gather_preact_rows<0, GR>(a.fk, a.q4, sm.ax_i, sm.ax_f, Ph, Rh, n_valid, q);
+    else
+      gather_preact_rows<1, GR>(a.fk, a.q4, sm.ax_i, sm.ax_f, Ph, Rh, n_valid, q);
+    PHASE_MARK(1);
+    decoder_weights_wait();
+    __syncthreads();
+    PHASE_MARK(2);
+    // ---- P3: layers 2 and 3 of this half's decoder
+    beta = sm.W[2 * QW_STRIDE];
+    mlp_tail_s(Wh, Ph, q, h1, h2, out);
+    if (half == 0)
+      sdf = tanhf(out[0]);
+    else {
+#pragma unroll
+      for (int c = 0; c < 3; ++c) rgb[c] = sigmoidf_(out[c]);
+    }
+  }
+  if (half == 0) {
+    sdf_to_alpha(sdf, beta, u, e, alpha);
+    one = __fadd_rn(__fsub_rn(1.0f, alpha), 1e-10f);
+    sm.one[q] = one;
+    sm.z[q] = zk;
+  } else {
+#pragma unroll
+    for (int c = 0; c < 3; ++c) sm.c[c][q] = rgb[c];
+  }
+  PHASE_MARK(3);
+  __syncthreads();
+  PHASE_MARK(4);
+  // ---- P4: compositing (sdf half)
+  float T = 1.0f, w = 0.f;
+  if (half == 0) {
+    for (int j = 0; j < k; ++j) T *= sm.one[rl * S + j];
+    w = valid ? alpha * T : 0.f;
+    sm.w[q] = w;
+  }
+  __syncthreads();
+  if (half == 0 && valid && k < 4) {
+    const float* v = (k == 0) ? sm.z : sm.c[k - 1];
+    float acc = 0.f;
+    for (int j = 0; j < S; ++j) acc = fmaf(sm.w[rl * S + j], v[rl * S + j], acc);
+    sm.rayv[k][rl] = acc;
+  }
+  __syncthreads();
+  // ---- P5: upstream gradients of depth / rgb per ray, and the loss sums
+  double ls[5] = {0.0, 0.0, 0.0, 0.0, 0.0};  // fs, center, tail, depth, colour
+  const int n_all = sm.norm[0], n_mask = sm.norm[2];
+  const float inv_f = a.w_fs / (float)sm.norm[3], inv_c = a.w_center / (float)sm.norm[4],
+              inv_t = a.w_tail / (float)sm.norm[5];
+  if (ray_owner) {
+    const float d = sm.rayd[rl];
+    const int m = a.ray_mask ? pre_m : (d > 0.f ? 1 : 0);
+    const float dr = sm.rayv[0][rl];
+    float gd = 0.f;
+    if (m) {
+      const float diff = d - dr;
+      gd = -2.0f * diff * (a.w_depth / (float)n_mask);
+      ls[3] = (double)(diff * diff);
+    }
+    sm.rayg[0][rl] = gd;
+    const bool col = a.ray_mask ? (m != 0) : true;
+    const double ncol = 3.0 * (double)(a.ray_mask ? n_mask : n_all);
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      float g = 0.f;
+      if (col) {
+        const double diff = sm.rayc[c][rl] - (double)sm.rayv[1 + c][rl];
+        g = (float)(-2.0 * diff * (a.w_color / ncol));
+        ls[4] += diff * diff;
+      }
+      sm.rayg[1 + c][rl] = g;
+    }
+    sm.raym[rl] = m;
+  }
+  __syncthreads();
+  // ---- compositing backward -> gradient at this half's decoder outputs
+  float g_beta = 0.f, gout[3] = {0.f, 0.f, 0.f};
+  {
+    float gw = 0.f;
+    if (half == 0) {
+      gw = sm.rayg[0][rl] * zk + sm.rayg[1][rl] * sm.c[0][q] + sm.rayg[2][rl] * sm.c[1][q] + sm.rayg[3][rl] * sm.c[2][q];
+      sm.gww[q] = valid ? gw * w : 0.f;
+    } else if (valid) {
+      const float ww = sm.w[q];
+#pragma unroll
+      for (int c = 0; c < 3; ++c) gout[c] = sm.rayg[1 + c][rl] * ww * rgb[c] * (1.0f - rgb[c]);
+    }
+    __syncthreads();
+    if (half == 0 && valid) {
+      float gdir = 0.f;
+      if (sm.raym[rl]) {
+        const float d = sm.rayd[rl];
+        const int band = sdf_band(zk, d, a.tr, a.tr04);
+        if (band == 0) {
+          const float r = sdf - 1.0f;
+          gdir = 2.0f * r * inv_f;
+          ls[0] = (double)(r * r);
+        } else if (band < 3) {
+          const float r = __fadd_rn(zk, __fmul_rn(sdf, a.tr)) - d;
+          gdir = 2.0f * r * a.tr * (band == 1 ? inv_c : inv_t);
+          ls[band] = (double)(r * r);
+        }
+      }
+      float B = 0.f;
+      for (int j = k + 1; j < S; ++j) B += sm.gww[rl * S + j];
+      const float g_alpha = gw * T - B / one;
+      const float du = u * (1.0f - u);
+      const float g_sdf = gdir + g_alpha * (-beta * beta * e * du);
+      g_beta = g_alpha * e * (u - beta * sdf * du);
+      gout[0] = g_sdf * (1.0f - sdf * sdf);
+    }
+  }
+  PHASE_MARK(5);
+  // ---- P6: backward through layers 3 and 2 -> gradient at the pre-activations
+  float ga1[16], ga2[16];
+  mlp_backward_hidden_s(Wh, gout, h1, h2, ga1, ga2);  // sdf: gout[1] = gout[2] = 0
+  PHASE_MARK(6);
+  if (GR && !CACHED) {  // coordinate gradient: J^T g (the thread's own row, written by the gather)
+    const float* row = Rh + q * RS;
+#pragma unroll
+    for (int ax = 0; ax < 3; ++ax) {
+      float acc = 0.f;
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        const float4 j4 = lds4(row + ax * 16 + c * 4);
+        acc = fmaf(j4.x, ga1[c * 4], acc);
+        acc = fmaf(j4.y, ga1[c * 4 + 1], acc);
+        acc = fmaf(j4.z, ga1[c * 4 + 2], acc);
+        acc = fmaf(j4.w, ga1[c * 4 + 3], acc);
+      }
+      sm.gp[half][ax][q] = valid ? acc : 0.f;
+    }
+  }
+  const bool wg = GF && !(a.dbg & 2);
+  if (GF) {
+    const float gb = warp_sum(g_beta);
+    if (lane == 0) sm.red[warp] = gb;
+  }
+  weight_grads_q(Rh, Ph, GF ? a.grad_arena + a.fk.dec_off : nullptr, half, q, h1, h2, ga1, ga2, gout, wg);
+  PHASE_MARK(7);
+  if (GF && tid == 0) {
+    float gb = 0.f;
+    for (int i = 0; i < NP / 32; ++i) gb += sm.red[i];  // only the sdf half carries beta gradients
+    atomicAdd(a.grad_arena + a.fk.dec_off + P_BETA, gb);
+  }
+  PHASE_MARK(8);
+  // ---- P7: reductions into the gradient images (gather layout, each half its own decoder) / cached coordinate gradients
+  {
+    const int wl = (tid & (NP - 1)) >> 5;
+    if (GF) {
+      const int qb = wl * 32 + (lane >> 3) * 8;  // 8 consecutive points per 8-lane group
+      if (a.dbg & 1) {
+      } else if (half == 0)
+        scatter_q<0>(a.fk, a.gq4, sm.ax_i, sm.ax_f, Ph, qb, n_valid, lane & 7);
+      else
+        scatter_q<1>(a.fk, a.gq4, sm.ax_i, sm.ax_f, Ph, qb, n_valid, lane & 7);
+    } else if (CACHED) {
+      if (half == 0)
+        coord_grads_q<0>(a.fk, a.q4, sm.ax_i, sm.ax_f, Ph, wl, lane >> 2, lane & 3, n_valid, sm.gp[0]);
+      else
+        coord_grads_q<1>(a.fk, a.q4, sm.ax_i, sm.ax_f, Ph, wl, lane >> 2, lane & 3, n_valid, sm.gp[1]);
+    }
+  }
+  PHASE_MARK(9);
+  // ---- P8: ray / pose gradients
+  if (GR) {
+    __syncthreads();
+    for (int t = tid; t < rays_here * 6; t += NT_BWD) {
+      const int r2 = t / 6, comp = t - r2 * 6, ax = comp % 3;
+      const bool is_d = comp >= 3;
+      const float scale = 2.0f / (a.fk.hi[ax] - a.fk.lo[ax]);
+      float acc = 0.f;
+      for (int j = 0; j < S; ++j) {
+        const float g = (sm.gp[0][ax][r2 * S + j] + sm.gp[1][ax][r2 * S + j]) * scale;
+        acc += is_d ? g * sm.z[r2 * S + j] : g;
+      }
+      sm.rayod[comp][r2] = acc;
+    }
+    if (a.pose_grad) {
+      __syncthreads();
+      if (tid < rays_here * 12) {
+        const int r2 = tid / 12, el = tid - r2 * 12, row = el >> 2, col = el & 3;
+        const float val = col == 3 ? sm.rayod[row][r2]               // d loss / d t
+                                   : sm.rayod[3 + row][r2] * pose_dir;  // d loss / d R[row][col]
+        atomicAdd(a.pose_grad + pose_frame * 12 + el, val);
+      }
+    }
+  }
+  PHASE_MARK(10);
+  // ---- loss sums
+  if (a.loss_acc) {
+#pragma unroll
+    for (int i = 0; i < 5; ++i) {
+      const double v = warp_sum_d(ls[i]);
+      if (lane == 0) sm.redd[warp * 5 + i] = v;
+    }
+    __syncthreads();
+    if (tid < 5) {
+      double v = 0.0;
+      for (int i = 0; i < NP / 32; ++i) v += sm.redd[i * 5 + tid];  // only the sdf half accumulates losses
+      atomicAdd(a.loss_acc + tid, v);
+    }
+  }
+}
+
+// tracker: pose gradient on the activations k_render_fwd_q kept (eslam_pose_backward_q)
+__global__ void __launch_bounds__(NT_BWD, 2) k_pose_bwd_q(const __grid_constant__ BwdArgs a) {
+  render_bwd_q_body<false, true, true>(a);
+}
+
+// mapper: gradient images + decoder gradients (+ poses) (eslam_loss_backward_q)
+template <bool GR>
+__global__ void __launch_bounds__(NT_BWD, 2) k_map_bwd_q(const __grid_constant__ BwdArgs a) {
+  render_bwd_q_body<true, GR, false>(a);
+}
+
+}  // namespace eslam

@@ -1,6 +1,6 @@
-// EXPERIMENTAL -- device-side building blocks of the Q form: the first decoder layer applied to
-// the planes (16-channel images Q = W1_half . plane, 64 bytes per texel) instead of to every sample.  Included by
-// render.cuh; the kernels that use them are in qplane.cuh and, for the backward, render_bwd_body<.., QF = true>.
+// Device-side building blocks of the Q form: the first decoder layer applied to the planes
+// (16-channel images Q = W1_slice . plane, 64 bytes per texel) instead of to every sample.  Included by render.cuh;
+// the kernels that use them are in qplane.cuh (image build, forward, optimiser tail) and qbwd.cuh (backward).
 // Gather layout of the Q form: 4 lanes per point, lane `sub` holds pre-activations 4*sub..4*sub+3.
 #pragma once
 #include "field.cuh"
@@ -165,110 +165,60 @@ __device__ __forceinline__ void coord_grads_q(const FieldK& fk, const float4* __
   }
 }
 
-// Q form of scatter_group for the mapping backward: P holds the gradient at the first layer's pre-activations.
-// 8-lane groups over 8 consecutive points of a ray as in scatter_group; within a group lanes 0-3 own the coarse scale
-// and lanes 4-7 the fine scale of the SAME points (lane & 3 = float4 of the 16-channel texel), so one code path serves
-// both scales and the run-length merge of the coarse cells keeps its run length.
-//   pass 1 (GF): tap-major reductions into the GQ images, four corner sums kept in registers while the cell repeats
-//   pass 2 (GR): point-major coordinate gradients, the scale's 12 corner loads in flight
-template <bool GF, bool GR, int FIELD>
-__device__ __forceinline__ void scatter_q(const FieldK& fk, const float4* __restrict__ q4, float4* __restrict__ gq4,
-                                          const ax_t (*ax_i)[NP], const float (*ax_f)[NP], const float4* P, int qb,
-                                          int n_valid, int sub8, float (*gp)[NP], int dbg) {
+// Q form of scatter_group's reductions for the mapping backward: P holds the gradient at the first layer's
+// pre-activations.  8-lane groups over 8 consecutive points of a ray as in scatter_group; within a group lanes 0-3 own
+// the coarse scale and lanes 4-7 the fine scale of the SAME points (lane & 3 = float4 of the 16-channel texel), so one
+// code path serves both scales and the run-length merge of the coarse cells keeps its run length: tap-major
+// reductions into the GQ images, four corner sums kept in registers while the cell repeats.
+// (The coordinate gradients need no corner fetch here: qbwd.cuh keeps J = d pre-activation / d coordinate.)
+template <int FIELD>
+__device__ __forceinline__ void scatter_q(const FieldK& fk, float4* __restrict__ gq4, const ax_t (*ax_i)[NP],
+                                          const float (*ax_f)[NP], const float4* P, int qb, int n_valid, int sub8) {
   const int sc = sub8 >> 2, sub = sub8 & 3;
   const int axb = FIELD * 6 + sc * 3;
-  const bool do_red = GF && !(dbg & 1);
-  if (do_red) {
 #pragma unroll
-    for (int p = 0; p < 3; ++p) {
-      const PlaneK pl = fk.pl[axb + p];
-      const int qoff = pl.off4 >> 1;
-      const int au = axb + pair_u(p), av = axb + pair_v(p);
-      int cur = -1, cdx = 0, cdy = 0;
-      float4 a00 = f4_zero(), a01 = f4_zero(), a10 = f4_zero(), a11 = f4_zero();
-#pragma unroll 1
-      for (int it = 0; it < 8; ++it) {
-        const int q = qb + it;
-        if (q < n_valid) {
-          const int u0 = ax_i[au][q], v0 = ax_i[av][q];
-          const float fu = ax_f[au][q], fv = ax_f[av][q];
-          const int base = qoff + (v0 * pl.W + u0) * 4 + sub;
-          const float4 g4 = P[p_slot(q, sub)];
-          const float w00 = (1.f - fu) * (1.f - fv), w01 = fu * (1.f - fv), w10 = (1.f - fu) * fv, w11 = fu * fv;
-          if (base != cur) {
-            if (cur >= 0) {
-              red_add_v4(gq4 + cur, a00);
-              red_add_v4(gq4 + cur + cdx, a01);
-              red_add_v4(gq4 + cur + cdy, a10);
-              red_add_v4(gq4 + cur + cdy + cdx, a11);
-            }
-            cur = base;
-            cdx = (u0 + 1 < pl.W) ? 4 : 0;
-            cdy = (v0 + 1 < pl.H) ? pl.W * 4 : 0;
-            a00 = f4_mul(w00, g4);
-            a01 = f4_mul(w01, g4);
-            a10 = f4_mul(w10, g4);
-            a11 = f4_mul(w11, g4);
-          } else {
-            a00 = f4_fma(w00, g4, a00);
-            a01 = f4_fma(w01, g4, a01);
-            a10 = f4_fma(w10, g4, a10);
-            a11 = f4_fma(w11, g4, a11);
-          }
-        }
-      }
-      if (cur >= 0) {
-        red_add_v4(gq4 + cur, a00);
-        red_add_v4(gq4 + cur + cdx, a01);
-        red_add_v4(gq4 + cur + cdy, a10);
-        red_add_v4(gq4 + cur + cdy + cdx, a11);
-      }
-    }
-  }
-  if (GR) {
+  for (int p = 0; p < 3; ++p) {
+    const PlaneK pl = fk.pl[axb + p];
+    const int qoff = pl.off4 >> 1;
+    const int au = axb + pair_u(p), av = axb + pair_v(p);
+    int cur = -1, cdx = 0, cdy = 0;
+    float4 a00 = f4_zero(), a01 = f4_zero(), a10 = f4_zero(), a11 = f4_zero();
 #pragma unroll 1
     for (int it = 0; it < 8; ++it) {
       const int q = qb + it;
-      float gpn[3] = {0.f, 0.f, 0.f};
       if (q < n_valid) {
+        const int u0 = ax_i[au][q], v0 = ax_i[av][q];
+        const float fu = ax_f[au][q], fv = ax_f[av][q];
+        const int base = qoff + (v0 * pl.W + u0) * 4 + sub;
         const float4 g4 = P[p_slot(q, sub)];
-        float4 v[3][4];
-        int u0[3], v0[3];
-        float fu[3], fv[3];
-#pragma unroll
-        for (int p = 0; p < 3; ++p) {
-          const PlaneK pl = fk.pl[axb + p];
-          const int au = axb + pair_u(p), av = axb + pair_v(p);
-          u0[p] = ax_i[au][q];
-          v0[p] = ax_i[av][q];
-          fu[p] = ax_f[au][q];
-          fv[p] = ax_f[av][q];
-          const int base = (pl.off4 >> 1) + (v0[p] * pl.W + u0[p]) * 4 + sub;
-          const int dx = (u0[p] + 1 < pl.W) ? 4 : 0, dy = (v0[p] + 1 < pl.H) ? pl.W * 4 : 0;
-          v[p][0] = ldg4(q4 + base);
-          v[p][1] = ldg4(q4 + base + dx);
-          v[p][2] = ldg4(q4 + base + dy);
-          v[p][3] = ldg4(q4 + base + dy + dx);
-        }
-#pragma unroll
-        for (int p = 0; p < 3; ++p) {
-          const PlaneK pl = fk.pl[axb + p];
-          const float d00 = f4_dot(g4, v[p][0]), d01 = f4_dot(g4, v[p][1]);
-          const float d10 = f4_dot(g4, v[p][2]), d11 = f4_dot(g4, v[p][3]);
-          const float du = (d01 - d00) * (1.f - fv[p]) + (d11 - d10) * fv[p];
-          const float dv = (d10 - d00) * (1.f - fu[p]) + (d11 - d01) * fu[p];
-          gpn[pair_u(p)] = fmaf(du, axis_grad_mult(u0[p], fu[p], pl.W), gpn[pair_u(p)]);
-          gpn[pair_v(p)] = fmaf(dv, axis_grad_mult(v0[p], fv[p], pl.H), gpn[pair_v(p)]);
+        const float w00 = (1.f - fu) * (1.f - fv), w01 = fu * (1.f - fv), w10 = (1.f - fu) * fv, w11 = fu * fv;
+        if (base != cur) {
+          if (cur >= 0) {
+            red_add_v4(gq4 + cur, a00);
+            red_add_v4(gq4 + cur + cdx, a01);
+            red_add_v4(gq4 + cur + cdy, a10);
+            red_add_v4(gq4 + cur + cdy + cdx, a11);
+          }
+          cur = base;
+          cdx = (u0 + 1 < pl.W) ? 4 : 0;
+          cdy = (v0 + 1 < pl.H) ? pl.W * 4 : 0;
+          a00 = f4_mul(w00, g4);
+          a01 = f4_mul(w01, g4);
+          a10 = f4_mul(w10, g4);
+          a11 = f4_mul(w11, g4);
+        } else {
+          a00 = f4_fma(w00, g4, a00);
+          a01 = f4_fma(w01, g4, a01);
+          a10 = f4_fma(w10, g4, a10);
+          a11 = f4_fma(w11, g4, a11);
         }
       }
-#pragma unroll
-      for (int c = 0; c < 3; ++c) {
-        float s = gpn[c];
-        s += __shfl_xor_sync(0xffffffffu, s, 1);
-        s += __shfl_xor_sync(0xffffffffu, s, 2);
-        s += __shfl_xor_sync(0xffffffffu, s, 4);
-        if (sub8 == 0) gp[c][q] = s;
-      }
+    }
+    if (cur >= 0) {
+      red_add_v4(gq4 + cur, a00);
+      red_add_v4(gq4 + cur + cdx, a01);
+      red_add_v4(gq4 + cur + cdy, a10);
+      red_add_v4(gq4 + cur + cdy + cdx, a11);
     }
   }
 }

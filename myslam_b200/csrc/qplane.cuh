@@ -16,48 +16,90 @@
 
 namespace eslam {
 
-struct QBuildArgs {
-  FieldK fk;
-  const float4* arena4;
-  const float* dec;  // packed decoder block (include/eslam_b200.h)
-  float4* q4;
+// The three planes of a (decoder, scale) group are contiguous in the arena and share one 16 x 32 slice of W1, so the
+// dense kernels below work on four flat texel ranges instead of twelve planes.
+struct QGroups {
+  int t0[4];     // first texel (arena float offset / 32) of group g = decoder * 2 + scale
+  int n[4];      // texels of the group
+  int unit0[5];  // first work unit (CTA or warp chunk) of the group; unit0[4] = total
 };
 
-// grid (x, 12): blockIdx.y = plane; 8 lanes per texel, lane `sub` holds input channels 4*sub..4*sub+3
+inline int make_q_groups(const eslam_field_t* f, int texels_per_unit, QGroups* out) {
+  int units = 0;
+  for (int g = 0; g < 4; ++g) {
+    long long n = 0;
+    for (int p = 0; p < 3; ++p) {
+      const eslam_plane_t& pl = f->plane[g * 3 + p];
+      if (pl.offset % 32 != 0) return ESLAM_EINVAL;
+      if (p > 0 && pl.offset != f->plane[g * 3 + p - 1].offset +
+                                    (long long)f->plane[g * 3 + p - 1].H * f->plane[g * 3 + p - 1].W * 32)
+        return ESLAM_EUNSUPPORTED;  // the planes of a group must be contiguous
+      n += (long long)pl.H * pl.W;
+    }
+    if (n > 0x3fffffff) return ESLAM_EUNSUPPORTED;
+    out->t0[g] = (int)(f->plane[g * 3].offset / 32);
+    out->n[g] = (int)n;
+    out->unit0[g] = units;
+    units += (int)((n + texels_per_unit - 1) / texels_per_unit);
+  }
+  out->unit0[4] = units;
+  return 0;
+}
+
+__device__ __forceinline__ int q_group_of(const QGroups& qg, int unit) {
+  return (unit >= qg.unit0[2]) ? (unit >= qg.unit0[3] ? 3 : 2) : (unit >= qg.unit0[1] ? 1 : 0);
+}
+
+struct QBuildArgs {
+  QGroups qg;
+  const float4* arena4;
+  const float* dec;  // packed decoder block (include/eslam_b200.h)
+  float2* q2;
+};
+
+// Q = W1_slice . texel for every texel of the map.  W1 changes with every optimiser step, so this runs once per
+// mapping iteration over all 212 k texels (room0): 27 MB read, 13.5 MB written, both L2 resident.  One CTA = QB_TPC
+// texels of one group: the tile is staged into shared memory with fully coalesced 16-byte loads (every byte in
+// flight is a distinct byte: 16 KB per CTA), then thread (texel, half) computes 8 of the texel's 16 outputs.
+constexpr int QB_TPC = 128;
+
+// swizzled texel tile: row t holds 8 float4; physical slot = c4 ^ (t & 7) (conflict-free for thread-per-row readers)
+__device__ __forceinline__ int t_slot(int t, int c4) { return t * 8 + (c4 ^ (t & 7)); }
+
 __global__ void __launch_bounds__(256) k_q_build(const __grid_constant__ QBuildArgs a) {
   __shared__ __align__(16) float sW[16 * 32];
-  const int pi = blockIdx.y;
-  const int field = pi / 6, scale = (pi % 6) / 3;
-  const int off4 = a.fk.pl[pi].off4;
-  const long long n = (long long)a.fk.pl[pi].H * a.fk.pl[pi].W;
-  const float* w1 = a.dec + (field ? C_W1 : S_W1) + scale * 32;  // columns of this scale (coarse | fine, decoders.py:84)
+  __shared__ float4 sT[QB_TPC * 8];
+  const int g = q_group_of(a.qg, blockIdx.x);
+  const int tl0 = (blockIdx.x - a.qg.unit0[g]) * QB_TPC;
+  const int cnt = min(QB_TPC, a.qg.n[g] - tl0);
+  const long long tbase = (long long)a.qg.t0[g] + tl0;
+  const float4* src = a.arena4 + tbase * 8;
+#pragma unroll
+  for (int u = 0; u < QB_TPC * 8 / 256; ++u) {
+    const int i = u * 256 + threadIdx.x, t = i >> 3;
+    if (t < cnt) sT[t_slot(t, i & 7)] = ldg4(src + i);
+  }
+  const float* w1 = a.dec + ((g >> 1) ? C_W1 : S_W1) + (g & 1) * 32;  // columns of this scale (coarse | fine, decoders.py:84)
   for (int i = threadIdx.x; i < 16 * 32; i += 256) sW[i] = w1[(i >> 5) * 64 + (i & 31)];
   __syncthreads();
-  const int sub = threadIdx.x & 7;
-  const long long n4 = (n + 3) & ~3ll;  // whole warps (4 texels each) per trip: the shuffles below are convergent
-  for (long long idx = (long long)blockIdx.x * 32 + (threadIdx.x >> 3); idx < n4; idx += (long long)gridDim.x * 32) {
-    const bool valid = idx < n;
-    const long long id = valid ? idx : n - 1;
-    const float4 t = ldg4(a.arena4 + off4 + id * 8 + sub);
-    float acc[16];
+  const int t = threadIdx.x >> 1, half = threadIdx.x & 1;
+  if (t >= cnt) return;
+  float o[8];
 #pragma unroll
-    for (int j = 0; j < 16; ++j) {
-      const float4 wj = lds4(sW + j * 32 + sub * 4);
-      acc[j] = fmaf(wj.w, t.w, fmaf(wj.z, t.z, fmaf(wj.y, t.y, wj.x * t.x)));
-    }
+  for (int j = 0; j < 8; ++j) o[j] = 0.f;
+  const float* w = sW + half * 8 * 32;
 #pragma unroll
-    for (int off = 1; off < 8; off <<= 1)
+  for (int c4 = 0; c4 < 8; ++c4) {
+    const float4 x = sT[t_slot(t, c4)];
 #pragma unroll
-      for (int j = 0; j < 16; ++j) acc[j] += __shfl_xor_sync(0xffffffffu, acc[j], off);
-    if (valid && sub < 4) {
-      float4 o;
-      o.x = sub == 0 ? acc[0] : sub == 1 ? acc[4] : sub == 2 ? acc[8] : acc[12];
-      o.y = sub == 0 ? acc[1] : sub == 1 ? acc[5] : sub == 2 ? acc[9] : acc[13];
-      o.z = sub == 0 ? acc[2] : sub == 1 ? acc[6] : sub == 2 ? acc[10] : acc[14];
-      o.w = sub == 0 ? acc[3] : sub == 1 ? acc[7] : sub == 2 ? acc[11] : acc[15];
-      a.q4[(long long)(off4 >> 1) + id * 4 + sub] = o;
+    for (int j = 0; j < 8; ++j) {
+      const float4 wj = lds4(w + j * 32 + c4 * 4);
+      o[j] = fmaf(wj.w, x.w, fmaf(wj.z, x.z, fmaf(wj.y, x.y, fmaf(wj.x, x.x, o[j]))));
     }
   }
+  float4* dst = reinterpret_cast<float4*>(a.q2) + (tbase + t) * 4 + half * 2;
+  dst[0] = make_float4(o[0], o[1], o[2], o[3]);
+  dst[1] = make_float4(o[4], o[5], o[6], o[7]);
 }
 
 struct SmemFwdQ {
@@ -72,101 +114,111 @@ struct SmemFwdQ {
 // images (layout of the Q arena).  Per texel the chain rule back to the parameters is dense and tiny:
 //     d loss / d plane[texel][c]   = sum_j W1[j][scale*32 + c] * GQ[texel][j]
 //     d loss / d W1[j][scale*32+c] = sum over the three planes of that scale and all texels of GQ[texel][j] * plane[texel][c]
-// so it is fused with the plane half of Adam: the plane gradient lives in registers only.  grid (x, 12): blockIdx.y =
-// plane; 8 lanes per texel, lane `sub` owns channels 4*sub..4*sub+3 of the texel (p, m, v) and the matching 16 x 4
-// slice of dW1, accumulated in registers over the CTA's texels and reduced once per CTA into the gradient arena's
-// decoder block (the decoders then take the ordinary Adam step, and k_q_build follows with the new W1).
-// Exact skip as in k_adam: a group of 4 texels whose GQ has been zero since the optimiser was created has m = v = 0
-// and a zero update; `touched` here is one flag per 4 texels of a plane (tq_base[plane] + texel / 4).
+// so it is fused with the plane half of Adam: the plane gradient lives in registers only.
+// One CTA = QA_TILE consecutive texels of one group, ONE THREAD PER TEXEL: the thread scans its texel's 64-byte
+// gradient row and `touched` byte; an active texel (non-zero row, or moments that are already non-zero) then takes
+// the whole 32-channel update in that thread, so a tile costs two dependent memory round trips however many of its
+// texels are active (an 8-lanes-per-texel form serialised up to 8 trips per warp and ran 40 us).  Exact skip as in
+// k_adam: a texel whose GQ has been zero since the optimiser was created has m = v = 0 and a zero update; a tile
+// without active texels ends after the scan.  dW1: rows and pre-update texels of the tile are parked in shared
+// memory and thread (j, c4) sums its four outputs over the tile's non-zero rows, one 16-byte reduction per thread
+// into the gradient arena's decoder block (the decoders then take the ordinary Adam step, k_q_build follows).
 struct QAdamArgs {
-  FieldK fk;
+  QGroups qg;      // units = tiles of QA_TILE texels
   float4* arena4;  // parameters; the planes are updated in place
   float4* gq4;     // gradient images, zeroed where consumed
   float4 *m4, *v4; // Adam moments in parameter-arena layout
   float* gdec;     // gradient arena's decoder block: dW1 is added here
   const float* dec;
-  unsigned char* touched;
-  int tq_base[12];
+  unsigned char* touched;  // one flag per texel, in texel order
   float step_sdf, step_rgb;  // lr / (1 - beta1^t) of the sdf / rgb planes
   AdamArgs adam;             // scalars only
 };
 
-__global__ void __launch_bounds__(256) k_q_adam_planes(const __grid_constant__ QAdamArgs a) {
+constexpr int QA_TILE = 128;
+
+__global__ void __launch_bounds__(QA_TILE, 4) k_q_adam_planes(const __grid_constant__ QAdamArgs a) {
   __shared__ __align__(16) float sW[16 * 32];
-  __shared__ float sdW[16 * 32];
-  const int pi = blockIdx.y;
-  const int field = pi / 6, scale = (pi % 6) / 3;
-  const int off4 = a.fk.pl[pi].off4;
-  const long long n = (long long)a.fk.pl[pi].H * a.fk.pl[pi].W;
-  const float* w1 = a.dec + (field ? C_W1 : S_W1) + scale * 32;
-  for (int i = threadIdx.x; i < 16 * 32; i += 256) {
-    sW[i] = w1[(i >> 5) * 64 + (i & 31)];
-    sdW[i] = 0.f;
+  __shared__ float4 sP[QA_TILE * 8];   // pre-update texels, t_slot layout
+  __shared__ float4 sG[QA_TILE * 4];   // gradient rows, p_slot layout
+  __shared__ int s_list[QA_TILE];
+  __shared__ int s_n;
+  const int g = q_group_of(a.qg, blockIdx.x);
+  const int t = threadIdx.x;
+  const int tl = (blockIdx.x - a.qg.unit0[g]) * QA_TILE + t;
+  const bool valid = tl < a.qg.n[g];
+  const long long texel = (long long)a.qg.t0[g] + tl;
+  // ---- scan
+  float4 r[4];
+  bool nz = false, flag = false;
+  if (valid) {
+    const float4* row = a.gq4 + texel * 4;
+#pragma unroll
+    for (int c = 0; c < 4; ++c) r[c] = row[c];
+    flag = a.touched[texel] != 0;
+#pragma unroll
+    for (int c = 0; c < 4; ++c) nz = nz || r[c].x != 0.f || r[c].y != 0.f || r[c].z != 0.f || r[c].w != 0.f;
+    if (nz && !flag) a.touched[texel] = 1;
+  }
+  const bool active = nz || flag;
+  if (t == 0) s_n = 0;
+  if (!__syncthreads_or(active)) return;  // nothing to do in this tile
+  const float* w1 = a.dec + ((g >> 1) ? C_W1 : S_W1) + (g & 1) * 32;
+  for (int i = t; i < 16 * 32; i += QA_TILE) sW[i] = w1[(i >> 5) * 64 + (i & 31)];
+  float4 pk[8];
+  if (active) {
+#pragma unroll
+    for (int c4 = 0; c4 < 8; ++c4) pk[c4] = a.arena4[texel * 8 + c4];
+  }
+  if (nz) {
+    s_list[atomicAdd(&s_n, 1)] = t;
+#pragma unroll
+    for (int c = 0; c < 4; ++c) sG[p_slot(t, c)] = r[c];
+#pragma unroll
+    for (int c4 = 0; c4 < 8; ++c4) sP[t_slot(t, c4)] = pk[c4];
   }
   __syncthreads();
-  const int lane = threadIdx.x & 31, sub = threadIdx.x & 7;
-  const float ss = field ? a.step_rgb : a.step_sdf;
-  float acc[16][4];
+  if (active) {
+    const float ss = (g >> 1) ? a.step_rgb : a.step_sdf;
+    const float gj[16] = {r[0].x, r[0].y, r[0].z, r[0].w, r[1].x, r[1].y, r[1].z, r[1].w,
+                          r[2].x, r[2].y, r[2].z, r[2].w, r[3].x, r[3].y, r[3].z, r[3].w};
+    const float4 z4 = f4_zero();
 #pragma unroll
-  for (int j = 0; j < 16; ++j)
+    for (int c4 = 0; c4 < 8; ++c4) {
+      const long long at = texel * 8 + c4;
+      float4 m = a.m4[at], v = a.v4[at], p = pk[c4];
+      float4 gr = z4;
+      if (nz) {
 #pragma unroll
-    for (int e = 0; e < 4; ++e) acc[j][e] = 0.f;
-  const float4 z4 = f4_zero();
-  const long long n4 = (n + 3) & ~3ll;  // whole warps (4 texels = one touched group) per trip
-  for (long long idx = (long long)blockIdx.x * 32 + (threadIdx.x >> 3); idx < n4; idx += (long long)gridDim.x * 32) {
-    const bool in = idx < n;
-    const long long id = in ? idx : n - 1;
-    float4* gq = a.gq4 + (long long)(off4 >> 1) + id * 4;
-    float4 g4[4];
-    bool nz = false;
-#pragma unroll
-    for (int c = 0; c < 4; ++c) {
-      g4[c] = in ? gq[c] : z4;
-      nz = nz || g4[c].x != 0.f || g4[c].y != 0.f || g4[c].z != 0.f || g4[c].w != 0.f;
+        for (int j = 0; j < 16; ++j) gr = f4_fma(gj[j], lds4(sW + j * 32 + c4 * 4), gr);
+      }
+      adam_one(p.x, gr.x, m.x, v.x, a.adam, ss);
+      adam_one(p.y, gr.y, m.y, v.y, a.adam, ss);
+      adam_one(p.z, gr.z, m.z, v.z, a.adam, ss);
+      adam_one(p.w, gr.w, m.w, v.w, a.adam, ss);
+      a.arena4[at] = p;
+      a.m4[at] = m;
+      a.v4[at] = v;
     }
-    const bool any = __ballot_sync(0xffffffffu, nz) != 0u;
-    unsigned char* flag = a.touched + a.tq_base[pi] + (idx >> 2);  // same byte for the whole warp
-    const bool was = *flag != 0;
-    if (!any && !was) continue;
-    if (!was && lane == 0) *flag = 1;
-    if (!in) continue;
-    const long long at = (long long)off4 + id * 8 + sub;
-    float4 p = a.arena4[at], m = a.m4[at], v = a.v4[at];
-    const float gj[16] = {g4[0].x, g4[0].y, g4[0].z, g4[0].w, g4[1].x, g4[1].y, g4[1].z, g4[1].w,
-                          g4[2].x, g4[2].y, g4[2].z, g4[2].w, g4[3].x, g4[3].y, g4[3].z, g4[3].w};
-    float4 g = z4;
+    if (nz) {
+      float4* row = a.gq4 + texel * 4;
 #pragma unroll
-    for (int j = 0; j < 16; ++j) {
-      const float4 wj = lds4(sW + j * 32 + sub * 4);
-      g = f4_fma(gj[j], wj, g);
-      acc[j][0] = fmaf(gj[j], p.x, acc[j][0]);
-      acc[j][1] = fmaf(gj[j], p.y, acc[j][1]);
-      acc[j][2] = fmaf(gj[j], p.z, acc[j][2]);
-      acc[j][3] = fmaf(gj[j], p.w, acc[j][3]);
+      for (int c = 0; c < 4; ++c) row[c] = z4;
     }
-    adam_one(p.x, g.x, m.x, v.x, a.adam, ss);
-    adam_one(p.y, g.y, m.y, v.y, a.adam, ss);
-    adam_one(p.z, g.z, m.z, v.z, a.adam, ss);
-    adam_one(p.w, g.w, m.w, v.w, a.adam, ss);
-    a.arena4[at] = p;
-    a.m4[at] = m;
-    a.v4[at] = v;
-    if (any && sub < 4) gq[sub] = z4;
   }
-  // dW1: lanes with the same `sub` (the 4 texels of a warp) first, then the CTA's warps, then one reduction per element
-#pragma unroll
-  for (int j = 0; j < 16; ++j)
-#pragma unroll
-    for (int e = 0; e < 4; ++e) {
-      float v = acc[j][e];
-      v += __shfl_xor_sync(0xffffffffu, v, 8);
-      v += __shfl_xor_sync(0xffffffffu, v, 16);
-      if (lane < 8 && v != 0.f) atomicAdd(&sdW[j * 32 + sub * 4 + e], v);
-    }
-  __syncthreads();
-  float* dst = a.gdec + (field ? C_W1 : S_W1) + scale * 32;
-  for (int i = threadIdx.x; i < 16 * 32; i += 256)
-    if (sdW[i] != 0.f) atomicAdd(dst + (i >> 5) * 64 + (i & 31), sdW[i]);
+  // ---- dW1 of the tile: thread (j, c4) over the non-zero rows
+  const int n = s_n;
+  if (n == 0) return;
+  const int j = t >> 3, c4 = t & 7;
+  float4 acc = f4_zero();
+  const float* sGf = reinterpret_cast<const float*>(sG);
+  for (int i = 0; i < n; ++i) {
+    const int tt = s_list[i];
+    const float gv = sGf[p_slot(tt, j >> 2) * 4 + (j & 3)];
+    acc = f4_fma(gv, sP[t_slot(tt, c4)], acc);
+  }
+  float4* dst = reinterpret_cast<float4*>(a.gdec + ((g >> 1) ? C_W1 : S_W1) + (g & 1) * 32);
+  if (acc.x != 0.f || acc.y != 0.f || acc.z != 0.f || acc.w != 0.f) red_add_v4(dst + j * 16 + c4, acc);
 }
 
 // layers 2 and 3 on h1 = relu(pre + b1), weights as constant-memory operands (field.cuh mlp_forward, minus layer 1)

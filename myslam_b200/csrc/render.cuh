@@ -611,8 +611,7 @@ struct BwdArgs {
   float* grad_arena;
   float *g_rays_o, *g_rays_d;
   float* pose_grad;
-  // experimental Q form (k_pose_bwd_q, k_map_bwd_q): the pre-activated plane images and, for the mapper, the gradient
-  // images the plane reductions go to; last, so that no other member moves
+  // Q form (qbwd.cuh): the Q images and, for the mapper, the gradient images the plane reductions go to
   const float4* q4;
   float4* gq4;
 };
@@ -776,9 +775,6 @@ __device__ __forceinline__ void half_sync(int half) {
 //   round 2  hidden and output layers: every owner thread parks (ga2 | h1 | h2 | gout) in ITS OWN row of the feature
 //            tile, which is dead after round 1 and is only rewritten by mlp_backward_input afterwards; per half:
 //            warps 0,1 dW2 (half of the points each, two tiles), warp 2 dW3 (two tiles), warp 3 db2 and db3
-// QF (experimental Q form): the input layer's weight gradient is formed per texel by the optimiser tail
-// (k_q_adam_planes), so round 1 only takes db1 and the feature tile is not read.
-template <bool QF = false>
 __device__ __forceinline__ void weight_grads(float* act0, float* act1, float4* F0, float4* F1, float* gdec, int half,
                                              int q, const float (&h1)[16], const float (&h2)[16], const float (&ga1)[16],
                                              const float (&ga2)[16], const float (&gout)[3]) {
@@ -801,15 +797,7 @@ __device__ __forceinline__ void weight_grads(float* act0, float* act1, float4* F
   }
   half_sync(half);
   const int g = lane >> 2, t = lane & 3;
-  if constexpr (QF) {
-    if (wl == 0) {
-      float acc[4];
-      const FromBuf a_lo(abuf, g, t), a_hi(abuf, g + 8, t);
-      wgrad_bias<16>(a_lo, a_hi, lane, acc);
-      wgrad_store_bias(gB1, 16, lane, acc);
-    }
-    (void)gW1;
-  } else {
+  {
     float acc[2][4];
     const FromBuf a_lo(abuf, g, t), a_hi(abuf, g + 8, t);
     const FromTile b[2] = {FromTile(F, wl * 16 + g, t), FromTile(F, wl * 16 + 8 + g, t)};
@@ -993,11 +981,10 @@ __device__ __forceinline__ void scatter_group(const FieldK& fk, int field, const
 // One CTA = NP points (whole rays) and NT_BWD = 2*NP threads: threads [0,NP) own the sdf decoder of point
 // q = tid, threads [NP,2NP) the rgb decoder of point q = tid-NP, so both decoders' gathers, MLPs and scatters
 // run side by side and every thread carries one decoder's activations only.
-// QF (experimental, qplane.cuh): pose-only backward of the tracker on the pre-activated plane images; the forward
-//         must have been k_render_fwd_q with activations (cached branch below).
-template <int MODE, bool GF, bool GR, bool QF>
+// This is the PARAMETER form (64-channel features, plane gradients into the gradient arena): autograd through
+// render_batch_ray / Decoders.forward and the cross-check of the Q form.  Both loops' iterations use qbwd.cuh.
+template <int MODE, bool GF, bool GR>
 __device__ __forceinline__ void render_bwd_body(const BwdArgs& a) {
-  static_assert(!QF || MODE == 1, "the Q form exists for the fused-loss mode (tracker and mapper iterations)");
   constexpr bool FUSED = MODE == 1;
   constexpr bool POINTS = MODE == 2;
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -1078,12 +1065,7 @@ __device__ __forceinline__ void render_bwd_body(const BwdArgs& a) {
     }
   } else {
   // ---- P2: gather this half's decoder features
-  if constexpr (QF) {  // first-layer pre-activations (without bias) from the Q images, p_slot layout
-    if (half == 0)
-      gather_preact_tile<0>(a.fk, a.q4, sm.ax_i, sm.ax_f, sm.F0, n_valid, q);
-    else
-      gather_preact_tile<1>(a.fk, a.q4, sm.ax_i, sm.ax_f, sm.F1, n_valid, q);
-  } else if (half == 0)
+  if (half == 0)
     gather_tile<0>(a.fk, 0, a.arena4, sm.ax_i, sm.ax_f, sm.F0, n_valid, q);
   else
     gather_tile<6>(a.fk, 1, a.arena4, sm.ax_i, sm.ax_f, sm.F1, n_valid, q);
@@ -1110,10 +1092,7 @@ __device__ __forceinline__ void render_bwd_body(const BwdArgs& a) {
       }
     }
   } else {
-    if constexpr (QF)
-      mlp_tail_s(Wh, Fh, q, h1, h2, out);
-    else
-      mlp_forward_s(Wh, Fh, q, h1, h2, out);
+    mlp_forward_s(Wh, Fh, q, h1, h2, out);
     if (half == 0) {
       sdf = tanhf(out[0]);
       sdf_to_alpha(sdf, beta, u, e, alpha);
@@ -1250,15 +1229,12 @@ __device__ __forceinline__ void render_bwd_body(const BwdArgs& a) {
   PHASE_MARK(6);
   if (GF && !(a.dbg & 2)) {
     float* gdec = a.grad_arena + a.fk.dec_off;
-    weight_grads<QF>(sm.act0, sm.act1, sm.F0, sm.F1, gdec, half, q, h1, h2, ga1, ga2, gout);
+    weight_grads(sm.act0, sm.act1, sm.F0, sm.F1, gdec, half, q, h1, h2, ga1, ga2, gout);
     const float gb = warp_sum(g_beta);
     if (lane == 0) sm.red[warp] = gb;
   }
   PHASE_MARK(7);
-  if constexpr (QF) {  // the first layer lives in the Q images: its pre-activation gradient is what the taps need
-#pragma unroll
-    for (int c = 0; c < 4; ++c) Fh[p_slot(q, c)] = make_float4(ga1[c * 4], ga1[c * 4 + 1], ga1[c * 4 + 2], ga1[c * 4 + 3]);
-  } else if (a.dbg & 4) {
+  if (a.dbg & 4) {
     Fh[q * 16] = make_float4(ga1[0], ga1[1], ga1[2], ga1[3]);
   } else {
     mlp_backward_input_s(Wh, ga1, Fh, q);
@@ -1271,20 +1247,7 @@ __device__ __forceinline__ void render_bwd_body(const BwdArgs& a) {
   }
   PHASE_MARK(8);
   // ---- P7: scatter to the planes / coordinate gradients (gather layout, each half its own decoder)
-  if constexpr (QF && GF) {
-    const int wl = (tid & (NP - 1)) >> 5;
-    const int qb = wl * 32 + (lane >> 3) * 8;  // 8 consecutive points per 8-lane group, as below
-    if (half == 0)
-      scatter_q<GF, GR, 0>(a.fk, a.q4, a.gq4, sm.ax_i, sm.ax_f, sm.F0, qb, n_valid, lane & 7, sm.gp[0], a.dbg);
-    else
-      scatter_q<GF, GR, 1>(a.fk, a.q4, a.gq4, sm.ax_i, sm.ax_f, sm.F1, qb, n_valid, lane & 7, sm.gp[1], a.dbg);
-  } else if constexpr (QF) {
-    const int wl = (tid & (NP - 1)) >> 5;
-    if (half == 0)
-      coord_grads_q<0>(a.fk, a.q4, sm.ax_i, sm.ax_f, sm.F0, wl, lane >> 2, lane & 3, n_valid, sm.gp[0]);
-    else
-      coord_grads_q<1>(a.fk, a.q4, sm.ax_i, sm.ax_f, sm.F1, wl, lane >> 2, lane & 3, n_valid, sm.gp[1]);
-  } else {
+  {
     const int wl = (tid & (NP - 1)) >> 5, grp = lane >> 3, sub = lane & 7;
     const int qb = wl * 32 + grp * 8;  // 8 consecutive points (samples along a ray) per 8-lane group
     float4* garena4 = reinterpret_cast<float4*>(a.grad_arena);
@@ -1350,21 +1313,9 @@ __device__ __forceinline__ void render_bwd_body(const BwdArgs& a) {
   (void)Fh;
 }
 
-// The kernels proper: the body is shared through render_bwd_body; the experimental Q form is its own __global__ function.
 template <int MODE, bool GF, bool GR>
 __global__ void __launch_bounds__(NT_BWD, 2) k_render_bwd(const __grid_constant__ BwdArgs a) {
-  render_bwd_body<MODE, GF, GR, false>(a);
-}
-
-__global__ void __launch_bounds__(NT_BWD, 2) k_pose_bwd_q(const __grid_constant__ BwdArgs a) {
-  render_bwd_body<1, false, true, true>(a);
-}
-
-// mapping iteration in the Q form: plane gradients as 16-channel reductions into the GQ images (a.gq4), decoder
-// gradients except dW1 into the gradient arena; the optimiser tail (k_q_adam_planes) turns GQ into dplane and dW1
-template <bool GR>
-__global__ void __launch_bounds__(NT_BWD, 2) k_map_bwd_q(const __grid_constant__ BwdArgs a) {
-  render_bwd_body<1, true, GR, true>(a);
+  render_bwd_body<MODE, GF, GR>(a);
 }
 
 }  // namespace eslam

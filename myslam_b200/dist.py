@@ -37,10 +37,12 @@ class MappingExchange:
             dist.all_reduce(self._norm, op=dist.ReduceOp.SUM, group=self.group)
         return self._norm
 
-    def reduce_grads(self, grad_arena: torch.Tensor, pose_grad=None, loss_acc=None) -> None:
+    def reduce_grads(self, grads, pose_grad=None, loss_acc=None) -> None:
+        """grads: the tensors holding this rank's map gradients (the gradient images and the decoder block)."""
         if self.world == 1:
             return
-        dist.all_reduce(grad_arena, op=dist.ReduceOp.SUM, group=self.group)
+        for g in ([grads] if torch.is_tensor(grads) else grads):
+            dist.all_reduce(g, op=dist.ReduceOp.SUM, group=self.group)
         if pose_grad is not None:
             dist.all_reduce(pose_grad, op=dist.ReduceOp.SUM, group=self.group)
         if loss_acc is not None:

@@ -112,12 +112,15 @@ class FieldStore:
         self.exp_avg_sq: Optional[torch.Tensor] = None
         self.touched: Optional[torch.Tensor] = None  # one flag per 128 parameters: any non-zero gradient since reset
         self._sig = None  # (data_ptr, version) of what was last pulled
-        # EXPERIMENTAL: 16-channel pre-activated plane images for the tracker's Q path; kept in
-        # step with the parameters by bind() while want_q is set (ESLAM_B200_QTRACK=1, see tracker._tracker_store)
-        self.want_q = False
+        # generation of the parameter arena: bumped by everything that writes it (imports, optimiser steps, exchanges).
+        # The Q images and autograd contexts remember the generation they were made from.
+        self.gen = 0
+        # Q images: the first decoder layer applied to the planes, 16 channels per texel, plane i
+        # at half the float offset of plane i in the parameter arena.  The render kernels of both loops read these.
         self.q_arena: Optional[torch.Tensor] = None
-        self.gq_arena: Optional[torch.Tensor] = None   # gradient images of the Q-form mapping backward
-        self.touched_q: Optional[torch.Tensor] = None  # exact-skip flags of eslam_q_adam_planes (one per 4 texels)
+        self.q_gen = -1
+        self.gq_arena: Optional[torch.Tensor] = None   # gradient images of the mapping backward (layout of q_arena)
+        self.touched_q: Optional[torch.Tensor] = None  # exact-skip flags of eslam_q_adam_planes (one per texel)
 
     # ------------------------------------------------------------------ construction helpers
     @classmethod
@@ -154,6 +157,7 @@ class FieldStore:
             if src.dtype != torch.float32 or not src.is_contiguous():
                 src = src.float().contiguous()
             call("eslam_plane_import", ptr(src), ptr(self.arena), C.byref(self.desc.plane[i]), stream())
+        self.gen += 1
 
     def pull_decoders(self, state: Dict[str, torch.Tensor], beta) -> None:
         dec = self.dec
@@ -163,6 +167,7 @@ class FieldStore:
                 dec[off:off + 1].copy_(val.detach().reshape(1).to(self.device, torch.float32), non_blocking=True)
             else:
                 dec[off:off + n].copy_(state[key].detach().reshape(-1), non_blocking=True)
+        self.gen += 1
 
     def signature(self, all_planes, dec_tensors) -> "Signature":
         return Signature(flatten_planes(all_planes) + list(dec_tensors))
@@ -195,19 +200,47 @@ class FieldStore:
         g = which[self.dec_off:self.dec_off + DEC_FLOATS]
         return {key: g[off:off + n] for key, off, n in DEC_LAYOUT}
 
+    def parameter_grads(self) -> torch.Tensor:
+        """Parameter-form gradient arena (layout of `arena`) from what eslam_loss_backward_q left: the gradient images
+        (d loss / d plane = GQ . W1_slice, dW1 = sum GQ (x) plane) and the decoder block of `grad`.  For callers that
+        want to LOOK at gradients (tests, autograd bridges); the optimiser consumes the images directly."""
+        out = torch.zeros_like(self.arena)
+        out[self.dec_off:] = self.grad[self.dec_off:]
+        for i in range(12):
+            h, w = self.shapes[i]
+            fld, sc = i // 6, (i % 6) // 3
+            w1 = self.dec_off + (1332 if fld else 0)
+            W = self.arena[w1:w1 + 1024].view(16, 64)[:, sc * 32:(sc + 1) * 32]
+            G = self.gq_arena[self.plane_off[i] // 2: self.plane_off[i] // 2 + h * w * 16].view(h * w, 16)
+            out[self.plane_off[i]: self.plane_off[i] + h * w * 32] = (G @ W).reshape(-1)
+            out[w1:w1 + 1024].view(16, 64)[:, sc * 32:(sc + 1) * 32] += G.t() @ self.plane_view(i).reshape(h * w, 32)
+        return out
+
     # ------------------------------------------------------------------ kernels' view
     def bind(self) -> None:
-        """Make this map's decoders the ones the kernels read (constant memory)."""
+        """Make this map's decoders the ones the forward-only kernels read (constant memory)."""
         call("eslam_bind_decoders", ptr(self.dec), stream())
-        if self.want_q:
-            if self.q_arena is None:
-                self.q_arena = torch.zeros(self.n_planes_end // 2, dtype=torch.float32, device=self.device)
+
+    def ensure_q(self) -> torch.Tensor:
+        """The Q images of the CURRENT parameters (rebuilt when the arena's generation moved on)."""
+        if self.q_arena is None:
+            self.q_arena = torch.zeros(self.n_planes_end // 2, dtype=torch.float32, device=self.device)
+        if self.q_gen != self.gen:
             call("eslam_q_build", self.ref(), ptr(self.arena), ptr(self.q_arena), stream())
+            self.q_gen = self.gen
+        return self.q_arena
 
     def ensure_grad(self) -> torch.Tensor:
         if self.grad is None:
             self.grad = torch.zeros_like(self.arena)
         return self.grad
+
+    def ensure_q_grad(self) -> torch.Tensor:
+        if self.gq_arena is None:
+            self.gq_arena = torch.zeros(self.n_planes_end // 2, dtype=torch.float32, device=self.device)
+            n = _lib.load().eslam_q_touched_bytes(self.ref())
+            self.touched_q = torch.zeros(n, dtype=torch.uint8, device=self.device)
+        return self.gq_arena
 
     def reset_adam(self) -> None:
         """Fresh optimiser state, as Mapper.optimize_mapping builds a new Adam per call (Mapper.py:291-299)."""
@@ -220,36 +253,37 @@ class FieldStore:
             self.exp_avg_sq.zero_()
             self.touched.zero_()
         self.ensure_grad().zero_()
-        if self.gq_arena is not None:
-            self.gq_arena.zero_()
-            self.touched_q.zero_()
+        self.ensure_q_grad().zero_()
+        self.touched_q.zero_()
 
     def adam_step_q(self, step: int, lr_dec: float, lr_planes: float, lr_cplanes: float, betas=(0.9, 0.999),
                     eps=1e-8) -> None:
-        """EXPERIMENTAL optimiser step of the Q form: the planes from the gradient images (which also yields dW1),
-        then the decoders with the ordinary kernel; zeroes the gradient images and the decoder gradients."""
+        """One torch.optim.Adam step (Mapper.py:348-350) from what eslam_loss_backward_q left: the planes from the
+        gradient images (eslam_q_adam_planes, which also completes dW1 in the gradient arena's decoder block), then
+        the decoders; zeroes the gradient images and the decoder gradients."""
+        if self.exp_avg is None or self.gq_arena is None:
+            raise RuntimeError("FieldStore.adam_step_q before reset_adam(): there is no optimiser state")
         call("eslam_q_adam_planes", self.ref(), ptr(self.arena), ptr(self.gq_arena), ptr(self.exp_avg),
              ptr(self.exp_avg_sq), ptr(self.grad), ptr(self.touched_q), lr_planes, lr_cplanes, step, betas[0], betas[1],
              eps, stream())
+        self.adam_step_decoders(step, lr_dec, betas, eps)
+
+    def adam_step_decoders(self, step: int, lr_dec: float, betas=(0.9, 0.999), eps=1e-8) -> None:
         seg_end = (C.c_int64 * 1)(DEC_FLOATS)
         seg_lr = (C.c_double * 1)(lr_dec)
         o = self.dec_off
         call("eslam_adam_step", ptr(self.arena[o:]), ptr(self.grad[o:]), ptr(self.exp_avg[o:]), ptr(self.exp_avg_sq[o:]),
              DEC_FLOATS, seg_end, seg_lr, 1, step, betas[0], betas[1], eps, stream())
-
-    def ensure_q_grad(self) -> torch.Tensor:
-        if self.gq_arena is None:
-            self.gq_arena = torch.zeros(self.n_planes_end // 2, dtype=torch.float32, device=self.device)
-            n = _lib.load().eslam_q_touched_bytes(self.ref())
-            self.touched_q = torch.zeros(n, dtype=torch.uint8, device=self.device)
-        return self.gq_arena
+        self.gen += 1
 
     def adam_step(self, step: int, lr_dec: float, lr_planes: float, lr_cplanes: float, betas=(0.9, 0.999),
                   eps=1e-8) -> None:
-        """One torch.optim.Adam step over planes (two lr groups) + decoders; zeroes the gradient arena."""
+        """One torch.optim.Adam step over planes (two lr groups) + decoders from the PARAMETER-form gradient arena
+        (what eslam_render_backward / eslam_loss_backward leave); zeroes the gradient arena."""
         seg_end = (C.c_int64 * 3)(self.n_sdf_end, self.n_planes_end, self.n_floats)
         seg_lr = (C.c_double * 3)(lr_planes, lr_cplanes, lr_dec)
         if self.exp_avg is None:
             raise RuntimeError("FieldStore.adam_step before reset_adam(): there is no optimiser state")
         call("eslam_adam_step_sparse", ptr(self.arena), ptr(self.grad), ptr(self.exp_avg), ptr(self.exp_avg_sq),
              self.n_floats, seg_end, seg_lr, 3, step, betas[0], betas[1], eps, ptr(self.touched), stream())
+        self.gen += 1

@@ -2,8 +2,13 @@
 sequence of kernel launches on the current stream, with no host synchronisation in the default
 mode:
 
-  tracking:  sample_rays -> render_forward -> track_mask -> loss_backward(pose) -> finalize -> pose Adam
-  mapping:   sample_rays -> importance_samples -> loss_backward(planes, decoders, poses) -> Adam -> pose Adam
+  tracking:  [q_build when the map changed] -> sample_rays -> render_forward_q -> track_mask -> pose_backward_q
+             -> finalize -> pose Adam
+  mapping:   q_build -> sample_rays -> importance_samples -> loss_backward_q(gradient images, decoders, poses)
+             -> q_adam_planes -> decoder Adam -> pose Adam
+
+Both loops run on the Q images of the map: the first (linear) decoder layer is applied to the planes once per
+parameter change instead of to every sample (decoders.py:87-125 commutes with the bilinear fetch of :64-85).
 
 `strict_rng=True` reproduces the reference's random-draw SHAPES ([R1,S], [R0,n_strat], [R0,n_imp]),
 which costs one host sync per iteration (the reference has >= 12); it is what parity runs use.
@@ -11,7 +16,6 @@ which costs one host sync per iteration (the reference has >= 12); it is what pa
 from __future__ import annotations
 
 import ctypes as C
-import os
 from dataclasses import dataclass
 from typing import Optional
 
@@ -137,7 +141,9 @@ def tracking_iteration(ws: Workspace, store: FieldStore, sc: StepCfg, pose7: tor
     the Adam step.  pose7: [1,7] contiguous fp32 device tensor (quaternion, translation).
     After the call: ws.loss_acc[5] = loss (float64), ws.grad7[0] = d loss / d pose.
     apply_adam: dict(step=, lr_q=, lr_t=[, m=, v=, betas=, eps=]) -> fused Adam (default betas .5,.999) on pose7 in
-    place, on the workspace's moments or on the given [1,7] rows."""
+    place, on the workspace's moments or on the given [1,7] rows.
+    The render kernels read the Q images of the map (FieldStore.ensure_q: rebuilt only when the parameters changed,
+    i.e. when the mapper published new planes; the decoders are frozen while tracking, Tracker.py:111-112)."""
     dev = ws.device
     draws = draws or TorchDraws(dev)
     cam, rc = sc.cam, sc.render
@@ -147,6 +153,7 @@ def tracking_iteration(ws: Workspace, store: FieldStore, sc: StepCfg, pose7: tor
     idx = draws.randint(n_crop, n_pixels)
     if bind:  # the decoders are frozen while a frame is tracked: a caller looping over iterations binds once
         store.bind()
+    q = store.ensure_q()
     if not sc.perturb:
         u = None
     elif strict_rng:
@@ -157,27 +164,16 @@ def tracking_iteration(ws: Workspace, store: FieldStore, sc: StepCfg, pose7: tor
     _sample(ws, store, sc, idx, 1, n_pixels, None, pose7, 0, gt_depth, gt_color, u, 1)
     N = n_pixels
     # the forward pass (needed first: the outlier mask is a median over the rendered depth, Tracker.py:192-195)
-    # keeps sdf, rgb and the ReLU masks of every sample, so the backward pass neither gathers features nor
-    # re-runs the forward MLPs
-    q = store.q_arena if store.want_q else None  # EXPERIMENTAL opt-in: the same two kernels on the Q images
-    if q is None:
-        call("eslam_render_forward_act", store.ref(), ptr(store.arena), ptr(ws.rays_o), ptr(ws.rays_d), ptr(ws.z), N, S,
-             ptr(ws.counters), ptr(ws.depth), ptr(ws.rgb), ptr(ws.sdf), ptr(ws.act4), ptr(ws.actm), stream())
-    else:
-        call("eslam_render_forward_q", store.ref(), ptr(q), ptr(ws.rays_o), ptr(ws.rays_d), ptr(ws.z), N, S,
-             ptr(ws.counters), ptr(ws.depth), ptr(ws.rgb), ptr(ws.sdf), ptr(ws.act4), ptr(ws.actm), stream())
+    # keeps sdf, rgb and the ReLU masks of every sample, so the backward pass neither re-runs the forward MLPs nor
+    # needs anything but the Q corners for the coordinate gradients
+    call("eslam_render_forward_q", store.ref(), ptr(q), ptr(ws.rays_o), ptr(ws.rays_d), ptr(ws.z), N, S,
+         ptr(ws.counters), ptr(ws.depth), ptr(ws.rgb), ptr(ws.sdf), ptr(ws.act4), ptr(ws.actm), stream())
     call("eslam_track_mask", ptr(ws.gt_depth), ptr(ws.depth), ptr(ws.band), N, ptr(ws.counters), ptr(ws.ray_mask),
          ptr(ws.scratch), stream())
-    if q is None:
-        call("eslam_pose_backward_act", store.ref(), ptr(store.arena), C.byref(cam), C.byref(rc), ptr(ws.rays_o),
-             ptr(ws.rays_d), ptr(ws.z), ptr(ws.gt_depth), ptr(ws.gt_color), ptr(ws.src), ptr(idx), n_pixels,
-             ptr(ws.ray_mask), ptr(ws.counters), N, ptr(ws.sdf), ptr(ws.act4), ptr(ws.actm), ptr(ws.pose_grad),
-             ptr(ws.loss_acc), stream())
-    else:
-        call("eslam_pose_backward_q", store.ref(), ptr(store.arena), ptr(q), C.byref(cam), C.byref(rc), ptr(ws.rays_o),
-             ptr(ws.rays_d), ptr(ws.z), ptr(ws.gt_depth), ptr(ws.gt_color), ptr(ws.src), ptr(idx), n_pixels,
-             ptr(ws.ray_mask), ptr(ws.counters), N, ptr(ws.sdf), ptr(ws.act4), ptr(ws.actm), ptr(ws.pose_grad),
-             ptr(ws.loss_acc), stream())
+    call("eslam_pose_backward_q", store.ref(), ptr(store.arena), ptr(q), C.byref(cam), C.byref(rc), ptr(ws.rays_o),
+         ptr(ws.rays_d), ptr(ws.z), ptr(ws.gt_depth), ptr(ws.gt_color), ptr(ws.src), ptr(idx), n_pixels,
+         ptr(ws.ray_mask), ptr(ws.counters), N, ptr(ws.sdf), ptr(ws.act4), ptr(ws.actm), ptr(ws.pose_grad),
+         ptr(ws.loss_acc), stream())
     call("eslam_finalize_loss", C.byref(rc), ptr(ws.counters), 1, ptr(ws.loss_acc), ptr(ws.loss_out), stream())
     if apply_adam is None:
         call("eslam_pose_adam_step", ptr(pose7), ptr(ws.pose_grad), None, None, 1, 0, 0.0, 0.0, 1, 0.5, 0.999, 1e-8,
@@ -198,9 +194,15 @@ def mapping_iteration(ws: Workspace, store: FieldStore, sc: StepCfg, c2ws, poses
     c2ws [b,4,4] fp32; poses7 [b,7] or None (joint_opt: frames 1.. are taken from poses7 and updated).
     gt_colors / gt_depths: stacked [b,H,W,3] f64 / [b,H,W] f32 tensors, or one FrameTable passed as both.
     Planes/decoders live in `store` (Adam state in store.exp_avg*, reset by the caller per call).
-    reduce_counters(counters)->norm and reduce_grads(grad, pose_grad, loss_acc) are the two exchange
+
+    The backward kernel works on the Q images of the map and reduces the plane gradients as 16-channel GRADIENT
+    IMAGES (store.gq_arena); the optimiser step (FieldStore.adam_step_q) turns them into plane gradients and dW1 on
+    the fly.  With apply_adam=False (tests, gradient inspection; the caller has called store.reset_adam()) the whole
+    gradient is left in store.grad in parameter form (FieldStore.parameter_grads) next to the gradient images.
+
+    reduce_counters(counters)->norm and reduce_grads(tensors, pose_grad, loss_acc) are the two exchange
     points of the ray-sharded multi-GPU mapping (myslam_b200.dist); None on one GPU.  `exchange` is an object
-    providing both; a dist.PeerExchange additionally replaces all-reduce + Adam by the fused peer-memory kernel."""
+    providing both; a dist.PeerExchange additionally replaces all-reduce + Adam by the fused peer-memory kernels."""
     dev = ws.device
     if exchange is not None:
         reduce_counters, reduce_grads = exchange.reduce_counters, exchange.reduce_grads
@@ -214,12 +216,8 @@ def mapping_iteration(ws: Workspace, store: FieldStore, sc: StepCfg, c2ws, poses
     _check_frames(gt_depths, gt_colors, b, cam)
     n_crop = (cam.H1 - cam.H0) * (cam.W1 - cam.W0)
     idx = draws.randint(n_crop, N)
-    # EXPERIMENTAL opt-in (ESLAM_B200_QMAP=1, one GPU): the iteration on the pre-activated plane
-    # images; bind() then also rebuilds them from the parameters of this step
-    q_form = os.environ.get("ESLAM_B200_QMAP", "0") == "1" and exchange is None and reduce_grads is None
-    if q_form:
-        store.want_q = True
     store.bind()
+    q = store.ensure_q()
     c2w_flat = c2ws.reshape(b, 16).float().contiguous()
     joint = poses7 is not None
     if strict_rng:
@@ -245,29 +243,18 @@ def mapping_iteration(ws: Workspace, store: FieldStore, sc: StepCfg, c2ws, poses
         call("eslam_importance_samples", store.ref(), ptr(store.arena), C.byref(rc), ptr(ws.rays_o), ptr(ws.rays_d),
              ptr(ws.dl_list), ptr(ws.counters), r0, ptr(u_c), ptr(u_f), ptr(linspace_table(ns, dev)), ptr(ws.z),
              stream())
-    grad = store.ensure_grad()
+    grad, gq = store.ensure_grad(), store.ensure_q_grad()
     if overlapped:
         exchange.end_counters()
     elif reduce_counters is not None:
         norm = reduce_counters(ws.counters)
-    if q_form and apply_adam:
-        call("eslam_loss_backward_q", store.ref(), ptr(store.arena), ptr(store.q_arena), ptr(store.ensure_q_grad()),
-             C.byref(cam), C.byref(rc), ptr(ws.rays_o), ptr(ws.rays_d), ptr(ws.z), ptr(ws.gt_depth), ptr(ws.gt_color),
-             ptr(ws.src), ptr(idx), pix_per_image, None, ptr(ws.counters), None, N, ptr(grad),
-             ptr(ws.pose_grad) if joint else None, ptr(ws.loss_acc) if want_loss else None, stream())
-        if want_loss:
-            call("eslam_finalize_loss", C.byref(rc), ptr(ws.counters), 0, ptr(ws.loss_acc), ptr(ws.loss_out), stream())
-        store.adam_step_q(step, lr_dec, lr_planes, lr_cplanes)
-        if joint:
-            call("eslam_pose_adam_step", ptr(poses7), ptr(ws.pose_grad), ptr(ws.pose_m), ptr(ws.pose_v), b, 1, lr_cam,
-                 lr_cam, step, 0.9, 0.999, 1e-8, ptr(ws.grad7), 1, stream())
-        return
-    call("eslam_loss_backward", store.ref(), ptr(store.arena), C.byref(cam), C.byref(rc), ptr(ws.rays_o),
-         ptr(ws.rays_d), ptr(ws.z), ptr(ws.gt_depth), ptr(ws.gt_color), ptr(ws.src), ptr(idx), pix_per_image, None,
-         ptr(ws.counters), ptr(norm) if norm is not None else None, N, ptr(grad),
+    call("eslam_loss_backward_q", store.ref(), ptr(store.arena), ptr(q), ptr(gq), C.byref(cam), C.byref(rc),
+         ptr(ws.rays_o), ptr(ws.rays_d), ptr(ws.z), ptr(ws.gt_depth), ptr(ws.gt_color), ptr(ws.src), ptr(idx),
+         pix_per_image, None, ptr(ws.counters), ptr(norm) if norm is not None else None, N, ptr(grad),
          ptr(ws.pose_grad) if joint else None, ptr(ws.loss_acc) if want_loss else None, stream())
     if fused_exchange:
-        # reduce-scatter + Adam + all-gather + zero_grad in one kernel over peer memory (csrc/exchange.cuh)
+        # reduce-scatter of the gradient images + plane Adam + all-gather, then the decoders' replicated step, as
+        # kernels over peer memory (csrc/exchange.cuh)
         pose_sum, loss_sum = exchange.adam_exchange(step, lr_dec, lr_planes, lr_cplanes, ws.pose_grad if joint else None,
                                                     b, ws.loss_acc if want_loss else None)
         if want_loss:
@@ -278,17 +265,17 @@ def mapping_iteration(ws: Workspace, store: FieldStore, sc: StepCfg, c2ws, poses
                  lr_cam, step, 0.9, 0.999, 1e-8, ptr(ws.grad7), 1, stream())
         return
     if reduce_grads is not None:
-        reduce_grads(grad, ws.pose_grad if joint else None, ws.loss_acc if want_loss else None)
+        reduce_grads([gq, grad[store.dec_off:]], ws.pose_grad if joint else None, ws.loss_acc if want_loss else None)
     if want_loss:
         call("eslam_finalize_loss", C.byref(rc), ptr(norm if norm is not None else ws.counters), 0, ptr(ws.loss_acc),
              ptr(ws.loss_out), stream())
     if not apply_adam:
+        store.grad.copy_(store.parameter_grads())  # inspection only: the whole gradient in parameter form
         if joint:
             call("eslam_pose_adam_step", ptr(poses7), ptr(ws.pose_grad), None, None, b, 1, 0.0, 0.0, 1, 0.9, 0.999,
                  1e-8, ptr(ws.grad7), 0, stream())
         return
-    store.adam_step(step, lr_dec, lr_planes, lr_cplanes)
+    store.adam_step_q(step, lr_dec, lr_planes, lr_cplanes)
     if joint:
         call("eslam_pose_adam_step", ptr(poses7), ptr(ws.pose_grad), ptr(ws.pose_m), ptr(ws.pose_v), b, 1, lr_cam,
              lr_cam, step, 0.9, 0.999, 1e-8, ptr(ws.grad7), 1, stream())
-

@@ -47,8 +47,7 @@ def _tracker_store(trk, st):
     if st["pulled_idx"] != pm:
         store.pull_planes(all_planes)
         st["pulled_idx"] = pm
-    # EXPERIMENTAL opt-in: track on the pre-activated plane images
-    store.want_q = os.environ.get("ESLAM_B200_QTRACK", "0") == "1"
+    store.ensure_q()  # outside any graph: a replayed frame graph reads the Q images, it does not rebuild them
     return store
 
 

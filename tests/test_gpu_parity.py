@@ -385,9 +385,9 @@ def test_grid_sdf_golden():
 
 
 def test_cached_pose_backward_equals_recomputing_backward():
-    """The tracker's backward pass on the activations the forward kernel kept (eslam_pose_backward_act: no gather,
-    no forward MLPs) gives the pose gradient and loss of the recomputing kernel (eslam_loss_backward) on the same
-    rays, samples and outlier mask."""
+    """The tracker's backward pass on the activations the forward kernel kept (eslam_pose_backward_q on the Q images:
+    no forward MLPs) gives the pose gradient and loss of the recomputing parameter-form kernel (eslam_loss_backward)
+    on the same rays, samples and outlier mask, up to the re-association of the first layer's sums."""
     import ctypes as C
     from myslam_b200 import ReplayDraws
     from myslam_b200._lib import call, ptr, stream
@@ -413,8 +413,8 @@ def test_cached_pose_backward_equals_recomputing_backward():
     call("eslam_finalize_loss", C.byref(sc.render), ptr(ws.counters), 1, ptr(ws.loss_acc), ptr(ws.loss_out), stream())
     call("eslam_pose_adam_step", ptr(pose), ptr(ws.pose_grad), None, None, 1, 0, 0.0, 0.0, 1, 0.5, 0.999, 1e-8,
          ptr(ws.grad7), 0, stream())
-    assert rel_err(g_cached, ws.grad7[0]) < 1e-5
-    assert abs(loss_cached - ws.loss_acc[5].item()) <= 1e-6 * abs(loss_cached)
+    assert rel_err(g_cached, ws.grad7[0]) < 1e-4
+    assert abs(loss_cached - ws.loss_acc[5].item()) <= 1e-5 * abs(loss_cached)
 
 
 def test_track_frame_graph_replay_matches_eager_loop(monkeypatch):

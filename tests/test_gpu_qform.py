@@ -1,5 +1,6 @@
-"""EXPERIMENTAL entry points (include/eslam_b200.h, "pre-activated planes"): not part of the
-product path yet; held to 1e-5 of the product's render forward on the same rays."""
+"""The Q form (the first decoder layer applied to the planes) against the parameter form of the same
+kernels and against the reference's golden gradients: render forward, the tracker's pose-only backward, the mapping
+backward into gradient images, and the optimiser tail that consumes them."""
 import pytest
 import torch
 
@@ -51,12 +52,11 @@ def test_render_forward_on_preactivated_planes_matches_render_forward(S):
     assert flips < 1e-3, flips
 
 
-@pytest.mark.skipif(__import__("os").environ.get("ESLAM_B200_EXPERIMENTAL", "0") != "1",
-                    reason="eslam_pose_backward_q has not run on hardware yet: set ESLAM_B200_EXPERIMENTAL=1")
-def test_pose_backward_on_preactivated_planes_matches_the_cached_backward():
-    """Tracker iteration on the golden frame twice: product path (eslam_render_forward_act + eslam_pose_backward_act)
-    and Q path (eslam_render_forward_q + eslam_pose_backward_q) on the same rays, samples and outlier mask; the
-    pose gradient and the loss must agree to the re-association of the first layer's sums."""
+def test_pose_backward_on_preactivated_planes_matches_the_parameter_form():
+    """Tracker iteration on the golden frame twice: the product path (eslam_render_forward_q + eslam_pose_backward_q
+    on the Q images) and the parameter-form kernels (eslam_render_forward_act + eslam_pose_backward_act) on the same
+    rays, samples and outlier mask; the pose gradient and the loss must agree to the re-association of the first
+    layer's sums."""
     import ctypes as C
 
     from conftest import load_npz, recorded_draws, rel_err
@@ -76,19 +76,16 @@ def test_pose_backward_on_preactivated_planes_matches_the_cached_backward():
     gc, gd = torch.from_numpy(d["gt_color"]).to(DEV), torch.from_numpy(d["gt_depth"]).to(DEV)
     tracking_iteration(st["ws"], store, st["sc"], pose, gc, gd, n_pix, draws=ReplayDraws(draws[:2], DEV), strict_rng=True)
     ws, sc = st["ws"], st["sc"]
-    g_ref, loss_ref = ws.grad7[0].clone(), ws.loss_acc[5].item()
-    mask_ref = ws.ray_mask.clone()
+    g_q, loss_q = ws.grad7[0].clone(), ws.loss_acc[5].item()
+    mask_q = ws.ray_mask.clone()
     idx = draws[0].to(DEV)
     S = sc.render.n_stratified + sc.render.n_importance
-    # the same iteration on the Q images: forward (keeps activations), outlier mask, pose-only backward
-    q_arena = torch.zeros(store.n_planes_end // 2, dtype=torch.float32, device=DEV)
-    call("eslam_q_build", store.ref(), ptr(store.arena), ptr(q_arena), stream())
     ws.loss_acc.zero_()
-    call("eslam_render_forward_q", store.ref(), ptr(q_arena), ptr(ws.rays_o), ptr(ws.rays_d), ptr(ws.z), n_pix, S,
+    call("eslam_render_forward_act", store.ref(), ptr(store.arena), ptr(ws.rays_o), ptr(ws.rays_d), ptr(ws.z), n_pix, S,
          ptr(ws.counters), ptr(ws.depth), ptr(ws.rgb), ptr(ws.sdf), ptr(ws.act4), ptr(ws.actm), stream())
     call("eslam_track_mask", ptr(ws.gt_depth), ptr(ws.depth), ptr(ws.band), n_pix, ptr(ws.counters), ptr(ws.ray_mask),
          ptr(ws.scratch), stream())
-    call("eslam_pose_backward_q", store.ref(), ptr(store.arena), ptr(q_arena), C.byref(sc.cam), C.byref(sc.render),
+    call("eslam_pose_backward_act", store.ref(), ptr(store.arena), C.byref(sc.cam), C.byref(sc.render),
          ptr(ws.rays_o), ptr(ws.rays_d), ptr(ws.z), ptr(ws.gt_depth), ptr(ws.gt_color), ptr(ws.src), ptr(idx), n_pix,
          ptr(ws.ray_mask), ptr(ws.counters), n_pix, ptr(ws.sdf), ptr(ws.act4), ptr(ws.actm), ptr(ws.pose_grad),
          ptr(ws.loss_acc), stream())
@@ -96,13 +93,11 @@ def test_pose_backward_on_preactivated_planes_matches_the_cached_backward():
     call("eslam_pose_adam_step", ptr(pose), ptr(ws.pose_grad), None, None, 1, 0, 0.0, 0.0, 1, 0.5, 0.999, 1e-8,
          ptr(ws.grad7), 0, stream())
     torch.cuda.synchronize()
-    assert torch.equal(ws.ray_mask, mask_ref), "the outlier mask must not depend on the form of the forward"
-    assert rel_err(ws.grad7[0], g_ref) < 1e-4
-    assert abs(ws.loss_acc[5].item() - loss_ref) <= 1e-5 * abs(loss_ref)
+    assert torch.equal(ws.ray_mask, mask_q), "the outlier mask must not depend on the form of the forward"
+    assert rel_err(g_q, ws.grad7[0]) < 1e-4
+    assert abs(ws.loss_acc[5].item() - loss_q) <= 1e-5 * abs(loss_q)
 
 
-@pytest.mark.skipif(__import__("os").environ.get("ESLAM_B200_EXPERIMENTAL", "0") != "1",
-                    reason="eslam_q_adam_planes has not run on hardware yet: set ESLAM_B200_EXPERIMENTAL=1")
 def test_q_adam_planes_matches_the_dense_chain_rule_and_adam():
     """Two optimiser steps of the Q form's dense tail on sparse gradient images against plain torch:
     dplane = GQ . W1_half, dW1_half = sum GQ (x) plane, Adam on the planes (oracle formula = torch.optim.Adam), gradient
@@ -157,8 +152,6 @@ def test_q_adam_planes_matches_the_dense_chain_rule_and_adam():
         assert torch.equal(store.plane_view(i)[~hit[i]], before[~hit[i]])
 
 
-@pytest.mark.skipif(__import__("os").environ.get("ESLAM_B200_EXPERIMENTAL", "0") != "1",
-                    reason="eslam_loss_backward_q has not run on hardware yet: set ESLAM_B200_EXPERIMENTAL=1")
 def test_mapping_backward_in_the_q_form_matches_the_reference_gradients():
     """The golden mapping iteration (reference gradients from tests/golden/mapping.npz) through the Q form:
     eslam_q_build -> eslam_loss_backward_q.  Plane gradients are recovered from the gradient images as GQ . W1_half,
@@ -187,7 +180,7 @@ def test_mapping_backward_in_the_q_form_matches_the_reference_gradients():
     poses7[1:] = matrix_to_cam_pose(c2ws[1:])
     gc, gd = torch.from_numpy(d["gt_colors"]).to(DEV), torch.from_numpy(d["gt_depths"]).to(DEV)
     draws = recorded_draws(d)
-    # the product path first: it leaves the compacted rays, samples and counters of the iteration in the workspace
+    # the iteration itself first: it leaves the compacted rays, samples and counters in the workspace
     mapping_iteration(st["ws"], store, st["sc"], c2ws, poses7, gc, gd, 100, 1, 1e-3, 5e-3, 5e-3, 1e-3,
                       draws=ReplayDraws(draws[:4], DEV), strict_rng=True, want_loss=True, apply_adam=False)
     ws, sc = st["ws"], st["sc"]

@@ -131,6 +131,21 @@ def main():
         "eslam_loss_backward", tstore.ref(), ptr(tstore.arena), C.byref(tsc.cam), C.byref(tsc.render), ptr(tws.rays_o),
         ptr(tws.rays_d), ptr(tws.z), ptr(tws.gt_depth), ptr(tws.gt_color), ptr(tws.src), ptr(tidx), 2000,
         ptr(tws.ray_mask), ptr(tws.counters), None, 2000, None, ptr(tws.pose_grad), None, stream()))
+    # the tracker's cached pose-only backward on the activations the forward left, parameter form and Q form
+    call("eslam_render_forward_act", tstore.ref(), ptr(tstore.arena), ptr(tws.rays_o), ptr(tws.rays_d), ptr(tws.z), 2000,
+         40, ptr(tws.counters), ptr(tws.depth), ptr(tws.rgb), ptr(tws.sdf), ptr(tws.act4), ptr(tws.actm), stream())
+    timeit("trk.pose_backward_act (cached)", lambda: call(
+        "eslam_pose_backward_act", tstore.ref(), ptr(tstore.arena), C.byref(tsc.cam), C.byref(tsc.render),
+        ptr(tws.rays_o), ptr(tws.rays_d), ptr(tws.z), ptr(tws.gt_depth), ptr(tws.gt_color), ptr(tws.src), ptr(tidx), 2000,
+        ptr(tws.ray_mask), ptr(tws.counters), 2000, ptr(tws.sdf), ptr(tws.act4), ptr(tws.actm), ptr(tws.pose_grad), None,
+        stream()))
+    call("eslam_render_forward_q", tstore.ref(), ptr(q_arena), ptr(tws.rays_o), ptr(tws.rays_d), ptr(tws.z), 2000, 40,
+         ptr(tws.counters), ptr(tws.depth), ptr(tws.rgb), ptr(tws.sdf), ptr(tws.act4), ptr(tws.actm), stream())
+    timeit("trk.pose_backward_q (cached)", lambda: call(
+        "eslam_pose_backward_q", tstore.ref(), ptr(tstore.arena), ptr(q_arena), C.byref(tsc.cam), C.byref(tsc.render),
+        ptr(tws.rays_o), ptr(tws.rays_d), ptr(tws.z), ptr(tws.gt_depth), ptr(tws.gt_color), ptr(tws.src), ptr(tidx), 2000,
+        ptr(tws.ray_mask), ptr(tws.counters), 2000, ptr(tws.sdf), ptr(tws.act4), ptr(tws.actm), ptr(tws.pose_grad), None,
+        stream()))
     timeit("trk.iteration (all launches)", lambda: tracking_iteration(tws, tstore, tsc, pose0, col1, dep1, 2000), 20)
     timeit("map.iteration (all launches)", lambda: mapping_iteration(ws, store, sc, poses, poses7, cols, deps, pix, 1,
                                                                     1e-3, 5e-3, 5e-3, 1e-3), 20)
