@@ -35,7 +35,7 @@ extern "C" {
 #define ESLAM_DEC_FLOATS 2700 /* 1329 (sdf, padded to 1332) + 1363 (rgb, padded to 1364) + beta, padded */
 #define ESLAM_MAX_SAMPLES 64  /* n_stratified + n_importance per ray */
 #define ESLAM_MAX_PEERS 8    /* GPUs of one NVLink/NVSwitch box */
-#define ESLAM_EXCH_CTAS 592   /* grid of eslam_adam_exchange (4 CTAs per SM), identical on every rank */
+#define ESLAM_EXCH_CTAS 592   /* grid of the push kernel of eslam_q_adam_exchange (4 CTAs per SM) */
 
 #define ESLAM_EINVAL (-1)
 #define ESLAM_EUNSUPPORTED (-2)
@@ -166,22 +166,23 @@ int eslam_grid_sdf_factored(const eslam_field_t* field_host, const float* xs, co
                             int ny, int nz, int64_t start, int64_t count, const float* pxy, const float* pxz,
                             const float* pyz, const float* hull_planes, int n_planes, float* sdf, eslam_stream_t s);
 
-/* ---- EXPERIMENTAL: pre-activated planes ------------------------------------------------
- * Everything from here to the next section is opt-in only (ESLAM_B200_QTRACK / ESLAM_B200_QMAP in the Python
- * mirror) and may change.  Validated on hardware so far: eslam_q_build + eslam_render_forward_q (1e-5 of
- * eslam_render_forward_act, tests/test_gpu_experimental.py); the backward and optimiser entry points below have
- * compiled but not run yet.  The first layer of decoders.py:87-125 commutes with the
- * bilinear fetch of decoders.py:64-85, so it can be applied to the planes once instead of to every sample:
- * eslam_q_build writes Q = W1_half . plane for the 12 planes as 16-channel channels-last images (q_arena: half the
- * plane floats of the parameter arena, plane i at half its float offset; decoders read from the arena);
- * eslam_render_forward_q is eslam_render_forward / _act on q_arena (layers 2-3 read the bound decoders). */
+/* ---- the Q form: the first decoder layer applied to the planes ----------------------------
+ * What both loops' iterations run on.  The first layer of decoders.py:87-125 is linear and commutes with the bilinear
+ * fetch of decoders.py:64-85:  W1 (sum_planes bilinear(plane)) + b1 = sum_planes bilinear(W1_slice . plane) + b1,
+ * so it is applied to the planes once per parameter change instead of to every sample.
+ * eslam_q_build writes Q = W1_slice . plane for the 12 planes as 16-channel channels-last images (q_arena: half the
+ * plane floats of the parameter arena, plane i at half its float offset; the planes of a (decoder, scale) group must
+ * be contiguous in the arena; the decoders are read from the arena).  eslam_render_forward_q is
+ * eslam_render_forward / _act on q_arena (layers 2-3 read the decoders bound by eslam_bind_decoders): 64 instead of
+ * 128 bytes per corner and no 64 -> 16 layer.  Values differ from the parameter form by the re-association of the
+ * first layer's sum (held to 1e-5 in tests/test_gpu_qform.py). */
 int eslam_q_build(const eslam_field_t* field_host, const float* arena, float* q_arena, eslam_stream_t s);
 int eslam_render_forward_q(const eslam_field_t* field_host, const float* q_arena, const float* rays_o,
                            const float* rays_d, const float* z, int n_rays, int n_samples, const int32_t* counters,
                            float* depth, float* rgb, float* sdf, float* act4, uint32_t* actm, eslam_stream_t s);
-/* eslam_pose_backward_act on q_arena: the cached activations must come from eslam_render_forward_q; `arena` still
- * supplies the decoders.  The backward-to-input pass of the first layer disappears (the taps need the 16 pre-activation
- * gradients only) and the coordinate-gradient re-gather reads 64 instead of 128 bytes per corner. */
+/* The tracker's loss + backward to the pose (Tracker.py:192-208) on q_arena: the cached activations must come from
+ * eslam_render_forward_q on the same rays; `arena` supplies the decoders.  No forward MLPs, no first-layer backward;
+ * the coordinate gradients fetch the Q corners once. */
 int eslam_pose_backward_q(const eslam_field_t* field_host, const float* arena, const float* q_arena,
                           const eslam_camera_t* cam, const eslam_render_cfg_t* cfg, const float* rays_o,
                           const float* rays_d, const float* z, const float* gt_depth, const double* gt_color,
@@ -189,9 +190,10 @@ int eslam_pose_backward_q(const eslam_field_t* field_host, const float* arena, c
                           const int32_t* counters, int max_rays, const float* sdf, const float* act4,
                           const uint32_t* actm, float* pose_grad, double* loss_acc, eslam_stream_t s);
 
-/* eslam_loss_backward (planes + decoders, poses if pose_grad) in the Q form: the forward recompute gathers q_arena, the
- * plane gradients are reduced as 16-channel pre-activation gradients into gq_arena (layout of q_arena, +=), grad_arena
- * receives the decoder gradients except dW1 (which eslam_q_adam_planes forms from gq_arena) and beta. */
+/* The mapper's fused loss + backward (Mapper.py:110-144,337-349; arguments as eslam_loss_backward) on q_arena: the
+ * plane gradients are reduced as 16-channel pre-activation gradients into gq_arena (layout of q_arena, +=),
+ * grad_arena's decoder block receives the decoder gradients except dW1 (which eslam_q_adam_planes forms from
+ * gq_arena) and beta; the coordinate (pose) gradients come from d pre-activation / d coordinate kept by the gather. */
 int eslam_loss_backward_q(const eslam_field_t* field_host, const float* arena, const float* q_arena, float* gq_arena,
                           const eslam_camera_t* cam, const eslam_render_cfg_t* cfg, const float* rays_o,
                           const float* rays_d, const float* z, const float* gt_depth, const double* gt_color,
@@ -199,11 +201,12 @@ int eslam_loss_backward_q(const eslam_field_t* field_host, const float* arena, c
                           const int32_t* counters, const int32_t* norm_counters, int max_rays, float* grad_arena,
                           float* pose_grad, double* loss_acc, eslam_stream_t s);
 
-/* Dense tail of a mapping iteration in the Q form (gq_arena is filled by eslam_loss_backward_q).  gq_arena holds d loss / d (first-layer pre-activation) reduced per texel, in the layout of q_arena.
- * Per texel: d loss / d plane = W1_half^T . GQ (consumed in registers by torch.optim.Adam's update of the planes,
- * Mapper.py:288-306,348-350, with the moments in parameter-arena layout), d loss / d W1_half += GQ (x) plane (added
- * into grad_arena's decoder block, so the decoders then take the ordinary eslam_adam_step), gq_arena zeroed where
- * consumed.  touched_q: eslam_q_touched_bytes() flags (one per 4 texels), zeroed together with the moments. */
+/* The plane half of `optimizer.step()` / `zero_grad()` (Mapper.py:288-306,348-350) from the gradient images.  Per
+ * texel: d loss / d plane = W1_slice^T . GQ (consumed in registers by torch.optim.Adam's update, moments in
+ * parameter-arena layout), d loss / d W1_slice += GQ (x) plane (added into grad_arena's decoder block, so the decoders
+ * then take the ordinary eslam_adam_step), gq_arena zeroed where consumed.  touched_q: eslam_q_touched_bytes() flags
+ * (one per texel), zeroed together with the moments: a texel whose gradient row has been zero since then is skipped
+ * exactly.  Square root and reciprocal of the update are the approximate instructions (2 ulp). */
 int eslam_q_touched_bytes(const eslam_field_t* field_host);
 int eslam_q_adam_planes(const eslam_field_t* field_host, float* arena, float* gq_arena, float* exp_avg,
                         float* exp_avg_sq, float* grad_arena, uint8_t* touched_q, double lr_planes, double lr_cplanes,
@@ -374,12 +377,12 @@ int eslam_keyframe_overlap(const eslam_camera_t* cam_host, const float* c2w, con
 
 /* ---- multi-GPU mapping over peer memory (new in this build; the reference is single-GPU) ---------------------
  * One process per GPU; every rank owns ONE symmetric (NVLink peer-mapped) allocation holding, at identical
- * offsets: the parameter arena, a gradient staging block of eslam_exchange_stage_floats(n, world) floats, two
+ * offsets: the parameter arena, a gradient-image staging block of eslam_q_exchange_stage_floats() floats, two
  * published copies of the aux blocks and counters, and a zero-initialised flag block of
  * eslam_exchange_flag_words() uint32.  The gradient arena stays in ordinary device memory.  Pointer tables
  * `x_host[r]` are rank r's copies as mapped into THIS process (index `rank` = local).
  * `epoch` must increase by one with every exchange call (either kind) and be the same on every rank;
- * `adam_seq` counts the eslam_adam_exchange calls (1-based); `local_sync` is a local zero-initialised
+ * `adam_seq` counts the eslam_q_adam_exchange calls (1-based); `local_sync` is a local zero-initialised
  * uint64[2]; `status` is a local int32 that becomes non-zero if a peer did not arrive within 4 s. */
 typedef struct {
   int32_t rank, world;
@@ -400,25 +403,29 @@ int eslam_exchange_flag_words(void);
 int eslam_exchange_counters(const eslam_peers_t* peers_host, const int32_t* counters, int32_t* const* pub_host,
                             int n, int32_t* norm, eslam_stream_t s);
 
-int64_t eslam_exchange_stage_floats(int64_t n, int world);
+/* Floats of the gradient-image staging block of one rank for `world` ranks. */
+int64_t eslam_q_exchange_stage_floats(const eslam_field_t* field_host, int world);
 
-/* Reduce-scatter + torch.optim.Adam + all-gather + zero_grad over peer memory, replacing `optimizer.step()` /
- * `zero_grad()` of Mapper.py:348-350 plus a gradient all-reduce.  Two kernels: (1) every rank stores slice q of
- * its gradient arena `grad` into rank q's staging (P2P stores) and zeroes it; (2) after a handshake rank r sums
- * its own slice and the staged rows in rank order, applies the Adam update of eslam_adam_step to slice r
- * (exp_avg / exp_avg_sq are local, only slice r is touched), zeroes its slice of `grad`, and stores the new
- * parameters into every rank's arena (P2P stores, or one multimem.st when mc_param != NULL); a closing handshake
- * makes the stores visible.  The local aux (float, pose gradients) / auxd (double, loss terms) blocks are
- * published, zeroed, and summed over all ranks into aux_sum / auxd_sum.  The call is identical on every rank.
- * Groups of 128 parameters whose gradient is zero on a rank are not sent (the staging must start zeroed; the
- * owner clears what it consumes), and with `touched` (as in eslam_adam_step_sparse, local, may be NULL) groups no
- * rank has touched since the optimiser was created are neither updated nor broadcast. */
-int eslam_adam_exchange(const eslam_peers_t* peers_host, float* const* param_host, float* const* stage_host,
-                        float* grad, float* mc_param, float* exp_avg, float* exp_avg_sq, int64_t n,
-                        const int64_t* seg_end_host, const double* seg_lr_host, int n_seg, int step, double beta1,
-                        double beta2, double eps, float* aux_local, float* const* aux_pub_host, float* aux_sum,
-                        int n_aux, double* auxd_local, double* const* auxd_pub_host, double* auxd_sum, int n_auxd,
-                        uint8_t* touched, eslam_stream_t s);
+/* `optimizer.step()` / `zero_grad()` of Mapper.py:348-350 plus the gradient all-reduce of a ray-sharded mapping, over
+ * peer memory.  Ownership is by tiles of eslam_q_adam_planes: rank r owns a contiguous slice of the gradient images.
+ * Three kernels: (1) every rank stores the peers' slices of its gradient image gq_arena into their staging rows (P2P
+ * stores) and zeroes them; (2) after a handshake rank r runs eslam_q_adam_planes on its tiles with the gradient rows
+ * summed over its own image and the staged rows in rank order (exp_avg / exp_avg_sq / touched_q are local, only the
+ * owned slice is touched) and stores the new texels into every rank's arena (P2P stores, or one multimem.st when
+ * mc_param != NULL); its decoder gradients (dW1 of the owned tiles + the backward's other decoder gradients in
+ * grad_arena) are published into dec_pub_host[rank] (ESLAM_DEC_FLOATS floats, alternate between two copies from call
+ * to call) and zeroed; a closing handshake makes everything visible; (3) every rank sums all ranks' published decoder
+ * gradients in rank order and takes the decoders' Adam step (replicated).  The local aux (float, pose gradients) /
+ * auxd (double, loss terms) blocks are published, zeroed, and summed over all ranks into aux_sum / auxd_sum.
+ * The call is identical on every rank.  All-zero groups of 128 floats are not sent (the staging must start zeroed; the
+ * owner clears what it consumes). */
+int eslam_q_adam_exchange(const eslam_peers_t* peers_host, const eslam_field_t* field_host, float* const* param_host,
+                          float* const* stage_host, float* gq_arena, float* grad_arena, float* mc_param,
+                          float* exp_avg, float* exp_avg_sq, uint8_t* touched_q, double lr_planes, double lr_cplanes,
+                          double lr_dec, int step, double beta1, double beta2, double eps,
+                          float* const* dec_pub_host, float* aux_local, float* const* aux_pub_host, float* aux_sum,
+                          int n_aux, double* auxd_local, double* const* auxd_pub_host, double* auxd_sum, int n_auxd,
+                          eslam_stream_t s);
 
 #ifdef __cplusplus
 }

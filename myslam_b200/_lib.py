@@ -104,9 +104,9 @@ PROTOTYPES = {
     "eslam_pose_to_matrix": [_P, _P, _I, _P],
     "eslam_keyframe_overlap": [_CP, _P, _P, _P, _I, _P, _I, _P, _I, _P, _P, _P],
     "eslam_exchange_counters": [C.POINTER(Peers), _P, C.POINTER(C.c_void_p), _I, _P, _P],
-    "eslam_adam_exchange": [C.POINTER(Peers), C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), _P, _P, _P, _P, _L,
-                            C.POINTER(C.c_int64), C.POINTER(C.c_double), _I, _I, _D, _D, _D, _P, C.POINTER(C.c_void_p),
-                            _P, _I, _P, C.POINTER(C.c_void_p), _P, _I, _P, _P],
+    "eslam_q_adam_exchange": [C.POINTER(Peers), _FP, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), _P, _P, _P, _P, _P, _P,
+                              _D, _D, _D, _I, _D, _D, _D, C.POINTER(C.c_void_p), _P, C.POINTER(C.c_void_p), _P, _I, _P,
+                              C.POINTER(C.c_void_p), _P, _I, _P],
 }
 
 _lib = None
@@ -128,8 +128,8 @@ def load():
     lib.eslam_abi_version.argtypes = []
     lib.eslam_exchange_flag_words.restype = C.c_int
     lib.eslam_exchange_flag_words.argtypes = []
-    lib.eslam_exchange_stage_floats.restype = C.c_int64
-    lib.eslam_exchange_stage_floats.argtypes = [C.c_int64, C.c_int]
+    lib.eslam_q_exchange_stage_floats.restype = C.c_int64
+    lib.eslam_q_exchange_stage_floats.argtypes = [C.POINTER(FieldDesc), C.c_int]
     lib.eslam_q_touched_bytes.restype = C.c_int
     lib.eslam_q_touched_bytes.argtypes = [C.POINTER(FieldDesc)]
     for name, argtypes in PROTOTYPES.items():

@@ -840,6 +840,20 @@ int eslam_adam_step_sparse(float* param, float* grad, float* exp_avg, float* exp
   return adam_step_impl(param, grad, exp_avg, exp_avg_sq, n, seg_end, seg_lr, n_seg, step, beta1, beta2, eps, touched, s);
 }
 
+static void fill_q_adam(QAdamArgs& a, double lr_planes, double lr_cplanes, int step, double beta1, double beta2,
+                        double eps) {
+  const double bc1 = 1.0 - pow(beta1, (double)step);
+  a.step_sdf = (float)(lr_planes / bc1);
+  a.step_rgb = (float)(lr_cplanes / bc1);
+  a.inv_bc2 = (float)(1.0 / sqrt(1.0 - pow(beta2, (double)step)));
+  a.adam.beta1 = (float)beta1;
+  a.adam.beta2 = (float)beta2;
+  a.adam.one_m_beta1 = (float)(1.0 - beta1);
+  a.adam.one_m_beta2 = (float)(1.0 - beta2);
+  a.adam.bc2_sqrt = (float)sqrt(1.0 - pow(beta2, (double)step));
+  a.adam.eps = (float)eps;
+}
+
 static int fill_peers(PeerSync& ps, const eslam_peers_t* p) {
   if (!p || p->world < 1 || p->world > MAX_PEERS || p->rank < 0 || p->rank >= p->world || !p->status || !p->local_sync)
     return ESLAM_EINVAL;
@@ -876,38 +890,82 @@ int eslam_exchange_counters(const eslam_peers_t* peers, const int32_t* counters,
   return 0;
 }
 
-int64_t eslam_exchange_stage_floats(int64_t n, int world) {
-  if (n <= 0 || world < 1) return 0;
-  const int64_t n4 = n / 4;
-  return 4 * world * ((n4 + world - 1) / world);
+// tiles [lo, hi) of the optimiser tail owned by rank r, and the first texel of a tile
+static void q_rank_units(const QGroups& qg, int world, int r, int* lo, int* hi) {
+  const int total = qg.unit0[4], base = total / world, rem = total % world;
+  *lo = r * base + std::min(r, rem);
+  *hi = *lo + base + (r < rem ? 1 : 0);
+}
+static long long q_unit_first_texel(const QGroups& qg, int u) {
+  if (u >= qg.unit0[4]) return (long long)qg.t0[3] + qg.n[3];
+  int g = 0;
+  while (g < 3 && u >= qg.unit0[g + 1]) ++g;
+  return (long long)qg.t0[g] + (long long)(u - qg.unit0[g]) * QA_TILE;
+}
+// lo4[r] = first float4 of rank r's slice of the gradient images; returns the staging row pitch (float4)
+static long long q_exchange_slices(const QGroups& qg, int world, long long* lo4) {
+  long long smax = 0;
+  for (int r = 0; r <= world; ++r) {
+    int lo, hi;
+    q_rank_units(qg, world, std::min(r, world - 1), &lo, &hi);
+    lo4[r] = 4 * q_unit_first_texel(qg, r < world ? lo : hi);
+  }
+  for (int r = 0; r < world; ++r) smax = std::max(smax, lo4[r + 1] - lo4[r]);
+  return (smax + 31) & ~31ll;
 }
 
-int eslam_adam_exchange(const eslam_peers_t* peers, float* const* param, float* const* stage, float* grad,
-                        float* mc_param, float* exp_avg, float* exp_avg_sq, int64_t n, const int64_t* seg_end,
-                        const double* seg_lr, int n_seg, int step, double beta1, double beta2, double eps,
-                        float* aux_local, float* const* aux_pub, float* aux_sum, int n_aux, double* auxd_local,
-                        double* const* auxd_pub, double* auxd_sum, int n_auxd, uint8_t* touched, eslam_stream_t s) {
-  REQUIRE(param && stage && grad && exp_avg && exp_avg_sq && n_aux >= 0 && n_auxd >= 0, "eslam_adam_exchange");
-  REQUIRE(n_aux == 0 || (aux_local && aux_pub && aux_sum), "eslam_adam_exchange(aux)");
-  REQUIRE(n_auxd == 0 || (auxd_local && auxd_pub && auxd_sum), "eslam_adam_exchange(auxd)");
-  AdamExchArgs a;
+int64_t eslam_q_exchange_stage_floats(const eslam_field_t* f, int world) {
+  if (!f || world < 1 || world > MAX_PEERS) return 0;
+  QGroups qg;
+  if (make_q_groups(f, QA_TILE, &qg)) return 0;
+  long long lo4[MAX_PEERS + 1];
+  return 4 * (int64_t)world * q_exchange_slices(qg, world, lo4);
+}
+
+int eslam_q_adam_exchange(const eslam_peers_t* peers, const eslam_field_t* f, float* const* param,
+                          float* const* stage, float* gq_arena, float* grad_arena, float* mc_param, float* exp_avg,
+                          float* exp_avg_sq, uint8_t* touched_q, double lr_planes, double lr_cplanes, double lr_dec,
+                          int step, double beta1, double beta2, double eps, float* const* dec_pub, float* aux_local,
+                          float* const* aux_pub, float* aux_sum, int n_aux, double* auxd_local,
+                          double* const* auxd_pub, double* auxd_sum, int n_auxd, eslam_stream_t s) {
+  REQUIRE(f && param && stage && gq_arena && grad_arena && exp_avg && exp_avg_sq && touched_q && dec_pub && step >= 1 &&
+              n_aux >= 0 && n_auxd >= 0,
+          "eslam_q_adam_exchange");
+  REQUIRE(n_aux == 0 || (aux_local && aux_pub && aux_sum), "eslam_q_adam_exchange(aux)");
+  REQUIRE(n_auxd == 0 || (auxd_local && auxd_pub && auxd_sum), "eslam_q_adam_exchange(auxd)");
+  QExchArgs a;
   memset(&a, 0, sizeof(a));
-  if (fill_peers(a.ps, peers)) return fail(ESLAM_EINVAL, "eslam_adam_exchange(peers)");
-  REQUIRE(peers->adam_seq >= 1, "eslam_adam_exchange(adam_seq)");
-  if (fill_adam(a.adam, n, seg_end, seg_lr, n_seg, step, beta1, beta2, eps))
-    return fail(ESLAM_EINVAL, "eslam_adam_exchange(adam)");
-  for (int r = 0; r < a.ps.world; ++r) {
-    REQUIRE(param[r] && stage[r], "eslam_adam_exchange(arenas)");
-    a.p[r] = reinterpret_cast<float4*>(param[r]);
+  if (fill_peers(a.ps, peers)) return fail(ESLAM_EINVAL, "eslam_q_adam_exchange(peers)");
+  REQUIRE(peers->adam_seq >= 1 && peers->world >= 2, "eslam_q_adam_exchange(adam_seq, world)");
+  int rc = make_q_groups(f, QA_TILE, &a.q.qg);
+  if (rc) return fail(rc, "eslam_q_adam_exchange(plane layout)");
+  const int world = a.ps.world, rank = a.ps.rank;
+  a.q.smax = q_exchange_slices(a.q.qg, world, a.lo4);
+  int ulo, uhi;
+  q_rank_units(a.q.qg, world, rank, &ulo, &uhi);
+  REQUIRE(uhi > ulo, "eslam_q_adam_exchange(fewer tiles than ranks)");
+  a.q.rank = rank;
+  a.q.world = world;
+  a.q.unit_lo = ulo;
+  a.q.lo4 = a.lo4[rank];
+  for (int r = 0; r < world; ++r) {
+    REQUIRE(param[r] && stage[r] && dec_pub[r], "eslam_q_adam_exchange(arenas)");
+    a.q.peer_p[r] = reinterpret_cast<float4*>(param[r]);
     a.stage[r] = reinterpret_cast<float4*>(stage[r]);
+    a.dec_pub[r] = dec_pub[r];
     if (n_aux) a.aux_pub[r] = aux_pub[r];
     if (n_auxd) a.auxd_pub[r] = auxd_pub[r];
   }
-  a.g = reinterpret_cast<float4*>(grad);
-  a.adam.touched = touched;
-  a.mc_p = reinterpret_cast<float4*>(mc_param);
-  a.m = reinterpret_cast<float4*>(exp_avg);
-  a.v = reinterpret_cast<float4*>(exp_avg_sq);
+  a.q.stage = a.stage[rank];
+  a.q.mc_p = reinterpret_cast<float4*>(mc_param);
+  a.q.arena4 = a.q.peer_p[rank];
+  a.q.gq4 = reinterpret_cast<float4*>(gq_arena);
+  a.q.m4 = reinterpret_cast<float4*>(exp_avg);
+  a.q.v4 = reinterpret_cast<float4*>(exp_avg_sq);
+  a.q.gdec = grad_arena + f->dec_offset;
+  a.q.dec = param[rank] + f->dec_offset;
+  a.q.touched = touched_q;
+  fill_q_adam(a.q, lr_planes, lr_cplanes, step, beta1, beta2, eps);
   a.aux_local = aux_local;
   a.aux_sum = aux_sum;
   a.n_aux = n_aux;
@@ -915,17 +973,30 @@ int eslam_adam_exchange(const eslam_peers_t* peers, float* const* param, float* 
   a.auxd_sum = auxd_sum;
   a.n_auxd = n_auxd;
   a.dbg = g_debug;
-  k_grad_push<<<ESLAM_EXCH_CTAS, EXCH_THREADS, 0, S_(s)>>>(a);
-  CHECK_LAUNCH("eslam_adam_exchange(push)");
-  if (mc_param)
-    k_adam_exchange<true, 8><<<ESLAM_EXCH_CTAS, EXCH_THREADS, 0, S_(s)>>>(a);
-  else if (a.ps.world <= 2)
-    k_adam_exchange<false, 2><<<ESLAM_EXCH_CTAS, EXCH_THREADS, 0, S_(s)>>>(a);
-  else if (a.ps.world <= 4)
-    k_adam_exchange<false, 4><<<ESLAM_EXCH_CTAS, EXCH_THREADS, 0, S_(s)>>>(a);
+  a.ps.done_target = (unsigned long long)peers->adam_seq * (unsigned long long)(uhi - ulo);
+  k_gq_push<<<ESLAM_EXCH_CTAS, EXCH_THREADS, 0, S_(s)>>>(a);
+  CHECK_LAUNCH("eslam_q_adam_exchange(push)");
+  const unsigned grid = (unsigned)(uhi - ulo);
+  if (world <= 2)
+    k_q_adam_exchange<2><<<grid, QA_THREADS, 0, S_(s)>>>(a);
+  else if (world <= 4)
+    k_q_adam_exchange<4><<<grid, QA_THREADS, 0, S_(s)>>>(a);
   else
-    k_adam_exchange<false, 8><<<ESLAM_EXCH_CTAS, EXCH_THREADS, 0, S_(s)>>>(a);
-  CHECK_LAUNCH("eslam_adam_exchange");
+    k_q_adam_exchange<8><<<grid, QA_THREADS, 0, S_(s)>>>(a);
+  CHECK_LAUNCH("eslam_q_adam_exchange");
+  DecPeersArgs d;
+  memset(&d, 0, sizeof(d));
+  d.world = world;
+  for (int r = 0; r < world; ++r) d.dec_pub[r] = dec_pub[r];
+  d.p = param[rank] + f->dec_offset;
+  d.m = exp_avg + f->dec_offset;
+  d.v = exp_avg_sq + f->dec_offset;
+  const int64_t seg_end[1] = {4};
+  const double seg_lr[1] = {lr_dec};
+  if (fill_adam(d.adam, 4, seg_end, seg_lr, 1, step, beta1, beta2, eps))
+    return fail(ESLAM_EINVAL, "eslam_q_adam_exchange(decoder adam)");
+  k_dec_adam_peers<<<1, 256, 0, S_(s)>>>(d);
+  CHECK_LAUNCH("eslam_q_adam_exchange(decoders)");
   return 0;
 }
 
@@ -1064,16 +1135,8 @@ int eslam_q_adam_planes(const eslam_field_t* f, float* arena, float* gq_arena, f
   a.gdec = grad_arena + f->dec_offset;
   a.dec = arena + f->dec_offset;
   a.touched = touched_q;
-  const double bc1 = 1.0 - pow(beta1, (double)step);
-  a.step_sdf = (float)(lr_planes / bc1);
-  a.step_rgb = (float)(lr_cplanes / bc1);
-  a.adam.beta1 = (float)beta1;
-  a.adam.beta2 = (float)beta2;
-  a.adam.one_m_beta1 = (float)(1.0 - beta1);
-  a.adam.one_m_beta2 = (float)(1.0 - beta2);
-  a.adam.bc2_sqrt = (float)sqrt(1.0 - pow(beta2, (double)step));
-  a.adam.eps = (float)eps;
-  k_q_adam_planes<<<a.qg.unit0[4], QA_TILE, 0, S_(s)>>>(a);
+  fill_q_adam(a, lr_planes, lr_cplanes, step, beta1, beta2, eps);
+  k_q_adam_planes<<<a.qg.unit0[4], QA_THREADS, 0, S_(s)>>>(a);
   CHECK_LAUNCH("eslam_q_adam_planes");
   return 0;
 }

@@ -2,18 +2,12 @@
 // src/Mapper.py:348-350 is the optimiser step this replaces on several GPUs).
 //
 // Every rank keeps, at the SAME offsets of one symmetric allocation (NVLink peer-mapped, one per process):
-//   parameter arena | gradient staging [world][slice] | published aux blocks (pose gradients, loss sums, counters)
-//   | flag block
-// The gradient arena itself stays in ORDINARY device memory: red.global.add into peer-mapped memory costs the
+//   parameter arena | gradient-image staging [world][slice] | published aux blocks (decoder gradients, pose
+//   gradients, loss sums, counters) | flag block
+// The gradient images themselves stay in ORDINARY device memory: red.global.add into peer-mapped memory costs the
 // fused backward +30 us per launch on B200 (tools/exchange_times.py), peer-mapped parameters cost nothing.
-// After the local backward has reduced a rank's rays into its gradient arena, two back-to-back kernels per rank do
-// reduce-scatter + Adam + all-gather + zero_grad over peer memory:
-//   k_grad_push:     slice q of the local gradient arena is stored into rank q's staging row [rank] (P2P stores)
-//                    and zeroed locally, for every q != rank
-//   k_adam_exchange: barrier -> rank r sums its own slice and the staged rows in rank order (local loads) ->
-//                    torch.optim.Adam on slice r (moments exist for the own slice only) -> the new parameters are
-//                    stored into every rank's arena (P2P stores or one multimem.st through the NVSwitch) -> barrier
-// No NCCL call and no separate Adam pass; replicas stay bit-identical because every parameter has one writer.
+// No NCCL call and no separate Adam pass; replicas stay bit-identical because every parameter has one writer
+// (planes: the owner of the tile; decoders: every rank computes the same sum in the same order).
 //
 // Synchronisation: one LEADER CTA per rank shakes hands with the peers (world_size flag stores + polls, one
 // system-scope fence); the other CTAs wait on / report to the leader through two local words with gpu-scope
@@ -26,6 +20,7 @@
 // that exceeds SPIN_LIMIT_NS raises the local status word and falls through, so a missing peer cannot hang the GPU.
 #pragma once
 #include "optim.cuh"
+#include "qplane.cuh"
 
 namespace eslam {
 
@@ -119,20 +114,30 @@ __global__ void __launch_bounds__(32) k_exchange_counters(const __grid_constant_
   }
 }
 
-// ---- reduce-scatter + Adam + all-gather ----------------------------------------------------------------------
-struct AdamExchArgs {
+// ---- reduce-scatter of the gradient images + plane Adam + all-gather, then the decoders' replicated step ----------
+// The mapping backward (qbwd.cuh) leaves a rank's plane gradients as 16-channel gradient images (13.5 MB for room0:
+// half of a parameter-form gradient arena) and its decoder gradients in the gradient arena's decoder block.
+// Ownership is by TILES of the optimiser tail (qplane.cuh: QA_TILE texels): rank r owns a contiguous range of
+// tiles, i.e. a contiguous slice of the images.
+//   k_gq_push          every rank stores the peers' slices of its gradient image into their staging rows [rank]
+//                      (P2P stores) and zeroes them locally; all-zero groups of 128 floats are not sent
+//   k_q_adam_exchange  barrier -> the tail (q_adam_tile) on the owned tiles, whose gradient rows are the sum of the
+//                      local image and the staged rows in rank order and whose updated texels go to EVERY rank's
+//                      arena -> the leader publishes this rank's decoder gradients (dW1 of the owned tiles, the
+//                      backward's other decoder gradients) -> barrier
+//   k_dec_adam_peers   every rank sums all ranks' published decoder gradients in rank order and takes the
+//                      decoders' Adam step (replicated: identical on every rank)
+struct QExchArgs {
   PeerSync ps;
-  float4* p[MAX_PEERS];      // parameter arena of every rank
-  float4* stage[MAX_PEERS];  // gradient staging of every rank: [world][slice_max] float4
-  float4* g;                 // local gradient arena (ordinary memory)
-  float4* mc_p;              // multicast alias of the parameter arenas (MULTIMEM only)
-  float4 *m, *v;             // local moments (only the own slice is ever touched)
-  AdamArgs adam;             // scalars + lr segments (p/g/m/v members unused)
-  float* aux_local;             // this rank's pose-gradient block: published, then zeroed
-  float* aux_pub[MAX_PEERS];    // every rank's published copy (this call's parity)
-  float* aux_sum;               // local [n_aux]: sum over ranks
+  QAdamArgs q;
+  long long lo4[MAX_PEERS + 1];  // first float4 of every rank's slice of the gradient images
+  float4* stage[MAX_PEERS];      // staging of every rank: [world][smax] float4
+  float* dec_pub[MAX_PEERS];     // every rank's published decoder gradients (this call's parity), DEC_N floats
+  float* aux_local;              // this rank's pose-gradient block: published, then zeroed
+  float* aux_pub[MAX_PEERS];     // every rank's published copy (this call's parity)
+  float* aux_sum;                // local [n_aux]: sum over ranks
   int n_aux;
-  double* auxd_local;           // this rank's loss sums
+  double* auxd_local;            // this rank's loss sums
   double* auxd_pub[MAX_PEERS];
   double* auxd_sum;
   int n_auxd;
@@ -142,12 +147,6 @@ struct AdamExchArgs {
 
 constexpr int EXCH_THREADS = 256;
 constexpr int SLOT_COUNTERS = 0, SLOT_IN = 1, SLOT_OUT = 2, N_SLOTS = 4;
-
-__device__ __forceinline__ void slice_of(long long n4, int world, int r, long long& lo, long long& hi) {
-  const long long base = n4 / world, rem = n4 % world;
-  lo = r * base + (r < rem ? r : rem);
-  hi = lo + base + (r < rem ? 1 : 0);
-}
 
 __device__ __forceinline__ void wait_local(const PeerSync& ps, int word, unsigned long long target) {
   if (threadIdx.x == 0) {
@@ -162,58 +161,48 @@ __device__ __forceinline__ void wait_local(const PeerSync& ps, int word, unsigne
   __syncthreads();
 }
 
-__device__ __forceinline__ long long slice_max(long long n4, int world) { return (n4 + world - 1) / world; }
-
 // ---- reduce-scatter, push half: my contribution to every other rank's slice goes into its staging row [rank] --
-__global__ void __launch_bounds__(EXCH_THREADS) k_grad_push(const __grid_constant__ AdamExchArgs a) {
+__global__ void __launch_bounds__(EXCH_THREADS) k_gq_push(const __grid_constant__ QExchArgs a) {
   const int rank = a.ps.rank, world = a.ps.world;
-  const long long n4 = a.adam.n >> 2;
-  const long long smax = slice_max(n4, world);
   const long long stride = (long long)gridDim.x * EXCH_THREADS;
   const long long first = (long long)blockIdx.x * EXCH_THREADS + threadIdx.x;
   if (a.dbg & 8) return;
   const float4 z = f4_zero();
   for (int dq = 1; dq < world; ++dq) {
     const int q = (rank + dq) % world;  // start with a different peer on every rank: spreads the link load
-    long long lo, hi;
-    slice_of(n4, world, q, lo, hi);
-    float4* dst = a.stage[q] + (long long)rank * smax - lo;
-    // Whole, globally aligned groups of 32 float4 (128 parameters) per warp and trip.  A group whose gradient is all
+    const long long lo = a.lo4[q], hi = a.lo4[q + 1];
+    float4* dst = a.stage[q] + (long long)rank * a.q.smax - lo;
+    // Whole, globally aligned groups of 32 float4 (8 texels) per warp and trip.  A group whose gradient is all
     // zero on this rank is not sent: the owner keeps its staging rows zero (it clears what it consumes), and a
     // mapping window only ever touches part of the planes, so most of the NVLink volume disappears.
     const long long lo_a = lo & ~31ll, hi_r = (hi + 31) & ~31ll;
     for (long long i = lo_a + first; i < hi_r; i += stride) {
       const bool in = i >= lo && i < hi;
-      const float4 v = in ? a.g[i] : z;
+      const float4 v = in ? a.q.gq4[i] : z;
       const bool nz = v.x != 0.f || v.y != 0.f || v.z != 0.f || v.w != 0.f;
       if (__ballot_sync(0xffffffffu, nz) == 0u) continue;
       if (in) {
         dst[i] = v;
-        a.g[i] = z;
+        a.q.gq4[i] = z;
       }
     }
   }
 }
 
-// ---- reduce-scatter (sum half) + Adam + all-gather ---------------------------------------------------------------
-// WMAX: compile-time bound of the world size (2, 4 or 8).
-template <bool MULTIMEM, int WMAX>
-__global__ void __launch_bounds__(EXCH_THREADS) k_adam_exchange(const __grid_constant__ AdamExchArgs a) {
+// WMAX: compile-time bound of the world size (2, 4 or 8).  Grid = the tiles this rank owns.
+template <int WMAX>
+__global__ void __launch_bounds__(QA_THREADS, 4) k_q_adam_exchange(const __grid_constant__ QExchArgs a) {
+  __shared__ SmemQAdam sm;
   const int rank = a.ps.rank, world = a.ps.world;
-  const int cta = blockIdx.x, nctas = gridDim.x;
-  const long long n4 = a.adam.n >> 2;
-  const long long smax = slice_max(n4, world);
-  const long long stride = (long long)nctas * EXCH_THREADS;
-  const long long first = (long long)cta * EXCH_THREADS + threadIdx.x;
-  const bool leader = cta == 0;
-  // ---- every rank's k_grad_push has completed (stream order on its side, handshake across ranks)
+  const bool leader = blockIdx.x == 0;
+  // ---- every rank's k_gq_push has completed (stream order on its side, handshake across ranks)
   if (leader) {
     // publish this rank's small blocks (pose gradients, loss sums) and clear the local ones for the next iteration
-    for (int t = threadIdx.x; t < a.n_aux; t += EXCH_THREADS) {
+    for (int t = threadIdx.x; t < a.n_aux; t += QA_THREADS) {
       a.aux_pub[rank][t] = a.aux_local[t];
       a.aux_local[t] = 0.f;
     }
-    for (int t = threadIdx.x; t < a.n_auxd; t += EXCH_THREADS) {
+    for (int t = threadIdx.x; t < a.n_auxd; t += QA_THREADS) {
       a.auxd_pub[rank][t] = a.auxd_local[t];
       a.auxd_local[t] = 0.0;
     }
@@ -222,64 +211,10 @@ __global__ void __launch_bounds__(EXCH_THREADS) k_adam_exchange(const __grid_con
   } else if (!(a.dbg & 32)) {
     wait_local(a.ps, 0, (unsigned long long)a.ps.epoch);
   }
-  long long lo, hi;
-  slice_of(n4, world, rank, lo, hi);
-  if (a.dbg & 8) hi = lo;
-  float4* const p_own = a.p[rank];
-  float4* const st_own = a.stage[rank] - lo;
-  const float4 z = f4_zero();
-  unsigned char* const touched = a.adam.touched;
-  // Whole, globally aligned groups of 128 parameters per warp and trip (see k_grad_push).  A group in which no rank
-  // has had a non-zero gradient since the optimiser was created still has m = v = 0: torch's update leaves p as it
-  // is on every replica, so nothing is read beyond the gradients and nothing is stored or broadcast (k_adam).
-  const long long lo_a = lo & ~31ll, hi_r = (hi + 31) & ~31ll;
-  for (long long i = lo_a + first; i < hi_r; i += stride) {
-    const bool in = i >= lo && i < hi;
-    float4 part[WMAX];
-    bool nz = false;
-#pragma unroll
-    for (int q = 0; q < WMAX; ++q)
-      if (q < world) {
-        part[q] = !in ? z : (q == rank) ? a.g[i] : ld_sys_v4(st_own + q * smax + i);
-        nz = nz || part[q].x != 0.f || part[q].y != 0.f || part[q].z != 0.f || part[q].w != 0.f;
-      }
-    const bool any = __ballot_sync(0xffffffffu, nz) != 0u;
-    const bool was = touched ? touched[i >> 5] != 0 : true;
-    if (!any && !was) continue;
-    if (touched && !was && (threadIdx.x & 31) == 0) touched[i >> 5] = 1;
-    if (!in) continue;
-    if (any) {  // consumed: the gradient arena and the staging rows go back to zero
-      a.g[i] = z;
-#pragma unroll
-      for (int q = 0; q < WMAX; ++q)
-        if (q < world && q != rank) st_own[q * smax + i] = z;
-    }
-    float4 p = p_own[i], m = a.m[i], v = a.v[i];
-    float4 g = part[0];
-#pragma unroll
-    for (int q = 1; q < WMAX; ++q)
-      if (q < world) g = f4_add(g, part[q]);  // fixed rank order: the sum does not depend on who owns the slice
-    const long long e = i << 2;
-    int seg = 0;
-    while (seg < a.adam.n_seg - 1 && e >= a.adam.seg_end[seg]) ++seg;
-    const float ss = a.adam.seg_step[seg];
-    adam_one(p.x, g.x, m.x, v.x, a.adam, ss);
-    adam_one(p.y, g.y, m.y, v.y, a.adam, ss);
-    adam_one(p.z, g.z, m.z, v.z, a.adam, ss);
-    adam_one(p.w, g.w, m.w, v.w, a.adam, ss);
-    a.m[i] = m;
-    a.v[i] = v;
-    if (MULTIMEM) {
-      multimem_st_v4(a.mc_p + i, p);
-    } else {
-#pragma unroll
-      for (int q = 0; q < WMAX; ++q)
-        if (q < world) a.p[q][i] = p;
-    }
-  }
+  if (!(a.dbg & 8)) q_adam_tile<WMAX>(a.q, a.q.unit_lo + blockIdx.x, sm);
   // ---- small replicated sums (pose gradients, loss terms): every rank adds all ranks' blocks in rank order
   if (leader) {
-    for (int t = threadIdx.x; t < a.n_aux; t += EXCH_THREADS) {
+    for (int t = threadIdx.x; t < a.n_aux; t += QA_THREADS) {
       float acc = 0.f;
       for (int p = 0; p < world; ++p) {
         float x;
@@ -288,7 +223,7 @@ __global__ void __launch_bounds__(EXCH_THREADS) k_adam_exchange(const __grid_con
       }
       a.aux_sum[t] = acc;
     }
-    for (int t = threadIdx.x; t < a.n_auxd; t += EXCH_THREADS) {
+    for (int t = threadIdx.x; t < a.n_auxd; t += QA_THREADS) {
       double acc = 0.0;
       for (int p = 0; p < world; ++p) {
         double x;
@@ -302,16 +237,44 @@ __global__ void __launch_bounds__(EXCH_THREADS) k_adam_exchange(const __grid_con
     if (threadIdx.x == 0) atomicAdd(a.ps.local + 1, 1ull);
     return;
   }
-  // ---- this CTA's parameter stores are performed system-wide; report to the leader and leave
+  // ---- this CTA's parameter stores and dW1 reductions are performed system-wide; report to the leader and leave
   __syncthreads();
   if (threadIdx.x == 0) {
     __threadfence_system();
     atomicAdd(a.ps.local + 1, 1ull);
   }
   if (!leader) return;
-  // ---- leader: all local CTAs have stored their slice into every rank -> tell the peers, wait for theirs
+  // ---- leader: all local CTAs are done -> publish the decoder gradients, tell the peers, wait for theirs
   wait_local(a.ps, 1, a.ps.done_target);
+  for (int t = threadIdx.x; t < DEC_N; t += QA_THREADS) {
+    a.dec_pub[rank][t] = __ldcg(a.q.gdec + t);
+    a.q.gdec[t] = 0.f;
+  }
   peer_barrier(a.ps, SLOT_OUT);
+}
+
+// the decoders' Adam step on the sum of all ranks' published gradients (torch/optim/adam.py, exact operation order)
+struct DecPeersArgs {
+  int world;
+  const float* dec_pub[MAX_PEERS];
+  float *p, *m, *v;  // local decoder block of the parameter / moment arenas
+  AdamArgs adam;     // seg_step[0] = lr / (1 - beta1^t)
+};
+
+__global__ void __launch_bounds__(256) k_dec_adam_peers(const __grid_constant__ DecPeersArgs a) {
+  for (int t = threadIdx.x; t < DEC_N; t += 256) {
+    float g = 0.f;
+    for (int q = 0; q < a.world; ++q) {
+      float x;
+      asm volatile("ld.relaxed.sys.global.f32 %0, [%1];" : "=f"(x) : "l"(a.dec_pub[q] + t) : "memory");
+      g = q == 0 ? x : g + x;
+    }
+    float p = a.p[t], m = a.m[t], v = a.v[t];
+    adam_one(p, g, m, v, a.adam, a.adam.seg_step[0]);
+    a.p[t] = p;
+    a.m[t] = m;
+    a.v[t] = v;
+  }
 }
 
 }  // namespace eslam

@@ -115,14 +115,18 @@ struct SmemFwdQ {
 //     d loss / d plane[texel][c]   = sum_j W1[j][scale*32 + c] * GQ[texel][j]
 //     d loss / d W1[j][scale*32+c] = sum over the three planes of that scale and all texels of GQ[texel][j] * plane[texel][c]
 // so it is fused with the plane half of Adam: the plane gradient lives in registers only.
-// One CTA = QA_TILE consecutive texels of one group, ONE THREAD PER TEXEL: the thread scans its texel's 64-byte
-// gradient row and `touched` byte; an active texel (non-zero row, or moments that are already non-zero) then takes
-// the whole 32-channel update in that thread, so a tile costs two dependent memory round trips however many of its
-// texels are active (an 8-lanes-per-texel form serialised up to 8 trips per warp and ran 40 us).  Exact skip as in
-// k_adam: a texel whose GQ has been zero since the optimiser was created has m = v = 0 and a zero update; a tile
-// without active texels ends after the scan.  dW1: rows and pre-update texels of the tile are parked in shared
-// memory and thread (j, c4) sums its four outputs over the tile's non-zero rows, one 16-byte reduction per thread
-// into the gradient arena's decoder block (the decoders then take the ordinary Adam step, k_q_build follows).
+// One CTA = one tile of QA_TILE consecutive texels of one group, three phases, every global access coalesced:
+//   A  the tile's gradient rows (16 KB... 8 KB), its texels (16 KB) and `touched` bytes go to shared memory, all loads
+//      in flight at once; on several GPUs the rows are the sum of the local image and the peers' staged slices
+//   B  thread (texel, c4): plane gradient of its four channels (64 FMA against W1 in shared memory), Adam, stores --
+//      only for ACTIVE texels (non-zero row now, or non-zero moments from an earlier iteration: exact skip as in
+//      k_adam); on several GPUs the new texel goes to every rank's arena (P2P stores)
+//   C  dW1 of the tile = G^T P, a 16 x 32 x 128 contraction on the tensor cores (split-bf16 mma, render.cuh), one
+//      16-byte reduction per lane into the gradient arena's decoder block
+// (An 8-lanes-per-texel form with dW1 in registers ran 40 us, a thread-per-texel form 34 us: after the first
+// iterations of a call nearly every 32-texel run holds an active texel, so per-texel divergence buys nothing, and
+// the tail is bound by issue slots -- hence the approximate reciprocal / square root in phase B, 2 ulp, where the
+// parameter-form k_adam keeps torch's exact operation order.)
 struct QAdamArgs {
   QGroups qg;      // units = tiles of QA_TILE texels
   float4* arena4;  // parameters; the planes are updated in place
@@ -132,93 +136,193 @@ struct QAdamArgs {
   const float* dec;
   unsigned char* touched;  // one flag per texel, in texel order
   float step_sdf, step_rgb;  // lr / (1 - beta1^t) of the sdf / rgb planes
+  float inv_bc2;
   AdamArgs adam;             // scalars only
+  // several GPUs (world > 1): this rank owns the units [unit_lo, unit_lo + gridDim.x)
+  int rank, world, unit_lo;
+  long long lo4, smax;              // first float4 of the owned slice of the gradient images; staging row pitch
+  float4* stage;                    // local staging rows [world][smax]: the peers' slices of this rank's texels
+  float4* peer_p[ESLAM_MAX_PEERS];  // every rank's parameter arena
+  float4* mc_p;                     // multicast alias of the parameter arenas or NULL
 };
 
-constexpr int QA_TILE = 128;
+constexpr int QA_TILE = 128, QA_THREADS = 256;
 
-__global__ void __launch_bounds__(QA_TILE, 4) k_q_adam_planes(const __grid_constant__ QAdamArgs a) {
-  __shared__ __align__(16) float sW[16 * 32];
-  __shared__ float4 sP[QA_TILE * 8];   // pre-update texels, t_slot layout
-  __shared__ float4 sG[QA_TILE * 4];   // gradient rows, p_slot layout
-  __shared__ int s_list[QA_TILE];
-  __shared__ int s_n;
-  const int g = q_group_of(a.qg, blockIdx.x);
-  const int t = threadIdx.x;
-  const int tl = (blockIdx.x - a.qg.unit0[g]) * QA_TILE + t;
-  const bool valid = tl < a.qg.n[g];
-  const long long texel = (long long)a.qg.t0[g] + tl;
-  // ---- scan
-  float4 r[4];
-  bool nz = false, flag = false;
-  if (valid) {
-    const float4* row = a.gq4 + texel * 4;
+struct SmemQAdam {
+  float4 sG[QA_TILE * 4];  // gradient rows, p_slot layout
+  float4 sP[QA_TILE * 8];  // texels before the update, t_slot layout
+  float sW[16 * 32];
+  unsigned char nz[QA_TILE], act[QA_TILE];
+};
+
+struct FromT {  // t_slot tile: rows = texels, c = channel (q0 is a multiple of 16, so the swizzle term depends on r only)
+  const float* base;
+  int o[4];
+  __device__ __forceinline__ FromT(const float4* T, int c, int t) : base(reinterpret_cast<const float*>(T)) {
+    const int r[4] = {2 * t, 2 * t + 1, 2 * t + 8, 2 * t + 9};
 #pragma unroll
-    for (int c = 0; c < 4; ++c) r[c] = row[c];
-    flag = a.touched[texel] != 0;
-#pragma unroll
-    for (int c = 0; c < 4; ++c) nz = nz || r[c].x != 0.f || r[c].y != 0.f || r[c].z != 0.f || r[c].w != 0.f;
-    if (nz && !flag) a.touched[texel] = 1;
+    for (int i = 0; i < 4; ++i) o[i] = (r[i] * 8 + ((c >> 2) ^ (r[i] & 7))) * 4 + (c & 3);
   }
-  const bool active = nz || flag;
-  if (t == 0) s_n = 0;
-  if (!__syncthreads_or(active)) return;  // nothing to do in this tile
-  const float* w1 = a.dec + ((g >> 1) ? C_W1 : S_W1) + (g & 1) * 32;
-  for (int i = t; i < 16 * 32; i += QA_TILE) sW[i] = w1[(i >> 5) * 64 + (i & 31)];
-  float4 pk[8];
-  if (active) {
+  __device__ __forceinline__ float at(int q0, int i) const { return base[q0 * 32 + o[i]]; }
+};
+struct FromG {  // p_slot tile: rows = texels, c = channel
+  const float* base;
+  int o[4];
+  __device__ __forceinline__ FromG(const float4* P, int c, int t) : base(reinterpret_cast<const float*>(P)) {
+    const int r[4] = {2 * t, 2 * t + 1, 2 * t + 8, 2 * t + 9};
 #pragma unroll
-    for (int c4 = 0; c4 < 8; ++c4) pk[c4] = a.arena4[texel * 8 + c4];
+    for (int i = 0; i < 4; ++i) o[i] = (r[i] * 4 + ((c >> 2) ^ ((r[i] >> 1) & 3))) * 4 + (c & 3);
   }
-  if (nz) {
-    s_list[atomicAdd(&s_n, 1)] = t;
+  __device__ __forceinline__ float at(int q0, int i) const { return base[q0 * 16 + o[i]]; }
+};
+
+__device__ __forceinline__ float4 ld_sys_f4(const float4* p) {
+  float4 v;
+  asm volatile("ld.relaxed.sys.global.v4.f32 {%0,%1,%2,%3}, [%4];"
+               : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
+               : "l"(p)
+               : "memory");
+  return v;
+}
+__device__ __forceinline__ bool f4_nonzero(float4 v) { return v.x != 0.f || v.y != 0.f || v.z != 0.f || v.w != 0.f; }
+
+// torch.optim.Adam's update with an approximate square root and reciprocal (2 ulp each)
+__device__ __forceinline__ void adam_fast(float& p, float g, float& m, float& v, const QAdamArgs& a, float ss) {
+  m = fmaf(a.adam.one_m_beta1, g - m, m);
+  v = fmaf(a.adam.one_m_beta2 * g, g, a.adam.beta2 * v);
+  float r;
+  asm("sqrt.approx.f32 %0, %1;" : "=f"(r) : "f"(v));
+  p = fmaf(-ss * m, __fdividef(1.0f, fmaf(r, a.inv_bc2, a.adam.eps)), p);
+}
+
+// WMAX: compile-time bound of the world size (1 = one GPU)
+template <int WMAX>
+__device__ __forceinline__ void q_adam_tile(const QAdamArgs& a, int unit, SmemQAdam& sm) {
+  const int g = q_group_of(a.qg, unit);
+  const int tl0 = (unit - a.qg.unit0[g]) * QA_TILE;
+  const int cnt = min(QA_TILE, a.qg.n[g] - tl0);
+  const long long tbase = (long long)a.qg.t0[g] + tl0;
+  const int tid = threadIdx.x, lane = tid & 31;
+  const float4 z4 = f4_zero();
+  // ---- phase A
 #pragma unroll
-    for (int c = 0; c < 4; ++c) sG[p_slot(t, c)] = r[c];
+  for (int k = 0; k < QA_TILE * 4 / QA_THREADS; ++k) {
+    const int i = tid + k * QA_THREADS, t = i >> 2, c = i & 3;
+    float4 v = z4;
+    bool nz = false;
+    if (t < cnt) {
+      const long long idx = tbase * 4 + i;
+      if (WMAX == 1) {
+        v = a.gq4[idx];
+        nz = f4_nonzero(v);
+        if (nz) a.gq4[idx] = z4;
+      } else {
+        // fixed rank order: the sum does not depend on who owns the slice
 #pragma unroll
-    for (int c4 = 0; c4 < 8; ++c4) sP[t_slot(t, c4)] = pk[c4];
-  }
-  __syncthreads();
-  if (active) {
-    const float ss = (g >> 1) ? a.step_rgb : a.step_sdf;
-    const float gj[16] = {r[0].x, r[0].y, r[0].z, r[0].w, r[1].x, r[1].y, r[1].z, r[1].w,
-                          r[2].x, r[2].y, r[2].z, r[2].w, r[3].x, r[3].y, r[3].z, r[3].w};
-    const float4 z4 = f4_zero();
-#pragma unroll
-    for (int c4 = 0; c4 < 8; ++c4) {
-      const long long at = texel * 8 + c4;
-      float4 m = a.m4[at], v = a.v4[at], p = pk[c4];
-      float4 gr = z4;
-      if (nz) {
-#pragma unroll
-        for (int j = 0; j < 16; ++j) gr = f4_fma(gj[j], lds4(sW + j * 32 + c4 * 4), gr);
+        for (int q = 0; q < WMAX; ++q)
+          if (q < a.world) {
+            float4* src = q == a.rank ? a.gq4 + idx : a.stage + q * a.smax + (idx - a.lo4);
+            const float4 part = q == a.rank ? *src : ld_sys_f4(src);
+            if (f4_nonzero(part)) {  // consumed: the image and the staging rows go back to zero
+              nz = true;
+              *src = z4;
+            }
+            v = q == 0 ? part : f4_add(v, part);
+          }
       }
-      adam_one(p.x, gr.x, m.x, v.x, a.adam, ss);
-      adam_one(p.y, gr.y, m.y, v.y, a.adam, ss);
-      adam_one(p.z, gr.z, m.z, v.z, a.adam, ss);
-      adam_one(p.w, gr.w, m.w, v.w, a.adam, ss);
-      a.arena4[at] = p;
-      a.m4[at] = m;
-      a.v4[at] = v;
     }
-    if (nz) {
-      float4* row = a.gq4 + texel * 4;
+    sm.sG[p_slot(t, c)] = v;
+    const unsigned b = __ballot_sync(0xffffffffu, nz);
+    if (c == 0) sm.nz[t] = ((b >> (lane & ~3)) & 0xfu) != 0u;
+  }
 #pragma unroll
-      for (int c = 0; c < 4; ++c) row[c] = z4;
+  for (int k = 0; k < QA_TILE * 8 / QA_THREADS; ++k) {
+    const int i = tid + k * QA_THREADS, t = i >> 3;
+    sm.sP[t_slot(t, i & 7)] = t < cnt ? a.arena4[tbase * 8 + i] : z4;
+  }
+  bool flag = false;
+  if (tid < cnt) flag = a.touched[tbase + tid] != 0;
+  const float* w1 = a.dec + ((g >> 1) ? C_W1 : S_W1) + (g & 1) * 32;
+  for (int i = tid; i < 16 * 32; i += QA_THREADS) sm.sW[i] = w1[(i >> 5) * 64 + (i & 31)];
+  __syncthreads();
+  bool mine_nz = false, mine_act = false;
+  if (tid < QA_TILE) {
+    mine_nz = sm.nz[tid] != 0;
+    mine_act = mine_nz || flag;
+    sm.act[tid] = mine_act;
+    if (mine_nz && !flag) a.touched[tbase + tid] = 1;
+  }
+  const bool any_act = __syncthreads_or(mine_act);
+  const bool any_nz = __syncthreads_or(mine_nz);
+  if (!any_act) return;
+  // ---- phase B: (texel, c4) items; the moments of the thread's four items are requested together
+  {
+    const int c4 = tid & 7;
+    const float ss = (g >> 1) ? a.step_rgb : a.step_sdf;
+    float4 m[4], v[4];
+    bool on[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const int t = (tid >> 3) + k * 32;
+      on[k] = t < cnt && sm.act[t];
+      if (on[k]) {
+        const long long at = (tbase + t) * 8 + c4;
+        m[k] = a.m4[at];
+        v[k] = a.v4[at];
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const int t = (tid >> 3) + k * 32;
+      if (!on[k]) continue;
+      const long long at = (tbase + t) * 8 + c4;
+      float4 p = sm.sP[t_slot(t, c4)];
+      float4 gr = z4;
+      if (sm.nz[t]) {
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          const float4 gv = sm.sG[p_slot(t, c)];
+          gr = f4_fma(gv.x, lds4(sm.sW + (c * 4 + 0) * 32 + c4 * 4), gr);
+          gr = f4_fma(gv.y, lds4(sm.sW + (c * 4 + 1) * 32 + c4 * 4), gr);
+          gr = f4_fma(gv.z, lds4(sm.sW + (c * 4 + 2) * 32 + c4 * 4), gr);
+          gr = f4_fma(gv.w, lds4(sm.sW + (c * 4 + 3) * 32 + c4 * 4), gr);
+        }
+      }
+      adam_fast(p.x, gr.x, m[k].x, v[k].x, a, ss);
+      adam_fast(p.y, gr.y, m[k].y, v[k].y, a, ss);
+      adam_fast(p.z, gr.z, m[k].z, v[k].z, a, ss);
+      adam_fast(p.w, gr.w, m[k].w, v[k].w, a, ss);
+      a.m4[at] = m[k];
+      a.v4[at] = v[k];
+      if (WMAX == 1) {
+        a.arena4[at] = p;
+      } else if (a.mc_p) {
+        asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(a.mc_p + at), "f"(p.x), "f"(p.y),
+                     "f"(p.z), "f"(p.w)
+                     : "memory");
+      } else {
+#pragma unroll
+        for (int q = 0; q < WMAX; ++q)
+          if (q < a.world) a.peer_p[q][at] = p;
+      }
     }
   }
-  // ---- dW1 of the tile: thread (j, c4) over the non-zero rows
-  const int n = s_n;
-  if (n == 0) return;
-  const int j = t >> 3, c4 = t & 7;
-  float4 acc = f4_zero();
-  const float* sGf = reinterpret_cast<const float*>(sG);
-  for (int i = 0; i < n; ++i) {
-    const int tt = s_list[i];
-    const float gv = sGf[p_slot(tt, j >> 2) * 4 + (j & 3)];
-    acc = f4_fma(gv, sP[t_slot(tt, c4)], acc);
+  // ---- phase C: dW1 += G^T P over the tile; warp w: channels 8 (w & 3) .., texels 64 (w >> 2) ..
+  if (any_nz) {
+    const int w = tid >> 5, nt = w & 3, kh = w >> 2;
+    const int gg = lane >> 2, tt = lane & 3;
+    float acc[1][4];
+    const FromG a_lo(sm.sG, gg, tt), a_hi(sm.sG, gg + 8, tt);
+    const FromT b[1] = {FromT(sm.sP, nt * 8 + gg, tt)};
+    wgrad_tiles<16, 1>(a_lo, a_hi, b, kh * (QA_TILE / 2), (kh + 1) * (QA_TILE / 2), lane, acc);
+    float* dst = a.gdec + ((g >> 1) ? C_W1 : S_W1) + (g & 1) * 32;
+    wgrad_store(dst, 64, nt * 8, 16, lane, acc[0]);
   }
-  float4* dst = reinterpret_cast<float4*>(a.gdec + ((g >> 1) ? C_W1 : S_W1) + (g & 1) * 32);
-  if (acc.x != 0.f || acc.y != 0.f || acc.z != 0.f || acc.w != 0.f) red_add_v4(dst + j * 16 + c4, acc);
+}
+
+__global__ void __launch_bounds__(QA_THREADS, 4) k_q_adam_planes(const __grid_constant__ QAdamArgs a) {
+  __shared__ SmemQAdam sm;
+  q_adam_tile<1>(a, blockIdx.x, sm);
 }
 
 // layers 2 and 3 on h1 = relu(pre + b1), weights as constant-memory operands (field.cuh mlp_forward, minus layer 1)

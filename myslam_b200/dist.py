@@ -2,16 +2,16 @@
 one process per GPU, parameters replicated, every rank renders its own slice of the keyframe-ray
 batch, and two exchanges per iteration make all ranks differentiate the SAME global-batch loss:
 
-  1. all-reduce of the 8 int32 loss normalisers (ray / band counts) -> `norm` for eslam_loss_backward
-  2. all-reduce (sum, fp32) of the gradient arena (12 planes + decoders, one contiguous buffer) and of
-     the [frames,12] pose-gradient block, over NCCL (NVLink 5 / NVSwitch), then the identical Adam step.
+  1. all-reduce of the 8 int32 loss normalisers (ray / band counts) -> `norm` for eslam_loss_backward_q
+  2. all-reduce (sum, fp32) of the map gradients (the 16-channel gradient images of the 12 planes, the decoder
+     block) and of the [frames,12] pose-gradient block, then the identical Adam step.
 
 `MappingExchange` does both with NCCL collectives (and with gloo on CPU tensors for the world_size-2 tests).
-`PeerExchange` is the B200 path: parameters, two alternating gradient arenas, published pose-gradient / loss /
-counter blocks and a flag block live in ONE symmetric (NVLink peer-mapped) allocation per rank, the normalisers
-are summed by a one-CTA kernel over peer loads, and `eslam_adam_exchange` does reduce-scatter + Adam + all-gather
-+ zero_grad in a single kernel over peer memory (P2P loads/stores, or multimem.ld_reduce / multimem.st through
-the NVSwitch).
+`PeerExchange` is the B200 path: parameters, a gradient-image staging block, published decoder-gradient /
+pose-gradient / loss / counter blocks and a flag block live in ONE symmetric (NVLink peer-mapped) allocation per
+rank, the normalisers are summed by a one-CTA kernel over peer loads, and `eslam_q_adam_exchange` does reduce-scatter
+of the gradient images + plane Adam + all-gather + zero_grad over peer memory (P2P loads/stores, or multimem.st through
+the NVSwitch), followed by the decoders' replicated step on the sum of the published decoder gradients.
 No NCCL call is left on the per-iteration path; torch.distributed only sets the allocation up.
 """
 from __future__ import annotations
@@ -49,6 +49,14 @@ class MappingExchange:
             dist.all_reduce(loss_acc, op=dist.ReduceOp.SUM, group=self.group)
 
 
+    def after_step(self, store) -> None:
+        """Keep the replicas bit-identical: the plane update is deterministic given the all-reduced gradient images,
+        but dW1 is summed with floating-point atomics whose order differs from rank to rank, so the decoders (2 700
+        floats) are taken from rank 0 after every step."""
+        if self.world > 1:
+            dist.broadcast(store.dec, src=0, group=self.group)
+
+
 class PeerExchange(MappingExchange):
     """Symmetric-memory exchange for one FieldStore.  Construct it on every rank at the same point (it is
     collective); afterwards `store.arena` is a view of the symmetric allocation.  The gradient arena stays in
@@ -72,7 +80,9 @@ class PeerExchange(MappingExchange):
         self.n_pose = frames * 12
         pose_blk = ((self.n_pose + 3) // 4) * 4
         flag_words = _lib.load().eslam_exchange_flag_words()
-        n_stage = int(_lib.load().eslam_exchange_stage_floats(n, self.world))
+        n_stage = int(_lib.load().eslam_q_exchange_stage_floats(store.ref(), self.world))
+        if n_stage <= 0:
+            raise RuntimeError("PeerExchange: the plane layout cannot be sliced over the ranks")
         self.off_stage = n
         o = n + n_stage
         self.off_pose = [o, o + pose_blk]
@@ -81,6 +91,8 @@ class PeerExchange(MappingExchange):
         o += 4 * _lib.N_LOSS
         self.off_cnt = [o, o + _lib.N_COUNTERS]
         o += 2 * _lib.N_COUNTERS
+        self.off_dec = [o, o + _lib.DEC_FLOATS]  # published decoder gradients, two copies
+        o += 2 * _lib.DEC_FLOATS
         self.off_flags = o
         total = o + flag_words
         grp = group if group is not None else dist.group.WORLD
@@ -108,6 +120,7 @@ class PeerExchange(MappingExchange):
         self._pose = [table(o_) for o_ in self.off_pose]
         self._loss = [table(o_) for o_ in self.off_loss]
         self._cnt = [table(o_) for o_ in self.off_cnt]
+        self._dec = [table(o_) for o_ in self.off_dec]
         self.peers = _lib.Peers()
         self.peers.rank, self.peers.world, self.peers.epoch, self.peers.adam_seq = self.rank, self.world, 0, 0
         for r in range(self.world):
@@ -124,7 +137,9 @@ class PeerExchange(MappingExchange):
         arena = self.buf[:n]
         arena.copy_(store.arena)
         store.arena = arena
+        store.gen += 1
         store.ensure_grad()
+        store.ensure_q_grad()
         torch.cuda.synchronize(dev)
         dist.barrier(group)  # nobody signals into a flag block that is not zeroed yet
 
@@ -163,9 +178,10 @@ class PeerExchange(MappingExchange):
 
     def adam_exchange(self, step: int, lr_dec: float, lr_planes: float, lr_cplanes: float, pose_grad=None,
                       n_pose_frames: int = 0, loss_acc=None, betas=(0.9, 0.999), eps=1e-8):
-        """The fused optimiser step of the ray-sharded mapping on `store.grad` (this iteration's gradient arena).
-        pose_grad [frames,12] / loss_acc float64[>=5] are this rank's local blocks: published, zeroed and summed
-        over the ranks.  Returns (pose_grad_sum, loss_sum).  store.grad is zero afterwards."""
+        """The fused optimiser step of the ray-sharded mapping on what eslam_loss_backward_q left on this rank
+        (`store.gq_arena`, the decoder block of `store.grad`).  pose_grad [frames,12] / loss_acc float64[>=5] are this
+        rank's local blocks: published, zeroed and summed over the ranks.  Returns (pose_grad_sum, loss_sum).  The
+        gradient images and the decoder gradients are zero afterwards."""
         from ._lib import call, ptr, stream
 
         st = self.store
@@ -173,15 +189,14 @@ class PeerExchange(MappingExchange):
             raise RuntimeError("PeerExchange: more frames than the published pose block was sized for")
         par = self.peers.adam_seq & 1
         self.peers.adam_seq += 1
-        seg_end = (C.c_int64 * 3)(st.n_sdf_end, st.n_planes_end, st.n_floats)
-        seg_lr = (C.c_double * 3)(lr_planes, lr_cplanes, lr_dec)
         n_aux = n_pose_frames * 12 if pose_grad is not None else 0
         n_auxd = 5 if loss_acc is not None else 0
-        call("eslam_adam_exchange", self._next_epoch(), self._param, self._stage, ptr(st.grad),
-             self._mc if self.multimem else None, ptr(st.exp_avg), ptr(st.exp_avg_sq), st.n_floats, seg_end, seg_lr, 3,
-             step, betas[0], betas[1], eps, ptr(pose_grad) if n_aux else None, self._pose[par], ptr(self.pose_sum),
-             n_aux, ptr(loss_acc) if n_auxd else None, self._loss[par], ptr(self.loss_sum), n_auxd,
-             ptr(st.touched) if getattr(st, "touched", None) is not None else None, stream())
+        call("eslam_q_adam_exchange", self._next_epoch(), st.ref(), self._param, self._stage, ptr(st.gq_arena),
+             ptr(st.grad), self._mc if self.multimem else None, ptr(st.exp_avg), ptr(st.exp_avg_sq), ptr(st.touched_q),
+             lr_planes, lr_cplanes, lr_dec, step, betas[0], betas[1], eps, self._dec[par],
+             ptr(pose_grad) if n_aux else None, self._pose[par], ptr(self.pose_sum), n_aux,
+             ptr(loss_acc) if n_auxd else None, self._loss[par], ptr(self.loss_sum), n_auxd, stream())
+        st.gen += 1
         return self.pose_sum, self.loss_sum
 
     def check(self) -> None:

@@ -276,6 +276,8 @@ def mapping_iteration(ws: Workspace, store: FieldStore, sc: StepCfg, c2ws, poses
                  1e-8, ptr(ws.grad7), 0, stream())
         return
     store.adam_step_q(step, lr_dec, lr_planes, lr_cplanes)
+    if exchange is not None and hasattr(exchange, "after_step"):
+        exchange.after_step(store)
     if joint:
         call("eslam_pose_adam_step", ptr(poses7), ptr(ws.pose_grad), ptr(ws.pose_m), ptr(ws.pose_v), b, 1, lr_cam,
              lr_cam, step, 0.9, 0.999, 1e-8, ptr(ws.grad7), 1, stream())

@@ -128,7 +128,8 @@ def _run_window(dev, rank, kind, iters=3):
     if hasattr(ex, "check"):
         ex.check()
     info = {"multimem": bool(getattr(ex, "multimem", False))}
-    return store.arena.clone().cpu(), out.cpu(), torch.stack(losses).cpu(), store.grad.abs().max().item(), info
+    gmax = max(store.grad.abs().max().item(), store.gq_arena.abs().max().item())
+    return store.arena.clone().cpu(), out.cpu(), torch.stack(losses).cpu(), gmax, info
 
 
 def _worker_fused(rank, world, port, out):
@@ -157,13 +158,13 @@ def test_fused_peer_exchange_equals_nccl_allreduce_plus_adam(tmp_path, world):
     assert torch.isfinite(ref_arena).all() and torch.isfinite(ref_loss).all()
     # 2 ranks: a+b has one rounding, so the peer path is bit-exact up to the Adam arithmetic both share; with more
     # ranks NCCL's reduction order differs from the fixed rank order used here
-    tol = 1e-6 if world == 2 else 1e-4
+    tol = 1e-5 if world == 2 else 1e-4
     for kind in ("peer_nomc", "peer"):
         for r in res:
             arena, c2w, loss, gmax, info = r[kind]
             # replicas are identical (every parameter has one writer) ...
             assert torch.equal(arena, res[0][kind][0]), kind
-            assert gmax == 0.0, "the gradient arena must be zeroed by the exchange kernels"
+            assert gmax == 0.0, "the gradient images and the decoder gradients must be zeroed by the exchange kernels"
             # ... and equal to all-reduce + Adam
             assert rel_err(arena, ref_arena) < tol, (kind, rel_err(arena, ref_arena))
             assert rel_err(c2w, ref_c2w) < tol
@@ -231,4 +232,4 @@ def test_optimize_mapping_dropin_with_peer_exchange(tmp_path):
         for a, b in zip(r0[kind], r1[kind]):
             assert torch.equal(a, b), f"{kind}: ranks differ"
     for a, b in zip(r0["peer"], r0["nccl"]):
-        assert torch.isfinite(a).all() and rel_err(a, b) < 1e-6
+        assert torch.isfinite(a).all() and rel_err(a, b) < 1e-5
