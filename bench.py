@@ -41,6 +41,37 @@ def measured_peaks():
     return 6650.0, "fallback (B200_PROFILING.md)", {}
 
 
+def l2_ceilings():
+    """Measured L2-resident ceilings of the hot path's access shape (tools/microbench/l2_gather_red.cu, run here):
+    random 64-byte / 128-byte line gathers (LDG.128) and red.global.add.v4.f32, alone and interleaved, plus the
+    bulk-async forms (TMA gather4, bulk reduce).  None if the binary is missing and cannot be built."""
+    exe = os.path.join(ROOT, "tools", "microbench", "l2_gather_red")
+    if not os.path.exists(exe):
+        try:
+            subprocess.run(["nvcc", "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-std=c++17", "-o", exe,
+                            exe + ".cu"], check=True, capture_output=True, timeout=300)
+        except Exception:
+            return None
+    try:
+        out = subprocess.run([exe, "--json"], capture_output=True, text=True, timeout=120).stdout
+        for line in out.splitlines():
+            if line.startswith("{"):
+                return json.loads(line)
+    except Exception:
+        return None
+    return None
+
+
+def ncu_traffic(kernel_key):
+    """DRAM bytes per launch of a kernel from this round's committed `ncu --set full` capture (profiles/)."""
+    prof = os.path.join(ROOT, "profiles", "r02_ncu_summary.json")
+    try:
+        d = json.load(open(prof))
+        return d[kernel_key]["dram_bytes_per_launch"], "profiles/r02_ncu_summary.json (ncu --set full, cold cache)"
+    except Exception:
+        return None, None
+
+
 class ClockSampler:
     """nvidia-smi clocks and throttle reasons during the timed region (B200_PROFILING.md recipe)."""
 
@@ -294,9 +325,11 @@ def run_reference(args, spec):
     m = spec["mapping"]
     n_frames = m["mapping_window_size"]
     run = OracleRun(spec, n_frames)
-    for _ in range(min(max(args.warmup, 1), 2)):
-        run.run_mapping(1)
-    per_iter = [run.run_mapping(1) for _ in range(max(args.steps, 1))]
+    iters = m["iters"]
+    for _ in range(min(max(args.warmup, 1), 1)):
+        run.run_mapping(2)
+    # one step = one optimize_mapping-shaped call of 15 iterations, as on the GPU arm (fresh Adam per call)
+    per_iter = [run.run_mapping(iters) for _ in range(max(args.steps, 1))]
     s_iter = sum(per_iter) / len(per_iter)
     value = m["pixels"] / s_iter
     run.run_tracking(1)
@@ -304,12 +337,12 @@ def run_reference(args, spec):
     line = {
         "impl": "reference", "metric": "mapping rays*iters/s (Replica room0 shape)", "value": value,
         "unit": "rays*iters/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": 1e3 * s_iter, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "ms_per_step": 1e3 * s_iter * iters, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
-        "config": {**workload_config(1, m["pixels"] // n_frames, n_frames, "none (host cores)"),
-                   "step": "1 mapping iteration of the same window (bounded sample of the 15-iteration call)"},
+        "config": workload_config(1, m["pixels"] // n_frames, n_frames, "none (host cores)"),
         "cpu_baseline": {"value": value, "unit": "rays*iters/s", "cores": cores, "kind": "port",
-                         "sample": f"{len(per_iter)} x 1 mapping iteration of 4000 rays, torch CPU, {cores} threads"},
+                         "sample": f"{len(per_iter)} optimize_mapping-shaped calls of {iters} iterations x 4000 rays "
+                                   f"(oracle port of the reference's PyTorch path, torch CPU, {cores} threads)"},
         "e2e": {"value": value, "unit": "rays*iters/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "tracking": {"value": 1.0 / (trk * spec["tracking"]["iters"]), "unit": "frames/s",
                      "ms_per_iter": 1e3 * trk},
@@ -332,7 +365,7 @@ def main():
 
     spec = S.REPLICA_ROOM0
     if args.impl == "reference":
-        args.steps = min(args.steps, 10)  # bounded: ~2 s of host work per step
+        args.steps = min(args.steps, 4)  # bounded: ~10-30 s of host work per 15-iteration step
         run_reference(args, spec)
         return
 
@@ -383,7 +416,7 @@ def main():
     ex, exchange_name = None, "none (1 GPU)"
     if dist_on:
         if os.environ.get("ESLAM_B200_EXCHANGE", "peer") == "nccl":
-            ex, exchange_name = MappingExchange(), "NCCL all-reduce of the gradient arena + replicated Adam"
+            ex, exchange_name = MappingExchange(), "NCCL all-reduce of the gradient images + replicated optimiser step"
         else:
             # symmetric (peer-mapped) memory needs P2P between all GPUs of the job: agree on it, and measure the NCCL
             # path (saying so) rather than nothing if the box does not offer it
@@ -395,12 +428,15 @@ def main():
             ok = torch.tensor([0 if err else 1], device=dev)
             dist.all_reduce(ok, op=dist.ReduceOp.MIN)
             if int(ok.item()) == 1:
-                exchange_name = ("own kernels over symmetric peer memory: push reduce-scatter + Adam + all-gather + "
-                                 "zero_grad (" + ("multimem.st parameter broadcast" if ex.multimem else "P2P stores")
-                                 + "), normalisers summed over peer loads; no NCCL call per iteration")
+                exchange_name = ("own kernels over symmetric NVLink peer memory, no NCCL call per iteration: push "
+                                 "reduce-scatter of the 16-channel gradient images + plane Adam on the owned tiles + "
+                                 "all-gather of the updated texels (" +
+                                 ("multimem.st" if ex.multimem else "P2P stores") + ") + zero_grad, replicated decoder "
+                                 "step on the published decoder gradients, normalisers summed over peer loads; "
+                                 "limiter: the exchange runs after the backward with nothing overlapped")
             else:
                 ex = MappingExchange()
-                exchange_name = ("NCCL all-reduce of the gradient arena + replicated Adam (symmetric memory "
+                exchange_name = ("NCCL all-reduce of the gradient images + replicated optimiser step (symmetric memory "
                                  f"unavailable: {err})")
     lr = m["lr"]
     pix = m["pixels"] // n_frames
@@ -437,19 +473,33 @@ def main():
              ptr(ws.pose_grad), None, stream())
 
     ms_k = time_region(bwd_kernel, 50, 5, False) / 50
+    gq_img.zero_()
+    store.grad.zero_()
     hbm_peak, peak_src, _ = measured_peaks()
     achieved = R * ALGO_BYTES_PER_RAY_ITER / (ms_k * 1e-3) / 1e9
+    traffic, traffic_src = ncu_traffic("k_map_bwd_q")
+    ceil = l2_ceilings() if rank == 0 else None
+    # what the Q-form kernel itself moves through L2: 64-byte lines (16 channels) where the algorithmic figure of
+    # SURVEY 8d counts 128-byte lines, i.e. half of it (before the run-length merge of the coarse reductions)
+    q_bytes = R * ALGO_BYTES_PER_RAY_ITER / 2
     roofline = {"bound": "hbm", "kernel": "k_map_bwd_q<poses> (eslam_loss_backward_q)",
                 "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
-                "traffic": None, "peak_source": peak_src, "us_per_launch": 1e3 * ms_k, "rays_per_launch": R,
-                "note": "algorithmic bytes = rays x 40 samples x 6144 B x (gather+scatter); the 27 MB plane set is "
-                        "L2-resident, so the HBM peak is a reference denominator, not a hard ceiling"}
-    prof = os.path.join(ROOT, "profiles", "r01_ncu_summary.json")
-    if os.path.exists(prof):
-        try:
-            roofline["traffic"] = json.load(open(prof)).get("loss_backward_dram_bytes_per_launch")
-        except Exception:
-            pass
+                "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
+                "us_per_launch": 1e3 * ms_k, "rays_per_launch": R,
+                "dram_frac": (traffic / (ms_k * 1e-3) / 1e9 / hbm_peak) if traffic else None,
+                "l2": None,
+                "note": "achieved = SURVEY 8d's algorithmic bytes (rays x 40 samples x 6144 B x (gather+scatter)) / "
+                        "kernel time, as the contract defines it; it is NOT a bandwidth the kernel sustains: the 27 MB "
+                        "plane set is L2-resident (see dram_frac) and the kernel works on 16-channel images, moving half "
+                        "those bytes.  The limit that applies is the L2 gather + reduction ceiling: see l2."}
+    if ceil:
+        peak_l2 = ceil["line64"]["ldg_red"]
+        roofline["l2"] = {"kernel_bytes": q_bytes, "achieved": q_bytes / (ms_k * 1e-3) / 1e9, "peak": peak_l2,
+                          "unit": "GB/s", "frac": q_bytes / (ms_k * 1e-3) / 1e9 / peak_l2,
+                          "peak_source": "tools/microbench/l2_gather_red (run inside this bench): random 64-byte "
+                                         "lines out of a 27 MB set, LDG.128 gathers interleaved with "
+                                         "red.global.add.v4.f32, best of 2/4/8 CTAs per SM",
+                          "ceilings_GBps": ceil}
 
     # ------------------------------------------------------------------ tracking (1 GPU: too few rays to shard)
     tracking = None
@@ -546,9 +596,72 @@ def main():
                   "frame is staged from pinned host memory one step ahead on a copy stream, the returned pose is "
                   "read back every step"
                   + ("; per rank, bytes are per rank" if dist_on else "")}
+    # the same drop-in call with the reference's random-draw SHAPES (strict_rng: seed-compatible with the reference,
+    # one host sync per iteration)
+    mp.strict_rng = True
+    ms_strict = time_region(mapping_e2e, max(n_e2e // 2, 2), 1, dist_on)
+    mp.strict_rng = False
+    e2e_strict = {"value": world * rays_per_step * max(n_e2e // 2, 2) / (ms_strict * 1e-3), "unit": "rays*iters/s",
+                  "ms_per_step": ms_strict / max(n_e2e // 2, 2),
+                  "what": "e2e with ESLAM_B200_STRICT_RNG semantics: uniforms drawn as [R1,S] / [R0,32] / [R0,8] like "
+                          "Renderer.py:59 / common.py:59, so a seeded run consumes torch's generator exactly as the "
+                          "reference does (the default draws fixed [N,S] blocks and never syncs)"}
     if hasattr(ex, "check"):
         ex.check()
     clocks = sampler.stop() if sampler else None
+    # ---- config 4 of BASELINE.json: 8 x 4000 = 32 000 rays per iteration, SHARDED over the ranks (strong scaling)
+    strong = None
+    try:
+        from myslam_b200.hotpath import Workspace
+
+        pix32 = (32000 // n_frames) // world
+        ws32 = Workspace(dev, pix32 * n_frames, sc.render.n_stratified + sc.render.n_importance, max(32, n_frames))
+
+        def call32():
+            map_window(store, ws32, sc, poses, cols, deps, pix32 * n_frames, m["iters"], lr["decoders_lr"],
+                       lr["planes_lr"], lr["c_planes_lr"], True, m["joint_opt_cam_lr"], exchange=ex)
+
+        ms32 = time_region(call32, max(args.steps // 4, 2), 1, dist_on)
+        n32 = max(args.steps // 4, 2)
+        strong = {"rays_per_iter_total": pix32 * n_frames * world, "value": world * m["iters"] * pix32 * n_frames * n32
+                  / (ms32 * 1e-3), "unit": "rays*iters/s", "ms_per_call": ms32 / n32, "scaling": "strong",
+                  "n_gpus": world, "what": "SURVEY 8d config 4: the 32 000-ray batch of a 20-keyframe window split "
+                  "evenly over the ranks (every rank renders 1600 / world pixels of every frame), same exchange"}
+        del ws32
+    except Exception as exc:  # noqa: BLE001
+        strong = {"error": repr(exc)}
+    # ---- multi-GPU parity inside the driver's run (its test box has one GPU): two iterations from the same state
+    # through the peer-memory exchange and through NCCL all-reduce + replicated step
+    exchange_check = None
+    if dist_on and isinstance(ex, PeerExchange):
+        a0 = store.arena.clone()
+
+        def two_iters(exch, seed):
+            store.arena.copy_(a0)
+            store.gen += 1
+            torch.manual_seed(seed + rank)
+            map_window(store, ws, sc, poses, cols, deps, m["pixels"], 2, lr["decoders_lr"], lr["planes_lr"],
+                       lr["c_planes_lr"], True, m["joint_opt_cam_lr"], exchange=exch)
+            torch.cuda.synchronize()
+            return store.arena.clone()
+
+        peer = two_iters(ex, 4242)
+        nccl = two_iters(MappingExchange(), 4242)
+        store.arena.copy_(a0)
+        store.gen += 1
+        h = peer.view(torch.int32).to(torch.int64).sum().reshape(1)
+        hs = [torch.zeros_like(h) for _ in range(world)]
+        dist.all_gather(hs, h)
+        hn = nccl.view(torch.int32).to(torch.int64).sum().reshape(1)
+        hns = [torch.zeros_like(hn) for _ in range(world)]
+        dist.all_gather(hns, hn)
+        exchange_check = {"bit_identical_replicas": all(int(x) == int(hs[0]) for x in hs),
+                          "bit_identical_replicas_nccl_path": all(int(x) == int(hns[0]) for x in hns),
+                          "max_rel_vs_nccl": ((peer - nccl).abs().max() / nccl.abs().max()).item(),
+                          "what": "2 joint-opt mapping iterations (own rays per rank) from the same state: peer-memory "
+                                  "exchange vs NCCL all-reduce of the gradient images + replicated optimiser step; "
+                                  "replicas compared by a checksum of the parameter arena's bits over all ranks"}
+        ex.check()
     extra = {}
     if not args.profile_only:
         try:
@@ -574,13 +687,19 @@ def main():
                                   f"(oracle port of the reference's PyTorch path, torch CPU, {cores} threads)",
                         "tracking_frames_per_s": 1.0 / (s_trk * t["iters"])}
         gpu = OracleRun(spec, n_frames, device=dev)
-        gpu.run_mapping(3)
-        g_iter = gpu.run_mapping(15)
-        gpu.run_tracking(3)
-        g_trk = gpu.run_tracking(16)
+        gpu.run_mapping(5)
+        g_runs = sorted(gpu.run_mapping(30) for _ in range(3))
+        gpu.run_tracking(8)
+        t_runs = sorted(gpu.run_tracking(32) for _ in range(3))
         del gpu
+        g_iter, g_trk = g_runs[1], t_runs[1]
         torch_gpu = {"mapping_rays_iters_per_s": m["pixels"] / g_iter, "tracking_frames_per_s": 1.0 / (g_trk * t["iters"]),
-                     "what": "the reference's PyTorch path (oracle port, stock ATen kernels, eager) on the same B200"}
+                     "mapping_best_of_3": m["pixels"] / g_runs[0], "mapping_worst_of_3": m["pixels"] / g_runs[2],
+                     "tracking_best_of_3": 1.0 / (t_runs[0] * t["iters"]),
+                     "what": "the reference's PyTorch path (oracle port, stock ATen kernels, eager) on the same B200: "
+                             "median of 3 x 30 mapping iterations / 3 x 32 tracking iterations after warm-up",
+                     "vs_torch_gpu": {"mapping": value / (m["pixels"] / g_iter),
+                                      "tracking": tracking["value"] / (1.0 / (g_trk * t["iters"])) if tracking else None}}
 
     if rank == 0:
         line = {
@@ -588,8 +707,9 @@ def main():
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_map / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": workload_config(world, pix, n_frames, exchange_name),
-            "e2e": e2e, "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu_baseline,
-            "torch_gpu_baseline": torch_gpu, "tracking": tracking, "clocks": clocks, **extra,
+            "e2e": e2e, "e2e_strict": e2e_strict, "gpu_launches": launches, "roofline": roofline,
+            "cpu_baseline": cpu_baseline, "torch_gpu_baseline": torch_gpu, "tracking": tracking, "clocks": clocks,
+            "mapping_32k": strong, "exchange_check": exchange_check, **extra,
         }
         print(json.dumps(line))
     if dist_on:

@@ -1107,7 +1107,7 @@ int eslam_q_build(const eslam_field_t* f, const float* arena, float* q_arena, es
   a.arena4 = reinterpret_cast<const float4*>(arena);
   a.dec = arena + f->dec_offset;
   a.q2 = reinterpret_cast<float2*>(q_arena);
-  k_q_build<<<a.qg.unit0[4], 256, 0, S_(s)>>>(a);
+  k_q_build<<<a.qg.unit0[4], QB_TPC, 0, S_(s)>>>(a);
   CHECK_LAUNCH("eslam_q_build");
   return 0;
 }

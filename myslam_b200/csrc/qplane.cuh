@@ -66,8 +66,10 @@ constexpr int QB_TPC = 128;
 // swizzled texel tile: row t holds 8 float4; physical slot = c4 ^ (t & 7) (conflict-free for thread-per-row readers)
 __device__ __forceinline__ int t_slot(int t, int c4) { return t * 8 + (c4 ^ (t & 7)); }
 
-__global__ void __launch_bounds__(256) k_q_build(const __grid_constant__ QBuildArgs a) {
-  __shared__ __align__(16) float sW[16 * 32];
+__global__ void __launch_bounds__(QB_TPC) k_q_build(const __grid_constant__ QBuildArgs a) {
+  // rows 8..15 (the second half's outputs) start 4 floats later, so the two addresses of a warp's weight load (one per
+  // half) fall into different banks
+  __shared__ __align__(16) float sW[16 * 32 + 4];
   __shared__ float4 sT[QB_TPC * 8];
   const int g = q_group_of(a.qg, blockIdx.x);
   const int tl0 = (blockIdx.x - a.qg.unit0[g]) * QB_TPC;
@@ -75,31 +77,37 @@ __global__ void __launch_bounds__(256) k_q_build(const __grid_constant__ QBuildA
   const long long tbase = (long long)a.qg.t0[g] + tl0;
   const float4* src = a.arena4 + tbase * 8;
 #pragma unroll
-  for (int u = 0; u < QB_TPC * 8 / 256; ++u) {
-    const int i = u * 256 + threadIdx.x, t = i >> 3;
-    if (t < cnt) sT[t_slot(t, i & 7)] = ldg4(src + i);
+  for (int u = 0; u < 8; ++u) {
+    const int i = u * QB_TPC + threadIdx.x, t = i >> 3;
+    sT[t_slot(t, i & 7)] = t < cnt ? ldg4(src + i) : f4_zero();
   }
   const float* w1 = a.dec + ((g >> 1) ? C_W1 : S_W1) + (g & 1) * 32;  // columns of this scale (coarse | fine, decoders.py:84)
-  for (int i = threadIdx.x; i < 16 * 32; i += 256) sW[i] = w1[(i >> 5) * 64 + (i & 31)];
+  for (int i = threadIdx.x; i < 16 * 32; i += QB_TPC) sW[i + ((i >> 8) << 2)] = w1[(i >> 5) * 64 + (i & 31)];
   __syncthreads();
-  const int t = threadIdx.x >> 1, half = threadIdx.x & 1;
-  if (t >= cnt) return;
-  float o[8];
+  // thread (texel pair, half): 8 of the 16 outputs of texels tp and tp + 64; each weight load feeds both texels
+  const int tp = threadIdx.x >> 1, half = threadIdx.x & 1;
+  float o[2][8];
 #pragma unroll
-  for (int j = 0; j < 8; ++j) o[j] = 0.f;
-  const float* w = sW + half * 8 * 32;
+  for (int j = 0; j < 8; ++j) o[0][j] = o[1][j] = 0.f;
+  const float* w = sW + half * (8 * 32 + 4);
 #pragma unroll
   for (int c4 = 0; c4 < 8; ++c4) {
-    const float4 x = sT[t_slot(t, c4)];
+    const float4 x0 = sT[t_slot(tp, c4)], x1 = sT[t_slot(tp + 64, c4)];
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
       const float4 wj = lds4(w + j * 32 + c4 * 4);
-      o[j] = fmaf(wj.w, x.w, fmaf(wj.z, x.z, fmaf(wj.y, x.y, fmaf(wj.x, x.x, o[j]))));
+      o[0][j] = fmaf(wj.w, x0.w, fmaf(wj.z, x0.z, fmaf(wj.y, x0.y, fmaf(wj.x, x0.x, o[0][j]))));
+      o[1][j] = fmaf(wj.w, x1.w, fmaf(wj.z, x1.z, fmaf(wj.y, x1.y, fmaf(wj.x, x1.x, o[1][j]))));
     }
   }
-  float4* dst = reinterpret_cast<float4*>(a.q2) + (tbase + t) * 4 + half * 2;
-  dst[0] = make_float4(o[0], o[1], o[2], o[3]);
-  dst[1] = make_float4(o[4], o[5], o[6], o[7]);
+#pragma unroll
+  for (int k = 0; k < 2; ++k) {
+    const int t = tp + 64 * k;
+    if (t >= cnt) continue;
+    float4* dst = reinterpret_cast<float4*>(a.q2) + (tbase + t) * 4 + half * 2;
+    dst[0] = make_float4(o[k][0], o[k][1], o[k][2], o[k][3]);
+    dst[1] = make_float4(o[k][4], o[k][5], o[k][6], o[k][7]);
+  }
 }
 
 struct SmemFwdQ {

@@ -624,10 +624,11 @@ def track_frame(fld: Field, cam: Camera, rc: RenderCfg, w: LossWeights, init_pos
 
 
 def map_window(fld: Field, cam: Camera, rc: RenderCfg, w: LossWeights, c2ws, gt_colors, gt_depths, n_pixels, iters,
-               lr_dec, lr_planes, lr_cplanes, joint_opt, lr_cam, draws):
+               lr_dec, lr_planes, lr_cplanes, joint_opt, lr_cam, draws, state_out=None):
     """The per-call body of Mapper.optimize_mapping (Mapper.py:249-362) for an
     already-selected window: fresh Adam, per-group lrs, first pose fixed.
-    Updates `fld` in place; returns (updated c2ws [b,4,4], losses)."""
+    Updates `fld` in place; returns (updated c2ws [b,4,4], losses).  state_out (dict): receives the optimiser's
+    final exp_avg / exp_avg_sq of the 12 planes (leaf order of Field.leaves()) for the post-Adam parity tests."""
     b = c2ws.shape[0]
     pix = n_pixels // b
     dec_params = [fld.dec[k].requires_grad_(True) for k in DECODER_KEYS] + [fld.beta.requires_grad_(True)]
@@ -646,6 +647,10 @@ def map_window(fld: Field, cam: Camera, rc: RenderCfg, w: LossWeights, c2ws, gt_
         out.loss.backward()
         opt.step()
         losses.append(out.loss.item())
+    if state_out is not None:
+        leaves = [p for g in fld.planes for p in g]
+        state_out["exp_avg"] = [opt.state[p]["exp_avg"].clone() for p in leaves]
+        state_out["exp_avg_sq"] = [opt.state[p]["exp_avg_sq"].clone() for p in leaves]
     for t in dec_params + pl + cpl:
         t.requires_grad_(False)
     if joint_opt:

@@ -109,3 +109,45 @@ def arena_index(k):
     from myslam_b200.field import arena_slot
 
     return arena_slot(k // 2, k % 2)
+
+
+class PaddedOracleDraws:
+    """Oracle-side view of the DEFAULT (non-strict) draw convention of myslam_b200.hotpath: the uniforms are drawn
+    as fixed [N,S] / [N,n_strat] / [N,n_imp] blocks and a kept ray uses the row of its ordinal among the rays of its
+    kind, i.e. the oracle's [R1,S] / [R0,n_strat] / [R0,n_imp] requests are the first rows of the padded blocks."""
+
+    def __init__(self, idx, blocks):
+        self.idx, self.blocks, self.pos = idx, list(blocks), 0
+
+    def randint(self, high, n):
+        assert self.idx.numel() == n
+        return self.idx
+
+    def rand(self, rows, cols):
+        t = self.blocks[self.pos]
+        self.pos += 1
+        assert t.shape[1] == cols and rows <= t.shape[0], (tuple(t.shape), rows, cols)
+        return t[:rows]
+
+
+class PaddedDeviceDraws:
+    """The same padded blocks handed to the CUDA path (TorchDraws' interface incl. rand_many)."""
+
+    def __init__(self, idx, blocks, device):
+        self.idx = idx.to(device).contiguous()
+        self.blocks = [b.to(device).float().contiguous() for b in blocks]
+        self.pos = 0
+
+    def randint(self, high, n):
+        assert self.idx.numel() == n
+        self.pos = 0
+        return self.idx
+
+    def rand(self, rows, cols):
+        t = self.blocks[self.pos]
+        self.pos += 1
+        assert tuple(t.shape) == (rows, cols), (tuple(t.shape), rows, cols)
+        return t
+
+    def rand_many(self, shapes):
+        return [self.rand(r, c) for r, c in shapes]

@@ -324,16 +324,39 @@ def test_optimize_mapping_call_golden():
                                   c2ws0[3].clone())
     after = torch.stack([c2ws0[0], kf[1]["est_c2w"], kf[2]["est_c2w"], new_cur], 0)
     assert rel_err(after, d["c2ws_after"]) < 1e-5
+    # the optimiser's moments come from the oracle (pinned to the reference at 0.0) run on the same recorded draws
+    from myslam_b200.decoders import synced_store
+    from myslam_b200.field import arena_slot
+
+    f_o, state = fld.clone(), {}
+    lr = mp.cfg["mapping"]["lr"]
+    O.map_window(f_o, O.Camera(*GOLDEN_CAM), O.RenderCfg(32, 8, TRUNC), O.MAP_W, torch.from_numpy(d["c2ws0"]),
+                 torch.from_numpy(d["gt_colors"]), torch.from_numpy(d["gt_depths"]), 400, int(d["iters"]),
+                 lr["decoders_lr"], lr["planes_lr"], lr["c_planes_lr"], True, 1e-3, O.ReplayDraws(recorded_draws(d)),
+                 state_out=state)
     names = ("xy", "xz", "yz", "c_xy", "c_xz", "c_yz")
     groups = (mp.planes_xy, mp.planes_xz, mp.planes_yz, mp.c_planes_xy, mp.c_planes_xz, mp.c_planes_yz)
-    for n, g in zip(names, groups):
+    store = synced_store(groups, mp.decoders, mp.bound)
+    for gi, (n, g) in enumerate(zip(names, groups)):
         for s in range(2):
-            # Adam's first steps move every touched texel by ~lr: compare the UPDATE, not only the value
-            before = fld.planes[names.index(n)][s]
-            upd_ref = torch.from_numpy(d[f"after.plane.{n}.{s}"]) - before
+            ref_after = torch.from_numpy(d[f"after.plane.{n}.{s}"])
+            assert rel_err(f_o.planes[gi][s], ref_after) < 1e-6, "the oracle run must reproduce the reference's planes"
+            assert rel_err(g[s], ref_after) < 1e-3
+            # Adam's state: first and second moments in the arena against torch.optim.Adam's (1e-3)
+            slot = arena_slot(gi, s)
+            m_ref, v_ref = state["exp_avg"][gi * 2 + s], state["exp_avg_sq"][gi * 2 + s]
+            assert rel_err(store.export_plane(slot, store.exp_avg), m_ref) < 1e-3, f"plane {n}[{s}] exp_avg"
+            assert rel_err(store.export_plane(slot, store.exp_avg_sq), v_ref) < 1e-3, f"plane {n}[{s}] exp_avg_sq"
+            # Adam's first steps move every touched texel by ~lr whatever the size of its gradient: compare the UPDATE
+            # where the gradient is above a floor (below it the direction m / sqrt(v) amplifies rounding noise)
+            before = fld.planes[gi][s]
+            upd_ref = ref_after - before
             upd = g[s].detach().cpu() - before
-            assert rel_err(upd, upd_ref) < 2e-2, f"plane {n}[{s}] update"
-            assert rel_err(g[s], d[f"after.plane.{n}.{s}"]) < 1e-3
+            big = m_ref.abs() > 1e-2 * m_ref.abs().max()
+            assert big.any()
+            err = ((upd - upd_ref).abs()[big].max() / upd_ref.abs().max()).item()
+            assert err < 1e-3, f"plane {n}[{s}] update: {err}"
+            assert rel_err(upd, upd_ref) < 2e-2, f"plane {n}[{s}] update (all texels)"
     sd = mp.decoders.state_dict()
     for name in O.DECODER_KEYS:
         assert rel_err(sd[name], d[f"after.dec.{name}"]) < 1e-3, name

@@ -72,5 +72,34 @@ def full(path):
                     print(f"    {h.split('issue_stalled_')[1].split('_per')[0]:24s} {v:.2f}")
 
 
+def to_json(path):
+    """Per kernel (first launch of each name): duration and DRAM bytes per launch, as JSON (bench.py reads
+    profiles/r02_ncu_summary.json for roofline.traffic)."""
+    import json
+
+    out = subprocess.run(["ncu", "-i", path, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    rows = list(csv.reader(io.StringIO(out)))
+    hdr, units = rows[0], rows[1]
+
+    def val(r, k):
+        i = hdr.index(k)
+        v = float(r[i].replace(",", ""))
+        u = units[i]
+        return v * {"Mbyte": 1e6, "Kbyte": 1e3, "Gbyte": 1e9, "byte": 1.0}.get(u, 1.0)
+
+    res = {"source": path, "how": "ncu --set full --clock-control none (cold cache, serialised)"}
+    for r in rows[2:]:
+        name = re.sub(r"<.*|\(.*", "", r[hdr.index("Kernel Name")]).replace("void ", "").replace("eslam::", "")
+        if name in res:
+            continue
+        res[name] = {"dram_bytes_per_launch": val(r, "dram__bytes_read.sum") + val(r, "dram__bytes_write.sum"),
+                     "duration_us": float(r[hdr.index("gpu__time_duration.sum")].replace(",", "")),
+                     "l2_read_sectors": float(r[hdr.index("lts__t_sectors_srcunit_tex_op_read.sum")].replace(",", "")),
+                     "l2_red_sectors": float(r[hdr.index("lts__t_sectors_srcunit_tex_op_red.sum")].replace(",", "")),
+                     "warps_active_pct": float(r[hdr.index("sm__warps_active.avg.pct_of_peak_sustained_active")]),
+                     "issue_active_pct": float(r[hdr.index("smsp__issue_active.avg.pct_of_peak_sustained_active")])}
+    print(json.dumps(res, indent=1))
+
+
 if __name__ == "__main__":
-    {"launches": launches, "full": full}[sys.argv[1]](sys.argv[2])
+    {"launches": launches, "full": full, "json": to_json}[sys.argv[1]](sys.argv[2])
