@@ -38,7 +38,8 @@ struct SmemBwdQ {
   int raym[16];        // per ray loss-mask flag
   double rayc[3][16];  // per ray gt colour
   int norm[8];         // loss normalisers (counters layout)
-  float rayod[6][16];  // per ray d loss / d (o, d)
+  float raydir[2][16]; // per ray camera-frame direction (x, y) of its pixel; z is -1
+  int rayframe[16];    // per ray frame of the window
   float red[NT_BWD / 32];
   double redd[(NT_BWD / 32) * 5];
 };
@@ -267,28 +268,32 @@ __device__ __forceinline__ void render_bwd_q_body(const BwdArgs& a) {
   }
   load_tail_weights(sm.W, reinterpret_cast<const float*>(a.arena4) + a.fk.dec_off, tid, NT_BWD);
   // per-ray inputs of the loss (owner: sample 0 of the ray, sdf half) and the normalisers travel global -> shared
-  // asynchronously in the weights' copy group; the outlier mask (a byte) goes through a register
+  // asynchronously in the weights' copy group; the outlier mask (a byte) goes through a register of the warp that
+  // will composite the ray (warp w: rays w, w + 8)
   const bool ray_owner = half == 0 && valid && k == 0;
-  int pre_m = 1;
+  int pre_m[2] = {1, 1};
   if (ray_owner) {
     cp_async_small<4>(&sm.rayd[rl], a.gt_depth + ray);
 #pragma unroll
     for (int c = 0; c < 3; ++c) cp_async_small<8>(&sm.rayc[c][rl], a.gt_color + (long long)ray * 3 + c);
-    if (a.ray_mask) pre_m = (int)a.ray_mask[ray];
+  }
+  if (a.ray_mask) {
+#pragma unroll
+    for (int i = 0; i < 2; ++i)
+      if (warp + 8 * i < rays_here) pre_m[i] = (int)a.ray_mask[ray0 + warp + 8 * i];
   }
   if (tid < 2) cp_async16(&sm.norm[4 * tid], a.norm + 4 * tid);
   asm volatile("cp.async.commit_group;" ::: "memory");
+  // source pixel of the ray (pose gradient): two dependent loads, parked in shared memory once the gather is out
   int pose_frame = 0;
-  float pose_dir = 0.f;
-  if (GR && a.pose_grad && tid < rays_here * 12) {
-    const int r2 = tid / 12, el = tid - r2 * 12, col = el & 3;
-    const int slot = a.src[ray0 + r2];
+  float pose_dx = 0.f, pose_dy = 0.f;
+  if (GR && a.pose_grad && tid < rays_here) {
+    const int slot = a.src[ray0 + tid];
     pose_frame = slot / a.n_per_img;
-    if (col < 3) {
-      const long long pix = a.pix_idx[slot];
-      const float pi = (float)(a.W0 + (int)(pix % a.Wc)), pj = (float)(a.H0 + (int)(pix / a.Wc));
-      pose_dir = col == 0 ? __fdiv_rn(__fsub_rn(pi, a.cx), a.fx) : (col == 1 ? -__fdiv_rn(__fsub_rn(pj, a.cy), a.fy) : -1.0f);
-    }
+    const long long pix = a.pix_idx[slot];
+    const float pi = (float)(a.W0 + (int)(pix % a.Wc)), pj = (float)(a.H0 + (int)(pix / a.Wc));
+    pose_dx = __fdiv_rn(__fsub_rn(pi, a.cx), a.fx);
+    pose_dy = -__fdiv_rn(__fsub_rn(pj, a.cy), a.fy);
   }
   if (!CACHED || GR) write_axis_setups<2>(a.fk, 2 * half, pn, sm.ax_i + 6 * half, sm.ax_f + 6 * half, q);
   __syncthreads();
@@ -347,96 +352,141 @@ __device__ __forceinline__ void render_bwd_q_body(const BwdArgs& a) {
     sdf_to_alpha(sdf, beta, u, e, alpha);
     one = __fadd_rn(__fsub_rn(1.0f, alpha), 1e-10f);
     sm.one[q] = one;
+    sm.w[q] = valid ? alpha : 0.f;  // replaced by the compositing weight below
     sm.z[q] = zk;
   } else {
 #pragma unroll
     for (int c = 0; c < 3; ++c) sm.c[c][q] = rgb[c];
   }
+  if (GR && a.pose_grad && tid < rays_here) {
+    sm.rayframe[tid] = pose_frame;
+    sm.raydir[0][tid] = pose_dx;
+    sm.raydir[1][tid] = pose_dy;
+  }
   PHASE_MARK(3);
   __syncthreads();
   PHASE_MARK(4);
-  // ---- P4: compositing (sdf half)
-  float T = 1.0f, w = 0.f;
-  if (half == 0) {
-    for (int j = 0; j < k; ++j) T *= sm.one[rl * S + j];
-    w = valid ? alpha * T : 0.f;
-    sm.w[q] = w;
-  }
-  __syncthreads();
-  if (half == 0 && valid && k < 4) {
-    const float* v = (k == 0) ? sm.z : sm.c[k - 1];
-    float acc = 0.f;
-    for (int j = 0; j < S; ++j) acc = fmaf(sm.w[rl * S + j], v[rl * S + j], acc);
-    sm.rayv[k][rl] = acc;
-  }
-  __syncthreads();
-  // ---- P5: upstream gradients of depth / rgb per ray, and the loss sums
+  // ---- P4/P5: one WARP per ray (lane l: samples l and l + 32): transmittance as a prefix product, the ray's depth and
+  //      colour, the loss gradients at them, and the backward of the compositing as a suffix sum -- shuffles only
+  //      (Renderer.py:140-147; Tracker.py:192-204 / Mapper.py:337-346).  Leaves w and d loss / d alpha per sample.
   double ls[5] = {0.0, 0.0, 0.0, 0.0, 0.0};  // fs, center, tail, depth, colour
   const int n_all = sm.norm[0], n_mask = sm.norm[2];
   const float inv_f = a.w_fs / (float)sm.norm[3], inv_c = a.w_center / (float)sm.norm[4],
               inv_t = a.w_tail / (float)sm.norm[5];
-  if (ray_owner) {
-    const float d = sm.rayd[rl];
-    const int m = a.ray_mask ? pre_m : (d > 0.f ? 1 : 0);
-    const float dr = sm.rayv[0][rl];
-    float gd = 0.f;
-    if (m) {
-      const float diff = d - dr;
-      gd = -2.0f * diff * (a.w_depth / (float)n_mask);
-      ls[3] = (double)(diff * diff);
+#pragma unroll
+  for (int i = 0; i < 2; ++i) {
+    const int r2 = warp + 8 * i;
+    if (r2 >= rays_here) break;
+    const int j0 = r2 * S + lane, j1 = j0 + 32;
+    const bool v0 = lane < S, v1 = lane + 32 < S;
+    const float o0 = v0 ? sm.one[j0] : 1.f, o1 = v1 ? sm.one[j1] : 1.f;
+    float inc0 = o0, inc1 = o1;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      const float t0 = __shfl_up_sync(0xffffffffu, inc0, d), t1 = __shfl_up_sync(0xffffffffu, inc1, d);
+      if (lane >= d) {
+        inc0 *= t0;
+        inc1 *= t1;
+      }
     }
-    sm.rayg[0][rl] = gd;
-    const bool col = a.ray_mask ? (m != 0) : true;
-    const double ncol = 3.0 * (double)(a.ray_mask ? n_mask : n_all);
+    const float tot0 = __shfl_sync(0xffffffffu, inc0, 31);
+    float T0 = __shfl_up_sync(0xffffffffu, inc0, 1), T1 = __shfl_up_sync(0xffffffffu, inc1, 1);
+    if (lane == 0) T0 = T1 = 1.f;
+    T1 *= tot0;
+    const float w0 = v0 ? sm.w[j0] * T0 : 0.f, w1 = v1 ? sm.w[j1] * T1 : 0.f;
+    const float z0 = v0 ? sm.z[j0] : 0.f, z1 = v1 ? sm.z[j1] : 0.f;
+    float c0[3], c1[3], rv[4];
 #pragma unroll
     for (int c = 0; c < 3; ++c) {
-      float g = 0.f;
-      if (col) {
-        const double diff = sm.rayc[c][rl] - (double)sm.rayv[1 + c][rl];
-        g = (float)(-2.0 * diff * (a.w_color / ncol));
-        ls[4] += diff * diff;
-      }
-      sm.rayg[1 + c][rl] = g;
+      c0[c] = v0 ? sm.c[c][j0] : 0.f;
+      c1[c] = v1 ? sm.c[c][j1] : 0.f;
     }
-    sm.raym[rl] = m;
+    rv[0] = warp_sum(fmaf(w0, z0, w1 * z1));
+#pragma unroll
+    for (int c = 0; c < 3; ++c) rv[1 + c] = warp_sum(fmaf(w0, c0[c], w1 * c1[c]));
+    // loss gradients at the rendered depth / colour (lane 0 does the float64 colour term and owns the loss sums)
+    const float d = sm.rayd[r2];
+    const int m = a.ray_mask ? pre_m[i] : (d > 0.f ? 1 : 0);
+    float rg[4] = {0.f, 0.f, 0.f, 0.f};
+    if (lane == 0) {
+      if (m) {
+        const float diff = d - rv[0];
+        rg[0] = -2.0f * diff * (a.w_depth / (float)n_mask);
+        ls[3] += (double)(diff * diff);
+      }
+      const bool col = a.ray_mask ? (m != 0) : true;
+      const double ncol = 3.0 * (double)(a.ray_mask ? n_mask : n_all);
+      if (col) {
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+          const double diff = sm.rayc[c][r2] - (double)rv[1 + c];
+          rg[1 + c] = (float)(-2.0 * diff * (a.w_color / ncol));
+          ls[4] += diff * diff;
+        }
+      }
+      sm.raym[r2] = m;
+#pragma unroll
+      for (int c = 0; c < 4; ++c) sm.rayg[c][r2] = rg[c];
+    }
+#pragma unroll
+    for (int c = 0; c < 4; ++c) rg[c] = __shfl_sync(0xffffffffu, rg[c], 0);
+    // backward of the compositing: gw = d loss / d w, B = sum over later samples of gw * w
+    const float gw0 = rg[0] * z0 + rg[1] * c0[0] + rg[2] * c0[1] + rg[3] * c0[2];
+    const float gw1 = rg[0] * z1 + rg[1] * c1[0] + rg[2] * c1[1] + rg[3] * c1[2];
+    float s0 = gw0 * w0, s1 = gw1 * w1;
+#pragma unroll
+    for (int dd = 1; dd < 32; dd <<= 1) {
+      const float t0 = __shfl_down_sync(0xffffffffu, s0, dd), t1 = __shfl_down_sync(0xffffffffu, s1, dd);
+      if (lane + dd < 32) {
+        s0 += t0;
+        s1 += t1;
+      }
+    }
+    const float tot1 = __shfl_sync(0xffffffffu, s1, 0);
+    float B0 = __shfl_down_sync(0xffffffffu, s0, 1), B1 = __shfl_down_sync(0xffffffffu, s1, 1);
+    if (lane == 31) B0 = B1 = 0.f;
+    B0 += tot1;
+    if (v0) {
+      sm.w[j0] = w0;
+      sm.gww[j0] = gw0 * T0 - B0 / o0;
+    }
+    if (v1) {
+      sm.w[j1] = w1;
+      sm.gww[j1] = gw1 * T1 - B1 / o1;
+    }
   }
   __syncthreads();
-  // ---- compositing backward -> gradient at this half's decoder outputs
+  // ---- gradient at this half's decoder outputs
   float g_beta = 0.f, gout[3] = {0.f, 0.f, 0.f};
-  {
-    float gw = 0.f;
-    if (half == 0) {
-      gw = sm.rayg[0][rl] * zk + sm.rayg[1][rl] * sm.c[0][q] + sm.rayg[2][rl] * sm.c[1][q] + sm.rayg[3][rl] * sm.c[2][q];
-      sm.gww[q] = valid ? gw * w : 0.f;
-    } else if (valid) {
+  if (half == 1) {
+    if (valid) {
       const float ww = sm.w[q];
 #pragma unroll
       for (int c = 0; c < 3; ++c) gout[c] = sm.rayg[1 + c][rl] * ww * rgb[c] * (1.0f - rgb[c]);
     }
-    __syncthreads();
-    if (half == 0 && valid) {
-      float gdir = 0.f;
-      if (sm.raym[rl]) {
-        const float d = sm.rayd[rl];
-        const int band = sdf_band(zk, d, a.tr, a.tr04);
-        if (band == 0) {
-          const float r = sdf - 1.0f;
-          gdir = 2.0f * r * inv_f;
-          ls[0] = (double)(r * r);
-        } else if (band < 3) {
-          const float r = __fadd_rn(zk, __fmul_rn(sdf, a.tr)) - d;
-          gdir = 2.0f * r * a.tr * (band == 1 ? inv_c : inv_t);
-          ls[band] = (double)(r * r);
-        }
+  } else if (valid) {
+    float gdir = 0.f;
+    if (sm.raym[rl]) {
+      const float d = sm.rayd[rl];
+      const int band = sdf_band(zk, d, a.tr, a.tr04);
+      if (band == 0) {
+        const float r = sdf - 1.0f;
+        gdir = 2.0f * r * inv_f;
+        ls[0] = (double)(r * r);
+      } else if (band < 3) {
+        const float r = __fadd_rn(zk, __fmul_rn(sdf, a.tr)) - d;
+        gdir = 2.0f * r * a.tr * (band == 1 ? inv_c : inv_t);
+        if (band == 1)
+          ls[1] = (double)(r * r);
+        else
+          ls[2] = (double)(r * r);
       }
-      float B = 0.f;
-      for (int j = k + 1; j < S; ++j) B += sm.gww[rl * S + j];
-      const float g_alpha = gw * T - B / one;
-      const float du = u * (1.0f - u);
-      const float g_sdf = gdir + g_alpha * (-beta * beta * e * du);
-      g_beta = g_alpha * e * (u - beta * sdf * du);
-      gout[0] = g_sdf * (1.0f - sdf * sdf);
     }
+    const float g_alpha = sm.gww[q];
+    const float du = u * (1.0f - u);
+    const float g_sdf = gdir + g_alpha * (-beta * beta * e * du);
+    g_beta = g_alpha * e * (u - beta * sdf * du);
+    gout[0] = g_sdf * (1.0f - sdf * sdf);
   }
   PHASE_MARK(5);
   // ---- P6: backward through layers 3 and 2 -> gradient at the pre-activations
@@ -490,27 +540,25 @@ __device__ __forceinline__ void render_bwd_q_body(const BwdArgs& a) {
     }
   }
   PHASE_MARK(9);
-  // ---- P8: ray / pose gradients
-  if (GR) {
+  // ---- P8: ray / pose gradients: one warp per (ray, component): d loss / d o = sum_k g_k, d loss / d d = sum_k z_k g_k
+  //      (g = coordinate gradient back in world units), then d loss / d t and d loss / d R = (d loss / d d) (x) dir_cam
+  if (GR && a.pose_grad) {
     __syncthreads();
-    for (int t = tid; t < rays_here * 6; t += NT_BWD) {
-      const int r2 = t / 6, comp = t - r2 * 6, ax = comp % 3;
+    for (int p = warp; p < rays_here * 6; p += NT_BWD / 32) {
+      const int r2 = p / 6, comp = p - r2 * 6, ax = comp % 3;
       const bool is_d = comp >= 3;
-      const float scale = 2.0f / (a.fk.hi[ax] - a.fk.lo[ax]);
       float acc = 0.f;
-      for (int j = 0; j < S; ++j) {
-        const float g = (sm.gp[0][ax][r2 * S + j] + sm.gp[1][ax][r2 * S + j]) * scale;
+      for (int j = lane; j < S; j += 32) {
+        const float g = sm.gp[0][ax][r2 * S + j] + sm.gp[1][ax][r2 * S + j];
         acc += is_d ? g * sm.z[r2 * S + j] : g;
       }
-      sm.rayod[comp][r2] = acc;
-    }
-    if (a.pose_grad) {
-      __syncthreads();
-      if (tid < rays_here * 12) {
-        const int r2 = tid / 12, el = tid - r2 * 12, row = el >> 2, col = el & 3;
-        const float val = col == 3 ? sm.rayod[row][r2]               // d loss / d t
-                                   : sm.rayod[3 + row][r2] * pose_dir;  // d loss / d R[row][col]
-        atomicAdd(a.pose_grad + pose_frame * 12 + el, val);
+      acc = warp_sum(acc) * (2.0f / (a.fk.hi[ax] - a.fk.lo[ax]));
+      float* dst = a.pose_grad + sm.rayframe[r2] * 12 + ax * 4;
+      if (!is_d) {
+        if (lane == 0) atomicAdd(dst + 3, acc);  // d loss / d t[ax]
+      } else if (lane < 3) {
+        const float dir = lane == 2 ? -1.0f : sm.raydir[lane][r2];
+        atomicAdd(dst + lane, acc * dir);  // d loss / d R[ax][lane]
       }
     }
   }
@@ -525,7 +573,7 @@ __device__ __forceinline__ void render_bwd_q_body(const BwdArgs& a) {
     __syncthreads();
     if (tid < 5) {
       double v = 0.0;
-      for (int i = 0; i < NP / 32; ++i) v += sm.redd[i * 5 + tid];  // only the sdf half accumulates losses
+      for (int i = 0; i < NT_BWD / 32; ++i) v += sm.redd[i * 5 + tid];
       atomicAdd(a.loss_acc + tid, v);
     }
   }

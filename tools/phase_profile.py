@@ -20,8 +20,8 @@ from myslam_b200._lib import load  # noqa: E402
 from myslam_b200.decoders import synced_store  # noqa: E402
 from myslam_b200.mapper import _mapper_state, map_window  # noqa: E402
 
-NAMES = ["P0 points+axes+weights", "P2 gather", "  barrier", "P3 MLP forward", "  barrier", "P4/P5 composite+loss+grad",
-         "P6 MLP backward (hidden)", "P6 weight gradients", "P6 backward (input) + barrier", "P7 scatter + regather",
+NAMES = ["P0 points+axes+weights", "P2 gather (+J)", "  barrier", "P3 MLP layers 2-3", "  barrier", "P4/P5 composite+loss+grad",
+         "P6 MLP backward (hidden)", "P6 J^T g + weight gradients", "P6 beta", "P7 reductions",
          "P8 ray/pose gradients"]
 
 
