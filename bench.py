@@ -307,6 +307,16 @@ def extras(scene, rnd, spec, dev, rank, world, dist_on, poses, deps, hbm_peak):
     return out
 
 
+def replicas_identical(t, world):
+    """True iff the bits of tensor `t` are the same on every rank (checksum of the int32 view, all-gathered)."""
+    import torch.distributed as dist
+
+    h = t.view(torch.int32).to(torch.int64).sum().reshape(1)
+    hs = [torch.zeros_like(h) for _ in range(world)]
+    dist.all_gather(hs, h)
+    return all(int(x) == int(hs[0]) for x in hs)
+
+
 def workload_config(world, pix, n_frames, exchange_name):
     return {"workload": "replica-room0-shaped 1200x680, 20-keyframe window, 4000 rays/iter per GPU, "
                         "15 iterations per optimize_mapping call, ESLAM.yaml defaults, joint pose optimisation",
@@ -447,8 +457,13 @@ def main():
                    lr["c_planes_lr"], True, m["joint_opt_cam_lr"], exchange=ex)
 
     sampler = ClockSampler(local).start() if rank == 0 else None
+    stages = {}
+    if dist_on:
+        stages["start"] = replicas_identical(store.arena, world)
     l0 = _lib.LAUNCHES
     ms_map = time_region(mapping_call, args.steps, args.warmup, dist_on)
+    if dist_on:
+        stages["after_timed_mapping_calls"] = replicas_identical(store.arena, world)
     launches = (_lib.LAUNCHES - l0) * args.steps // (args.steps + args.warmup)
     rays_per_step = m["iters"] * pix * n_frames
     value = world * rays_per_step * args.steps / (ms_map * 1e-3)
@@ -502,6 +517,11 @@ def main():
                           "ceilings_GBps": ceil}
 
     # ------------------------------------------------------------------ tracking (1 GPU: too few rays to shard)
+    # the tracker shares this process's FieldStore and re-imports the reference-layout planes when it first runs
+    # (Tracker.py:222-232 semantics): publish the arena to them first, as optimize_mapping does at the end of a call,
+    # so rank 0's parameters stay what the other ranks hold
+    store.push_planes(scene.all_planes)
+    store.push_decoders(scene.decoders)
     tracking = None
     e2e = None
     if rank == 0:
@@ -588,6 +608,8 @@ def main():
 
     n_e2e = max(args.steps // 2, 2)
     ms_e2e = time_region(mapping_e2e, n_e2e, 2, dist_on)
+    if dist_on:
+        stages["after_e2e_dropin_calls"] = replicas_identical(store.arena, world)
     e2e = {"value": world * rays_per_step * n_e2e / (ms_e2e * 1e-3), "unit": "rays*iters/s",
            "h2d_bytes_per_step": h_col.numel() * 8 + h_dep.numel() * 4 + 64, "d2h_bytes_per_step": 64,
            "ms_per_step": ms_e2e / n_e2e,
@@ -649,14 +671,9 @@ def main():
         nccl = two_iters(MappingExchange(), 4242)
         store.arena.copy_(a0)
         store.gen += 1
-        h = peer.view(torch.int32).to(torch.int64).sum().reshape(1)
-        hs = [torch.zeros_like(h) for _ in range(world)]
-        dist.all_gather(hs, h)
-        hn = nccl.view(torch.int32).to(torch.int64).sum().reshape(1)
-        hns = [torch.zeros_like(hn) for _ in range(world)]
-        dist.all_gather(hns, hn)
-        exchange_check = {"bit_identical_replicas": all(int(x) == int(hs[0]) for x in hs),
-                          "bit_identical_replicas_nccl_path": all(int(x) == int(hns[0]) for x in hns),
+        exchange_check = {"bit_identical_replicas": replicas_identical(peer, world),
+                          "bit_identical_replicas_nccl_path": replicas_identical(nccl, world),
+                          "replicas_identical_at": {**stages, "check_start": replicas_identical(a0, world)},
                           "max_rel_vs_nccl": ((peer - nccl).abs().max() / nccl.abs().max()).item(),
                           "what": "2 joint-opt mapping iterations (own rays per rank) from the same state: peer-memory "
                                   "exchange vs NCCL all-reduce of the gradient images + replicated optimiser step; "

@@ -257,12 +257,14 @@ int eslam_depth_samples(const eslam_render_cfg_t* cfg_host, const float* gt_dept
 
 /* The depth-less half of render_batch_ray's sampling (Renderer.py:108-134, common.py:41-77):
  * coarse SDF pass + inverse-cdf resampling for the rays in dl_list; fills their rows of z.
+ * The SDF pass reads the Q images of the current parameters (q_arena, eslam_q_build) and the decoders from `arena`
+ * (not from the constant bank: no eslam_bind_decoders needed).
  * u_coarse[>=R0][n_stratified], u_fine[>=R0][n_importance] indexed by depth-less ordinal.
  * max_rays bounds the launch (R0 is read on the device from counters[1]). */
-int eslam_importance_samples(const eslam_field_t* field_host, const float* arena, const eslam_render_cfg_t* cfg_host,
-                             const float* rays_o, const float* rays_d, const int32_t* dl_list,
-                             const int32_t* counters, int max_rays, const float* u_coarse, const float* u_fine,
-                             const float* t_uni, float* z, eslam_stream_t s);
+int eslam_importance_samples(const eslam_field_t* field_host, const float* arena, const float* q_arena,
+                             const eslam_render_cfg_t* cfg_host, const float* rays_o, const float* rays_d,
+                             const int32_t* dl_list, const int32_t* counters, int max_rays, const float* u_coarse,
+                             const float* u_fine, const float* t_uni, float* z, eslam_stream_t s);
 
 /* ---- render --------------------------------------------------------------------------------- */
 /* The second half of Renderer.render_batch_ray (Renderer.py:136-147): points -> decoders -> sdf2alpha ->

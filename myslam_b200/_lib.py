@@ -85,7 +85,7 @@ PROTOTYPES = {
     "eslam_sample_rays_frames": [_FP, _CP, _RP, _P, _I, _I, _P, _P, _I, _P, _P, _P, _P, _P, _I, _P, _P, _P, _P, _P, _P,
                                  _P, _P, _P, _P, _P, _P],
     "eslam_depth_samples": [_RP, _P, _I, _P, _P, _P, _P, _P, _P, _P, _P],
-    "eslam_importance_samples": [_FP, _P, _RP, _P, _P, _P, _P, _I, _P, _P, _P, _P, _P],
+    "eslam_importance_samples": [_FP, _P, _P, _RP, _P, _P, _P, _P, _I, _P, _P, _P, _P, _P],
     "eslam_render_forward": [_FP, _P, _P, _P, _P, _I, _I, _P, _P, _P, _P, _P],
     "eslam_render_forward_act": [_FP, _P, _P, _P, _P, _I, _I, _P, _P, _P, _P, _P, _P, _P],
     "eslam_render_backward": [_FP, _P, _P, _P, _P, _I, _I, _P, _P, _P, _P, _P, _P, _P],
@@ -156,11 +156,14 @@ def stream():
 
 LAUNCHES = 0  # kernels launched through the ABI (bench.py reports it as gpu_launches)
 _NO_KERNEL = ("eslam_bind_decoders",)
+BOUND_DECODERS = {}  # device index -> (id(FieldStore), generation) whose decoders the constant bank holds (field.py)
 
 
 def call(name, *args):
     global LAUNCHES
     lib = load()
+    if name == "eslam_bind_decoders":
+        BOUND_DECODERS.clear()  # whoever binds records what it bound afterwards (FieldStore.bind)
     rc = getattr(lib, name)(*args)
     if name not in _NO_KERNEL:
         LAUNCHES += 1

@@ -474,11 +474,11 @@ int eslam_depth_samples(const eslam_render_cfg_t* cfg, const float* gt_depth, in
   return 0;
 }
 
-int eslam_importance_samples(const eslam_field_t* f, const float* arena, const eslam_render_cfg_t* cfg,
-                             const float* rays_o, const float* rays_d, const int32_t* dl_list,
-                             const int32_t* counters, int max_rays, const float* u_coarse, const float* u_fine,
-                             const float* t_uni, float* z, eslam_stream_t s) {
-  REQUIRE(f && arena && cfg && rays_o && rays_d && dl_list && counters && u_coarse && u_fine && t_uni && z &&
+int eslam_importance_samples(const eslam_field_t* f, const float* arena, const float* q_arena,
+                             const eslam_render_cfg_t* cfg, const float* rays_o, const float* rays_d,
+                             const int32_t* dl_list, const int32_t* counters, int max_rays, const float* u_coarse,
+                             const float* u_fine, const float* t_uni, float* z, eslam_stream_t s) {
+  REQUIRE(f && arena && q_arena && cfg && rays_o && rays_d && dl_list && counters && u_coarse && u_fine && t_uni && z &&
               max_rays >= 0,
           "eslam_importance_samples");
   if (max_rays == 0) return 0;
@@ -488,6 +488,7 @@ int eslam_importance_samples(const eslam_field_t* f, const float* arena, const e
   rc = make_field_k(f, &a.fk);
   if (rc) return fail(rc, "eslam_importance_samples(field)");
   a.arena4 = reinterpret_cast<const float4*>(arena);
+  a.q4 = reinterpret_cast<const float4*>(q_arena);
   a.n_strat = cfg->n_stratified;
   a.n_imp = cfg->n_importance;
   a.rays_o = rays_o;
@@ -995,7 +996,7 @@ int eslam_q_adam_exchange(const eslam_peers_t* peers, const eslam_field_t* f, fl
   const double seg_lr[1] = {lr_dec};
   if (fill_adam(d.adam, 4, seg_end, seg_lr, 1, step, beta1, beta2, eps))
     return fail(ESLAM_EINVAL, "eslam_q_adam_exchange(decoder adam)");
-  k_dec_adam_peers<<<1, 256, 0, S_(s)>>>(d);
+  k_dec_adam_peers<<<(DEC_N + 255) / 256, 256, 0, S_(s)>>>(d);
   CHECK_LAUNCH("eslam_q_adam_exchange(decoders)");
   return 0;
 }

@@ -104,12 +104,14 @@ __global__ void __launch_bounds__(32) k_exchange_counters(const __grid_constant_
   if ((int)threadIdx.x < a.n) a.pub[a.ps.rank][threadIdx.x] = a.local[threadIdx.x];
   peer_barrier(a.ps, 0);
   if ((int)threadIdx.x < a.n) {
+    int v[MAX_PEERS];
+#pragma unroll
+    for (int p = 0; p < MAX_PEERS; ++p)
+      if (p < a.ps.world) asm volatile("ld.relaxed.sys.global.s32 %0, [%1];" : "=r"(v[p]) : "l"(a.pub[p] + threadIdx.x) : "memory");
     int acc = 0;
-    for (int p = 0; p < a.ps.world; ++p) {
-      int v;
-      asm volatile("ld.relaxed.sys.global.s32 %0, [%1];" : "=r"(v) : "l"(a.pub[p] + threadIdx.x) : "memory");
-      acc += v;
-    }
+#pragma unroll
+    for (int p = 0; p < MAX_PEERS; ++p)
+      if (p < a.ps.world) acc += v[p];
     a.norm[threadIdx.x] = acc;
   }
 }
@@ -212,24 +214,29 @@ __global__ void __launch_bounds__(QA_THREADS, 4) k_q_adam_exchange(const __grid_
     wait_local(a.ps, 0, (unsigned long long)a.ps.epoch);
   }
   if (!(a.dbg & 8)) q_adam_tile<WMAX>(a.q, a.q.unit_lo + blockIdx.x, sm);
-  // ---- small replicated sums (pose gradients, loss terms): every rank adds all ranks' blocks in rank order
+  // ---- small replicated sums (pose gradients, loss terms): every rank adds all ranks' blocks in rank order (the peer
+  //      loads of an element are independent: one NVLink round trip, not world_size of them)
   if (leader) {
     for (int t = threadIdx.x; t < a.n_aux; t += QA_THREADS) {
+      float x[MAX_PEERS];
+#pragma unroll
+      for (int p = 0; p < MAX_PEERS; ++p)
+        if (p < world) asm volatile("ld.relaxed.sys.global.f32 %0, [%1];" : "=f"(x[p]) : "l"(a.aux_pub[p] + t) : "memory");
       float acc = 0.f;
-      for (int p = 0; p < world; ++p) {
-        float x;
-        asm volatile("ld.relaxed.sys.global.f32 %0, [%1];" : "=f"(x) : "l"(a.aux_pub[p] + t) : "memory");
-        acc += x;
-      }
+#pragma unroll
+      for (int p = 0; p < MAX_PEERS; ++p)
+        if (p < world) acc += x[p];
       a.aux_sum[t] = acc;
     }
     for (int t = threadIdx.x; t < a.n_auxd; t += QA_THREADS) {
+      double x[MAX_PEERS];
+#pragma unroll
+      for (int p = 0; p < MAX_PEERS; ++p)
+        if (p < world) asm volatile("ld.relaxed.sys.global.f64 %0, [%1];" : "=d"(x[p]) : "l"(a.auxd_pub[p] + t) : "memory");
       double acc = 0.0;
-      for (int p = 0; p < world; ++p) {
-        double x;
-        asm volatile("ld.relaxed.sys.global.f64 %0, [%1];" : "=d"(x) : "l"(a.auxd_pub[p] + t) : "memory");
-        acc += x;
-      }
+#pragma unroll
+      for (int p = 0; p < MAX_PEERS; ++p)
+        if (p < world) acc += x[p];
       a.auxd_sum[t] = acc;
     }
   }
@@ -261,20 +268,24 @@ struct DecPeersArgs {
   AdamArgs adam;     // seg_step[0] = lr / (1 - beta1^t)
 };
 
+// one element per thread: the peer loads of a thread are independent and all in flight at once, so the kernel costs
+// one NVLink round trip (a single CTA striding over the 2 700 floats paid eleven of them back to back: 33 us)
 __global__ void __launch_bounds__(256) k_dec_adam_peers(const __grid_constant__ DecPeersArgs a) {
-  for (int t = threadIdx.x; t < DEC_N; t += 256) {
-    float g = 0.f;
-    for (int q = 0; q < a.world; ++q) {
-      float x;
-      asm volatile("ld.relaxed.sys.global.f32 %0, [%1];" : "=f"(x) : "l"(a.dec_pub[q] + t) : "memory");
-      g = q == 0 ? x : g + x;
-    }
-    float p = a.p[t], m = a.m[t], v = a.v[t];
-    adam_one(p, g, m, v, a.adam, a.adam.seg_step[0]);
-    a.p[t] = p;
-    a.m[t] = m;
-    a.v[t] = v;
-  }
+  const int t = blockIdx.x * 256 + threadIdx.x;
+  if (t >= DEC_N) return;
+  float x[MAX_PEERS];
+#pragma unroll
+  for (int q = 0; q < MAX_PEERS; ++q)
+    if (q < a.world) asm volatile("ld.relaxed.sys.global.f32 %0, [%1];" : "=f"(x[q]) : "l"(a.dec_pub[q] + t) : "memory");
+  float g = x[0];
+#pragma unroll
+  for (int q = 1; q < MAX_PEERS; ++q)
+    if (q < a.world) g += x[q];  // rank order: identical on every rank
+  float p = a.p[t], m = a.m[t], v = a.v[t];
+  adam_one(p, g, m, v, a.adam, a.adam.seg_step[0]);
+  a.p[t] = p;
+  a.m[t] = m;
+  a.v[t] = v;
 }
 
 }  // namespace eslam

@@ -110,6 +110,35 @@ __device__ __forceinline__ void mlp_tail_s(const float* __restrict__ W, const fl
   }
 }
 
+constexpr int QW_STRIDE = DW_STRIDE - DW_B1;  // b1 W2 b2 W3 b3 of one decoder (field.cuh's block minus W1): 340 floats
+constexpr int QW_TOTAL = 2 * QW_STRIDE + 4;
+
+template <int BYTES>
+__device__ __forceinline__ void cp_async_small(void* smem_dst, const void* gmem_src) {
+  const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.ca.shared.global [%0], [%1], %2;" ::"r"(d), "l"(gmem_src), "n"(BYTES) : "memory");
+}
+
+// b1 W2 b2 W3 b3 of both decoders -> shared memory (cp.async; decoder_weights_wait() + barrier before first use).
+// The packed arena block (include/eslam_b200.h) holds them contiguously: sdf floats [1024, 1329), rgb [2356, 2695).
+__device__ __forceinline__ void load_tail_weights(float* sW, const float* __restrict__ dec, int tid, int nthreads) {
+  constexpr int SDF4 = 304 / 4;  // b1 W2 b2 W3[0]
+  constexpr int RGB4 = 336 / 4;  // b1 W2 b2 W3[0..2]
+  for (int i = tid; i < SDF4 + RGB4; i += nthreads) {
+    if (i < SDF4)
+      cp_async16(sW + 4 * i, dec + S_B1 + 4 * i);
+    else
+      cp_async16(sW + QW_STRIDE + 4 * (i - SDF4), dec + C_B1 + 4 * (i - SDF4));
+  }
+  asm volatile("cp.async.commit_group;" ::: "memory");
+  if (tid < 32) sW[304 + tid] = 0.f;  // sdf W3 rows 1-2 (the sdf decoder has one output)
+  if (tid == 32) sW[336] = dec[S_B3];
+  if (tid >= 33 && tid < 36) sW[336 + (tid - 32)] = 0.f;
+  if (tid >= 36 && tid < 39) sW[QW_STRIDE + 336 + (tid - 36)] = dec[C_B3 + (tid - 36)];
+  if (tid == 39) sW[QW_STRIDE + 339] = 0.f;
+  if (tid == 40) sW[2 * QW_STRIDE] = dec[P_BETA];
+}
+
 // Q form of the coordinate-gradient half of scatter_group (pose-only backward): P holds the
 // gradient at the first layer's pre-activations (16 per point, p_slot layout); 4 lanes per point fetch the corners of
 // the 16-channel Q images and the coordinate gradient is d/du of bilinear(Q) . g, with the clip rule of scatter_group.

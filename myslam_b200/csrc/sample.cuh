@@ -422,7 +422,8 @@ __global__ void __launch_bounds__(SB) k_depth_ordinals(const __grid_constant__ D
 // ---------------------------------------------------------------------------------------------------
 struct ImportanceArgs {
   FieldK fk;
-  const float4* arena4;
+  const float4* arena4;  // decoders (layers 2-3 of the sdf decoder, beta)
+  const float4* q4;      // Q images of the current parameters
   int n_strat, n_imp;
   const float *rays_o, *rays_d;
   const int* dl_list;
@@ -432,8 +433,19 @@ struct ImportanceArgs {
   float* z;
 };
 
+struct SmemImp {
+  float4 P[NP * 4];  // first-layer pre-activations of the sdf decoder (p_slot layout)
+  ax_t ax_i[6][NP];
+  float ax_f[6][NP];
+  float W[QW_TOTAL];
+  float one[NP], w[NP], z[NP];
+};
+
+// The SDF-only forward of the coarse samples runs on the Q images with the decoder tail in shared memory, so the
+// kernel depends neither on the constant bank (no eslam_bind_decoders in the mapping loop, whose decoders change
+// every iteration) nor on the 64-channel gather.
 __global__ void __launch_bounds__(NP) k_importance(const __grid_constant__ ImportanceArgs a) {
-  __shared__ SmemFwd sm;
+  __shared__ SmemImp sm;
   __shared__ float s_zi[NP];  // resampled depths, [rl*n_imp + i]
   const int R0 = a.counters[1];
   const int NS = a.n_strat;
@@ -448,6 +460,7 @@ __global__ void __launch_bounds__(NP) k_importance(const __grid_constant__ Impor
   const int k = q - rl * NS;
   const int r0 = r00 + rl;
   const int ray = a.dl_list[r0];
+  load_tail_weights(sm.W, reinterpret_cast<const float*>(a.arena4) + a.fk.dec_off, q, NP);
   float o[3], d[3];
 #pragma unroll
   for (int c = 0; c < 3; ++c) {
@@ -467,13 +480,14 @@ __global__ void __launch_bounds__(NP) k_importance(const __grid_constant__ Impor
   }
   write_axis_setups<2>(a.fk, 0, pn, sm.ax_i, sm.ax_f, q);
   __syncthreads();
-  gather_tile<0>(a.fk, 0, a.arena4, sm.ax_i, sm.ax_f, sm.F, n_valid);
+  gather_preact_tile<0>(a.fk, a.q4, sm.ax_i, sm.ax_f, sm.P, n_valid, q);
+  decoder_weights_wait();
   __syncthreads();
-  float h1[16], h2[16], os[1];
-  mlp_forward<S_W1, S_B1, S_W2, S_B2, S_W3, S_B3, 1>(sm.F, q, h1, h2, os);
+  float h1[16], h2[16], os[3];
+  mlp_tail_s(sm.W - DW_B1, sm.P, q, h1, h2, os);
   const float sdf = tanhf(os[0]);
   float u, e, alpha;
-  sdf_to_alpha(sdf, c_dec[P_BETA], u, e, alpha);
+  sdf_to_alpha(sdf, sm.W[2 * QW_STRIDE], u, e, alpha);
   sm.one[q] = __fadd_rn(__fsub_rn(1.0f, alpha), 1e-10f);
   sm.z[q] = zp;
   __syncthreads();

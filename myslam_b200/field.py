@@ -217,9 +217,14 @@ class FieldStore:
         return out
 
     # ------------------------------------------------------------------ kernels' view
-    def bind(self) -> None:
-        """Make this map's decoders the ones the forward-only kernels read (constant memory)."""
+    def bind(self, force: bool = False) -> None:
+        """Make this map's decoders the ones the forward-only kernels read (constant memory, process-global per
+        device).  Skipped when this store at this generation is what the device's constant bank already holds."""
+        key = (id(self), self.gen)
+        if not force and _lib.BOUND_DECODERS.get(self.device.index) == key:
+            return
         call("eslam_bind_decoders", ptr(self.dec), stream())
+        _lib.BOUND_DECODERS[self.device.index] = key
 
     def ensure_q(self) -> torch.Tensor:
         """The Q images of the CURRENT parameters (rebuilt when the arena's generation moved on)."""

@@ -216,8 +216,7 @@ def mapping_iteration(ws: Workspace, store: FieldStore, sc: StepCfg, c2ws, poses
     _check_frames(gt_depths, gt_colors, b, cam)
     n_crop = (cam.H1 - cam.H0) * (cam.W1 - cam.W0)
     idx = draws.randint(n_crop, N)
-    store.bind()
-    q = store.ensure_q()
+    q = store.ensure_q()  # nothing in this loop reads the constant-bank decoders (they change every iteration)
     c2w_flat = c2ws.reshape(b, 16).float().contiguous()
     joint = poses7 is not None
     if strict_rng:
@@ -240,7 +239,7 @@ def mapping_iteration(ws: Workspace, store: FieldStore, sc: StepCfg, c2ws, poses
         if strict_rng or u_c is None:
             u_c = draws.rand(r0, ns)
             u_f = draws.rand(r0, ni)
-        call("eslam_importance_samples", store.ref(), ptr(store.arena), C.byref(rc), ptr(ws.rays_o), ptr(ws.rays_d),
+        call("eslam_importance_samples", store.ref(), ptr(store.arena), ptr(q), C.byref(rc), ptr(ws.rays_o), ptr(ws.rays_d),
              ptr(ws.dl_list), ptr(ws.counters), r0, ptr(u_c), ptr(u_f), ptr(linspace_table(ns, dev)), ptr(ws.z),
              stream())
     grad, gq = store.ensure_grad(), store.ensure_q_grad()

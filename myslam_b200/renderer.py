@@ -176,7 +176,8 @@ class Renderer(object):
                 raise RuntimeError("rendering.perturb=False with depth-less rays is not supported by the kernels")
             u_c = draws.rand(r0, ns)
             u_f = draws.rand(r0, ni)
-            call("eslam_importance_samples", store.ref(), ptr(store.arena), C.byref(cfg), ptr(rays_o), ptr(rays_d),
+            call("eslam_importance_samples", store.ref(), ptr(store.arena), ptr(store.ensure_q()), C.byref(cfg),
+                 ptr(rays_o), ptr(rays_d),
                  ptr(dl), ptr(cnt), r0, ptr(u_c), ptr(u_f), ptr(t_uni), ptr(z), stream())
         return z
 

@@ -57,45 +57,56 @@ def main():
     poses7[1:] = matrix_to_cam_pose(poses[1:])
     res = {}
 
-    def bwd(arena=None, grad=None):
-        call("eslam_loss_backward", store.ref(), ptr(store.arena if arena is None else arena), C.byref(sc.cam),
-             C.byref(sc.render), ptr(ws.rays_o), ptr(ws.rays_d), ptr(ws.z), ptr(ws.gt_depth), ptr(ws.gt_color),
-             ptr(ws.src), ptr(idx), pix, None, ptr(ws.counters), None, N,
-             ptr(store.ensure_grad() if grad is None else grad), ptr(ws.pose_grad), None, stream())
+    def bwd():
+        call("eslam_loss_backward_q", store.ref(), ptr(store.arena), ptr(store.ensure_q()), ptr(store.ensure_q_grad()),
+             C.byref(sc.cam), C.byref(sc.render), ptr(ws.rays_o), ptr(ws.rays_d), ptr(ws.z), ptr(ws.gt_depth),
+             ptr(ws.gt_color), ptr(ws.src), ptr(idx), pix, None, ptr(ws.counters), None, N, ptr(store.ensure_grad()),
+             ptr(ws.pose_grad), None, stream())
 
+    # every timed region = the backward kernel (so the gradient images carry a real iteration's content) + one way of
+    # turning them into the optimiser step; subtract the first line
     mapping_iteration(ws, store, sc, poses, poses7, cols, deps, pix, 1, 1e-3, 5e-3, 5e-3, 1e-3, apply_adam=False)
+    store.reset_adam()
     idx = torch.randint(spec["H"] * spec["W"], (N,), device=dev)
-    store.bind()
-    res["bwd, ordinary gradient arena"] = time_region(bwd, 50, 5, True) / 50
+    res["bwd alone"] = time_region(bwd, 50, 5, True) / 50
+    store.reset_adam()
+
+    def local_step():
+        bwd()
+        store.adam_step_q(1, 1e-3, 5e-3, 5e-3)
+
+    res["bwd + 1-GPU tail (no exchange: replicas would diverge)"] = time_region(local_step, 50, 5, True) / 50
     nccl = MappingExchange()
 
     def nccl_step():
-        nccl.reduce_grads(store.grad, ws.pose_grad, None)
-        store.adam_step(1, 1e-3, 5e-3, 5e-3)
+        bwd()
+        nccl.reduce_grads([store.gq_arena, store.grad[store.dec_off:]], ws.pose_grad, None)
+        store.adam_step_q(1, 1e-3, 5e-3, 5e-3)
+        nccl.after_step(store)
 
-    res["NCCL all-reduce(arena)+all-reduce(poses)+Adam"] = time_region(nccl_step, 50, 5, True) / 50
+    res["bwd + NCCL all-reduce(images, decoders, poses) + tail + decoder broadcast"] = time_region(nccl_step, 50, 5, True) / 50
     res["NCCL all-reduce of 8 counters"] = time_region(lambda: nccl.reduce_counters(ws.counters), 50, 5, True) / 50
-    res["Adam alone (1-GPU kernel)"] = time_region(lambda: store.adam_step(1, 1e-3, 5e-3, 5e-3), 50, 5, True) / 50
-    for mm in (True, False):
+    for mm in (False, True):
         ex = PeerExchange(store, ws, multimem=mm)
+        if mm and not ex.multimem:
+            continue
         tag = "multimem" if ex.multimem else "P2P"
-        mapping_iteration(ws, store, sc, poses, poses7, cols, deps, pix, 1, 1e-3, 5e-3, 5e-3, 1e-3, apply_adam=False)
-        store.bind()
-        if mm:
-            a_ord, g_sym = store.arena.clone(), ex.buf[ex.off_stage:ex.off_stage + store.n_floats]
-            res["bwd, symmetric params + ordinary grads (as used)"] = time_region(bwd, 50, 5, True) / 50
-            res["bwd, ordinary params + symmetric grads"] = time_region(lambda: bwd(a_ord, g_sym), 50, 5, True) / 50
-            del a_ord
-            g_sym.zero_()
+        store.reset_adam()
+        res[f"bwd alone, parameters in symmetric memory ({tag})"] = time_region(bwd, 50, 5, True) / 50
+        store.reset_adam()
+
+        def peer_step():
+            bwd()
+            ex.adam_exchange(1, 1e-3, 5e-3, 5e-3, ws.pose_grad, nf, None)
+
         res[f"peer counters exchange ({tag})"] = time_region(lambda: ex.reduce_counters(ws.counters), 50, 5, True) / 50
-        res[f"peer reduce-scatter+Adam+all-gather ({tag})"] = time_region(
-            lambda: ex.adam_exchange(1, 1e-3, 5e-3, 5e-3, ws.pose_grad, nf, None), 50, 5, True) / 50
+        res[f"bwd + peer exchange: push + tile Adam + all-gather + decoder step ({tag})"] = time_region(peer_step, 50, 5, True) / 50
         lib = M._lib.load()
         for bits, what in ((8, "barriers only"), (32, "no barriers"), (8 | 32, "empty launches")):
             lib.eslam_set_debug(bits)
-            res[f"  [{what}] ({tag})"] = time_region(lambda: ex.adam_exchange(1, 1e-3, 5e-3, 5e-3, ws.pose_grad, nf, None), 50, 5,
-                                                     True) / 50
+            res[f"  [{what}] ({tag})"] = time_region(peer_step, 50, 5, True) / 50
         lib.eslam_set_debug(0)
+        store.reset_adam()
         ex.check()
     if rank == 0:
         print(f"# world {world}, arena {store.n_floats * 4 / 1e6:.1f} MB")

@@ -91,7 +91,8 @@ def main():
         store.grad.zero_()
     timeit("map.sample_rays", lambda: _sample(ws, store, sc, idx, nf, pix, c2w, poses7, 1, deps, cols, u, 0))
     timeit("map.importance", lambda: call(
-        "eslam_importance_samples", store.ref(), ptr(store.arena), C.byref(sc.render), ptr(ws.rays_o), ptr(ws.rays_d),
+        "eslam_importance_samples", store.ref(), ptr(store.arena), ptr(store.ensure_q()), C.byref(sc.render),
+        ptr(ws.rays_o), ptr(ws.rays_d),
         ptr(ws.dl_list), ptr(ws.counters), N, ptr(uc), ptr(uf), ptr(linspace_table(32, dev)), ptr(ws.z), stream()))
     timeit("map.adam (6.79M params)", lambda: store.adam_step(1, 1e-3, 5e-3, 5e-3))
     timeit("map.render_forward 4000 rays", lambda: call(
@@ -99,7 +100,7 @@ def main():
         ptr(ws.counters), ptr(ws.depth), ptr(ws.rgb), ptr(ws.sdf), stream()))
     timeit("torch.randint+3 rand (draws)", lambda: (torch.randint(816000, (N,), device=dev), torch.rand(N, 40, device=dev),
                                                     torch.rand(N, 32, device=dev), torch.rand(N, 8, device=dev)))
-    timeit("bind_decoders", lambda: store.bind())
+    timeit("bind_decoders", lambda: store.bind(force=True))
     res["map.R"] = int(ws.counters[0])
     res["map.R0"] = int(ws.counters[1])
     # tracking
