@@ -80,7 +80,9 @@ typedef struct {
 
 /* Device-side counters written by eslam_sample_rays / eslam_track_mask (int32[8]):
  * [0] R rays kept  [1] R0 depth-less rays among them  [2] rays in the loss mask
- * [3] front samples [4] center samples [5] tail samples (over masked rays)  [6],[7] reserved */
+ * [3] front samples [4] center samples [5] tail samples (over masked rays)  [6] reserved
+ * [7] tile dispatch ticket of the compaction kernel (its CTAs take their tile in arrival order, so the look-back over
+ *     earlier tiles cannot wait for a CTA that is not running) */
 #define ESLAM_N_COUNTERS 8
 /* The counters BUFFER handed to eslam_sample_rays* / eslam_depth_samples must hold ESLAM_COUNTER_WORDS int32
  * (8-byte aligned): the 8 counters, then one 64-bit word per CTA of the compaction kernel (its totals, published
@@ -361,6 +363,14 @@ int eslam_finalize_loss(const eslam_render_cfg_t* cfg_host, const int32_t* count
 int eslam_ingest_frame(const uint8_t* bgr, const uint16_t* depth_u16, int H, int W, int crop_edge,
                        double png_depth_scale, double scale, double* color, float* depth, eslam_stream_t s);
 
+/* eslam_ingest_frame for frames whose colour image is larger than the depth image (ScanNet: 1296x968 vs 640x480;
+ * datasets.py:92-94 `cv2.resize(color_data, (W, H))` on the float64 image): bgr[Hs][Ws][3] -> colour resized to the
+ * depth's [H][W] and cropped.  The resize restates what the opencv-python wheels compute (Intel IPP: float64 weights,
+ * row pass then column pass, fma(w, b - a, a)); bit-exact with the reference's `ScanNet` loader run in this container
+ * (tests/golden/ingest_scannet.npz).  No undistortion (TUM keeps cv2.undistort on the host, then this path). */
+int eslam_ingest_frame_resized(const uint8_t* bgr, int Hs, int Ws, const uint16_t* depth_u16, int H, int W, int crop_edge,
+                               double png_depth_scale, double scale, double* color, float* depth, eslam_stream_t s);
+
 /* matrix_to_cam_pose / cam_pose_to_matrix (common.py:155-181 over pytorch3d 0.7.1 matrix_to_quaternion /
  * quaternion_to_matrix) for n cameras: c2w[n][16] row-major <-> poses[n][7] = (qw,qx,qy,qz,tx,ty,tz), evaluated in
  * torch's operation order.  Used once per optimize_mapping call for the window's poses (Mapper.py:289,352-362). */
@@ -376,6 +386,30 @@ int eslam_pose_to_matrix(const float* poses, float* c2w, int n, eslam_stream_t s
 int eslam_keyframe_overlap(const eslam_camera_t* cam_host, const float* c2w, const float* depth,
                            const int64_t* pix_idx, int n_rays, const float* t_vals, int n_samples,
                            const float* kf_c2w, int n_keyframes, int32_t* inside, int32_t* n_pts, eslam_stream_t s);
+
+/* ---- mesh extraction around the grid query (Mesher.get_mesh, src/utils/Mesher.py:188-264) ---------------------------
+ * Marching cubes over the SDF lattice sdf[(iy*nx + ix)*nz + iz] (what eslam_grid_sdf* writes) ON THE DEVICE, replacing
+ * the D2H of the 1.3 GB volume + skimage.measure.marching_cubes (Mesher.py:219-243).  Case tables: n_tri[256] uint8 and
+ * tri[256][15] int8 edge ids (myslam_b200/mc_tables.py: generated, conventions there; corner "inside" <=> value < level,
+ * triangles wound with the normal towards increasing values).  Two passes without per-cell storage:
+ *   eslam_mc_count  block_count[eslam_mc_blocks()] = triangles of each block of 256 consecutive cells
+ *   eslam_mc_emit   block_base = exclusive scan of block_count (int64); writes the triangle soup verts[3T][3] (world
+ *                   coordinates: lattice coordinate + linear interpolation along the crossed edge, Mesher.py:245) and
+ *                   keys[3T] = 3 * flat(lower lattice corner) + axis, the lattice edge of each vertex (equal keys =
+ *                   the same vertex: what welding needs). */
+int64_t eslam_mc_blocks(int nx, int ny, int nz);
+int eslam_mc_count(const float* sdf, int nx, int ny, int nz, double level, const uint8_t* n_tri, const int8_t* tri,
+                   int32_t* block_count, eslam_stream_t s);
+int eslam_mc_emit(const float* sdf, const float* xs, const float* ys, const float* zs, int nx, int ny, int nz,
+                  double level, const uint8_t* n_tri, const int8_t* tri, const int64_t* block_base, float* verts,
+                  int64_t* keys, eslam_stream_t s);
+
+/* One frame of cull_mesh (src/tools/cull_mesh.py:58-100): seen[v] |= vertex v projects into the frame (in front of the
+ * camera, inside the image; with eval_rec also not more than `truncation` behind the frame's depth, sampled
+ * bilinearly like F.grid_sample(zeros, align_corners=True)).  w2c[16]: row-major inverse of the frame's c2w.  The
+ * caller loops over the frames and drops the faces whose three vertices were never seen (cull_mesh.py:102-105). */
+int eslam_cull_frame(const float* verts, int64_t n, const float* w2c, const float* depth,
+                     const eslam_camera_t* cam_host, double truncation, int eval_rec, uint8_t* seen, eslam_stream_t s);
 
 /* ---- multi-GPU mapping over peer memory (new in this build; the reference is single-GPU) ---------------------
  * One process per GPU; every rank owns ONE symmetric (NVLink peer-mapped) allocation holding, at identical

@@ -100,9 +100,13 @@ PROTOTYPES = {
     "eslam_pose_adam_step": [_P, _P, _P, _P, _I, _I, _D, _D, _I, _D, _D, _D, _P, _I, _P],
     "eslam_finalize_loss": [_RP, _P, _I, _P, _P, _P],
     "eslam_ingest_frame": [_P, _P, _I, _I, _I, _D, _D, _P, _P, _P],
+    "eslam_ingest_frame_resized": [_P, _I, _I, _P, _I, _I, _I, _D, _D, _P, _P, _P],
     "eslam_matrix_to_pose": [_P, _P, _I, _P],
     "eslam_pose_to_matrix": [_P, _P, _I, _P],
     "eslam_keyframe_overlap": [_CP, _P, _P, _P, _I, _P, _I, _P, _I, _P, _P, _P],
+    "eslam_mc_count": [_P, _I, _I, _I, _D, _P, _P, _P, _P],
+    "eslam_mc_emit": [_P, _P, _P, _P, _I, _I, _I, _D, _P, _P, _P, _P, _P, _P],
+    "eslam_cull_frame": [_P, _L, _P, _P, _CP, _D, _I, _P, _P],
     "eslam_exchange_counters": [C.POINTER(Peers), _P, C.POINTER(C.c_void_p), _I, _P, _P],
     "eslam_q_adam_exchange": [C.POINTER(Peers), _FP, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), _P, _P, _P, _P, _P, _P,
                               _D, _D, _D, _I, _D, _D, _D, C.POINTER(C.c_void_p), _P, C.POINTER(C.c_void_p), _P, _I, _P,
@@ -130,6 +134,8 @@ def load():
     lib.eslam_exchange_flag_words.argtypes = []
     lib.eslam_q_exchange_stage_floats.restype = C.c_int64
     lib.eslam_q_exchange_stage_floats.argtypes = [C.POINTER(FieldDesc), C.c_int]
+    lib.eslam_mc_blocks.restype = C.c_int64
+    lib.eslam_mc_blocks.argtypes = [C.c_int, C.c_int, C.c_int]
     lib.eslam_q_touched_bytes.restype = C.c_int
     lib.eslam_q_touched_bytes.argtypes = [C.POINTER(FieldDesc)]
     for name, argtypes in PROTOTYPES.items():

@@ -15,6 +15,7 @@
 #include "ingest.cuh"
 #include "qplane.cuh"
 #include "qbwd.cuh"
+#include "mcubes.cuh"
 
 using namespace eslam;
 
@@ -84,6 +85,14 @@ static int ensure_smem(K kernel, size_t bytes, bool* done) {
 template <typename K>
 static int set_smem(K kernel, size_t bytes) {
   return (int)cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+}
+
+// cudaFuncSetAttribute is per DEVICE: remember per device which kernels have been configured
+constexpr int MAX_DEVICES = 64;
+static int current_device() {
+  int d = 0;
+  cudaGetDevice(&d);
+  return d >= 0 && d < MAX_DEVICES ? d : 0;
 }
 
 extern "C" {
@@ -551,13 +560,14 @@ int eslam_render_forward_act(const eslam_field_t* f, const float* arena, const f
 
 template <int MODE, bool GF, bool GR>
 static int launch_bwd(const BwdArgs& a, int n_rays, cudaStream_t st) {
-  static bool configured = false;
+  static bool configured[MAX_DEVICES] = {false};
   const size_t bytes = sizeof(SmemBwd<GF>);
   static_assert(sizeof(SmemBwd<true>) <= 113 * 1024, "two CTAs of the backward kernel must fit one SM's shared memory");
-  if (!configured) {
+  const int dev = current_device();
+  if (!configured[dev]) {
     int rc = set_smem(k_render_bwd<MODE, GF, GR>, bytes);
     if (rc) return rc;
-    configured = true;
+    configured[dev] = true;
   }
   const int rpb = MODE == 2 ? NP : ((NP / a.S) < 16 ? (NP / a.S) : 16);
   k_render_bwd<MODE, GF, GR><<<(n_rays + rpb - 1) / rpb, NT_BWD, bytes, st>>>(a);
@@ -698,14 +708,15 @@ static int loss_backward_impl(const eslam_field_t* f, const float* arena, const 
   a.gq4 = reinterpret_cast<float4*>(gq_arena);
   if (q_arena && grad_arena) {  // mapping iteration in the Q form
     REQUIRE(gq_arena && !act4, "eslam_loss_backward_q");
-    static bool configured[2] = {false, false};
+    static bool configured[MAX_DEVICES][2] = {{false, false}};
     const size_t bytes = sizeof(SmemBwdQ<true>);
     static_assert(sizeof(SmemBwdQ<true>) <= 113 * 1024, "two CTAs of the Q backward must fit one SM's shared memory");
     const int gr = pose_grad ? 1 : 0;
-    if (!configured[gr]) {
+    const int dev = current_device();
+    if (!configured[dev][gr]) {
       rc = gr ? set_smem(k_map_bwd_q<true>, bytes) : set_smem(k_map_bwd_q<false>, bytes);
       if (rc) return fail(rc, "eslam_loss_backward_q(shared memory)");
-      configured[gr] = true;
+      configured[dev][gr] = true;
     }
     const int S = a.S, rpb = (NP / S) < 16 ? (NP / S) : 16;
     const unsigned grid = (unsigned)((max_rays + rpb - 1) / rpb);
@@ -716,12 +727,13 @@ static int loss_backward_impl(const eslam_field_t* f, const float* arena, const 
     rc = (int)cudaGetLastError();
   } else if (q_arena) {
     REQUIRE(!grad_arena && pose_grad && sdf && act4 && actm, "eslam_pose_backward_q");
-    static bool configured = false;
+    static bool configured[MAX_DEVICES] = {false};
     const size_t bytes = sizeof(SmemBwdQ<false>);
-    if (!configured) {
+    const int dev = current_device();
+    if (!configured[dev]) {
       rc = set_smem(k_pose_bwd_q, bytes);
       if (rc) return fail(rc, "eslam_pose_backward_q(shared memory)");
-      configured = true;
+      configured[dev] = true;
     }
     const int S = a.S, rpb = (NP / S) < 16 ? (NP / S) : 16;
     k_pose_bwd_q<<<(max_rays + rpb - 1) / rpb, NT_BWD, bytes, S_(s)>>>(a);
@@ -1053,6 +1065,33 @@ int eslam_ingest_frame(const uint8_t* bgr, const uint16_t* depth_u16, int H, int
   return 0;
 }
 
+int eslam_ingest_frame_resized(const uint8_t* bgr, int Hs, int Ws, const uint16_t* depth_u16, int H, int W, int crop_edge,
+                               double png_depth_scale, double scale, double* color, float* depth, eslam_stream_t s) {
+  REQUIRE(bgr && depth_u16 && color && depth && H > 0 && W > 0 && Hs > 0 && Ws > 0 && crop_edge >= 0 &&
+              2 * crop_edge < H && 2 * crop_edge < W,
+          "eslam_ingest_frame_resized");
+  IngestResizeArgs a;
+  a.bgr = bgr;
+  a.depth = depth_u16;
+  a.Hs = Hs;
+  a.Ws = Ws;
+  a.H = H;
+  a.W = W;
+  a.edge = crop_edge;
+  a.sx = (double)Ws / (double)W;
+  a.sy = (double)Hs / (double)H;
+  a.png_depth_scale = (float)png_depth_scale;
+  a.scale = (float)scale;
+  a.color = color;
+  a.out_depth = depth;
+  const long long n = (long long)(H - 2 * crop_edge) * (W - 2 * crop_edge);
+  long long blocks = (n + 255) / 256;
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  k_ingest_resize<<<(unsigned)blocks, 256, 0, S_(s)>>>(a);
+  CHECK_LAUNCH("eslam_ingest_frame_resized");
+  return 0;
+}
+
 int eslam_matrix_to_pose(const float* c2w, float* poses, int n, eslam_stream_t s) {
   REQUIRE(c2w && poses && n >= 0, "eslam_matrix_to_pose");
   if (n == 0) return 0;
@@ -1167,6 +1206,79 @@ int eslam_render_forward_q(const eslam_field_t* f, const float* q_arena, const f
   const int rpb = NP / n_samples;
   k_render_fwd_q<<<(n_rays + rpb - 1) / rpb, NP, 0, S_(s)>>>(a);
   CHECK_LAUNCH("eslam_render_forward_q");
+  return 0;
+}
+
+// ---- marching cubes, mesh culling (mcubes.cuh) ------------------------------------------------------------------
+static int fill_mc(McArgs& a, const float* sdf, int nx, int ny, int nz, double level, const uint8_t* n_tri,
+                   const int8_t* tri) {
+  if (!(sdf && n_tri && tri && nx >= 2 && ny >= 2 && nz >= 2)) return ESLAM_EINVAL;
+  memset(&a, 0, sizeof(a));
+  a.sdf = sdf;
+  a.nx = nx;
+  a.ny = ny;
+  a.nz = nz;
+  a.level = (float)level;
+  a.n_tri = n_tri;
+  a.tri = reinterpret_cast<const signed char*>(tri);
+  a.n_cells = (long long)(nx - 1) * (ny - 1) * (nz - 1);
+  if ((a.n_cells + MC_THREADS - 1) / MC_THREADS > 0x7fffffffLL) return ESLAM_EUNSUPPORTED;
+  return 0;
+}
+
+int64_t eslam_mc_blocks(int nx, int ny, int nz) {
+  if (nx < 2 || ny < 2 || nz < 2) return 0;
+  return ((int64_t)(nx - 1) * (ny - 1) * (nz - 1) + MC_THREADS - 1) / MC_THREADS;
+}
+
+int eslam_mc_count(const float* sdf, int nx, int ny, int nz, double level, const uint8_t* n_tri, const int8_t* tri,
+                   int32_t* block_count, eslam_stream_t s) {
+  McArgs a;
+  int rc = fill_mc(a, sdf, nx, ny, nz, level, n_tri, tri);
+  if (rc || !block_count) return fail(rc ? rc : ESLAM_EINVAL, "eslam_mc_count");
+  a.block_count = block_count;
+  k_mc_count<<<(unsigned)eslam_mc_blocks(nx, ny, nz), MC_THREADS, 0, S_(s)>>>(a);
+  CHECK_LAUNCH("eslam_mc_count");
+  return 0;
+}
+
+int eslam_mc_emit(const float* sdf, const float* xs, const float* ys, const float* zs, int nx, int ny, int nz,
+                  double level, const uint8_t* n_tri, const int8_t* tri, const int64_t* block_base, float* verts,
+                  int64_t* keys, eslam_stream_t s) {
+  McArgs a;
+  int rc = fill_mc(a, sdf, nx, ny, nz, level, n_tri, tri);
+  if (rc || !(xs && ys && zs && block_base && verts && keys)) return fail(rc ? rc : ESLAM_EINVAL, "eslam_mc_emit");
+  a.xs = xs;
+  a.ys = ys;
+  a.zs = zs;
+  a.block_base = reinterpret_cast<const long long*>(block_base);
+  a.verts = verts;
+  a.keys = reinterpret_cast<long long*>(keys);
+  k_mc_emit<<<(unsigned)eslam_mc_blocks(nx, ny, nz), MC_THREADS, 0, S_(s)>>>(a);
+  CHECK_LAUNCH("eslam_mc_emit");
+  return 0;
+}
+
+int eslam_cull_frame(const float* verts, int64_t n, const float* w2c, const float* depth, const eslam_camera_t* cam,
+                     double truncation, int eval_rec, uint8_t* seen, eslam_stream_t s) {
+  REQUIRE(verts && w2c && depth && cam && seen && n >= 0, "eslam_cull_frame");
+  if (n == 0) return 0;
+  CullArgs a;
+  a.verts = verts;
+  a.n = n;
+  a.w2c = w2c;
+  a.depth = depth;
+  a.H = cam->H;
+  a.W = cam->W;
+  a.fx = cam->fx;
+  a.fy = cam->fy;
+  a.cx = cam->cx;
+  a.cy = cam->cy;
+  a.truncation = (float)truncation;
+  a.eval_rec = eval_rec;
+  a.seen = seen;
+  k_cull_frame<<<(unsigned)((n + 255) / 256), 256, 0, S_(s)>>>(a);
+  CHECK_LAUNCH("eslam_cull_frame");
   return 0;
 }
 

@@ -153,11 +153,17 @@ __device__ __forceinline__ void block_scan2(int f0, int f1, int& ex0, int& ex1, 
 
 // Ordered compaction across CTAs without re-evaluating the preceding slots: CTA b publishes its two totals in
 // agg[b] (one 64-bit word, bit 0 = ready; zeroed by the host entry point before the launch) and sums the words of
-// the CTAs before it, spinning on those not yet published.  CTAs are dispatched in index order and never wait for
-// a later one, so the chain cannot deadlock even when the grid exceeds what is resident.
-__device__ __forceinline__ void lookback2(unsigned long long* agg, int tot0, int tot1, int* sh /*[2*SB/32+2]*/,
+// the CTAs before it, spinning on those not yet published.  b is the CTA's TILE, taken from a dispatch ticket
+// (tile_ticket) rather than from blockIdx: a tile only ever waits for tiles whose CTAs already run, whatever order
+// the hardware dispatches CTAs in, so the chain cannot deadlock even when the grid exceeds what is resident.
+__device__ __forceinline__ int tile_ticket(int* ticket, int* sh_slot) {
+  if (threadIdx.x == 0) *sh_slot = atomicAdd(ticket, 1);
+  __syncthreads();
+  return *sh_slot;
+}
+
+__device__ __forceinline__ void lookback2(unsigned long long* agg, int b, int tot0, int tot1, int* sh /*[2*SB/32+2]*/,
                                           int& base0, int& base1) {
-  const int b = blockIdx.x;
   if (threadIdx.x == 0) {
     const unsigned long long w = ((unsigned long long)(unsigned)tot0 << 32) | ((unsigned long long)(unsigned)tot1 << 1) | 1ull;
     __threadfence();
@@ -257,8 +263,10 @@ __device__ __forceinline__ void depth_guided_z_warp(float d, int n_strat, int n_
 
 __global__ void __launch_bounds__(SB) k_sample_rays(const __grid_constant__ SampleArgs a) {
   __shared__ int sh[2 * SB / 32 + 2];
+  __shared__ int s_tile;
   const int N = a.n_img * a.n_per_img;
-  const int start = blockIdx.x * SB;
+  const int tile = tile_ticket(a.counters + 7, &s_tile);  // counters[7]: zeroed with the counters before the launch
+  const int start = tile * SB;
   const int slot = start + threadIdx.x;
   RayEval e;
   e.keep = false;
@@ -270,7 +278,7 @@ __global__ void __launch_bounds__(SB) k_sample_rays(const __grid_constant__ Samp
   block_scan2(fk_, fd_, ex0, ex1, tot0, tot1, sh);
   // kept / depth-less counts of all preceding slots: the order-preserving compaction of Tracker.py:184-187 /
   // Mapper.py:329-332 (boolean indexing) across CTAs
-  lookback2(a.agg, tot0, tot1, sh, base0, base1);
+  lookback2(a.agg, tile, tot0, tot1, sh, base0, base1);
   if (e.keep) {
     const int r = base0 + ex0;
     const int r0 = base1 + ex1;  // ordinal among depth-less rays
@@ -392,14 +400,16 @@ struct DepthOrdArgs {
 
 __global__ void __launch_bounds__(SB) k_depth_ordinals(const __grid_constant__ DepthOrdArgs a) {
   __shared__ int sh[2 * SB / 32 + 2];
-  const int start = blockIdx.x * SB;
+  __shared__ int s_tile;
+  const int tile = tile_ticket(a.counters + 7, &s_tile);
+  const int start = tile * SB;
   const int r = start + threadIdx.x;
   const bool in = r < a.n_rays;
   const float d = in ? a.gt_depth[r] : 1.f;
   const int fd_ = (in && !(d > 0.f)) ? 1 : 0;
   int ex0, ex1, tot0, tot1, base0, base1;
   block_scan2(fd_, 0, ex0, ex1, tot0, tot1, sh);
-  lookback2(a.agg, tot0, tot1, sh, base0, base1);
+  lookback2(a.agg, tile, tot0, tot1, sh, base0, base1);
   if (in) {
     const int r0 = base0 + ex0;
     if (d > 0.f) {
@@ -413,7 +423,7 @@ __global__ void __launch_bounds__(SB) k_depth_ordinals(const __grid_constant__ D
     if (tot0) atomicAdd(a.counters + 1, tot0);
     const int here = min(SB, a.n_rays - start);
     if (here - tot0) atomicAdd(a.counters + 2, here - tot0);
-    if (blockIdx.x == 0) a.counters[0] = a.n_rays;
+    if (tile == 0) a.counters[0] = a.n_rays;
   }
 }
 

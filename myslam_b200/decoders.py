@@ -70,13 +70,16 @@ class _DecodeFn(torch.autograd.Function):
         call("eslam_decode_points", store.ref(), ptr(store.arena), ptr(pts), n, ptr(raw), 0, stream())
         ctx.store, ctx.dts = store, dts
         ctx.save_for_backward(pts)
-        ctx.arena_version = store.arena._version
+        ctx.gen = store.gen
         return raw
 
     @staticmethod
     def backward(ctx, g_raw):
         (pts,) = ctx.saved_tensors
         store = ctx.store
+        if store.gen != ctx.gen:
+            raise RuntimeError("Decoders.forward: the map's parameters changed between forward and backward (another "
+                               "model or an optimiser step re-used this device's FieldStore); run backward first")
         needs = ctx.needs_input_grad
         need_pts, need_leaves = needs[0], needs[3:]
         want_field = any(need_leaves)

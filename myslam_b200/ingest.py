@@ -6,8 +6,10 @@
     color, depth = ingest_frame(color_u8, depth_u16, png_depth_scale, crop_edge, device)
 
 returns exactly what the reference's loader followed by `.to(device)` returns -- colour [H',W',3] float64 RGB in
-[0,1], depth [H',W'] float32 -- but moves 8 bytes per pixel over PCIe instead of 28.  Same-size colour and depth
-only (Replica); datasets that undistort or resize the colour image (ScanNet, TUM) keep the reference's host path.
+[0,1], depth [H',W'] float32 -- but moves 8 bytes per pixel over PCIe instead of 28.  A colour image larger than the
+depth image (ScanNet: 1296x968 vs 640x480) is resized to the depth's size on the device like the loader's
+`cv2.resize(color_data, (W, H))`; undistortion (TUM: cv2.undistort on the uint8 image) stays on the host and feeds this
+function, `crop_size` (TUM) is not handled here.
 """
 from __future__ import annotations
 
@@ -29,14 +31,19 @@ def ingest_frame(color_u8, depth_u16, png_depth_scale: float, crop_edge: int = 0
         depth_u16 = torch.from_numpy(np.ascontiguousarray(depth_u16).view(np.int16))  # same bits; torch-friendly dtype
     if color_u8.dtype != torch.uint8 or color_u8.dim() != 3 or color_u8.shape[2] != 3:
         raise RuntimeError("colour must be [H,W,3] uint8 (BGR, as cv2.imread returns it)")
-    if depth_u16.dtype not in (torch.int16, torch.uint16) or tuple(depth_u16.shape) != tuple(color_u8.shape[:2]):
-        raise RuntimeError("depth must be [H,W] 16-bit with the colour image's size (no resize on this path)")
-    H, W = int(color_u8.shape[0]), int(color_u8.shape[1])
+    if depth_u16.dtype not in (torch.int16, torch.uint16) or depth_u16.dim() != 2:
+        raise RuntimeError("depth must be [H,W] 16-bit")
+    H, W = int(depth_u16.shape[0]), int(depth_u16.shape[1])
+    Hs, Ws = int(color_u8.shape[0]), int(color_u8.shape[1])
     e = int(crop_edge)
     c = color_u8.contiguous().to(dev, non_blocking=True)
     d = depth_u16.contiguous().to(dev, non_blocking=True)
     color = torch.empty(H - 2 * e, W - 2 * e, 3, dtype=torch.float64, device=dev)
     depth = torch.empty(H - 2 * e, W - 2 * e, dtype=torch.float32, device=dev)
-    call("eslam_ingest_frame", ptr(c), ptr(d), H, W, e, float(png_depth_scale), float(scale), ptr(color), ptr(depth),
-         stream())
+    if (Hs, Ws) == (H, W):
+        call("eslam_ingest_frame", ptr(c), ptr(d), H, W, e, float(png_depth_scale), float(scale), ptr(color),
+             ptr(depth), stream())
+    else:  # datasets.py:92-94: the colour image is resized to the depth image's size
+        call("eslam_ingest_frame_resized", ptr(c), Hs, Ws, ptr(d), H, W, e, float(png_depth_scale), float(scale),
+             ptr(color), ptr(depth), stream())
     return color, depth

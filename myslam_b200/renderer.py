@@ -95,7 +95,7 @@ class _RenderFn(torch.autograd.Function):
         sdf = torch.empty(R, S, dtype=torch.float32, device=dev)
         call("eslam_render_forward", store.ref(), ptr(store.arena), ptr(rays_o), ptr(rays_d), ptr(z), R, S, None,
              ptr(depth), ptr(rgb), ptr(sdf), stream())
-        ctx.store, ctx.dts = store, dts
+        ctx.store, ctx.dts, ctx.gen = store, dts, store.gen
         ctx.save_for_backward(rays_d, rays_o, z)
         return depth, rgb, sdf
 
@@ -103,6 +103,9 @@ class _RenderFn(torch.autograd.Function):
     def backward(ctx, g_depth, g_rgb, g_sdf):
         rays_d, rays_o, z = ctx.saved_tensors
         store = ctx.store
+        if store.gen != ctx.gen:
+            raise RuntimeError("render_batch_ray: the map's parameters changed between forward and backward (another "
+                               "model or an optimiser step re-used this device's FieldStore); run backward first")
         R, S = z.shape
         needs = ctx.needs_input_grad
         need_rays = needs[0] or needs[1]

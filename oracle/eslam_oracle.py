@@ -806,3 +806,161 @@ def ingest_frame(color_u8_bgr, depth_u16, png_depth_scale, crop_edge=0, scale=1.
         color = color[crop_edge:-crop_edge, crop_edge:-crop_edge]
         depth = depth[crop_edge:-crop_edge, crop_edge:-crop_edge]
     return color.contiguous(), depth.contiguous()
+
+
+def _fma(a, b, c):
+    """round(a * b + c) with ONE rounding, exactly (python has no math.fma before 3.13)."""
+    from fractions import Fraction
+
+    return float(Fraction(a) * Fraction(b) + Fraction(c))
+
+
+def _linear_taps(n_src, n_dst):
+    """Source index pair and float64 weight of every destination index of cv2.resize(INTER_LINEAR) along one axis."""
+    import numpy as np
+
+    f = (np.arange(n_dst) + 0.5) * (n_src / n_dst) - 0.5
+    s = np.floor(f).astype(np.int64)
+    return np.clip(s, 0, n_src - 1), np.clip(s + 1, 0, n_src - 1), f - s
+
+
+def ingest_frame_resized(color_u8_bgr, depth_u16, png_depth_scale, crop_edge=0, scale=1.0):
+    """BaseDataset.__getitem__ (datasets.py:88-112) when the colour image is larger than the depth image (ScanNet:
+    1296x968 colour, 640x480 depth): colour / 255 in float64, cv2.resize to the depth's size, crop_edge.
+    cv2.resize(INTER_LINEAR) of a float64 image is third-party arithmetic: the opencv-python wheels (x86-64, this
+    container's 4.13 and the reference's environment alike) route it to Intel IPP, whose result this restates bit for
+    bit (found by comparing against cv2 here): weights in float64, a row pass then a column pass, each tap
+    fma(w, b - a, a).  An OpenCV built WITHOUT IPP uses float32 weights (differences up to ~4e-7)."""
+    import numpy as np
+
+    color = color_u8_bgr[:, :, ::-1] / 255.
+    H, W = depth_u16.shape
+    hs, ws = color.shape[:2]
+    x0, x1, fx = _linear_taps(ws, W)
+    y0, y1, fy = _linear_taps(hs, H)
+    rows = sorted(set(y0.tolist()) | set(y1.tolist()))
+    hor = {}
+    for r in rows:
+        hor[r] = np.array([[_fma(fx[c], color[r, x1[c], ch] - color[r, x0[c], ch], color[r, x0[c], ch]) for ch in range(3)]
+                           for c in range(W)])
+    out = np.empty((H, W, 3))
+    for r in range(H):
+        a, b = hor[int(y0[r])], hor[int(y1[r])]
+        for c in range(W):
+            for ch in range(3):
+                out[r, c, ch] = _fma(fy[r], b[c, ch] - a[c, ch], a[c, ch])
+    depth = depth_u16.astype(np.float32) / png_depth_scale
+    color = torch.from_numpy(np.ascontiguousarray(out))
+    depth = torch.from_numpy(depth) * scale
+    if crop_edge > 0:
+        color = color[crop_edge:-crop_edge, crop_edge:-crop_edge]
+        depth = depth[crop_edge:-crop_edge, crop_edge:-crop_edge]
+    return color.contiguous(), depth.contiguous()
+
+
+# ----------------------------------------------------------------------------
+# (f)-2: mesh extraction around the query   (Mesher.py:219-247, cull_mesh.py:58-105)
+# ----------------------------------------------------------------------------
+# skimage.measure.marching_cubes is third party (Lewiner's variant, environment.yaml: scikit-image 0.19.2) and absent
+# here: PARITY UNPINNED against it.  What the reference's mesh and this restatement share by construction is the vertex
+# set: one vertex on every lattice edge whose end values straddle the level, at the linear interpolation point.  The
+# restatement below re-derives a cell's polygons from first principles PER CELL (contour segments on the six faces,
+# chained into loops); it does not read the product's generated case tables, so the two can be compared.
+
+
+def _mc_face_quads():
+    quads = []
+    for a in range(3):
+        u, v = (a + 1) % 3, (a + 2) % 3
+        for side in (0, 1):
+            quad = [(0, 0), (1, 0), (1, 1), (0, 1)]
+            if side == 0:
+                quad = quad[::-1]
+            quads.append([tuple((side if d == a else (bu if d == u else bv)) for d in range(3)) for bu, bv in quad])
+    return quads
+
+
+def marching_cubes_vertices(vol, level, xs, ys, zs):
+    """{lattice edge: world position} of every level crossing; vol[ix, iy, iz].  The vertex set of Mesher.py:219-247."""
+    out = {}
+    P = (np.asarray(xs, np.float64), np.asarray(ys, np.float64), np.asarray(zs, np.float64))
+    for axis in range(3):
+        lo = [slice(None)] * 3
+        hi = [slice(None)] * 3
+        lo[axis], hi[axis] = slice(0, -1), slice(1, None)
+        v0, v1 = vol[tuple(lo)], vol[tuple(hi)]
+        for idx in np.argwhere((v0 < level) != (v1 < level)):
+            i = tuple(int(x) for x in idx)
+            a, b = float(v0[i]), float(v1[i])
+            t = (level - a) / (b - a)
+            p = [float(P[d][i[d]]) for d in range(3)]
+            p[axis] = p[axis] + t * (float(P[axis][i[axis] + 1]) - p[axis])
+            out[(i, axis)] = np.array(p)
+    return out
+
+
+def marching_cubes_loops(vol, level):
+    """Per cell, the closed polygons of the iso-surface as lists of lattice edges ((ix,iy,iz), axis), oriented with the
+    normal towards values >= level; ambiguous faces separate the inside (< level) corners."""
+    quads = _mc_face_quads()
+    nx, ny, nz = vol.shape
+    inside = vol < level
+    loops = {}
+    for cx in range(nx - 1):
+        for cy in range(ny - 1):
+            for cz in range(nz - 1):
+                blk = inside[cx:cx + 2, cy:cy + 2, cz:cz + 2]
+                if blk.all() or not blk.any():
+                    continue
+                nxt = {}
+                for quad in quads:
+                    flags = [bool(blk[c]) for c in quad]
+                    for x in range(4):
+                        if not (flags[x] and not flags[(x + 1) % 4]):
+                            continue
+                        i = x
+                        while not (not flags[(i - 1) % 4] and flags[i]):
+                            i = (i - 1) % 4
+                        i = (i - 1) % 4  # the boundary step that entered this inside arc
+
+                        def edge(c0, c1):
+                            axis = [d for d in range(3) if c0[d] != c1[d]][0]
+                            lo = tuple(min(c0[d], c1[d]) for d in range(3))
+                            return ((cx + lo[0], cy + lo[1], cz + lo[2]), axis)
+
+                        nxt[edge(quad[x], quad[(x + 1) % 4])] = edge(quad[i], quad[(i + 1) % 4])
+                cell, seen = [], set()
+                for s in nxt:
+                    if s in seen:
+                        continue
+                    loop, e = [], s
+                    while e not in seen:
+                        seen.add(e)
+                        loop.append(e)
+                        e = nxt[e]
+                    cell.append(loop)
+                loops[(cx, cy, cz)] = cell
+    return loops
+
+
+def cull_mask(points, depth, c2w, K, H, W, truncation, eval_rec):
+    """Visibility of mesh vertices in one frame, cull_mesh.py:58-100 (torch ops as there)."""
+    fx, fy, cx, cy = K
+    w2c = torch.inverse(c2w)
+    Km = torch.tensor([[fx, 0.0, cx], [0.0, fy, cy], [0.0, 0.0, 1.0]], dtype=torch.float32)
+    ones = torch.ones_like(points[:, 0]).reshape(-1, 1)
+    homo = torch.cat([points, ones], dim=1).reshape(-1, 4, 1).float()
+    cam = (w2c @ homo)[:, :3]
+    cam[:, 0] *= -1
+    uv = Km @ cam.float()
+    z = uv[:, -1:] + 1e-5
+    uv = (uv[:, :2] / z).squeeze(-1)
+    grid = uv[None, None].clone()
+    grid[..., 0] = grid[..., 0] / W
+    grid[..., 1] = grid[..., 1] / H
+    grid = 2 * grid - 1
+    ds = F.grid_sample(depth[None, None], grid, padding_mode="zeros", align_corners=True).squeeze()
+    front = (0 <= -z[:, 0, 0]) & (uv[:, 0] < W) & (uv[:, 0] > 0) & (uv[:, 1] < H) & (uv[:, 1] > 0)
+    if eval_rec:
+        return (ds + truncation >= -z[:, 0, 0]) & front
+    return front

@@ -174,6 +174,24 @@ def test_ingest_frame_bit_exact():
     assert torch.equal(c2.cpu(), oc) and torch.equal(d2.cpu(), od)
 
 
+def test_ingest_scannet_shaped_frame_bit_exact():
+    """eslam_ingest_frame_resized == the reference's ScanNet loader (colour 2x the depth's size, resized by cv2.resize
+    on the float64 image, crop_edge) on the fixture frame, bit for bit; and the oracle on a second, odd-sized case."""
+    from myslam_b200.ingest import ingest_frame
+
+    d = load_npz("ingest_scannet.npz")
+    color, depth = ingest_frame(d["bgr"], d["depth_u16"], float(d["png_depth_scale"]), int(d["crop_edge"]), DEV)
+    assert color.dtype == torch.float64 and depth.dtype == torch.float32
+    assert torch.equal(depth.cpu(), torch.from_numpy(d["depth"]))
+    assert torch.equal(color.cpu(), torch.from_numpy(d["color"]))
+    rng = np.random.default_rng(5)
+    bgr = rng.integers(0, 256, size=(61, 83, 3), dtype=np.uint8)
+    dep = rng.integers(0, 65536, size=(29, 40), dtype=np.uint16)
+    c2, d2 = ingest_frame(bgr, dep, 1000.0, 1, DEV)
+    oc, od = O.ingest_frame_resized(bgr, dep, 1000.0, 1)
+    assert torch.equal(c2.cpu(), oc) and torch.equal(d2.cpu(), od)
+
+
 def test_grid_query_with_convex_mesh_bound():
     """Mesher.get_mesh forces sdf = -1 outside the convex hull of the observed region (Mesher.py:206-217); here the
     half-space test runs inside the grid query.  Against the plain query + a float64 half-space mask, away from the

@@ -162,3 +162,13 @@ def test_ingest_golden():
     color, depth = O.ingest_frame(d["bgr"], d["depth_u16"], float(d["png_depth_scale"]), int(d["crop_edge"]))
     assert color.dtype == torch.float64 and depth.dtype == torch.float32
     assert torch.equal(color, torch.from_numpy(d["color"])) and torch.equal(depth, torch.from_numpy(d["depth"]))
+
+
+def test_ingest_scannet_golden():
+    """Oracle restatement of the ScanNet-shaped loader path (datasets.py:88-112 with cv2.resize of the float64 colour
+    image to the depth's size) against what the reference's ScanNet loader returned (make_golden_ingest_scannet.py)."""
+    d = load_npz("ingest_scannet.npz")
+    assert d["bgr"].shape[0] > d["depth_u16"].shape[0] and d["bgr"].shape[1] > d["depth_u16"].shape[1]
+    color, depth = O.ingest_frame_resized(d["bgr"], d["depth_u16"], float(d["png_depth_scale"]), int(d["crop_edge"]))
+    assert color.dtype == torch.float64 and depth.dtype == torch.float32
+    assert torch.equal(color, torch.from_numpy(d["color"])) and torch.equal(depth, torch.from_numpy(d["depth"]))
