@@ -93,14 +93,16 @@ def test_get_mesh_on_the_golden_scene_and_vertex_colours():
     fld, d = golden_field(), load_npz("mesh.npz")
     planes, dec = to_device_scene(fld)
     res = float(d["resolution"])
-    out = get_mesh(planes, dec, [], None, d["mc_bound"], res, level_set=0.0, bound=fld.bound)
     axes = grid_axes(d["mc_bound"], res)
     sdf = query_grid_sdf(planes, dec, axes, fld.bound)
+    # the fixture map is untrained (its sdf does not cross 0): extract the level set at the median in-bound value
+    level = float(sdf[sdf > -1].median())
+    out = get_mesh(planes, dec, [], None, d["mc_bound"], res, level_set=level, bound=fld.bound)
     nx, ny, nz = (len(a) for a in axes)
     vol = sdf.cpu().numpy().reshape(ny, nx, nz).transpose(1, 0, 2).astype(np.float64)
-    pos = O.marching_cubes_vertices(vol, 0.0, *[a.astype(np.float32).astype(np.float64) for a in axes])
+    pos = O.marching_cubes_vertices(vol, level, *[a.astype(np.float32).astype(np.float64) for a in axes])
     assert out["vertices"].shape[0] == len(pos) > 100
-    loops = O.marching_cubes_loops(vol, 0.0)
+    loops = O.marching_cubes_loops(vol, level)
     assert out["faces"].shape[0] == sum(len(l) - 2 for cell in loops.values() for l in cell)
     raw = O.query_points(fld, out["vertices"].cpu())
     assert rel_err(out["vertex_colors"], raw[:, :3]) < 1e-4
