@@ -260,6 +260,34 @@ def extras(scene, rnd, spec, dev, rank, world, dist_on, poses, deps, hbm_peak):
     del buf
     if rank != 0:
         return out
+    # ---- marching cubes over the same 1 cm lattice on the device (Mesher.py:219-247).  The synthetic map is untrained
+    # (its sdf has no surface), so the volume here is the analytic signed distance of the box room the frames were
+    # rendered from: a surface of the size a trained room0 map has.
+    try:
+        from myslam_b200.mesher import marching_cubes
+
+        xs, ys, zs = (torch.from_numpy(a).float().to(dev) for a in axes)
+        room = torch.tensor(spec["room"], dtype=torch.float32, device=dev)
+        dx = torch.minimum(xs - room[0, 0], room[0, 1] - xs)[None, :, None]
+        dy = torch.minimum(ys - room[1, 0], room[1, 1] - ys)[:, None, None]
+        dz = torch.minimum(zs - room[2, 0], room[2, 1] - zs)[None, None, :]
+        vol = torch.minimum(torch.minimum(dx.expand(len(ys), len(xs), len(zs)), dy.expand(len(ys), len(xs), len(zs))),
+                            dz.expand(len(ys), len(xs), len(zs))).contiguous().reshape(-1)  # (iy*nx + ix)*nz + iz
+        del dx, dy, dz
+        res_mc = {}
+        ms_soup = time_region(lambda: res_mc.__setitem__("m", marching_cubes(vol, axes, 0.0, weld=False)), 3, 1, False) / 3
+        ms_weld = time_region(lambda: res_mc.__setitem__("m", marching_cubes(vol, axes, 0.0, weld=True)), 2, 1, False) / 2
+        v, f = res_mc["m"]
+        out["mesh_extract"] = {"ms_marching_cubes": ms_soup, "ms_with_welding": ms_weld, "triangles": int(f.shape[0]),
+                               "vertices": int(v.shape[0]), "cells": (len(xs) - 1) * (len(ys) - 1) * (len(zs) - 1),
+                               "GBps_volume_read": vol.numel() * 4 / (ms_soup * 1e-3) / 1e9,
+                               "what": "device marching cubes over the 990x680x490 lattice (two passes over the "
+                                       "1.32 GB volume, which never leaves HBM; the reference copies it to the host "
+                                       "for skimage): count + emit kernels; welding = torch.unique on the vertices' "
+                                       "lattice-edge keys"}
+        del vol, v, f, res_mc
+    except Exception as exc:  # noqa: BLE001
+        out["mesh_extract"] = {"error": repr(exc)}
     # ---- full-frame inference (Renderer.render_img, 1200x680 = 816 k rays, one pass)
     fn = lambda: rnd.render_img(scene.all_planes, scene.decoders, poses[0], spec["truncation"], dev, gt_depth=deps[0])
     ms = time_region(fn, 3, 1, False) / 3

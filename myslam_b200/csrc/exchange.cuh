@@ -193,7 +193,7 @@ __global__ void __launch_bounds__(EXCH_THREADS) k_gq_push(const __grid_constant_
 
 // WMAX: compile-time bound of the world size (2, 4 or 8).  Grid = the tiles this rank owns.
 template <int WMAX>
-__global__ void __launch_bounds__(QA_THREADS, 4) k_q_adam_exchange(const __grid_constant__ QExchArgs a) {
+__global__ void __launch_bounds__(QA_THREADS, 3) k_q_adam_exchange(const __grid_constant__ QExchArgs a) {
   __shared__ SmemQAdam sm;
   const int rank = a.ps.rank, world = a.ps.world;
   const bool leader = blockIdx.x == 0;

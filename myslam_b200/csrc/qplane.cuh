@@ -127,7 +127,7 @@ struct SmemFwdQ {
 //   A  the tile's gradient rows (16 KB... 8 KB), its texels (16 KB) and `touched` bytes go to shared memory, all loads
 //      in flight at once; on several GPUs the rows are the sum of the local image and the peers' staged slices
 //   B  thread (texel, c4): plane gradient of its four channels (64 FMA against W1 in shared memory), Adam, stores --
-//      only for ACTIVE texels (non-zero row now, or non-zero moments from an earlier iteration: exact skip as in
+//      the moments were requested in phase A already -- only for ACTIVE texels (non-zero row now, or non-zero moments from an earlier iteration: exact skip as in
 //      k_adam); on several GPUs the new texel goes to every rank's arena (P2P stores)
 //   C  dW1 of the tile = G^T P, a 16 x 32 x 128 contraction on the tensor cores (split-bf16 mma, render.cuh), one
 //      16-byte reduction per lane into the gradient arena's decoder block
@@ -212,7 +212,24 @@ __device__ __forceinline__ void q_adam_tile(const QAdamArgs& a, int unit, SmemQA
   const long long tbase = (long long)a.qg.t0[g] + tl0;
   const int tid = threadIdx.x, lane = tid & 31;
   const float4 z4 = f4_zero();
-  // ---- phase A
+  // ---- phase A.  The moments of the thread's four (texel, c4) items are requested here already, for the texels whose
+  // `touched` flag is up: a texel that has never had a gradient has m = v = 0 and needs no load, so phase B's only
+  // dependent round trip disappears behind the staging of the tile.
+  float4 m[4], v[4];
+  {
+    bool fl[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const int t = (tid >> 3) + k * 32;
+      fl[k] = t < cnt && a.touched[tbase + t] != 0;
+    }
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const long long at = (tbase + (tid >> 3) + k * 32) * 8 + (tid & 7);
+      m[k] = fl[k] ? a.m4[at] : z4;
+      v[k] = fl[k] ? a.v4[at] : z4;
+    }
+  }
 #pragma unroll
   for (int k = 0; k < QA_TILE * 4 / QA_THREADS; ++k) {
     const int i = tid + k * QA_THREADS, t = i >> 2, c = i & 3;
@@ -267,22 +284,10 @@ __device__ __forceinline__ void q_adam_tile(const QAdamArgs& a, int unit, SmemQA
   {
     const int c4 = tid & 7;
     const float ss = (g >> 1) ? a.step_rgb : a.step_sdf;
-    float4 m[4], v[4];
-    bool on[4];
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
       const int t = (tid >> 3) + k * 32;
-      on[k] = t < cnt && sm.act[t];
-      if (on[k]) {
-        const long long at = (tbase + t) * 8 + c4;
-        m[k] = a.m4[at];
-        v[k] = a.v4[at];
-      }
-    }
-#pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      const int t = (tid >> 3) + k * 32;
-      if (!on[k]) continue;
+      if (!(t < cnt && sm.act[t])) continue;
       const long long at = (tbase + t) * 8 + c4;
       float4 p = sm.sP[t_slot(t, c4)];
       float4 gr = z4;
@@ -328,7 +333,7 @@ __device__ __forceinline__ void q_adam_tile(const QAdamArgs& a, int unit, SmemQA
   }
 }
 
-__global__ void __launch_bounds__(QA_THREADS, 4) k_q_adam_planes(const __grid_constant__ QAdamArgs a) {
+__global__ void __launch_bounds__(QA_THREADS, 3) k_q_adam_planes(const __grid_constant__ QAdamArgs a) {
   __shared__ SmemQAdam sm;
   q_adam_tile<1>(a, blockIdx.x, sm);
 }
