@@ -228,6 +228,69 @@ class OracleRun:
                                                  iters, t["lr_T"], t["lr_R"], self.draws)) / iters
 
 
+class ReferenceRun:
+    """The UNMODIFIED reference (MohammadJohari/myslam, Python) on the host cores, when its sources are reachable
+    (ESLAM_REFERENCE or /root/reference: the build container; the GPU box does not have them and falls back to the
+    oracle port).  Its Mapper / Tracker are instantiated with object.__new__ and given exactly the attributes
+    optimize_mapping / optimize_tracking read (as tests/golden/make_golden.py does); import-only stand-ins for
+    colorama / matplotlib / trimesh / open3d / skimage and the restated pytorch3d.transforms come from oracle/standins."""
+
+    @staticmethod
+    def path():
+        p = os.environ.get("ESLAM_REFERENCE", "/root/reference")
+        return p if os.path.exists(os.path.join(p, "src", "Mapper.py")) else None
+
+    def __init__(self, spec, n_frames, seed=0):
+        import types
+
+        for q in (os.path.join(ROOT, "oracle"), os.path.join(ROOT, "oracle", "standins"), self.path()):
+            if q not in sys.path:
+                sys.path.insert(0, q)
+        import eslam_oracle as O
+        from src.Mapper import Mapper
+        from src.networks.decoders import Decoders
+        from src.utils.Renderer import Renderer
+
+        self.O, self.spec = O, spec
+        gen = torch.Generator().manual_seed(seed)
+        bound = O.rounded_bound(spec["bound"], spec["bound_dividable"])
+        fld = O.make_field(bound, spec["planes_res"], spec["c_planes_res"], generator=gen)
+        poses, cols, deps = build_inputs(spec, "cpu", n_frames, seed)
+        dec = Decoders(c_dim=32, truncation=spec["truncation"], learnable_beta=True)
+        dec.load_state_dict({**{k: v.clone() for k, v in fld.dec.items()}, "beta": fld.beta.clone()})
+        dec.bound = bound.clone()
+        cam = dict(H=spec["H"], W=spec["W"], fx=spec["fx"], fy=spec["fy"], cx=spec["cx"], cy=spec["cy"])
+        es = types.SimpleNamespace(bound=bound.clone(), device="cpu", **cam)
+        rnd = Renderer({"rendering": {"perturb": True, "n_stratified": spec["n_stratified"],
+                                      "n_importance": spec["n_importance"]}, "scale": 1}, es)
+        m = spec["mapping"]
+        mp = object.__new__(Mapper)
+        (mp.planes_xy, mp.planes_xz, mp.planes_yz, mp.c_planes_xy, mp.c_planes_xz, mp.c_planes_yz) = \
+            tuple([p.clone() for p in g] for g in fld.planes)
+        mp.device, mp.bound, mp.renderer, mp.decoders, mp.truncation = "cpu", bound.clone(), rnd, dec, spec["truncation"]
+        for k, v in cam.items():
+            setattr(mp, k, v)
+        w = O.MAP_W
+        mp.w_sdf_fs, mp.w_sdf_center, mp.w_sdf_tail, mp.w_depth, mp.w_color = w.fs, w.center, w.tail, w.depth, w.color
+        mp.cfg = {"mapping": {"lr": dict(m["lr"])}}
+        mp.keyframe_selection_method, mp.mapping_window_size, mp.mapping_pixels = "global", n_frames, m["pixels"]
+        mp.joint_opt, mp.joint_opt_cam_lr, mp.no_vis_on_first_frame = True, m["joint_opt_cam_lr"], True
+        mp.visualizer = types.SimpleNamespace(save_imgs=lambda *a, **k: None)
+        self.kf = [{"gt_c2w": poses[k], "idx": torch.tensor(4 * k), "color": cols[k], "depth": deps[k],
+                    "est_c2w": poses[k].clone()} for k in range(n_frames - 1)]
+        mp.keyframe_dict = self.kf
+        self.mp, self.cur = mp, (cols[-1], deps[-1], poses[-1])
+        self.kf_list = list(range(0, 4 * (n_frames - 1), 4))
+
+    def run_mapping(self, iters):
+        """seconds per iteration of one Mapper.optimize_mapping call of `iters` iterations (Mapper.py:211-364)."""
+        col, dep, c2w = self.cur
+        t0 = time.perf_counter()
+        self.mp.optimize_mapping(iters, 1.0, torch.tensor(4 * len(self.kf) + 4), col, dep, c2w.clone(), self.kf,
+                                 self.kf_list, c2w.clone())
+        return (time.perf_counter() - t0) / iters
+
+
 def extras(scene, rnd, spec, dev, rank, world, dist_on, poses, deps, hbm_peak):
     """Secondary workloads of BASELINE.json (configs 3 and 5) and the full-frame render, each a few launches."""
     import torch.distributed as dist
@@ -362,7 +425,15 @@ def run_reference(args, spec):
     torch.set_num_threads(cores)
     m = spec["mapping"]
     n_frames = m["mapping_window_size"]
+    kind = "port"
     run = OracleRun(spec, n_frames)
+    if ReferenceRun.path():
+        try:
+            ref = ReferenceRun(spec, n_frames)
+            ref.run_tracking = run.run_tracking  # the tracking extra stays on the port
+            run, kind = ref, "reference"
+        except Exception as exc:  # noqa: BLE001
+            print(f"reference sources found but not usable ({exc!r}); timing the oracle port", file=sys.stderr)
     iters = m["iters"]
     for _ in range(min(max(args.warmup, 1), 1)):
         run.run_mapping(2)
@@ -378,9 +449,11 @@ def run_reference(args, spec):
         "ms_per_step": 1e3 * s_iter * iters, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
         "config": workload_config(1, m["pixels"] // n_frames, n_frames, "none (host cores)"),
-        "cpu_baseline": {"value": value, "unit": "rays*iters/s", "cores": cores, "kind": "port",
+        "cpu_baseline": {"value": value, "unit": "rays*iters/s", "cores": cores, "kind": kind,
                          "sample": f"{len(per_iter)} optimize_mapping-shaped calls of {iters} iterations x 4000 rays "
-                                   f"(oracle port of the reference's PyTorch path, torch CPU, {cores} threads)"},
+                                   + ("(the unmodified reference's Mapper.optimize_mapping" if kind == "reference"
+                                      else "(oracle port of the reference's PyTorch path") +
+                                   f", torch CPU, {cores} threads)"},
         "e2e": {"value": value, "unit": "rays*iters/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "tracking": {"value": 1.0 / (trk * spec["tracking"]["iters"]), "unit": "frames/s",
                      "ms_per_iter": 1e3 * trk},

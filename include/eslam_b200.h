@@ -161,9 +161,12 @@ int eslam_grid_sdf_separable(const eslam_field_t* field_host, const float* arena
  * evaluates [start, start+count): three 64-byte reads, 32 adds and the 16 -> 16 -> 1 tail per voxel.  Values agree with
  * eslam_grid_sdf / _hull to a few ulp of the first layer's pre-activation (re-associated sum: NOT bit-identical;
  * the tests hold 1e-5 against the direct form and 1e-4 against the reference).  n_planes may be 0.  The faces must
- * be recomputed after the parameters change; layers 2-3 read the decoders bound by eslam_bind_decoders. */
+ * be recomputed after the parameters change; layers 2-3 read the decoders bound by eslam_bind_decoders.
+ * [iy0, iy1): the lattice rows whose xy / yz face entries are computed (a rank that queries the flat range of a y-slab
+ * needs only those; 0, ny for everything); the xz face is always computed whole. */
 int eslam_grid_preact(const eslam_field_t* field_host, const float* arena, const float* xs, const float* ys,
-                      const float* zs, int nx, int ny, int nz, float* pxy, float* pxz, float* pyz, eslam_stream_t s);
+                      const float* zs, int nx, int ny, int nz, int iy0, int iy1, float* pxy, float* pxz, float* pyz,
+                      eslam_stream_t s);
 int eslam_grid_sdf_factored(const eslam_field_t* field_host, const float* xs, const float* ys, const float* zs, int nx,
                             int ny, int nz, int64_t start, int64_t count, const float* pxy, const float* pxz,
                             const float* pyz, const float* hull_planes, int n_planes, float* sdf, eslam_stream_t s);

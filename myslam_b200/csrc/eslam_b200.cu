@@ -256,8 +256,10 @@ int eslam_grid_sdf_separable(const eslam_field_t* f, const float* arena, const f
 }
 
 int eslam_grid_preact(const eslam_field_t* f, const float* arena, const float* xs, const float* ys, const float* zs,
-                      int nx, int ny, int nz, float* pxy, float* pxz, float* pyz, eslam_stream_t s) {
-  REQUIRE(f && arena && xs && ys && zs && pxy && pxz && pyz && nx > 0 && ny > 0 && nz > 0, "eslam_grid_preact");
+                      int nx, int ny, int nz, int iy0, int iy1, float* pxy, float* pxz, float* pyz, eslam_stream_t s) {
+  REQUIRE(f && arena && xs && ys && zs && pxy && pxz && pyz && nx > 0 && ny > 0 && nz > 0 && iy0 >= 0 && iy1 > iy0 &&
+              iy1 <= ny,
+          "eslam_grid_preact");
   REQUIRE(nx <= 32767 && ny <= 32767 && nz <= 32767, "eslam_grid_preact(lattice size)");
   GridPreArgs a;
   memset(&a, 0, sizeof(a));
@@ -265,10 +267,13 @@ int eslam_grid_preact(const eslam_field_t* f, const float* arena, const float* x
   if (rc) return fail(rc, "eslam_grid_preact(field)");
   a.arena4 = reinterpret_cast<const float4*>(arena);
   a.w1 = arena + f->dec_offset + S_W1;
-  const float* us[3] = {xs, xs, ys};
-  const float* vs[3] = {ys, zs, zs};
-  const int na[3] = {nx, nx, ny}, nb[3] = {ny, nz, nz}, ua[3] = {0, 0, 1}, va[3] = {1, 2, 2};
-  float* out[3] = {pxy, pxz, pyz};
+  // rows of y in [iy0, iy1) only: the xy face out[iy][ix][4] and the yz face out[iy][4][iz] are both y-major, so a
+  // row range is the same kernel on a shorter face (shifted coordinate and output pointers); the xz face is whole
+  const int nyr = iy1 - iy0;
+  const float* us[3] = {xs, xs, ys + iy0};
+  const float* vs[3] = {ys + iy0, zs, zs};
+  const int na[3] = {nx, nx, nyr}, nb[3] = {nyr, nz, nz}, ua[3] = {0, 0, 1}, va[3] = {1, 2, 2};
+  float* out[3] = {pxy + (long long)iy0 * nx * 16, pxz, pyz + (long long)iy0 * nz * 16};
   for (int p = 0; p < 3; ++p) {
     a.us = us[p];
     a.vs = vs[p];

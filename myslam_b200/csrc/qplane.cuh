@@ -435,20 +435,35 @@ __global__ void __launch_bounds__(NP) k_render_fwd_q(const __grid_constant__ Ren
     a.act4[(long long)ray * S + k] = make_float4(sm.c[0][q], sm.c[1][q], sm.c[2][q], __uint_as_float(mask_s));
     a.actm[(long long)ray * S + k] = mask_c;
   }
-  __syncthreads();
-  float T = 1.0f;
-  for (int j = 0; j < k; ++j) T *= sm.one[rl * S + j];
-  sm.w[q] = valid ? alpha * T : 0.f;
+  sm.w[q] = valid ? alpha : 0.f;
   if (valid && a.sdf) a.sdf[(long long)ray * S + k] = sdf;
   __syncthreads();
-  if (valid && k < 4) {
-    const float* v = (k == 0) ? sm.z : sm.c[k - 1];
-    float acc = 0.f;
-    for (int j = 0; j < S; ++j) acc = fmaf(sm.w[rl * S + j], v[rl * S + j], acc);
-    if (k == 0)
-      a.depth[ray] = acc;
-    else
-      a.rgb[ray * 3 + (k - 1)] = acc;
+  // compositing (Renderer.py:140-147), one WARP per ray: lane l holds samples l and l + 32, the transmittance is a
+  // prefix product by shuffles
+  const int warp = q >> 5, lane = q & 31;
+  for (int r2 = warp; r2 < rays_here; r2 += NP / 32) {
+    const int j0 = r2 * S + lane, j1 = j0 + 32;
+    const bool v0 = lane < S, v1 = lane + 32 < S;
+    float inc0 = v0 ? sm.one[j0] : 1.f, inc1 = v1 ? sm.one[j1] : 1.f;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      const float t0 = __shfl_up_sync(0xffffffffu, inc0, d), t1 = __shfl_up_sync(0xffffffffu, inc1, d);
+      if (lane >= d) {
+        inc0 *= t0;
+        inc1 *= t1;
+      }
+    }
+    const float tot0 = __shfl_sync(0xffffffffu, inc0, 31);
+    float T0 = __shfl_up_sync(0xffffffffu, inc0, 1), T1 = __shfl_up_sync(0xffffffffu, inc1, 1);
+    if (lane == 0) T0 = T1 = 1.f;
+    T1 *= tot0;
+    const float w0 = v0 ? sm.w[j0] * T0 : 0.f, w1 = v1 ? sm.w[j1] * T1 : 0.f;
+    float rv[4];
+    rv[0] = warp_sum(fmaf(w0, v0 ? sm.z[j0] : 0.f, w1 * (v1 ? sm.z[j1] : 0.f)));
+#pragma unroll
+    for (int c = 0; c < 3; ++c) rv[1 + c] = warp_sum(fmaf(w0, v0 ? sm.c[c][j0] : 0.f, w1 * (v1 ? sm.c[c][j1] : 0.f)));
+    if (lane == 0) a.depth[ray0 + r2] = rv[0];
+    if (lane >= 1 && lane < 4) a.rgb[(ray0 + r2) * 3 + (lane - 1)] = lane == 1 ? rv[1] : (lane == 2 ? rv[2] : rv[3]);
   }
 }
 

@@ -60,7 +60,7 @@ def map_window(store: FieldStore, ws: Workspace, sc: StepCfg, c2ws, gt_colors, g
 def keyframe_selection_overlap(self, gt_color, gt_depth, c2w, num_keyframes, num_samples=8, num_rays=50):
     """Keyframes whose frusta see the current view's surface (reference Mapper.py:146-209): one kernel projects the
     50 x 8 sample points into every keyframe (eslam_keyframe_overlap); the pixel draw (randint, common.py:108),
-    the nonzero + CPU randperm pick (Mapper.py:205-209) and the returned list are the reference's."""
+    the CPU randperm pick (Mapper.py:205-209) and the returned list are the reference's."""
     device = self.device
     draws = getattr(self, "draws", None) or TorchDraws(device)
     idx = draws.randint(self.H * self.W, num_rays)
@@ -77,9 +77,12 @@ def keyframe_selection_overlap(self, gt_color, gt_depth, c2w, num_keyframes, num
     call("eslam_keyframe_overlap", C.byref(cam), ptr(cur), ptr(depth), ptr(idx), num_rays,
          ptr(linspace_table(num_samples, device)), num_samples, ptr(kf_c2w), K, ptr(inside), ptr(n_pts), stream())
     self._last_overlap = (inside, n_pts)  # percent_inside = inside / n_pts (tests)
-    sel = torch.nonzero(inside).squeeze(-1)
+    # Mapper.py:205-209 (nonzero, CPU randperm, first num_keyframes, .cpu()) with ONE device->host copy: the K
+    # per-keyframe counts (4 K bytes); the selection and the permutation (torch's CPU generator, as the reference) then
+    # run on the host, where the list is needed anyway.  The reference syncs twice (nonzero, .cpu()).
+    sel = torch.nonzero(inside.cpu()).squeeze(-1)
     sel = sel[torch.randperm(sel.shape[0])[:num_keyframes]]
-    return list(sel.cpu().numpy())
+    return list(sel.numpy())
 
 
 def _device_frame(self, t: torch.Tensor, dtype) -> torch.Tensor:

@@ -86,8 +86,12 @@ def query_grid_sdf(all_planes, decoders, axes, bound=None, start=0, count=None, 
     if factored and fits:
         mode = "factored"
         faces = [torch.empty(n, dtype=torch.float32, device=dev) for n in (ny * nx * 16, nx * nz * 16, ny * nz * 16)]
-        call("eslam_grid_preact", store.ref(), ptr(store.arena), ptr(xs), ptr(ys), ptr(zs), nx, ny, nz, ptr(faces[0]),
-             ptr(faces[1]), ptr(faces[2]), stream())
+        # only the lattice rows this flat range touches (flat = (iy*nx + ix)*nz + iz): a rank of a sharded query
+        # resamples 1/world of the xy and yz faces instead of all of them
+        iy0 = (start // nz) // nx
+        iy1 = ((start + max(count, 1) - 1) // nz) // nx + 1
+        call("eslam_grid_preact", store.ref(), ptr(store.arena), ptr(xs), ptr(ys), ptr(zs), nx, ny, nz, iy0, iy1,
+             ptr(faces[0]), ptr(faces[1]), ptr(faces[2]), stream())
     elif separable and fits:
         mode = "separable"
         faces = [torch.empty(b, a, 64, dtype=torch.float32, device=dev) for a, b in ((nx, ny), (nx, nz), (ny, nz))]
