@@ -442,6 +442,14 @@ int eslam_exchange_flag_words(void);
 int eslam_exchange_counters(const eslam_peers_t* peers_host, const int32_t* counters, int32_t* const* pub_host,
                             int n, int32_t* norm, eslam_stream_t s);
 
+/* aux_sum[i] = sum over ranks of aux_local[i] (float, the [frames][12] pose-gradient block) and auxd_sum likewise
+ * (double, the loss terms): published into *_pub_host[rank] (alternate between two copies from call to call), handshake,
+ * summed in rank order on every rank, local blocks zeroed.  One CTA: meant for a side stream, so the pose step and the
+ * next iteration's ray sampling overlap eslam_q_adam_exchange. */
+int eslam_exchange_aux(const eslam_peers_t* peers_host, float* aux_local, float* const* aux_pub_host, float* aux_sum,
+                       int n_aux, double* auxd_local, double* const* auxd_pub_host, double* auxd_sum, int n_auxd,
+                       eslam_stream_t s);
+
 /* Floats of the gradient-image staging block of one rank for `world` ranks. */
 int64_t eslam_q_exchange_stage_floats(const eslam_field_t* field_host, int world);
 

@@ -108,6 +108,7 @@ PROTOTYPES = {
     "eslam_mc_emit": [_P, _P, _P, _P, _I, _I, _I, _D, _P, _P, _P, _P, _P, _P],
     "eslam_cull_frame": [_P, _L, _P, _P, _CP, _D, _I, _P, _P],
     "eslam_exchange_counters": [C.POINTER(Peers), _P, C.POINTER(C.c_void_p), _I, _P, _P],
+    "eslam_exchange_aux": [C.POINTER(Peers), _P, C.POINTER(C.c_void_p), _P, _I, _P, C.POINTER(C.c_void_p), _P, _I, _P],
     "eslam_q_adam_exchange": [C.POINTER(Peers), _FP, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), _P, _P, _P, _P, _P, _P,
                               _D, _D, _D, _I, _D, _D, _D, C.POINTER(C.c_void_p), _P, C.POINTER(C.c_void_p), _P, _I, _P,
                               C.POINTER(C.c_void_p), _P, _I, _P],

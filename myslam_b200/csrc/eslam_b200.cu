@@ -932,6 +932,29 @@ static long long q_exchange_slices(const QGroups& qg, int world, long long* lo4)
   return (smax + 31) & ~31ll;
 }
 
+int eslam_exchange_aux(const eslam_peers_t* peers, float* aux_local, float* const* aux_pub, float* aux_sum, int n_aux,
+                       double* auxd_local, double* const* auxd_pub, double* auxd_sum, int n_auxd, eslam_stream_t s) {
+  REQUIRE(n_aux >= 0 && n_auxd >= 0 && (n_aux == 0 || (aux_local && aux_pub && aux_sum)) &&
+              (n_auxd == 0 || (auxd_local && auxd_pub && auxd_sum)),
+          "eslam_exchange_aux");
+  AuxExchArgs a;
+  memset(&a, 0, sizeof(a));
+  if (fill_peers(a.ps, peers)) return fail(ESLAM_EINVAL, "eslam_exchange_aux(peers)");
+  for (int r = 0; r < a.ps.world; ++r) {
+    if (n_aux) a.aux_pub[r] = aux_pub[r];
+    if (n_auxd) a.auxd_pub[r] = auxd_pub[r];
+  }
+  a.aux_local = aux_local;
+  a.aux_sum = aux_sum;
+  a.n_aux = n_aux;
+  a.auxd_local = auxd_local;
+  a.auxd_sum = auxd_sum;
+  a.n_auxd = n_auxd;
+  k_exchange_aux<<<1, 256, 0, S_(s)>>>(a);
+  CHECK_LAUNCH("eslam_exchange_aux");
+  return 0;
+}
+
 int64_t eslam_q_exchange_stage_floats(const eslam_field_t* f, int world) {
   if (!f || world < 1 || world > MAX_PEERS) return 0;
   QGroups qg;

@@ -116,6 +116,58 @@ __global__ void __launch_bounds__(32) k_exchange_counters(const __grid_constant_
   }
 }
 
+// ---- small replicated sums on their own (pose gradients, loss terms): publish, handshake, add in rank order, clear the
+//      local block.  One CTA; used on a side stream so that the pose step and the next iteration's ray sampling need
+//      not wait for the plane exchange.
+struct AuxExchArgs {
+  PeerSync ps;
+  float* aux_local;
+  float* aux_pub[MAX_PEERS];
+  float* aux_sum;
+  int n_aux;
+  double* auxd_local;
+  double* auxd_pub[MAX_PEERS];
+  double* auxd_sum;
+  int n_auxd;
+};
+
+constexpr int SLOT_AUX = 3;
+
+__global__ void __launch_bounds__(256) k_exchange_aux(const __grid_constant__ AuxExchArgs a) {
+  const int rank = a.ps.rank, world = a.ps.world;
+  for (int t = threadIdx.x; t < a.n_aux; t += 256) {
+    a.aux_pub[rank][t] = a.aux_local[t];
+    a.aux_local[t] = 0.f;
+  }
+  for (int t = threadIdx.x; t < a.n_auxd; t += 256) {
+    a.auxd_pub[rank][t] = a.auxd_local[t];
+    a.auxd_local[t] = 0.0;
+  }
+  peer_barrier(a.ps, SLOT_AUX);
+  for (int t = threadIdx.x; t < a.n_aux; t += 256) {
+    float x[MAX_PEERS];
+#pragma unroll
+    for (int p = 0; p < MAX_PEERS; ++p)
+      if (p < world) asm volatile("ld.relaxed.sys.global.f32 %0, [%1];" : "=f"(x[p]) : "l"(a.aux_pub[p] + t) : "memory");
+    float acc = 0.f;
+#pragma unroll
+    for (int p = 0; p < MAX_PEERS; ++p)
+      if (p < world) acc += x[p];
+    a.aux_sum[t] = acc;
+  }
+  for (int t = threadIdx.x; t < a.n_auxd; t += 256) {
+    double x[MAX_PEERS];
+#pragma unroll
+    for (int p = 0; p < MAX_PEERS; ++p)
+      if (p < world) asm volatile("ld.relaxed.sys.global.f64 %0, [%1];" : "=d"(x[p]) : "l"(a.auxd_pub[p] + t) : "memory");
+    double acc = 0.0;
+#pragma unroll
+    for (int p = 0; p < MAX_PEERS; ++p)
+      if (p < world) acc += x[p];
+    a.auxd_sum[t] = acc;
+  }
+}
+
 // ---- reduce-scatter of the gradient images + plane Adam + all-gather, then the decoders' replicated step ----------
 // The mapping backward (qbwd.cuh) leaves a rank's plane gradients as 16-channel gradient images (13.5 MB for room0:
 // half of a parameter-form gradient arena) and its decoder gradients in the gradient arena's decoder block.

@@ -93,6 +93,11 @@ class PeerExchange(MappingExchange):
         o += 2 * _lib.N_COUNTERS
         self.off_dec = [o, o + _lib.DEC_FLOATS]  # published decoder gradients, two copies
         o += 2 * _lib.DEC_FLOATS
+        # reduce_small() publishes through its own two copies (its calls interleave with adam_exchange's on another stream)
+        self.off_pose_s = [o, o + pose_blk]
+        o += 2 * pose_blk
+        self.off_loss_s = [o, o + 2 * _lib.N_LOSS]
+        o += 4 * _lib.N_LOSS
         self.off_flags = o
         total = o + flag_words
         grp = group if group is not None else dist.group.WORLD
@@ -121,6 +126,8 @@ class PeerExchange(MappingExchange):
         self._loss = [table(o_) for o_ in self.off_loss]
         self._cnt = [table(o_) for o_ in self.off_cnt]
         self._dec = [table(o_) for o_ in self.off_dec]
+        self._pose_s = [table(o_) for o_ in self.off_pose_s]
+        self._loss_s = [table(o_) for o_ in self.off_loss_s]
         self.peers = _lib.Peers()
         self.peers.rank, self.peers.world, self.peers.epoch, self.peers.adam_seq = self.rank, self.world, 0, 0
         for r in range(self.world):
@@ -133,6 +140,7 @@ class PeerExchange(MappingExchange):
         self.pose_sum = torch.zeros(frames, 12, dtype=torch.float32, device=dev)
         self.loss_sum = torch.zeros(_lib.N_LOSS, dtype=torch.float64, device=dev)
         self._n_cnt = 0
+        self._n_aux = 0
         # move the store's arenas into the symmetric allocation
         arena = self.buf[:n]
         arena.copy_(store.arena)
@@ -197,6 +205,22 @@ class PeerExchange(MappingExchange):
              ptr(pose_grad) if n_aux else None, self._pose[par], ptr(self.pose_sum), n_aux,
              ptr(loss_acc) if n_auxd else None, self._loss[par], ptr(self.loss_sum), n_auxd, stream())
         st.gen += 1
+        return self.pose_sum, self.loss_sum
+
+    def reduce_small(self, pose_grad=None, n_pose_frames: int = 0, loss_acc=None):
+        """Sum of the ranks' pose-gradient blocks / loss terms on the CURRENT stream, apart from the plane exchange (the
+        pipelined window loop runs it on its side stream).  Returns (pose_grad_sum, loss_sum); local blocks zeroed."""
+        from ._lib import call, ptr, stream
+
+        if n_pose_frames * 12 > self.n_pose:
+            raise RuntimeError("PeerExchange: more frames than the published pose block was sized for")
+        par = self._n_aux & 1
+        self._n_aux += 1
+        n_aux = n_pose_frames * 12 if pose_grad is not None else 0
+        n_auxd = 5 if loss_acc is not None else 0
+        call("eslam_exchange_aux", self._next_epoch(), ptr(pose_grad) if n_aux else None, self._pose_s[par],
+             ptr(self.pose_sum), n_aux, ptr(loss_acc) if n_auxd else None, self._loss_s[par], ptr(self.loss_sum), n_auxd,
+             stream())
         return self.pose_sum, self.loss_sum
 
     def check(self) -> None:

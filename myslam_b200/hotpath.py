@@ -280,3 +280,100 @@ def mapping_iteration(ws: Workspace, store: FieldStore, sc: StepCfg, c2ws, poses
     if joint:
         call("eslam_pose_adam_step", ptr(poses7), ptr(ws.pose_grad), ptr(ws.pose_m), ptr(ws.pose_v), b, 1, lr_cam,
              lr_cam, step, 0.9, 0.999, 1e-8, ptr(ws.grad7), 1, stream())
+
+
+class _Pipe:
+    """Side stream, events and the persistent random-draw buffers of the pipelined window loop (one per Workspace)."""
+
+    def __init__(self, ws: Workspace, N: int, S: int, ns: int, ni: int):
+        dev = ws.device
+        self.key = (N, S, ns, ni)
+        self.side = torch.cuda.Stream(device=dev)
+        self.ev_prep, self.ev_bwd, self.ev_side = torch.cuda.Event(), torch.cuda.Event(), torch.cuda.Event()
+        self.idx = torch.empty(N, dtype=torch.int64, device=dev)
+        self.ubuf = torch.empty(N * (S + ns + ni), dtype=torch.float32, device=dev)
+        self.u = self.ubuf[:N * S].view(N, S)
+        self.u_c = self.ubuf[N * S:N * (S + ns)].view(N, ns)
+        self.u_f = self.ubuf[N * (S + ns):].view(N, ni)
+
+
+def mapping_window_pipelined(ws: Workspace, store: FieldStore, sc: StepCfg, c2ws, poses7, gt_colors, gt_depths,
+                             pix_per_image: int, iters: int, lr_dec: float, lr_planes: float, lr_cplanes: float,
+                             lr_cam: float, exchange=None):
+    """`iters` iterations of Mapper.optimize_mapping's loop (Mapper.py:308-350) on the DEFAULT path (torch's generator,
+    fixed-shape draws, no host sync), software-pipelined over two streams.  What an iteration's ray sampling needs of
+    the previous one is only the poses, so per iteration
+
+        main   importance(it) -> backward(it) ->  plane optimiser tail / peer exchange(it) -> decoder step -> Q(it+1)
+        side                      [after backward]  pose sums + pose Adam(it) -> draws(it+1) -> ray sampling(it+1)
+                                                    (-> normaliser exchange(it+1))
+
+    and the main stream waits for the side stream's sampling only when it reaches importance(it+1).  The draws live in
+    persistent buffers (filled in place), so nothing is allocated on the side stream.  Same arithmetic as
+    mapping_iteration; the uniforms are consumed in the same [N,S] | [N,n_strat] | [N,n_imp] blocks."""
+    dev = ws.device
+    cam, rc = sc.cam, sc.render
+    ns, ni = rc.n_stratified, rc.n_importance
+    S = ns + ni
+    b = c2ws.shape[0]
+    N = pix_per_image * b
+    _check_frames(gt_depths, gt_colors, b, cam)
+    n_crop = (cam.H1 - cam.H0) * (cam.W1 - cam.W0)
+    pipe = getattr(ws, "_pipe", None)
+    if pipe is None or pipe.key != (N, S, ns, ni):
+        pipe = ws._pipe = _Pipe(ws, N, S, ns, ni)
+    peer = exchange is not None and hasattr(exchange, "adam_exchange")
+    if exchange is not None and not peer:
+        raise RuntimeError("mapping_window_pipelined: only the peer-memory exchange (or none) is pipelined")
+    joint = poses7 is not None
+    c2w_flat = c2ws.reshape(b, 16).float().contiguous()
+    t_uni = linspace_table(ns, dev)
+    main = torch.cuda.current_stream()
+    side = pipe.side
+    norm = [None]
+
+    def prep():  # draws + ray selection + depth-guided samples (+ the exchange of the loss normalisers)
+        torch.randint(n_crop, (N,), out=pipe.idx)
+        if sc.perturb:
+            pipe.ubuf.uniform_()
+        _sample(ws, store, sc, pipe.idx, b, pix_per_image, c2w_flat, poses7, 1, gt_depths, gt_colors,
+                pipe.u if sc.perturb else None, 0)
+        if peer:
+            norm[0] = exchange.reduce_counters(ws.counters)
+
+    grad, gq = store.ensure_grad(), store.ensure_q_grad()
+    side.wait_stream(main)
+    with torch.cuda.stream(side):
+        prep()
+        pipe.ev_prep.record(side)
+    for it in range(iters):
+        step = it + 1
+        q = store.ensure_q()
+        main.wait_event(pipe.ev_prep)
+        if sc.perturb:
+            call("eslam_importance_samples", store.ref(), ptr(store.arena), ptr(q), C.byref(rc), ptr(ws.rays_o),
+                 ptr(ws.rays_d), ptr(ws.dl_list), ptr(ws.counters), N, ptr(pipe.u_c), ptr(pipe.u_f), ptr(t_uni), ptr(ws.z),
+                 stream())
+        call("eslam_loss_backward_q", store.ref(), ptr(store.arena), ptr(q), ptr(gq), C.byref(cam), C.byref(rc),
+             ptr(ws.rays_o), ptr(ws.rays_d), ptr(ws.z), ptr(ws.gt_depth), ptr(ws.gt_color), ptr(ws.src), ptr(pipe.idx),
+             pix_per_image, None, ptr(ws.counters), ptr(norm[0]) if norm[0] is not None else None, N, ptr(grad),
+             ptr(ws.pose_grad) if joint else None, None, stream())
+        pipe.ev_bwd.record(main)
+        side.wait_event(pipe.ev_bwd)
+        with torch.cuda.stream(side):
+            if joint:
+                pg = ws.pose_grad
+                if peer:
+                    pg, _ = exchange.reduce_small(ws.pose_grad, b, None)
+                call("eslam_pose_adam_step", ptr(poses7), ptr(pg), ptr(ws.pose_m), ptr(ws.pose_v), b, 1, lr_cam, lr_cam,
+                     step, 0.9, 0.999, 1e-8, ptr(ws.grad7), 1, stream())
+            if step < iters:
+                prep()
+                pipe.ev_prep.record(side)
+            else:
+                pipe.ev_side.record(side)
+        if peer:
+            exchange.adam_exchange(step, lr_dec, lr_planes, lr_cplanes, None, 0, None)
+        else:
+            store.adam_step_q(step, lr_dec, lr_planes, lr_cplanes)
+    main.wait_event(pipe.ev_side)

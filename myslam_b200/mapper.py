@@ -16,7 +16,7 @@ from .common import cam_pose_to_matrix, get_samples, matrix_to_cam_pose, random_
 from .decoders import decoder_tensors, synced_store
 from .field import FieldStore
 from ._lib import call, ptr, stream
-from .hotpath import FrameTable, StepCfg, Workspace, make_camera, mapping_iteration
+from .hotpath import FrameTable, StepCfg, Workspace, make_camera, mapping_iteration, mapping_window_pipelined
 from .renderer import TorchDraws, linspace_table
 from .renderer import make_cfg
 
@@ -44,12 +44,19 @@ def map_window(store: FieldStore, ws: Workspace, sc: StepCfg, c2ws, gt_colors, g
         ws.pose_m.zero_()
         ws.pose_v.zero_()
         ws.pose_grad.zero_()
-    for it in range(iters):
-        mapping_iteration(ws, store, sc, c2ws, poses7, gt_colors, gt_depths, pix, it + 1, lr_dec, lr_planes,
-                          lr_cplanes, lr_cam, draws=draws, strict_rng=strict_rng, want_loss=losses is not None,
-                          exchange=exchange)
-        if losses is not None:
-            losses.append(ws.loss_acc[5].clone())
+    pipelined = (draws is None and not strict_rng and losses is None and iters > 0 and sc.perturb
+                 and (exchange is None or hasattr(exchange, "adam_exchange"))
+                 and os.environ.get("ESLAM_B200_PIPELINE", "1") == "1")
+    if pipelined:  # the default path: two streams, the next iteration's sampling under this one's optimiser step
+        mapping_window_pipelined(ws, store, sc, c2ws, poses7, gt_colors, gt_depths, pix, iters, lr_dec, lr_planes,
+                                 lr_cplanes, lr_cam, exchange=exchange)
+    else:
+        for it in range(iters):
+            mapping_iteration(ws, store, sc, c2ws, poses7, gt_colors, gt_depths, pix, it + 1, lr_dec, lr_planes,
+                              lr_cplanes, lr_cam, draws=draws, strict_rng=strict_rng, want_loss=losses is not None,
+                              exchange=exchange)
+            if losses is not None:
+                losses.append(ws.loss_acc[5].clone())
     if joint_opt and b > 1:  # cam_pose_to_matrix of the optimised poses (Mapper.py:352-362) as one launch
         out = c2ws.clone()
         call("eslam_pose_to_matrix", ptr(poses7[1:]), ptr(out[1:]), b - 1, stream())
