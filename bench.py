@@ -413,6 +413,9 @@ def workload_config(world, pix, n_frames, exchange_name):
                         "15 iterations per optimize_mapping call, ESLAM.yaml defaults, joint pose optimisation",
             "rays_per_iter_total": world * pix * n_frames, "exchange": exchange_name,
             "l2": "inputs larger than L2 (471 MB of window frames + 109 MB parameter/optimiser arenas); no flush",
+            "launch": ("one CUDA-graph replay per call (reset + 15 pipelined iterations over two streams + pose "
+                       "conversion; captured on the second call of a shape)" if world == 1 and
+                       os.environ.get("ESLAM_B200_GRAPH", "1") == "1" else "kernel by kernel over two streams"),
             "seed": 0}
 
 
@@ -524,6 +527,9 @@ def main():
     st = _mapper_state(mp, m["pixels"], n_frames)
     store = synced_store(scene.all_planes, scene.decoders, scene.bound)
     ws, sc = st["ws"], st["sc"]
+    from myslam_b200.hotpath import FrameTable
+    # the window as optimize_mapping stages it: a table of per-frame pointers, the frames read where they live
+    window = FrameTable([cols[k] for k in range(n_frames)], [deps[k] for k in range(n_frames)], sc.cam, dev)
     ex, exchange_name = None, "none (1 GPU)"
     if dist_on:
         if os.environ.get("ESLAM_B200_EXCHANGE", "peer") == "nccl":
@@ -554,7 +560,7 @@ def main():
 
     def mapping_call():
         # Mapper.optimize_mapping's per-call loop (fresh Adam, joint pose optimisation, 15 iterations)
-        map_window(store, ws, sc, poses, cols, deps, m["pixels"], m["iters"], lr["decoders_lr"], lr["planes_lr"],
+        map_window(store, ws, sc, poses, window, window, m["pixels"], m["iters"], lr["decoders_lr"], lr["planes_lr"],
                    lr["c_planes_lr"], True, m["joint_opt_cam_lr"], exchange=ex)
 
     sampler = ClockSampler(local).start() if rank == 0 else None

@@ -283,12 +283,16 @@ def mapping_iteration(ws: Workspace, store: FieldStore, sc: StepCfg, c2ws, poses
 
 
 class _Pipe:
-    """Side stream, events and the persistent random-draw buffers of the pipelined window loop (one per Workspace)."""
+    """Side stream, events and the persistent random-draw buffers of the pipelined window loop: one per Workspace and
+    batch shape, never replaced (a captured window graph addresses these buffers)."""
 
     def __init__(self, ws: Workspace, N: int, S: int, ns: int, ni: int):
         dev = ws.device
         self.key = (N, S, ns, ni)
-        self.side = torch.cuda.Stream(device=dev)
+        side = getattr(ws, "_side_stream", None)
+        if side is None:
+            side = ws._side_stream = torch.cuda.Stream(device=dev)
+        self.side = side
         self.ev_prep, self.ev_bwd, self.ev_side = torch.cuda.Event(), torch.cuda.Event(), torch.cuda.Event()
         self.idx = torch.empty(N, dtype=torch.int64, device=dev)
         self.ubuf = torch.empty(N * (S + ns + ni), dtype=torch.float32, device=dev)
@@ -319,9 +323,10 @@ def mapping_window_pipelined(ws: Workspace, store: FieldStore, sc: StepCfg, c2ws
     N = pix_per_image * b
     _check_frames(gt_depths, gt_colors, b, cam)
     n_crop = (cam.H1 - cam.H0) * (cam.W1 - cam.W0)
-    pipe = getattr(ws, "_pipe", None)
-    if pipe is None or pipe.key != (N, S, ns, ni):
-        pipe = ws._pipe = _Pipe(ws, N, S, ns, ni)
+    pipes = ws.__dict__.setdefault("_pipes", {})
+    pipe = pipes.get((N, S, ns, ni))
+    if pipe is None:
+        pipe = pipes[(N, S, ns, ni)] = _Pipe(ws, N, S, ns, ni)
     peer = exchange is not None and hasattr(exchange, "adam_exchange")
     if exchange is not None and not peer:
         raise RuntimeError("mapping_window_pipelined: only the peer-memory exchange (or none) is pipelined")

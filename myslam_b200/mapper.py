@@ -25,28 +25,22 @@ def _strict_default() -> bool:
     return os.environ.get("ESLAM_B200_STRICT_RNG", "0") == "1"
 
 
-def map_window(store: FieldStore, ws: Workspace, sc: StepCfg, c2ws, gt_colors, gt_depths, n_pixels: int, iters: int,
-               lr_dec: float, lr_planes: float, lr_cplanes: float, joint_opt: bool, lr_cam: float, draws=None,
-               strict_rng: bool = False, losses: Optional[list] = None, exchange=None):
-    """The loop of Mapper.optimize_mapping (Mapper.py:288-350) for an already chosen window:
-    fresh Adam state, `iters` fused iterations on `store`.  Returns the window's c2ws [b,4,4] after the
-    call (frame 0 is held fixed, Mapper.py:314).  `exchange` (myslam_b200.dist) makes the call one rank of a
-    ray-sharded multi-GPU mapping: every rank passes the same window and draws its own `n_pixels` rays."""
+def _window_body(store: FieldStore, ws: Workspace, sc: StepCfg, c2ws, poses7, gt_colors, gt_depths, pix: int, iters: int,
+                 lr_dec, lr_planes, lr_cplanes, lr_cam, out, pipelined: bool, draws=None, strict_rng=False, losses=None,
+                 exchange=None):
+    """Everything map_window puts on the stream, on buffers the caller owns (so that it can be captured):
+    fresh Adam state, the poses of frames 1.. from their matrices, `iters` iterations, the matrices of the optimised
+    poses into `out` [b,4,4]."""
     b = c2ws.shape[0]
-    pix = n_pixels // b
     store.reset_adam()
-    poses7 = None
-    c2ws = c2ws.float().contiguous()
-    if joint_opt:
-        poses7 = torch.zeros(b, 7, dtype=torch.float32, device=c2ws.device)
+    out.copy_(c2ws)
+    if poses7 is not None:
+        poses7.zero_()
         if b > 1:  # matrix_to_cam_pose(c2ws[1:]) (Mapper.py:289) as one launch
             call("eslam_matrix_to_pose", ptr(c2ws[1:]), ptr(poses7[1:]), b - 1, stream())
         ws.pose_m.zero_()
         ws.pose_v.zero_()
         ws.pose_grad.zero_()
-    pipelined = (draws is None and not strict_rng and losses is None and iters > 0 and sc.perturb
-                 and (exchange is None or hasattr(exchange, "adam_exchange"))
-                 and os.environ.get("ESLAM_B200_PIPELINE", "1") == "1")
     if pipelined:  # the default path: two streams, the next iteration's sampling under this one's optimiser step
         mapping_window_pipelined(ws, store, sc, c2ws, poses7, gt_colors, gt_depths, pix, iters, lr_dec, lr_planes,
                                  lr_cplanes, lr_cam, exchange=exchange)
@@ -57,11 +51,90 @@ def map_window(store: FieldStore, ws: Workspace, sc: StepCfg, c2ws, gt_colors, g
                               exchange=exchange)
             if losses is not None:
                 losses.append(ws.loss_acc[5].clone())
-    if joint_opt and b > 1:  # cam_pose_to_matrix of the optimised poses (Mapper.py:352-362) as one launch
-        out = c2ws.clone()
+    if poses7 is not None and b > 1:  # cam_pose_to_matrix of the optimised poses (Mapper.py:352-362) as one launch
         call("eslam_pose_to_matrix", ptr(poses7[1:]), ptr(out[1:]), b - 1, stream())
-        c2ws = out
-    return c2ws
+
+
+class _WindowGraph:
+    """One `optimize_mapping` call's device work -- optimiser reset, `iters` pipelined iterations over both streams,
+    pose conversion -- captured once as a CUDA graph and replayed (the loop is ~16 ctypes launches per iteration; a
+    replay costs the host one call, so the mapper process is free while the window runs and the launch gaps between
+    the kernels close).  Everything the kernels address is persistent: the parameter / optimiser arenas, the
+    workspace and its draw buffers, and the three buffers below (window poses in, poses out, frame-pointer table),
+    which are rewritten before every replay.  Adam restarts at step 1 in every call (Mapper.py:291-299), so the bias
+    corrections baked into the launches are the same for every call of the same shape.  The random draws are
+    torch's (its CUDA generator is graph safe)."""
+
+    def __init__(self, store, ws, sc, frames: FrameTable, b, pix, iters, lrs, joint, lr_cam):
+        from . import _lib
+
+        dev = ws.device
+        self.c2ws = torch.zeros(b, 4, 4, dtype=torch.float32, device=dev)
+        self.out = torch.zeros(b, 4, 4, dtype=torch.float32, device=dev)
+        self.poses7 = torch.zeros(b, 7, dtype=torch.float32, device=dev) if joint else None
+        self.frames = FrameTable(frames.colors, frames.depths, sc.cam, dev)  # own table; pointers rewritten per replay
+        self.iters = iters
+        store.q_gen = -1  # the graph rebuilds the Q images itself: whatever changed the parameters between two calls
+        torch.cuda.synchronize(dev)
+        self.graph = torch.cuda.CUDAGraph()
+        l0 = _lib.LAUNCHES
+        with torch.cuda.graph(self.graph, capture_error_mode="thread_local"):
+            _window_body(store, ws, sc, self.c2ws, self.poses7, self.frames, self.frames, pix, iters, *lrs, lr_cam,
+                         self.out, True)
+        self.n_launches = _lib.LAUNCHES - l0
+        store.q_gen = -1  # nothing ran: the bookkeeping of the captured loop does not describe the arena
+
+    def run(self, store, c2ws, frames: FrameTable):
+        from . import _lib
+
+        self.c2ws.copy_(c2ws)
+        self.frames.colors, self.frames.depths = frames.colors, frames.depths  # keep the frames alive
+        self.frames.table.copy_(frames.table)
+        self.graph.replay()
+        _lib.LAUNCHES += self.n_launches
+        store.gen += self.iters  # one optimiser step per iteration; the Q images are those of the last but one
+        store.q_gen = -1
+        return self.out.clone()
+
+
+def _graph_on() -> bool:
+    return os.environ.get("ESLAM_B200_GRAPH", "1") == "1"
+
+
+def map_window(store: FieldStore, ws: Workspace, sc: StepCfg, c2ws, gt_colors, gt_depths, n_pixels: int, iters: int,
+               lr_dec: float, lr_planes: float, lr_cplanes: float, joint_opt: bool, lr_cam: float, draws=None,
+               strict_rng: bool = False, losses: Optional[list] = None, exchange=None):
+    """The loop of Mapper.optimize_mapping (Mapper.py:288-350) for an already chosen window:
+    fresh Adam state, `iters` fused iterations on `store`.  Returns the window's c2ws [b,4,4] after the
+    call (frame 0 is held fixed, Mapper.py:314).  `exchange` (myslam_b200.dist) makes the call one rank of a
+    ray-sharded multi-GPU mapping: every rank passes the same window and draws its own `n_pixels` rays.
+
+    On the default path (torch's generator, fixed-shape draws) a single-GPU call whose shape has been seen before
+    replays a CUDA graph of the whole call (_WindowGraph; ESLAM_B200_GRAPH=0 launches kernel by kernel)."""
+    b = c2ws.shape[0]
+    pix = n_pixels // b
+    c2ws = c2ws.float().contiguous()
+    pipelined = (draws is None and not strict_rng and losses is None and iters > 0 and sc.perturb
+                 and (exchange is None or hasattr(exchange, "adam_exchange"))
+                 and os.environ.get("ESLAM_B200_PIPELINE", "1") == "1")
+    if pipelined and exchange is None and isinstance(gt_depths, FrameTable) and gt_colors is gt_depths and _graph_on():
+        graphs = ws.__dict__.setdefault("_window_graphs", {})
+        key = (id(store), store.arena.data_ptr(), b, pix, iters, lr_dec, lr_planes, lr_cplanes, bool(joint_opt), lr_cam)
+        ent = graphs.get(key)
+        if ent is None:
+            graphs[key] = "seen"  # the first call of a shape runs kernel by kernel (lazy allocations happen there)
+        else:
+            if ent == "seen":
+                if len(graphs) > 64:
+                    graphs.clear()
+                ent = graphs[key] = _WindowGraph(store, ws, sc, gt_depths, b, pix, iters, (lr_dec, lr_planes, lr_cplanes),
+                                                 joint_opt, lr_cam)
+            return ent.run(store, c2ws, gt_depths)
+    poses7 = torch.zeros(b, 7, dtype=torch.float32, device=c2ws.device) if joint_opt else None
+    out = torch.empty_like(c2ws)
+    _window_body(store, ws, sc, c2ws, poses7, gt_colors, gt_depths, pix, iters, lr_dec, lr_planes, lr_cplanes, lr_cam,
+                 out, pipelined, draws=draws, strict_rng=strict_rng, losses=losses, exchange=exchange)
+    return out
 
 
 def keyframe_selection_overlap(self, gt_color, gt_depth, c2w, num_keyframes, num_samples=8, num_rays=50):

@@ -198,3 +198,55 @@ def test_consecutive_launches_read_their_own_decoders_eager_and_in_a_graph():
     torch.cuda.synchronize()
     for name in ("A", "B"):
         assert torch.equal(outs[name][0], eager[name][0]) and torch.equal(outs[name][1], eager[name][1]), name
+
+
+def test_mapping_window_graph_replay_matches_kernel_by_kernel(monkeypatch):
+    """map_window on the default path three times from the SAME parameters, window and generator seed: launched kernel
+    by kernel (ESLAM_B200_GRAPH=0), then twice with graphs on (the first call of a shape is launched kernel by kernel,
+    the second is captured and replayed).  Torch's generator is graph safe, so all three draw the same pixels and
+    uniforms; planes, decoders and optimised poses must agree to the noise of the float atomics."""
+    from myslam_b200.decoders import synced_store
+    from myslam_b200.hotpath import FrameTable
+    from myslam_b200.mapper import _WindowGraph, _mapper_state, map_window
+
+    fld, d = golden_field(), load_npz("mapping.npz")
+    c2ws = torch.from_numpy(d["c2ws0"]).to(DEV)
+    cols, deps = torch.from_numpy(d["gt_colors"]).to(DEV), torch.from_numpy(d["gt_depths"]).to(DEV)
+    mp = make_mapper(fld, d)
+    mp.strict_rng = False
+    all_planes = (mp.planes_xy, mp.planes_xz, mp.planes_yz, mp.c_planes_xy, mp.c_planes_xz, mp.c_planes_yz)
+    st = _mapper_state(mp, 400, 4)
+    store = synced_store(all_planes, mp.decoders, mp.bound)
+    arena0 = store.arena.clone()
+
+    def run(frames):
+        store.arena.copy_(arena0)
+        store.gen += 1
+        torch.manual_seed(99)
+        out = map_window(store, st["ws"], st["sc"], c2ws, frames, frames, 400, 3, 1e-3, 5e-3, 5e-3, True, 1e-3)
+        torch.cuda.synchronize()
+        return store.arena.clone(), out.clone()
+
+    table = lambda: FrameTable([cols[k] for k in range(4)], [deps[k] for k in range(4)], st["sc"].cam, DEV)
+    monkeypatch.setenv("ESLAM_B200_GRAPH", "0")
+    a_ref, p_ref = run(table())
+    a_ref2, p_ref2 = run(table())  # the same again: run-to-run noise of the float atomics (amplified by Adam's g/|g|)
+    assert not getattr(st["ws"], "_window_graphs", None)
+    monkeypatch.setenv("ESLAM_B200_GRAPH", "1")
+    a_1, p_1 = run(table())
+    a_2, p_2 = run(table())  # captured + replayed; a different table object whose pointers are copied in
+    graphs = st["ws"]._window_graphs
+    assert len(graphs) == 1 and isinstance(next(iter(graphs.values())), _WindowGraph)
+    a_3, p_3 = run(table())  # replayed again
+    upd = (a_ref - arena0).abs()
+    assert float(upd.max()) > 1e-4, "the call must have moved the parameters"
+    noise_max = float((a_ref2 - a_ref).abs().max())
+    noise_mean = float((a_ref2 - a_ref).abs().mean())
+    for a, p in ((a_1, p_1), (a_2, p_2), (a_3, p_3)):
+        diff = (a - a_ref).abs()
+        assert float(diff.max()) <= max(8 * noise_max, 1e-5 * float(upd.max())), (float(diff.max()), noise_max)
+        assert float(diff.mean()) <= max(4 * noise_mean, 1e-6 * float(upd.mean())), (float(diff.mean()), noise_mean)
+        assert float(diff.mean()) < 1e-3 * float(upd.mean())
+        assert float((p - p_ref).abs().max()) < max(1e-5, 8 * float((p_ref2 - p_ref).abs().max()))
+    assert float((p_ref[1:] - c2ws[1:]).abs().max()) > 0, "joint optimisation must have moved the poses"
+    assert torch.equal(p_ref[0], c2ws[0])

@@ -6,8 +6,8 @@ import subprocess
 import sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-KEEP = ("map.loss_backward planes+poses  ", "map.iteration", "trk.iteration", "map.render_forward 4000", "map.adam",
-        "trk.render_forward", "trk.loss_backward")
+KEEP = ("map.loss_backward_q", "map.q_adam_planes", "map.q_build", "map.importance", "map.sample_rays", "map.iteration",
+        "trk.iteration", "trk.render_forward_q", "trk.pose_backward_q", "map.render_forward_q")
 
 
 def main():
