@@ -206,6 +206,21 @@ int eslam_loss_backward_q(const eslam_field_t* field_host, const float* arena, c
                           const int32_t* counters, const int32_t* norm_counters, int max_rays, float* grad_arena,
                           float* pose_grad, double* loss_acc, eslam_stream_t s);
 
+/* eslam_loss_backward_q as one launch of a PAIR (no ray mask, no loss sums): part 1 handles only the tiles (groups of
+ * 128 / S consecutive kept rays) whose rays all carry a sensor depth, part 2 only the tiles holding a depth-less ray;
+ * part 0 is every tile.  dl_list: the ascending list of depth-less kept rays eslam_sample_rays* left (counters[1]
+ * entries), from which part 2 enumerates its tiles with a small persistent grid.  The depth-less rays (Renderer.py:108-134) are the only ones whose samples depend on the
+ * current parameters.  Part 1 is launched with programmatic stream serialization: put right behind
+ * eslam_importance_samples on the same stream it starts while that kernel runs (behind any other kernel: ordinary stream
+ * order); part 2 goes behind the importance pass on another stream and fills part 1's last wave.  The two launches add
+ * into the same gradient images / decoder / pose gradients. */
+int eslam_loss_backward_q_part(const eslam_field_t* field_host, const float* arena, const float* q_arena,
+                               float* gq_arena, const eslam_camera_t* cam, const eslam_render_cfg_t* cfg,
+                               const float* rays_o, const float* rays_d, const float* z, const float* gt_depth,
+                               const double* gt_color, const int32_t* src, const int64_t* pix_idx, int n_per_img,
+                               const int32_t* dl_list, const int32_t* counters, const int32_t* norm_counters,
+                               int max_rays, float* grad_arena, float* pose_grad, int part, eslam_stream_t s);
+
 /* The plane half of `optimizer.step()` / `zero_grad()` (Mapper.py:288-306,348-350) from the gradient images.  Per
  * texel: d loss / d plane = W1_slice^T . GQ (consumed in registers by torch.optim.Adam's update, moments in
  * parameter-arena layout), d loss / d W1_slice += GQ (x) plane (added into grad_arena's decoder block, so the decoders

@@ -93,6 +93,7 @@ PROTOTYPES = {
     "eslam_loss_backward": [_FP, _P, _CP, _RP, _P, _P, _P, _P, _P, _P, _P, _I, _P, _P, _P, _I, _P, _P, _P, _P],
     "eslam_pose_backward_act": [_FP, _P, _CP, _RP, _P, _P, _P, _P, _P, _P, _P, _I, _P, _P, _I, _P, _P, _P, _P, _P, _P],
     "eslam_loss_backward_q": [_FP, _P, _P, _P, _CP, _RP, _P, _P, _P, _P, _P, _P, _P, _I, _P, _P, _P, _I, _P, _P, _P, _P],
+    "eslam_loss_backward_q_part": [_FP, _P, _P, _P, _CP, _RP, _P, _P, _P, _P, _P, _P, _P, _I, _P, _P, _P, _I, _P, _P, _I, _P],
     "eslam_pose_backward_q": [_FP, _P, _P, _CP, _RP, _P, _P, _P, _P, _P, _P, _P, _I, _P, _P, _I, _P, _P, _P, _P, _P, _P],
     "eslam_adam_step": [_P, _P, _P, _P, _L, C.POINTER(C.c_int64), C.POINTER(C.c_double), _I, _I, _D, _D, _D, _P],
     "eslam_adam_step_sparse": [_P, _P, _P, _P, _L, C.POINTER(C.c_int64), C.POINTER(C.c_double), _I, _I, _D, _D, _D, _P,

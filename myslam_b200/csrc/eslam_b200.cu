@@ -662,9 +662,11 @@ static int loss_backward_impl(const eslam_field_t* f, const float* arena, const 
                               const int64_t* pix_idx, int n_per_img, const uint8_t* ray_mask, const int32_t* counters,
                               const int32_t* norm_counters, int max_rays, float* grad_arena, float* pose_grad,
                               double* loss_acc, const float* sdf, const float* act4, const uint32_t* actm,
-                              const float* q_arena, float* gq_arena, eslam_stream_t s) {
+                              const float* q_arena, float* gq_arena, eslam_stream_t s, int part = 0,
+                              const int32_t* dl_list = nullptr) {
   REQUIRE(f && arena && cam && cfg && rays_o && rays_d && z && gt_depth && gt_color && counters && max_rays >= 0,
           "eslam_loss_backward");
+  REQUIRE(part >= 0 && part <= 2 && (part != 2 || dl_list), "eslam_loss_backward(part)");
   REQUIRE(!pose_grad || (src && pix_idx && n_per_img > 0), "eslam_loss_backward(pose)");
   if (max_rays == 0) return 0;
   int rc = check_samples(cfg->n_stratified, cfg->n_importance);
@@ -682,6 +684,8 @@ static int loss_backward_impl(const eslam_field_t* f, const float* arena, const 
   a.S = k.n_strat + k.n_imp;
   a.counters = counters;
   a.dbg = g_debug;
+  a.part = part;
+  a.dl_list = dl_list;
   a.norm = norm_counters ? norm_counters : counters;
   a.gt_depth = gt_depth;
   a.gt_color = gt_color;
@@ -725,11 +729,42 @@ static int loss_backward_impl(const eslam_field_t* f, const float* arena, const 
     }
     const int S = a.S, rpb = (NP / S) < 16 ? (NP / S) : 16;
     const unsigned grid = (unsigned)((max_rays + rpb - 1) / rpb);
-    if (gr)
+    if (part == 2) {
+      static bool configured_dl[MAX_DEVICES][2] = {{false, false}};
+      if (!configured_dl[dev][gr]) {
+        rc = gr ? set_smem(k_map_bwd_q_dl<true>, bytes) : set_smem(k_map_bwd_q_dl<false>, bytes);
+        if (rc) return fail(rc, "eslam_loss_backward_q_part(shared memory)");
+        configured_dl[dev][gr] = true;
+      }
+      int sms = 148;
+      cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+      const unsigned g2 = grid < (unsigned)(2 * sms) ? grid : (unsigned)(2 * sms);
+      if (gr)
+        k_map_bwd_q_dl<true><<<g2, NT_BWD, bytes, S_(s)>>>(a);
+      else
+        k_map_bwd_q_dl<false><<<g2, NT_BWD, bytes, S_(s)>>>(a);
+    } else if (part == 1) {
+      // part 1 reads nothing the importance pass writes: launched with programmatic stream serialization, it starts
+      // when the kernel in front of it in the stream has let its dependents go (k_importance does so at once; any
+      // other kernel never does, which leaves ordinary stream order).  Its own CTAs hold every register of an SM, so
+      // started the ordinary way -- beside the importance kernel on another stream -- it would starve that kernel.
+      cudaLaunchConfig_t lc;
+      memset(&lc, 0, sizeof(lc));
+      lc.gridDim = dim3(grid);
+      lc.blockDim = dim3(NT_BWD);
+      lc.dynamicSmemBytes = bytes;
+      lc.stream = S_(s);
+      cudaLaunchAttribute at[1];
+      at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+      at[0].val.programmaticStreamSerializationAllowed = 1;
+      lc.attrs = at;
+      lc.numAttrs = 1;
+      rc = (int)(gr ? cudaLaunchKernelEx(&lc, k_map_bwd_q<true>, a) : cudaLaunchKernelEx(&lc, k_map_bwd_q<false>, a));
+    } else if (gr)
       k_map_bwd_q<true><<<grid, NT_BWD, bytes, S_(s)>>>(a);
     else
       k_map_bwd_q<false><<<grid, NT_BWD, bytes, S_(s)>>>(a);
-    rc = (int)cudaGetLastError();
+    if (!rc) rc = (int)cudaGetLastError();
   } else if (q_arena) {
     REQUIRE(!grad_arena && pose_grad && sdf && act4 && actm, "eslam_pose_backward_q");
     static bool configured[MAX_DEVICES] = {false};
@@ -777,7 +812,7 @@ int eslam_pose_backward_act(const eslam_field_t* f, const float* arena, const es
                             counters, nullptr, max_rays, nullptr, pose_grad, loss_acc, sdf, act4, actm, nullptr, nullptr, s);
 }
 
-// experimental (qplane.cuh): eslam_pose_backward_act on the pre-activated plane images; the cached activations must
+// Q form (qbwd.cuh): eslam_pose_backward_act on the pre-activated plane images; the cached activations must
 // come from eslam_render_forward_q on the same q_arena
 int eslam_pose_backward_q(const eslam_field_t* f, const float* arena, const float* q_arena, const eslam_camera_t* cam,
                           const eslam_render_cfg_t* cfg, const float* rays_o, const float* rays_d, const float* z,
@@ -791,7 +826,7 @@ int eslam_pose_backward_q(const eslam_field_t* f, const float* arena, const floa
                             s);
 }
 
-// experimental (qplane.cuh): eslam_loss_backward with planes + decoders (+ poses) in the Q form.  The plane gradients
+// Q form (qbwd.cuh): eslam_loss_backward with planes + decoders (+ poses) in the Q form.  The plane gradients
 // arrive as 16-channel reductions in gq_arena (layout of q_arena); grad_arena receives the decoder gradients except
 // dW1 (formed by eslam_q_adam_planes from gq_arena) and beta.
 int eslam_loss_backward_q(const eslam_field_t* f, const float* arena, const float* q_arena, float* gq_arena,
@@ -804,6 +839,18 @@ int eslam_loss_backward_q(const eslam_field_t* f, const float* arena, const floa
   return loss_backward_impl(f, arena, cam, cfg, rays_o, rays_d, z, gt_depth, gt_color, src, pix_idx, n_per_img, ray_mask,
                             counters, norm_counters, max_rays, grad_arena, pose_grad, loss_acc, nullptr, nullptr,
                             nullptr, q_arena, gq_arena, s);
+}
+
+int eslam_loss_backward_q_part(const eslam_field_t* f, const float* arena, const float* q_arena, float* gq_arena,
+                               const eslam_camera_t* cam, const eslam_render_cfg_t* cfg, const float* rays_o,
+                               const float* rays_d, const float* z, const float* gt_depth, const double* gt_color,
+                               const int32_t* src, const int64_t* pix_idx, int n_per_img, const int32_t* dl_list,
+                               const int32_t* counters, const int32_t* norm_counters, int max_rays, float* grad_arena,
+                               float* pose_grad, int part, eslam_stream_t s) {
+  REQUIRE(q_arena && gq_arena && grad_arena, "eslam_loss_backward_q_part");
+  return loss_backward_impl(f, arena, cam, cfg, rays_o, rays_d, z, gt_depth, gt_color, src, pix_idx, n_per_img, nullptr,
+                            counters, norm_counters, max_rays, grad_arena, pose_grad, nullptr, nullptr, nullptr,
+                            nullptr, q_arena, gq_arena, s, part, dl_list);
 }
 
 static int fill_adam(AdamArgs& a, int64_t n, const int64_t* seg_end, const double* seg_lr, int n_seg, int step,
@@ -1165,7 +1212,7 @@ int eslam_keyframe_overlap(const eslam_camera_t* cam, const float* c2w, const fl
   return 0;
 }
 
-// ---- experimental: pre-activated planes (qplane.cuh) ---------------------------------------
+// ---- the Q form: pre-activated planes (qplane.cuh) ---------------------------------------
 int eslam_q_build(const eslam_field_t* f, const float* arena, float* q_arena, eslam_stream_t s) {
   REQUIRE(f && arena && q_arena, "eslam_q_build");
   QBuildArgs a;

@@ -206,7 +206,7 @@ __device__ __forceinline__ void weight_grads_q(float* R, float4* P, float* gdec,
 // k_render_fwd_q on the same rays, so neither the gather nor the forward MLPs run; the coordinate gradients then
 // fetch the Q corners once (coord_grads_q).
 template <bool GF, bool GR, bool CACHED>
-__device__ __forceinline__ void render_bwd_q_body(const BwdArgs& a) {
+__device__ __forceinline__ void render_bwd_q_body(const BwdArgs& a, const int tile) {
   static_assert(!(GF && CACHED), "the cached form has no activations for weight gradients");
   constexpr bool ROWS = !CACHED;
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -214,9 +214,14 @@ __device__ __forceinline__ void render_bwd_q_body(const BwdArgs& a) {
   const int R = a.counters ? min(a.counters[0], a.n_rays) : a.n_rays;
   const int S = a.S;
   const int RPB = min(NP / S, 16);
-  const int ray0 = blockIdx.x * RPB;
+  const int ray0 = tile * RPB;
   if (ray0 >= R) return;
   const int rays_here = min(RPB, R - ray0);
+  if (GF && a.part == 1) {  // CTA-uniform: a tile holding a depth-less ray belongs to the other launch of the pair
+    bool depthless = false;
+    for (int r = 0; r < rays_here; ++r) depthless = depthless || !(a.gt_depth[ray0 + r] > 0.f);
+    if (depthless) return;
+  }
   const int n_valid = rays_here * S;
   const int tid = threadIdx.x;
   const int half = tid >> 7;  // 0: sdf decoder, 1: rgb decoder (warp-uniform)
@@ -553,13 +558,28 @@ __device__ __forceinline__ void render_bwd_q_body(const BwdArgs& a) {
 
 // tracker: pose gradient on the activations k_render_fwd_q kept (eslam_pose_backward_q)
 __global__ void __launch_bounds__(NT_BWD, 2) k_pose_bwd_q(const __grid_constant__ BwdArgs a) {
-  render_bwd_q_body<false, true, true>(a);
+  render_bwd_q_body<false, true, true>(a, blockIdx.x);
 }
 
 // mapper: gradient images + decoder gradients (+ poses) (eslam_loss_backward_q)
 template <bool GR>
 __global__ void __launch_bounds__(NT_BWD, 2) k_map_bwd_q(const __grid_constant__ BwdArgs a) {
-  render_bwd_q_body<true, GR, false>(a);
+  render_bwd_q_body<true, GR, false>(a, blockIdx.x);
+}
+
+// mapper, part 2 of the split launch: only the tiles that hold a depth-less ray, enumerated from the (ascending) list
+// of depth-less rays the sampling kernel left; a tile belongs to its first listed ray.  A small persistent grid: the
+// list is a few percent of the batch, and a grid over all tiles would be CTAs that start only to leave.
+template <bool GR>
+__global__ void __launch_bounds__(NT_BWD, 2) k_map_bwd_q_dl(const __grid_constant__ BwdArgs a) {
+  const int R0 = a.counters[1];
+  const int RPB = min(NP / a.S, 16);
+  for (int i = blockIdx.x; i < R0; i += gridDim.x) {
+    const int tile = a.dl_list[i] / RPB;
+    if (i > 0 && a.dl_list[i - 1] / RPB == tile) continue;
+    __syncthreads();  // the previous tile's shared memory is done with
+    render_bwd_q_body<true, GR, false>(a, tile);
+  }
 }
 
 }  // namespace eslam

@@ -1,6 +1,5 @@
-// EXPERIMENTAL -- pre-activated planes ("apply the first decoder layer on the planes").
-// Not wired into the product path yet: the Python mirror never calls these entry points; tests/test_gpu_experimental.py
-// holds them to 1e-5 of the product's render forward.
+// The Q form: pre-activated planes.  The default path of both loops; tests/test_gpu_qform.py
+// holds it to the parameter form (forward 1e-5, gradients 1e-3) and tests/test_gpu_default_path.py to the oracle.
 //
 // Bilinear interpolation is linear, so the first decoder layer of decoders.py:87-125 commutes with the plane fetch
 // of decoders.py:64-85:

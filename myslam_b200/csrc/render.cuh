@@ -614,6 +614,11 @@ struct BwdArgs {
   // Q form (qbwd.cuh): the Q images and, for the mapper, the gradient images the plane reductions go to
   const float4* q4;
   float4* gq4;
+  // split launch of the mapper's backward (eslam_loss_backward_q_part): 0 = every tile, 1 = only the tiles whose rays
+  // all carry a sensor depth; the tiles holding a depth-less ray (which wait for the importance samples) are
+  // enumerated from dl_list by k_map_bwd_q_dl
+  int part;
+  const int* dl_list;
 };
 
 // ---- weight gradients on the tensor cores ----------------------------------------------------------------------

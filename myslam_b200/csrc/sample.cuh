@@ -457,6 +457,10 @@ struct SmemImp {
 __global__ void __launch_bounds__(NP) k_importance(const __grid_constant__ ImportanceArgs a) {
   __shared__ SmemImp sm;
   __shared__ float s_zi[NP];  // resampled depths, [rl*n_imp + i]
+  // A kernel launched behind this one with programmatic stream serialization (eslam_loss_backward_q_part, part 1: the
+  // tiles that do not read what this kernel writes) may start as soon as every CTA here is resident or gone; without
+  // such a dependent the instruction does nothing.
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   const int R0 = a.counters[1];
   const int NS = a.n_strat;
   const int RPB = NP / NS;

@@ -16,6 +16,7 @@ which costs one host sync per iteration (the reference has >= 12); it is what pa
 from __future__ import annotations
 
 import ctypes as C
+import os
 from dataclasses import dataclass
 from typing import Optional
 
@@ -293,6 +294,11 @@ class _Pipe:
         if side is None:
             side = ws._side_stream = torch.cuda.Stream(device=dev)
         self.side = side
+        imp = getattr(ws, "_imp_stream", None)
+        if imp is None:
+            imp = ws._imp_stream = torch.cuda.Stream(device=dev)
+        self.imp = imp
+        self.ev_q, self.ev_imp = torch.cuda.Event(), torch.cuda.Event()
         self.ev_prep, self.ev_bwd, self.ev_side = torch.cuda.Event(), torch.cuda.Event(), torch.cuda.Event()
         self.idx = torch.empty(N, dtype=torch.int64, device=dev)
         self.ubuf = torch.empty(N * (S + ns + ni), dtype=torch.float32, device=dev)
@@ -312,7 +318,10 @@ def mapping_window_pipelined(ws: Workspace, store: FieldStore, sc: StepCfg, c2ws
         side                      [after backward]  pose sums + pose Adam(it) -> draws(it+1) -> ray sampling(it+1)
                                                     (-> normaliser exchange(it+1))
 
-    and the main stream waits for the side stream's sampling only when it reaches importance(it+1).  The draws live in
+    and the main stream waits for the side stream's sampling only when it reaches importance(it+1).  The backward is a
+    pair of launches (eslam_loss_backward_q_part; ESLAM_B200_SPLIT_BWD=0: one launch behind the importance pass): the
+    tiles whose rays all carry a depth start while the importance kernel runs, the tiles with a depth-less ray follow
+    that kernel on a third stream.  The draws live in
     persistent buffers (filled in place), so nothing is allocated on the side stream.  Same arithmetic as
     mapping_iteration; the uniforms are consumed in the same [N,S] | [N,n_strat] | [N,n_imp] blocks."""
     dev = ws.device
@@ -331,6 +340,7 @@ def mapping_window_pipelined(ws: Workspace, store: FieldStore, sc: StepCfg, c2ws
     if exchange is not None and not peer:
         raise RuntimeError("mapping_window_pipelined: only the peer-memory exchange (or none) is pipelined")
     joint = poses7 is not None
+    split = os.environ.get("ESLAM_B200_SPLIT_BWD", "1") == "1"
     c2w_flat = c2ws.reshape(b, 16).float().contiguous()
     t_uni = linspace_table(ns, dev)
     main = torch.cuda.current_stream()
@@ -355,14 +365,35 @@ def mapping_window_pipelined(ws: Workspace, store: FieldStore, sc: StepCfg, c2ws
         step = it + 1
         q = store.ensure_q()
         main.wait_event(pipe.ev_prep)
-        if sc.perturb:
+
+        def importance():
             call("eslam_importance_samples", store.ref(), ptr(store.arena), ptr(q), C.byref(rc), ptr(ws.rays_o),
                  ptr(ws.rays_d), ptr(ws.dl_list), ptr(ws.counters), N, ptr(pipe.u_c), ptr(pipe.u_f), ptr(t_uni), ptr(ws.z),
                  stream())
-        call("eslam_loss_backward_q", store.ref(), ptr(store.arena), ptr(q), ptr(gq), C.byref(cam), C.byref(rc),
-             ptr(ws.rays_o), ptr(ws.rays_d), ptr(ws.z), ptr(ws.gt_depth), ptr(ws.gt_color), ptr(ws.src), ptr(pipe.idx),
-             pix_per_image, None, ptr(ws.counters), ptr(norm[0]) if norm[0] is not None else None, N, ptr(grad),
-             ptr(ws.pose_grad) if joint else None, None, stream())
+
+        def backward(part):
+            call("eslam_loss_backward_q_part", store.ref(), ptr(store.arena), ptr(q), ptr(gq), C.byref(cam), C.byref(rc),
+                 ptr(ws.rays_o), ptr(ws.rays_d), ptr(ws.z), ptr(ws.gt_depth), ptr(ws.gt_color), ptr(ws.src),
+                 ptr(pipe.idx), pix_per_image, ptr(ws.dl_list), ptr(ws.counters),
+                 ptr(norm[0]) if norm[0] is not None else None, N, ptr(grad), ptr(ws.pose_grad) if joint else None, part,
+                 stream())
+
+        if split:
+            # Only the depth-less rays' samples depend on the current parameters (Renderer.py:108-134).  The tiles
+            # without such a ray (part 1) are launched behind the importance kernel with programmatic stream
+            # serialization and start while it runs; the few tiles that need its samples (part 2) follow it on another
+            # stream and fill the last, partial wave of part 1.
+            importance()
+            pipe.ev_q.record(main)
+            pipe.imp.wait_event(pipe.ev_q)
+            with torch.cuda.stream(pipe.imp):
+                backward(2)
+                pipe.ev_imp.record(pipe.imp)
+            backward(1)
+            main.wait_event(pipe.ev_imp)
+        else:
+            importance()
+            backward(0)
         pipe.ev_bwd.record(main)
         side.wait_event(pipe.ev_bwd)
         with torch.cuda.stream(side):

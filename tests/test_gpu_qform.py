@@ -222,3 +222,28 @@ def test_mapping_backward_in_the_q_form_matches_the_reference_gradients():
         assert rel_err(got, ref) < 1e-3, name
     assert rel_err(gdec["beta"], d["it0_beta_grad"]) < 1e-3
     assert rel_err(ws.grad7[1:4], d["it0_pose_grad"]) < 1e-3
+    # ---- the same backward as a PAIR of launches (eslam_loss_backward_q_part: tiles without / with a depth-less ray),
+    # the way the pipelined window loop issues it: every tile belongs to exactly one part, so the sums are the same
+    n_dl = int(ws.counters[0]) - int((ws.gt_depth[: int(ws.counters[0])] > 0).sum())
+    assert n_dl > 0, "the fixture must hold depth-less rays, or part 2 is empty"
+    def launch(parts):
+        out = torch.zeros_like(gq)
+        store.grad.zero_()
+        ws.pose_grad.zero_()
+        after = []
+        for part in parts:
+            call("eslam_loss_backward_q_part", store.ref(), ptr(store.arena), ptr(q_arena), ptr(out), C.byref(sc.cam),
+                 C.byref(sc.render), ptr(ws.rays_o), ptr(ws.rays_d), ptr(ws.z), ptr(ws.gt_depth), ptr(ws.gt_color),
+                 ptr(ws.src), ptr(idx), 100, ptr(ws.dl_list), ptr(ws.counters), None, N, ptr(store.grad),
+                 ptr(ws.pose_grad), part, stream())
+            torch.cuda.synchronize()
+            after.append(out.clone())
+        return out, store.grad.clone(), ws.pose_grad.clone(), after
+
+    gq_one, grad_one, pose_one, _ = launch((0,))
+    gq_pair, grad_pair, pose_pair, seen = launch((1, 2))
+    assert rel_err(gq_one, gq) < 1e-5
+    assert float(seen[0].abs().max()) > 0 and float((seen[1] - seen[0]).abs().max()) > 0, "both parts must contribute"
+    assert rel_err(gq_pair, gq_one) < 1e-5
+    assert rel_err(grad_pair[store.dec_off:], grad_one[store.dec_off:]) < 1e-5
+    assert rel_err(pose_pair, pose_one) < 1e-5

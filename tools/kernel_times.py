@@ -73,8 +73,8 @@ def main():
         _lib.load().eslam_set_debug(flags)
         timeit(f"map.loss_backward planes+poses [{name}]", bwd(True, True))
     _lib.load().eslam_set_debug(0)
-    # experimental Q form of the mapping iteration: backward into gradient images, dense tail
-    if os.environ.get("ESLAM_B200_EXPERIMENTAL", "0") == "1":
+    # the Q form (the default path): backward into gradient images, optimiser tail, Q rebuild
+    if True:
         mq = torch.zeros(store.n_planes_end // 2, dtype=torch.float32, device=dev)
         mgq = torch.zeros_like(mq)
         tq = torch.zeros(_lib.load().eslam_q_touched_bytes(store.ref()), dtype=torch.uint8, device=dev)
