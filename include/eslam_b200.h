@@ -389,6 +389,19 @@ int eslam_ingest_frame(const uint8_t* bgr, const uint16_t* depth_u16, int H, int
 int eslam_ingest_frame_resized(const uint8_t* bgr, int Hs, int Ws, const uint16_t* depth_u16, int H, int W, int crop_edge,
                                double png_depth_scale, double scale, double* color, float* depth, eslam_stream_t s);
 
+/* TUM-shaped frames (datasets.py:83-86): cv2.undistort(img, K, distortion) of the uint8 colour image with the new
+ * camera matrix = K, on the device (OpenCV's initUndistortRectifyMap + remap(INTER_LINEAR, BORDER_CONSTANT): source
+ * positions in float64 rounded to 1/32 pixel, integer blend).  distortion5_host = (k1, k2, p1, p2, k3);
+ * inv_k9_host: the row-major inverse of K as the caller computed it (NULL: the closed form).  dst != src. */
+int eslam_undistort_u8(const uint8_t* src, uint8_t* dst, int H, int W, double fx, double fy, double cx, double cy,
+                       const double* distortion5_host, const double* inv_k9_host, eslam_stream_t s);
+
+/* eslam_ingest_frame with the loader's `crop_size` step (datasets.py:98-106): the colour image / 255 resized to
+ * [Ho][Wo] like F.interpolate(mode='bilinear', align_corners=True) on float64 (torch's CPU arithmetic, bit for bit),
+ * the depth like F.interpolate(mode='nearest'), then crop_edge.  color [Ho-2e][Wo-2e][3], depth [Ho-2e][Wo-2e]. */
+int eslam_ingest_frame_crop(const uint8_t* bgr, const uint16_t* depth_u16, int H, int W, int Ho, int Wo, int crop_edge,
+                            double png_depth_scale, double scale, double* color, float* depth, eslam_stream_t s);
+
 /* matrix_to_cam_pose / cam_pose_to_matrix (common.py:155-181 over pytorch3d 0.7.1 matrix_to_quaternion /
  * quaternion_to_matrix) for n cameras: c2w[n][16] row-major <-> poses[n][7] = (qw,qx,qy,qz,tx,ty,tz), evaluated in
  * torch's operation order.  Used once per optimize_mapping call for the window's poses (Mapper.py:289,352-362). */

@@ -102,6 +102,8 @@ PROTOTYPES = {
     "eslam_finalize_loss": [_RP, _P, _I, _P, _P, _P],
     "eslam_ingest_frame": [_P, _P, _I, _I, _I, _D, _D, _P, _P, _P],
     "eslam_ingest_frame_resized": [_P, _I, _I, _P, _I, _I, _I, _D, _D, _P, _P, _P],
+    "eslam_undistort_u8": [_P, _P, _I, _I, _D, _D, _D, _D, C.POINTER(C.c_double), C.POINTER(C.c_double), _P],
+    "eslam_ingest_frame_crop": [_P, _P, _I, _I, _I, _I, _I, _D, _D, _P, _P, _P],
     "eslam_matrix_to_pose": [_P, _P, _I, _P],
     "eslam_pose_to_matrix": [_P, _P, _I, _P],
     "eslam_keyframe_overlap": [_CP, _P, _P, _P, _I, _P, _I, _P, _I, _P, _P, _P],

@@ -27,10 +27,12 @@ def build_library(force: bool = False, verbose: bool = False) -> str:
     if not force and up_to_date():
         return OUT
     cmd = [nvcc_path(), "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
-           "--split-compile", "4", "-Xcompiler", "-fPIC", "-shared", "-o", OUT, SRC]
+           "--split-compile", "1", "-Xcompiler", "-fPIC", "-shared", "-o", OUT, SRC]
     # A fixed thread count on purpose: the optimiser partitions the module by the number of split-compile threads, and
-    # the partitioning changes the code of nearly every kernel (8 threads, 2-4 threads and 1 thread give three different
-    # builds of the same source; "0" = "as many as there are CPUs right now" made that vary from build to build).
+    # the partitioning changes the code of nearly every kernel (1 thread and 4-8 threads give different builds of the
+    # same source; "0" = "as many as there are CPUs right now" made that vary from build to build).  Pinned by
+    # measurement (tools/build_variants.py + tools/variant_times.py, profiles/r02_variant_times.txt): the unsplit build
+    # runs the dominant kernel in 151.5 us instead of 157.1 and a mapping iteration in 217.5 us instead of 223.7.
     if verbose:
         cmd.insert(1, "-Xptxas")
         cmd.insert(2, "-v")

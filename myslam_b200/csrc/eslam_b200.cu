@@ -1167,6 +1167,65 @@ int eslam_ingest_frame_resized(const uint8_t* bgr, int Hs, int Ws, const uint16_
   return 0;
 }
 
+int eslam_undistort_u8(const uint8_t* src, uint8_t* dst, int H, int W, double fx, double fy, double cx, double cy,
+                       const double* distortion5_host, const double* inv_k9_host, eslam_stream_t s) {
+  REQUIRE(src && dst && src != dst && H > 0 && W > 0 && distortion5_host && fx != 0.0 && fy != 0.0, "eslam_undistort_u8");
+  UndistortArgs a;
+  a.src = src;
+  a.dst = dst;
+  a.H = H;
+  a.W = W;
+  if (inv_k9_host) {
+    for (int i = 0; i < 9; ++i) a.ir[i] = inv_k9_host[i];
+  } else {  // inverse of [[fx 0 cx] [0 fy cy] [0 0 1]]
+    const double ir[9] = {1.0 / fx, 0.0, -cx / fx, 0.0, 1.0 / fy, -cy / fy, 0.0, 0.0, 1.0};
+    for (int i = 0; i < 9; ++i) a.ir[i] = ir[i];
+  }
+  a.fx = fx;
+  a.fy = fy;
+  a.cx = cx;
+  a.cy = cy;
+  a.k1 = distortion5_host[0];
+  a.k2 = distortion5_host[1];
+  a.p1 = distortion5_host[2];
+  a.p2 = distortion5_host[3];
+  a.k3 = distortion5_host[4];
+  long long blocks = ((long long)H * W + 255) / 256;
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  k_undistort_u8<<<(unsigned)blocks, 256, 0, S_(s)>>>(a);
+  CHECK_LAUNCH("eslam_undistort_u8");
+  return 0;
+}
+
+int eslam_ingest_frame_crop(const uint8_t* bgr, const uint16_t* depth_u16, int H, int W, int Ho, int Wo, int crop_edge,
+                            double png_depth_scale, double scale, double* color, float* depth, eslam_stream_t s) {
+  REQUIRE(bgr && depth_u16 && color && depth && H > 1 && W > 1 && Ho > 1 && Wo > 1 && crop_edge >= 0 &&
+              2 * crop_edge < Ho && 2 * crop_edge < Wo,
+          "eslam_ingest_frame_crop");
+  IngestCropArgs a;
+  a.bgr = bgr;
+  a.depth = depth_u16;
+  a.H = H;
+  a.W = W;
+  a.Ho = Ho;
+  a.Wo = Wo;
+  a.edge = crop_edge;
+  a.sy = (double)(H - 1) / (double)(Ho - 1);
+  a.sx = (double)(W - 1) / (double)(Wo - 1);
+  a.ny = (float)H / (float)Ho;
+  a.nx = (float)W / (float)Wo;
+  a.png_depth_scale = (float)png_depth_scale;
+  a.scale = (float)scale;
+  a.color = color;
+  a.out_depth = depth;
+  const long long n = (long long)(Ho - 2 * crop_edge) * (Wo - 2 * crop_edge);
+  long long blocks = (n + 255) / 256;
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  k_ingest_crop<<<(unsigned)blocks, 256, 0, S_(s)>>>(a);
+  CHECK_LAUNCH("eslam_ingest_frame_crop");
+  return 0;
+}
+
 int eslam_matrix_to_pose(const float* c2w, float* poses, int n, eslam_stream_t s) {
   REQUIRE(c2w && poses && n >= 0, "eslam_matrix_to_pose");
   if (n == 0) return 0;

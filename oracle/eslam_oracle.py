@@ -858,6 +858,111 @@ def ingest_frame_resized(color_u8_bgr, depth_u16, png_depth_scale, crop_edge=0, 
     return color.contiguous(), depth.contiguous()
 
 
+def undistort_u8(bgr_u8, fx, fy, cx, cy, distortion):
+    """cv2.undistort(img, K, distortion) of an 8-bit image with the new camera matrix = K (datasets.py:83-86; third
+    party: OpenCV's initUndistortRectifyMap + remap(INTER_LINEAR, BORDER_CONSTANT), restated from their published
+    algorithm and pinned bit for bit against cv2 4.13 here): the source position of every pixel in float64, rounded
+    to 1/32 pixel, the four taps blended with integer weights 32 (32 - ax)(32 - ay) ... that sum to 2^15, rounded
+    by + 2^14 >> 15; taps outside the image are 0.  distortion = (k1, k2, p1, p2, k3)."""
+    import numpy as np
+
+    k1, k2, p1, p2, k3 = [float(v) for v in distortion]
+    H, W = bgr_u8.shape[:2]
+    K = np.array([[fx, 0.0, cx], [0.0, fy, cy], [0.0, 0.0, 1.0]])
+    ir = np.linalg.inv(K)
+    i = np.arange(H, dtype=np.float64)[:, None]
+    j = np.arange(W, dtype=np.float64)[None, :]
+    _x = i * ir[0, 1] + ir[0, 2] + j * ir[0, 0]
+    _y = i * ir[1, 1] + ir[1, 2] + j * ir[1, 0]
+    _w = i * ir[2, 1] + ir[2, 2] + j * ir[2, 0]
+    w = 1.0 / _w
+    x, y = _x * w, _y * w
+    x2, y2 = x * x, y * y
+    r2, _2xy = x2 + y2, 2 * x * y
+    kr = 1 + ((k3 * r2 + k2) * r2 + k1) * r2
+    xd = x * kr + p1 * _2xy + p2 * (r2 + 2 * x2)
+    yd = y * kr + p1 * (r2 + 2 * y2) + p2 * _2xy
+    iu = np.rint((fx * xd + cx) * 32).astype(np.int64)
+    iv = np.rint((fy * yd + cy) * 32).astype(np.int64)
+    sx, sy, ax, ay = iu >> 5, iv >> 5, iu & 31, iv & 31
+
+    def tap(yy, xx):
+        ok = (yy >= 0) & (yy < H) & (xx >= 0) & (xx < W)
+        v = bgr_u8[np.clip(yy, 0, H - 1), np.clip(xx, 0, W - 1)].astype(np.int64)
+        v[~ok] = 0
+        return v
+
+    acc = (tap(sy, sx) * ((32 - ay) * (32 - ax) * 32)[..., None] + tap(sy, sx + 1) * ((32 - ay) * ax * 32)[..., None] +
+           tap(sy + 1, sx) * (ay * (32 - ax) * 32)[..., None] + tap(sy + 1, sx + 1) * (ay * ax * 32)[..., None])
+    return ((acc + (1 << 14)) >> 15).astype(np.uint8)
+
+
+def _align_corners_taps(n_in, n_out):
+    """Index pair and weights of F.interpolate(mode='bilinear', align_corners=True) along one axis, as ATen's CPU kernel
+    computes them: position = i (n_in - 1) / (n_out - 1) in float64, the lower index from floorf() of the position
+    ROUNDED TO FLOAT32 (so a position a hair below an integer already belongs to it), weights from the float64 rest."""
+    import numpy as np
+
+    scale = (n_in - 1) / (n_out - 1) if n_out > 1 else 0.0
+    real = scale * np.arange(n_out, dtype=np.float64)
+    i0 = np.minimum(np.floor(real.astype(np.float32)).astype(np.int64), n_in - 1)
+    l1 = np.clip(real - i0, 0.0, 1.0)
+    return i0, i0 + (i0 < n_in - 1), 1.0 - l1, l1
+
+
+def resize_bilinear_align_corners(img, size):
+    """F.interpolate(img.permute(2,0,1)[None], size, mode='bilinear', align_corners=True) for a float64 [H,W,C] image
+    (datasets.py:100-104), bit for bit as torch's CPU kernel evaluates it here: the four weight products, then
+    (w01 b) -> fma(w00, a, .) -> fma(w10, c, .) -> fma(w11, d, .)."""
+    import numpy as np
+
+    Hi, Wi, C = img.shape
+    Ho, Wo = size
+    y0, y1, hy, ly = _align_corners_taps(Hi, Ho)
+    x0, x1, hx, lx = _align_corners_taps(Wi, Wo)
+    out = np.empty((Ho, Wo, C))
+    for r in range(Ho):
+        for c in range(Wo):
+            w00, w01, w10, w11 = hy[r] * hx[c], hy[r] * lx[c], ly[r] * hx[c], ly[r] * lx[c]
+            for ch in range(C):
+                acc = w01 * img[y0[r], x1[c], ch]
+                acc = _fma(w00, img[y0[r], x0[c], ch], acc)
+                acc = _fma(w10, img[y1[r], x0[c], ch], acc)
+                out[r, c, ch] = _fma(w11, img[y1[r], x1[c], ch], acc)
+    return out
+
+
+def _nearest_index(n_in, n_out):
+    """F.interpolate(mode='nearest'): min(floorf(i * (float32)(n_in / n_out)), n_in - 1)."""
+    import numpy as np
+
+    scale = np.float32(n_in) / np.float32(n_out)
+    return np.minimum(np.floor(np.arange(n_out, dtype=np.float32) * scale).astype(np.int64), n_in - 1)
+
+
+def ingest_frame_tum(color_u8_bgr, depth_u16, png_depth_scale, cam=None, distortion=None, crop_size=None, crop_edge=0,
+                     scale=1.0):
+    """BaseDataset.__getitem__ (datasets.py:79-112) for TUM-shaped frames (colour and depth of one size): optional
+    cv2.undistort of the uint8 colour image (cam = (fx, fy, cx, cy)), / 255 in float64, optional crop_size (bilinear
+    align_corners resize of the colour, nearest of the depth), crop_edge."""
+    import numpy as np
+
+    bgr = color_u8_bgr
+    if distortion is not None:
+        bgr = undistort_u8(bgr, *cam, distortion)
+    color = bgr[:, :, ::-1] / 255.
+    depth = torch.from_numpy(depth_u16.astype(np.float32) / png_depth_scale) * scale
+    if crop_size is not None:
+        color = resize_bilinear_align_corners(np.ascontiguousarray(color), crop_size)
+        iy, ix = _nearest_index(depth.shape[0], crop_size[0]), _nearest_index(depth.shape[1], crop_size[1])
+        depth = depth[torch.from_numpy(iy)][:, torch.from_numpy(ix)]
+    color = torch.from_numpy(np.ascontiguousarray(color))
+    if crop_edge > 0:
+        color = color[crop_edge:-crop_edge, crop_edge:-crop_edge]
+        depth = depth[crop_edge:-crop_edge, crop_edge:-crop_edge]
+    return color.contiguous(), depth.contiguous()
+
+
 # ----------------------------------------------------------------------------
 # (f)-2: mesh extraction around the query   (Mesher.py:219-247, cull_mesh.py:58-105)
 # ----------------------------------------------------------------------------

@@ -192,6 +192,33 @@ def test_ingest_scannet_shaped_frame_bit_exact():
     assert torch.equal(c2.cpu(), oc) and torch.equal(d2.cpu(), od)
 
 
+def test_ingest_tum_shaped_frame_bit_exact():
+    """Undistortion + crop_size + crop_edge on the device == the reference's TUM_RGBD loader on the fixture frame, bit
+    for bit (eslam_undistort_u8 against cv2.undistort's own output, eslam_ingest_frame_crop against the loader's
+    F.interpolate steps); and the oracle on a second, odd-sized case with and without each step."""
+    from myslam_b200.ingest import ingest_frame, undistort
+
+    d = load_npz("ingest_tum.npz")
+    cam, dist, crop = tuple(d["cam"]), d["distortion"], tuple(int(v) for v in d["crop_size"])
+    und = undistort(torch.from_numpy(d["bgr"]).to(DEV), cam, dist)
+    assert torch.equal(und.cpu(), torch.from_numpy(d["undistorted"]))
+    color, depth = ingest_frame(d["bgr"], d["depth_u16"], float(d["png_depth_scale"]), int(d["crop_edge"]), DEV, cam=cam,
+                                distortion=dist, crop_size=crop)
+    assert color.dtype == torch.float64 and depth.dtype == torch.float32
+    assert torch.equal(depth.cpu(), torch.from_numpy(d["depth"]))
+    assert torch.equal(color.cpu(), torch.from_numpy(d["color"]))
+    rng = np.random.default_rng(9)
+    bgr = rng.integers(0, 256, size=(45, 61, 3), dtype=np.uint8)
+    dep = rng.integers(0, 65536, size=(45, 61), dtype=np.uint16)
+    cam2, dist2 = (50.3, 49.1, 30.2, 22.6), (0.2312, -0.7849, -0.0033, -0.0001, 0.9172)
+    for kw in (dict(cam=cam2, distortion=dist2, crop_size=(37, 50)), dict(crop_size=(36, 49)),
+               dict(cam=cam2, distortion=dist2)):
+        c2, d2 = ingest_frame(bgr, dep, 5000.0, 3, DEV, **kw)
+        oc, od = O.ingest_frame_tum(bgr, dep, 5000.0, kw.get("cam"), kw.get("distortion"), kw.get("crop_size"), 3)
+        assert torch.equal(d2.cpu(), od), kw
+        assert torch.equal(c2.cpu(), oc), kw
+
+
 def test_grid_query_with_convex_mesh_bound():
     """Mesher.get_mesh forces sdf = -1 outside the convex hull of the observed region (Mesher.py:206-217); here the
     half-space test runs inside the grid query.  Against the plain query + a float64 half-space mask, away from the

@@ -164,6 +164,18 @@ def test_ingest_golden():
     assert torch.equal(color, torch.from_numpy(d["color"])) and torch.equal(depth, torch.from_numpy(d["depth"]))
 
 
+def test_ingest_tum_golden():
+    """Oracle restatement of the TUM-shaped loader path (datasets.py:79-112: cv2.undistort of the uint8 colour image,
+    crop_size = bilinear align_corners / nearest resize, crop_edge) against what the reference's TUM_RGBD loader returned
+    (make_golden_ingest_tum.py), and the undistortion alone against cv2's own output kept in the fixture."""
+    d = load_npz("ingest_tum.npz")
+    assert np.array_equal(O.undistort_u8(d["bgr"], *d["cam"], d["distortion"]), d["undistorted"])
+    color, depth = O.ingest_frame_tum(d["bgr"], d["depth_u16"], float(d["png_depth_scale"]), tuple(d["cam"]),
+                                      d["distortion"], tuple(int(v) for v in d["crop_size"]), int(d["crop_edge"]))
+    assert color.dtype == torch.float64 and depth.dtype == torch.float32
+    assert torch.equal(color, torch.from_numpy(d["color"])) and torch.equal(depth, torch.from_numpy(d["depth"]))
+
+
 def test_ingest_scannet_golden():
     """Oracle restatement of the ScanNet-shaped loader path (datasets.py:88-112 with cv2.resize of the float64 colour
     image to the depth's size) against what the reference's ScanNet loader returned (make_golden_ingest_scannet.py)."""
