@@ -10,6 +10,7 @@ SRC = os.path.join(HERE, "csrc", "eslam_b200.cu")
 OUT = os.path.join(HERE, "libeslam_b200.so")
 DEPS = [os.path.join(HERE, "csrc", f) for f in ("eslam_b200.cu", "field.cuh", "render.cuh", "sample.cuh", "optim.cuh", "exchange.cuh", "keyframes.cuh", "ingest.cuh", "qplane.cuh", "qform.cuh", "qbwd.cuh", "mcubes.cuh")]
 DEPS.append(os.path.join(os.path.dirname(HERE), "include", "eslam_b200.h"))
+DEPS.append(os.path.abspath(__file__))  # the flags live here
 
 
 def nvcc_path() -> str:
