@@ -308,7 +308,11 @@ def extras(scene, rnd, spec, dev, rank, world, dist_on, poses, deps, hbm_peak):
     q = lambda **kw: (lambda: query_grid_sdf(scene.all_planes, scene.decoders, axes, scene.bound, start=start,
                                              count=count, out=buf, **kw))
     ms = time_region(q(), 3, 1, dist_on) / 3  # the default form (factored)
-    forms = {"factored_ms": ms, "separable_ms": time_region(q(separable=True), 3, 1, dist_on) / 3,
+    os.environ["ESLAM_B200_GRID_ROWS"] = "0"
+    ms_voxel = time_region(q(), 3, 1, dist_on) / 3  # the factored form without the tensor-core rows kernel
+    del os.environ["ESLAM_B200_GRID_ROWS"]
+    forms = {"factored_ms": ms, "factored_per_voxel_ms": ms_voxel,
+             "separable_ms": time_region(q(separable=True), 3, 1, dist_on) / 3,
              "direct_ms": time_region(q(separable=False), 3, 1, dist_on) / 3}
     out["mesh_query"] = {"value": total / (ms * 1e-3), "unit": "points/s", "ms": ms, "points": total,
                          "lattice": [len(a) for a in axes], "n_gpus": world, "scaling": "strong", "forms": forms,
@@ -318,8 +322,11 @@ def extras(scene, rnd, spec, dev, rank, world, dist_on, poses, deps, hbm_peak):
                          "what": "Mesher.get_grid_uniform + eval_points (Mesher.py:130-186), SDF head only, coordinates "
                                  "generated in-kernel.  direct: every voxel gathers its 24 corners; separable: the "
                                  "planes are resampled once on the lattice's faces (768 B per point, bit-identical); "
-                                 "factored (default): the first decoder layer is applied on the faces too (192 B and "
-                                 "272 FMA per point, equal to 1e-5).  Face resampling is inside every timed call."}
+                                 "factored (default): the first decoder layer is applied on the faces too (equal to "
+                                 "1e-5); whole lattice rows run the 16->16 layer as mma.sync 3xTF32 with the xz face "
+                                 "values in registers (eslam_grid_sdf_rows), ragged range ends the per-voxel kernel "
+                                 "(192 B and 272 FMA per point: factored_per_voxel_ms).  Face resampling is inside "
+                                 "every timed call."}
     del buf
     if rank != 0:
         return out

@@ -171,6 +171,15 @@ int eslam_grid_sdf_factored(const eslam_field_t* field_host, const float* xs, co
                             int ny, int nz, int64_t start, int64_t count, const float* pxy, const float* pxz,
                             const float* pyz, const float* hull_planes, int n_planes, float* sdf, eslam_stream_t s);
 
+/* eslam_grid_sdf_factored for WHOLE lattice rows iy in [iy0, iy1) (all ix, iz): a warp keeps one x and 64 z and walks y,
+ * so the xz face values stay in registers, the yz values are shared through L1, and the hidden 16 -> 16 layer runs as
+ * packed FP32 (fma.rn.f32x2: two voxels per issue slot).  sdf[flat - out_base] for flat = (iy * nx + ix) * nz + iz;
+ * out_base <= iy0 * nx * nz.  Same faces, bound and hull tests and the same operation order as
+ * eslam_grid_sdf_factored: bit-identical values. */
+int eslam_grid_sdf_rows(const eslam_field_t* field_host, const float* xs, const float* ys, const float* zs, int nx,
+                        int ny, int nz, int iy0, int iy1, int64_t out_base, const float* pxy, const float* pxz,
+                        const float* pyz, const float* hull_planes, int n_planes, float* sdf, eslam_stream_t s);
+
 /* ---- the Q form: the first decoder layer applied to the planes ----------------------------
  * What both loops' iterations run on.  The first layer of decoders.py:87-125 is linear and commutes with the bilinear
  * fetch of decoders.py:64-85:  W1 (sum_planes bilinear(plane)) + b1 = sum_planes bilinear(W1_slice . plane) + b1,

@@ -77,6 +77,7 @@ PROTOTYPES = {
     "eslam_grid_sdf_separable": [_FP, _P, _P, _P, _P, _I, _I, _I, _L, _L, _P, _P, _P, _P, _I, _P, _P],
     "eslam_grid_preact": [_FP, _P, _P, _P, _P, _I, _I, _I, _I, _I, _P, _P, _P, _P],
     "eslam_grid_sdf_factored": [_FP, _P, _P, _P, _I, _I, _I, _L, _L, _P, _P, _P, _P, _I, _P, _P],
+    "eslam_grid_sdf_rows": [_FP, _P, _P, _P, _I, _I, _I, _I, _I, _L, _P, _P, _P, _P, _I, _P, _P],
     "eslam_q_build": [_FP, _P, _P, _P],
     "eslam_q_adam_planes": [_FP, _P, _P, _P, _P, _P, _P, _D, _D, _I, _D, _D, _D, _P],
     "eslam_render_forward_q": [_FP, _P, _P, _P, _P, _I, _I, _P, _P, _P, _P, _P, _P, _P],

@@ -326,6 +326,41 @@ int eslam_grid_sdf_factored(const eslam_field_t* f, const float* xs, const float
   return 0;
 }
 
+int eslam_grid_sdf_rows(const eslam_field_t* f, const float* xs, const float* ys, const float* zs, int nx, int ny, int nz,
+                        int iy0, int iy1, int64_t out_base, const float* pxy, const float* pxz, const float* pyz,
+                        const float* hull_planes, int n_planes, float* sdf, eslam_stream_t s) {
+  REQUIRE(f && xs && ys && zs && pxy && pxz && pyz && sdf && nx > 0 && ny > 0 && nz > 0 && iy0 >= 0 && iy1 <= ny &&
+              iy0 <= iy1 && nx <= 32767 && ny <= 32767 && nz <= 32767 && out_base >= 0 &&
+              out_base <= (int64_t)iy0 * nx * nz && n_planes >= 0 && (n_planes == 0 || hull_planes),
+          "eslam_grid_sdf_rows");
+  if (iy0 == iy1) return 0;
+  GridRowsArgs a;
+  memset(&a, 0, sizeof(a));
+  for (int k = 0; k < 3; ++k) {
+    a.lo[k] = f->bound[k][0];
+    a.hi[k] = f->bound[k][1];
+  }
+  a.xs = xs;
+  a.ys = ys;
+  a.zs = zs;
+  a.nx = nx;
+  a.ny = ny;
+  a.nz = nz;
+  a.iy0 = iy0;
+  a.iy1 = iy1;
+  a.out_base = out_base;
+  a.pxy = reinterpret_cast<const float4*>(pxy);
+  a.pxz = reinterpret_cast<const float4*>(pxz);
+  a.pyz = reinterpret_cast<const float4*>(pyz);
+  a.hull = reinterpret_cast<const float4*>(hull_planes);
+  a.n_hull = n_planes;
+  a.sdf_out = sdf;
+  const dim3 grid((unsigned)((nx + GR_X - 1) / GR_X), (unsigned)((nz + GR_Z - 1) / GR_Z));
+  k_grid_sdf_rows<<<grid, GR_THREADS, 0, S_(s)>>>(a);
+  CHECK_LAUNCH("eslam_grid_sdf_rows");
+  return 0;
+}
+
 static int sample_rays_impl(const eslam_field_t* f, const eslam_camera_t* cam, const eslam_render_cfg_t* cfg,
                             const int64_t* pix_idx, int n_img, int n_per_img, const float* c2w, const float* poses,
                             int pose_first, const float* depth, const double* color, bool frame_table,

@@ -314,36 +314,33 @@ __global__ void __launch_bounds__(FAC_THREADS) k_grid_sdf_factored(const __grid_
       if (valid[k]) a.sdf_out[gi[k]] = -1.0f;
     return;
   }
-  float h1[FAC_PT][16];
+  static_assert(FAC_PT == 2, "the hidden layer is packed FP32 over the thread's two voxels");
+  float2 h1[16];  // channel i of voxel 0 / 1 in .x / .y
 #pragma unroll
-  for (int k = 0; k < FAC_PT; ++k) {
-#pragma unroll
-    for (int c = 0; c < 4; ++c) {
-      const float4 v = f4_add(f4_add(ldg4(qxy[k] + c), ldg4(qxz[k] + (long long)c * nz)), ldg4(qyz[k] + (long long)c * nz));
-      h1[k][c * 4 + 0] = fmaxf(v.x, 0.f);
-      h1[k][c * 4 + 1] = fmaxf(v.y, 0.f);
-      h1[k][c * 4 + 2] = fmaxf(v.z, 0.f);
-      h1[k][c * 4 + 3] = fmaxf(v.w, 0.f);
-    }
+  for (int c = 0; c < 4; ++c) {
+    const float4 v0 = f4_add(f4_add(ldg4(qxy[0] + c), ldg4(qxz[0] + (long long)c * nz)), ldg4(qyz[0] + (long long)c * nz));
+    const float4 v1 = f4_add(f4_add(ldg4(qxy[1] + c), ldg4(qxz[1] + (long long)c * nz)), ldg4(qyz[1] + (long long)c * nz));
+    h1[c * 4 + 0] = make_float2(fmaxf(v0.x, 0.f), fmaxf(v1.x, 0.f));
+    h1[c * 4 + 1] = make_float2(fmaxf(v0.y, 0.f), fmaxf(v1.y, 0.f));
+    h1[c * 4 + 2] = make_float2(fmaxf(v0.z, 0.f), fmaxf(v1.z, 0.f));
+    h1[c * 4 + 3] = make_float2(fmaxf(v0.w, 0.f), fmaxf(v1.w, 0.f));
   }
-  float o[FAC_PT];
-#pragma unroll
-  for (int k = 0; k < FAC_PT; ++k) o[k] = c_dec[S_B3];
+  // fma.rn.f32x2 (SASS FFMA2 R, R.F32x2, UR.F32, R): both voxels against one weight per issue slot; two exact FMAs, the
+  // operation order of the scalar form
+  float2 o2 = make_float2(c_dec[S_B3], c_dec[S_B3]);
 #pragma unroll
   for (int j = 0; j < 16; ++j) {
-    float acc[FAC_PT];
-#pragma unroll
-    for (int k = 0; k < FAC_PT; ++k) acc[k] = c_dec[S_B2 + j];
+    const float bj = c_dec[S_B2 + j];
+    float2 acc = make_float2(bj, bj);
 #pragma unroll
     for (int i = 0; i < 16; ++i) {
       const float w = c_dec[S_W2 + j * 16 + i];
-#pragma unroll
-      for (int k = 0; k < FAC_PT; ++k) acc[k] = fmaf(w, h1[k][i], acc[k]);
+      acc = __ffma2_rn(make_float2(w, w), h1[i], acc);
     }
     const float w3 = c_dec[S_W3 + j];
-#pragma unroll
-    for (int k = 0; k < FAC_PT; ++k) o[k] = fmaf(w3, fmaxf(acc[k], 0.f), o[k]);
+    o2 = __ffma2_rn(make_float2(w3, w3), make_float2(fmaxf(acc.x, 0.f), fmaxf(acc.y, 0.f)), o2);
   }
+  const float o[FAC_PT] = {o2.x, o2.y};
 #pragma unroll
   for (int k = 0; k < FAC_PT; ++k) {
     float sdf = tanhf(o[k]);
@@ -581,6 +578,103 @@ __global__ void __launch_bounds__(NP) k_render_fwd(const __grid_constant__ Rende
 // ---------------------------------------------------------------------------------------------------
 // fused loss + backward
 // ---------------------------------------------------------------------------------------------------
+// ---- the factored lattice query over whole lattice rows ---------------------------------------------------------------
+// k_grid_sdf_factored is bound by issue slots: 590 instructions per voxel, 280 of them the FFMAs of the hidden layer,
+// the rest loads, index arithmetic and the three-face sum.  Here a warp owns one x and 64 z (lane: z and z + 32) and
+// walks y: the xz face values of its two voxels stay in registers for the whole column, the yz values are shared by
+// the CTA's warps (8 x) through L1, the xy texel is one line read by the whole warp; and the hidden layer is packed
+// FP32 -- `fma.rn.f32x2` (SASS FFMA2 R, R.F32x2, UR.F32, R: the two voxels of a lane against one weight in a uniform
+// register), two exact FMAs per issue slot, so the values are those of k_grid_sdf_factored bit for bit.
+// (The same layer as mma.sync m16n8k8 TF32 with both operands split in two -- three products per tile, the precision
+// the 1e-5 bar needs -- was measured first: 6.24 ms for the 990x680x490 lattice against 5.96 ms per voxel.  The legacy
+// tensor path at 24 HMMA per 32 voxels is slower than 256 FFMA per voxel; tcgen05 would need the three-face sum staged
+// through shared memory for a K = N = 16 tile.)
+struct GridRowsArgs {
+  float lo[3], hi[3];
+  const float *xs, *ys, *zs;
+  int nx, ny, nz;
+  int iy0, iy1;        // lattice rows [iy0, iy1)
+  long long out_base;  // flat lattice index of sdf_out[0]
+  const float4 *pxy, *pxz, *pyz;
+  const float4* hull;
+  int n_hull;
+  float* sdf_out;
+};
+
+constexpr int GR_THREADS = 256, GR_X = GR_THREADS / 32, GR_Z = 64;
+
+__device__ __forceinline__ float2 relu2(float2 v) { return make_float2(fmaxf(v.x, 0.f), fmaxf(v.y, 0.f)); }
+
+__global__ void __launch_bounds__(GR_THREADS, 2) k_grid_sdf_rows(const __grid_constant__ GridRowsArgs a) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int x = blockIdx.x * GR_X + warp;
+  if (x >= a.nx) return;  // warp-uniform; no CTA barrier below
+  const int zA = blockIdx.y * GR_Z + lane, zB = zA + 32;
+  const bool okA = zA < a.nz, okB = zB < a.nz;
+  const int za = okA ? zA : a.nz - 1, zb = okB ? zB : a.nz - 1;
+  // xz face values of the lane's two voxels: channel c of voxel A / B in .x / .y
+  float2 fxz[16];
+#pragma unroll
+  for (int c = 0; c < 4; ++c) {
+    const float4 va = ldg4(a.pxz + ((long long)x * 4 + c) * a.nz + za), vb = ldg4(a.pxz + ((long long)x * 4 + c) * a.nz + zb);
+    fxz[c * 4 + 0] = make_float2(va.x, vb.x);
+    fxz[c * 4 + 1] = make_float2(va.y, vb.y);
+    fxz[c * 4 + 2] = make_float2(va.z, vb.z);
+    fxz[c * 4 + 3] = make_float2(va.w, vb.w);
+  }
+  const float px = a.xs[x], pzA = a.zs[za], pzB = a.zs[zb];
+  const bool in_x = px < a.hi[0] && px > a.lo[0];
+  const bool inA0 = okA && in_x && pzA < a.hi[2] && pzA > a.lo[2], inB0 = okB && in_x && pzB < a.hi[2] && pzB > a.lo[2];
+#pragma unroll 1
+  for (int y = a.iy0; y < a.iy1; ++y) {
+    float4 cxy[4], cyA[4], cyB[4];  // no software prefetch: two CTAs per SM hide the loads, 48 more registers would not fit
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      cxy[c] = ldg4(a.pxy + ((long long)y * a.nx + x) * 4 + c);
+      cyA[c] = ldg4(a.pyz + ((long long)y * 4 + c) * a.nz + za);
+      cyB[c] = ldg4(a.pyz + ((long long)y * 4 + c) * a.nz + zb);
+    }
+    const float py = a.ys[y];
+    const bool in_y = py < a.hi[1] && py > a.lo[1];  // Mesher.py:214-215
+    bool inA = inA0 && in_y, inB = inB0 && in_y;
+    for (int h = 0; h < a.n_hull && (inA || inB); ++h) {  // Mesher.py:210-217: mesh_bound.contains -> sdf = -1
+      const float4 hp = __ldg(a.hull + h);
+      inA = inA && fmaf(hp.x, px, fmaf(hp.y, py, fmaf(hp.z, pzA, hp.w))) <= 0.f;
+      inB = inB && fmaf(hp.x, px, fmaf(hp.y, py, fmaf(hp.z, pzB, hp.w))) <= 0.f;
+    }
+    float* dst = a.sdf_out + ((((long long)y * a.nx + x) * a.nz + zA) - a.out_base);
+    if (!__any_sync(0xffffffffu, inA || inB)) {  // the warp's 64 voxels all lie outside: nothing to decode
+      if (okA) dst[0] = -1.0f;
+      if (okB) dst[32] = -1.0f;
+      continue;
+    }
+    // h1 = relu((xy + xz) + yz), the sum order of k_grid_sdf_factored
+    float2 h1[16];
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      h1[c * 4 + 0] = relu2(__fadd2_rn(__fadd2_rn(make_float2(cxy[c].x, cxy[c].x), fxz[c * 4 + 0]), make_float2(cyA[c].x, cyB[c].x)));
+      h1[c * 4 + 1] = relu2(__fadd2_rn(__fadd2_rn(make_float2(cxy[c].y, cxy[c].y), fxz[c * 4 + 1]), make_float2(cyA[c].y, cyB[c].y)));
+      h1[c * 4 + 2] = relu2(__fadd2_rn(__fadd2_rn(make_float2(cxy[c].z, cxy[c].z), fxz[c * 4 + 2]), make_float2(cyA[c].z, cyB[c].z)));
+      h1[c * 4 + 3] = relu2(__fadd2_rn(__fadd2_rn(make_float2(cxy[c].w, cxy[c].w), fxz[c * 4 + 3]), make_float2(cyA[c].w, cyB[c].w)));
+    }
+    float2 o = make_float2(c_dec[S_B3], c_dec[S_B3]);
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+      const float bj = c_dec[S_B2 + j];
+      float2 acc = make_float2(bj, bj);
+#pragma unroll
+      for (int i = 0; i < 16; ++i) {
+        const float w = c_dec[S_W2 + j * 16 + i];
+        acc = __ffma2_rn(make_float2(w, w), h1[i], acc);
+      }
+      const float w3 = c_dec[S_W3 + j];
+      o = __ffma2_rn(make_float2(w3, w3), relu2(acc), o);
+    }
+    if (okA) dst[0] = inA ? tanhf(o.x) : -1.0f;
+    if (okB) dst[32] = inB ? tanhf(o.y) : -1.0f;
+  }
+}
+
 struct BwdArgs {
   FieldK fk;
   const float4* arena4;

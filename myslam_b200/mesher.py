@@ -100,6 +100,24 @@ def query_grid_sdf(all_planes, decoders, axes, bound=None, start=0, count=None, 
     else:
         mode = "direct" if hull is None else "hull"
     done = 0
+    if mode == "factored" and os.environ.get("ESLAM_B200_GRID_ROWS", "1") == "1":
+        # whole lattice rows go to the tensor-core form (eslam_grid_sdf_rows); what is left of a range that does not
+        # start / end on a row boundary (a rank's shard) to the per-voxel form below
+        row = nx * nz
+        r0, r1 = -(-start // row), (start + count) // row
+        if r1 > r0:
+            def flat(lo, hi):
+                if hi > lo:
+                    call("eslam_grid_sdf_factored", store.ref(), ptr(xs), ptr(ys), ptr(zs), nx, ny, nz, lo, hi - lo,
+                         ptr(faces[0]), ptr(faces[1]), ptr(faces[2]), hull_p, hull_n, out[lo - start:hi - start].data_ptr(),
+                         stream())
+
+            store.bind()
+            flat(start, r0 * row)
+            call("eslam_grid_sdf_rows", store.ref(), ptr(xs), ptr(ys), ptr(zs), nx, ny, nz, r0, r1, start,
+                 ptr(faces[0]), ptr(faces[1]), ptr(faces[2]), hull_p, hull_n, ptr(out), stream())
+            flat(r1 * row, start + count)
+            return out
     while done < count:
         n = min(chunk, count - done)
         dst = out[done:done + n].data_ptr()

@@ -1,5 +1,7 @@
 """GPU: SURVEY.md 8(f)-1 -- keyframe selection by view overlap (one projection kernel) and the frame table that
 replaces the reference's per-call torch.stack of the window's frames."""
+import os
+
 import numpy as np
 import pytest
 import torch
@@ -258,6 +260,16 @@ def test_grid_query_with_convex_mesh_bound():
     assert (fac - plain).abs().max().item() < 1e-5 and (fac_b - bounded).abs().max().item() < 1e-5
     assert torch.equal(fac_b == -1.0, bounded == -1.0)
     cuts = (0, 77, n // 3 + 5, n - 300, n)  # ragged ranges: CTAs straddle z columns and range ends
-    parts = [query_grid_sdf(planes, mp.decoders, axes, fld.bound, start=a, count=b - a, hull=hp, factored=True).cpu()
-             for a, b in zip(cuts[:-1], cuts[1:])]
-    assert torch.equal(torch.cat(parts), fac_b)
+    ragged = lambda: torch.cat([query_grid_sdf(planes, mp.decoders, axes, fld.bound, start=a, count=b - a, hull=hp,
+                                               factored=True).cpu() for a, b in zip(cuts[:-1], cuts[1:])])
+    # whole lattice rows run eslam_grid_sdf_rows (a warp walks y with the xz values in registers), the ragged ends of a
+    # range the per-voxel kernel: the same operation order (packed FP32 is two exact FMAs), so the same bits
+    assert torch.equal(ragged(), fac_b)
+    os.environ["ESLAM_B200_GRID_ROWS"] = "0"
+    try:  # the per-voxel kernel alone
+        voxel_b = query_grid_sdf(planes, mp.decoders, axes, fld.bound, hull=hp, factored=True).cpu()
+        voxel = query_grid_sdf(planes, mp.decoders, axes, fld.bound, factored=True).cpu()
+        assert torch.equal(ragged(), voxel_b)
+    finally:
+        del os.environ["ESLAM_B200_GRID_ROWS"]
+    assert torch.equal(voxel_b, fac_b) and torch.equal(voxel, fac)
