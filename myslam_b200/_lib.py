@@ -161,25 +161,56 @@ def ptr(t):
     return t.data_ptr()
 
 
+_RAW_STREAM = getattr(torch._C, "_cuda_getCurrentRawStream", None)
+_CUR_DEVICE = getattr(torch._C, "_cuda_getDevice", None)
+_STREAM_OVERRIDE = None
+
+
 def stream():
+    """cudaStream_t the next launch goes to: torch's current stream of the current device (through the raw binding --
+    torch.cuda.current_stream() costs as much host time as a launch), or the handle set by `on_stream`."""
+    if _STREAM_OVERRIDE is not None:
+        return _STREAM_OVERRIDE
+    if _RAW_STREAM is not None and _CUR_DEVICE is not None:
+        return _RAW_STREAM(_CUR_DEVICE())
     return torch.cuda.current_stream().cuda_stream
+
+
+class on_stream:
+    """`with on_stream(s.cuda_stream):` -- launches of THIS library inside go to that stream.  Only a variable is set:
+    torch's own current stream does not change (torch ops inside still need torch.cuda.stream), which is what makes
+    it cheap enough for a loop that switches streams several times per iteration."""
+
+    def __init__(self, handle):
+        self.handle = handle
+
+    def __enter__(self):
+        global _STREAM_OVERRIDE
+        self.prev, _STREAM_OVERRIDE = _STREAM_OVERRIDE, self.handle
+
+    def __exit__(self, *exc):
+        global _STREAM_OVERRIDE
+        _STREAM_OVERRIDE = self.prev
 
 
 LAUNCHES = 0  # kernels launched through the ABI (bench.py reports it as gpu_launches)
 _NO_KERNEL = ("eslam_bind_decoders",)
 BOUND_DECODERS = {}  # device index -> (id(FieldStore), generation) whose decoders the constant bank holds (field.py)
+_FN = {}
 
 
 def call(name, *args):
     global LAUNCHES
-    lib = load()
+    fn = _FN.get(name)
+    if fn is None:
+        fn = _FN[name] = getattr(load(), name)
     if name == "eslam_bind_decoders":
         BOUND_DECODERS.clear()  # whoever binds records what it bound afterwards (FieldStore.bind)
-    rc = getattr(lib, name)(*args)
-    if name not in _NO_KERNEL:
+    else:
         LAUNCHES += 1
+    rc = fn(*args)
     if rc != 0:
-        raise RuntimeError(f"{name} failed ({rc}): {lib.eslam_last_error().decode()}")
+        raise RuntimeError(f"{name} failed ({rc}): {load().eslam_last_error().decode()}")
 
 
 def require_cuda(t, what):

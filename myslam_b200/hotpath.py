@@ -22,7 +22,7 @@ from typing import Optional
 
 import torch
 
-from ._lib import COUNTER_WORDS, N_COUNTERS, N_LOSS, Camera, RenderCfg, call, ptr, stream
+from ._lib import COUNTER_WORDS, N_COUNTERS, N_LOSS, Camera, RenderCfg, call, on_stream, ptr, stream
 from .field import FieldStore
 from .renderer import TorchDraws, linspace_table, make_cfg
 
@@ -347,10 +347,13 @@ def mapping_window_pipelined(ws: Workspace, store: FieldStore, sc: StepCfg, c2ws
     side = pipe.side
     norm = [None]
 
+    s_side, s_imp = side.cuda_stream, pipe.imp.cuda_stream  # raw handles: see _lib.on_stream
+
     def prep():  # draws + ray selection + depth-guided samples (+ the exchange of the loss normalisers)
-        torch.randint(n_crop, (N,), out=pipe.idx)
-        if sc.perturb:
-            pipe.ubuf.uniform_()
+        with torch.cuda.stream(side):  # torch's generator kernels: the one place torch's current stream matters
+            torch.randint(n_crop, (N,), out=pipe.idx)
+            if sc.perturb:
+                pipe.ubuf.uniform_()
         _sample(ws, store, sc, pipe.idx, b, pix_per_image, c2w_flat, poses7, 1, gt_depths, gt_colors,
                 pipe.u if sc.perturb else None, 0)
         if peer:
@@ -358,7 +361,7 @@ def mapping_window_pipelined(ws: Workspace, store: FieldStore, sc: StepCfg, c2ws
 
     grad, gq = store.ensure_grad(), store.ensure_q_grad()
     side.wait_stream(main)
-    with torch.cuda.stream(side):
+    with on_stream(s_side):
         prep()
         pipe.ev_prep.record(side)
     for it in range(iters):
@@ -386,7 +389,7 @@ def mapping_window_pipelined(ws: Workspace, store: FieldStore, sc: StepCfg, c2ws
             importance()
             pipe.ev_q.record(main)
             pipe.imp.wait_event(pipe.ev_q)
-            with torch.cuda.stream(pipe.imp):
+            with on_stream(s_imp):
                 backward(2)
                 pipe.ev_imp.record(pipe.imp)
             backward(1)
@@ -396,7 +399,7 @@ def mapping_window_pipelined(ws: Workspace, store: FieldStore, sc: StepCfg, c2ws
             backward(0)
         pipe.ev_bwd.record(main)
         side.wait_event(pipe.ev_bwd)
-        with torch.cuda.stream(side):
+        with on_stream(s_side):
             if joint:
                 pg = ws.pose_grad
                 if peer:

@@ -6,6 +6,7 @@ two-stream pipelining on/off (ESLAM_B200_PIPELINE).  Prints us per iteration for
 """
 import os
 import sys
+import time
 
 import torch
 
@@ -60,7 +61,14 @@ def main():
         store.gen += 1
         torch.manual_seed(7)
         ms = time_region(run, n_calls, 3, False) / n_calls
-        print(f"{name:40s} {ms:7.3f} ms per call   {1e3 * ms / m['iters']:7.1f} us per iteration", flush=True)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()  # host time to ENQUEUE a call (no sync inside): what a launch-bound loop is limited by
+        for _ in range(n_calls):
+            run()
+        host = (time.perf_counter() - t0) / n_calls * 1e3
+        torch.cuda.synchronize()
+        print(f"{name:40s} {ms:7.3f} ms per call   {1e3 * ms / m['iters']:7.1f} us per iteration   "
+              f"host enqueue {host:6.3f} ms per call", flush=True)
 
 
 if __name__ == "__main__":
