@@ -108,9 +108,12 @@ class PeerExchange(MappingExchange):
         bases = [int(b) for b in self.handle.buffer_ptrs]
         mc = int(getattr(self.handle, "multicast_ptr", 0) or 0)
         if multimem is None:
-            # P2P stores by default; ESLAM_B200_MULTIMEM=1 broadcasts the parameters with one multimem.st per
-            # element through the NVSwitch instead of world_size point-to-point stores
-            multimem = os.environ.get("ESLAM_B200_MULTIMEM", "0") == "1"
+            # The all-gather of the updated texels: world_size point-to-point stores per element, or ONE multimem.st
+            # through the NVSwitch.  Measured (tools/exchange_times.py): no difference at 2 GPUs, 14 us per iteration
+            # less at 8 (235 vs 249 us for backward + exchange): the switch by default from 4 ranks up;
+            # ESLAM_B200_MULTIMEM=0 / 1 forces either.
+            env = os.environ.get("ESLAM_B200_MULTIMEM", "")
+            multimem = env == "1" if env in ("0", "1") else self.world >= 4
         self.multimem = bool(multimem and mc)
         self._mc = mc
 

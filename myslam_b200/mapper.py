@@ -69,6 +69,7 @@ class _WindowGraph:
         from . import _lib
 
         dev = ws.device
+        self.store = store  # kept alive: the graph addresses its arenas (and its id is part of the cache key)
         self.c2ws = torch.zeros(b, 4, 4, dtype=torch.float32, device=dev)
         self.out = torch.zeros(b, 4, 4, dtype=torch.float32, device=dev)
         self.poses7 = torch.zeros(b, 7, dtype=torch.float32, device=dev) if joint else None
