@@ -607,7 +607,8 @@ def main():
     hbm_peak, peak_src, _ = measured_peaks()
     achieved = R * ALGO_BYTES_PER_RAY_ITER / (ms_k * 1e-3) / 1e9
     traffic, traffic_src = ncu_traffic("k_map_bwd_q")
-    ceil = l2_ceilings() if rank == 0 else None
+    # (not under --profile-only: ncu would replay every launch of the microbenchmark subprocess as well)
+    ceil = l2_ceilings() if rank == 0 and not args.profile_only else None
     # what the Q-form kernel itself moves through L2: 64-byte lines (16 channels) where the algorithmic figure of
     # SURVEY 8d counts 128-byte lines, i.e. half of it (before the run-length merge of the coarse reductions)
     q_bytes = R * ALGO_BYTES_PER_RAY_ITER / 2
