@@ -581,8 +581,9 @@ __global__ void __launch_bounds__(NP) k_render_fwd(const __grid_constant__ Rende
 // ---- the factored lattice query over whole lattice rows ---------------------------------------------------------------
 // k_grid_sdf_factored is bound by issue slots: 590 instructions per voxel, 280 of them the FFMAs of the hidden layer,
 // the rest loads, index arithmetic and the three-face sum.  Here a warp owns one x and 64 z (lane: z and z + 32) and
-// walks y: the xz face values of its two voxels stay in registers for the whole column, the yz values are shared by
-// the CTA's warps (8 x) through L1, the xy texel is one line read by the whole warp; and the hidden layer is packed
+// walks y: the xz face values of its two voxels are the same eight lines every row (L1 hits; holding them in registers
+// costs a resident CTA: 5.0 ms against 4.75), the yz values are shared by the CTA's warps (8 x) through L1, the xy
+// texel is one line read by the whole warp; and the hidden layer is packed
 // FP32 -- `fma.rn.f32x2` (SASS FFMA2 R, R.F32x2, UR.F32, R: the two voxels of a lane against one weight in a uniform
 // register), two exact FMAs per issue slot, so the values are those of k_grid_sdf_factored bit for bit.
 // (The same layer as mma.sync m16n8k8 TF32 with both operands split in two -- three products per tile, the precision
@@ -602,10 +603,13 @@ struct GridRowsArgs {
 };
 
 constexpr int GR_THREADS = 256, GR_X = GR_THREADS / 32, GR_Z = 64;
+#ifndef GR_RESIDENT
+#define GR_RESIDENT 3  // 3: the xz values are re-read through L1 every row (<= 84 registers); 2: kept in registers
+#endif
 
 __device__ __forceinline__ float2 relu2(float2 v) { return make_float2(fmaxf(v.x, 0.f), fmaxf(v.y, 0.f)); }
 
-__global__ void __launch_bounds__(GR_THREADS, 2) k_grid_sdf_rows(const __grid_constant__ GridRowsArgs a) {
+__global__ void __launch_bounds__(GR_THREADS, GR_RESIDENT) k_grid_sdf_rows(const __grid_constant__ GridRowsArgs a) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int x = blockIdx.x * GR_X + warp;
   if (x >= a.nx) return;  // warp-uniform; no CTA barrier below
@@ -613,6 +617,7 @@ __global__ void __launch_bounds__(GR_THREADS, 2) k_grid_sdf_rows(const __grid_co
   const bool okA = zA < a.nz, okB = zB < a.nz;
   const int za = okA ? zA : a.nz - 1, zb = okB ? zB : a.nz - 1;
   // xz face values of the lane's two voxels: channel c of voxel A / B in .x / .y
+#if GR_RESIDENT == 2
   float2 fxz[16];
 #pragma unroll
   for (int c = 0; c < 4; ++c) {
@@ -622,18 +627,30 @@ __global__ void __launch_bounds__(GR_THREADS, 2) k_grid_sdf_rows(const __grid_co
     fxz[c * 4 + 2] = make_float2(va.z, vb.z);
     fxz[c * 4 + 3] = make_float2(va.w, vb.w);
   }
+#endif
   const float px = a.xs[x], pzA = a.zs[za], pzB = a.zs[zb];
   const bool in_x = px < a.hi[0] && px > a.lo[0];
   const bool inA0 = okA && in_x && pzA < a.hi[2] && pzA > a.lo[2], inB0 = okB && in_x && pzB < a.hi[2] && pzB > a.lo[2];
 #pragma unroll 1
   for (int y = a.iy0; y < a.iy1; ++y) {
-    float4 cxy[4], cyA[4], cyB[4];  // no software prefetch: two CTAs per SM hide the loads, 48 more registers would not fit
+    float4 cxy[4], cyA[4], cyB[4];  // no software prefetch: the resident CTAs hide the loads
 #pragma unroll
     for (int c = 0; c < 4; ++c) {
       cxy[c] = ldg4(a.pxy + ((long long)y * a.nx + x) * 4 + c);
       cyA[c] = ldg4(a.pyz + ((long long)y * 4 + c) * a.nz + za);
       cyB[c] = ldg4(a.pyz + ((long long)y * 4 + c) * a.nz + zb);
     }
+#if GR_RESIDENT != 2
+    float2 fxz[16];  // the same 8 lines every row: L1 hits
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      const float4 va = ldg4(a.pxz + ((long long)x * 4 + c) * a.nz + za), vb = ldg4(a.pxz + ((long long)x * 4 + c) * a.nz + zb);
+      fxz[c * 4 + 0] = make_float2(va.x, vb.x);
+      fxz[c * 4 + 1] = make_float2(va.y, vb.y);
+      fxz[c * 4 + 2] = make_float2(va.z, vb.z);
+      fxz[c * 4 + 3] = make_float2(va.w, vb.w);
+    }
+#endif
     const float py = a.ys[y];
     const bool in_y = py < a.hi[1] && py > a.lo[1];  // Mesher.py:214-215
     bool inA = inA0 && in_y, inB = inB0 && in_y;
