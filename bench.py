@@ -420,9 +420,9 @@ def workload_config(world, pix, n_frames, exchange_name):
                         "15 iterations per optimize_mapping call, ESLAM.yaml defaults, joint pose optimisation",
             "rays_per_iter_total": world * pix * n_frames, "exchange": exchange_name,
             "l2": "inputs larger than L2 (471 MB of window frames + 109 MB parameter/optimiser arenas); no flush",
-            "launch": ("one CUDA-graph replay per call (reset + 15 pipelined iterations over two streams + pose "
+            "launch": ("one CUDA-graph replay per call (reset + 15 pipelined iterations over three streams + pose "
                        "conversion; captured on the second call of a shape)" if world == 1 and
-                       os.environ.get("ESLAM_B200_GRAPH", "1") == "1" else "kernel by kernel over two streams"),
+                       os.environ.get("ESLAM_B200_GRAPH", "1") == "1" else "kernel by kernel over three streams"),
             "seed": 0}
 
 

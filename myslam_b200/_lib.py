@@ -179,7 +179,8 @@ def stream():
 class on_stream:
     """`with on_stream(s.cuda_stream):` -- launches of THIS library inside go to that stream.  Only a variable is set:
     torch's own current stream does not change (torch ops inside still need torch.cuda.stream), which is what makes
-    it cheap enough for a loop that switches streams several times per iteration."""
+    it cheap enough for a loop that switches streams several times per iteration.  Process-wide, not per thread: the
+    tracker and the mapper are separate processes (ESLAM.py:246-260), each launching from one thread."""
 
     def __init__(self, handle):
         self.handle = handle

@@ -56,8 +56,8 @@ def _window_body(store: FieldStore, ws: Workspace, sc: StepCfg, c2ws, poses7, gt
 
 
 class _WindowGraph:
-    """One `optimize_mapping` call's device work -- optimiser reset, `iters` pipelined iterations over both streams,
-    pose conversion -- captured once as a CUDA graph and replayed (the loop is ~16 ctypes launches per iteration; a
+    """One `optimize_mapping` call's device work -- optimiser reset, `iters` pipelined iterations over the loop's three
+    streams, pose conversion -- captured once as a CUDA graph and replayed (the loop is ~20 launches per iteration; a
     replay costs the host one call, so the mapper process is free while the window runs and the launch gaps between
     the kernels close).  Everything the kernels address is persistent: the parameter / optimiser arenas, the
     workspace and its draw buffers, and the three buffers below (window poses in, poses out, frame-pointer table),
@@ -128,9 +128,18 @@ def map_window(store: FieldStore, ws: Workspace, sc: StepCfg, c2ws, gt_colors, g
             if ent == "seen":
                 if len(graphs) > 64:
                     graphs.clear()
-                ent = graphs[key] = _WindowGraph(store, ws, sc, gt_depths, b, pix, iters, (lr_dec, lr_planes, lr_cplanes),
-                                                 joint_opt, lr_cam)
-            return ent.run(store, c2ws, gt_depths)
+                try:
+                    ent = _WindowGraph(store, ws, sc, gt_depths, b, pix, iters, (lr_dec, lr_planes, lr_cplanes),
+                                       joint_opt, lr_cam)
+                except Exception as exc:  # capture refused (driver / torch build): same kernels, launched one by one
+                    import warnings
+
+                    warnings.warn(f"myslam_b200: CUDA-graph capture of the mapping window failed ({exc}); "
+                                  "launching kernel by kernel")
+                    ent = "eager"
+                graphs[key] = ent
+            if ent != "eager":
+                return ent.run(store, c2ws, gt_depths)
     poses7 = torch.zeros(b, 7, dtype=torch.float32, device=c2ws.device) if joint_opt else None
     out = torch.empty_like(c2ws)
     _window_body(store, ws, sc, c2ws, poses7, gt_colors, gt_depths, pix, iters, lr_dec, lr_planes, lr_cplanes, lr_cam,
