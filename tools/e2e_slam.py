@@ -197,6 +197,8 @@ def main():
     ap.add_argument("--seed", type=int, default=0)
     ap.add_argument("--fast-rng", action="store_true", help="upper-bound draw shapes (no host sync); default: the "
                     "reference's draw shapes, so both arms consume the same random stream")
+    ap.add_argument("--ours-only", action="store_true", help="skip the reference arm (its statistics over seeds are in "
+                    "profiles/r02_e2e_slam.json): ATE / depth-L1 of this build alone")
     ap.add_argument("--out", default=os.path.join(ROOT, "gpurun_out", "e2e_slam.json"))
     args = ap.parse_args()
     dev = "cuda:0"
@@ -216,7 +218,8 @@ def main():
     frames = [S.render_box_room(gt_c2ws[k], *cam, spec["room"], dev, hole_frac=0.02, generator=gen)
               for k in range(args.frames)]
     res = {}
-    for name, cls in (("b200", OursArm), ("reference_torch_gpu", OracleArm)):
+    arms = (("b200", OursArm),) if args.ours_only else (("b200", OursArm), ("reference_torch_gpu", OracleArm))
+    for name, cls in arms:
         arm = cls(spec, cfg, fld, dev)
         if isinstance(arm, OursArm):
             arm.trk.strict_rng = arm.mp.strict_rng = not args.fast_rng
@@ -233,7 +236,7 @@ def main():
         print(name, {k: v for k, v in res[name].items() if k != "_arm"}, flush=True)
     # depth L1 with our renderer on both final maps
     probe = OursArm(spec, cfg, fld, dev)
-    for name in ("b200", "reference_torch_gpu"):
+    for name, _ in arms:
         arm = res[name].pop("_arm")
         if isinstance(arm, OracleArm):
             f = arm.fld
@@ -251,12 +254,13 @@ def main():
             ok = dep > 0
             l1.append((d[ok].float() - dep[ok]).abs().mean().item())
         res[name]["depth_l1_m"] = float(np.mean(l1))
-    a, b = res["b200"], res["reference_torch_gpu"]
-    res["ate_ratio"] = a["ate_rmse_m"] / max(b["ate_rmse_m"], 1e-12)
-    res["depth_l1_ratio"] = a["depth_l1_m"] / max(b["depth_l1_m"], 1e-12)
-    res["speedup_wall"] = b["wall_s"] / a["wall_s"]
+    if not args.ours_only:
+        a, b = res["b200"], res["reference_torch_gpu"]
+        res["ate_ratio"] = a["ate_rmse_m"] / max(b["ate_rmse_m"], 1e-12)
+        res["depth_l1_ratio"] = a["depth_l1_m"] / max(b["depth_l1_m"], 1e-12)
+        res["speedup_wall"] = b["wall_s"] / a["wall_s"]
     res["config"] = {"frames": args.frames, "iters_first": args.iters_first, "H": spec["H"], "W": spec["W"],
-                     "seed": args.seed}
+                     "seed": args.seed, "fast_rng": bool(args.fast_rng)}
     os.makedirs(os.path.dirname(args.out), exist_ok=True)
     json.dump(res, open(args.out, "w"), indent=1)
     print(json.dumps(res))
