@@ -110,3 +110,23 @@ sys.exit(1 if bad else 0)
 """ % ROOT
     r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=300)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+
+
+def test_stream_override_nests_and_restores():
+    """_lib.on_stream only redirects THIS library's launches (a module variable, no CUDA call): nested blocks restore
+    the outer handle, also when an exception leaves the block."""
+    from myslam_b200 import _lib
+
+    assert _lib._STREAM_OVERRIDE is None
+    with _lib.on_stream(111):
+        assert _lib.stream() == 111
+        with _lib.on_stream(222):
+            assert _lib.stream() == 222
+        assert _lib.stream() == 111
+        try:
+            with _lib.on_stream(333):
+                raise ValueError("leave the block")
+        except ValueError:
+            pass
+        assert _lib.stream() == 111
+    assert _lib._STREAM_OVERRIDE is None
